@@ -1,0 +1,894 @@
+// Layer-thickness and tracer transport: advect prelude + CPPM
+// (cppm_compatibility='full', cppm_limiting='non_oscillatory').
+//
+// Reference: phy/mod_advect.F90:59-189, phy/mod_cppm.F90:101-359 (static
+// tables), :361-434 (thickness edges), :490-818 (compatible tracer parabolas),
+// :1373-1468 (flux integrals), :1470-1785 (directional passes), :2504-2834.
+//
+// B200 design (not the reference's pencil loops):
+//  * tables are SoA device arrays in (i,j) layout for BOTH directions (the
+//    reference transposes the j tables for its CPU pencils; lanes run along i
+//    here in both passes so no transpose is wanted);
+//  * each directional pass is two kernels: `hedges` (limited 4th-order
+//    thickness edges) and `flux` (tracer edge LU solves, limiters, parabolas,
+//    upstream flux integrals, divergence update) — `flux` runs the dependent
+//    stages edge -> curvature -> parabola -> face flux -> cell update through
+//    shared memory inside one thread block with a 2+3-cell skirt, so the
+//    reference's tel/ter/d2t/tpc*/hf/htf pencils never touch HBM;
+//  * the two Strang passes ping-pong between the state arrays and a scratch
+//    set, which removes the in-place read/write hazard without extra traffic.
+#include "common.cuh"
+
+namespace blom {
+
+namespace {
+
+enum { stencil_0000 = 0, stencil_1111 = 1, stencil_1110 = 2, stencil_0111 = 3,
+       stencil_1100 = 4, stencil_0110 = 5, stencil_0011 = 6, stencil_0100 = 7,
+       stencil_0010 = 8 };
+
+#define K0 0.
+#define K1 1.
+#define K2 2.
+#define K3 3.
+#define K4 4.
+#define K5 5.
+#define K6 6.
+#define K12 12.
+#define K18 18.
+#define K42 42.
+#define K60 60.
+#define K1_2 (1. / 2.)
+#define K1_3 (1. / 3.)
+#define K2_3 (2. / 3.)
+#define K1_4 (1. / 4.)
+#define K3_4 (3. / 4.)
+#define K1_5 (1. / 5.)
+#define K1_6 (1. / 6.)
+#define K1_10 (1. / 10.)
+#define K1_12 (1. / 12.)
+#define K1_15 (1. / 15.)
+#define K1_20 (1. / 20.)
+#define DPEPS 1.e-12
+
+// table levels inside the per-direction table pack
+enum { T_HEVC1 = 0, T_HEVC2 = 1, T_HEVC3 = 2, T_HEVC4 = 3, T_TMC0 = 4, T_TMCL = 16, T_TMCR = 28,
+       T_SSC = 40, T_SCC = 41, T_D2M = 42, T_STEN = 43, T_NLEV = 44 };
+
+__device__ __forceinline__ double fsign(double a, double b) { return copysign(a, b); }
+
+// ---- static tables -----------------------------------------------------------
+// One thread per interior point computes both directions' tables
+// (set_stencil_coeffs / set_slope_coeffs / set_d2_mask, mod_cppm.F90:101-359).
+__device__ void stencil_coeffs(const int* sm, const double* dx, double* tab, long lev) {
+  double a12, a22, a32, a42, a13, a23, a33, a43, a14, a24, a34, a44;
+  const double d1 = dx[0], d2 = dx[1], d3 = dx[2], d4 = dx[3];
+  a12 = -d2 - K1_2 * d1;
+  a22 = -K1_2 * d2;
+  a32 = K1_2 * d3;
+  a42 = d3 + K1_2 * d4;
+  a13 = a12 * a12 + K1_12 * d1 * d1;
+  a23 = -K2_3 * a22 * d2;
+  a33 = K2_3 * a32 * d3;
+  a43 = a42 * a42 + K1_12 * d4 * d4;
+  a14 = (a13 + K1_6 * d1 * d1) * a12;
+  a24 = -K3_4 * a23 * d2;
+  a34 = K3_4 * a33 * d3;
+  a44 = (a43 + K1_6 * d4 * d4) * a42;
+  double tl[12], tr[12], t0[12];
+  tl[0] = -K1_12 * d1;
+  tl[1] = (K1_10 * d1 + K1_6 * d2) * d1;
+  tl[2] = -(K1_10 * (d1 + K3 * d2) * d1 + K1_4 * (d2 * d2)) * d1;
+  tl[3] = -K1_12 * d2;
+  tl[4] = K1_10 * (d2 * d2);
+  tl[5] = -K1_10 * (d2 * d2 * d2);
+  tl[6] = -K1_12 * d3;
+  tl[7] = -K1_15 * (d3 * d3);
+  tl[8] = -K1_20 * (d3 * d3 * d3);
+  tl[9] = -K1_12 * d4;
+  tl[10] = -(K1_15 * d4 + K1_6 * d3) * d4;
+  tl[11] = -(K1_5 * (K1_4 * d4 + d3) * d4 + K1_4 * (d3 * d3)) * d4;
+  tr[0] = K1_12 * d1;
+  tr[1] = -(K1_15 * d1 + K1_6 * d2) * d1;
+  tr[2] = (K1_5 * (K1_4 * d1 + d2) * d1 + K1_4 * (d2 * d2)) * d1;
+  tr[3] = K1_12 * d2;
+  tr[4] = -K1_15 * (d2 * d2);
+  tr[5] = K1_20 * (d2 * d2 * d2);
+  tr[6] = K1_12 * d3;
+  tr[7] = K1_10 * (d3 * d3);
+  tr[8] = K1_10 * (d3 * d3 * d3);
+  tr[9] = K1_12 * d4;
+  tr[10] = (K1_10 * d4 + K1_6 * d3) * d4;
+  tr[11] = (K1_10 * (d4 + K3 * d3) * d4 + K1_4 * (d3 * d3)) * d4;
+  t0[0] = a12;
+  t0[1] = a13 - tl[1] - tr[1];
+  t0[2] = a14 - tl[2] - tr[2];
+  t0[3] = a22;
+  t0[4] = a23 - tl[4] - tr[4];
+  t0[5] = a24 - tl[5] - tr[5];
+  t0[6] = a32;
+  t0[7] = a33 - tl[7] - tr[7];
+  t0[8] = a34 - tl[8] - tr[8];
+  t0[9] = a42;
+  t0[10] = a43 - tl[10] - tr[10];
+  t0[11] = a44 - tl[11] - tr[11];
+#pragma unroll
+  for (int r = 0; r < 12; ++r) {
+    tab[(T_TMC0 + r) * lev] = t0[r];
+    tab[(T_TMCL + r) * lev] = tl[r];
+    tab[(T_TMCR + r) * lev] = tr[r];
+  }
+  int stencil;
+  double hevc1, hevc2, hevc3, hevc4;
+  const int s0 = sm[0], s1 = sm[1], s2 = sm[2], s3 = sm[3];
+  if (s0 == 1 && s1 == 1 && s2 == 1 && s3 == 1) {
+    stencil = stencil_1111;
+    a22 = a22 - a12; a32 = a32 - a12; a42 = a42 - a12;
+    a23 = (a23 - a13) / a22;
+    a33 = a33 - a13 - a23 * a32;
+    a43 = a43 - a13 - a23 * a42;
+    a24 = (a24 - a14) / a22;
+    a34 = a34 - a14 - a24 * a32;
+    a44 = a44 - a14 - a24 * a42;
+    a34 = a34 / a33;
+    a44 = a44 - a34 * a43;
+    hevc2 = -a12;
+    hevc3 = -a13 - a23 * hevc2;
+    hevc4 = -a14 - a24 * hevc2 - a34 * hevc3;
+    hevc4 = hevc4 / a44;
+    hevc3 = (hevc3 - a43 * hevc4) / a33;
+    hevc2 = (hevc2 - a32 * hevc3 - a42 * hevc4) / a22;
+    hevc1 = K1 - hevc2 - hevc3 - hevc4;
+  } else if (s0 == 1 && s1 == 1 && s2 == 1 && s3 == 0) {
+    stencil = stencil_1110;
+    a22 = a22 - a12; a32 = a32 - a12;
+    a23 = (a23 - a13) / a22;
+    a33 = a33 - a13 - a23 * a32;
+    hevc2 = -a12;
+    hevc3 = -a13 - a23 * hevc2;
+    hevc3 = hevc3 / a33;
+    hevc2 = (hevc2 - a32 * hevc3) / a22;
+    hevc1 = K1 - hevc2 - hevc3;
+    hevc4 = K0;
+  } else if (s0 == 0 && s1 == 1 && s2 == 1 && s3 == 1) {
+    stencil = stencil_0111;
+    a32 = a32 - a22; a42 = a42 - a22;
+    a33 = (a33 - a23) / a32;
+    a43 = a43 - a23 - a33 * a42;
+    hevc3 = -a22;
+    hevc4 = -a23 - a33 * hevc3;
+    hevc4 = hevc4 / a43;
+    hevc3 = (hevc3 - a42 * hevc4) / a32;
+    hevc2 = K1 - hevc3 - hevc4;
+    hevc1 = K0;
+  } else if (s0 == 0 && s1 == 1 && s2 == 1 && s3 == 0) {
+    stencil = stencil_0110;
+    a32 = a32 - a22;
+    hevc3 = -a22 / a32;
+    hevc2 = K1 - hevc3;
+    hevc1 = K0; hevc4 = K0;
+  } else if (s0 == 1 && s1 == 1) {
+    stencil = stencil_1100;
+    a22 = a22 - a12;
+    hevc2 = -a12 / a22;
+    hevc1 = K1 - hevc2;
+    hevc3 = K0; hevc4 = K0;
+  } else if (s2 == 1 && s3 == 1) {
+    stencil = stencil_0011;
+    a42 = a42 - a32;
+    hevc4 = -a32 / a42;
+    hevc3 = K1 - hevc4;
+    hevc1 = K0; hevc2 = K0;
+  } else if (s1 == 1) {
+    stencil = stencil_0100;
+    hevc1 = K0; hevc2 = K1; hevc3 = K0; hevc4 = K0;
+  } else if (s2 == 1) {
+    stencil = stencil_0010;
+    hevc1 = K0; hevc2 = K0; hevc3 = K1; hevc4 = K0;
+  } else {
+    stencil = stencil_0000;
+    hevc1 = K0; hevc2 = K0; hevc3 = K0; hevc4 = K0;
+  }
+  tab[T_HEVC1 * lev] = hevc1; tab[T_HEVC2 * lev] = hevc2;
+  tab[T_HEVC3 * lev] = hevc3; tab[T_HEVC4 * lev] = hevc4;
+  tab[T_STEN * lev] = (double)stencil;
+}
+
+__global__ void cppm_tables_kernel(Geom g, const int* __restrict__ ip, const double* __restrict__ scpx,
+                                   const double* __restrict__ scpy, double* __restrict__ ti,
+                                   double* __restrict__ tj) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)g.ii * g.jj) return;
+  const int i = (int)(t % g.ii) + 1, j = (int)(t / g.ii) + 1;
+  const long x = ix2(g, i, j);
+  int sm[4]; double dx[4];
+  for (int q = 0; q < 4; ++q) { sm[q] = ip[ix2(g, i - 2 + q, j)]; dx[q] = scpx[ix2(g, i - 2 + q, j)]; }
+  stencil_coeffs(sm, dx, ti + x, g.lev);
+  {
+    const bool any0 = sm[1] == 0 || sm[2] == 0 || sm[3] == 0;
+    ti[T_SSC * g.lev + x] = any0 ? K0 : K2;
+    ti[T_SCC * g.lev + x] = any0 ? K0 : K2 * dx[2] / (dx[1] + K2 * dx[2] + dx[3]);
+    ti[T_D2M * g.lev + x] = any0 ? K0 : K1;
+  }
+  for (int q = 0; q < 4; ++q) { sm[q] = ip[ix2(g, i, j - 2 + q)]; dx[q] = scpy[ix2(g, i, j - 2 + q)]; }
+  stencil_coeffs(sm, dx, tj + x, g.lev);
+  {
+    const bool any0 = sm[1] == 0 || sm[2] == 0 || sm[3] == 0;
+    tj[T_SSC * g.lev + x] = any0 ? K0 : K2;
+    tj[T_SCC * g.lev + x] = any0 ? K0 : K2 * dx[2] / (dx[1] + K2 * dx[2] + dx[3]);
+    tj[T_D2M * g.lev + x] = any0 ? K0 : K1;
+  }
+}
+
+__device__ __forceinline__ double swap_tag(double s) {
+  switch ((int)s) {
+    case stencil_1110: return stencil_0111;
+    case stencil_0111: return stencil_1110;
+    case stencil_1100: return stencil_0011;
+    case stencil_0011: return stencil_1100;
+    case stencil_0100: return stencil_0010;
+    case stencil_0010: return stencil_0100;
+    default: return s;
+  }
+}
+// arctic swaps of tags / hevc (mod_cppm.F90:2650-2720); northern tile only
+__global__ void cppm_tables_arctic(Geom g, double* ti, double* tj) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nrow = 1 + g.nb;  // row jj (i tables + right half of j tables) and rows jj+1..jj+nb
+  if (t >= (long)g.ldi * nrow) return;
+  const int i = (int)(t % g.ldi) + 1 - g.nb, r = (int)(t / g.ldi);
+  const int j = g.jj + r;
+  const long x = ix2(g, i, j);
+  auto swp = [&](double* tb) {
+    tb[T_STEN * g.lev + x] = swap_tag(tb[T_STEN * g.lev + x]);
+    double a = tb[T_HEVC1 * g.lev + x]; tb[T_HEVC1 * g.lev + x] = tb[T_HEVC4 * g.lev + x]; tb[T_HEVC4 * g.lev + x] = a;
+    a = tb[T_HEVC2 * g.lev + x]; tb[T_HEVC2 * g.lev + x] = tb[T_HEVC3 * g.lev + x]; tb[T_HEVC3 * g.lev + x] = a;
+  };
+  if (r == 0) {
+    swp(ti);
+    if (i >= max(1, g.itdm / 2 - g.i0 + 1) && i <= g.ii) swp(tj);
+  } else if (i >= 1 && i <= g.ii) {
+    swp(tj);
+  }
+}
+__global__ void cppm_tags_to_int(Geom g, const double* __restrict__ ti, const double* __restrict__ tj,
+                                 int* __restrict__ si, int* __restrict__ sj) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.lev) return;
+  si[t] = __double2int_rn(ti[T_STEN * g.lev + t]);
+  sj[t] = __double2int_rn(tj[T_STEN * g.lev + t]);
+}
+
+// ---- advect prelude (mod_advect.F90:71-94) ----------------------------------
+__global__ void advect_flux_area(Geom g, int m, int mm, int nn, double delt1, double dlt,
+                                 const int* __restrict__ iu, const int* __restrict__ iv,
+                                 const double* __restrict__ u, const double* __restrict__ v,
+                                 const double* __restrict__ dpu, const double* __restrict__ dpv,
+                                 const double* __restrict__ ubflxs_p, const double* __restrict__ vbflxs_p,
+                                 const double* __restrict__ pbu, const double* __restrict__ pbv,
+                                 const double* __restrict__ umfltd, const double* __restrict__ vmfltd,
+                                 const double* __restrict__ umflsm, const double* __restrict__ vmflsm,
+                                 const double* __restrict__ scuy, const double* __restrict__ scvx,
+                                 const double* __restrict__ umax, const double* __restrict__ vmax,
+                                 double* __restrict__ cau, double* __restrict__ cav) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y + 1, k = blockIdx.z + 1;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j);
+  const long xm = x + (long)(k + mm - 1) * g.lev, xn = x + (long)(k + nn - 1) * g.lev;
+  const long xk = x + (long)(k - 1) * g.lev, x2 = x + (long)(m - 1) * g.lev;
+  if (iu[x] == 1) {
+    double dtdl = delt1 * scuy[x];
+    double ca_tmp = u[xm] * dtdl + ubflxs_p[x2] * dlt / pbu[x2] + (umfltd[xm] + umflsm[xm]) / fmax(onemm, dpu[xn]);
+    cau[xk] = fmax(-umax[x] * dtdl, fmin(umax[x] * dtdl, ca_tmp));
+  }
+  if (iv[x] == 1) {
+    double dtdl = delt1 * scvx[x];
+    double ca_tmp = v[xm] * dtdl + vbflxs_p[x2] * dlt / pbv[x2] + (vmfltd[xm] + vmflsm[xm]) / fmax(onemm, dpv[xn]);
+    cav[xk] = fmax(-vmax[x] * dtdl, fmin(vmax[x] * dtdl, ca_tmp));
+  }
+}
+
+// ---- thickness edges (h_edges_nosc, mod_cppm.F90:361-434) --------------------
+// DIR 0: i-pass, DIR 1: j-pass.  One thread per interior cell and level.
+// sp = element stride along the pass direction, sc = along the cross direction.
+template <int DIR>
+__global__ void __launch_bounds__(256)
+cppm_hedges(Geom g, bool second_pass, const double* __restrict__ dp /* level 1 of source set */,
+            const double* __restrict__ cac /* cross-direction flux area, level 1 */,
+            const double* __restrict__ scp2i, const double* __restrict__ tab,
+            double* __restrict__ hel3, double* __restrict__ her3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y + 1, k = blockIdx.z + 1;
+  if (i > g.ii) return;
+  const long sp = DIR == 0 ? 1 : g.ldi, sc = DIR == 0 ? g.ldi : 1;
+  const long x = ix2(g, i, j), xk = x + (long)(k - 1) * g.lev;
+  double hm[7];  // cells c-3..c+3
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    const long y = x + (q - 3) * sp, yk = xk + (q - 3) * sp;
+    double h = fmax(K0, dp[yk]) + DPEPS;
+    if (second_pass) h = h / (K1 - (cac[yk + sc] - cac[yk]) * scp2i[y]);
+    hm[q] = h;
+  }
+  // edges e = c-1..c+2 -> he[0..3]; edge e uses cells e-2..e+1
+  double he[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const long y = x + (q - 1) * sp;
+    he[q] = tab[T_HEVC1 * g.lev + y] * hm[q] + tab[T_HEVC2 * g.lev + y] * hm[q + 1] +
+            tab[T_HEVC3 * g.lev + y] * hm[q + 2] + tab[T_HEVC4 * g.lev + y] * hm[q + 3];
+  }
+  // d2h at c-1, c, c+1: hel(c')=he(c'), her(c')=he(c'+1)
+  double d2h[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+    d2h[q] = tab[T_D2M * g.lev + x + (q - 1) * sp] * (he[q] - K2 * hm[q + 2] + he[q + 1]);
+  double hel = he[1], her = he[2];
+  const double hmm = hm[2], hm0 = hm[3], hmp = hm[4];
+  const double ssc = tab[T_SSC * g.lev + x], scc = tab[T_SCC * g.lev + x];
+  double sl, sr, sc_, d, q_, r, a2;
+  if (d2h[0] * d2h[1] <= K0 || d2h[1] * d2h[2] <= K0) {
+    sl = ssc * (hm0 - hmm);
+    sr = ssc * (hmp - hm0);
+    if (sl * sr > K0) {
+      sc_ = scc * (hmp - hmm);
+      sc_ = fsign(fmin(fmin(fabs(sl), fabs(sr)), fabs(sc_)), sc_);
+      if ((hmm - hel) * (hm0 - hel) > K0) hel = hm0 - fsign(fmin(K1_2 * fabs(sc_), fabs(hel - hm0)), sc_);
+      if ((hmp - her) * (hm0 - her) > K0) her = hm0 + fsign(fmin(K1_2 * fabs(sc_), fabs(her - hm0)), sc_);
+      d = her - hel;
+      q_ = d * (K2 * hm0 - hel - her);
+      r = K1_3 * d * d;
+      if (q_ > r) hel = K3 * hm0 - K2 * her;
+      else if (-r > q_) her = K3 * hm0 - K2 * hel;
+    } else {
+      hel = hm0;
+      her = hm0;
+    }
+  }
+  hel = fmax(hel, DPEPS);
+  her = fmax(her, DPEPS);
+  sl = K2 * (K3 * hm0 - K2 * hel - her);
+  a2 = K3 * (hel - K2 * hm0 + her);
+  sr = sl + K2 * a2;
+  if (sl < K0 && sr > K0) {
+    if (a2 * hel - K1_4 * sl * sl < a2 * DPEPS) {
+      q_ = K3 * hm0 / (K3 * sl * sr + K4 * a2 * a2);
+      hel = sl * sl * q_;
+      her = sr * sr * q_;
+    }
+  }
+  hel3[xk] = hel;
+  her3[xk] = her;
+}
+
+// arctic swap of hel/her after their halo update (mod_cppm.F90:1531-1541, :1686-1703)
+template <int DIR>
+__global__ void cppm_swap_edges(Geom g, bool fold_fix, double* hel3, double* her3) {
+  const int k = blockIdx.y;
+  const int nrow = DIR == 0 ? 1 : 1 + 4;
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)g.ldi * nrow) return;
+  const int i = (int)(t % g.ldi) + 1 - g.nb, r = (int)(t / g.ldi);
+  bool doit;
+  if (DIR == 0) doit = (i >= -3 && i <= g.ii + 4);
+  // reference quirk (mod_cppm.F90:1690): only the right half of row jj is swapped unless
+  // option cppm_fold_fix=1 asks for the whole (mirrored) row
+  else doit = r == 0 ? (i >= (fold_fix ? 1 : max(1, g.itdm / 2 - g.i0 + 1)) && i <= g.ii)
+                     : (i >= 1 && i <= g.ii);
+  if (!doit) return;
+  const long x = ix2(g, i, g.jj + r) + (long)k * g.lev;
+  double a = hel3[x]; hel3[x] = her3[x]; her3[x] = a;
+}
+
+// ---- compatible tracer edge weights (per-interface LU, :519-722) --------------
+// c0..c3 are the 4 cells e-2..e+1; tb points at this interface's table entry.
+__device__ __forceinline__ void tracer_edge_weights(int stencil, const double* __restrict__ tb, long lev,
+                                                    const double hm[4], const double hel[4],
+                                                    const double her[4], double& tevc1, double& tevc2,
+                                                    double& tevc3, double& tevc4) {
+  double h1i, h2i, h3i, h4i, a12, a22, a32, a42, a13, a23, a33, a43, a14, a24, a34, a44, q;
+#define TM0(r) tb[(T_TMC0 + (r) - 1) * lev]
+#define TML(r) tb[(T_TMCL + (r) - 1) * lev]
+#define TMR(r) tb[(T_TMCR + (r) - 1) * lev]
+#define EL(r, c, hi) (TM0(r) + (TML(r) * hel[c] + TMR(r) * her[c]) * hi)
+  switch (stencil) {
+    case stencil_1111:
+      h1i = K1 / hm[0]; h2i = K1 / hm[1]; h3i = K1 / hm[2]; h4i = K1 / hm[3];
+      a12 = EL(1, 0, h1i); a13 = EL(2, 0, h1i); a14 = EL(3, 0, h1i);
+      a22 = EL(4, 1, h2i) - a12; a23 = EL(5, 1, h2i) - a13; a24 = EL(6, 1, h2i) - a14;
+      a32 = EL(7, 2, h3i) - a12; a33 = EL(8, 2, h3i) - a13; a34 = EL(9, 2, h3i) - a14;
+      a42 = EL(10, 3, h4i) - a12; a43 = EL(11, 3, h4i) - a13; a44 = EL(12, 3, h4i) - a14;
+      q = K1 / a22;
+      a23 = a23 * q;
+      a33 = a33 - a23 * a32;
+      a43 = a43 - a23 * a42;
+      a24 = a24 * q;
+      a34 = a34 - a24 * a32;
+      a44 = a44 - a24 * a42;
+      a34 = a34 / a33;
+      a44 = a44 - a34 * a43;
+      tevc2 = -a12;
+      tevc3 = -a13 - a23 * tevc2;
+      tevc4 = -a14 - a24 * tevc2 - a34 * tevc3;
+      tevc4 = tevc4 / a44;
+      tevc3 = (tevc3 - a43 * tevc4) / a33;
+      tevc2 = (tevc2 - a32 * tevc3 - a42 * tevc4) / a22;
+      tevc1 = K1 - tevc2 - tevc3 - tevc4;
+      break;
+    case stencil_1110:
+      h1i = K1 / hm[0]; h2i = K1 / hm[1]; h3i = K1 / hm[2];
+      a12 = EL(1, 0, h1i); a13 = EL(2, 0, h1i);
+      a22 = EL(4, 1, h2i) - a12; a23 = EL(5, 1, h2i) - a13;
+      a32 = EL(7, 2, h3i) - a12; a33 = EL(8, 2, h3i) - a13;
+      a23 = a23 / a22;
+      a33 = a33 - a23 * a32;
+      tevc2 = -a12;
+      tevc3 = -a13 - a23 * tevc2;
+      tevc3 = tevc3 / a33;
+      tevc2 = (tevc2 - a32 * tevc3) / a22;
+      tevc1 = K1 - tevc2 - tevc3;
+      tevc4 = K0;
+      break;
+    case stencil_0111:
+      h2i = K1 / hm[1]; h3i = K1 / hm[2]; h4i = K1 / hm[3];
+      a22 = EL(4, 1, h2i); a23 = EL(5, 1, h2i);
+      a32 = EL(7, 2, h3i) - a22; a33 = EL(8, 2, h3i) - a23;
+      a42 = EL(10, 3, h4i) - a22; a43 = EL(11, 3, h4i) - a23;
+      a33 = a33 / a32;
+      a43 = a43 - a33 * a42;
+      tevc3 = -a22;
+      tevc4 = -a23 - a33 * tevc3;
+      tevc4 = tevc4 / a43;
+      tevc3 = (tevc3 - a42 * tevc4) / a32;
+      tevc2 = K1 - tevc3 - tevc4;
+      tevc1 = K0;
+      break;
+    case stencil_1100:
+      h1i = K1 / hm[0]; h2i = K1 / hm[1];
+      a12 = EL(1, 0, h1i);
+      a22 = EL(4, 1, h2i) - a12;
+      tevc2 = -a12 / a22;
+      tevc1 = K1 - tevc2;
+      tevc3 = K0; tevc4 = K0;
+      break;
+    case stencil_0110:
+      h2i = K1 / hm[1]; h3i = K1 / hm[2];
+      a22 = EL(4, 1, h2i);
+      a32 = EL(7, 2, h3i) - a22;
+      tevc3 = -a22 / a32;
+      tevc2 = K1 - tevc3;
+      tevc1 = K0; tevc4 = K0;
+      break;
+    case stencil_0011:
+      h3i = K1 / hm[2]; h4i = K1 / hm[3];
+      a32 = EL(7, 2, h3i);
+      a42 = EL(10, 3, h4i) - a32;
+      tevc4 = -a32 / a42;
+      tevc3 = K1 - tevc4;
+      tevc1 = K0; tevc2 = K0;
+      break;
+    case stencil_0100:
+      tevc1 = K0; tevc2 = K1; tevc3 = K0; tevc4 = K0;
+      break;
+    case stencil_0010:
+      tevc1 = K0; tevc2 = K0; tevc3 = K1; tevc4 = K0;
+      break;
+    default:
+      tevc1 = K0; tevc2 = K0; tevc3 = K0; tevc4 = K0;
+      break;
+  }
+#undef TM0
+#undef TML
+#undef TMR
+#undef EL
+}
+
+template <int NT>
+struct ScalarPtrs {
+  const double* src[NT];  // level-1 pointers of the source set (temp, saln, trc...)
+  double* dst[NT];        // level-1 pointers of the destination set
+};
+
+// ---- flux kernel ------------------------------------------------------------
+// Thread block = TP positions along the pass direction x TC along the cross
+// direction; it produces TP-5 updated cells per cross position.  Stage data
+// flows through shared memory:
+//   cells (hm,hel,her,tm) -> A: edge values te -> B: curvature d2t
+//   -> C: limited parabolas -> D: face fluxes -> E: cell update.
+template <int DIR, int NT, int TP, int TC>
+__global__ void __launch_bounds__(TP* TC)
+cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */,
+          const double* __restrict__ dp_src, double* __restrict__ dp_dst, ScalarPtrs<NT> S,
+          const double* __restrict__ hel3, const double* __restrict__ her3,
+          const double* __restrict__ cad /* pass-direction flux area */,
+          const double* __restrict__ cac /* cross-direction flux area */,
+          const double* __restrict__ p, const double* __restrict__ pbd /* pbu or pbv */,
+          const double* __restrict__ scp2i, const double* __restrict__ tab,
+          const int* __restrict__ sten, double* __restrict__ flx, double* __restrict__ tflx,
+          double* __restrict__ sflx /* level km=1+mm .. pointers at level 1+mm */) {
+  constexpr int NCELL = TP + 3;
+  extern __shared__ double smem[];
+  // layout per cross position tc: cells[(3+NT)][NCELL], E[NT][TP], D[NT][TP], PAR[3+3NT][TP], F[1+NT][TP]
+  constexpr int PER_TC = (3 + NT) * NCELL + (NT + NT + 3 + 3 * NT + 1 + NT) * TP;
+  const int tp = DIR == 0 ? threadIdx.x : threadIdx.y;
+  const int tc = DIR == 0 ? threadIdx.y : threadIdx.x;
+  double* base = smem + (long)tc * PER_TC;
+  double* s_hm = base;
+  double* s_hel = s_hm + NCELL;
+  double* s_her = s_hel + NCELL;
+  double* s_tm = s_her + NCELL;              // [NT][NCELL]
+  double* s_E = s_tm + NT * NCELL;           // [NT][TP]
+  double* s_D = s_E + NT * TP;               // [NT][TP]
+  double* s_P = s_D + NT * TP;               // [3+3NT][TP]
+  double* s_F = s_P + (3 + 3 * NT) * TP;     // [1+NT][TP]
+
+  constexpr int NOUT = TP - 5;
+  const int npass = DIR == 0 ? g.idm : g.jdm;
+  const int ncross = DIR == 0 ? g.jdm : g.idm;
+  const int tile = DIR == 0 ? blockIdx.x : blockIdx.y;
+  const int ctile = DIR == 0 ? blockIdx.y : blockIdx.x;
+  const int k = blockIdx.z + 1;
+  const int s0 = 1 + tile * NOUT;   // first updated cell of this tile
+  const int p0 = s0 - 2;            // pass index of thread tp=0
+  const int cc = 1 + ctile * TC + tc;
+  const bool cvalid = cc <= ncross;
+  const int ccl = min(cc, ncross);
+  const long sp = DIR == 0 ? 1 : g.ldi, sc = DIR == 0 ? g.ldi : 1;
+  const int pmax = npass + g.nb;    // last addressable pass index
+  // address of (pass index pi, cross ccl) in a 2-D level
+  auto addr = [&](int pi) -> long {
+    return DIR == 0 ? ix2(g, pi, ccl) : ix2(g, ccl, pi);
+  };
+  const long koff = (long)(k - 1) * g.lev;
+
+  // ---- stage cell values: cells p0-2 .. p0+TP (NCELL of them) ----
+  for (int q = tp; q < NCELL; q += TP) {
+    const int pi = min(p0 - 2 + q, pmax);
+    const long y = addr(pi), yk = y + koff;
+    double h = fmax(K0, dp_src[yk]) + DPEPS;
+    if (second_pass) h = h / (K1 - (cac[yk + sc] - cac[yk]) * scp2i[y]);
+    s_hm[q] = h;
+    s_hel[q] = hel3[yk];
+    s_her[q] = her3[yk];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) s_tm[nt * NCELL + q] = S.src[nt][yk];
+  }
+  __syncthreads();
+
+  // own cell / edge / face index
+  const int e = p0 + tp;
+  const int el = min(e, pmax);
+  const long xe = addr(el), xek = xe + koff;
+  const int qc = tp + 2;  // smem index of own cell
+  const double hm_c = s_hm[qc], hel_c = s_hel[qc], her_c = s_her[qc];
+  double tm_c[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) tm_c[nt] = s_tm[nt * NCELL + qc];
+
+  // ---- A: tracer edge values at edge e from cells e-2..e+1 (smem tp..tp+3) ----
+  {
+    double hm4[4], hel4[4], her4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { hm4[q] = s_hm[tp + q]; hel4[q] = s_hel[tp + q]; her4[q] = s_her[tp + q]; }
+    double w1, w2, w3, w4;
+    tracer_edge_weights(sten[xe], tab + xe, g.lev, hm4, hel4, her4, w1, w2, w3, w4);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+      s_E[nt * TP + tp] = w1 * s_tm[nt * NCELL + tp] + w2 * s_tm[nt * NCELL + tp + 1] +
+                          w3 * s_tm[nt * NCELL + tp + 2] + w4 * s_tm[nt * NCELL + tp + 3];
+  }
+  __syncthreads();
+
+  // ---- B: thickness factors and curvature proxy of own cell ----
+  double tel[NT], ter[NT];
+  double hf1m, hf1l, hf1r, hf2m, hf2l, hf2r;
+  {
+    const double q = K1 / (K12 * hm_c - hel_c - her_c);
+    hf1m = K60 * hm_c * q;
+    hf1l = -(K42 * hm_c + K4 * hel_c - K6 * her_c) * q;
+    hf1r = -(K18 * hm_c - K4 * hel_c + K6 * her_c) * q;
+    hf2m = -hf1m;
+    hf2l = K5 * (K6 * hm_c + hel_c - her_c) * q;
+    hf2r = K5 * (K6 * hm_c - hel_c + her_c) * q;
+    const double d2m = tab[T_D2M * g.lev + xe];
+    const int tq = min(tp + 1, TP - 1);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      tel[nt] = s_E[nt * TP + tp];
+      ter[nt] = s_E[nt * TP + tq];
+      s_D[nt * TP + tp] = d2m * (hf2m * tm_c[nt] + hf2l * tel[nt] + hf2r * ter[nt]);
+    }
+  }
+  __syncthreads();
+
+  // ---- C: limiters and parabola coefficients of own cell ----
+  double hpc0, hpc1, hpc2, tpc0[NT], tpc1[NT], tpc2[NT];
+  {
+    const double ssc = tab[T_SSC * g.lev + xe], scc = tab[T_SCC * g.lev + xe];
+    const int tm1 = max(tp - 1, 0), tp1 = min(tp + 1, TP - 1);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const double d2c = s_D[nt * TP + tp], d2l = s_D[nt * TP + tm1], d2r = s_D[nt * TP + tp1];
+      const double tmm = s_tm[nt * NCELL + qc - 1], tmp = s_tm[nt * NCELL + qc + 1], tmc = tm_c[nt];
+      double sl, sr, scv, a2;
+      if (d2l * d2c <= K0 || d2c * d2r <= K0) {
+        sl = ssc * (tmc - tmm);
+        sr = ssc * (tmp - tmc);
+        if (sl * sr > K0) {
+          scv = scc * (tmp - tmm);
+          scv = fsign(fmin(fmin(fabs(sl), fabs(sr)), fabs(scv)), scv);
+          if ((tmm - tel[nt]) * (tmc - tel[nt]) > K0)
+            tel[nt] = tmc - fsign(fmin(K1_2 * fabs(scv), fabs(tel[nt] - tmc)), scv);
+          if ((tmp - ter[nt]) * (tmc - ter[nt]) > K0)
+            ter[nt] = tmc + fsign(fmin(K1_2 * fabs(scv), fabs(ter[nt] - tmc)), scv);
+          sl = hf1m * tmc + hf1l * tel[nt] + hf1r * ter[nt];
+          a2 = hf2m * tmc + hf2l * tel[nt] + hf2r * ter[nt];
+          sr = sl + K2 * a2;
+          if (sl * sr < K0) {
+            if ((ter[nt] - tel[nt]) * a2 < K0)
+              tel[nt] = -((hf1m + K2 * hf2m) * tmc + (hf1r + K2 * hf2r) * ter[nt]) / (hf1l + K2 * hf2l);
+            else
+              ter[nt] = -(hf1m * tmc + hf1l * tel[nt]) / hf1r;
+          }
+        } else {
+          tel[nt] = tmc;
+          ter[nt] = tmc;
+        }
+      }
+      if (nt >= 1) {  // positivity for everything but temperature (:788-801)
+        tel[nt] = fmax(tel[nt], K0);
+        ter[nt] = fmax(ter[nt], K0);
+        sl = hf1m * tmc + hf1l * tel[nt] + hf1r * ter[nt];
+        a2 = hf2m * tmc + hf2l * tel[nt] + hf2r * ter[nt];
+        sr = sl + K2 * a2;
+        if (sl < K0 && sr > K0) {
+          if (a2 * tel[nt] - K1_4 * sl * sl < K0) {
+            const double q = K3 * tmc / (K3 * sl * sr + K4 * a2 * a2);
+            tel[nt] = sl * sl * q;
+            ter[nt] = sr * sr * q;
+          }
+        }
+      }
+      tpc0[nt] = tel[nt];
+      tpc1[nt] = hf1m * tmc + hf1l * tel[nt] + hf1r * ter[nt];
+      tpc2[nt] = hf2m * tmc + hf2l * tel[nt] + hf2r * ter[nt];
+      s_P[(3 + 3 * nt + 0) * TP + tp] = tpc0[nt];
+      s_P[(3 + 3 * nt + 1) * TP + tp] = tpc1[nt];
+      s_P[(3 + 3 * nt + 2) * TP + tp] = tpc2[nt];
+    }
+    hpc0 = hel_c;
+    hpc1 = K6 * hm_c - K4 * hel_c - K2 * her_c;
+    hpc2 = K3 * (hel_c - K2 * hm_c + her_c);
+    s_P[0 * TP + tp] = hpc0; s_P[1 * TP + tp] = hpc1; s_P[2 * TP + tp] = hpc2;
+  }
+  __syncthreads();
+
+  // ---- D: flux through face e (flux_integration, :1373-1468) ----
+  const double ai_c = scp2i[xe];
+  double hf, htf[NT];
+  {
+    const double ca = cad[xek];
+    const double db = pbd[xe + (long)(n_lev2d - 1) * g.lev];
+    if (ca < K0) {
+      const double c = ca * ai_c;
+      const double du = p[xek], dl = p[xek + g.lev];
+      double p0_, p1_, p2_;
+      if (dl > db) {
+        const double hb = fmax(K0, db - du);
+        hf = hb * ca;
+        p0_ = hb;
+        p1_ = -K1_2 * hb * c;
+        p2_ = K1_3 * hb * c * c;
+      } else {
+        hf = (hpc0 - (K1_2 * hpc1 - K1_3 * hpc2 * c) * c) * ca;
+        p0_ = hpc0 - (K1_2 * hpc1 - K1_3 * hpc2 * c) * c;
+        p1_ = -(K1_2 * hpc0 - (K1_3 * hpc1 - K1_4 * hpc2 * c) * c) * c;
+        p2_ = (K1_3 * hpc0 - (K1_4 * hpc1 - K1_5 * hpc2 * c) * c) * c * c;
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) htf[nt] = (p0_ * tpc0[nt] + p1_ * tpc1[nt] + p2_ * tpc2[nt]) * ca;
+    } else {
+      const int tm1 = max(tp - 1, 0);
+      const long xu = xe - sp, xuk = xek - sp;  // upstream cell e-1
+      const double c = ca * scp2i[xu];
+      const double q1 = K1 - K1_2 * c;
+      const double q2 = K1 - (K1 - K1_3 * c) * c;
+      const double du = p[xuk], dl = p[xuk + g.lev];
+      const double u0 = s_P[0 * TP + tm1], u1 = s_P[1 * TP + tm1], u2 = s_P[2 * TP + tm1];
+      double p0_, p1_, p2_;
+      if (dl > db) {
+        const double hb = fmax(K0, db - du);
+        hf = hb * ca;
+        p0_ = hb;
+        p1_ = q1 * hb;
+        p2_ = q2 * hb;
+      } else {
+        hf = (u0 + q1 * u1 + q2 * u2) * ca;
+        const double q3 = K1_4 * (K1 + K3 * (K1 - c) * q2);
+        const double q4 = K1_5 * (K1 + K4 * (K1 - c) * q3);
+        p0_ = u0 + q1 * u1 + q2 * u2;
+        p1_ = q1 * u0 + q2 * u1 + q3 * u2;
+        p2_ = q2 * u0 + q3 * u1 + q4 * u2;
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        htf[nt] = (p0_ * s_P[(3 + 3 * nt + 0) * TP + tm1] + p1_ * s_P[(3 + 3 * nt + 1) * TP + tm1] +
+                   p2_ * s_P[(3 + 3 * nt + 2) * TP + tm1]) * ca;
+    }
+    s_F[tp] = hf;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) s_F[(1 + nt) * TP + tp] = htf[nt];
+  }
+  __syncthreads();
+
+  // ---- E: divergence update of own cell + flux accumulation at own face ----
+  if (!cvalid) return;
+  const bool face_ok = tp >= 2 && tp <= TP - 3 && e >= 1 && e <= npass + 1;
+  const bool cell_ok = tp >= 2 && tp <= TP - 4 && e >= 1 && e <= npass;
+  if (cell_ok) {
+    const double ho = fmax(K0, dp_src[xek]) + DPEPS;
+    const double hn = ho - (s_F[tp + 1] - hf) * ai_c;
+    const double hni = K1 / hn;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+      S.dst[nt][xek] = (ho * tm_c[nt] - (s_F[(1 + nt) * TP + tp + 1] - htf[nt]) * ai_c) * hni;
+    dp_dst[xek] = fmax(K0, hn - DPEPS);
+  }
+  // faces s0..s0+NOUT-1 belong to this tile; the last tile also owns face npass+1
+  if (face_ok && (tp <= TP - 4 || e == npass + 1)) {
+    flx[xek] = flx[xek] + hf;
+    tflx[xek] = tflx[xek] + htf[0];
+    sflx[xek] = sflx[xek] + htf[1];
+  }
+}
+
+template <int DIR, int NT>
+void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, const ScalarPtrs<NT>& S,
+                 const double* hel3, const double* her3, const double* cad, const double* cac,
+                 const double* p, const double* pbd, const double* scp2i, const double* tab,
+                 const int* sten, double* flx, double* tflx, double* sflx) {
+  Ctx& c = C(); const Geom& g = c.g;
+  constexpr int TP = DIR == 0 ? 128 : 32;
+  constexpr int TC = DIR == 0 ? 2 : 16;
+  constexpr int NOUT = TP - 5;
+  constexpr int NCELL = TP + 3;
+  constexpr int PER_TC = (3 + NT) * NCELL + (NT + NT + 3 + 3 * NT + 1 + NT) * TP;
+  const size_t smem = sizeof(double) * PER_TC * TC;
+  auto kern = cppm_flux<DIR, NT, TP, TC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 block, grid;
+  if (DIR == 0) {
+    block = dim3(TP, TC);
+    grid = dim3(cdiv(g.idm, NOUT), cdiv(g.jdm, TC), g.kdm);
+  } else {
+    block = dim3(TC, TP);
+    grid = dim3(cdiv(g.idm, TC), cdiv(g.jdm, NOUT), g.kdm);
+  }
+  // NB: the face npass+1 must be covered: tiles cover cells 1..ntile*NOUT >= npass and
+  // thread tp = npass+1-p0 <= TP-3 of the last tile owns it.
+  LAUNCH(kern, grid, block, smem, g, second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd,
+         scp2i, tab, sten, flx, tflx, sflx);
+}
+
+template <int DIR, int NT>
+void cppm_pass(bool second_pass, int n, int mm, double* dp_src, double* dp_dst, ScalarPtrs<NT> S) {
+  Ctx& c = C(); const Geom& g = c.g;
+  const int mh = DIR == 0 ? 4 : 0, nh = DIR == 0 ? 0 : 4;
+  // halo of the transported fields in the pass direction (:1485-1490 / :1640-1645)
+  std::vector<HaloReq> reqs{{dp_src, g.kdm, halo_ps}};
+  for (int nt = 0; nt < NT; ++nt) reqs.push_back({const_cast<double*>(S.src[nt]), g.kdm, halo_ps});
+  halo_update(reqs, mh, nh);
+  double* hel3 = c.owned("cppm_hel_3d", g.kdm);
+  double* her3 = c.owned("cppm_her_3d", g.kdm);
+  const double* tab = c.dev(DIR == 0 ? "cppm_tab_i" : "cppm_tab_j");
+  const int* sten = c.idev(DIR == 0 ? "cppm_sten_i" : "cppm_sten_j");
+  const double* cad = c.dev(DIR == 0 ? "cau" : "cav");
+  const double* cac = c.dev(DIR == 0 ? "cav" : "cau");
+  const double* scp2i = c.dev("scp2i");
+  {
+    dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
+    LAUNCH(cppm_hedges<DIR>, grid, 128, 0, g, second_pass, dp_src, cac, scp2i, tab, hel3, her3);
+  }
+  halo_update(std::vector<HaloReq>{{hel3, g.kdm, halo_ps}, {her3, g.kdm, halo_ps}}, mh, nh);
+  if (g.nreg == 2 && g.north) {
+    const int nrow = DIR == 0 ? 1 : 5;
+    dim3 grid(cdiv((long)g.ldi * nrow, 256), g.kdm);
+    LAUNCH(cppm_swap_edges<DIR>, grid, 256, 0, g, c.option("cppm_fold_fix", "0") == "1", hel3, her3);
+  }
+  const long om = (long)mm * g.lev;
+  launch_flux<DIR, NT>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, c.dev("p"),
+                       c.dev(DIR == 0 ? "pbu" : "pbv"), scp2i, tab, sten,
+                       c.dev(DIR == 0 ? "uflx" : "vflx") + om, c.dev(DIR == 0 ? "utflx" : "vtflx") + om,
+                       c.dev(DIR == 0 ? "usflx" : "vsflx") + om);
+}
+
+template <int NT>
+void cppm_run(int n, int mm, int nn) {
+  Ctx& c = C(); const Geom& g = c.g;
+  const int nstep = (int)c.scalar("nstep");
+  halo_update(std::vector<HaloReq>{{c.dev("cau"), g.kdm, halo_uv}, {c.dev("cav"), g.kdm, halo_vv}}, 4, 4);
+  const long on = (long)nn * g.lev;
+  double* dpA = c.dev("dp") + on;
+  double* dpB = c.owned("cppm_tmp_dp", g.kdm);
+  ScalarPtrs<NT> AB{}, BA{};
+  double* a[NT]; double* b[NT];
+  a[0] = c.dev("temp") + on; a[1] = c.dev("saln") + on;
+  b[0] = c.owned("cppm_tmp_temp", g.kdm); b[1] = c.owned("cppm_tmp_saln", g.kdm);
+  for (int nt = 2; nt < NT; ++nt) {
+    a[nt] = c.dev("trc") + on + (long)(nt - 2) * 2 * g.kdm * g.lev;
+    b[nt] = c.owned("cppm_tmp_trc" + std::to_string(nt - 1), g.kdm);
+  }
+  for (int nt = 0; nt < NT; ++nt) { AB.src[nt] = a[nt]; AB.dst[nt] = b[nt]; BA.src[nt] = b[nt]; BA.dst[nt] = a[nt]; }
+  if (nstep % 2 == 1) {
+    cppm_pass<0, NT>(false, n, mm, dpA, dpB, AB);
+    cppm_pass<1, NT>(true, n, mm, dpB, dpA, BA);
+  } else {
+    cppm_pass<1, NT>(false, n, mm, dpA, dpB, AB);
+    cppm_pass<0, NT>(true, n, mm, dpB, dpA, BA);
+  }
+}
+
+}  // namespace
+
+// init_cppm (mod_cppm.F90:2504-2746)
+void init_cppm_dev() {
+  Ctx& c = C(); const Geom& g = c.g;
+  const std::string comp = c.option("cppm_compatibility", "full"), lim = c.option("cppm_limiting", "non_oscillatory");
+  if (comp != "full")
+    throw std::runtime_error(" init_cppm: cppm_compatibility = " + comp + " is unsupported!");
+  if (lim != "non_oscillatory")
+    throw std::runtime_error(" init_cppm: cppm_limiting = " + lim + " is unsupported!");
+  double* ti = c.owned("cppm_tab_i", T_NLEV);
+  double* tj = c.owned("cppm_tab_j", T_NLEV);
+  CUDA_CHECK(cudaMemsetAsync(ti, 0, sizeof(double) * g.lev * T_NLEV, c.stream));
+  CUDA_CHECK(cudaMemsetAsync(tj, 0, sizeof(double) * g.lev * T_NLEV, c.stream));
+  LAUNCH(cppm_tables_kernel, cdiv((long)g.ii * g.jj, 128), 128, 0, g, c.idev("ip"), c.dev("scpx"),
+         c.dev("scpy"), ti, tj);
+  // halos: coefficient tables travel as u/v-type scalars, slope/curvature masks
+  // as p-type (:2605-2646)
+  halo_update(std::vector<HaloReq>{{ti, T_SSC, halo_us}, {ti + (long)T_STEN * g.lev, 1, halo_us},
+                                   {ti + (long)T_SSC * g.lev, 3, halo_ps}}, g.nb, 0);
+  halo_update(std::vector<HaloReq>{{tj, T_SSC, halo_vs}, {tj + (long)T_STEN * g.lev, 1, halo_vs},
+                                   {tj + (long)T_SSC * g.lev, 3, halo_ps}}, 0, g.nb);
+  if (g.nreg == 2 && g.north)
+    LAUNCH(cppm_tables_arctic, cdiv((long)g.ldi * (1 + g.nb), 128), 128, 0, g, ti, tj);
+  int* si = c.owned_int("cppm_sten_i", 1);
+  int* sj = c.owned_int("cppm_sten_j", 1);
+  LAUNCH(cppm_tags_to_int, cdiv(g.lev, 256), 256, 0, g, ti, tj, si, sj);
+  c.owned("cppm_hel_3d", g.kdm);
+  c.owned("cppm_her_3d", g.kdm);
+}
+
+// advect (mod_advect.F90:59-189), advmth='cppm'
+void advect_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
+  (void)k1m; (void)k1n;
+  Ctx& c = C(); const Geom& g = c.g;
+  const std::string advmth = c.option("advmth", "cppm");
+  if (advmth != "cppm") throw std::runtime_error(" advmth = " + advmth + " is unsupported!");
+  if (!c.has("cppm_tab_i")) throw std::runtime_error("advect: init_cppm has not been called");
+  dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
+  LAUNCH(advect_flux_area, grid, 128, 0, g, m, mm, nn, c.scalar("delt1"), c.scalar("dlt"), c.idev("iu"),
+         c.idev("iv"), c.dev("u"), c.dev("v"), c.dev("dpu"), c.dev("dpv"), c.dev("ubflxs_p"),
+         c.dev("vbflxs_p"), c.dev("pbu"), c.dev("pbv"), c.dev("umfltd"), c.dev("vmfltd"),
+         c.dev("umflsm"), c.dev("vmflsm"), c.dev("scuy"), c.dev("scvx"), c.dev("umax"), c.dev("vmax"),
+         c.dev("cau"), c.dev("cav"));
+  switch (2 + g.ntr) {
+    case 2: cppm_run<2>(n, mm, nn); break;
+    case 3: cppm_run<3>(n, mm, nn); break;
+    case 4: cppm_run<4>(n, mm, nn); break;
+    default: throw std::runtime_error("advect: this build transports at most 2 passive tracers (ntr<=2)");
+  }
+  const long on = (long)nn * g.lev;
+  std::vector<HaloReq> reqs{{c.dev("dp") + on, g.kdm, halo_ps}, {c.dev("temp") + on, g.kdm, halo_ps},
+                            {c.dev("saln") + on, g.kdm, halo_ps}};
+  for (int nt = 0; nt < g.ntr; ++nt)
+    reqs.push_back({c.dev("trc") + on + (long)nt * 2 * g.kdm * g.lev, g.kdm, halo_ps});
+  halo_update(reqs, 1, 1);
+}
+
+}  // namespace blom

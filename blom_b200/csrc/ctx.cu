@@ -1,0 +1,260 @@
+// Context, array registry and the extern "C" boundary (include/blomgpu.h).
+#include "common.cuh"
+#include "../../include/blomgpu.h"
+#include <cstring>
+
+namespace blom {
+
+Ctx& C() { static Ctx c; return c; }
+
+double* Ctx::owned(const std::string& n, int nlev) {
+  auto it = f.find(n);
+  if (it != f.end() && it->second.nlev == nlev) return it->second.d;
+  if (it != f.end() && it->second.h == nullptr && it->second.d) cudaFree(it->second.d);
+  DField fd; fd.nlev = nlev; fd.h = nullptr;
+  size_t bytes = sizeof(double) * (size_t)g.lev * nlev;
+  CUDA_CHECK(cudaMalloc(&fd.d, bytes));
+  CUDA_CHECK(cudaMemsetAsync(fd.d, 0, bytes, stream));
+  f[n] = fd;
+  return fd.d;
+}
+int* Ctx::owned_int(const std::string& n, int nlev) {
+  auto it = fi.find(n);
+  if (it != fi.end() && it->second.nlev == nlev) return it->second.d;
+  IFieldD fd; fd.nlev = nlev; fd.h = nullptr;
+  size_t bytes = sizeof(int) * (size_t)g.lev * nlev;
+  CUDA_CHECK(cudaMalloc(&fd.d, bytes));
+  CUDA_CHECK(cudaMemsetAsync(fd.d, 0, bytes, stream));
+  fi[n] = fd;
+  return fd.d;
+}
+
+ScopedTimer::ScopedTimer(const char* n) : name(n), on(C().timers_on) {
+  if (!on) return;
+  l0 = C().launches;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, C().stream);
+}
+ScopedTimer::~ScopedTimer() {
+  if (!on) return;
+  cudaEventRecord(e1, C().stream);
+  cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  Ctx& c = C();
+  if (!c.timers.count(name)) c.timer_order.push_back(name);
+  Timer& t = c.timers[name];
+  t.ms += ms; t.calls++; t.launches += c.launches - l0;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+}  // namespace blom
+
+using namespace blom;
+
+static char g_err[2048] = "";
+
+#define GUARD(...)                                          \
+  try { __VA_ARGS__; return 0; }                            \
+  catch (const std::exception& e) {                         \
+    std::snprintf(g_err, sizeof g_err, "%s", e.what());     \
+    std::fprintf(stderr, "blomgpu error: %s\n", g_err);     \
+    return 1;                                               \
+  }
+
+static void do_init(const int* dims, const int* tile, int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw std::runtime_error("blomgpu_init: no CUDA device available (this library has no CPU fallback)");
+  CUDA_CHECK(cudaSetDevice(device));
+  Ctx& c = C();
+  Geom& g = c.g;
+  g.itdm = dims[0]; g.jtdm = dims[1]; g.kdm = dims[2]; g.idm = dims[3]; g.jdm = dims[4];
+  g.nb = dims[5]; g.ntr = dims[6]; g.nreg = dims[7];
+  g.i0 = tile[0]; g.j0 = tile[1]; g.ii = tile[2]; g.jj = tile[3];
+  g.rank = tile[4]; g.nranks = tile[5];
+  if (g.ii != g.idm || g.jj != g.jdm)
+    throw std::runtime_error("blomgpu_init: tile extent must equal idm/jdm");
+  if (g.i0 != 0 || g.ii != g.itdm)
+    throw std::runtime_error("blomgpu_init: only j-band decompositions (i0=0, ii=itdm) are supported");
+  g.ldi = g.idm + 2 * g.nb; g.ldj = g.jdm + 2 * g.nb;
+  g.lev = (long)g.ldi * g.ldj;
+  g.south = (g.j0 == 0); g.north = (g.j0 + g.jj == g.jtdm);
+  c.device = device;
+  if (!c.stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  c.red_cap = 1 << 16;
+  CUDA_CHECK(cudaMalloc(&c.d_red, c.red_cap * sizeof(double)));
+  CUDA_CHECK(cudaMallocHost(&c.h_red, c.red_cap * sizeof(double)));
+}
+
+static void do_finalize() {
+  Ctx& c = C();
+  if (c.stream) cudaStreamSynchronize(c.stream);
+  for (auto& kv : c.f) if (kv.second.d) cudaFree(kv.second.d);
+  for (auto& kv : c.fi) if (kv.second.d) cudaFree(kv.second.d);
+  if (c.d_red) cudaFree(c.d_red);
+  if (c.h_red) cudaFreeHost(c.h_red);
+  for (int s = 0; s < 2; ++s) {
+    if (c.halo_send[s]) cudaFree(c.halo_send[s]);
+    if (c.halo_recv[s]) cudaFree(c.halo_recv[s]);
+  }
+  cudaStream_t st = c.stream;
+  void* nccl = c.nccl;
+  c = Ctx();
+  c.stream = st;
+  c.nccl = nccl;
+}
+
+static void do_register(const char* name, double* host, int nlev) {
+  Ctx& c = C();
+  auto it = c.f.find(name);
+  if (it != c.f.end() && it->second.nlev == nlev) { it->second.h = host; return; }
+  if (it != c.f.end() && it->second.d) cudaFree(it->second.d);
+  DField fd; fd.h = host; fd.nlev = nlev;
+  CUDA_CHECK(cudaMalloc(&fd.d, sizeof(double) * (size_t)c.g.lev * nlev));
+  c.f[name] = fd;
+}
+static void do_register_int(const char* name, int* host, int nlev) {
+  Ctx& c = C();
+  auto it = c.fi.find(name);
+  if (it != c.fi.end() && it->second.nlev == nlev) { it->second.h = host; return; }
+  if (it != c.fi.end() && it->second.d) cudaFree(it->second.d);
+  IFieldD fd; fd.h = host; fd.nlev = nlev;
+  CUDA_CHECK(cudaMalloc(&fd.d, sizeof(int) * (size_t)c.g.lev * nlev));
+  c.fi[name] = fd;
+}
+
+static void do_copy(const char* name, bool up) {
+  Ctx& c = C();
+  auto it = c.f.find(name);
+  if (it != c.f.end()) {
+    DField& fd = it->second;
+    if (!fd.h) throw std::runtime_error(std::string("blomgpu: no host array bound to ") + name);
+    size_t bytes = sizeof(double) * (size_t)c.g.lev * fd.nlev;
+    if (up) CUDA_CHECK(cudaMemcpyAsync(fd.d, fd.h, bytes, cudaMemcpyHostToDevice, c.stream));
+    else CUDA_CHECK(cudaMemcpyAsync(fd.h, fd.d, bytes, cudaMemcpyDeviceToHost, c.stream));
+    return;
+  }
+  auto jt = c.fi.find(name);
+  if (jt == c.fi.end()) throw std::runtime_error(std::string("blomgpu: field not registered: ") + name);
+  IFieldD& fd = jt->second;
+  if (!fd.h) throw std::runtime_error(std::string("blomgpu: no host array bound to ") + name);
+  size_t bytes = sizeof(int) * (size_t)c.g.lev * fd.nlev;
+  if (up) CUDA_CHECK(cudaMemcpyAsync(fd.d, fd.h, bytes, cudaMemcpyHostToDevice, c.stream));
+  else CUDA_CHECK(cudaMemcpyAsync(fd.h, fd.d, bytes, cudaMemcpyDeviceToHost, c.stream));
+}
+static void do_copy_all(bool up) {
+  Ctx& c = C();
+  for (auto& kv : c.f) if (kv.second.h) do_copy(kv.first.c_str(), up);
+  for (auto& kv : c.fi) if (kv.second.h) do_copy(kv.first.c_str(), up);
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+static const int* mask_for_itype(int itype) {
+  switch (itype) {
+    case halo_ps: case halo_pv: return C().idev("ip");
+    case halo_qs: case halo_qv: return C().idev("iq");
+    case halo_us: case halo_uv: return C().idev("iu");
+    case halo_vs: case halo_vv: return C().idev("iv");
+    default: throw std::runtime_error(" chksum: itype is unsupported!");
+  }
+}
+
+static int not_impl(const char* what) {
+  std::snprintf(g_err, sizeof g_err, "blomgpu: %s is not implemented in this build", what);
+  std::fprintf(stderr, "%s\n", g_err);
+  return 2;
+}
+
+extern "C" {
+
+const char* blomgpu_last_error(void) { return g_err; }
+int blomgpu_parity_build(void) {
+#ifdef BLOM_PARITY_BUILD
+  return 1;
+#else
+  return 0;
+#endif
+}
+int blomgpu_init(const int dims[8], const int tile[6], int device) { GUARD(do_init(dims, tile, device)) }
+int blomgpu_finalize(void) { GUARD(do_finalize()) }
+
+int blomgpu_register(const char* name, double* host, int nlev) { GUARD(do_register(name, host, nlev)) }
+int blomgpu_register_int(const char* name, int* host, int nlev) { GUARD(do_register_int(name, host, nlev)) }
+int blomgpu_upload(const char* name) { GUARD(do_copy(name, true)) }
+int blomgpu_download(const char* name) { GUARD(do_copy(name, false); CUDA_CHECK(cudaStreamSynchronize(C().stream))) }
+int blomgpu_upload_all(void) { GUARD(do_copy_all(true)) }
+int blomgpu_download_all(void) { GUARD(do_copy_all(false)) }
+int blomgpu_sync(void) { GUARD(CUDA_CHECK(cudaStreamSynchronize(C().stream))) }
+int blomgpu_device_ptr(const char* name, void** dptr, int* nlev) {
+  GUARD(
+    Ctx& c = C();
+    auto it = c.f.find(name);
+    if (it != c.f.end()) { *dptr = it->second.d; if (nlev) *nlev = it->second.nlev; }
+    else {
+      auto jt = c.fi.find(name);
+      if (jt == c.fi.end()) throw std::runtime_error(std::string("blomgpu: field not registered: ") + name);
+      *dptr = jt->second.d; if (nlev) *nlev = jt->second.nlev;
+    })
+}
+
+int blomgpu_set_option(const char* key, const char* value) { GUARD(C().opt[key] = value) }
+int blomgpu_set_scalar(const char* key, double value) { GUARD(C().sc[key] = value) }
+
+int blomgpu_xctilr(const char* name, int koff, int l1, int ld, int mh, int nh, int itype) {
+  GUARD(
+    Ctx& c = C();
+    if (koff < 1 || koff - 1 + ld > c.nlev(name)) throw std::runtime_error("blomgpu_xctilr: level range outside array");
+    ScopedTimer t("xctilr");
+    xctilr_exact(c.dev(name) + (size_t)(koff - 1) * c.g.lev, l1, ld, mh, nh, itype))
+}
+int blomgpu_xcsum(const char* name, int lev, const char* mask, double* sum) {
+  GUARD(Ctx& c = C(); *sum = xcsum_dev(c.dev(name) + (size_t)(lev - 1) * c.g.lev, c.idev(mask)))
+}
+int blomgpu_xcmax(const char* name, int lev, const char* mask, double* out) {
+  GUARD(Ctx& c = C(); *out = xcmax_dev(c.dev(name) + (size_t)(lev - 1) * c.g.lev, c.idev(mask), true))
+}
+int blomgpu_xcmin(const char* name, int lev, const char* mask, double* out) {
+  GUARD(Ctx& c = C(); *out = xcmax_dev(c.dev(name) + (size_t)(lev - 1) * c.g.lev, c.idev(mask), false))
+}
+int blomgpu_chksum(const char* name, int kcsd, int itype, uint32_t* crc) {
+  GUARD(Ctx& c = C(); *crc = xccrc_dev(c.dev(name), kcsd, mask_for_itype(itype)))
+}
+
+int blomgpu_bigrid(const char* depth_name) { GUARD(bigrid_dev(depth_name)) }
+int blomgpu_nreg(void) { return C().g.nreg; }
+int blomgpu_init_cppm(void) { GUARD(init_cppm_dev()) }
+int blomgpu_inieos(void) { GUARD(inieos_dev()) }
+int blomgpu_numerical_bounds(void) { GUARD(numerical_bounds_dev()) }
+int blomgpu_init_fluxes(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(init_fluxes_dev(m, n, mm, nn, k1m, k1n)) }
+
+int blomgpu_tmsmt1(int nn) { GUARD(ScopedTimer t("tmsmt1"); tmsmt1_dev(nn)) }
+int blomgpu_eddtra(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("eddtra"); eddtra_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_advect(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("advect"); advect_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_pbcor1(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("pbcor1"); pbcor1_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_diffus(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("diffus"); diffus_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_pgforc(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("pgforc"); pgforc_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_momtum(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("momtum"); momtum_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_barotp(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("barotp"); barotp_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_pbcor2(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("pbcor2"); pbcor2_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_tmsmt2(int m, int mm, int nn, int k1m) { GUARD(ScopedTimer t("tmsmt2"); tmsmt2_dev(m, mm, nn, k1m)) }
+
+long blomgpu_launch_count(void) { return C().launches; }
+void blomgpu_launch_count_reset(void) { C().launches = 0; }
+int blomgpu_timers_enable(int enable) { C().timers_on = enable != 0; return 0; }
+int blomgpu_timers_get(int cap, char names[][32], double* ms_total, long* calls, long* launches) {
+  Ctx& c = C();
+  int n = 0;
+  for (auto& nm : c.timer_order) {
+    if (n >= cap) break;
+    Timer& t = c.timers[nm];
+    std::snprintf(names[n], 32, "%s", nm.c_str());
+    ms_total[n] = t.ms; calls[n] = t.calls; launches[n] = t.launches;
+    ++n;
+  }
+  return n;
+}
+void blomgpu_timers_reset(void) { C().timers.clear(); C().timer_order.clear(); }
+void* blomgpu_stream(void) { return (void*)C().stream; }
+
+}  // extern "C"

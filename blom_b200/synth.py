@@ -1,0 +1,350 @@
+"""Seeded synthetic ocean state on the reference's grid dimensions.
+
+Every value is a pure function of (seed, field id, level, GLOBAL j, GLOBAL i),
+so a j-band of a multi-GPU run holds exactly the rows of the one-tile state and
+the same arrays can be fed to the CUDA path and to the test oracle
+(SURVEY.md §8d).  Only interiors are generated; halos are filled afterwards with
+xctilr of the proper grid type (`fill_halos`).
+
+Grids (itdm, jtdm, kdm, nreg): bld/<grid>/ of the reference, see CONFIGS.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .lib import (HALO_PS, HALO_PV, HALO_QS, HALO_QV, HALO_US, HALO_UV, HALO_VS, HALO_VV)
+
+ONEM = 9806.0
+
+# name: (itdm, jtdm, kdm, nreg, baclin, batrop)
+CONFIGS = {
+    "tiny0": (20, 18, 4, 0, 1800.0, 36.0),
+    "tiny1": (24, 18, 5, 1, 1800.0, 36.0),
+    "tiny2": (24, 20, 5, 2, 1800.0, 36.0),
+    "tiny3": (20, 18, 4, 3, 1800.0, 36.0),
+    "tiny4": (20, 22, 4, 4, 1800.0, 36.0),
+    "fuk95": (156, 32, 12, 4, 180.0, 6.0),        # tests/fuk95/limits:131-143
+    "channel": (208, 512, 53, 1, 1800.0, 36.0),    # bld/channel/patch.input.1
+    "tnx1v4": (360, 385, 53, 2, 3200.0, 64.0),     # namelist_definition_blom.xml:179-201
+    "tnx0.25v4": (1440, 1153, 53, 2, 900.0, 15.0),
+    "tnx0.125v4": (2880, 2165, 53, 2, 300.0, 6.0),
+}
+
+# xctilr grid/field type of every array the hot path touches
+ITYPE = {
+    # p-points
+    "depths": HALO_PS, "scpx": HALO_PS, "scpy": HALO_PS, "scp2": HALO_PS, "scp2i": HALO_PS,
+    "dp": HALO_PS, "temp": HALO_PS, "saln": HALO_PS, "sigma": HALO_PS, "p": HALO_PS, "phi": HALO_PS,
+    "pb": HALO_PS, "pb_p": HALO_PS, "sealv": HALO_PS, "trc": HALO_PS, "difint": HALO_PS,
+    "difiso": HALO_PS, "difwgt": HALO_PS, "coriop": HALO_PS, "pbath": HALO_PS,
+    "dpold": HALO_PS, "told": HALO_PS, "sold": HALO_PS, "mld": HALO_PS, "OBLdepth": HALO_PS,
+    # u-points
+    "scux": HALO_US, "scuy": HALO_US, "scu2": HALO_US, "scuxi": HALO_US, "scuyi": HALO_US,
+    "u": HALO_UV, "dpu": HALO_US, "pu": HALO_US, "uflx": HALO_UV, "utflx": HALO_UV, "usflx": HALO_UV,
+    "cau": HALO_UV, "ub": HALO_UV, "pbu": HALO_US, "pbu_p": HALO_US, "ubflx": HALO_UV,
+    "ubflxs": HALO_UV, "ubflxs_p": HALO_UV, "ubcors_p": HALO_UV, "umfltd": HALO_UV, "umflsm": HALO_UV,
+    "utfltd": HALO_UV, "utflsm": HALO_UV, "utflld": HALO_UV, "usfltd": HALO_UV, "usflsm": HALO_UV,
+    "usflld": HALO_UV, "umax": HALO_US, "taux": HALO_UV, "nslpx": HALO_US, "pgfx": HALO_UV,
+    "pgfxm": HALO_UV, "xixp": HALO_US, "xixm": HALO_US, "dpuold": HALO_US, "uja": HALO_UV, "ujb": HALO_UV,
+    "pgfxo": HALO_UV, "pgfxm_o": HALO_UV, "xixp_o": HALO_US, "xixm_o": HALO_US, "ubrhs": HALO_UV,
+    "mu_nonloc": HALO_UV, "uflux": HALO_UV, "uflux2": HALO_UV, "uflux3": HALO_UV,
+    # v-points
+    "scvx": HALO_VS, "scvy": HALO_VS, "scv2": HALO_VS, "scvxi": HALO_VS, "scvyi": HALO_VS,
+    "v": HALO_VV, "dpv": HALO_VS, "pv": HALO_VS, "vflx": HALO_VV, "vtflx": HALO_VV, "vsflx": HALO_VV,
+    "cav": HALO_VV, "vb": HALO_VV, "pbv": HALO_VS, "pbv_p": HALO_VS, "vbflx": HALO_VV,
+    "vbflxs": HALO_VV, "vbflxs_p": HALO_VV, "vbcors_p": HALO_VV, "vmfltd": HALO_VV, "vmflsm": HALO_VV,
+    "vtfltd": HALO_VV, "vtflsm": HALO_VV, "vtflld": HALO_VV, "vsfltd": HALO_VV, "vsflsm": HALO_VV,
+    "vsflld": HALO_VV, "vmax": HALO_VS, "tauy": HALO_VV, "nslpy": HALO_VS, "pgfy": HALO_VV,
+    "pgfym": HALO_VV, "xiyp": HALO_VS, "xiym": HALO_VS, "dpvold": HALO_VS, "via": HALO_VV, "vib": HALO_VV,
+    "pgfyo": HALO_VV, "pgfym_o": HALO_VV, "xiyp_o": HALO_VS, "xiym_o": HALO_VS, "vbrhs": HALO_VV,
+    "mv_nonloc": HALO_VV, "vflux": HALO_VV, "vflux2": HALO_VV, "vflux3": HALO_VV,
+    # q-points
+    "scqx": HALO_QS, "scqy": HALO_QS, "scq2": HALO_QS, "scq2i": HALO_QS, "corioq": HALO_QS,
+    "pvtrop": HALO_QS,
+}
+
+
+def _mix(x: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser on uint64 arrays."""
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+class Synth:
+    """Synthetic state of one j-band [j0+1, j0+jj] of a (itdm, jtdm, kdm) grid."""
+
+    def __init__(self, itdm, jtdm, kdm, nreg, *, ntr=0, nbdy=4, j0=0, jj=None, seed=20240611,
+                 baclin=1800.0, batrop=36.0, land=True, metric="tripolar"):
+        self.itdm, self.jtdm, self.kdm, self.nreg, self.ntr, self.nb = itdm, jtdm, kdm, nreg, ntr, nbdy
+        self.j0 = j0
+        self.jj = jtdm if jj is None else jj
+        self.seed = seed
+        self.baclin, self.batrop = baclin, batrop
+        self.land, self.metric = land, metric
+        self.ldi, self.ldj = itdm + 2 * nbdy, self.jj + 2 * nbdy
+        self._fid = 0
+        with np.errstate(over="ignore"):
+            self._build_geometry()
+
+    @classmethod
+    def from_config(cls, name, **kw):
+        itdm, jtdm, kdm, nreg, baclin, batrop = CONFIGS[name]
+        return cls(itdm, jtdm, kdm, nreg, baclin=baclin, batrop=batrop, **kw)
+
+    # ---- helpers ---------------------------------------------------------------
+    def zeros(self, nlev=1, dtype=np.float64):
+        return np.zeros((nlev, self.ldj, self.ldi), dtype=dtype)
+
+    def interior(self, a):
+        nb = self.nb
+        return a[..., nb:nb + self.jj, nb:nb + self.itdm]
+
+    def _uniform(self, nlev, fid=None, rows=None):
+        """U[0,1) on the band interior, shape (nlev, jj, itdm), keyed on global indices."""
+        if fid is None:
+            self._fid += 1
+            fid = self._fid
+        jg = (np.arange(self.jj, dtype=np.uint64) + np.uint64(self.j0)) if rows is None else rows
+        ig = np.arange(self.itdm, dtype=np.uint64)
+        k = np.arange(nlev, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            key = (np.uint64(self.seed) * np.uint64(0x9E3779B97F4A7C15)
+                   + np.uint64(fid) * np.uint64(0xD1B54A32D192ED03))
+            x = (key + k[:, None, None] * np.uint64(0x8CB92BA72F3D8DD7)
+                 + jg[None, :, None] * np.uint64(0xA24BAED4963EE407)
+                 + ig[None, None, :] * np.uint64(0x9FB21C651E98DF25))
+            x = _mix(_mix(x))
+        return (x >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+
+    def _normal(self, nlev):
+        u1 = self._uniform(nlev)
+        u2 = self._uniform(nlev)
+        return np.sqrt(-2.0 * np.log(1.0 - u1)) * np.cos(2.0 * np.pi * u2)
+
+    def _put(self, a, vals):
+        self.interior(a)[...] = vals
+        return a
+
+    # ---- geometry (global 2-D, then sliced) ---------------------------------------
+    def _build_geometry(self):
+        itdm, jtdm, nreg = self.itdm, self.jtdm, self.nreg
+        ig = np.arange(1, itdm + 1)[None, :]
+        jg = np.arange(1, jtdm + 1)[:, None]
+        x = 2 * np.pi * (ig - 0.5) / itdm
+        y = (jg - 0.5) / jtdm
+        depth = 3200.0 + 1500.0 * np.sin(3 * x + 0.7) * np.cos(2 * np.pi * 1.5 * y) \
+            + 250.0 * np.cos(7 * x - 1.1) * np.sin(2 * np.pi * 4 * y + 0.3)
+        depth = np.clip(depth, 200.0, 5000.0)
+        if self.land:
+            blob = np.sin(2 * x + 0.4) * np.sin(2 * np.pi * 1.25 * y + 0.9) \
+                + 0.35 * np.sin(5 * x - 0.3) * np.cos(2 * np.pi * 3 * y)
+            depth = np.where(blob > 0.62, 0.0, depth)
+        # closed boundaries per region type (phy/mod_bigrid.F90:59-107)
+        if nreg in (0, 1, 2):
+            depth[0, :] = 0.0
+        if nreg in (0, 1):
+            depth[-1, :] = 0.0
+        if nreg in (0, 4):
+            depth[:, 0] = 0.0
+            depth[:, -1] = 0.0
+        if nreg == 2:
+            depth[-3:, :] = np.maximum(depth[-3:, :], 300.0)  # open water at the fold
+        for _ in range(50):
+            if nreg == 2:
+                depth[-1, :] = depth[-2, ::-1]  # p-grid fold: a(i,jj) = a(ii+1-i,jj-1)
+            d = self._pad_global(depth)
+            wet = d[1:-1, 1:-1] > 0
+            nzero = ((d[1:-1, :-2] <= 0).astype(int) + (d[1:-1, 2:] <= 0) + (d[:-2, 1:-1] <= 0)
+                     + (d[2:, 1:-1] <= 0))
+            bad = wet & (nzero >= 3)
+            if not bad.any():
+                break
+            depth[bad] = 0.0
+        else:
+            raise RuntimeError("synthetic bathymetry did not converge")
+        self.depth_global = depth
+
+        lat = -78.0 + 166.0 * y  # degrees, tripolar-like
+        gs = 1.0e5 * 360.0 / itdm
+        if self.metric == "uniform":
+            fx = np.ones_like(y)
+        else:
+            fx = np.maximum(0.2, np.cos(np.deg2rad(lat)))
+        wob = 1.0 + 0.05 * np.sin(2 * x + 0.2) * np.cos(2 * np.pi * y)
+        self._scpx_g = gs * fx * wob
+        self._scpy_g = gs * (1.0 + 0.03 * np.cos(x - 0.5) * np.sin(2 * np.pi * y + 0.1)) * np.ones_like(x)
+        self._lat_g = lat * np.ones_like(x)
+
+    def _pad_global(self, a):
+        """1-wide ring of a global 2-D array according to nreg (land where closed)."""
+        nreg = self.nreg
+        p = np.zeros((a.shape[0] + 2, a.shape[1] + 2), dtype=a.dtype)
+        p[1:-1, 1:-1] = a
+        if nreg in (1, 2, 3):
+            p[1:-1, 0] = a[:, -1]
+            p[1:-1, -1] = a[:, 0]
+        if nreg in (3, 4):
+            p[0, 1:-1] = a[-1, :]
+            p[-1, 1:-1] = a[0, :]
+        if nreg == 3:
+            p[0, 0], p[0, -1], p[-1, 0], p[-1, -1] = a[-1, -1], a[-1, 0], a[0, -1], a[0, 0]
+        if nreg == 2:
+            p[-1, 1:-1] = a[-3, ::-1]  # row jj+1 <- row jj-2 mirrored
+            p[-1, 0], p[-1, -1] = p[-1, -2], p[-1, 1]
+        return p
+
+    def _band(self, g2d):
+        return g2d[self.j0:self.j0 + self.jj, :]
+
+    # ---- fields ---------------------------------------------------------------------
+    def grid(self):
+        """Metric arrays of mod_grid (phy/mod_grid.F90:48-88) + depths."""
+        out = {}
+        scpx, scpy = self._band(self._scpx_g), self._band(self._scpy_g)
+        # staggered metrics: same smooth functions evaluated half a cell away
+        def shift_i(a):
+            return 0.5 * (a + np.roll(a, 1, axis=1))
+
+        def shift_j(gfun):
+            g = 0.5 * (gfun + np.vstack([gfun[:1], gfun[:-1]]))
+            return self._band(g)
+        scux, scuy = shift_i(scpx), shift_i(scpy)
+        scvx, scvy = shift_j(self._scpx_g), shift_j(self._scpy_g)
+        scqx, scqy = shift_i(scvx), shift_i(scvy)
+        vals = {
+            "depths": self._band(self.depth_global),
+            "scpx": scpx, "scpy": scpy, "scux": scux, "scuy": scuy, "scvx": scvx, "scvy": scvy,
+            "scqx": scqx, "scqy": scqy,
+            "scp2": scpx * scpy, "scu2": scux * scuy, "scv2": scvx * scvy, "scq2": scqx * scqy,
+        }
+        vals["scp2i"] = 1.0 / vals["scp2"]
+        vals["scq2i"] = 1.0 / vals["scq2"]
+        vals["scuxi"] = 1.0 / scux
+        vals["scuyi"] = 1.0 / scuy
+        vals["scvxi"] = 1.0 / scvx
+        vals["scvyi"] = 1.0 / scvy
+        omega2 = 2.0 * 7.2921e-5
+        latq = shift_i(shift_j(self._lat_g))
+        vals["corioq"] = omega2 * np.sin(np.deg2rad(latq))
+        vals["coriop"] = omega2 * np.sin(np.deg2rad(self._band(self._lat_g)))
+        for k, v in vals.items():
+            out[k] = self._put(self.zeros(), v)
+        return out
+
+    def masks_np(self):
+        """ip/iu/iv on the band interior (generator-side only; the product computes its
+        own masks with blomgpu_bigrid)."""
+        d = self._pad_global(self.depth_global)
+        ip = (d > 0).astype(np.int32)
+        iu = ip[1:-1, 1:-1] * ip[1:-1, :-2]
+        iv = ip[1:-1, 1:-1] * ip[:-2, 1:-1]
+        return self._band(ip[1:-1, 1:-1]), self._band(iu), self._band(iv)
+
+    def state(self, grid):
+        """Prognostic + auxiliary arrays for the whole hot path."""
+        kk, nb = self.kdm, self.nb
+        ipm, ium, ivm = self.masks_np()
+        depth = self._band(self.depth_global)
+        st = {}
+        # --- layer thickness: positive partition of pb with massless layers near the bottom
+        pb = depth * ONEM
+        w = 0.2 + self._uniform(kk)
+        kbot = np.floor(kk * (0.7 + 0.3 * self._uniform(1)[0])).astype(int)
+        kbot = np.clip(kbot, 1, kk)
+        kidx = np.arange(1, kk + 1)[:, None, None]
+        w = np.where(kidx > kbot[None], 0.0, w)
+        w[0] += 0.05
+        dpm = pb[None] * w / w.sum(axis=0, keepdims=True)
+        pert = 1.0 + 2.0e-3 * (self._uniform(kk) - 0.5)
+        dpn = dpm * pert
+        dpn *= np.where(pb > 0, pb / np.maximum(dpn.sum(axis=0), 1e-30), 0.0)[None]
+        dp = self.zeros(2 * kk)
+        self.interior(dp)[:kk] = dpm
+        self.interior(dp)[kk:] = dpn
+        st["dp"] = dp
+        # --- temperature / salinity / tracers
+        zfrac = (np.arange(kk) + 0.5)[:, None, None] / kk
+        for nm, base, amp in (("temp", 25.0 * (1 - zfrac) ** 1.5, 0.1), ("saln", 34.0 + 2.0 * zfrac, 0.05)):
+            a = self.zeros(2 * kk)
+            lvl = base + amp * (self._uniform(kk) - 0.5) + 0.5 * np.sin(
+                2 * np.pi * (np.arange(self.itdm)[None, None, :] / self.itdm))
+            self.interior(a)[:kk] = lvl * ipm
+            self.interior(a)[kk:] = (lvl + 0.02 * (self._uniform(kk) - 0.5)) * ipm
+            st[nm] = a
+        if self.ntr > 0:
+            trc = self.zeros(2 * kk * self.ntr)
+            for nt in range(self.ntr):
+                lvl = np.maximum(0.0, 1.0 + 0.5 * np.cos(3 * np.pi * zfrac) + 0.3 * (self._uniform(kk) - 0.5))
+                self.interior(trc)[nt * 2 * kk:nt * 2 * kk + kk] = lvl * ipm
+                self.interior(trc)[nt * 2 * kk + kk:(nt + 1) * 2 * kk] = lvl * ipm
+            st["trc"] = trc
+        st["sigma"] = self.zeros(2 * kk)
+        # --- velocities
+        for nm, msk in (("u", ium), ("v", ivm)):
+            a = self.zeros(2 * kk)
+            base = 0.05 * self._normal(kk)
+            self.interior(a)[:kk] = base * msk
+            self.interior(a)[kk:] = (base + 0.005 * self._normal(kk)) * msk
+            st[nm] = a
+        # --- flux accumulators (init_fluxes zeroes them each step)
+        for nm in ("uflx", "vflx", "utflx", "vtflx", "usflx", "vsflx"):
+            st[nm] = self.zeros(2 * kk)
+        for nm in ("umfltd", "vmfltd", "umflsm", "vmflsm", "utfltd", "vtfltd", "utflsm", "vtflsm",
+                   "utflld", "vtflld", "usfltd", "vsfltd", "usflsm", "vsflsm", "usflld", "vsflld"):
+            st[nm] = self.zeros(2 * kk)
+        # small eddy-induced mass fluxes so that advect's (umfltd+umflsm)/dpu term is exercised
+        scale = 1.0e-4 * ONEM * grid["scuy"][0, nb:nb + self.jj, nb:nb + self.itdm] * self.baclin
+        self.interior(st["umfltd"])[:] = np.tile(scale * self._normal(kk) * ium, (2, 1, 1))
+        scale = 1.0e-4 * ONEM * grid["scvx"][0, nb:nb + self.jj, nb:nb + self.itdm] * self.baclin
+        self.interior(st["vmfltd"])[:] = np.tile(scale * self._normal(kk) * ivm, (2, 1, 1))
+        st["cau"] = self.zeros(kk)
+        st["cav"] = self.zeros(kk)
+        for nm in ("p", "pu", "pv", "phi"):
+            st[nm] = self.zeros(kk + 1)
+        st["dpu"] = self.zeros(2 * kk)
+        st["dpv"] = self.zeros(2 * kk)
+        for nm in ("pb", "pbu", "pbv", "ub", "vb", "ubflxs_p", "vbflxs_p"):
+            st[nm] = self.zeros(2)
+        for nm in ("ubflxs", "vbflxs"):
+            st[nm] = self.zeros(3)
+        for nm in ("pb_p", "pbu_p", "pbv_p", "ubcors_p", "vbcors_p", "sealv", "umax", "vmax"):
+            st[nm] = self.zeros(1)
+        self.interior(st["pb"])[0] = dpm.sum(axis=0)
+        self.interior(st["pb"])[1] = dpn.sum(axis=0)
+        self.interior(st["pb_p"])[0] = dpn.sum(axis=0)
+        # predicted barotropic mass flux sums: small, masked
+        su = grid["scuy"][0, nb:nb + self.jj, nb:nb + self.itdm]
+        sv = grid["scvx"][0, nb:nb + self.jj, nb:nb + self.itdm]
+        self.interior(st["ubflxs_p"])[:] = (2.0e-3 * self._normal(2)) * su * pb[None] * ium / max(self.batrop, 1.0) * 0.1
+        self.interior(st["vbflxs_p"])[:] = (2.0e-3 * self._normal(2)) * sv * pb[None] * ivm / max(self.batrop, 1.0) * 0.1
+        # lateral diffusivities and friends
+        st["difint"] = self._put(self.zeros(kk), 100.0 + 1400.0 * self._uniform(kk))
+        st["difiso"] = self._put(self.zeros(kk), 100.0 + 1400.0 * self._uniform(kk))
+        st["difwgt"] = self._put(self.zeros(1), self._uniform(1))
+        st["nslpx"] = self._put(self.zeros(kk), 1.0e-4 * self._normal(kk) * ium)
+        st["nslpy"] = self._put(self.zeros(kk), 1.0e-4 * self._normal(kk) * ivm)
+        st["taux"] = self._put(self.zeros(1), 0.1 * self._normal(1) * ium)
+        st["tauy"] = self._put(self.zeros(1), 0.1 * self._normal(1) * ivm)
+        return st
+
+    def scalars(self, nstep=1):
+        """Step-control scalars (phy/mod_time.F90:121-142, mod_blom_step.F90:300)."""
+        lstep = 2 * int(np.ceil(0.5 * self.baclin / self.batrop))
+        dlt = self.baclin / lstep
+        return {"baclin": self.baclin, "batrop": self.batrop, "lstep": lstep, "dlt": dlt,
+                "delt1": 2.0 * self.baclin, "nstep": nstep}
+
+
+def fill_halos(backend, arrays: dict, nbdy=4, names=None):
+    """xctilr(nbdy,nbdy) of every registered array with its grid type.  `backend` is a
+    BlomGpu (product) or the test Oracle; arrays must already be registered."""
+    for name, a in arrays.items():
+        if names is not None and name not in names:
+            continue
+        it = ITYPE.get(name)
+        if it is None:
+            continue
+        lev = a.shape[-1] * a.shape[-2]
+        nlev = a.size // lev
+        backend.xctilr(name, 1, nlev, nbdy, nbdy, it)

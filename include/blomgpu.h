@@ -1,0 +1,119 @@
+/*
+ * blomgpu.h — C ABI of the B200-native BLOM horizontal stencil step.
+ *
+ * The reference (NorESMhub/BLOM) has no FFI / plugin layer: the hot-path
+ * routines are Fortran module procedures `X(m,n,mm,nn,k1m,k1n)` that work on
+ * module-global arrays (phy/mod_blom_step.F90:146-227).  The drop-in boundary
+ * is therefore (entry-point signature + global array layout); this header is
+ * what an ISO_C_BINDING shim binds (blom_b200/fortran/mod_blomgpu.F90, and the
+ * reference-side stub in INTEGRATION.md).
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; every function returns 0 on success,
+ *    non-zero on error (the Fortran shim then calls xchalt, matching the
+ *    reference's "print + xcstop/xchalt + stop" convention,
+ *    phy/mod_advect.F90:166-171).  blomgpu_last_error() gives the message.
+ *  - arrays are the reference's own: real(8) a(1-nbdy:idm+nbdy,
+ *    1-nbdy:jdm+nbdy [,nlev]), column-major, i fastest (phy/mod_xc.F90:45,
+ *    phy/mod_state.F90:34-86).  Host memory stays owned by the caller; the
+ *    library keeps a device-resident copy per registered name and only moves
+ *    data on explicit upload/download.
+ *  - time-level selectors (m,n,mm,nn,k1m,k1n) have the meaning of
+ *    phy/mod_blom_step.F90:89-94.
+ *  - no CPU fallback: every compute entry point runs CUDA kernels for sm_100a
+ *    and fails loudly without a device.
+ */
+#ifndef BLOMGPU_H
+#define BLOMGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- life cycle ------------------------------------------------------- */
+/* dims = {itdm,jtdm,kdm,idm,jdm,nbdy,ntr,nreg}  (dimensions.F, bld/blom_dimensions:150-183)
+ * tile = {i0,j0,ii,jj,rank,nranks}: this process' tile in the global grid
+ *        (phy/mod_xc.F90:1407-1442); j-band decomposition: i0=0, ii=itdm.
+ * device: CUDA device ordinal. */
+int blomgpu_init(const int dims[8], const int tile[6], int device);
+int blomgpu_finalize(void);
+const char* blomgpu_last_error(void);
+/* 1 if the library was built with -fmad=false (parity build), else 0 */
+int blomgpu_parity_build(void);
+
+/* ---- multi-GPU plumbing (replaces MPI in mod_xc, phy/mod_xc.F90:1332-1700)
+ * NCCL bootstrap: rank 0 fills a 128-byte unique id, the host side broadcasts
+ * it (any transport), every rank calls comm_init. */
+int blomgpu_comm_unique_id(char id[128]);
+int blomgpu_comm_init(const char id[128], int rank, int nranks);
+
+/* ---- array registration (module variables of mod_state, mod_grid, ...) -- */
+int blomgpu_register(const char* name, double* host, int nlev);
+int blomgpu_register_int(const char* name, int* host, int nlev);
+int blomgpu_upload(const char* name);      /* host -> device */
+int blomgpu_download(const char* name);    /* device -> host */
+int blomgpu_upload_all(void);
+int blomgpu_download_all(void);
+int blomgpu_sync(void);
+/* raw device pointer of a registered/owned array (for zero-copy interop) */
+int blomgpu_device_ptr(const char* name, void** dptr, int* nlev);
+
+/* ---- options: namelist strings / scalars (phy/mod_rdlim.F90:137,
+ *      phy/mod_time.F90:121-142).  Keys: advmth, pgfmth, mommth, bmcmth, eitmth,
+ *      ltedtp, ...; scalars: baclin, batrop, delt1, dlt, lstep, nstep, ... */
+int blomgpu_set_option(const char* key, const char* value);
+int blomgpu_set_scalar(const char* key, double value);
+
+/* ---- mod_xc (serial/MPI comm layer) ------------------------------------ */
+/* xctilr(a(1-nbdy,1-nbdy,koff),l1,ld,mh,nh,itype)  phy/mod_xc.F90:2342,4222 */
+int blomgpu_xctilr(const char* name, int koff, int l1, int ld, int mh, int nh, int itype);
+/* xcsum(sum,a(:,:,lev),mask) bit-reproducible order  phy/mod_xc.F90:2071,4116 */
+int blomgpu_xcsum(const char* name, int lev, const char* mask, double* sum);
+/* xcmax/xcmin over mask==1 interior points of level lev  phy/mod_xc.F90:1157,1285 */
+int blomgpu_xcmax(const char* name, int lev, const char* mask, double* out);
+int blomgpu_xcmin(const char* name, int lev, const char* mask, double* out);
+/* chksum(a,kcsd,itype,text) -> crc  phy/mod_checksum.F90:41-74, phy/mod_xc.F90:2195,4164 */
+int blomgpu_chksum(const char* name, int kcsd, int itype, uint32_t* crc);
+
+/* ---- setup ------------------------------------------------------------- */
+/* bigrid(depth): masks ip,iu,iv,iq (+nreg resolution)  phy/mod_bigrid.F90:44-317 */
+int blomgpu_bigrid(const char* depth_name);
+int blomgpu_nreg(void);
+/* init_cppm  phy/mod_cppm.F90:2504-2746 */
+int blomgpu_init_cppm(void);
+/* inieos  phy/mod_eos.F90:83-155 */
+int blomgpu_inieos(void);
+/* numerical_bounds  phy/mod_blom_init.F90:446-555 */
+int blomgpu_numerical_bounds(void);
+/* init_fluxes  phy/mod_state.F90:341-383 */
+int blomgpu_init_fluxes(int m, int n, int mm, int nn, int k1m, int k1n);
+
+/* ---- hot-path entry points, same argument lists as the reference -------- */
+int blomgpu_tmsmt1(int nn);                                   /* phy/mod_tmsmt.F90:209 */
+int blomgpu_eddtra(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_eddtra.F90:1808 */
+int blomgpu_advect(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_advect.F90:59 */
+int blomgpu_pbcor1(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_pbcor.F90:66 */
+int blomgpu_diffus(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_diffus.F90:41 */
+int blomgpu_pgforc(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_pgforc.F90:438 */
+int blomgpu_momtum(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_momtum.F90:215 */
+int blomgpu_barotp(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_barotp.F90:148 */
+int blomgpu_pbcor2(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_pbcor.F90:416 */
+int blomgpu_tmsmt2(int m, int mm, int nn, int k1m);           /* phy/mod_tmsmt.F90:281 */
+
+/* ---- instrumentation ---------------------------------------------------- */
+/* kernels launched by this library since the last reset */
+long blomgpu_launch_count(void);
+void blomgpu_launch_count_reset(void);
+/* per-routine device timers (CUDA events on the library stream), the analogue
+ * of mod_timing (phy/mod_timing.F90:107-494).  enable!=0 turns them on. */
+int blomgpu_timers_enable(int enable);
+/* writes up to cap entries; returns number of routines with samples */
+int blomgpu_timers_get(int cap, char names[][32], double* ms_total, long* calls, long* launches);
+void blomgpu_timers_reset(void);
+/* the CUDA stream (cudaStream_t) all kernels are launched on */
+void* blomgpu_stream(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLOMGPU_H */

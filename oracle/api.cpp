@@ -1,0 +1,114 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see core.hpp header).
+// Flat C entry points so tests / bench.py can drive the restatement with ctypes.
+#include "core.hpp"
+#include <cstdio>
+#include <cstring>
+
+namespace orc {
+void init_cppm();
+void cppm(int, int, int, int, int, int);
+void advect(int, int, int, int, int, int);
+const double* cppm_table(const char*, size_t*);
+const int* cppm_stencil(const char*, size_t*);
+void diffus(int, int, int, int, int, int);
+void tmsmt1(int);
+void tmsmt2(int, int, int, int);
+void pgforc(int, int, int, int, int, int);
+void inieos();
+void momtum(int, int, int, int, int, int);
+void barotp(int, int, int, int, int, int);
+void eddtra(int, int, int, int, int, int);
+void numerical_bounds();
+void pbcor1(int, int, int, int, int, int);
+void pbcor2(int, int, int, int, int, int);
+}
+
+static char g_err[1024] = "";
+
+#define GUARD(stmt)                                        \
+  try { stmt; return 0; }                                  \
+  catch (const std::exception& e) {                        \
+    std::snprintf(g_err, sizeof g_err, "%s", e.what());    \
+    return 1;                                              \
+  }
+
+extern "C" {
+
+const char* oracle_last_error() { return g_err; }
+
+// dims: itdm,jtdm,kdm,idm,jdm,nbdy,ntr,nreg  (single tile: idm=itdm, jdm=jtdm)
+int oracle_init(const int* dims) {
+  orc::Oracle& o = orc::O();
+  o = orc::Oracle();
+  orc::Dims& d = o.d;
+  d.itdm = dims[0]; d.jtdm = dims[1]; d.kdm = dims[2]; d.idm = dims[3]; d.jdm = dims[4];
+  d.nbdy = dims[5]; d.ntr = dims[6]; d.nreg = dims[7];
+  d.i0 = 0; d.j0 = 0; d.ii = d.idm; d.jj = d.jdm; d.kk = d.kdm;
+  d.ldi = d.idm + 2 * d.nbdy; d.ldj = d.jdm + 2 * d.nbdy;
+  d.lev = (size_t)d.ldi * d.ldj;
+  return 0;
+}
+int oracle_nreg() { return orc::O().d.nreg; }
+
+int oracle_register(const char* name, double* p, int nlev) {
+  orc::O().f[name] = orc::Field{p, nlev};
+  return 0;
+}
+int oracle_register_int(const char* name, int* p, int nlev) {
+  orc::O().fi[name] = orc::IField{p, nlev};
+  return 0;
+}
+int oracle_set_option(const char* k, const char* v) { orc::O().opt[k] = v; return 0; }
+int oracle_set_scalar(const char* k, double v) { orc::O().sc[k] = v; return 0; }
+
+// copy an oracle-owned int array (masks, span tables) out; returns length or -1
+long oracle_get_int(const char* name, int* out, long cap) {
+  auto& m = orc::O().owni;
+  auto it = m.find(name);
+  if (it == m.end()) return -1;
+  long n = (long)it->second.size();
+  if (out && cap >= n) std::memcpy(out, it->second.data(), sizeof(int) * n);
+  return n;
+}
+long oracle_get_owned(const char* name, double* out, long cap) {
+  auto& m = orc::O().own;
+  auto it = m.find(name);
+  if (it == m.end()) return -1;
+  long n = (long)it->second.size();
+  if (out && cap >= n) std::memcpy(out, it->second.data(), sizeof(double) * n);
+  return n;
+}
+long oracle_cppm_table(const char* name, double* out, long cap) {
+  size_t n; const double* p = orc::cppm_table(name, &n);
+  if (!p) return -1;
+  if (out && cap >= (long)n) std::memcpy(out, p, 8 * n);
+  return (long)n;
+}
+long oracle_cppm_stencil(const char* name, int* out, long cap) {
+  size_t n; const int* p = orc::cppm_stencil(name, &n);
+  if (!p) return -1;
+  if (out && cap >= (long)n) std::memcpy(out, p, 4 * n);
+  return (long)n;
+}
+
+int oracle_xctilr(const char* name, int l1, int ld, int mh, int nh, int itype) {
+  GUARD(orc::xctilr(orc::O().a3(name), l1, ld, mh, nh, itype))
+}
+// xctilr on a sub-view starting at level `koff` (Fortran a(1-nbdy,1-nbdy,koff))
+int oracle_xctilr_at(const char* name, int koff, int l1, int ld, int mh, int nh, int itype) {
+  GUARD(orc::xctilr(orc::O().a3(name).from(koff), l1, ld, mh, nh, itype))
+}
+int oracle_xcsum(const char* name, int lev, const char* mask, double* out) {
+  GUARD(*out = orc::xcsum(orc::O().a3(name).level(lev), orc::O().i2(mask)))
+}
+int oracle_xccrc(const char* name, int ld, const char* mask, uint32_t* out) {
+  GUARD(*out = orc::xccrc(orc::O().a3(name), ld, orc::O().i2(mask)))
+}
+uint32_t oracle_crc32(const void* p, long n, uint32_t init) { return orc::crc32_bytes(p, (size_t)n, init); }
+int oracle_bigrid(const char* depth) { GUARD(orc::bigrid(orc::O().a2(depth))) }
+
+int oracle_init_cppm() { GUARD(orc::init_cppm()) }
+int oracle_advect(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::advect(m, n, mm, nn, k1m, k1n)) }
+int oracle_cppm(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::cppm(m, n, mm, nn, k1m, k1n)) }
+
+}  // extern "C"

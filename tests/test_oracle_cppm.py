@@ -1,0 +1,89 @@
+"""Pins the oracle's CPPM/advect restatement on CPU through properties the scheme
+guarantees (the reference ships no golden outputs):
+ - mass, heat, salt and tracer inventories conserved to round-off on closed and
+   periodic domains (flux form);
+ - compatibility: a spatially uniform tracer stays uniform to round-off;
+ - thickness stays non-negative, tracers nt>=2 stay non-negative;
+ - tripolar fold: conserved to round-off only with cppm_fold_fix=1 (the reference
+   swaps hel/her on half of row jj only, phy/mod_cppm.F90:1690 — reproduced by default)."""
+import numpy as np
+import pytest
+
+from util import Case, interior
+
+
+def inventories(a, c, nn, rows=slice(None)):
+    kk = c.dims[2]
+    scp2 = interior(a["scp2"][0])[rows]
+    dp = interior(a["dp"][nn:nn + kk])[:, rows]
+    out = {"mass": (dp * scp2).sum()}
+    out["heat"] = (dp * interior(a["temp"][nn:nn + kk])[:, rows] * scp2).sum()
+    out["salt"] = (dp * interior(a["saln"][nn:nn + kk])[:, rows] * scp2).sum()
+    if "trc" in a:
+        out["trc"] = (dp * interior(a["trc"][nn:nn + kk])[:, rows] * scp2).sum()
+    return out
+
+
+@pytest.mark.parametrize("cfg", ["tiny0", "tiny1", "tiny3", "tiny4"])
+@pytest.mark.parametrize("nstep", [1, 2])
+def test_conservation_roundoff(cfg, nstep):
+    c = Case(cfg, ntr=1, nstep=nstep)
+    o = c.new_oracle(); o.init_cppm()
+    m, n, mm, nn, k1m, k1n = c.levels
+    inv0 = inventories(o.arrays, c, nn)
+    o.advect(*c.levels)
+    inv1 = inventories(o.arrays, c, nn)
+    for k in inv0:
+        assert abs(inv1[k] - inv0[k]) <= 2e-14 * abs(inv0[k]), (k, inv0[k], inv1[k])
+    assert o.arrays["dp"].min() >= 0.0
+    assert interior(o.arrays["saln"]).min() >= 0.0 and interior(o.arrays["trc"]).min() >= 0.0
+    # dp actually moved
+    assert np.abs(o.arrays["dp"][nn:nn + c.dims[2]] - c.state["dp"][nn:nn + c.dims[2]]).max() > 1.0
+
+
+@pytest.mark.parametrize("nstep", [1, 2])
+def test_fold_conservation(nstep):
+    rows = slice(0, -1)  # row jj duplicates row jj-1 on the tripolar grid
+    res = {}
+    for fix in ("0", "1"):
+        c = Case("tiny2", ntr=1, nstep=nstep)
+        o = c.new_oracle(); o.set_option("cppm_fold_fix", fix); o.init_cppm()
+        nn = c.levels[3]
+        inv0 = inventories(o.arrays, c, nn, rows)
+        o.advect(*c.levels)
+        inv1 = inventories(o.arrays, c, nn, rows)
+        res[fix] = {k: abs(inv1[k] - inv0[k]) / abs(inv0[k]) for k in inv0}
+    # with the whole mirrored row swapped, thickness fluxes cancel across the fold exactly;
+    # tracer fluxes only nearly: the reference mirrors hevc*/tags but not tmc0/tmcl/tmcr
+    # (phy/mod_cppm.F90:2650-2720), so tracer edge weights right of the fold centre are inexact
+    assert res["1"]["mass"] <= 2e-15
+    assert max(res["1"].values()) <= 1e-10
+    assert 1e-12 < res["0"]["mass"] < 1e-5  # the reference quirk is visible but small
+
+
+@pytest.mark.parametrize("cfg", ["tiny1", "tiny2", "tiny3"])
+def test_uniform_tracer_stays_uniform(cfg):
+    c = Case(cfg, ntr=1, nstep=1)
+    kk = c.dims[2]
+    c.state["trc"][:] = 3.25
+    c.state["temp"][:] = 7.5
+    o = c.new_oracle(); o.init_cppm()
+    nn = c.levels[3]
+    o.advect(*c.levels)
+    ip = interior(c.masks["ip"]) == 1
+    t = interior(o.arrays["temp"][nn:nn + kk])[:, ip]
+    tr = interior(o.arrays["trc"][nn:nn + kk])[:, ip]
+    assert np.abs(t - 7.5).max() <= 1e-12
+    assert np.abs(tr - 3.25).max() <= 1e-12
+
+
+def test_zero_velocity_is_identity():
+    c = Case("tiny1", ntr=0, nstep=1)
+    for nm in ("u", "v", "umfltd", "vmfltd", "ubflxs_p", "vbflxs_p"):
+        c.state[nm][:] = 0.0
+    o = c.new_oracle(); o.init_cppm()
+    kk = c.dims[2]; nn = c.levels[3]
+    o.advect(*c.levels)
+    d0 = interior(c.state["dp"][nn:nn + kk]); d1 = interior(o.arrays["dp"][nn:nn + kk])
+    assert np.abs(d1 - d0).max() <= 1e-9  # dpeps add/subtract only
+    assert np.abs(interior(o.arrays["uflx"])).max() == 0.0

@@ -1,0 +1,137 @@
+"""Shared test scaffolding: builds one synthetic case and hands identical copies
+to the oracle (CPU restatement, test infrastructure) and to the CUDA library."""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+from blom_b200 import synth  # noqa: E402
+from blom_b200.lib import BlomGpu, time_levels  # noqa: E402
+from oracle.oracle import Oracle  # noqa: E402
+
+
+class Case:
+    """Synthetic case prepared with the oracle's xctilr/bigrid (CPU)."""
+
+    def __init__(self, config="tiny2", ntr=0, nstep=1, land=True, metric="tripolar", seed=20240611):
+        itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS[config]
+        self.config = config
+        self.dims = (itdm, jtdm, kdm, nreg)
+        self.ntr, self.nstep = ntr, nstep
+        self.syn = synth.Synth(itdm, jtdm, kdm, nreg, ntr=ntr, baclin=baclin, batrop=batrop, land=land,
+                               metric=metric, seed=seed)
+        self.grid = self.syn.grid()
+        self.state = self.syn.state(self.grid)
+        self.scalars = self.syn.scalars(nstep)
+        self.levels = time_levels(nstep, kdm)
+        prep = self.new_oracle(setup=False)
+        synth.fill_halos(prep, {**self.grid, **self.state})
+        prep.bigrid("depths")
+        self.nreg = prep.nreg
+        self.masks = {k: prep.get_int(k).reshape(self.syn.ldj, self.syn.ldi).copy() for k in ("ip", "iu", "iv", "iq")}
+        derive(self, prep)
+
+    def arrays(self):
+        return {k: v.copy() for k, v in {**self.grid, **self.state}.items()}
+
+    def new_oracle(self, setup=True):
+        itdm, jtdm, kdm, nreg = self.dims
+        o = Oracle(itdm, jtdm, kdm, nreg, ntr=self.ntr)
+        arrs = self.arrays() if setup else {**self.grid, **self.state}
+        o.register_all(arrs)
+        o.set_scalars(**self.scalars)
+        if setup:
+            o.bigrid("depths")
+        return o
+
+    def new_gpu(self, parity=True, **kw):
+        itdm, jtdm, kdm, nreg = self.dims
+        g = BlomGpu(itdm, jtdm, kdm, nreg, ntr=self.ntr, parity=parity, **kw)
+        g.register_all(self.arrays())
+        g.set_scalars(**self.scalars)
+        g.bigrid("depths")
+        return g
+
+
+def derive(case: Case, prep: Oracle):
+    """Fields other routines of the model would have produced before the hot path runs:
+    p from dp(kn), pbu/pbv, dpu/dpv (phy/mod_pgforc.F90:452-484), umax/vmax
+    (phy/mod_blom_init.F90:514-523).  numpy on whole arrays, then halos refreshed."""
+    st, gr = case.state, case.grid
+    kk = case.dims[2]
+    m, n, mm, nn, k1m, k1n = case.levels
+    ip = case.masks["ip"]
+    iu, iv = case.masks["iu"], case.masks["iv"]
+    dp, p = st["dp"], st["p"]
+    p[0] = 0.0
+    for k in range(kk):
+        p[k + 1] = p[k] + dp[k + nn]
+    pb = st["pb"]
+    pb[n - 1] = p[kk]
+    pb[m - 1] = dp[mm:mm + kk].sum(axis=0)
+    st["pb_p"][0] = pb[n - 1]
+    for lvl in range(2):
+        st["pbu"][lvl][:, 1:] = np.minimum(pb[lvl][:, 1:], pb[lvl][:, :-1])
+        st["pbv"][lvl][1:, :] = np.minimum(pb[lvl][1:, :], pb[lvl][:-1, :])
+    st["pbu_p"][0] = st["pbu"][n - 1]
+    st["pbv_p"][0] = st["pbv"][n - 1]
+    for (koff, pl) in ((nn, p),):
+        for k in range(kk):
+            q1 = np.minimum(st["pbu"][n - 1][:, 1:], 0.5 * (pl[k + 1][:, 1:] + pl[k + 1][:, :-1]))
+            q0 = np.minimum(st["pbu"][n - 1][:, 1:], 0.5 * (pl[k][:, 1:] + pl[k][:, :-1]))
+            st["dpu"][k + koff][:, 1:] = np.maximum(0.0, q1 - q0) * iu[:, 1:]
+            q1 = np.minimum(st["pbv"][n - 1][1:, :], 0.5 * (pl[k + 1][1:, :] + pl[k + 1][:-1, :]))
+            q0 = np.minimum(st["pbv"][n - 1][1:, :], 0.5 * (pl[k][1:, :] + pl[k][:-1, :]))
+            st["dpv"][k + koff][1:, :] = np.maximum(0.0, q1 - q0) * iv[1:, :]
+    # level m thicknesses at u/v points from dp(km)
+    pm = np.zeros_like(p)
+    for k in range(kk):
+        pm[k + 1] = pm[k] + dp[k + mm]
+    for k in range(kk):
+        q1 = np.minimum(st["pbu"][m - 1][:, 1:], 0.5 * (pm[k + 1][:, 1:] + pm[k + 1][:, :-1]))
+        q0 = np.minimum(st["pbu"][m - 1][:, 1:], 0.5 * (pm[k][:, 1:] + pm[k][:, :-1]))
+        st["dpu"][k + mm][:, 1:] = np.maximum(0.0, q1 - q0) * iu[:, 1:]
+        q1 = np.minimum(st["pbv"][m - 1][1:, :], 0.5 * (pm[k + 1][1:, :] + pm[k + 1][:-1, :]))
+        q0 = np.minimum(st["pbv"][m - 1][1:, :], 0.5 * (pm[k][1:, :] + pm[k][:-1, :]))
+        st["dpv"][k + mm][1:, :] = np.maximum(0.0, q1 - q0) * iv[1:, :]
+    baclin = case.scalars["baclin"]
+    scp2, scuy, scvx = gr["scp2"][0], gr["scuy"][0], gr["scvx"][0]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        st["umax"][0][:, 1:] = 0.9 * 0.125 * np.minimum(scp2[:, 1:], scp2[:, :-1]) / (scuy[:, 1:] * baclin)
+        st["vmax"][0][1:, :] = 0.9 * 0.125 * np.minimum(scp2[1:, :], scp2[:-1, :]) / (scvx[1:, :] * baclin)
+    for nm in ("umax", "vmax"):
+        st[nm][~np.isfinite(st[nm])] = 0.0
+    synth.fill_halos(prep, {**gr, **st}, names={"p", "pb", "pb_p", "pbu", "pbv", "pbu_p", "pbv_p", "dpu",
+                                                "dpv", "umax", "vmax"})
+    # land points carry zero bottom pressure; keep divisions finite like the model does
+    for nm in ("pbu", "pbv"):
+        a = st[nm]
+        a[a <= 0.0] = 0.0
+
+
+def interior(a, nb=4, halo=0):
+    """View of the interior (+`halo` rings) of a (nlev, ldj, ldi) array."""
+    s = nb - halo
+    return a[..., s:a.shape[-2] - s, s:a.shape[-1] - s]
+
+
+def max_rel_err(a, b, floor=1e-300):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = max(np.max(np.abs(b)), floor)
+    return float(np.max(np.abs(a - b)) / scale)
+
+
+def ulp_diff(a, b):
+    """max distance in units of last place between two float64 arrays."""
+    ai = np.asarray(a, dtype=np.float64).view(np.int64).astype(np.int64)
+    bi = np.asarray(b, dtype=np.float64).view(np.int64).astype(np.int64)
+    ai = np.where(ai < 0, np.int64(-2 ** 63) - ai, ai)
+    bi = np.where(bi < 0, np.int64(-2 ** 63) - bi, bi)
+    return int(np.max(np.abs(ai - bi))) if ai.size else 0
