@@ -1,0 +1,384 @@
+// Split-explicit barotropic subcycle (phy/mod_barotp.F90:148-1003).
+//
+// Five blocks of lstep/2 forward-backward substeps; each substep is continuity
+// followed by the two momentum equations, u before v on odd substeps and v
+// before u on even ones (the second equation uses the first one's new flux).
+// Halos of the three subcycled fields are refreshed once per two substeps with
+// a 2(3)-wide halo exactly like the reference (:395-397), so the odd substep
+// runs on the widened ranges and the even one on the interior.
+//
+// Kernel structure: each phase is one launch over the 2-D domain with i across
+// lanes; the many read-only coefficient arrays stay L2-resident across the
+// substeps at 1 degree (working set ~58 MB < 126 MB L2).  All pointers travel in
+// one by-value parameter block.
+#include "common.cuh"
+
+namespace blom {
+
+namespace {
+
+struct BtP {
+  double *pb_ml, *pb_nl, *ub_ml, *ub_nl, *vb_ml, *vb_nl;
+  const double *scp2i, *scvxi, *scuyi, *scuxi, *scvyi, *scuy, *scvx;
+  const double *pvo, *pvm, *pvn;
+  const double *pgfxm_o, *xixp_o, *xixm_o, *pgfxm_m, *xixp_m, *xixm_m, *pgfxm_n, *xixp_n, *xixm_n;
+  const double *pgfym_o, *xiyp_o, *xiym_o, *pgfym_m, *xiyp_m, *xiym_m, *pgfym_n, *xiyp_n, *xiym_n;
+  const double *utotn, *vtotn, *uglue, *vglue, *umaxb, *uminb, *vmaxb, *vminb;
+  double *ubflxs_t, *ubcors_t, *vbflxs_t, *vbcors_t;
+  const int *ip, *iu, *iv;
+  double wo, wm, wn, dlt;
+  int enscon;
+};
+
+constexpr double WBARO = .125;  // phy/mod_tmsmt.F90:51
+
+// :177-224  clamp fluxes and coastal damping coefficients
+__global__ void bt_prologue(Geom g, int m, int nn, double cwbdts, double cwbdls, const int* __restrict__ iu,
+                            const int* __restrict__ iv, const double* __restrict__ u,
+                            const double* __restrict__ v, const double* __restrict__ pbu,
+                            const double* __restrict__ pbv, const double* __restrict__ umax,
+                            const double* __restrict__ vmax, const double* __restrict__ scuy,
+                            const double* __restrict__ scvx, double* __restrict__ umaxb,
+                            double* __restrict__ uminb, double* __restrict__ uglue, double* __restrict__ vmaxb,
+                            double* __restrict__ vminb, double* __restrict__ vglue) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j), x2 = x + (long)(m - 1) * g.lev;
+  if (iu[x] == 1) {
+    double mx = 0., mn = 0.;
+    for (int k = 1; k <= g.kdm; ++k) {
+      const double uk = u[x + (long)(k + nn - 1) * g.lev];
+      mx = fmax(mx, uk); mn = fmin(mn, uk);
+    }
+    uglue[x] = cwbdts * exp(1. - pbu[x2] / (cwbdls * onem));
+    umaxb[x] = (umax[x] - mx) * pbu[x2] * scuy[x];
+    uminb[x] = (umax[x] + mn) * pbu[x2] * scuy[x];
+  }
+  if (iv[x] == 1) {
+    double mx = 0., mn = 0.;
+    for (int k = 1; k <= g.kdm; ++k) {
+      const double vk = v[x + (long)(k + nn - 1) * g.lev];
+      mx = fmax(mx, vk); mn = fmin(mn, vk);
+    }
+    vglue[x] = cwbdts * exp(1. - pbv[x2] / (cwbdls * onem));
+    vmaxb[x] = (vmax[x] - mx) * pbv[x2] * scvx[x];
+    vminb[x] = (vmax[x] + mn) * pbv[x2] * scvx[x];
+  }
+}
+
+// :230-269  pvtrop_o <- pvtrop(n); new pvtrop(n).  Gather form of the reference's
+// three scatter loops: the last writer in the reference's sequential order wins.
+__global__ void bt_pvtrop(Geom g, const int* __restrict__ iu, const int* __restrict__ iv,
+                          const int* __restrict__ iq, const double* __restrict__ corioq,
+                          const double* __restrict__ pb_p, double* __restrict__ pvn, double* __restrict__ pvo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..ii+1
+  const int j = (int)blockIdx.y - 2;                   // -2..jj+3
+  if (i > g.ii + 1) return;
+  const long x = ix2(g, i, j), s = g.ldi;
+  double val = pvn[x];
+  pvo[x] = val;
+  const double cq = corioq[x];
+  const bool iin = i >= 1 && i <= g.ii;
+  if (iin && j - 1 >= 0 && j - 1 <= g.jj && iu[x - s] == 1) val = cq * (2. / (pb_p[x - s] + pb_p[x - s - 1]));
+  if (iin && j >= 0 && j <= g.jj && iu[x] == 1) val = cq * (2. / (pb_p[x] + pb_p[x - 1]));
+  if (j >= 1 && j <= g.jj) {
+    if (i - 1 >= 0 && i - 1 <= g.ii && iv[x - 1] == 1) val = cq * (2. / (pb_p[x - 1] + pb_p[x - 1 - s]));
+    if (i <= g.ii && iv[x] == 1) val = cq * (2. / (pb_p[x] + pb_p[x - s]));
+    if (iin && iq[x] == 1) val = cq * 4. / (pb_p[x] + pb_p[x - 1] + pb_p[x - s] + pb_p[x - s - 1]);
+  }
+  pvn[x] = val;
+}
+
+// :290-319 arctic switches in the halo region next to the fold
+__global__ void bt_arctic_swap(Geom g, double* umaxb, double* uminb, double* xixp, double* xixm, double* vmaxb,
+                               double* vminb, double* xiyp, double* xiym) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..ii+1
+  const int j = g.jj + blockIdx.y;                     // jj..jj+2
+  if (i > g.ii + 1) return;
+  const long x = ix2(g, i, j);
+  double q = umaxb[x]; umaxb[x] = uminb[x]; uminb[x] = q;
+  q = xixp[x]; xixp[x] = xixm[x]; xixm[x] = q;
+  if (j > g.jj || i >= max(0, g.itdm / 2 - g.i0 + 1)) {
+    q = vmaxb[x]; vmaxb[x] = vminb[x]; vminb[x] = q;
+    q = xiyp[x]; xiyp[x] = xiym[x]; xiym[x] = q;
+  }
+}
+
+__global__ void bt_init_block1(Geom g, const double* __restrict__ pb_mn, const double* __restrict__ ub_mn,
+                               const double* __restrict__ vb_mn, double* pb_t, double* ub_t, double* vb_t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j);
+  pb_t[x] = pb_mn[x]; pb_t[x + g.lev] = pb_mn[x + g.lev];
+  ub_t[x] = ub_mn[x]; ub_t[x + g.lev] = ub_mn[x + g.lev];
+  vb_t[x] = vb_mn[x]; vb_t[x + g.lev] = vb_mn[x + g.lev];
+}
+
+__global__ void bt_zero_acc(Geom g, BtP P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..ii+1
+  const int j = (int)blockIdx.y - 1;                   // -1..jj+2
+  if (i > g.ii + 1) return;
+  const long x = ix2(g, i, j);
+  if (P.iu[x] == 1) { P.ubflxs_t[x] = 0.; P.ubcors_t[x] = 0.; }
+  if (j >= 0 && i <= g.ii && P.iv[x] == 1) { P.vbflxs_t[x] = 0.; P.vbcors_t[x] = 0.; }
+}
+
+__global__ void bt_continuity(Geom g, BtP P, int i0, int i1, int j0, int j1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + i0, j = blockIdx.y + j0;
+  if (i > i1 || j > j1) return;
+  const long x = ix2(g, i, j);
+  if (P.ip[x] != 1) return;
+  P.pb_nl[x] = (1. - WBARO) * P.pb_ml[x] + WBARO * P.pb_nl[x] -
+               (1. + WBARO) * P.dlt * (P.ub_ml[x + 1] - P.ub_ml[x] + P.vb_ml[x + g.ldi] - P.vb_ml[x]) * P.scp2i[x];
+}
+
+// vb: level of vbflx_t entering the Coriolis term (ml on odd, nl on even substeps)
+__global__ void bt_ueq(Geom g, BtP P, const double* __restrict__ vb, int i0, int i1, int j0, int j1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + i0, j = blockIdx.y + j0;
+  if (i > i1 || j > j1) return;
+  const long x = ix2(g, i, j), s = g.ldi;
+  if (P.iu[x] != 1) return;
+  const double uml = P.ub_ml[x], unl = P.ub_nl[x];
+  P.ubflxs_t[x] = P.ubflxs_t[x] - WBARO * unl + (1. + WBARO) * uml;
+  double q;
+  if (P.enscon)
+    q = (vb[x] * P.scvxi[x] + vb[x + s] * P.scvxi[x + s] + vb[x - 1] * P.scvxi[x - 1] +
+         vb[x - 1 + s] * P.scvxi[x - 1 + s]) *
+        (P.wo * (P.pvo[x] + P.pvo[x + s]) + P.wm * (P.pvm[x] + P.pvm[x + s]) + P.wn * (P.pvn[x] + P.pvn[x + s])) * .125;
+  else
+    q = .25 * ((vb[x] * P.scvxi[x] + vb[x - 1] * P.scvxi[x - 1]) * (P.wo * P.pvo[x] + P.wm * P.pvm[x] + P.wn * P.pvn[x]) +
+               (vb[x + s] * P.scvxi[x + s] + vb[x - 1 + s] * P.scvxi[x - 1 + s]) *
+                   (P.wo * P.pvo[x + s] + P.wm * P.pvm[x + s] + P.wn * P.pvn[x + s]));
+  P.ubcors_t[x] = P.ubcors_t[x] + q;
+  const double pbc = P.pb_nl[x], pbw = P.pb_nl[x - 1];
+  const double utndcy = q + (P.wo * (P.pgfxm_o[x] - (P.xixp_o[x] * pbc - P.xixm_o[x] * pbw)) +
+                             P.wm * (P.pgfxm_m[x] - (P.xixp_m[x] * pbc - P.xixm_m[x] * pbw)) +
+                             P.wn * (P.pgfxm_n[x] - (P.xixp_n[x] * pbc - P.xixm_n[x] * pbw))) * P.scuxi[x];
+  double un = (1. - WBARO) * uml + WBARO * unl +
+              (1. + WBARO) * P.dlt * ((utndcy + P.utotn[x]) * P.scuy[x] * fmin(pbw, pbc) - P.uglue[x] * uml);
+  P.ub_nl[x] = fmax(-P.uminb[x], fmin(P.umaxb[x], un));
+}
+
+__global__ void bt_veq(Geom g, BtP P, const double* __restrict__ ub, int i0, int i1, int j0, int j1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + i0, j = blockIdx.y + j0;
+  if (i > i1 || j > j1) return;
+  const long x = ix2(g, i, j), s = g.ldi;
+  if (P.iv[x] != 1) return;
+  const double vml = P.vb_ml[x], vnl = P.vb_nl[x];
+  P.vbflxs_t[x] = P.vbflxs_t[x] - WBARO * vnl + (1. + WBARO) * vml;
+  double q;
+  if (P.enscon)
+    q = -(ub[x] * P.scuyi[x] + ub[x + 1] * P.scuyi[x + 1] + ub[x - s] * P.scuyi[x - s] +
+          ub[x + 1 - s] * P.scuyi[x + 1 - s]) *
+        (P.wo * (P.pvo[x] + P.pvo[x + 1]) + P.wm * (P.pvm[x] + P.pvm[x + 1]) + P.wn * (P.pvn[x] + P.pvn[x + 1])) * .125;
+  else
+    q = -.25 * ((ub[x] * P.scuyi[x] + ub[x - s] * P.scuyi[x - s]) * (P.wo * P.pvo[x] + P.wm * P.pvm[x] + P.wn * P.pvn[x]) +
+                (ub[x + 1] * P.scuyi[x + 1] + ub[x + 1 - s] * P.scuyi[x + 1 - s]) *
+                    (P.wo * P.pvo[x + 1] + P.wm * P.pvm[x + 1] + P.wn * P.pvn[x + 1]));
+  P.vbcors_t[x] = P.vbcors_t[x] + q;
+  const double pbc = P.pb_nl[x], pbs = P.pb_nl[x - s];
+  const double vtndcy = q + (P.wo * (P.pgfym_o[x] - (P.xiyp_o[x] * pbc - P.xiym_o[x] * pbs)) +
+                             P.wm * (P.pgfym_m[x] - (P.xiyp_m[x] * pbc - P.xiym_m[x] * pbs)) +
+                             P.wn * (P.pgfym_n[x] - (P.xiyp_n[x] * pbc - P.xiym_n[x] * pbs))) * P.scvyi[x];
+  double vn = (1. - WBARO) * vml + WBARO * vnl +
+              (1. + WBARO) * P.dlt * ((vtndcy + P.vtotn[x]) * P.scvx[x] * fmin(pbs, pbc) - P.vglue[x] * vml);
+  P.vb_nl[x] = fmax(-P.vminb[x], fmin(P.vmaxb[x], vn));
+}
+
+struct HvP {
+  double *pb, *pbu, *pbv, *ub, *vb, *ubflx, *vbflx, *ubflxs, *vbflxs, *ubflxs_p, *vbflxs_p;
+  double *pb_p, *pbu_p, *pbv_p, *ubcors_p, *vbcors_p, *pb_mn, *ub_mn, *vb_mn;
+  const double *scuy, *scvx;
+};
+
+// :847-977
+__global__ void bt_harvest(Geom g, BtP P, HvP H, int nb, int m, int n, int ml, int nl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j), s = g.ldi, L = g.lev;
+  const long xm = x + (long)(m - 1) * L, xn = x + (long)(n - 1) * L, x3 = x + 2 * L;
+  // after the last swap P.pb_ml is level `ml`
+  const bool isp = P.ip[x] == 1, isu = P.iu[x] == 1, isv = P.iv[x] == 1;
+  const double pbc = P.pb_ml[x];
+  if (nb == 1 || nb == 3) {
+    const long xl = nb == 1 ? xm : xn;
+    if (isp) H.pb[xl] = pbc;
+    if (isu) {
+      const double pu = fmin(pbc, P.pb_ml[x - 1]);
+      H.pbu[xl] = pu;
+      const double f = P.ub_ml[x];
+      H.ubflx[xl] = f;
+      H.ub[xl] = f / (pu * H.scuy[x]);
+      if (nb == 1) {
+        H.ubflxs[xn] = H.ubflxs[xn] + P.ubflxs_t[x];
+        H.ubflxs[xm] = H.ubflxs[x3] + P.ubflxs_t[x];
+      } else {
+        H.ubflxs_p[xm] = H.ubflxs[xm] + P.ubflxs_t[x];
+        H.ubflxs_p[xn] = H.ubflxs_p[xn] + P.ubflxs_t[x];
+        H.ubcors_p[x] = H.ubcors_p[x] + P.ubcors_t[x];
+      }
+    }
+    if (isv) {
+      const double pv = fmin(pbc, P.pb_ml[x - s]);
+      H.pbv[xl] = pv;
+      const double f = P.vb_ml[x];
+      H.vbflx[xl] = f;
+      H.vb[xl] = f / (pv * H.scvx[x]);
+      if (nb == 1) {
+        H.vbflxs[xn] = H.vbflxs[xn] + P.vbflxs_t[x];
+        H.vbflxs[xm] = H.vbflxs[x3] + P.vbflxs_t[x];
+      } else {
+        H.vbflxs_p[xm] = H.vbflxs[xm] + P.vbflxs_t[x];
+        H.vbflxs_p[xn] = H.vbflxs_p[xn] + P.vbflxs_t[x];
+        H.vbcors_p[x] = H.vbcors_p[x] + P.vbcors_t[x];
+      }
+    }
+  } else if (nb == 2) {
+    const long xml = x + (long)(ml - 1) * L, xnl = x + (long)(nl - 1) * L;
+    if (isp) { H.pb_mn[xml] = P.pb_ml[x]; H.pb_mn[xnl] = P.pb_nl[x]; }
+    if (isu) {
+      H.ub_mn[xml] = P.ub_ml[x]; H.ub_mn[xnl] = P.ub_nl[x];
+      H.ubflxs[xm] = H.ubflxs[xm] + P.ubflxs_t[x];
+      H.ubflxs[x3] = P.ubflxs_t[x];
+      H.ubflxs_p[xn] = P.ubflxs_t[x];
+      H.ubcors_p[x] = P.ubcors_t[x];
+    }
+    if (isv) {
+      H.vb_mn[xml] = P.vb_ml[x]; H.vb_mn[xnl] = P.vb_nl[x];
+      H.vbflxs[xm] = H.vbflxs[xm] + P.vbflxs_t[x];
+      H.vbflxs[x3] = P.vbflxs_t[x];
+      H.vbflxs_p[xn] = P.vbflxs_t[x];
+      H.vbcors_p[x] = P.vbcors_t[x];
+    }
+  } else {
+    if (nb == 5 && isp) H.pb_p[x] = pbc;
+    if (isu) {
+      if (nb == 5) H.pbu_p[x] = fmin(pbc, P.pb_ml[x - 1]);
+      H.ubflxs_p[xn] = H.ubflxs_p[xn] + P.ubflxs_t[x];
+      H.ubcors_p[x] = H.ubcors_p[x] + P.ubcors_t[x];
+    }
+    if (isv) {
+      if (nb == 5) H.pbv_p[x] = fmin(pbc, P.pb_ml[x - s]);
+      H.vbflxs_p[xn] = H.vbflxs_p[xn] + P.vbflxs_t[x];
+      H.vbcors_p[x] = H.vbcors_p[x] + P.vbcors_t[x];
+    }
+  }
+}
+
+}  // namespace
+
+void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
+  (void)mm; (void)k1m; (void)k1n;
+  Ctx& c = C(); const Geom& g = c.g;
+  const long L = g.lev;
+  const int lstep = (int)c.scalar("lstep");
+  const std::string mommth = c.option("mommth", "enscon");
+  if (mommth != "enscon" && mommth != "enecon" && mommth != "enedis")
+    throw std::runtime_error(" mommth = " + mommth + " is unsupported!");
+  double *pb_t = c.owned("barotp_pb_t", 2), *ub_t = c.owned("barotp_ubflx_t", 2), *vb_t = c.owned("barotp_vbflx_t", 2);
+  double *umaxb = c.owned("barotp_umaxb", 1), *uminb = c.owned("barotp_uminb", 1), *vmaxb = c.owned("barotp_vmaxb", 1),
+         *vminb = c.owned("barotp_vminb", 1), *uglue = c.owned("barotp_uglue", 1), *vglue = c.owned("barotp_vglue", 1);
+  const dim3 gint(cdiv(g.ii, 128), g.jj);
+  LAUNCH(bt_prologue, gint, 128, 0, g, m, nn, c.scalar("cwbdts", 0.0), c.scalar("cwbdls", 25.0), c.idev("iu"),
+         c.idev("iv"), c.dev("u"), c.dev("v"), c.dev("pbu"), c.dev("pbv"), c.dev("umax"), c.dev("vmax"),
+         c.dev("scuy"), c.dev("scvx"), umaxb, uminb, uglue, vmaxb, vminb, vglue);
+  double* pvn = c.dev("pvtrop") + (long)(n - 1) * L;
+  {
+    dim3 grid(cdiv(g.ii + 2, 128), g.jj + 6);
+    LAUNCH(bt_pvtrop, grid, 128, 0, g, c.idev("iu"), c.idev("iv"), c.idev("iq"), c.dev("corioq"), c.dev("pb_p"), pvn,
+           c.dev("pvtrop_o"));
+  }
+  const long on2 = (long)(n - 1) * L, om2 = (long)(m - 1) * L;
+  halo_update(std::vector<HaloReq>{{uglue, 1, halo_us}, {c.dev("utotn"), 1, halo_uv}, {umaxb, 1, halo_us},
+                                   {uminb, 1, halo_us}, {vglue, 1, halo_vs}, {c.dev("vtotn"), 1, halo_vv},
+                                   {vmaxb, 1, halo_vs}, {vminb, 1, halo_vs}, {c.dev("pgfxm") + on2, 1, halo_uv},
+                                   {c.dev("xixp") + on2, 1, halo_us}, {c.dev("xixm") + on2, 1, halo_us},
+                                   {c.dev("pgfym") + on2, 1, halo_vv}}, 1, 2);
+  halo_update(std::vector<HaloReq>{{c.dev("xiyp") + on2, 1, halo_vs}, {c.dev("xiym") + on2, 1, halo_vs}}, 1, 2);
+  halo_update(pvn, 1, 1, 3, halo_qs);
+  if (g.nreg == 2 && g.north) {
+    dim3 grid(cdiv(g.ii + 2, 128), 3);
+    LAUNCH(bt_arctic_swap, grid, 128, 0, g, umaxb, uminb, c.dev("xixp") + on2, c.dev("xixm") + on2, vmaxb, vminb,
+           c.dev("xiyp") + on2, c.dev("xiym") + on2);
+  }
+
+  BtP P{};
+  P.scp2i = c.dev("scp2i"); P.scvxi = c.dev("scvxi"); P.scuyi = c.dev("scuyi"); P.scuxi = c.dev("scuxi");
+  P.scvyi = c.dev("scvyi"); P.scuy = c.dev("scuy"); P.scvx = c.dev("scvx");
+  P.pvo = c.dev("pvtrop_o"); P.pvm = c.dev("pvtrop") + om2; P.pvn = pvn;
+  P.pgfxm_o = c.dev("pgfxm_o"); P.xixp_o = c.dev("xixp_o"); P.xixm_o = c.dev("xixm_o");
+  P.pgfxm_m = c.dev("pgfxm") + om2; P.xixp_m = c.dev("xixp") + om2; P.xixm_m = c.dev("xixm") + om2;
+  P.pgfxm_n = c.dev("pgfxm") + on2; P.xixp_n = c.dev("xixp") + on2; P.xixm_n = c.dev("xixm") + on2;
+  P.pgfym_o = c.dev("pgfym_o"); P.xiyp_o = c.dev("xiyp_o"); P.xiym_o = c.dev("xiym_o");
+  P.pgfym_m = c.dev("pgfym") + om2; P.xiyp_m = c.dev("xiyp") + om2; P.xiym_m = c.dev("xiym") + om2;
+  P.pgfym_n = c.dev("pgfym") + on2; P.xiyp_n = c.dev("xiyp") + on2; P.xiym_n = c.dev("xiym") + on2;
+  P.utotn = c.dev("utotn"); P.vtotn = c.dev("vtotn"); P.uglue = uglue; P.vglue = vglue;
+  P.umaxb = umaxb; P.uminb = uminb; P.vmaxb = vmaxb; P.vminb = vminb;
+  P.ubflxs_t = c.owned("barotp_ubflxs_t", 1); P.ubcors_t = c.owned("barotp_ubcors_t", 1);
+  P.vbflxs_t = c.owned("barotp_vbflxs_t", 1); P.vbcors_t = c.owned("barotp_vbcors_t", 1);
+  P.ip = c.idev("ip"); P.iu = c.idev("iu"); P.iv = c.idev("iv");
+  P.dlt = c.scalar("dlt");
+  P.enscon = mommth == "enscon";
+  HvP H{};
+  H.pb = c.dev("pb"); H.pbu = c.dev("pbu"); H.pbv = c.dev("pbv"); H.ub = c.dev("ub"); H.vb = c.dev("vb");
+  H.ubflx = c.dev("ubflx"); H.vbflx = c.dev("vbflx"); H.ubflxs = c.dev("ubflxs"); H.vbflxs = c.dev("vbflxs");
+  H.ubflxs_p = c.dev("ubflxs_p"); H.vbflxs_p = c.dev("vbflxs_p"); H.pb_p = c.dev("pb_p"); H.pbu_p = c.dev("pbu_p");
+  H.pbv_p = c.dev("pbv_p"); H.ubcors_p = c.dev("ubcors_p"); H.vbcors_p = c.dev("vbcors_p");
+  H.pb_mn = c.dev("pb_mn"); H.ub_mn = c.dev("ubflx_mn"); H.vb_mn = c.dev("vbflx_mn");
+  H.scuy = c.dev("scuy"); H.scvx = c.dev("scvx");
+
+  auto set_levels = [&](int ml, int nl) {
+    P.pb_ml = pb_t + (long)(ml - 1) * L; P.pb_nl = pb_t + (long)(nl - 1) * L;
+    P.ub_ml = ub_t + (long)(ml - 1) * L; P.ub_nl = ub_t + (long)(nl - 1) * L;
+    P.vb_ml = vb_t + (long)(ml - 1) * L; P.vb_nl = vb_t + (long)(nl - 1) * L;
+  };
+  auto range_launch = [&](auto kern, const double* extra, int i0, int i1, int j0, int j1) {
+    dim3 grid(cdiv(i1 - i0 + 1, 128), j1 - j0 + 1);
+    LAUNCH(kern, grid, 128, 0, g, P, extra, i0, i1, j0, j1);
+  };
+
+  int lll0 = 1, ml = 1, nl = 2;
+  double woa = 0, wob = 0, wna = 0, wnb = 0;
+  for (int nb = 1; nb <= 5; ++nb) {
+    if (nb == 1) {
+      lll0 = 1; ml = 1; nl = 2;
+      woa = -1. / lstep; wob = .5 + (lll0 - .5) / lstep; wna = 0.; wnb = 0.;
+      LAUNCH(bt_init_block1, gint, 128, 0, g, c.dev("pb_mn"), c.dev("ubflx_mn"), c.dev("vbflx_mn"), pb_t, ub_t, vb_t);
+    } else if (nb == 2) {
+      woa = 0.; wob = 0.; wna = 1. / lstep; wnb = -(lll0 - .5) / lstep;
+    } else if (nb == 4) {
+      wna = 0.; wnb = 1.;
+    }
+    {
+      dim3 grid(cdiv(g.ii + 2, 128), g.jj + 4);
+      LAUNCH(bt_zero_acc, grid, 128, 0, g, P);
+    }
+    for (int lll = lll0; lll <= lll0 + lstep / 2 - 1; ++lll) {
+      P.wo = woa * lll + wob; P.wn = wna * lll + wnb; P.wm = 1. - P.wo - P.wn;
+      set_levels(ml, nl);
+      if (lll % 2 == 1) {
+        halo_update(std::vector<HaloReq>{{pb_t, 2, halo_ps}, {ub_t, 2, halo_uv}}, 2, 2);
+        halo_update(vb_t, 2, 2, 3, halo_vv);
+        {
+          dim3 grid(cdiv(g.ii + 3, 128), g.jj + 4);
+          LAUNCH(bt_continuity, grid, 128, 0, g, P, -1, g.ii + 1, -1, g.jj + 2);
+        }
+        range_launch(bt_ueq, P.vb_ml, 0, g.ii + 1, -1, g.jj + 2);
+        range_launch(bt_veq, P.ub_nl, 0, g.ii, 0, g.jj + 2);
+      } else {
+        {
+          dim3 grid(cdiv(g.ii + 1, 128), g.jj + 2);
+          LAUNCH(bt_continuity, grid, 128, 0, g, P, 0, g.ii, 0, g.jj + 1);
+        }
+        range_launch(bt_veq, P.ub_ml, 0, g.ii, 1, g.jj + 1);
+        range_launch(bt_ueq, P.vb_nl, 1, g.ii, 1, g.jj);
+      }
+      std::swap(ml, nl);
+    }
+    lll0 = lll0 + lstep / 2;
+    set_levels(ml, nl);
+    LAUNCH(bt_harvest, gint, 128, 0, g, P, H, nb, m, n, ml, nl);
+  }
+}
+
+}  // namespace blom

@@ -3,13 +3,7 @@
 #include "common.cuh"
 namespace blom {
 #define NOT_YET(sig, what) void sig { throw std::runtime_error("blomgpu: " what " is not implemented in this build"); }
-NOT_YET(diffus_dev(int, int, int, int, int, int), "diffus")
-NOT_YET(tmsmt1_dev(int), "tmsmt1")
-NOT_YET(tmsmt2_dev(int, int, int, int), "tmsmt2")
-NOT_YET(inieos_dev(), "inieos")
-NOT_YET(pgforc_dev(int, int, int, int, int, int), "pgforc")
 NOT_YET(momtum_dev(int, int, int, int, int, int), "momtum")
-NOT_YET(barotp_dev(int, int, int, int, int, int), "barotp")
 NOT_YET(eddtra_dev(int, int, int, int, int, int), "eddtra")
 NOT_YET(pbcor1_dev(int, int, int, int, int, int), "pbcor1")
 NOT_YET(pbcor2_dev(int, int, int, int, int, int), "pbcor2")

@@ -1,0 +1,117 @@
+"""Host driver of the hot path: the part of `blom_step` (phy/mod_blom_step.F90:74-324)
+that this package replaces, on synthetic state.
+
+`HotPath` owns one BlomGpu tile, builds its band of the synthetic state, and runs
+the reference's call order for the routines on the path:
+
+    tmsmt1 -> eddtra -> advect -> [pbcor1] -> diffus -> pgforc -> momtum
+           -> barotp -> [pbcor2] -> tmsmt2
+
+Routines that the reference runs in between (ALE regrid, cmnfld2, difest, column
+physics, forcing) are out of scope; the halo refreshes those routines would have
+done for the path (phy/mod_difest.F90:826-831, phy/mod_cmnfld_routines.F90:1171-1172)
+are issued here so that the chain stays valid on device.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import synth
+from .lib import BlomGpu, time_levels, HALO_PS, HALO_UV, HALO_VV, HALO_US, HALO_VS
+
+# routines of one baroclinic step in reference order; each entry:
+# (name, needs six time-level args?)
+STEP_SEQUENCE = ["tmsmt1", "eddtra", "advect", "pbcor1", "diffus", "pgforc", "momtum", "barotp",
+                 "pbcor2", "tmsmt2"]
+
+
+def band(jtdm: int, rank: int, nranks: int):
+    """Contiguous j-band of `rank`: first bands get the remainder rows."""
+    base, rem = divmod(jtdm, nranks)
+    jj = base + (1 if rank < rem else 0)
+    j0 = rank * base + min(rank, rem)
+    return j0, jj
+
+
+class HotPath:
+    def __init__(self, config="tnx1v4", *, ntr=0, nstep=1, rank=0, nranks=1, device=0, parity=False,
+                 comm_uid: bytes | None = None, routines=None, seed=20240611, options=None):
+        itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS[config]
+        self.config, self.kdm, self.ntr = config, kdm, ntr
+        self.itdm, self.jtdm, self.nreg = itdm, jtdm, nreg
+        self.rank, self.nranks = rank, nranks
+        j0, jj = band(jtdm, rank, nranks)
+        self.j0, self.jj = j0, jj
+        self.syn = synth.Synth(itdm, jtdm, kdm, nreg, ntr=ntr, j0=j0, jj=jj, baclin=baclin, batrop=batrop,
+                               seed=seed)
+        self.grid = self.syn.grid()
+        self.state = self.syn.state(self.grid)
+        self.nstep = nstep
+        self.scalars = self.syn.scalars(nstep)
+        self.levels = time_levels(nstep, kdm)
+        g = self.gpu = BlomGpu(itdm, jtdm, kdm, nreg, ntr=ntr, j0=j0, jj=jj, rank=rank, nranks=nranks,
+                               device=device, parity=parity)
+        if nranks > 1:
+            if comm_uid is None:
+                raise ValueError("multi-rank HotPath needs the NCCL unique id")
+            g.comm_init(comm_uid)
+        for k, v in (options or {}).items():
+            g.set_option(k, v)
+        self.arrays = {**self.grid, **self.state}
+        g.register_all(self.arrays)
+        g.set_scalars(**self.scalars)
+        synth.fill_halos(g, self.arrays)
+        g.bigrid("depths")
+        g.download_all()
+        self.masks = {k: g.fetch(k, 1, np.int32)[0].copy() for k in ("ip", "iu", "iv", "iq")}
+        synth.derive(self.grid, self.state, self.masks, self.levels, self.scalars, g,
+                     sync_in=lambda names: [g.upload(n) for n in names],
+                     sync_out=lambda names: [g.download(n) for n in names])
+        g.upload_all()
+        self.routines = list(routines) if routines is not None else self.available_routines()
+        self.setup()
+
+    # which routines this build provides (stubs raise "not implemented")
+    @staticmethod
+    def available_routines():
+        return ["advect"]
+
+    def setup(self):
+        g = self.gpu
+        if "advect" in self.routines:
+            g.init_cppm()
+
+    def set_step(self, nstep):
+        self.nstep = nstep
+        self.levels = time_levels(nstep, self.kdm)
+        self.gpu.set_scalar("nstep", nstep)
+
+    def step(self):
+        """One pass of the hot path over the resident state."""
+        g = self.gpu
+        m, n, mm, nn, k1m, k1n = self.levels
+        for r in self.routines:
+            if r == "tmsmt1":
+                g.tmsmt1(nn)
+            elif r == "tmsmt2":
+                g.tmsmt2(m, mm, nn, k1m)
+            else:
+                getattr(g, r)(m, n, mm, nn, k1m, k1n)
+
+    def upload_inputs(self):
+        """Host->device copy of the prognostic state (e2e leg)."""
+        for nm in ("dp", "temp", "saln", "u", "v", "trc"):
+            if nm in self.arrays:
+                self.gpu.upload(nm)
+
+    def download_outputs(self):
+        for nm in ("dp", "temp", "saln", "u", "v", "trc"):
+            if nm in self.arrays:
+                self.gpu.download(nm)
+
+    def io_bytes(self):
+        b = sum(self.arrays[nm].nbytes for nm in ("dp", "temp", "saln", "u", "v", "trc") if nm in self.arrays)
+        return b, b
+
+    def finalize(self):
+        self.gpu.finalize()

@@ -37,7 +37,7 @@ ITYPE = {
     "dp": HALO_PS, "temp": HALO_PS, "saln": HALO_PS, "sigma": HALO_PS, "p": HALO_PS, "phi": HALO_PS,
     "pb": HALO_PS, "pb_p": HALO_PS, "sealv": HALO_PS, "trc": HALO_PS, "difint": HALO_PS,
     "difiso": HALO_PS, "difwgt": HALO_PS, "coriop": HALO_PS, "pbath": HALO_PS,
-    "dpold": HALO_PS, "told": HALO_PS, "sold": HALO_PS, "mld": HALO_PS, "OBLdepth": HALO_PS,
+    "dpold": HALO_PS, "told": HALO_PS, "sold": HALO_PS, "trcold": HALO_PS, "pb_mn": HALO_PS, "mld": HALO_PS, "OBLdepth": HALO_PS,
     # u-points
     "scux": HALO_US, "scuy": HALO_US, "scu2": HALO_US, "scuxi": HALO_US, "scuyi": HALO_US,
     "u": HALO_UV, "dpu": HALO_US, "pu": HALO_US, "uflx": HALO_UV, "utflx": HALO_UV, "usflx": HALO_UV,
@@ -46,7 +46,7 @@ ITYPE = {
     "utfltd": HALO_UV, "utflsm": HALO_UV, "utflld": HALO_UV, "usfltd": HALO_UV, "usflsm": HALO_UV,
     "usflld": HALO_UV, "umax": HALO_US, "taux": HALO_UV, "nslpx": HALO_US, "pgfx": HALO_UV,
     "pgfxm": HALO_UV, "xixp": HALO_US, "xixm": HALO_US, "dpuold": HALO_US, "uja": HALO_UV, "ujb": HALO_UV,
-    "pgfxo": HALO_UV, "pgfxm_o": HALO_UV, "xixp_o": HALO_US, "xixm_o": HALO_US, "ubrhs": HALO_UV,
+    "pgfx_o": HALO_UV, "pgfxm_o": HALO_UV, "ubflx_mn": HALO_UV, "utotn": HALO_UV, "xixp_o": HALO_US, "xixm_o": HALO_US, "ubrhs": HALO_UV,
     "mu_nonloc": HALO_UV, "uflux": HALO_UV, "uflux2": HALO_UV, "uflux3": HALO_UV,
     # v-points
     "scvx": HALO_VS, "scvy": HALO_VS, "scv2": HALO_VS, "scvxi": HALO_VS, "scvyi": HALO_VS,
@@ -56,11 +56,11 @@ ITYPE = {
     "vtfltd": HALO_VV, "vtflsm": HALO_VV, "vtflld": HALO_VV, "vsfltd": HALO_VV, "vsflsm": HALO_VV,
     "vsflld": HALO_VV, "vmax": HALO_VS, "tauy": HALO_VV, "nslpy": HALO_VS, "pgfy": HALO_VV,
     "pgfym": HALO_VV, "xiyp": HALO_VS, "xiym": HALO_VS, "dpvold": HALO_VS, "via": HALO_VV, "vib": HALO_VV,
-    "pgfyo": HALO_VV, "pgfym_o": HALO_VV, "xiyp_o": HALO_VS, "xiym_o": HALO_VS, "vbrhs": HALO_VV,
+    "pgfy_o": HALO_VV, "pgfym_o": HALO_VV, "vbflx_mn": HALO_VV, "vtotn": HALO_VV, "xiyp_o": HALO_VS, "xiym_o": HALO_VS, "vbrhs": HALO_VV,
     "mv_nonloc": HALO_VV, "vflux": HALO_VV, "vflux2": HALO_VV, "vflux3": HALO_VV,
     # q-points
     "scqx": HALO_QS, "scqy": HALO_QS, "scq2": HALO_QS, "scq2i": HALO_QS, "corioq": HALO_QS,
-    "pvtrop": HALO_QS,
+    "pvtrop": HALO_QS, "pvtrop_o": HALO_QS,
 }
 
 
@@ -326,6 +326,43 @@ class Synth:
         st["nslpy"] = self._put(self.zeros(kk), 1.0e-4 * self._normal(kk) * ivm)
         st["taux"] = self._put(self.zeros(1), 0.1 * self._normal(1) * ium)
         st["tauy"] = self._put(self.zeros(1), 0.1 * self._normal(1) * ivm)
+        # --- time smoother work arrays (phy/mod_tmsmt.F90:53-66)
+        st["dpold"] = self.zeros(2 * kk)
+        self.interior(st["dpold"])[:] = self.interior(dp) * (1.0 + 1.0e-3 * (self._uniform(2 * kk) - 0.5))
+        st["told"] = self._put(self.zeros(kk), self.interior(st["temp"])[:kk] + 0.01)
+        st["sold"] = self._put(self.zeros(kk), self.interior(st["saln"])[:kk] + 0.001)
+        st["dpuold"] = self.zeros(kk)
+        st["dpvold"] = self.zeros(kk)
+        if self.ntr > 0:
+            st["trcold"] = self.zeros(kk * self.ntr)
+            for nt in range(self.ntr):
+                self.interior(st["trcold"])[nt * kk:(nt + 1) * kk] = \
+                    self.interior(st["trc"])[nt * 2 * kk:nt * 2 * kk + kk] * 1.01
+        # --- pressure gradient force arrays (phy/mod_pgforc.F90:51-80); bottom geopotential
+        self.interior(st["phi"])[kk] = -9.806 * depth
+        for nm, msk in (("pgfx", ium), ("pgfy", ivm)):
+            st[nm] = self._put(self.zeros(2 * kk), 1.0e-2 * self._normal(2 * kk) * msk)
+        st["pgfx_o"] = self.zeros(kk)
+        st["pgfy_o"] = self.zeros(kk)
+        for nm, msk, amp in (("pgfxm", ium, 1e-2), ("pgfym", ivm, 1e-2), ("xixp", ium, 1e-7), ("xixm", ium, 1e-7),
+                             ("xiyp", ivm, 1e-7), ("xiym", ivm, 1e-7)):
+            base = 1.0e-3 / 9806.0 if nm.startswith("xi") else 0.0
+            st[nm] = self._put(self.zeros(2), (base + amp * 1e-3 * self._normal(2)) * msk)
+            st[nm + "_o"] = self._put(self.zeros(1), (base + amp * 1e-3 * self._normal(1)) * msk)
+        # --- barotropic solver arrays (phy/mod_barotp.F90:57-67)
+        pbm = dpm.sum(axis=0)
+        st["pb_mn"] = self._put(self.zeros(2), np.stack([pbm, pbm * (1.0 + 1e-6 * (self._uniform(1)[0] - 0.5))]))
+        for nm, msk, sc_ in (("ubflx", ium, su), ("vbflx", ivm, sv)):
+            base = 1.0e-3 * self._normal(1)[0] * sc_ * pb * msk
+            st[nm] = self._put(self.zeros(2), np.stack([base, base]))
+            st[nm + "_mn"] = self._put(self.zeros(2), np.stack([base, base * 0.999]))
+        omega2 = 2.0 * 7.2921e-5
+        latq = self.interior(grid["corioq"])[0]
+        pvq = np.where(pb > 0, latq / np.maximum(pb, 1.0), 0.0)
+        st["pvtrop"] = self._put(self.zeros(2), np.stack([pvq, pvq]))
+        st["pvtrop_o"] = self._put(self.zeros(1), pvq)
+        st["utotn"] = self._put(self.zeros(1), 1.0e-6 * self._normal(1) * ium)
+        st["vtotn"] = self._put(self.zeros(1), 1.0e-6 * self._normal(1) * ivm)
         return st
 
     def scalars(self, nstep=1):
@@ -333,7 +370,8 @@ class Synth:
         lstep = 2 * int(np.ceil(0.5 * self.baclin / self.batrop))
         dlt = self.baclin / lstep
         return {"baclin": self.baclin, "batrop": self.batrop, "lstep": lstep, "dlt": dlt,
-                "delt1": 2.0 * self.baclin, "nstep": nstep}
+                "delt1": 2.0 * self.baclin, "nstep": nstep, "pref": 2000.0 * ONEM / 9.806 * 9.806,
+                "cwbdts": 5.0e-5, "cwbdls": 25.0}
 
 
 def fill_halos(backend, arrays: dict, nbdy=4, names=None):
@@ -348,3 +386,63 @@ def fill_halos(backend, arrays: dict, nbdy=4, names=None):
         lev = a.shape[-1] * a.shape[-2]
         nlev = a.size // lev
         backend.xctilr(name, 1, nlev, nbdy, nbdy, it)
+
+
+def derive(gr, st, masks, levels, scalars, backend, sync_in=None, sync_out=None):
+    """Fields other routines of the model would have produced before the hot path runs:
+    p from dp(kn), pbu/pbv, dpu/dpv (phy/mod_pgforc.F90:452-484), umax/vmax
+    (phy/mod_blom_init.F90:514-523).  numpy on whole arrays, then halos refreshed."""
+    m, n, mm, nn, k1m, k1n = levels
+    kk = st["dp"].shape[0] // 2
+    iu, iv = masks["iu"], masks["iv"]
+    dp, p = st["dp"], st["p"]
+    p[0] = 0.0
+    for k in range(kk):
+        p[k + 1] = p[k] + dp[k + nn]
+    pb = st["pb"]
+    pb[n - 1] = p[kk]
+    pb[m - 1] = dp[mm:mm + kk].sum(axis=0)
+    st["pb_p"][0] = pb[n - 1]
+    for lvl in range(2):
+        st["pbu"][lvl][:, 1:] = np.minimum(pb[lvl][:, 1:], pb[lvl][:, :-1])
+        st["pbv"][lvl][1:, :] = np.minimum(pb[lvl][1:, :], pb[lvl][:-1, :])
+    st["pbu_p"][0] = st["pbu"][n - 1]
+    st["pbv_p"][0] = st["pbv"][n - 1]
+    for (koff, pl) in ((nn, p),):
+        for k in range(kk):
+            q1 = np.minimum(st["pbu"][n - 1][:, 1:], 0.5 * (pl[k + 1][:, 1:] + pl[k + 1][:, :-1]))
+            q0 = np.minimum(st["pbu"][n - 1][:, 1:], 0.5 * (pl[k][:, 1:] + pl[k][:, :-1]))
+            st["dpu"][k + koff][:, 1:] = np.maximum(0.0, q1 - q0) * iu[:, 1:]
+            q1 = np.minimum(st["pbv"][n - 1][1:, :], 0.5 * (pl[k + 1][1:, :] + pl[k + 1][:-1, :]))
+            q0 = np.minimum(st["pbv"][n - 1][1:, :], 0.5 * (pl[k][1:, :] + pl[k][:-1, :]))
+            st["dpv"][k + koff][1:, :] = np.maximum(0.0, q1 - q0) * iv[1:, :]
+    # level m thicknesses at u/v points from dp(km)
+    pm = np.zeros_like(p)
+    for k in range(kk):
+        pm[k + 1] = pm[k] + dp[k + mm]
+    for k in range(kk):
+        q1 = np.minimum(st["pbu"][m - 1][:, 1:], 0.5 * (pm[k + 1][:, 1:] + pm[k + 1][:, :-1]))
+        q0 = np.minimum(st["pbu"][m - 1][:, 1:], 0.5 * (pm[k][:, 1:] + pm[k][:, :-1]))
+        st["dpu"][k + mm][:, 1:] = np.maximum(0.0, q1 - q0) * iu[:, 1:]
+        q1 = np.minimum(st["pbv"][m - 1][1:, :], 0.5 * (pm[k + 1][1:, :] + pm[k + 1][:-1, :]))
+        q0 = np.minimum(st["pbv"][m - 1][1:, :], 0.5 * (pm[k][1:, :] + pm[k][:-1, :]))
+        st["dpv"][k + mm][1:, :] = np.maximum(0.0, q1 - q0) * iv[1:, :]
+    baclin = scalars["baclin"]
+    scp2, scuy, scvx = gr["scp2"][0], gr["scuy"][0], gr["scvx"][0]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        st["umax"][0][:, 1:] = 0.9 * 0.125 * np.minimum(scp2[:, 1:], scp2[:, :-1]) / (scuy[:, 1:] * baclin)
+        st["vmax"][0][1:, :] = 0.9 * 0.125 * np.minimum(scp2[1:, :], scp2[:-1, :]) / (scvx[1:, :] * baclin)
+    for nm in ("umax", "vmax"):
+        st[nm][~np.isfinite(st[nm])] = 0.0
+    names = {"p", "pb", "pb_p", "pbu", "pbv", "pbu_p", "pbv_p", "dpu", "dpv", "umax", "vmax"}
+    if sync_in is not None:
+        sync_in(names)      # e.g. upload the freshly derived arrays to the device
+    fill_halos(backend, {**gr, **st}, names=names)
+    if sync_out is not None:
+        sync_out(names)     # e.g. download the halo-filled arrays
+    # land points carry zero bottom pressure; keep divisions finite like the model does
+    for nm in ("pbu", "pbv"):
+        a = st[nm]
+        a[a <= 0.0] = 0.0
+
+

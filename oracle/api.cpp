@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see core.hpp header).
 // Flat C entry points so tests / bench.py can drive the restatement with ctypes.
 #include "core.hpp"
+#include "eos.hpp"
 #include <cstdio>
 #include <cstring>
 
@@ -110,5 +111,31 @@ int oracle_bigrid(const char* depth) { GUARD(orc::bigrid(orc::O().a2(depth))) }
 int oracle_init_cppm() { GUARD(orc::init_cppm()) }
 int oracle_advect(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::advect(m, n, mm, nn, k1m, k1n)) }
 int oracle_cppm(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::cppm(m, n, mm, nn, k1m, k1n)) }
+
+int oracle_inieos() { GUARD(orc::inieos()) }
+int oracle_diffus(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::diffus(m, n, mm, nn, k1m, k1n)) }
+int oracle_tmsmt1(int nn) { GUARD(orc::tmsmt1(nn)) }
+int oracle_tmsmt2(int m, int mm, int nn, int k1m) { GUARD(orc::tmsmt2(m, mm, nn, k1m)) }
+
+int oracle_pgforc(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::pgforc(m, n, mm, nn, k1m, k1n)) }
+
+int oracle_barotp(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::barotp(m, n, mm, nn, k1m, k1n)) }
+
+// scalar access to the EOS restatement for the unit checks in tests/test_oracle_ops.py
+int oracle_eos(const char* fn, const double* a, double* out) {
+  using namespace orc::eos;
+  std::string f(fn);
+  if (f == "rho") out[0] = rho(a[0], a[1], a[2]);
+  else if (f == "alp") out[0] = alp(a[0], a[1], a[2]);
+  else if (f == "sig") out[0] = sig(a[0], a[1]);
+  else if (f == "sig0") out[0] = sig0(a[0], a[1]);
+  else if (f == "p_alpha") out[0] = p_alpha(a[0], a[1], a[2], a[3]);
+  else if (f == "dalpdt") out[0] = dalpdt(a[0], a[1], a[2]);
+  else if (f == "dalpds") out[0] = dalpds(a[0], a[1], a[2]);
+  else if (f == "delphi") delphi(a[0], a[1], a[2], a[3], out[0], out[1], out[2]);
+  else if (f == "dynh_derivatives") dynh_derivatives(a[0], a[1], a[2], a[3], a[4], out[0], out[1]);
+  else return 1;
+  return 0;
+}
 
 }  // extern "C"

@@ -145,6 +145,13 @@ class Oracle:
     def crc32(self, data: bytes, init=0):
         return self.lib.oracle_crc32(data, C.c_long(len(data)), C.c_uint32(init))
 
+    def eos(self, fn, *args, nout=1):
+        a = (C.c_double * len(args))(*args)
+        out = (C.c_double * 3)()
+        if self.lib.oracle_eos(fn.encode(), a, out) != 0:
+            raise OracleError(f"unknown eos function {fn}")
+        return out[0] if nout == 1 else tuple(out[:nout])
+
     def bigrid(self, depth="depths"):
         self._ck(self.lib.oracle_bigrid(depth.encode()))
 

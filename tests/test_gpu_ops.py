@@ -1,0 +1,119 @@
+"""GPU parity (through the C ABI) of diffus, tmsmt1/2, pgforc and barotp against the
+oracle on identical seeded inputs.
+
+Tolerances (float64, stated per routine): parity build (-fmad=false) <= 1e-13 relative
+to the field's max-norm for the streaming routines, <= 1e-12 for pgforc (CUDA exp/log-free
+but long recurrences) and <= 1e-11 for barotp (125+ chained substeps, one libm exp);
+performance build (FMA contraction) 1e-10."""
+import numpy as np
+import pytest
+
+from util import Case, interior, max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def pair(cfg, ntr=1, nstep=1, parity=True, opts=None):
+    c = Case(cfg, ntr=ntr, nstep=nstep)
+    o = c.new_oracle(); g = c.new_gpu(parity=parity)
+    for k, v in (opts or {}).items():
+        o.set_option(k, v); g.set_option(k, v)
+    o.inieos(); g.inieos()
+    return c, o, g
+
+
+def check(g, o, names, tol, halo=0):
+    g.download_all()
+    for nm in names:
+        err = max_rel_err(interior(g.arrays[nm], halo=halo), interior(o.arrays[nm], halo=halo))
+        assert err <= tol, (nm, err)
+
+
+@pytest.mark.parametrize("cfg", ["tiny0", "tiny1", "tiny2", "tiny3", "tiny4"])
+@pytest.mark.parametrize("parity", [True, False])
+def test_diffus(cfg, parity):
+    c, o, g = pair(cfg, parity=parity)
+    try:
+        o.diffus(*c.levels); g.diffus(*c.levels)
+        check(g, o, ["temp", "saln", "trc", "sigma", "usflld", "utflld", "vsflld", "vtflld", "usflx", "utflx",
+                     "vsflx", "vtflx"], 1e-13 if parity else 1e-11, halo=1)
+        assert np.abs(interior(g.arrays["temp"]) - interior(c.state["temp"])).max() > 1e-6
+    finally:
+        g.finalize()
+
+
+def test_diffus_neutral_and_bad_option():
+    from blom_b200.lib import BlomGpuError
+    c, o, g = pair("tiny1", opts={"ltedtp": "neutral"})
+    try:
+        o.diffus(*c.levels); g.diffus(*c.levels)
+        check(g, o, ["temp", "saln", "dp"], 0.0, halo=1)
+        g.set_option("ltedtp", "bogus")
+        with pytest.raises(BlomGpuError, match="ltedtp = bogus is unsupported"):
+            g.diffus(*c.levels)
+    finally:
+        g.finalize()
+
+
+@pytest.mark.parametrize("cfg", ["tiny0", "tiny2", "tiny3"])
+@pytest.mark.parametrize("vcoord", ["cntiso_hybrid", "isopyc_bulkml"])
+def test_tmsmt(cfg, vcoord):
+    c, o, g = pair(cfg, opts={"vcoord": vcoord})
+    try:
+        m, n, mm, nn, k1m, k1n = c.levels
+        o.tmsmt1(nn); g.tmsmt1(nn)
+        check(g, o, ["dpold", "told", "sold", "trcold", "dpuold", "dpvold"], 0.0)
+        o.tmsmt2(m, mm, nn, k1m); g.tmsmt2(m, mm, nn, k1m)
+        check(g, o, ["dp", "temp", "saln", "trc", "dpu", "dpv"], 1e-14)
+        check(g, o, ["p"], 1e-15, halo=2)
+    finally:
+        g.finalize()
+
+
+@pytest.mark.parametrize("cfg", ["tiny0", "tiny1", "tiny2", "tiny3", "tiny4"])
+@pytest.mark.parametrize("parity", [True, False])
+def test_pgforc(cfg, parity):
+    c, o, g = pair(cfg, parity=parity)
+    try:
+        o.pgforc(*c.levels); g.pgforc(*c.levels)
+        tol = 1e-12 if parity else 1e-10
+        check(g, o, ["pgfx", "pgfy", "pgfx_o", "pgfy_o", "pgfxm", "pgfym", "xixp", "xixm", "xiyp", "xiym", "sealv",
+                     "phi"], tol)
+        check(g, o, ["p"], 1e-15, halo=2)
+        check(g, o, ["dpu", "dpv", "pu", "pv", "xixp_o", "pgfxm_o", "xiym_o"], 1e-15, halo=1)
+    finally:
+        g.finalize()
+
+
+BT_FIELDS = ["pb", "pbu", "pbv", "ub", "vb", "ubflx", "vbflx", "ubflxs", "vbflxs", "ubflxs_p", "vbflxs_p", "pb_p",
+             "pbu_p", "pbv_p", "ubcors_p", "vbcors_p", "pb_mn", "ubflx_mn", "vbflx_mn"]
+
+
+@pytest.mark.parametrize("cfg,mommth", [("tiny0", "enscon"), ("tiny1", "enecon"), ("tiny2", "enscon"),
+                                        ("tiny3", "enscon"), ("tiny4", "enedis"), ("fuk95", "enscon")])
+def test_barotp(cfg, mommth):
+    c, o, g = pair(cfg, opts={"mommth": mommth})
+    try:
+        o.pgforc(*c.levels); g.pgforc(*c.levels)
+        o.barotp(*c.levels); g.barotp(*c.levels)
+        check(g, o, BT_FIELDS, 1e-11)
+        check(g, o, ["pvtrop"], 1e-14, halo=1)
+        # the routine-local save arrays carry over to the next call: run a second step
+        o.barotp(*c.levels); g.barotp(*c.levels)
+        check(g, o, BT_FIELDS, 1e-10)
+    finally:
+        g.finalize()
+
+
+def test_barotp_perf_build_and_bad_option():
+    from blom_b200.lib import BlomGpuError
+    c, o, g = pair("tiny2", parity=False)
+    try:
+        o.pgforc(*c.levels); g.pgforc(*c.levels)
+        o.barotp(*c.levels); g.barotp(*c.levels)
+        check(g, o, BT_FIELDS, 1e-9)
+        g.set_option("mommth", "bogus")
+        with pytest.raises(BlomGpuError, match="mommth = bogus is unsupported"):
+            g.barotp(*c.levels)
+    finally:
+        g.finalize()

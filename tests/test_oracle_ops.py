@@ -1,0 +1,167 @@
+"""CPU pins of the oracle's EOS, diffus, tmsmt, pgforc and barotp restatements through
+identities and conservation properties (the reference ships no golden outputs)."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from util import Case, interior
+
+ONEM = 9806.0
+
+
+@pytest.fixture(scope="module")
+def eos():
+    o = Oracle(12, 10, 2, 0)
+    o.set_scalar("pref", 2000.0 * ONEM)
+    o.inieos()
+    return o
+
+
+def test_eos_identities(eos):
+    p, t, s = 1500.0 * ONEM, 7.3, 34.9
+    assert eos.eos("rho", 0.0, 0.0, 0.0) == pytest.approx(9.9985372432159340e+02, rel=1e-15)
+    assert eos.eos("rho", p, t, s) * eos.eos("alp", p, t, s) == pytest.approx(1.0, rel=1e-15)
+    # sigma-units potential densities are rho(pref) - 1/alpha0 and rho(0) - 1/alpha0
+    assert eos.eos("sig0", t, s) == pytest.approx(eos.eos("rho", 0.0, t, s) - 1000.0, rel=1e-12)
+    assert eos.eos("sig", t, s) == pytest.approx(eos.eos("rho", 2000.0 * ONEM, t, s) - 1000.0, rel=1e-12)
+    assert 1020.0 < eos.eos("rho", 0.0, 10.0, 35.0) < 1030.0  # sea water
+
+
+def gauss(f, a, b, n=24):
+    x, w = np.polynomial.legendre.leggauss(n)
+    xm, xr = 0.5 * (a + b), 0.5 * (b - a)
+    return xr * sum(wi * f(xm + xr * xi) for xi, wi in zip(x, w))
+
+
+def test_eos_pressure_integrals_match_quadrature(eos):
+    t, s = 4.2, 35.1
+    for p1, p2 in ((0.0, 50 * ONEM), (900 * ONEM, 1000 * ONEM), (0.0, 5000 * ONEM)):
+        ref = gauss(lambda p: eos.eos("alp", p, t, s), p1, p2)
+        assert eos.eos("p_alpha", p1, p2, t, s) == pytest.approx(ref, rel=2e-13)
+        dphi, a1, a2 = eos.eos("delphi", p1, p2, t, s, nout=3)
+        assert dphi == pytest.approx(-ref, rel=2e-13)
+        assert a1 == pytest.approx(eos.eos("alp", p1, t, s), rel=1e-15)
+        assert a2 == pytest.approx(eos.eos("alp", p2, t, s), rel=1e-15)
+
+
+def test_eos_derivatives_match_differences(eos):
+    p, t, s = 800 * ONEM, 9.1, 35.3
+    h = 1e-5
+    dadt = (eos.eos("alp", p, t + h, s) - eos.eos("alp", p, t - h, s)) / (2 * h)
+    dads = (eos.eos("alp", p, t, s + h) - eos.eos("alp", p, t, s - h)) / (2 * h)
+    assert eos.eos("dalpdt", p, t, s) == pytest.approx(dadt, rel=1e-7)
+    assert eos.eos("dalpds", p, t, s) == pytest.approx(dads, rel=1e-7)
+    # dynamic enthalpy h(p;T,S) = int_p0^p alpha dp'; its T,S derivatives averaged over [p1,p2]
+    p0, p1, p2 = 0.0, 700 * ONEM, 900 * ONEM
+
+    def mean_h(tt, ss):
+        return gauss(lambda q: eos.eos("p_alpha", p0, q, tt, ss), p1, p2) / (p2 - p1)
+    d_t, d_s = eos.eos("dynh_derivatives", p0, p1, p2, t, s, nout=2)
+    assert d_t == pytest.approx((mean_h(t + 1e-3, s) - mean_h(t - 1e-3, s)) / 2e-3, rel=1e-6)
+    assert d_s == pytest.approx((mean_h(t, s + 1e-3) - mean_h(t, s - 1e-3)) / 2e-3, rel=1e-6)
+
+
+def prep(cfg, ntr=1, nstep=1):
+    c = Case(cfg, ntr=ntr, nstep=nstep)
+    o = c.new_oracle()
+    o.inieos()
+    return c, o
+
+
+@pytest.mark.parametrize("cfg", ["tiny1", "tiny3", "tiny2"])
+def test_diffus_conserves_and_keeps_uniform(cfg):
+    c, o = prep(cfg)
+    kk = c.dims[2]; m, n, mm, nn, k1m, k1n = c.levels
+    a = o.arrays
+    rows = slice(0, -1) if cfg == "tiny2" else slice(None)
+    w = lambda: np.maximum(interior(a["dp"][nn:nn + kk]), 1e-5)[:, rows] * interior(a["scp2"][0])[rows]
+    ip = (interior(c.masks["ip"]) == 1)[rows]
+    s0 = (w() * interior(a["saln"][nn:nn + kk])[:, rows])[:, ip].sum()
+    t_before = a["temp"].copy()
+    a["trc"][:] = 2.5
+    o.diffus(*c.levels)
+    s1 = (w() * interior(a["saln"][nn:nn + kk])[:, rows])[:, ip].sum()
+    assert abs(s1 - s0) <= 1e-13 * abs(s0)
+    assert np.abs(interior(a["temp"][nn:nn + kk]) - interior(t_before[nn:nn + kk])).max() > 1e-6
+    assert np.abs(interior(a["trc"][nn:nn + kk])[:, interior(c.masks["ip"]) == 1] - 2.5).max() <= 1e-13
+    sg = interior(a["sigma"][nn:nn + kk])[:, interior(c.masks["ip"]) == 1]
+    assert 15.0 < sg.min() and sg.max() < 50.0
+
+
+def test_diffus_neutral_only_refreshes_halos():
+    c, o = prep("tiny1")
+    o.set_option("ltedtp", "neutral")
+    before = o.arrays["temp"].copy()
+    o.diffus(*c.levels)
+    assert np.array_equal(interior(o.arrays["temp"]), interior(before))
+
+
+@pytest.mark.parametrize("cfg", ["tiny0", "tiny2"])
+def test_tmsmt(cfg):
+    c, o = prep(cfg)
+    kk = c.dims[2]; m, n, mm, nn, k1m, k1n = c.levels
+    a = o.arrays
+    o.tmsmt1(nn)
+    ip = interior(c.masks["ip"]) == 1
+    assert np.array_equal(interior(a["dpold"][nn:nn + kk])[:, ip], interior(a["dp"][nn:nn + kk])[:, ip])
+    assert np.array_equal(interior(a["told"])[:, ip], interior(a["temp"][nn:nn + kk])[:, ip])
+    a["temp"][:] = 5.0; a["told"][:] = 5.0
+    o.tmsmt2(m, mm, nn, k1m)
+    t = interior(a["temp"][mm:mm + kk])[:, ip]
+    assert np.abs(t - 5.0).max() <= 1e-13
+    # smoothed thicknesses still add up to pb(m) (weights .875 + 2*.0625 = 1)
+    tot = interior(a["dp"][mm:mm + kk]).sum(axis=0)[ip]
+    assert np.abs(tot / interior(a["pb"][m - 1])[ip] - 1.0).max() <= 1e-13
+    # p rebuilt from dp(km) on -2..+2
+    p = a["p"]
+    assert np.allclose(interior(p[kk], halo=2)[interior(c.masks["ip"], halo=2) == 1],
+                       interior(a["dp"][mm:mm + kk].sum(axis=0), halo=2)[interior(c.masks["ip"], halo=2) == 1],
+                       rtol=1e-13)
+
+
+@pytest.mark.parametrize("cfg", ["tiny1", "tiny2", "tiny4"])
+def test_pgforc_basic(cfg):
+    c, o = prep(cfg)
+    kk = c.dims[2]; m, n, mm, nn, k1m, k1n = c.levels
+    a = o.arrays
+    old_pgfx = a["pgfx"].copy()
+    o.pgforc(*c.levels)
+    iu = interior(c.masks["iu"]) == 1; ip = interior(c.masks["ip"]) == 1
+    for nm in ("pgfx", "pgfy", "phi", "pgfxm", "xixp", "xixm", "sealv", "dpu", "pu"):
+        assert np.isfinite(a[nm]).all(), nm
+    assert np.array_equal(interior(a["pgfx_o"])[:, iu], interior(old_pgfx[nn:nn + kk])[:, iu])
+    # baroclinic part has zero dpu-weighted depth mean
+    mean = (interior(a["pgfx"][nn:nn + kk]) * interior(a["dpu"][nn:nn + kk])).sum(axis=0)[iu]
+    scale = (np.abs(interior(a["pgfx"][nn:nn + kk])) * interior(a["dpu"][nn:nn + kk])).sum(axis=0)[iu]
+    assert np.abs(mean).max() <= 1e-12 * scale.max()
+    # dpu sums to pbu = min of neighbouring bottom pressures; sea level ~ metres
+    pbu = np.minimum(a["p"][kk][:, 1:], a["p"][kk][:, :-1])[4:-4, 3:-4]
+    assert np.allclose(interior(a["dpu"][nn:nn + kk]).sum(axis=0)[iu], pbu[iu], rtol=1e-12)
+    assert np.abs(interior(a["sealv"][0])[ip]).max() < 500.0
+    # geopotential decreases downward monotonically (alpha > 0)
+    phi = interior(a["phi"])[:, ip]
+    assert (np.diff(phi, axis=0) <= 0).all()
+
+
+@pytest.mark.parametrize("cfg,mommth", [("tiny0", "enscon"), ("tiny2", "enscon"), ("tiny3", "enecon")])
+def test_barotp_mass_and_bounds(cfg, mommth):
+    c, o = prep(cfg)
+    a = o.arrays
+    a["pb_mn"][1] = a["pb_mn"][0]
+    o.set_option("mommth", mommth)
+    m, n = c.levels[0], c.levels[1]
+    rows = slice(0, -1) if cfg == "tiny2" else slice(None)
+    scp2 = interior(a["scp2"][0])[rows]
+    mass0 = (interior(a["pb_mn"][0])[rows] * scp2).sum()
+    o.pgforc(*c.levels)
+    o.barotp(*c.levels)
+    for nm in ("pb", "pb_p", "ub", "vb", "ubflxs_p", "ubcors_p", "pvtrop", "pb_mn", "ubflx_mn"):
+        assert np.isfinite(a[nm]).all(), nm
+    for lvl in (m - 1, n - 1):
+        mass = (interior(a["pb"][lvl])[rows] * scp2).sum()
+        assert abs(mass - mass0) <= 1e-12 * mass0, (lvl, mass, mass0)
+    assert abs((interior(a["pb_p"][0])[rows] * scp2).sum() - mass0) <= 1e-12 * mass0
+    ip = interior(c.masks["ip"]) == 1
+    assert np.abs(interior(a["pb"][n - 1])[ip] / interior(c.state["pb"][n - 1])[ip] - 1).max() < 0.05
+    iu = interior(c.masks["iu"]) == 1
+    assert np.abs(interior(a["ub"][n - 1])[iu]).max() < 5.0

@@ -35,7 +35,7 @@ class Case:
         prep.bigrid("depths")
         self.nreg = prep.nreg
         self.masks = {k: prep.get_int(k).reshape(self.syn.ldj, self.syn.ldi).copy() for k in ("ip", "iu", "iv", "iq")}
-        derive(self, prep)
+        synth.derive(self.grid, self.state, self.masks, self.levels, self.scalars, prep)
 
     def arrays(self):
         return {k: v.copy() for k, v in {**self.grid, **self.state}.items()}
@@ -57,62 +57,6 @@ class Case:
         g.set_scalars(**self.scalars)
         g.bigrid("depths")
         return g
-
-
-def derive(case: Case, prep: Oracle):
-    """Fields other routines of the model would have produced before the hot path runs:
-    p from dp(kn), pbu/pbv, dpu/dpv (phy/mod_pgforc.F90:452-484), umax/vmax
-    (phy/mod_blom_init.F90:514-523).  numpy on whole arrays, then halos refreshed."""
-    st, gr = case.state, case.grid
-    kk = case.dims[2]
-    m, n, mm, nn, k1m, k1n = case.levels
-    ip = case.masks["ip"]
-    iu, iv = case.masks["iu"], case.masks["iv"]
-    dp, p = st["dp"], st["p"]
-    p[0] = 0.0
-    for k in range(kk):
-        p[k + 1] = p[k] + dp[k + nn]
-    pb = st["pb"]
-    pb[n - 1] = p[kk]
-    pb[m - 1] = dp[mm:mm + kk].sum(axis=0)
-    st["pb_p"][0] = pb[n - 1]
-    for lvl in range(2):
-        st["pbu"][lvl][:, 1:] = np.minimum(pb[lvl][:, 1:], pb[lvl][:, :-1])
-        st["pbv"][lvl][1:, :] = np.minimum(pb[lvl][1:, :], pb[lvl][:-1, :])
-    st["pbu_p"][0] = st["pbu"][n - 1]
-    st["pbv_p"][0] = st["pbv"][n - 1]
-    for (koff, pl) in ((nn, p),):
-        for k in range(kk):
-            q1 = np.minimum(st["pbu"][n - 1][:, 1:], 0.5 * (pl[k + 1][:, 1:] + pl[k + 1][:, :-1]))
-            q0 = np.minimum(st["pbu"][n - 1][:, 1:], 0.5 * (pl[k][:, 1:] + pl[k][:, :-1]))
-            st["dpu"][k + koff][:, 1:] = np.maximum(0.0, q1 - q0) * iu[:, 1:]
-            q1 = np.minimum(st["pbv"][n - 1][1:, :], 0.5 * (pl[k + 1][1:, :] + pl[k + 1][:-1, :]))
-            q0 = np.minimum(st["pbv"][n - 1][1:, :], 0.5 * (pl[k][1:, :] + pl[k][:-1, :]))
-            st["dpv"][k + koff][1:, :] = np.maximum(0.0, q1 - q0) * iv[1:, :]
-    # level m thicknesses at u/v points from dp(km)
-    pm = np.zeros_like(p)
-    for k in range(kk):
-        pm[k + 1] = pm[k] + dp[k + mm]
-    for k in range(kk):
-        q1 = np.minimum(st["pbu"][m - 1][:, 1:], 0.5 * (pm[k + 1][:, 1:] + pm[k + 1][:, :-1]))
-        q0 = np.minimum(st["pbu"][m - 1][:, 1:], 0.5 * (pm[k][:, 1:] + pm[k][:, :-1]))
-        st["dpu"][k + mm][:, 1:] = np.maximum(0.0, q1 - q0) * iu[:, 1:]
-        q1 = np.minimum(st["pbv"][m - 1][1:, :], 0.5 * (pm[k + 1][1:, :] + pm[k + 1][:-1, :]))
-        q0 = np.minimum(st["pbv"][m - 1][1:, :], 0.5 * (pm[k][1:, :] + pm[k][:-1, :]))
-        st["dpv"][k + mm][1:, :] = np.maximum(0.0, q1 - q0) * iv[1:, :]
-    baclin = case.scalars["baclin"]
-    scp2, scuy, scvx = gr["scp2"][0], gr["scuy"][0], gr["scvx"][0]
-    with np.errstate(invalid="ignore", divide="ignore"):
-        st["umax"][0][:, 1:] = 0.9 * 0.125 * np.minimum(scp2[:, 1:], scp2[:, :-1]) / (scuy[:, 1:] * baclin)
-        st["vmax"][0][1:, :] = 0.9 * 0.125 * np.minimum(scp2[1:, :], scp2[:-1, :]) / (scvx[1:, :] * baclin)
-    for nm in ("umax", "vmax"):
-        st[nm][~np.isfinite(st[nm])] = 0.0
-    synth.fill_halos(prep, {**gr, **st}, names={"p", "pb", "pb_p", "pbu", "pbv", "pbu_p", "pbv_p", "dpu",
-                                                "dpv", "umax", "vmax"})
-    # land points carry zero bottom pressure; keep divisions finite like the model does
-    for nm in ("pbu", "pbv"):
-        a = st[nm]
-        a[a <= 0.0] = 0.0
 
 
 def interior(a, nb=4, halo=0):
