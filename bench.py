@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — simulated years per day of the BLOM hot path on B200 (+ roofline, CPU baseline).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+A "step" is one pass of the hot path (driver.STEP_SEQUENCE, reference call order of
+phy/mod_blom_step.F90:96-227) over one synthetic state of the named grid.
+  value  : SYPD = 86400 / (steps_per_year * t_step), steps_per_year = 365*86400/baclin,
+           state resident in HBM, CUDA-event time on the library stream, max over ranks
+  e2e    : same metric through the public host API with pinned HOST buffers: per step
+           upload of the prognostic state, the step, download of the result (wall clock)
+  roofline: dominant kernel, algorithmic bytes (SURVEY.md §8d word counts) / live CUDA-event
+           duration, against the measured HBM copy peak in MEASURED_PEAKS.json
+  cpu_baseline: the oracle (C++ restatement of the reference, kind "port") timed on a
+           bounded row-band sample of the same grid; the Fortran reference cannot be built in
+           this image (no gfortran/meson/netCDF), see DESIGN.md.
+Multi-GPU (torchrun, one rank per GPU): the global grid is split into j-bands, so the
+total work is fixed -> "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from blom_b200 import synth  # noqa: E402
+from blom_b200.driver import HotPath, available_routines, STEP_SEQUENCE  # noqa: E402
+
+# compulsory 8-byte words moved per interior cell per call (SURVEY.md §8a/§8d, T=2 scalars)
+WORDS = {"advect": 10 + 29, "diffus": 19, "pgforc": 15, "momtum": 29, "tmsmt1": 6, "tmsmt2": 13,
+         "eddtra": 21, "init_fluxes": 6}
+# per-kernel algorithmic words per interior cell per LAUNCH (DESIGN.md "kernels" table)
+KERNEL_WORDS = {
+    "cppm_flux<i>": 10 + 2 + 2,   # R dp,T,S,hel,her,ca,cross-ca,p(2),flux(3)  W dp,T,S,flux(3) -> see DESIGN.md
+    "cppm_flux<j>": 10 + 2 + 2,
+    "cppm_hedges<i>": 4, "cppm_hedges<j>": 4,
+    "advect_flux_area": 10,
+    "diffus_flux": 15, "diffus_update": 10,
+    "pg_dynh_march": 13, "pg_dpuv": 5, "pg_finalize": 4,
+    "tmsmt1_kernel": 6, "tmsmt2_kernel": 13,
+    "zero_fluxes": 6,
+}
+BT_WORDS_PER_SUBSTEP = 53  # 46R + 7W distinct 2-D arrays per substep
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (profiling recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = [float(r[1]) for r in rows]
+        out["sm_mhz"] = float(np.median(sm))
+        out["sm_max_mhz"] = float(rows[0][2])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for k, nm in enumerate(names):
+            if any("Active" in r[5 + k] and "Not" not in r[5 + k] for r in rows):
+                out["reasons"].append(nm)
+        out["samples"] = len(rows)
+        return out
+
+
+def steps_per_year(baclin):
+    return 365.0 * 86400.0 / baclin
+
+
+def sypd(t_step_s, baclin):
+    return 86400.0 / (steps_per_year(baclin) * t_step_s)
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle on a bounded row-band sample of the same grid
+# ------------------------------------------------------------------------------------------
+def oracle_sample(config, routines, steps, warmup, target_rows=None):
+    from oracle.oracle import Oracle, build
+    from blom_b200.lib import time_levels
+    build()
+    itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS[config]
+    # sample = a closed band of `rows` rows, full i extent and all layers, same seed/fields
+    # ~7.5e6 cells per step is ~8 s of one host core per step for the full path
+    rows = target_rows or max(16, min(jtdm, int(7.5e6 // (itdm * kdm))))
+    sreg = nreg if rows == jtdm else (1 if nreg in (1, 2, 3) else 0)
+    syn = synth.Synth(itdm, rows, kdm, sreg, baclin=baclin, batrop=batrop)
+    grid = syn.grid(); state = syn.state(grid)
+    o = Oracle(itdm, rows, kdm, sreg)
+    arrs = {**grid, **state}
+    o.register_all(arrs)
+    scal = syn.scalars(1)
+    o.set_scalars(**scal)
+    synth.fill_halos(o, arrs)
+    o.bigrid("depths")
+    masks = {k: o.get_int(k).reshape(syn.ldj, syn.ldi) for k in ("ip", "iu", "iv", "iq")}
+    synth.derive(grid, state, masks, time_levels(1, kdm), scal, o)
+    o.inieos(); o.numerical_bounds()
+    if "advect" in routines:
+        o.init_cppm()
+
+    def one(nstep):
+        m, n, mm, nn, k1m, k1n = time_levels(nstep, kdm)
+        o.set_scalar("nstep", nstep)
+        for r in routines:
+            if r == "tmsmt1":
+                o.tmsmt1(nn)
+                # same out-of-scope halo refreshes as HotPath.halo_refresh_out_of_scope
+                o.xctilr("u", 1, 2 * kdm, 2, 2, 13); o.xctilr("v", 1, 2 * kdm, 2, 2, 14)
+                for nm, it in (("ubflxs_p", 13), ("vbflxs_p", 14), ("pbu", 3), ("pbv", 4)):
+                    o.xctilr(nm, 1, 2, 2, 2, it)
+                o.xctilr("temp", 1, 2 * kdm, 3, 3, 1); o.xctilr("saln", 1, 2 * kdm, 3, 3, 1)
+            elif r == "tmsmt2":
+                o.tmsmt2(m, mm, nn, k1m)
+            else:
+                getattr(o, r)(m, n, mm, nn, k1m, k1n)
+    ns = 1
+    for _ in range(warmup):
+        one(ns); ns += 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one(ns); ns += 1
+    t = (time.perf_counter() - t0) / max(steps, 1)
+    # scale the sample time to the full grid by cell count
+    scale = (itdm * jtdm * kdm) / float(itdm * rows * kdm)
+    t_full = t * scale
+    sample = (f"{rows} of {jtdm} rows x {itdm} x {kdm} layers (closed band, same seed), {steps} steps after "
+              f"{warmup} warm-up, time scaled by {scale:.2f} to the full grid")
+    return sypd(t_full, baclin), t, sample
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    routines = [r for r in STEP_SEQUENCE if r in available_routines()]
+    v, t, sample = oracle_sample(args.config, routines, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "simulated_years_per_day_hot_path", "value": v, "unit": "SYPD",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": args.config, "routines": routines},
+            "cpu_baseline": {"value": v, "unit": "SYPD", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "SYPD", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "C++ restatement of the reference algorithm (oracle/); the Fortran reference cannot be "
+                    "built in this image (no Fortran compiler, meson or netCDF)"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=os.environ.get("BLOM_BENCH_CONFIG", "tnx1v4"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    def pinned(shape):
+        return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+
+    if world > 1:
+        from blom_b200.lib import load_library
+        import ctypes
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            load_library(False).blomgpu_comm_unique_id(buf)
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().numpy().tobytes())
+
+    t_setup = time.perf_counter()
+    hp = HotPath(args.config, nstep=1, rank=rank, nranks=world, device=local_rank, comm_uid=uid,
+                 pinned_alloc=pinned)
+    g = hp.gpu
+    t_setup = time.perf_counter() - t_setup
+    stream = torch.cuda.ExternalStream(g.stream())
+
+    def barrier():
+        g.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident timing ---------------------------------------------------------
+    for _ in range(args.warmup):
+        hp.advance()
+    barrier()
+    g.launch_count_reset()
+    clocks = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        hp.advance()
+    e1.record(stream)
+    barrier()
+    launches = g.launch_count()
+    t_ms = e0.elapsed_time(e1)
+    tt = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_step = float(tt.item()) / 1e3 / args.steps
+    clk = clocks.stop()
+
+    # ---- end to end through the host API (pinned host buffers, copies inside) ------------
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        hp.upload_inputs()
+        hp.advance()
+        hp.download_outputs()
+    g.sync()
+    w1 = time.perf_counter()
+    te = torch.tensor([(w1 - w0) / args.steps], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te.item())
+    h2d, d2h = hp.io_bytes()
+
+    # ---- per-routine and per-kernel device times (2 extra steps, event pair per launch) ---
+    g.timers_enable(True); g.timers_reset()
+    hp.advance(); hp.advance()
+    g.sync()
+    rt = g.timers()
+    g.timers_enable(False)
+    g.ktimers_enable(True)
+    hp.advance(); hp.advance()
+    kt = g.ktimers()
+    g.ktimers_enable(False)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = peaks()
+    cells_local = hp.itdm * hp.jj * hp.kdm
+    cells2d_local = hp.itdm * hp.jj
+    routines_ms = {k: v["ms"] / v["calls"] for k, v in rt.items() if v["calls"]}
+    ksum = sum(v["ms"] for v in kt.values()) or 1.0
+    # dominant kernel by total device time among kernels with a known algorithmic byte count
+    best = None
+    for name, v in kt.items():
+        if name in KERNEL_WORDS:
+            nbytes = 8.0 * KERNEL_WORDS[name] * cells_local
+        elif name in ("bt_ueq", "bt_veq", "bt_continuity"):
+            nbytes = 8.0 * {"bt_ueq": 23, "bt_veq": 23, "bt_continuity": 7}[name] * cells2d_local
+        else:
+            continue
+        if best is None or v["ms"] > best[1]["ms"]:
+            best = (name, v, nbytes)
+    roof = None
+    if best is not None:
+        name, v, nbytes = best
+        dur = v["ms"] / v["launches"] / 1e3
+        ach = nbytes / dur / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_us": dur * 1e6, "share_of_step": v["ms"] / ksum,
+                "algorithmic_bytes_per_launch": nbytes}
+    # whole-step algorithmic bandwidth
+    lstep = hp.scalars["lstep"]
+    alg_bytes = 8.0 * hp.cells * sum(WORDS.get(r, 0) for r in hp.routines)
+    if "barotp" in hp.routines:
+        alg_bytes += 8.0 * BT_WORDS_PER_SUBSTEP * hp.itdm * hp.jtdm * (5 * lstep // 2)
+    line = {
+        "metric": "simulated_years_per_day_hot_path", "value": sypd(t_step, hp.baclin), "unit": "SYPD",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.config, "grid": [hp.itdm, hp.jtdm, hp.kdm], "nreg": hp.nreg,
+                   "routines": hp.routines, "missing_routines": [r for r in STEP_SEQUENCE if r not in hp.routines],
+                   "barotropic_substeps": 5 * lstep // 2, "parallelism": f"j-bands x{world}",
+                   "cache": "state arrays (>=5 GB at tnx1v4) exceed the 126 MB L2; no flush needed",
+                   "setup_s": round(t_setup, 1)},
+        "e2e": {"value": sypd(t_e2e, hp.baclin), "unit": "SYPD", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": roof,
+        "step_algorithmic_GBps": alg_bytes / t_step / 1e9,
+        "step_frac_of_hbm_peak": alg_bytes / t_step / 1e9 / hbm_peak,
+        "routines_ms": routines_ms,
+        "kernels_ms_per_step": {k: v["ms"] / 2.0 for k, v in sorted(kt.items(), key=lambda kv: -kv[1]["ms"])[:12]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, t, sample = oracle_sample(args.config, hp.routines, 2, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "SYPD", "cores": 1, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

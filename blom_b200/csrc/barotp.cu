@@ -332,9 +332,9 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     P.ub_ml = ub_t + (long)(ml - 1) * L; P.ub_nl = ub_t + (long)(nl - 1) * L;
     P.vb_ml = vb_t + (long)(ml - 1) * L; P.vb_nl = vb_t + (long)(nl - 1) * L;
   };
-  auto range_launch = [&](auto kern, const double* extra, int i0, int i1, int j0, int j1) {
+  auto range_launch = [&](const char* name, auto kern, const double* extra, int i0, int i1, int j0, int j1) {
     dim3 grid(cdiv(i1 - i0 + 1, 128), j1 - j0 + 1);
-    LAUNCH(kern, grid, 128, 0, g, P, extra, i0, i1, j0, j1);
+    LAUNCH_NAMED(name, kern, grid, 128, 0, g, P, extra, i0, i1, j0, j1);
   };
 
   int lll0 = 1, ml = 1, nl = 2;
@@ -363,15 +363,15 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
           dim3 grid(cdiv(g.ii + 3, 128), g.jj + 4);
           LAUNCH(bt_continuity, grid, 128, 0, g, P, -1, g.ii + 1, -1, g.jj + 2);
         }
-        range_launch(bt_ueq, P.vb_ml, 0, g.ii + 1, -1, g.jj + 2);
-        range_launch(bt_veq, P.ub_nl, 0, g.ii, 0, g.jj + 2);
+        range_launch("bt_ueq", bt_ueq, P.vb_ml, 0, g.ii + 1, -1, g.jj + 2);
+        range_launch("bt_veq", bt_veq, P.ub_nl, 0, g.ii, 0, g.jj + 2);
       } else {
         {
           dim3 grid(cdiv(g.ii + 1, 128), g.jj + 2);
           LAUNCH(bt_continuity, grid, 128, 0, g, P, 0, g.ii, 0, g.jj + 1);
         }
-        range_launch(bt_veq, P.ub_ml, 0, g.ii, 1, g.jj + 1);
-        range_launch(bt_ueq, P.vb_nl, 1, g.ii, 1, g.jj);
+        range_launch("bt_veq", bt_veq, P.ub_ml, 0, g.ii, 1, g.jj + 1);
+        range_launch("bt_ueq", bt_ueq, P.vb_nl, 1, g.ii, 1, g.jj);
       }
       std::swap(ml, nl);
     }

@@ -65,6 +65,11 @@ struct Ctx {
   std::map<std::string, double> sc;
   long launches = 0;
   bool timers_on = false;
+  // per-kernel device timers (bench.py roofline leg): one event pair per launch
+  bool ktimers_on = false;
+  struct KEv { const char* name; cudaEvent_t e0, e1; };
+  std::vector<KEv> kev;
+  std::map<std::string, Timer> ktimers;
   std::map<std::string, Timer> timers;
   std::vector<std::string> timer_order;
   void* nccl = nullptr;      // ncclComm_t
@@ -121,12 +126,25 @@ Ctx& C();
   } while (0)
 
 // every kernel launch goes through this so gpu_launches is a real count
-#define LAUNCH(kernel, grid, block, smem, ...)                              \
+#define LAUNCH_NAMED(kname, kernel, grid, block, smem, ...)                 \
   do {                                                                      \
-    kernel<<<(grid), (block), (smem), blom::C().stream>>>(__VA_ARGS__);     \
-    blom::C().launches++;                                                   \
+    blom::Ctx& c_ = blom::C();                                              \
+    cudaEvent_t ke0_ = nullptr, ke1_ = nullptr;                             \
+    if (c_.ktimers_on) {                                                    \
+      cudaEventCreate(&ke0_); cudaEventCreate(&ke1_);                       \
+      cudaEventRecord(ke0_, c_.stream);                                     \
+    }                                                                       \
+    kernel<<<(grid), (block), (smem), c_.stream>>>(__VA_ARGS__);            \
+    if (c_.ktimers_on) {                                                    \
+      cudaEventRecord(ke1_, c_.stream);                                     \
+      c_.kev.push_back(blom::Ctx::KEv{kname, ke0_, ke1_});                  \
+    }                                                                       \
+    c_.launches++;                                                          \
     CUDA_CHECK(cudaGetLastError());                                         \
   } while (0)
+
+#define LAUNCH(kernel, grid, block, smem, ...) \
+  LAUNCH_NAMED(#kernel, kernel, grid, block, smem, __VA_ARGS__)
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 

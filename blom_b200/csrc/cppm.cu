@@ -771,7 +771,7 @@ void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, 
   }
   // NB: the face npass+1 must be covered: tiles cover cells 1..ntile*NOUT >= npass and
   // thread tp = npass+1-p0 <= TP-3 of the last tile owns it.
-  LAUNCH(kern, grid, block, smem, g, second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd,
+  LAUNCH_NAMED(DIR == 0 ? "cppm_flux<i>" : "cppm_flux<j>", kern, grid, block, smem, g, second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd,
          scp2i, tab, sten, flx, tflx, sflx);
 }
 
@@ -792,7 +792,7 @@ void cppm_pass(bool second_pass, int n, int mm, double* dp_src, double* dp_dst, 
   const double* scp2i = c.dev("scp2i");
   {
     dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
-    LAUNCH(cppm_hedges<DIR>, grid, 128, 0, g, second_pass, dp_src, cac, scp2i, tab, hel3, her3);
+    LAUNCH_NAMED(DIR == 0 ? "cppm_hedges<i>" : "cppm_hedges<j>", cppm_hedges<DIR>, grid, 128, 0, g, second_pass, dp_src, cac, scp2i, tab, hel3, her3);
   }
   halo_update(std::vector<HaloReq>{{hel3, g.kdm, halo_ps}, {her3, g.kdm, halo_ps}}, mh, nh);
   if (g.nreg == 2 && g.north) {

@@ -200,6 +200,7 @@ int blomgpu_device_ptr(const char* name, void** dptr, int* nlev) {
 
 int blomgpu_set_option(const char* key, const char* value) { GUARD(C().opt[key] = value) }
 int blomgpu_set_scalar(const char* key, double value) { GUARD(C().sc[key] = value) }
+int blomgpu_get_scalar(const char* key, double* value) { GUARD(*value = C().scalar(key)) }
 
 int blomgpu_xctilr(const char* name, int koff, int l1, int ld, int mh, int nh, int itype) {
   GUARD(
@@ -255,6 +256,31 @@ int blomgpu_timers_get(int cap, char names[][32], double* ms_total, long* calls,
   return n;
 }
 void blomgpu_timers_reset(void) { C().timers.clear(); C().timer_order.clear(); }
+int blomgpu_ktimers_enable(int enable) {
+  Ctx& c = C();
+  c.ktimers_on = enable != 0;
+  if (enable) { c.ktimers.clear(); }
+  return 0;
+}
+int blomgpu_ktimers_get(int cap, char names[][64], double* ms_total, long* launches) {
+  Ctx& c = C();
+  cudaStreamSynchronize(c.stream);
+  for (auto& e : c.kev) {
+    float ms = 0; cudaEventElapsedTime(&ms, e.e0, e.e1);
+    Timer& t = c.ktimers[e.name];
+    t.ms += ms; t.launches++;
+    cudaEventDestroy(e.e0); cudaEventDestroy(e.e1);
+  }
+  c.kev.clear();
+  int n = 0;
+  for (auto& kv : c.ktimers) {
+    if (n >= cap) break;
+    std::snprintf(names[n], 64, "%s", kv.first.c_str());
+    ms_total[n] = kv.second.ms; launches[n] = kv.second.launches;
+    ++n;
+  }
+  return n;
+}
 void* blomgpu_stream(void) { return (void*)C().stream; }
 
 }  // extern "C"

@@ -7,6 +7,4 @@ NOT_YET(momtum_dev(int, int, int, int, int, int), "momtum")
 NOT_YET(eddtra_dev(int, int, int, int, int, int), "eddtra")
 NOT_YET(pbcor1_dev(int, int, int, int, int, int), "pbcor1")
 NOT_YET(pbcor2_dev(int, int, int, int, int, int), "pbcor2")
-NOT_YET(numerical_bounds_dev(), "numerical_bounds")
-NOT_YET(init_fluxes_dev(int, int, int, int, int, int), "init_fluxes")
 }

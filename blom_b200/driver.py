@@ -4,41 +4,50 @@ that this package replaces, on synthetic state.
 `HotPath` owns one BlomGpu tile, builds its band of the synthetic state, and runs
 the reference's call order for the routines on the path:
 
-    tmsmt1 -> eddtra -> advect -> [pbcor1] -> diffus -> pgforc -> momtum
-           -> barotp -> [pbcor2] -> tmsmt2
+    init_fluxes -> tmsmt1 -> [eddtra] -> advect -> [pbcor1] -> diffus -> pgforc
+                -> [momtum] -> barotp -> [pbcor2] -> tmsmt2
 
 Routines that the reference runs in between (ALE regrid, cmnfld2, difest, column
 physics, forcing) are out of scope; the halo refreshes those routines would have
 done for the path (phy/mod_difest.F90:826-831, phy/mod_cmnfld_routines.F90:1171-1172)
-are issued here so that the chain stays valid on device.
+are issued here so that the chain stays valid on device.  Bracketed routines run
+only when this build provides them (`available_routines`).
 """
 from __future__ import annotations
 
 import numpy as np
 
 from . import synth
-from .lib import BlomGpu, time_levels, HALO_PS, HALO_UV, HALO_VV, HALO_US, HALO_VS
+from .lib import (BlomGpu, BlomGpuError, time_levels, HALO_PS, HALO_UV, HALO_VV, HALO_US, HALO_VS)
 
-# routines of one baroclinic step in reference order; each entry:
-# (name, needs six time-level args?)
-STEP_SEQUENCE = ["tmsmt1", "eddtra", "advect", "pbcor1", "diffus", "pgforc", "momtum", "barotp",
-                 "pbcor2", "tmsmt2"]
+# reference order of one baroclinic step (phy/mod_blom_step.F90:96-227)
+STEP_SEQUENCE = ["init_fluxes", "tmsmt1", "eddtra", "advect", "pbcor1", "diffus", "pgforc", "momtum",
+                 "barotp", "pbcor2", "tmsmt2"]
+# prognostic arrays that cross the host<->device boundary in the end-to-end leg
+IO_FIELDS = ("dp", "temp", "saln", "u", "v", "trc")
 
 
 def band(jtdm: int, rank: int, nranks: int):
-    """Contiguous j-band of `rank`: first bands get the remainder rows."""
+    """Contiguous j-band of `rank`: the first bands get the remainder rows."""
     base, rem = divmod(jtdm, nranks)
     jj = base + (1 if rank < rem else 0)
     j0 = rank * base + min(rank, rem)
     return j0, jj
 
 
+def available_routines():
+    """Routines of STEP_SEQUENCE implemented by the loaded library (stubs raise)."""
+    return ["init_fluxes", "tmsmt1", "advect", "diffus", "pgforc", "barotp", "tmsmt2"]
+
+
 class HotPath:
     def __init__(self, config="tnx1v4", *, ntr=0, nstep=1, rank=0, nranks=1, device=0, parity=False,
-                 comm_uid: bytes | None = None, routines=None, seed=20240611, options=None):
+                 comm_uid: bytes | None = None, routines=None, seed=20240611, options=None,
+                 pinned_alloc=None):
         itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS[config]
         self.config, self.kdm, self.ntr = config, kdm, ntr
         self.itdm, self.jtdm, self.nreg = itdm, jtdm, nreg
+        self.baclin = baclin
         self.rank, self.nranks = rank, nranks
         j0, jj = band(jtdm, rank, nranks)
         self.j0, self.jj = j0, jj
@@ -46,6 +55,12 @@ class HotPath:
                                seed=seed)
         self.grid = self.syn.grid()
         self.state = self.syn.state(self.grid)
+        if pinned_alloc is not None:  # e2e leg: prognostic state lives in pinned host memory
+            for nm in IO_FIELDS:
+                if nm in self.state:
+                    buf = pinned_alloc(self.state[nm].shape)
+                    buf[...] = self.state[nm]
+                    self.state[nm] = buf
         self.nstep = nstep
         self.scalars = self.syn.scalars(nstep)
         self.levels = time_levels(nstep, kdm)
@@ -68,23 +83,37 @@ class HotPath:
                      sync_in=lambda names: [g.upload(n) for n in names],
                      sync_out=lambda names: [g.download(n) for n in names])
         g.upload_all()
-        self.routines = list(routines) if routines is not None else self.available_routines()
+        self.routines = [r for r in STEP_SEQUENCE if r in (routines or available_routines())]
         self.setup()
-
-    # which routines this build provides (stubs raise "not implemented")
-    @staticmethod
-    def available_routines():
-        return ["advect"]
 
     def setup(self):
         g = self.gpu
+        g.inieos()
+        g.numerical_bounds()
         if "advect" in self.routines:
             g.init_cppm()
+        g.sync()
+
+    @property
+    def cells(self):
+        """interior (i,j,k) cells of the GLOBAL grid"""
+        return self.itdm * self.jtdm * self.kdm
 
     def set_step(self, nstep):
         self.nstep = nstep
         self.levels = time_levels(nstep, self.kdm)
         self.gpu.set_scalar("nstep", nstep)
+
+    def halo_refresh_out_of_scope(self):
+        """Halo updates that out-of-scope routines (difest, cmnfld2, ALE) issue between the
+        hot-path routines; kept so the on-device chain sees the validity the reference has."""
+        g, kk = self.gpu, self.kdm
+        g.xctilr("u", 1, 2 * kk, 2, 2, HALO_UV)          # phy/mod_difest.F90:826-827
+        g.xctilr("v", 1, 2 * kk, 2, 2, HALO_VV)
+        for nm, it in (("ubflxs_p", HALO_UV), ("vbflxs_p", HALO_VV), ("pbu", HALO_US), ("pbv", HALO_VS)):
+            g.xctilr(nm, 1, 2, 2, 2, it)                 # phy/mod_difest.F90:828-831
+        g.xctilr("temp", 1, 2 * kk, 3, 3, HALO_PS)       # phy/mod_cmnfld_routines.F90:1171-1172
+        g.xctilr("saln", 1, 2 * kk, 3, 3, HALO_PS)
 
     def step(self):
         """One pass of the hot path over the resident state."""
@@ -93,24 +122,29 @@ class HotPath:
         for r in self.routines:
             if r == "tmsmt1":
                 g.tmsmt1(nn)
+                self.halo_refresh_out_of_scope()
             elif r == "tmsmt2":
                 g.tmsmt2(m, mm, nn, k1m)
             else:
                 getattr(g, r)(m, n, mm, nn, k1m, k1n)
 
+    def advance(self):
+        """step() followed by the leap-frog role swap of the time levels."""
+        self.step()
+        self.set_step(self.nstep + 1)
+
     def upload_inputs(self):
-        """Host->device copy of the prognostic state (e2e leg)."""
-        for nm in ("dp", "temp", "saln", "u", "v", "trc"):
+        for nm in IO_FIELDS:
             if nm in self.arrays:
                 self.gpu.upload(nm)
 
     def download_outputs(self):
-        for nm in ("dp", "temp", "saln", "u", "v", "trc"):
+        for nm in IO_FIELDS:
             if nm in self.arrays:
                 self.gpu.download(nm)
 
     def io_bytes(self):
-        b = sum(self.arrays[nm].nbytes for nm in ("dp", "temp", "saln", "u", "v", "trc") if nm in self.arrays)
+        b = sum(self.arrays[nm].nbytes for nm in IO_FIELDS if nm in self.arrays)
         return b, b
 
     def finalize(self):

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "blomgpu_comm_unique_id", "blomgpu_comm_init",
     "blomgpu_register", "blomgpu_register_int", "blomgpu_upload", "blomgpu_download",
     "blomgpu_upload_all", "blomgpu_download_all", "blomgpu_sync", "blomgpu_device_ptr",
-    "blomgpu_set_option", "blomgpu_set_scalar",
+    "blomgpu_set_option", "blomgpu_set_scalar", "blomgpu_get_scalar",
     "blomgpu_xctilr", "blomgpu_xcsum", "blomgpu_xcmax", "blomgpu_xcmin", "blomgpu_chksum",
     "blomgpu_bigrid", "blomgpu_nreg", "blomgpu_init_cppm", "blomgpu_inieos",
     "blomgpu_numerical_bounds", "blomgpu_init_fluxes",
@@ -36,6 +36,7 @@ ABI_SYMBOLS = [
     "blomgpu_pgforc", "blomgpu_momtum", "blomgpu_barotp", "blomgpu_pbcor2", "blomgpu_tmsmt2",
     "blomgpu_launch_count", "blomgpu_launch_count_reset", "blomgpu_timers_enable",
     "blomgpu_timers_get", "blomgpu_timers_reset", "blomgpu_stream",
+    "blomgpu_ktimers_enable", "blomgpu_ktimers_get",
 ]
 
 
@@ -140,6 +141,11 @@ class BlomGpu:
 
     def set_scalar(self, key, value):
         self._ck(self.lib.blomgpu_set_scalar(key.encode(), C.c_double(float(value))))
+
+    def get_scalar(self, key):
+        out = C.c_double()
+        self._ck(self.lib.blomgpu_get_scalar(key.encode(), C.byref(out)))
+        return out.value
 
     def set_scalars(self, **kw):
         for k, v in kw.items():
@@ -252,6 +258,17 @@ class BlomGpu:
         n = self.lib.blomgpu_timers_get(cap, names, ms, calls, launches)
         return {names[i].value.decode(): {"ms": ms[i], "calls": calls[i], "launches": launches[i]}
                 for i in range(n)}
+
+    def ktimers_enable(self, on=True):
+        self.lib.blomgpu_ktimers_enable(1 if on else 0)
+
+    def ktimers(self):
+        cap = 128
+        names = ((C.c_char * 64) * cap)()
+        ms = (C.c_double * cap)()
+        launches = (C.c_long * cap)()
+        n = self.lib.blomgpu_ktimers_get(cap, names, ms, launches)
+        return {names[i].value.decode(): {"ms": ms[i], "launches": launches[i]} for i in range(n)}
 
     def stream(self):
         return self.lib.blomgpu_stream()

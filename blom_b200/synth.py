@@ -84,6 +84,7 @@ class Synth:
         self.land, self.metric = land, metric
         self.ldi, self.ldj = itdm + 2 * nbdy, self.jj + 2 * nbdy
         self._fid = 0
+        self._cubes = {}
         with np.errstate(over="ignore"):
             self._build_geometry()
 
@@ -100,27 +101,50 @@ class Synth:
         nb = self.nb
         return a[..., nb:nb + self.jj, nb:nb + self.itdm]
 
-    def _uniform(self, nlev, fid=None, rows=None):
+    def _hash_uniform(self, nlev, fid):
         """U[0,1) on the band interior, shape (nlev, jj, itdm), keyed on global indices."""
-        if fid is None:
-            self._fid += 1
-            fid = self._fid
-        jg = (np.arange(self.jj, dtype=np.uint64) + np.uint64(self.j0)) if rows is None else rows
+        jg = np.arange(self.jj, dtype=np.uint64) + np.uint64(self.j0)
         ig = np.arange(self.itdm, dtype=np.uint64)
         k = np.arange(nlev, dtype=np.uint64)
         with np.errstate(over="ignore"):
             key = (np.uint64(self.seed) * np.uint64(0x9E3779B97F4A7C15)
                    + np.uint64(fid) * np.uint64(0xD1B54A32D192ED03))
-            x = (key + k[:, None, None] * np.uint64(0x8CB92BA72F3D8DD7)
-                 + jg[None, :, None] * np.uint64(0xA24BAED4963EE407)
+            x = (key + jg[None, :, None] * np.uint64(0xA24BAED4963EE407)
                  + ig[None, None, :] * np.uint64(0x9FB21C651E98DF25))
-            x = _mix(_mix(x))
+            x = _mix(x)                                       # (1, jj, itdm): one hash per column
+            x = _mix(x + k[:, None, None] * np.uint64(0x8CB92BA72F3D8DD7))
         return (x >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
 
+    def _base(self, kind):
+        """Base noise cubes (kdm levels), hashed once; every field is a cheap re-indexing
+        of one of them (still a pure function of global indices)."""
+        if kind not in self._cubes:
+            if kind == "u":
+                self._cubes[kind] = self._hash_uniform(self.kdm, 1)
+            else:
+                u1 = self._hash_uniform(self.kdm, 2)
+                u2 = self._hash_uniform(self.kdm, 3)
+                self._cubes[kind] = np.sqrt(-2.0 * np.log(1.0 - u1)) * np.cos(2.0 * np.pi * u2)
+        return self._cubes[kind]
+
+    def _variant(self, kind, nlev):
+        self._fid += 1
+        f = self._fid
+        base = self._base(kind)
+        reps = -(-nlev // self.kdm)
+        out = []
+        for r in range(reps):
+            sh_i = (f * 37 + r * 101) % self.itdm
+            sh_k = (f * 5 + r * 3) % self.kdm
+            out.append(np.roll(base, (sh_k, sh_i), axis=(0, 2)))
+        a = out[0] if reps == 1 else np.concatenate(out, axis=0)
+        return a[:nlev]
+
+    def _uniform(self, nlev):
+        return self._variant("u", nlev)
+
     def _normal(self, nlev):
-        u1 = self._uniform(nlev)
-        u2 = self._uniform(nlev)
-        return np.sqrt(-2.0 * np.log(1.0 - u1)) * np.cos(2.0 * np.pi * u2)
+        return self._variant("n", nlev)
 
     def _put(self, a, vals):
         self.interior(a)[...] = vals
@@ -361,6 +385,13 @@ class Synth:
         pvq = np.where(pb > 0, latq / np.maximum(pb, 1.0), 0.0)
         st["pvtrop"] = self._put(self.zeros(2), np.stack([pvq, pvq]))
         st["pvtrop_o"] = self._put(self.zeros(1), pvq)
+        # --- momentum: bounds filled by numerical_bounds, non-local momentum flux profile
+        st["difmxp"] = self.zeros(1)
+        st["difmxq"] = self.zeros(1)
+        prof = np.clip(1.0 - np.arange(kk + 1) / max(3.0, 0.15 * kk), 0.0, 1.0)[:, None, None]
+        st["mu_nonloc"] = self._put(self.zeros(kk + 1), prof * ium)
+        st["mv_nonloc"] = self._put(self.zeros(kk + 1), prof * ivm)
+        st["ustarb"] = self.zeros(1)
         st["utotn"] = self._put(self.zeros(1), 1.0e-6 * self._normal(1) * ium)
         st["vtotn"] = self._put(self.zeros(1), 1.0e-6 * self._normal(1) * ivm)
         return st

@@ -63,6 +63,8 @@ int blomgpu_device_ptr(const char* name, void** dptr, int* nlev);
  *      ltedtp, ...; scalars: baclin, batrop, delt1, dlt, lstep, nstep, ... */
 int blomgpu_set_option(const char* key, const char* value);
 int blomgpu_set_scalar(const char* key, double value);
+/* read back a scalar (e.g. btdtmx estimated by numerical_bounds) */
+int blomgpu_get_scalar(const char* key, double* value);
 
 /* ---- mod_xc (serial/MPI comm layer) ------------------------------------ */
 /* xctilr(a(1-nbdy,1-nbdy,koff),l1,ld,mh,nh,itype)  phy/mod_xc.F90:2342,4222 */
@@ -110,6 +112,10 @@ int blomgpu_timers_enable(int enable);
 /* writes up to cap entries; returns number of routines with samples */
 int blomgpu_timers_get(int cap, char names[][32], double* ms_total, long* calls, long* launches);
 void blomgpu_timers_reset(void);
+/* per-kernel device timers: one CUDA-event pair around every launch while enabled
+ * (used by bench.py to time the dominant kernel live for the roofline figure). */
+int blomgpu_ktimers_enable(int enable);
+int blomgpu_ktimers_get(int cap, char names[][64], double* ms_total, long* launches);
 /* the CUDA stream (cudaStream_t) all kernels are launched on */
 void* blomgpu_stream(void);
 

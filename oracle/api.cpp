@@ -22,6 +22,7 @@ void eddtra(int, int, int, int, int, int);
 void numerical_bounds();
 void pbcor1(int, int, int, int, int, int);
 void pbcor2(int, int, int, int, int, int);
+void init_fluxes(int, int, int, int, int, int);
 }
 
 static char g_err[1024] = "";
@@ -120,6 +121,10 @@ int oracle_tmsmt2(int m, int mm, int nn, int k1m) { GUARD(orc::tmsmt2(m, mm, nn,
 int oracle_pgforc(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::pgforc(m, n, mm, nn, k1m, k1n)) }
 
 int oracle_barotp(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::barotp(m, n, mm, nn, k1m, k1n)) }
+
+int oracle_numerical_bounds() { GUARD(orc::numerical_bounds()) }
+int oracle_init_fluxes(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::init_fluxes(m, n, mm, nn, k1m, k1n)) }
+double oracle_get_scalar(const char* k) { return orc::O().scalar(k, 0.0); }
 
 // scalar access to the EOS restatement for the unit checks in tests/test_oracle_ops.py
 int oracle_eos(const char* fn, const double* a, double* out) {

@@ -86,6 +86,10 @@ class Oracle:
     def set_scalar(self, key, value):
         self._ck(self.lib.oracle_set_scalar(key.encode(), C.c_double(float(value))))
 
+    def get_scalar(self, key):
+        self.lib.oracle_get_scalar.restype = C.c_double
+        return self.lib.oracle_get_scalar(key.encode())
+
     def set_scalars(self, **kw):
         for k, v in kw.items():
             self.set_scalar(k, v)
