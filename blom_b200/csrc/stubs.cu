@@ -3,7 +3,6 @@
 #include "common.cuh"
 namespace blom {
 #define NOT_YET(sig, what) void sig { throw std::runtime_error("blomgpu: " what " is not implemented in this build"); }
-NOT_YET(momtum_dev(int, int, int, int, int, int), "momtum")
 NOT_YET(eddtra_dev(int, int, int, int, int, int), "eddtra")
 NOT_YET(pbcor1_dev(int, int, int, int, int, int), "pbcor1")
 NOT_YET(pbcor2_dev(int, int, int, int, int, int), "pbcor2")

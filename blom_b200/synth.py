@@ -392,6 +392,12 @@ class Synth:
         st["mu_nonloc"] = self._put(self.zeros(kk + 1), prof * ium)
         st["mv_nonloc"] = self._put(self.zeros(kk + 1), prof * ivm)
         st["ustarb"] = self.zeros(1)
+        st["absvor"] = self.zeros(2 * kk)
+        st["dpvor"] = self.zeros(2 * kk)
+        # hybrid coordinate: dpuold/dpvold come from the (out-of-scope) ALE step; any positive
+        # thickness-like field exercises the velocity time filter
+        self.interior(st["dpuold"])[:] = 0.5 * (dpn + np.roll(dpn, 1, axis=2)) * ium
+        self.interior(st["dpvold"])[:] = 0.5 * (dpn + np.roll(dpn, 1, axis=1)) * ivm
         st["utotn"] = self._put(self.zeros(1), 1.0e-6 * self._normal(1) * ium)
         st["vtotn"] = self._put(self.zeros(1), 1.0e-6 * self._normal(1) * ivm)
         return st
@@ -402,7 +408,11 @@ class Synth:
         dlt = self.baclin / lstep
         return {"baclin": self.baclin, "batrop": self.batrop, "lstep": lstep, "dlt": dlt,
                 "delt1": 2.0 * self.baclin, "nstep": nstep, "pref": 2000.0 * ONEM / 9.806 * 9.806,
-                "cwbdts": 5.0e-5, "cwbdls": 25.0}
+                "cwbdts": 5.0e-5, "cwbdls": 25.0,
+                # momentum dissipation / bottom friction (namelist LIMITS, tests/fuk95/limits:144-155;
+                # biharmonic terms switched on so that every branch of momtum is exercised)
+                "mdv2hi": 0.1, "mdv2lo": 0.05, "mdv4hi": 0.01, "mdv4lo": 0.005, "vsc2hi": 0.2, "vsc2lo": 0.15,
+                "vsc4hi": 0.06, "vsc4lo": 0.05, "cbar": 0.05, "cb": 0.002}
 
 
 def fill_halos(backend, arrays: dict, nbdy=4, names=None):

@@ -117,3 +117,45 @@ def test_barotp_perf_build_and_bad_option():
             g.barotp(*c.levels)
     finally:
         g.finalize()
+
+
+MT_FIELDS = ["u", "v", "utotn", "vtotn", "pu", "pv", "ustarb"]
+
+
+@pytest.mark.parametrize("cfg,mommth,vcoord", [("tiny0", "enscon", "cntiso_hybrid"), ("tiny1", "enecon", "cntiso_hybrid"),
+                                               ("tiny2", "enscon", "cntiso_hybrid"), ("tiny2", "enedis", "isopyc_bulkml"),
+                                               ("tiny3", "enedis", "cntiso_hybrid"), ("tiny4", "enscon", "isopyc_bulkml"),
+                                               ("fuk95", "enscon", "cntiso_hybrid")])
+def test_momtum(cfg, mommth, vcoord):
+    """tolerance 1e-11 of the field max-norm (parity build): one sqrt-heavy routine, ~300 flops/cell"""
+    c, o, g = pair(cfg, ntr=0, opts={"mommth": mommth, "vcoord": vcoord})
+    try:
+        for b in (o, g):
+            b.numerical_bounds()
+            b.pgforc(*c.levels)
+            b.momtum(*c.levels)
+        check(g, o, MT_FIELDS, 1e-11)
+        check(g, o, ["p"], 1e-15, halo=1)
+        kk = c.dims[2]
+        g.download_all()
+        iq = interior(c.masks["iq"]) == 1
+        for nm in ("absvor", "dpvor"):
+            a, b = interior(g.arrays[nm][:kk])[:, iq], interior(o.arrays[nm][:kk])[:, iq]
+            assert max_rel_err(a, b) <= 1e-11, nm
+        assert np.abs(interior(g.arrays["u"]) - interior(c.state["u"])).max() > 1e-4
+        # second call: module work arrays / stale halos carry over identically
+        for b in (o, g):
+            b.momtum(*c.levels)
+        check(g, o, MT_FIELDS, 1e-10)
+    finally:
+        g.finalize()
+
+
+def test_momtum_perf_build():
+    c, o, g = pair("tiny2", ntr=0, parity=False)
+    try:
+        for b in (o, g):
+            b.numerical_bounds(); b.pgforc(*c.levels); b.momtum(*c.levels)
+        check(g, o, MT_FIELDS, 1e-9)
+    finally:
+        g.finalize()
