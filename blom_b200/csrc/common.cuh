@@ -79,6 +79,14 @@ struct Ctx {
   double* halo_send[2] = {nullptr, nullptr};  // [0]=to south, [1]=to north
   double* halo_recv[2] = {nullptr, nullptr};
   size_t halo_cap = 0;
+  // device-raised fatal conditions (the reference's "print + xchalt"): kernels
+  // atomicMax a code into this mapped pinned word; check_errors() reports it at
+  // the next sync / download.
+  int* err_host = nullptr;
+  int* err_devptr = nullptr;
+  std::string error_source;
+  int* error_flag();
+  void check_errors();
 
   double* dev(const std::string& n) const {
     auto it = f.find(n);

@@ -29,6 +29,24 @@ int* Ctx::owned_int(const std::string& n, int nlev) {
   return fd.d;
 }
 
+int* Ctx::error_flag() {
+  if (!err_host) {
+    CUDA_CHECK(cudaHostAlloc(&err_host, sizeof(int), cudaHostAllocMapped));
+    *err_host = 0;
+    CUDA_CHECK(cudaHostGetDevicePointer(&err_devptr, err_host, 0));
+  }
+  return err_devptr;
+}
+// call after the stream has been synchronised
+void Ctx::check_errors() {
+  if (err_host && *err_host != 0) {
+    const int code = *err_host;
+    *err_host = 0;
+    throw std::runtime_error("blomgpu: device-side fatal condition, code " + std::to_string(code) + " " +
+                             error_source);
+  }
+}
+
 ScopedTimer::ScopedTimer(const char* n) : name(n), on(C().timers_on) {
   if (!on) return;
   l0 = C().launches;
@@ -94,6 +112,7 @@ static void do_finalize() {
   for (auto& kv : c.fi) if (kv.second.d) cudaFree(kv.second.d);
   if (c.d_red) cudaFree(c.d_red);
   if (c.h_red) cudaFreeHost(c.h_red);
+  if (c.err_host) cudaFreeHost(c.err_host);
   for (int s = 0; s < 2; ++s) {
     if (c.halo_send[s]) cudaFree(c.halo_send[s]);
     if (c.halo_recv[s]) cudaFree(c.halo_recv[s]);
@@ -148,6 +167,7 @@ static void do_copy_all(bool up) {
   for (auto& kv : c.f) if (kv.second.h) do_copy(kv.first.c_str(), up);
   for (auto& kv : c.fi) if (kv.second.h) do_copy(kv.first.c_str(), up);
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  c.check_errors();
 }
 
 static const int* mask_for_itype(int itype) {
@@ -182,10 +202,10 @@ int blomgpu_finalize(void) { GUARD(do_finalize()) }
 int blomgpu_register(const char* name, double* host, int nlev) { GUARD(do_register(name, host, nlev)) }
 int blomgpu_register_int(const char* name, int* host, int nlev) { GUARD(do_register_int(name, host, nlev)) }
 int blomgpu_upload(const char* name) { GUARD(do_copy(name, true)) }
-int blomgpu_download(const char* name) { GUARD(do_copy(name, false); CUDA_CHECK(cudaStreamSynchronize(C().stream))) }
+int blomgpu_download(const char* name) { GUARD(do_copy(name, false); CUDA_CHECK(cudaStreamSynchronize(C().stream)); C().check_errors()) }
 int blomgpu_upload_all(void) { GUARD(do_copy_all(true)) }
 int blomgpu_download_all(void) { GUARD(do_copy_all(false)) }
-int blomgpu_sync(void) { GUARD(CUDA_CHECK(cudaStreamSynchronize(C().stream))) }
+int blomgpu_sync(void) { GUARD(CUDA_CHECK(cudaStreamSynchronize(C().stream)); C().check_errors()) }
 int blomgpu_device_ptr(const char* name, void** dptr, int* nlev) {
   GUARD(
     Ctx& c = C();

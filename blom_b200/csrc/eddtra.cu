@@ -1,0 +1,321 @@
+// Eddy-induced transport for the hybrid coordinate: eddtra -> eddtra_ale
+// (phy/mod_eddtra.F90:1808-1928, :1001-1739; rmeanfilt :121-151), eitmth='gm',
+// mlrmth none|fox08|bod23.
+//
+// B200 design: the reference walks j rows and, per face, a column loop with a
+// data-dependent iterative limiter.  Here one thread owns one face column with
+// i across lanes, so every level access `a[x + k*lev]` is a coalesced row
+// segment; the interface work arrays live in thread-local memory (interleaved
+// by the hardware, i.e. also coalesced).  The depth-invariant submesoscale
+// factor (upssmx/upssmy), the face top pressure (ptu/ptv) and the heat/salt
+// flux diagnosis of `eddtra` are fused into the column kernel, so the 2-D
+// temporaries of the reference never exist and temp/saln(km) are read once.
+// Fatal conditions of the reference (no convergence after 1000 sweeps, the
+// '>'/'<' consistency checks) raise a device error flag that the next
+// blomgpu_sync/download reports, matching "print + xchalt".
+#include "common.cuh"
+#include "eos.cuh"
+
+namespace blom {
+
+namespace {
+
+constexpr int KM = 64;  // compile-time bound on kdm for the thread-local interface arrays
+
+__device__ __forceinline__ void rmeanfilt(double& filtered, double signal, double wg, double wd) {
+  const double wf = signal >= filtered ? wg : wd;
+  filtered = wf * filtered + (1. - wf) * signal;
+}
+
+struct MlParams {
+  int mode;  // 0 none, 1 fox08, 2 bod23
+  double wg_hbl, wd_hbl, wg_hml, wd_hml, mstar, nstar, wpup_min, mlbl_max_ratio;
+  double csm, rtau, lfmin, dbcl82;
+};
+
+// running-mean filters of the boundary/mixed layer depths (:1054-1101)
+__global__ void eddtra_mlfilter(Geom g, MlParams P, const int* __restrict__ ip,
+                                const double* __restrict__ OBLdepth, const double* __restrict__ mld,
+                                const double* __restrict__ ustar3, const double* __restrict__ wstar3,
+                                double* __restrict__ hbl_tf, double* __restrict__ wpup_tf,
+                                double* __restrict__ hml_tf1, double* __restrict__ hml_tf,
+                                double* __restrict__ hml_tfbnd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j);
+  if (ip[x] != 1) return;
+  double hb = hbl_tf[x], h1 = hml_tf1[x], h = hml_tf[x];
+  rmeanfilt(hb, OBLdepth[x], P.wg_hbl, P.wd_hbl);
+  if (P.mode == 2) {
+    double w = wpup_tf[x];
+    const double wpup = fmax(P.wpup_min, pow(P.mstar * ustar3[x] + P.nstar * wstar3[x], 2. / 3.));
+    rmeanfilt(w, wpup, P.wg_hbl, P.wd_hbl);
+    wpup_tf[x] = w;
+  }
+  rmeanfilt(h1, mld[x], P.wg_hbl, P.wd_hbl);
+  rmeanfilt(h, h1, P.wg_hml, P.wd_hml);
+  hbl_tf[x] = hb; hml_tf1[x] = h1; hml_tf[x] = h;
+  hml_tfbnd[x] = fmin(h, P.mlbl_max_ratio * hb);
+}
+
+// vertically averaged mixed layer potential density (:1105-1127)
+__global__ void eddtra_mldens(Geom g, eos::Coef ec, int nn, const int* __restrict__ ip,
+                              const double* __restrict__ p, const double* __restrict__ dp,
+                              const double* __restrict__ temp, const double* __restrict__ saln,
+                              const double* __restrict__ hml_tfbnd, double* __restrict__ util1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j);
+  if (ip[x] != 1) return;
+  const int kk = g.kdm;
+  const double p1 = p[x];
+  const double pml = fmin(p1 + hml_tfbnd[x] * onem, p[x + (long)kk * g.lev]);
+  const double dpmli = 1. / (pml - p1);
+  double tmldp = 0., smldp = 0., pk = p1;
+  for (int k = 1; k <= kk; ++k) {
+    const long xn = x + (long)(k + nn - 1) * g.lev;
+    const double pk1 = p[x + (long)k * g.lev];
+    if (pk1 < pml) {
+      const double d = dp[xn];
+      tmldp = tmldp + temp[xn] * d;
+      smldp = smldp + saln[xn] * d;
+    } else {
+      tmldp = tmldp + temp[xn] * (pml - pk);
+      smldp = smldp + saln[xn] * (pml - pk);
+      break;
+    }
+    pk = pk1;
+  }
+  util1[x] = eos::sig0(ec, tmldp * dpmli, smldp * dpmli);
+}
+
+// One thread per face column.  DIR 0: u faces (minus point i-1), DIR 1: v faces (j-1).
+template <int DIR>
+__global__ void __launch_bounds__(128)
+eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int* __restrict__ mask,
+              const double* __restrict__ p, const double* __restrict__ dp, const double* __restrict__ dpf,
+              const double* __restrict__ temp, const double* __restrict__ saln,
+              const double* __restrict__ difint, const double* __restrict__ nslp,
+              const double* __restrict__ pbf, const double* __restrict__ sc2, const double* __restrict__ scl,
+              const double* __restrict__ scp2, const double* __restrict__ coriop,
+              const double* __restrict__ hbl_tf, const double* __restrict__ wpup_tf,
+              const double* __restrict__ hml_tfbnd, const double* __restrict__ util1,
+              double* __restrict__ mfltd, double* __restrict__ mflsm_o, double* __restrict__ tfltd,
+              double* __restrict__ tflsm, double* __restrict__ sfltd, double* __restrict__ sflsm,
+              int* __restrict__ err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j);
+  if (mask[x] != 1) return;
+  const long xm = x - (DIR == 0 ? 1 : g.ldi);
+  const long lev = g.lev;
+  const int kk = g.kdm;
+  const double ffac = .0625, fface = .99 * ffac, eps = 1.e-14, c5_21 = 5. / 21.;
+
+  double puv[KM + 2], mflgm[KM + 2], mflsm[KM + 2], dlm[KM + 1], dlp[KM + 1];
+  double* mfl = puv;  // puv is dead once the interface fluxes are built
+
+  const double hml = .5 * (hml_tfbnd[xm] + hml_tfbnd[x]);
+  // depth-invariant submesoscale transport component (:1130-1185)
+  double upssm = 0.;
+  if (P.mode == 2) {
+    const double hbl = .5 * (hbl_tf[xm] + hbl_tf[x]);
+    const double absf = .5 * fabs(coriop[xm] + coriop[x]);
+    const double wpup = .5 * (wpup_tf[xm] + wpup_tf[x]);
+    const double drho = util1[x] - util1[xm];
+    upssm = P.csm * absf * hbl * hml * hml * drho / wpup;
+  } else if (P.mode == 1) {
+    const double f = .5 * (coriop[xm] + coriop[x]);
+    const double absfi = 1. / sqrt(f * f + P.rtau * P.rtau);
+    const double lfi = 1. / fmax(sqrt(P.dbcl82 * hml) * absfi, P.lfmin);
+    const double drho = util1[x] - util1[xm];
+    upssm = P.csm * hml * hml * drho * lfi * absfi;
+  }
+  const double ptf = fmax(p[xm], p[x]);
+  const double mfleps = eps * epsilp * sc2[x];
+  const double et2mf = -grav * rho0 * delt1 * scl[x];
+  const double pb = pbf[x + (long)(n - 1) * lev];
+
+  int kmax = 1;
+  puv[1] = ptf;
+  for (int k = 1; k <= kk; ++k) {
+    const long o = (long)(k + nn - 1) * lev;
+    puv[k + 1] = puv[k] + dpf[x + o];
+    if (dp[xm + o] > epsilp || dp[x + o] > epsilp) kmax = k;
+  }
+  const double pml = fmin(puv[1] + hml * onem, puv[kmax + 1]);
+  const double dpmli = 1. / (pml - puv[1]);
+  int kml = kmax + 1;
+  for (int k = kmax; k >= 2; --k) {
+    if (puv[k] > pml) kml = k; else break;
+  }
+  for (int k = kml; k <= kmax; ++k) {
+    const long o1 = (long)(k - 2) * lev, o2 = (long)(k - 1) * lev;
+    const double kappa = .25 * (difint[xm + o1] + difint[x + o1] + difint[xm + o2] + difint[x + o2]);
+    mflgm[k] = -kappa * nslp[x + o2] * et2mf;
+  }
+  mflgm[kmax + 1] = 0.;
+  mflgm[1] = 0.;
+  mflsm[1] = 0.;
+  for (int k = 2; k <= kml - 1; ++k) {
+    mflgm[k] = mflgm[kml] * (puv[k] - puv[1]) * dpmli;
+    double q = 2. * (puv[1] - puv[k]) * dpmli + 1.;
+    q = q * q;
+    mflsm[k] = -upssm * (1. - q) * (1. + c5_21 * q) * et2mf;
+  }
+  for (int k = kml; k <= kmax + 1; ++k) mflsm[k] = 0.;
+  for (int k = 1; k <= kmax + 1; ++k) mfl[k] = mflgm[k] + mflsm[k];
+  {
+    double pm0 = p[xm], pp0 = p[x];
+    for (int k = 1; k <= kmax; ++k) {
+      const double pm1 = p[xm + (long)k * lev], pp1 = p[x + (long)k * lev];
+      dlm[k] = fmax(0., fmin(pm1, pb) - fmax(pm0, ptf));
+      dlp[k] = fmax(0., fmin(pp1, pb) - fmax(pp0, ptf));
+      pm0 = pm1; pp0 = pp1;
+    }
+  }
+  const double am = scp2[xm], ap = scp2[x];
+
+  // alternate downward/upward limiter sweeps (:1318-1394)
+  bool changed = true;
+  int niter = 0, kdir = 1;
+  while (changed) {
+    niter++;
+    if (niter == 1000) { atomicMax(err, 1); break; }
+    changed = false;
+    kdir = -kdir;
+    const int k0 = (1 + kdir + (1 - kdir) * kmax) / 2;
+    for (int s = 0, k = k0; s < kmax; ++s, k += kdir) {
+      const double lo = mfl[k], hi = mfl[k + 1];
+      if (fabs(hi - lo) > fmax(mfleps, eps * fabs(hi + lo))) {
+        if (hi - lo > ffac * fmax(epsilp, dlm[k]) * am) {
+          const double q = fface * dlm[k] * am;
+          if (hi > -lo) {
+            if (lo > -.5 * q) mfl[k + 1] = lo + q;
+            else { mfl[k + 1] = .5 * q; mfl[k] = -mfl[k + 1]; }
+          } else {
+            if (hi < .5 * q) mfl[k] = hi - q;
+            else { mfl[k] = -.5 * q; mfl[k + 1] = -mfl[k]; }
+          }
+          changed = true;
+        } else if (hi - lo < -ffac * fmax(epsilp, dlp[k]) * ap) {
+          const double q = fface * dlp[k] * ap;
+          if (hi < -lo) {
+            if (lo < .5 * q) mfl[k + 1] = lo - q;
+            else { mfl[k + 1] = -.5 * q; mfl[k] = -mfl[k + 1]; }
+          } else {
+            if (hi > -.5 * q) mfl[k] = hi + q;
+            else { mfl[k] = .5 * q; mfl[k + 1] = -mfl[k]; }
+          }
+          changed = true;
+        }
+      }
+    }
+  }
+
+  // split the limited total back into GM and submesoscale parts (:1398-1436)
+  for (int k = 1; k <= kmax + 1; ++k) {
+    const double f = mfl[k];
+    double gm = mflgm[k], sm = mflsm[k];
+    if (fabs(f) < mfleps) {
+      mfl[k] = 0.; gm = 0.; sm = 0.;
+    } else if (f > 0.) {
+      if (gm > sm) {
+        if (f > 2. * sm) gm = f - sm; else { gm = .5 * f; sm = gm; }
+      } else {
+        if (f > 2. * gm) sm = f - gm; else { sm = .5 * f; gm = sm; }
+      }
+    } else {
+      if (gm < sm) {
+        if (f < 2. * sm) gm = f - sm; else { gm = .5 * f; sm = gm; }
+      } else {
+        if (f < 2. * gm) sm = f - gm; else { sm = .5 * f; gm = sm; }
+      }
+    }
+    mflgm[k] = gm; mflsm[k] = sm;
+  }
+
+  // layer fluxes + heat/salt components (:1442-1468, :1876-1902)
+  for (int k = 1; k <= kk; ++k) {
+    const long xk = x + (long)(k + mm - 1) * lev, xmk = xm + (long)(k + mm - 1) * lev;
+    double fgm = 0., fsm = 0.;
+    if (k <= kmax) {
+      if (fabs(mfl[k + 1] - mfl[k]) > fmax(mfleps, eps * fabs(mfl[k + 1] + mfl[k]))) {
+        fgm = mflgm[k + 1] - mflgm[k];
+        fsm = mflsm[k + 1] - mflsm[k];
+      }
+      if (fgm + fsm > ffac * fmax(epsilp, dlm[k]) * am) atomicMax(err, 2);
+      if (fgm + fsm < -ffac * fmax(epsilp, dlp[k]) * ap) atomicMax(err, 3);
+    }
+    const double qt = .5 * (temp[xmk] + temp[xk]);
+    const double qs = .5 * (saln[xmk] + saln[xk]);
+    mfltd[xk] = fgm; mflsm_o[xk] = fsm;
+    tfltd[xk] = fgm * qt; tflsm[xk] = fsm * qt;
+    sfltd[xk] = fgm * qs; sflsm[xk] = fsm * qs;
+  }
+}
+
+}  // namespace
+
+void eddtra_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
+  (void)m; (void)k1m; (void)k1n;
+  Ctx& c = C(); const Geom& g = c.g;
+  if (c.option("vcoord", "cntiso_hybrid") == "isopyc_bulkml")
+    throw std::runtime_error("(eddtra) vcoord = 'isopyc_bulkml' is not implemented in this build");
+  if (c.option("eitmth", "gm") != "gm")
+    throw std::runtime_error("(eddtra) eitmth_opt is unsupported for vcoord = 'cntiso_hybrid'!");
+  if (g.kdm > KM) throw std::runtime_error("eddtra: kdm exceeds the compiled column bound (64)");
+  const std::string mlrmth = c.option("mlrmth", "fox08");
+  const double delt1 = c.scalar("delt1");
+  MlParams P{};
+  if (mlrmth == "none") P.mode = 0;
+  else if (mlrmth == "fox08") P.mode = 1;
+  else if (mlrmth == "bod23") P.mode = 2;
+  else throw std::runtime_error(" init_eddtra: mlrmth = " + mlrmth + " is unsupported!");
+  // namelist defaults, phy/mod_eddtra.F90:54-98; dbcl82 phy/mod_cmnfld.F90:48
+  const double ce = c.scalar("ce", .06), cl = c.scalar("cl", .25), tau_mlr = c.scalar("tau_mlr", 86400.);
+  const double tg_hbl = c.scalar("tau_growing_hbl", 300.), td_hbl = c.scalar("tau_decaying_hbl", 86400.);
+  const double tg_hml = c.scalar("tau_growing_hml", 3600.), td_hml = c.scalar("tau_decaying_hml", 259200.);
+  P.wg_hbl = tg_hbl / (tg_hbl + delt1); P.wd_hbl = td_hbl / (td_hbl + delt1);
+  P.wg_hml = tg_hml / (tg_hml + delt1); P.wd_hml = td_hml / (td_hml + delt1);
+  P.mstar = c.scalar("mstar", .5); P.nstar = c.scalar("nstar", .066);
+  P.wpup_min = c.scalar("wpup_min", 1.e-3); P.mlbl_max_ratio = c.scalar("mlbl_max_ratio", 3.);
+  P.lfmin = c.scalar("lfmin", 5.e3); P.dbcl82 = c.scalar("dbcl82", .0003);
+  P.rtau = 1. / tau_mlr;
+  P.csm = P.mode == 2 ? grav * alpha0 * ce / cl : grav * alpha0 * ce;
+
+  double* hml_tfbnd = c.has("hml_tfbnd") ? c.dev("hml_tfbnd") : c.owned("hml_tfbnd", 1);
+  double *hbl_tf = nullptr, *wpup_tf = nullptr, *util1 = nullptr, *coriop = nullptr;
+  dim3 grid2(cdiv(g.ii, 128), g.jj);
+  if (P.mode != 0) {
+    hbl_tf = c.dev("hbl_tf");
+    wpup_tf = P.mode == 2 ? c.dev("wpup_tf") : hbl_tf;
+    util1 = c.dev("util1");
+    coriop = c.dev("coriop");
+    const double* u3 = P.mode == 2 ? c.dev("ustar3") : hbl_tf;
+    const double* w3 = P.mode == 2 ? c.dev("wstar3") : hbl_tf;
+    LAUNCH(eddtra_mlfilter, grid2, 128, 0, g, P, c.idev("ip"), c.dev("OBLdepth"), c.dev("mld"), u3, w3, hbl_tf,
+           wpup_tf, c.dev("hml_tf1"), c.dev("hml_tf"), hml_tfbnd);
+    if (P.mode == 2)
+      halo_update(std::vector<HaloReq>{{hbl_tf, 1, halo_ps}, {wpup_tf, 1, halo_ps}, {hml_tfbnd, 1, halo_ps}}, 1, 1);
+    else
+      halo_update(hml_tfbnd, 1, 1, 1, halo_ps);
+    LAUNCH(eddtra_mldens, grid2, 128, 0, g, eos::host_coef(), nn, c.idev("ip"), c.dev("p"), c.dev("dp"),
+           c.dev("temp"), c.dev("saln"), hml_tfbnd, util1);
+    halo_update(util1, 1, 1, 1, halo_ps);
+  }
+  int* err = c.error_flag();
+  LAUNCH_NAMED("eddtra_column<u>", eddtra_column<0>, grid2, 128, 0, g, P, n, mm, nn, delt1, c.idev("iu"),
+               c.dev("p"), c.dev("dp"), c.dev("dpu"), c.dev("temp"), c.dev("saln"), c.dev("difint"),
+               c.dev("nslpx"), c.dev("pbu"), c.dev("scu2"), c.dev("scuy"), c.dev("scp2"), coriop, hbl_tf, wpup_tf,
+               hml_tfbnd, util1, c.dev("umfltd"), c.dev("umflsm"), c.dev("utfltd"), c.dev("utflsm"),
+               c.dev("usfltd"), c.dev("usflsm"), err);
+  LAUNCH_NAMED("eddtra_column<v>", eddtra_column<1>, grid2, 128, 0, g, P, n, mm, nn, delt1, c.idev("iv"),
+               c.dev("p"), c.dev("dp"), c.dev("dpv"), c.dev("temp"), c.dev("saln"), c.dev("difint"),
+               c.dev("nslpy"), c.dev("pbv"), c.dev("scv2"), c.dev("scvx"), c.dev("scp2"), coriop, hbl_tf, wpup_tf,
+               hml_tfbnd, util1, c.dev("vmfltd"), c.dev("vmflsm"), c.dev("vtfltd"), c.dev("vtflsm"),
+               c.dev("vsfltd"), c.dev("vsflsm"), err);
+  c.error_source = "(eddtra_ale) 1: no convergence, 2: flux exceeds +ffac*mass, 3: flux exceeds -ffac*mass";
+}
+
+}  // namespace blom

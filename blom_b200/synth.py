@@ -37,6 +37,8 @@ ITYPE = {
     "dp": HALO_PS, "temp": HALO_PS, "saln": HALO_PS, "sigma": HALO_PS, "p": HALO_PS, "phi": HALO_PS,
     "pb": HALO_PS, "pb_p": HALO_PS, "sealv": HALO_PS, "trc": HALO_PS, "difint": HALO_PS,
     "difiso": HALO_PS, "difwgt": HALO_PS, "coriop": HALO_PS, "pbath": HALO_PS,
+    "hbl_tf": HALO_PS, "wpup_tf": HALO_PS, "hml_tf1": HALO_PS, "hml_tf": HALO_PS, "hml_tfbnd": HALO_PS,
+    "ustar3": HALO_PS, "wstar3": HALO_PS, "util1": HALO_PS,
     "dpold": HALO_PS, "told": HALO_PS, "sold": HALO_PS, "trcold": HALO_PS, "pb_mn": HALO_PS, "mld": HALO_PS, "OBLdepth": HALO_PS,
     # u-points
     "scux": HALO_US, "scuy": HALO_US, "scu2": HALO_US, "scuxi": HALO_US, "scuyi": HALO_US,
@@ -348,6 +350,18 @@ class Synth:
         st["difwgt"] = self._put(self.zeros(1), self._uniform(1))
         st["nslpx"] = self._put(self.zeros(kk), 1.0e-4 * self._normal(kk) * ium)
         st["nslpy"] = self._put(self.zeros(kk), 1.0e-4 * self._normal(kk) * ivm)
+        # --- eddy-induced transport: boundary/mixed layer inputs from the (out-of-scope) column
+        # physics and the running-mean filter state of mod_eddtra (phy/mod_eddtra.F90:49-50)
+        st["OBLdepth"] = self._put(self.zeros(1), (10.0 + 90.0 * self._uniform(1)) * ipm)
+        st["mld"] = self._put(self.zeros(1), (10.0 + 140.0 * self._uniform(1)) * ipm)
+        st["ustar3"] = self._put(self.zeros(1), 2.0e-6 * self._uniform(1) * ipm)
+        st["wstar3"] = self._put(self.zeros(1), 1.0e-6 * self._uniform(1) * ipm)
+        st["hbl_tf"] = self._put(self.zeros(1), (20.0 + 60.0 * self._uniform(1)) * ipm)
+        st["wpup_tf"] = self._put(self.zeros(1), (1.0e-3 + 1.0e-4 * self._uniform(1)) * ipm)
+        st["hml_tf1"] = self._put(self.zeros(1), (20.0 + 100.0 * self._uniform(1)) * ipm)
+        st["hml_tf"] = self._put(self.zeros(1), (20.0 + 100.0 * self._uniform(1)) * ipm)
+        st["hml_tfbnd"] = self.zeros(1)
+        st["util1"] = self.zeros(1)
         st["taux"] = self._put(self.zeros(1), 0.1 * self._normal(1) * ium)
         st["tauy"] = self._put(self.zeros(1), 0.1 * self._normal(1) * ivm)
         # --- time smoother work arrays (phy/mod_tmsmt.F90:53-66)

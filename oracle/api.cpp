@@ -122,6 +122,9 @@ int oracle_pgforc(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::p
 
 int oracle_barotp(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::barotp(m, n, mm, nn, k1m, k1n)) }
 
+int oracle_eddtra(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::eddtra(m, n, mm, nn, k1m, k1n)) }
+int oracle_pbcor1(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::pbcor1(m, n, mm, nn, k1m, k1n)) }
+int oracle_pbcor2(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::pbcor2(m, n, mm, nn, k1m, k1n)) }
 int oracle_momtum(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::momtum(m, n, mm, nn, k1m, k1n)) }
 int oracle_numerical_bounds() { GUARD(orc::numerical_bounds()) }
 int oracle_init_fluxes(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::init_fluxes(m, n, mm, nn, k1m, k1n)) }

@@ -159,3 +159,45 @@ def test_momtum_perf_build():
         check(g, o, MT_FIELDS, 1e-9)
     finally:
         g.finalize()
+
+
+ED_FIELDS = ["umfltd", "vmfltd", "umflsm", "vmflsm", "utfltd", "vtfltd", "utflsm", "vtflsm", "usfltd", "vsfltd",
+             "usflsm", "vsflsm", "hbl_tf", "wpup_tf", "hml_tf1", "hml_tf", "hml_tfbnd", "util1"]
+
+
+@pytest.mark.parametrize("cfg,mlrmth,slope,parity", [
+    ("tiny0", "none", 1.0, True), ("tiny1", "fox08", 1.0, True), ("tiny2", "bod23", 1.0, True),
+    ("tiny3", "fox08", 3.0e3, True), ("tiny4", "bod23", 3.0e3, True), ("fuk95", "bod23", 1.0e3, True),
+    ("tiny2", "fox08", 3.0e3, False), ("fuk95", "fox08", 1.0, False)])
+def test_eddtra(cfg, mlrmth, slope, parity):
+    """eddtra_ale + heat/salt flux diagnosis.  Tolerance 1e-13 of the field max-norm for the parity
+    build (only pow() of the bod23 filter input differs from host libm, <=1 ulp), 1e-10 for the FMA
+    build; steep synthetic slopes (x3e3) drive the iterative limiter through several sweeps."""
+    c = Case(cfg, ntr=0)
+    c.state["nslpx"] *= slope; c.state["nslpy"] *= slope
+    o = c.new_oracle(); g = c.new_gpu(parity=parity)
+    try:
+        for b in (o, g):
+            b.set_option("mlrmth", mlrmth); b.inieos()
+        for rep in range(2):   # second call: the running-mean filter state carries over
+            o.eddtra(*c.levels); g.eddtra(*c.levels)
+            g.sync()
+            check(g, o, ED_FIELDS, 1e-13 if parity else 1e-10)
+        kk = c.dims[2]; mm = c.levels[2]
+        assert np.abs(interior(g.arrays["umfltd"][mm:mm + kk])).max() > 0.0
+    finally:
+        g.finalize()
+
+
+def test_eddtra_bad_option():
+    from blom_b200.lib import BlomGpuError
+    c, o, g = pair("tiny0", ntr=0)
+    try:
+        g.set_option("mlrmth", "bogus")
+        with pytest.raises(BlomGpuError, match="mlrmth = bogus is unsupported"):
+            g.eddtra(*c.levels)
+        g.set_option("mlrmth", "fox08"); g.set_option("eitmth", "intdif")
+        with pytest.raises(BlomGpuError, match="eitmth_opt is unsupported"):
+            g.eddtra(*c.levels)
+    finally:
+        g.finalize()

@@ -165,3 +165,54 @@ def test_barotp_mass_and_bounds(cfg, mommth):
     assert np.abs(interior(a["pb"][n - 1])[ip] / interior(c.state["pb"][n - 1])[ip] - 1).max() < 0.05
     iu = interior(c.masks["iu"]) == 1
     assert np.abs(interior(a["ub"][n - 1])[iu]).max() < 5.0
+
+
+# ---- eddtra_ale (phy/mod_eddtra.F90:1001-1739) ----------------------------------------------
+@pytest.mark.parametrize("cfg,mlrmth,slope", [("tiny1", "fox08", 1.0), ("tiny2", "bod23", 1.0), ("tiny0", "none", 1.0),
+                                              ("tiny2", "fox08", 3.0e3), ("fuk95", "bod23", 1.0e3)])
+def test_eddtra_properties(cfg, mlrmth, slope):
+    """Pins of the restatement by the routine's own contracts: (i) the interface fluxes vanish at
+    the surface and below the last layer with mass, so every face column of layer fluxes sums to
+    zero (no net eddy-induced transport); (ii) after limiting no layer flux depletes more than
+    ffac=1/16 of the donor cell; (iii) heat/salt components are flux x face-mean T,S."""
+    c = Case(cfg, ntr=0)
+    o = c.new_oracle()
+    o.set_option("mlrmth", mlrmth)
+    o.arrays["nslpx"] *= slope; o.arrays["nslpy"] *= slope
+    o.inieos()
+    m, n, mm, nn, k1m, k1n = c.levels
+    kk = c.dims[2]
+    o.eddtra(*c.levels)
+    a = o.arrays
+    for f, msk in (("u", "iu"), ("v", "iv")):
+        tot = interior(a[f + "mfltd"][mm:mm + kk]) + interior(a[f + "mflsm"][mm:mm + kk])
+        scale = np.abs(tot).max()
+        assert scale > 0.0
+        assert np.abs(tot.sum(axis=0)).max() <= 1e-12 * scale
+    # depletion bound at the donor cells (u faces)
+    ffac = 0.0625
+    p, pbu, scp2 = a["p"], a["pbu"][n - 1], a["scp2"][0]
+    ptu = np.maximum(p[0][:, 1:], p[0][:, :-1])
+    iu = c.masks["iu"][:, 1:] == 1
+    for k in range(kk):
+        f = (a["umfltd"][k + mm] + a["umflsm"][k + mm])[:, 1:]
+        dlm = np.maximum(0.0, np.minimum(p[k + 1][:, :-1], pbu[:, 1:]) - np.maximum(p[k][:, :-1], ptu))
+        dlp = np.maximum(0.0, np.minimum(p[k + 1][:, 1:], pbu[:, 1:]) - np.maximum(p[k][:, 1:], ptu))
+        sl = (slice(4, -4), slice(3, -4))
+        ok = (f <= ffac * np.maximum(1e-12, dlm) * scp2[:, :-1]) & (f >= -ffac * np.maximum(1e-12, dlp) * scp2[:, 1:])
+        assert ok[sl][iu[sl]].all(), k
+    if slope > 1.0:
+        # the limiter was active: some flux sits exactly at the (1-eps)*ffac bound
+        assert np.abs(interior(a["umfltd"][mm:mm + kk])).max() > 0.0
+    qt = 0.5 * (a["temp"][mm:mm + kk][:, :, 1:] + a["temp"][mm:mm + kk][:, :, :-1])
+    np.testing.assert_array_equal(interior(a["utfltd"][mm:mm + kk]),
+                                  interior(np.pad(a["umfltd"][mm:mm + kk][:, :, 1:] * qt, ((0, 0), (0, 0), (1, 0)))))
+
+
+def test_eddtra_bad_option():
+    from oracle.oracle import OracleError
+    c = Case("tiny0", ntr=0)
+    o = c.new_oracle(); o.inieos()
+    o.set_option("mlrmth", "bogus")
+    with pytest.raises(OracleError, match="mlrmth = bogus is unsupported"):
+        o.eddtra(*c.levels)
