@@ -37,7 +37,7 @@ def band(jtdm: int, rank: int, nranks: int):
 
 def available_routines():
     """Routines of STEP_SEQUENCE implemented by the loaded library (stubs raise)."""
-    return ["init_fluxes", "tmsmt1", "eddtra", "advect", "diffus", "pgforc", "momtum", "barotp", "tmsmt2"]
+    return list(STEP_SEQUENCE)
 
 
 class HotPath:

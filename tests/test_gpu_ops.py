@@ -201,3 +201,43 @@ def test_eddtra_bad_option():
             g.eddtra(*c.levels)
     finally:
         g.finalize()
+
+
+PBC_FIELDS = ["dp", "temp", "saln", "trc", "uflx", "vflx", "utflx", "vtflx", "usflx", "vsflx", "sigma"]
+
+
+@pytest.mark.parametrize("cfg,bmcmth,parity", [("tiny0", "uc", True), ("tiny1", "dluc", True), ("tiny2", "uc", True),
+                                               ("tiny2", "dluc", True), ("tiny3", "uc", True), ("tiny4", "dluc", True),
+                                               ("fuk95", "uc", True), ("tiny2", "uc", False), ("fuk95", "dluc", False)])
+def test_pbcor(cfg, bmcmth, parity):
+    """pbcor1 then pbcor2 on the same state.  Tolerance: 1e-13 of the field max-norm (parity
+    build; only + - * / and max/min) and 1e-10 for the FMA build."""
+    c, o, g = pair(cfg, parity=parity, opts={"bmcmth": bmcmth})
+    try:
+        m, n, mm, nn, k1m, k1n = c.levels
+        for b in (o, g):
+            b.arrays["ubflxs"][n - 1] = b.arrays["ubflxs_p"][m - 1] * 1.01
+            b.arrays["vbflxs"][n - 1] = b.arrays["vbflxs_p"][m - 1] * 1.01
+        g.upload("ubflxs"); g.upload("vbflxs")
+        tol = 1e-13 if parity else 1e-10
+        o.pbcor1(*c.levels); g.pbcor1(*c.levels)
+        check(g, o, PBC_FIELDS, tol)
+        check(g, o, ["p"], tol, halo=1)
+        assert np.abs(interior(g.arrays["dp"]) - interior(c.state["dp"])).max() > 0.0
+        o.pbcor2(*c.levels); g.pbcor2(*c.levels)
+        check(g, o, PBC_FIELDS + ["utotn", "vtotn"], tol)
+        check(g, o, ["p", "dp"], tol, halo=1)
+    finally:
+        g.finalize()
+
+
+def test_pbcor_bad_option():
+    from blom_b200.lib import BlomGpuError
+    c, o, g = pair("tiny0", ntr=0, opts={"bmcmth": "bogus"})
+    try:
+        with pytest.raises(BlomGpuError, match="bmcmth = bogus is unsupported"):
+            g.pbcor1(*c.levels)
+        with pytest.raises(BlomGpuError, match="bmcmth = bogus is unsupported"):
+            g.pbcor2(*c.levels)
+    finally:
+        g.finalize()

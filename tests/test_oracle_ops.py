@@ -216,3 +216,54 @@ def test_eddtra_bad_option():
     o.set_option("mlrmth", "bogus")
     with pytest.raises(OracleError, match="mlrmth = bogus is unsupported"):
         o.eddtra(*c.levels)
+
+
+# ---- pbcor1 / pbcor2 (phy/mod_pbcor.F90:66-743) ------------------------------------------------
+@pytest.mark.parametrize("cfg,bmcmth", [("tiny0", "uc"), ("tiny1", "dluc"), ("tiny2", "uc"), ("tiny2", "dluc"),
+                                        ("tiny3", "uc"), ("fuk95", "uc")])
+def test_pbcor_contracts(cfg, bmcmth):
+    """Contracts of the correction pinned on the restatement: (i) the residual is distributed
+    completely, sum_k uflx(k) == dlt*ubflxs_p (pbcor1) / dlt*ubflxs(n) (pbcor2) at every wet face;
+    (ii) the corrected column adds up to the barotropic bottom pressure pb_p / pb(m);
+    (iii) a uniform tracer stays uniform (flux form with consistent mass fluxes)."""
+    c = Case(cfg, ntr=1)
+    o = c.new_oracle()
+    o.set_option("bmcmth", bmcmth)
+    o.inieos()
+    m, n, mm, nn, k1m, k1n = c.levels
+    kk = c.dims[2]
+    a = o.arrays
+    a["trc"][:] = np.where(a["trc"] != 0.0, 1.0, 0.0) * 0 + 1.0
+    dlt = c.scalars["dlt"]
+    iu = interior(c.masks["iu"]) == 1
+    wet = interior(c.masks["ip"]) == 1
+    o.pbcor1(*c.levels)
+    tot = interior(a["uflx"][mm:mm + kk]).sum(axis=0)
+    ref = dlt * interior(a["ubflxs_p"][m - 1])
+    assert np.abs(tot - ref)[iu].max() <= 1e-12 * np.abs(ref).max()
+    col = interior(a["dp"][nn:nn + kk]).sum(axis=0)
+    assert np.abs(col - interior(a["pb_p"][0]))[wet].max() <= 1e-13 * col.max()
+    t = interior(a["trc"][nn:nn + kk])[:, wet]
+    assert np.abs(t - 1.0).max() <= 1e-9
+    assert np.isfinite(interior(a["temp"])).all()
+    # pbcor2 works on the mid level against ubflxs(n), pb(m)
+    a["ubflxs"][n - 1] = a["ubflxs_p"][m - 1] * 1.01
+    a["vbflxs"][n - 1] = a["vbflxs_p"][m - 1] * 1.01
+    o.pbcor2(*c.levels)
+    tot = interior(a["uflx"][nn:nn + kk]).sum(axis=0)
+    ref = dlt * interior(a["ubflxs"][n - 1])
+    assert np.abs(tot - ref)[iu].max() <= 1e-12 * np.abs(ref).max()
+    col = interior(a["dp"][mm:mm + kk]).sum(axis=0)
+    assert np.abs(col - interior(a["pb"][m - 1]))[wet].max() <= 1e-13 * col.max()
+    np.testing.assert_allclose(interior(a["p"][kk])[wet], interior(a["pb"][m - 1])[wet], rtol=1e-13)
+    t = interior(a["trc"][mm:mm + kk])[:, wet]
+    assert np.abs(t - 1.0).max() <= 1e-9
+
+
+def test_pbcor_bad_option():
+    from oracle.oracle import OracleError
+    c = Case("tiny0", ntr=0)
+    o = c.new_oracle()
+    o.set_option("bmcmth", "bogus")
+    with pytest.raises(OracleError, match="bmcmth = bogus is unsupported"):
+        o.pbcor1(*c.levels)
