@@ -23,6 +23,8 @@ CONFIGS = {
     "tiny2": (24, 20, 5, 2, 1800.0, 36.0),
     "tiny3": (20, 18, 4, 3, 1800.0, 36.0),
     "tiny4": (20, 22, 4, 4, 1800.0, 36.0),
+    "mid1": (48, 44, 6, 1, 1800.0, 36.0),          # multi-band parity cases (periodic-i / tripolar)
+    "mid2": (48, 46, 6, 2, 1800.0, 36.0),
     "fuk95": (156, 32, 12, 4, 180.0, 6.0),        # tests/fuk95/limits:131-143
     "channel": (208, 512, 53, 1, 1800.0, 36.0),    # bld/channel/patch.input.1
     "tnx1v4": (360, 385, 53, 2, 3200.0, 64.0),     # namelist_definition_blom.xml:179-201
@@ -411,7 +413,8 @@ class Synth:
         # hybrid coordinate: dpuold/dpvold come from the (out-of-scope) ALE step; any positive
         # thickness-like field exercises the velocity time filter
         self.interior(st["dpuold"])[:] = 0.5 * (dpn + np.roll(dpn, 1, axis=2)) * ium
-        self.interior(st["dpvold"])[:] = 0.5 * (dpn + np.roll(dpn, 1, axis=1)) * ivm
+        # (no j-neighbour here: a band must hold exactly the rows of the one-tile state)
+        self.interior(st["dpvold"])[:] = 0.5 * (dpn + np.roll(dpn, -1, axis=2)) * ivm
         st["utotn"] = self._put(self.zeros(1), 1.0e-6 * self._normal(1) * ium)
         st["vtotn"] = self._put(self.zeros(1), 1.0e-6 * self._normal(1) * ivm)
         return st

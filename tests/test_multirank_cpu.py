@@ -1,0 +1,102 @@
+"""Host-side logic of the N>1 path on CPU (gloo, world_size 2): band decomposition, band-wise
+synthetic state == rows of the one-tile state, NCCL-id style broadcast plumbing, and a host
+emulation of the N/S band-edge exchange checked against the oracle's one-tile xctilr."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from blom_b200 import synth  # noqa: E402
+from blom_b200.driver import band  # noqa: E402
+
+
+def test_band_partition_covers_grid():
+    for jtdm in (385, 1153, 2165, 46):
+        for n in (1, 2, 4, 8):
+            rows = [band(jtdm, r, n) for r in range(n)]
+            assert rows[0][0] == 0 and sum(jj for _, jj in rows) == jtdm
+            for (a, ja), (b, _) in zip(rows, rows[1:]):
+                assert a + ja == b
+            assert max(jj for _, jj in rows) - min(jj for _, jj in rows) <= 1
+            assert min(jj for _, jj in rows) >= 4  # nbdy-wide halos come from the direct neighbour only
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS["mid2"]
+        # the 128-byte communicator id travels from rank 0 like in bench.py
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid[:] = torch.arange(128, dtype=torch.uint8)
+        dist.broadcast(uid, 0)
+        assert uid[77].item() == 77
+        j0, jj = band(jtdm, rank, world)
+        syn = synth.Synth(itdm, jtdm, kdm, nreg, ntr=1, j0=j0, jj=jj, baclin=baclin, batrop=batrop)
+        gr = syn.grid(); st = syn.state(gr)
+        nb = 4
+        # N/S exchange of nh rows with the neighbours (host emulation of comm.cu exchange_ns)
+        a = st["temp"]
+        nh = 3
+        reqs = []
+        if rank + 1 < world:
+            send = torch.from_numpy(np.ascontiguousarray(a[:, nb + jj - nh:nb + jj, nb:nb + itdm]))
+            recv_n = torch.empty_like(send)
+            reqs += [dist.isend(send, rank + 1), dist.irecv(recv_n, rank + 1)]
+        if rank > 0:
+            send_s = torch.from_numpy(np.ascontiguousarray(a[:, nb:nb + nh, nb:nb + itdm]))
+            recv_s = torch.empty_like(send_s)
+            reqs += [dist.isend(send_s, rank - 1), dist.irecv(recv_s, rank - 1)]
+        for r in reqs:
+            r.wait()
+        if rank + 1 < world:
+            a[:, nb + jj:nb + jj + nh, nb:nb + itdm] = recv_n.numpy()
+        if rank > 0:
+            a[:, nb - nh:nb, nb:nb + itdm] = recv_s.numpy()
+        # gather the bands (interior + the exchanged inner halo rows) on rank 0
+        payload = {"j0": j0, "jj": jj, **gr, **st}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, payload)
+        if rank == 0:
+            q.put(gathered)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_two_ranks_band_state_and_exchange():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS["mid2"]
+    one = synth.Synth(itdm, jtdm, kdm, nreg, ntr=1, baclin=baclin, batrop=batrop)
+    g1 = one.grid(); s1 = one.state(g1)
+    nb = 4
+    for b in gathered:
+        j0, jj = b["j0"], b["jj"]
+        for nm, ref in {**g1, **s1}.items():   # EVERY synthetic array: band rows == one-tile rows
+            np.testing.assert_array_equal(b[nm][..., nb:nb + jj, nb:nb + itdm],
+                                          ref[..., nb + j0:nb + j0 + jj, nb:nb + itdm], err_msg=nm)
+    # exchanged rows equal the neighbour's interior rows == one-tile rows (what xctilr gives inside the domain)
+    lo, hi = gathered
+    nh = 3
+    np.testing.assert_array_equal(lo["temp"][:, nb + lo["jj"]:nb + lo["jj"] + nh, nb:nb + itdm],
+                                  s1["temp"][:, nb + lo["jj"]:nb + lo["jj"] + nh, nb:nb + itdm])
+    np.testing.assert_array_equal(hi["temp"][:, nb - nh:nb, nb:nb + itdm],
+                                  s1["temp"][:, nb + hi["j0"] - nh:nb + hi["j0"], nb:nb + itdm])
