@@ -60,9 +60,12 @@ __device__ __forceinline__ double fsign(double a, double b) { return copysign(a,
 // ---- static tables -----------------------------------------------------------
 // One thread per interior point computes both directions' tables
 // (set_stencil_coeffs / set_slope_coeffs / set_d2_mask, mod_cppm.F90:101-359).
-__device__ void stencil_coeffs(const int* sm, const double* dx, double* tab, long lev) {
+// Moment coefficients of the 4-cell edge stencil (mod_cppm.F90:118-175): functions of the four cell
+// widths only.  Used by the table kernel and recomputed inside the flux kernel (cheaper than
+// re-reading 36 table words per interface and level).
+struct TmCoef { double t0[12], tl[12], tr[12]; };
+__device__ __forceinline__ void tm_coeffs(double d1, double d2, double d3, double d4, TmCoef& c, double a[12]) {
   double a12, a22, a32, a42, a13, a23, a33, a43, a14, a24, a34, a44;
-  const double d1 = dx[0], d2 = dx[1], d3 = dx[2], d4 = dx[3];
   a12 = -d2 - K1_2 * d1;
   a22 = -K1_2 * d2;
   a32 = K1_2 * d3;
@@ -75,7 +78,7 @@ __device__ void stencil_coeffs(const int* sm, const double* dx, double* tab, lon
   a24 = -K3_4 * a23 * d2;
   a34 = K3_4 * a33 * d3;
   a44 = (a43 + K1_6 * d4 * d4) * a42;
-  double tl[12], tr[12], t0[12];
+  double* tl = c.tl; double* tr = c.tr; double* t0 = c.t0;
   tl[0] = -K1_12 * d1;
   tl[1] = (K1_10 * d1 + K1_6 * d2) * d1;
   tl[2] = -(K1_10 * (d1 + K3 * d2) * d1 + K1_4 * (d2 * d2)) * d1;
@@ -112,6 +115,16 @@ __device__ void stencil_coeffs(const int* sm, const double* dx, double* tab, lon
   t0[9] = a42;
   t0[10] = a43 - tl[10] - tr[10];
   t0[11] = a44 - tl[11] - tr[11];
+  a[0] = a12; a[1] = a22; a[2] = a32; a[3] = a42; a[4] = a13; a[5] = a23; a[6] = a33; a[7] = a43;
+  a[8] = a14; a[9] = a24; a[10] = a34; a[11] = a44;
+}
+
+__device__ void stencil_coeffs(const int* sm, const double* dx, double* tab, long lev) {
+  TmCoef tc; double av[12];
+  tm_coeffs(dx[0], dx[1], dx[2], dx[3], tc, av);
+  double a12 = av[0], a22 = av[1], a32 = av[2], a42 = av[3], a13 = av[4], a23 = av[5], a33 = av[6], a43 = av[7],
+         a14 = av[8], a24 = av[9], a34 = av[10], a44 = av[11];
+  const double* t0 = tc.t0; const double* tl = tc.tl; const double* tr = tc.tr;
 #pragma unroll
   for (int r = 0; r < 12; ++r) {
     tab[(T_TMC0 + r) * lev] = t0[r];
@@ -382,16 +395,14 @@ __global__ void cppm_swap_edges(Geom g, bool fold_fix, double* hel3, double* her
 }
 
 // ---- compatible tracer edge weights (per-interface LU, :519-722) --------------
-// c0..c3 are the 4 cells e-2..e+1; tb points at this interface's table entry.
-__device__ __forceinline__ void tracer_edge_weights(int stencil, const double* __restrict__ tb, long lev,
+// c0..c3 are the 4 cells e-2..e+1; t0/tl/tr are this interface's moment coefficients.
+__device__ __forceinline__ void tracer_edge_weights(int stencil, const double* __restrict__ t0,
+                                                    const double* __restrict__ tl, const double* __restrict__ tr,
                                                     const double hm[4], const double hel[4],
                                                     const double her[4], double& tevc1, double& tevc2,
                                                     double& tevc3, double& tevc4) {
   double h1i, h2i, h3i, h4i, a12, a22, a32, a42, a13, a23, a33, a43, a14, a24, a34, a44, q;
-#define TM0(r) tb[(T_TMC0 + (r) - 1) * lev]
-#define TML(r) tb[(T_TMCL + (r) - 1) * lev]
-#define TMR(r) tb[(T_TMCR + (r) - 1) * lev]
-#define EL(r, c, hi) (TM0(r) + (TML(r) * hel[c] + TMR(r) * her[c]) * hi)
+#define EL(r, c, hi) (t0[(r) - 1] + (tl[(r) - 1] * hel[c] + tr[(r) - 1] * her[c]) * hi)
   switch (stencil) {
     case stencil_1111:
       h1i = K1 / hm[0]; h2i = K1 / hm[1]; h3i = K1 / hm[2]; h4i = K1 / hm[3];
@@ -478,9 +489,6 @@ __device__ __forceinline__ void tracer_edge_weights(int stencil, const double* _
       tevc1 = K0; tevc2 = K0; tevc3 = K0; tevc4 = K0;
       break;
   }
-#undef TM0
-#undef TML
-#undef TMR
 #undef EL
 }
 
@@ -490,271 +498,352 @@ struct ScalarPtrs {
   double* dst[NT];        // level-1 pointers of the destination set
 };
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 // ---- flux kernel ------------------------------------------------------------
 // Thread block = TP positions along the pass direction x TC along the cross
-// direction; it produces TP-5 updated cells per cross position.  Stage data
-// flows through shared memory:
+// direction; it produces TP-5 updated cells per cross position and marches
+// through a chunk of levels.  Everything that depends on (i,j) only (stencil
+// tag, limiter coefficients, cell widths, 1/area, bottom pressure at the face)
+// is loaded once per chunk; the level-dependent operands of level k+1 are
+// fetched with cp.async into the second half of a double buffer while level k
+// is computed, so DRAM latency is hidden by the pipeline instead of by
+// occupancy.  Per level the stage data flows through shared memory:
 //   cells (hm,hel,her,tm) -> A: edge values te -> B: curvature d2t
 //   -> C: limited parabolas -> D: face fluxes -> E: cell update.
+// The 36 moment coefficients of an interface are recomputed from the four
+// cell widths (tm_coeffs) instead of being re-read per level; only interfaces
+// on the tripolar fold rows, whose table entries are mirrored images
+// (mod_cppm.F90:2605-2646), read the tables.
+template <int NT, int TP>
+struct FluxSmem {
+  static constexpr int NCELL = TP + 3;
+  static constexpr int NRAW = 5 + NT;   // dp, hel, her, cross flux area (+,-), tm[NT]
+  static constexpr int NOPS = 5;        // pass flux area, p(k+1), flx, tflx, sflx
+  static constexpr int BUF = NRAW * NCELL + NOPS * TP;
+  // hm, 1/area, width, E|F (1+NT rows), D (NT), P (3+3NT)
+  static constexpr int WORK = 3 * NCELL + (1 + NT + NT + 3 + 3 * NT) * TP;
+  static constexpr int PER_TC = 2 * BUF + WORK;
+};
+
 template <int DIR, int NT, int TP, int TC>
-__global__ void __launch_bounds__(TP* TC)
-cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */,
+__global__ void __launch_bounds__(TP* TC, DIR == 0 ? 2 : 1)
+cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */, int kchunk,
           const double* __restrict__ dp_src, double* __restrict__ dp_dst, ScalarPtrs<NT> S,
           const double* __restrict__ hel3, const double* __restrict__ her3,
           const double* __restrict__ cad /* pass-direction flux area */,
           const double* __restrict__ cac /* cross-direction flux area */,
           const double* __restrict__ p, const double* __restrict__ pbd /* pbu or pbv */,
-          const double* __restrict__ scp2i, const double* __restrict__ tab,
-          const int* __restrict__ sten, double* __restrict__ flx, double* __restrict__ tflx,
-          double* __restrict__ sflx /* level km=1+mm .. pointers at level 1+mm */) {
-  constexpr int NCELL = TP + 3;
+          const double* __restrict__ scp2i, const double* __restrict__ scpd /* scpx or scpy */,
+          const double* __restrict__ tab, const int* __restrict__ sten, double* __restrict__ flx,
+          double* __restrict__ tflx, double* __restrict__ sflx /* pointers at level 1+mm */) {
+  using L = FluxSmem<NT, TP>;
+  constexpr int NCELL = L::NCELL;
   extern __shared__ double smem[];
-  // layout per cross position tc: cells[(3+NT)][NCELL], E[NT][TP], D[NT][TP], PAR[3+3NT][TP], F[1+NT][TP]
-  constexpr int PER_TC = (3 + NT) * NCELL + (NT + NT + 3 + 3 * NT + 1 + NT) * TP;
   const int tp = DIR == 0 ? threadIdx.x : threadIdx.y;
   const int tc = DIR == 0 ? threadIdx.y : threadIdx.x;
-  double* base = smem + (long)tc * PER_TC;
-  double* s_hm = base;
-  double* s_hel = s_hm + NCELL;
-  double* s_her = s_hel + NCELL;
-  double* s_tm = s_her + NCELL;              // [NT][NCELL]
-  double* s_E = s_tm + NT * NCELL;           // [NT][TP]
-  double* s_D = s_E + NT * TP;               // [NT][TP]
+  double* base = smem + (long)tc * L::PER_TC;
+  double* bufs = base;                       // [2][BUF]
+  double* s_hm = base + 2 * L::BUF;          // [NCELL]
+  double* s_ai = s_hm + NCELL;               // [NCELL] 1/area of the staged cells
+  double* s_dx = s_ai + NCELL;               // [NCELL] width of the staged cells along the pass
+  double* s_F = s_dx + NCELL;                // [1+NT][TP]; rows 1.. double as the edge values E
+  double* s_E = s_F + TP;
+  double* s_D = s_F + (1 + NT) * TP;         // [NT][TP]
   double* s_P = s_D + NT * TP;               // [3+3NT][TP]
-  double* s_F = s_P + (3 + 3 * NT) * TP;     // [1+NT][TP]
 
   constexpr int NOUT = TP - 5;
   const int npass = DIR == 0 ? g.idm : g.jdm;
   const int ncross = DIR == 0 ? g.jdm : g.idm;
   const int tile = DIR == 0 ? blockIdx.x : blockIdx.y;
   const int ctile = DIR == 0 ? blockIdx.y : blockIdx.x;
-  const int k = blockIdx.z + 1;
+  const int k_first = blockIdx.z * kchunk + 1;
+  const int k_last = min(g.kdm, k_first + kchunk - 1);
   const int s0 = 1 + tile * NOUT;   // first updated cell of this tile
   const int p0 = s0 - 2;            // pass index of thread tp=0
   const int cc = 1 + ctile * TC + tc;
   const bool cvalid = cc <= ncross;
   const int ccl = min(cc, ncross);
-  const long sp = DIR == 0 ? 1 : g.ldi, sc = DIR == 0 ? g.ldi : 1;
+  const long sc = DIR == 0 ? g.ldi : 1;
   const int pmax = npass + g.nb;    // last addressable pass index
-  // address of (pass index pi, cross ccl) in a 2-D level
-  auto addr = [&](int pi) -> long {
-    return DIR == 0 ? ix2(g, pi, ccl) : ix2(g, ccl, pi);
-  };
-  const long koff = (long)(k - 1) * g.lev;
-
-  // ---- stage cell values: cells p0-2 .. p0+TP (NCELL of them) ----
-  for (int q = tp; q < NCELL; q += TP) {
-    const int pi = min(p0 - 2 + q, pmax);
-    const long y = addr(pi), yk = y + koff;
-    double h = fmax(K0, dp_src[yk]) + DPEPS;
-    if (second_pass) h = h / (K1 - (cac[yk + sc] - cac[yk]) * scp2i[y]);
-    s_hm[q] = h;
-    s_hel[q] = hel3[yk];
-    s_her[q] = her3[yk];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) s_tm[nt * NCELL + q] = S.src[nt][yk];
-  }
-  __syncthreads();
+  auto addr = [&](int pi) -> long { return DIR == 0 ? ix2(g, pi, ccl) : ix2(g, ccl, pi); };
+  const long lev = g.lev;
 
   // own cell / edge / face index
   const int e = p0 + tp;
   const int el = min(e, pmax);
-  const long xe = addr(el), xek = xe + koff;
+  const long xe = addr(el);
   const int qc = tp + 2;  // smem index of own cell
-  const double hm_c = s_hm[qc], hel_c = s_hel[qc], her_c = s_her[qc];
-  double tm_c[NT];
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) tm_c[nt] = s_tm[nt * NCELL + qc];
+  const int tm1 = max(tp - 1, 0), tp1 = min(tp + 1, TP - 1);
 
-  // ---- A: tracer edge values at edge e from cells e-2..e+1 (smem tp..tp+3) ----
-  {
-    double hm4[4], hel4[4], her4[4];
+  // issue the level-dependent loads of level k into buffer b
+  auto issue = [&](int k, int b) {
+    double* B = bufs + b * L::BUF;
+    const long koff = (long)(k - 1) * lev;
+    for (int q = tp; q < NCELL; q += TP) {
+      const long yk = addr(min(p0 - 2 + q, pmax)) + koff;
+      cp_async8(B + 0 * NCELL + q, dp_src + yk);
+      cp_async8(B + 1 * NCELL + q, hel3 + yk);
+      cp_async8(B + 2 * NCELL + q, her3 + yk);
+      if (second_pass) {
+        cp_async8(B + 3 * NCELL + q, cac + yk + sc);
+        cp_async8(B + 4 * NCELL + q, cac + yk);
+      }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { hm4[q] = s_hm[tp + q]; hel4[q] = s_hel[tp + q]; her4[q] = s_her[tp + q]; }
-    double w1, w2, w3, w4;
-    tracer_edge_weights(sten[xe], tab + xe, g.lev, hm4, hel4, her4, w1, w2, w3, w4);
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-      s_E[nt * TP + tp] = w1 * s_tm[nt * NCELL + tp] + w2 * s_tm[nt * NCELL + tp + 1] +
-                          w3 * s_tm[nt * NCELL + tp + 2] + w4 * s_tm[nt * NCELL + tp + 3];
-  }
-  __syncthreads();
-
-  // ---- B: thickness factors and curvature proxy of own cell ----
-  double tel[NT], ter[NT];
-  double hf1m, hf1l, hf1r, hf2m, hf2l, hf2r;
-  {
-    const double q = K1 / (K12 * hm_c - hel_c - her_c);
-    hf1m = K60 * hm_c * q;
-    hf1l = -(K42 * hm_c + K4 * hel_c - K6 * her_c) * q;
-    hf1r = -(K18 * hm_c - K4 * hel_c + K6 * her_c) * q;
-    hf2m = -hf1m;
-    hf2l = K5 * (K6 * hm_c + hel_c - her_c) * q;
-    hf2r = K5 * (K6 * hm_c - hel_c + her_c) * q;
-    const double d2m = tab[T_D2M * g.lev + xe];
-    const int tq = min(tp + 1, TP - 1);
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      tel[nt] = s_E[nt * TP + tp];
-      ter[nt] = s_E[nt * TP + tq];
-      s_D[nt * TP + tp] = d2m * (hf2m * tm_c[nt] + hf2l * tel[nt] + hf2r * ter[nt]);
+      for (int nt = 0; nt < NT; ++nt) cp_async8(B + (5 + nt) * NCELL + q, S.src[nt] + yk);
     }
-  }
-  __syncthreads();
+    double* O = B + L::NRAW * NCELL;
+    cp_async8(O + 0 * TP + tp, cad + xe + koff);
+    cp_async8(O + 1 * TP + tp, p + xe + koff + lev);
+    cp_async8(O + 2 * TP + tp, flx + xe + koff);
+    cp_async8(O + 3 * TP + tp, tflx + xe + koff);
+    cp_async8(O + 4 * TP + tp, sflx + xe + koff);
+    cp_async_commit();
+  };
+  issue(k_first, 0);
 
-  // ---- C: limiters and parabola coefficients of own cell ----
-  double hpc0, hpc1, hpc2, tpc0[NT], tpc1[NT], tpc2[NT];
-  {
-    const double ssc = tab[T_SSC * g.lev + xe], scc = tab[T_SCC * g.lev + xe];
-    const int tm1 = max(tp - 1, 0), tp1 = min(tp + 1, TP - 1);
+  // ---- per-(i,j) invariants of the chunk ----
+  for (int q = tp; q < NCELL; q += TP) {
+    const long y = addr(min(p0 - 2 + q, pmax));
+    s_ai[q] = scp2i[y];
+    s_dx[q] = scpd[y];
+  }
+  const int stencil = sten[xe];
+  const double d2m = tab[T_D2M * lev + xe], ssc = tab[T_SSC * lev + xe], scc = tab[T_SCC * lev + xe];
+  const double db = pbd[xe + (long)(n_lev2d - 1) * lev];
+  // interfaces on the fold rows carry mirrored table entries: read them instead of recomputing
+  // (xctilr rewrites row jj of u-type tables with the mirror of row jj-1 even for nh=0, so the
+  //  i-pass needs them on row jj; the j-pass on rows >= jj)
+  const bool use_tab = g.nreg == 2 && g.north && (DIR == 1 ? e >= g.jj : cc == g.jj);
+  double p_own = p[xe + (long)(k_first - 1) * lev];
+  double p_up = p[addr(min(max(e - 1, 1 - g.nb), pmax)) + (long)(k_first - 1) * lev];
+  const bool face_ok = cvalid && tp >= 2 && tp <= TP - 3 && e >= 1 && e <= npass + 1 &&
+                       (tp <= TP - 4 || e == npass + 1);
+  const bool cell_ok = cvalid && tp >= 2 && tp <= TP - 4 && e >= 1 && e <= npass;
+
+  for (int k = k_first; k <= k_last; ++k) {
+    const int b = (k - k_first) & 1;
+    const double* B = bufs + b * L::BUF;
+    const double* s_dp = B;
+    const double* s_hel = B + NCELL;
+    const double* s_her = B + 2 * NCELL;
+    const double* s_tm = B + 5 * NCELL;       // [NT][NCELL]
+    const double* O = B + L::NRAW * NCELL;
+    cp_async_wait_all();
+    __syncthreads();                           // level k landed; everybody is done with level k-1
+    if (k < k_last) issue(k + 1, b ^ 1);
+
+    // ---- cell mean thickness of the staged cells ----
+    for (int q = tp; q < NCELL; q += TP) {
+      double h = fmax(K0, s_dp[q]) + DPEPS;
+      if (second_pass) h = h / (K1 - (B[3 * NCELL + q] - B[4 * NCELL + q]) * s_ai[q]);
+      s_hm[q] = h;
+    }
+    __syncthreads();
+
+    const double hm_c = s_hm[qc], hel_c = s_hel[qc], her_c = s_her[qc];
+    double tm_c[NT];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const double d2c = s_D[nt * TP + tp], d2l = s_D[nt * TP + tm1], d2r = s_D[nt * TP + tp1];
-      const double tmm = s_tm[nt * NCELL + qc - 1], tmp = s_tm[nt * NCELL + qc + 1], tmc = tm_c[nt];
-      double sl, sr, scv, a2;
-      if (d2l * d2c <= K0 || d2c * d2r <= K0) {
-        sl = ssc * (tmc - tmm);
-        sr = ssc * (tmp - tmc);
-        if (sl * sr > K0) {
-          scv = scc * (tmp - tmm);
-          scv = fsign(fmin(fmin(fabs(sl), fabs(sr)), fabs(scv)), scv);
-          if ((tmm - tel[nt]) * (tmc - tel[nt]) > K0)
-            tel[nt] = tmc - fsign(fmin(K1_2 * fabs(scv), fabs(tel[nt] - tmc)), scv);
-          if ((tmp - ter[nt]) * (tmc - ter[nt]) > K0)
-            ter[nt] = tmc + fsign(fmin(K1_2 * fabs(scv), fabs(ter[nt] - tmc)), scv);
+    for (int nt = 0; nt < NT; ++nt) tm_c[nt] = s_tm[nt * NCELL + qc];
+
+    // ---- A: tracer edge values at edge e from cells e-2..e+1 (smem tp..tp+3) ----
+    {
+      double hm4[4], hel4[4], her4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { hm4[q] = s_hm[tp + q]; hel4[q] = s_hel[tp + q]; her4[q] = s_her[tp + q]; }
+      double w1, w2, w3, w4;
+      TmCoef tcf;
+      if (use_tab) {
+#pragma unroll
+        for (int r = 0; r < 12; ++r) {
+          tcf.t0[r] = tab[(T_TMC0 + r) * lev + xe];
+          tcf.tl[r] = tab[(T_TMCL + r) * lev + xe];
+          tcf.tr[r] = tab[(T_TMCR + r) * lev + xe];
+        }
+      } else {
+        double av[12];
+        tm_coeffs(s_dx[tp], s_dx[tp + 1], s_dx[tp + 2], s_dx[tp + 3], tcf, av);
+      }
+      tracer_edge_weights(stencil, tcf.t0, tcf.tl, tcf.tr, hm4, hel4, her4, w1, w2, w3, w4);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        s_E[nt * TP + tp] = w1 * s_tm[nt * NCELL + tp] + w2 * s_tm[nt * NCELL + tp + 1] +
+                            w3 * s_tm[nt * NCELL + tp + 2] + w4 * s_tm[nt * NCELL + tp + 3];
+    }
+    __syncthreads();
+
+    // ---- B: thickness factors and curvature proxy of own cell ----
+    double tel[NT], ter[NT];
+    double hf1m, hf1l, hf1r, hf2m, hf2l, hf2r;
+    {
+      const double q = K1 / (K12 * hm_c - hel_c - her_c);
+      hf1m = K60 * hm_c * q;
+      hf1l = -(K42 * hm_c + K4 * hel_c - K6 * her_c) * q;
+      hf1r = -(K18 * hm_c - K4 * hel_c + K6 * her_c) * q;
+      hf2m = -hf1m;
+      hf2l = K5 * (K6 * hm_c + hel_c - her_c) * q;
+      hf2r = K5 * (K6 * hm_c - hel_c + her_c) * q;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        tel[nt] = s_E[nt * TP + tp];
+        ter[nt] = s_E[nt * TP + tp1];
+        s_D[nt * TP + tp] = d2m * (hf2m * tm_c[nt] + hf2l * tel[nt] + hf2r * ter[nt]);
+      }
+    }
+    __syncthreads();
+
+    // ---- C: limiters and parabola coefficients of own cell ----
+    double hpc0, hpc1, hpc2, tpc0[NT], tpc1[NT], tpc2[NT];
+    {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const double d2c = s_D[nt * TP + tp], d2l = s_D[nt * TP + tm1], d2r = s_D[nt * TP + tp1];
+        const double tmm = s_tm[nt * NCELL + qc - 1], tmp = s_tm[nt * NCELL + qc + 1], tmc = tm_c[nt];
+        double sl, sr, scv, a2;
+        if (d2l * d2c <= K0 || d2c * d2r <= K0) {
+          sl = ssc * (tmc - tmm);
+          sr = ssc * (tmp - tmc);
+          if (sl * sr > K0) {
+            scv = scc * (tmp - tmm);
+            scv = fsign(fmin(fmin(fabs(sl), fabs(sr)), fabs(scv)), scv);
+            if ((tmm - tel[nt]) * (tmc - tel[nt]) > K0)
+              tel[nt] = tmc - fsign(fmin(K1_2 * fabs(scv), fabs(tel[nt] - tmc)), scv);
+            if ((tmp - ter[nt]) * (tmc - ter[nt]) > K0)
+              ter[nt] = tmc + fsign(fmin(K1_2 * fabs(scv), fabs(ter[nt] - tmc)), scv);
+            sl = hf1m * tmc + hf1l * tel[nt] + hf1r * ter[nt];
+            a2 = hf2m * tmc + hf2l * tel[nt] + hf2r * ter[nt];
+            sr = sl + K2 * a2;
+            if (sl * sr < K0) {
+              if ((ter[nt] - tel[nt]) * a2 < K0)
+                tel[nt] = -((hf1m + K2 * hf2m) * tmc + (hf1r + K2 * hf2r) * ter[nt]) / (hf1l + K2 * hf2l);
+              else
+                ter[nt] = -(hf1m * tmc + hf1l * tel[nt]) / hf1r;
+            }
+          } else {
+            tel[nt] = tmc;
+            ter[nt] = tmc;
+          }
+        }
+        if (nt >= 1) {  // positivity for everything but temperature (:788-801)
+          tel[nt] = fmax(tel[nt], K0);
+          ter[nt] = fmax(ter[nt], K0);
           sl = hf1m * tmc + hf1l * tel[nt] + hf1r * ter[nt];
           a2 = hf2m * tmc + hf2l * tel[nt] + hf2r * ter[nt];
           sr = sl + K2 * a2;
-          if (sl * sr < K0) {
-            if ((ter[nt] - tel[nt]) * a2 < K0)
-              tel[nt] = -((hf1m + K2 * hf2m) * tmc + (hf1r + K2 * hf2r) * ter[nt]) / (hf1l + K2 * hf2l);
-            else
-              ter[nt] = -(hf1m * tmc + hf1l * tel[nt]) / hf1r;
-          }
-        } else {
-          tel[nt] = tmc;
-          ter[nt] = tmc;
-        }
-      }
-      if (nt >= 1) {  // positivity for everything but temperature (:788-801)
-        tel[nt] = fmax(tel[nt], K0);
-        ter[nt] = fmax(ter[nt], K0);
-        sl = hf1m * tmc + hf1l * tel[nt] + hf1r * ter[nt];
-        a2 = hf2m * tmc + hf2l * tel[nt] + hf2r * ter[nt];
-        sr = sl + K2 * a2;
-        if (sl < K0 && sr > K0) {
-          if (a2 * tel[nt] - K1_4 * sl * sl < K0) {
-            const double q = K3 * tmc / (K3 * sl * sr + K4 * a2 * a2);
-            tel[nt] = sl * sl * q;
-            ter[nt] = sr * sr * q;
+          if (sl < K0 && sr > K0) {
+            if (a2 * tel[nt] - K1_4 * sl * sl < K0) {
+              const double q = K3 * tmc / (K3 * sl * sr + K4 * a2 * a2);
+              tel[nt] = sl * sl * q;
+              ter[nt] = sr * sr * q;
+            }
           }
         }
+        tpc0[nt] = tel[nt];
+        tpc1[nt] = hf1m * tmc + hf1l * tel[nt] + hf1r * ter[nt];
+        tpc2[nt] = hf2m * tmc + hf2l * tel[nt] + hf2r * ter[nt];
+        s_P[(3 + 3 * nt + 0) * TP + tp] = tpc0[nt];
+        s_P[(3 + 3 * nt + 1) * TP + tp] = tpc1[nt];
+        s_P[(3 + 3 * nt + 2) * TP + tp] = tpc2[nt];
       }
-      tpc0[nt] = tel[nt];
-      tpc1[nt] = hf1m * tmc + hf1l * tel[nt] + hf1r * ter[nt];
-      tpc2[nt] = hf2m * tmc + hf2l * tel[nt] + hf2r * ter[nt];
-      s_P[(3 + 3 * nt + 0) * TP + tp] = tpc0[nt];
-      s_P[(3 + 3 * nt + 1) * TP + tp] = tpc1[nt];
-      s_P[(3 + 3 * nt + 2) * TP + tp] = tpc2[nt];
+      hpc0 = hel_c;
+      hpc1 = K6 * hm_c - K4 * hel_c - K2 * her_c;
+      hpc2 = K3 * (hel_c - K2 * hm_c + her_c);
+      s_P[0 * TP + tp] = hpc0; s_P[1 * TP + tp] = hpc1; s_P[2 * TP + tp] = hpc2;
     }
-    hpc0 = hel_c;
-    hpc1 = K6 * hm_c - K4 * hel_c - K2 * her_c;
-    hpc2 = K3 * (hel_c - K2 * hm_c + her_c);
-    s_P[0 * TP + tp] = hpc0; s_P[1 * TP + tp] = hpc1; s_P[2 * TP + tp] = hpc2;
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- D: flux through face e (flux_integration, :1373-1468) ----
-  const double ai_c = scp2i[xe];
-  double hf, htf[NT];
-  {
-    const double ca = cad[xek];
-    const double db = pbd[xe + (long)(n_lev2d - 1) * g.lev];
-    if (ca < K0) {
-      const double c = ca * ai_c;
-      const double du = p[xek], dl = p[xek + g.lev];
-      double p0_, p1_, p2_;
-      if (dl > db) {
-        const double hb = fmax(K0, db - du);
-        hf = hb * ca;
-        p0_ = hb;
-        p1_ = -K1_2 * hb * c;
-        p2_ = K1_3 * hb * c * c;
-      } else {
-        hf = (hpc0 - (K1_2 * hpc1 - K1_3 * hpc2 * c) * c) * ca;
-        p0_ = hpc0 - (K1_2 * hpc1 - K1_3 * hpc2 * c) * c;
-        p1_ = -(K1_2 * hpc0 - (K1_3 * hpc1 - K1_4 * hpc2 * c) * c) * c;
-        p2_ = (K1_3 * hpc0 - (K1_4 * hpc1 - K1_5 * hpc2 * c) * c) * c * c;
-      }
+    // ---- D: flux through face e (flux_integration, :1373-1468) ----
+    const double ai_c = s_ai[qc];
+    const double dl_own = O[1 * TP + tp], dl_up = O[1 * TP + tm1];
+    double hf, htf[NT];
+    {
+      const double ca = O[0 * TP + tp];
+      if (ca < K0) {
+        const double c = ca * ai_c;
+        const double du = p_own, dl = dl_own;
+        double p0_, p1_, p2_;
+        if (dl > db) {
+          const double hb = fmax(K0, db - du);
+          hf = hb * ca;
+          p0_ = hb;
+          p1_ = -K1_2 * hb * c;
+          p2_ = K1_3 * hb * c * c;
+        } else {
+          hf = (hpc0 - (K1_2 * hpc1 - K1_3 * hpc2 * c) * c) * ca;
+          p0_ = hpc0 - (K1_2 * hpc1 - K1_3 * hpc2 * c) * c;
+          p1_ = -(K1_2 * hpc0 - (K1_3 * hpc1 - K1_4 * hpc2 * c) * c) * c;
+          p2_ = (K1_3 * hpc0 - (K1_4 * hpc1 - K1_5 * hpc2 * c) * c) * c * c;
+        }
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) htf[nt] = (p0_ * tpc0[nt] + p1_ * tpc1[nt] + p2_ * tpc2[nt]) * ca;
-    } else {
-      const int tm1 = max(tp - 1, 0);
-      const long xu = xe - sp, xuk = xek - sp;  // upstream cell e-1
-      const double c = ca * scp2i[xu];
-      const double q1 = K1 - K1_2 * c;
-      const double q2 = K1 - (K1 - K1_3 * c) * c;
-      const double du = p[xuk], dl = p[xuk + g.lev];
-      const double u0 = s_P[0 * TP + tm1], u1 = s_P[1 * TP + tm1], u2 = s_P[2 * TP + tm1];
-      double p0_, p1_, p2_;
-      if (dl > db) {
-        const double hb = fmax(K0, db - du);
-        hf = hb * ca;
-        p0_ = hb;
-        p1_ = q1 * hb;
-        p2_ = q2 * hb;
+        for (int nt = 0; nt < NT; ++nt) htf[nt] = (p0_ * tpc0[nt] + p1_ * tpc1[nt] + p2_ * tpc2[nt]) * ca;
       } else {
-        hf = (u0 + q1 * u1 + q2 * u2) * ca;
-        const double q3 = K1_4 * (K1 + K3 * (K1 - c) * q2);
-        const double q4 = K1_5 * (K1 + K4 * (K1 - c) * q3);
-        p0_ = u0 + q1 * u1 + q2 * u2;
-        p1_ = q1 * u0 + q2 * u1 + q3 * u2;
-        p2_ = q2 * u0 + q3 * u1 + q4 * u2;
+        const double c = ca * s_ai[qc - 1];  // upstream cell e-1
+        const double q1 = K1 - K1_2 * c;
+        const double q2 = K1 - (K1 - K1_3 * c) * c;
+        const double du = p_up, dl = dl_up;
+        const double u0 = s_P[0 * TP + tm1], u1 = s_P[1 * TP + tm1], u2 = s_P[2 * TP + tm1];
+        double p0_, p1_, p2_;
+        if (dl > db) {
+          const double hb = fmax(K0, db - du);
+          hf = hb * ca;
+          p0_ = hb;
+          p1_ = q1 * hb;
+          p2_ = q2 * hb;
+        } else {
+          hf = (u0 + q1 * u1 + q2 * u2) * ca;
+          const double q3 = K1_4 * (K1 + K3 * (K1 - c) * q2);
+          const double q4 = K1_5 * (K1 + K4 * (K1 - c) * q3);
+          p0_ = u0 + q1 * u1 + q2 * u2;
+          p1_ = q1 * u0 + q2 * u1 + q3 * u2;
+          p2_ = q2 * u0 + q3 * u1 + q4 * u2;
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+          htf[nt] = (p0_ * s_P[(3 + 3 * nt + 0) * TP + tm1] + p1_ * s_P[(3 + 3 * nt + 1) * TP + tm1] +
+                     p2_ * s_P[(3 + 3 * nt + 2) * TP + tm1]) * ca;
       }
+      s_F[tp] = hf;                             // (E rows are dead since stage B)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) s_F[(1 + nt) * TP + tp] = htf[nt];
+    }
+    p_own = dl_own; p_up = dl_up;               // p(k+1) is the upper interface of the next level
+    __syncthreads();
+
+    // ---- E: divergence update of own cell + flux accumulation at own face ----
+    const long xek = xe + (long)(k - 1) * lev;
+    if (cell_ok) {
+      const double ho = fmax(K0, s_dp[qc]) + DPEPS;
+      const double hn = ho - (s_F[tp + 1] - hf) * ai_c;
+      const double hni = K1 / hn;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
-        htf[nt] = (p0_ * s_P[(3 + 3 * nt + 0) * TP + tm1] + p1_ * s_P[(3 + 3 * nt + 1) * TP + tm1] +
-                   p2_ * s_P[(3 + 3 * nt + 2) * TP + tm1]) * ca;
+        S.dst[nt][xek] = (ho * tm_c[nt] - (s_F[(1 + nt) * TP + tp + 1] - htf[nt]) * ai_c) * hni;
+      dp_dst[xek] = fmax(K0, hn - DPEPS);
     }
-    s_F[tp] = hf;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) s_F[(1 + nt) * TP + tp] = htf[nt];
-  }
-  __syncthreads();
-
-  // ---- E: divergence update of own cell + flux accumulation at own face ----
-  if (!cvalid) return;
-  const bool face_ok = tp >= 2 && tp <= TP - 3 && e >= 1 && e <= npass + 1;
-  const bool cell_ok = tp >= 2 && tp <= TP - 4 && e >= 1 && e <= npass;
-  if (cell_ok) {
-    const double ho = fmax(K0, dp_src[xek]) + DPEPS;
-    const double hn = ho - (s_F[tp + 1] - hf) * ai_c;
-    const double hni = K1 / hn;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-      S.dst[nt][xek] = (ho * tm_c[nt] - (s_F[(1 + nt) * TP + tp + 1] - htf[nt]) * ai_c) * hni;
-    dp_dst[xek] = fmax(K0, hn - DPEPS);
-  }
-  // faces s0..s0+NOUT-1 belong to this tile; the last tile also owns face npass+1
-  if (face_ok && (tp <= TP - 4 || e == npass + 1)) {
-    flx[xek] = flx[xek] + hf;
-    tflx[xek] = tflx[xek] + htf[0];
-    sflx[xek] = sflx[xek] + htf[1];
+    // faces s0..s0+NOUT-1 belong to this tile; the last tile also owns face npass+1
+    if (face_ok) {
+      flx[xek] = O[2 * TP + tp] + hf;
+      tflx[xek] = O[3 * TP + tp] + htf[0];
+      sflx[xek] = O[4 * TP + tp] + htf[1];
+    }
   }
 }
 
 template <int DIR, int NT>
 void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, const ScalarPtrs<NT>& S,
                  const double* hel3, const double* her3, const double* cad, const double* cac,
-                 const double* p, const double* pbd, const double* scp2i, const double* tab,
+                 const double* p, const double* pbd, const double* scp2i, const double* scpd, const double* tab,
                  const int* sten, double* flx, double* tflx, double* sflx) {
   Ctx& c = C(); const Geom& g = c.g;
   constexpr int TP = DIR == 0 ? 128 : 32;
   constexpr int TC = DIR == 0 ? 2 : 16;
   constexpr int NOUT = TP - 5;
-  constexpr int NCELL = TP + 3;
-  constexpr int PER_TC = (3 + NT) * NCELL + (NT + NT + 3 + 3 * NT + 1 + NT) * TP;
-  const size_t smem = sizeof(double) * PER_TC * TC;
+  const size_t smem = sizeof(double) * FluxSmem<NT, TP>::PER_TC * TC;
   auto kern = cppm_flux<DIR, NT, TP, TC>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -764,15 +853,21 @@ void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, 
   dim3 block, grid;
   if (DIR == 0) {
     block = dim3(TP, TC);
-    grid = dim3(cdiv(g.idm, NOUT), cdiv(g.jdm, TC), g.kdm);
+    grid = dim3(cdiv(g.idm, NOUT), cdiv(g.jdm, TC), 1);
   } else {
     block = dim3(TC, TP);
-    grid = dim3(cdiv(g.idm, TC), cdiv(g.jdm, NOUT), g.kdm);
+    grid = dim3(cdiv(g.idm, TC), cdiv(g.jdm, NOUT), 1);
   }
+  // level chunks: enough blocks for ~4 waves of the 148 SMs, but at least 6 levels per chunk so the
+  // per-chunk invariant loads stay amortised
+  const long tiles = (long)grid.x * grid.y;
+  int nz = (int)std::min<long>(std::max<long>(1, (148L * 2 * 4 + tiles - 1) / tiles), std::max(1, g.kdm / 6));
+  const int kchunk = cdiv(g.kdm, nz);
+  grid.z = cdiv(g.kdm, kchunk);
   // NB: the face npass+1 must be covered: tiles cover cells 1..ntile*NOUT >= npass and
   // thread tp = npass+1-p0 <= TP-3 of the last tile owns it.
-  LAUNCH_NAMED(DIR == 0 ? "cppm_flux<i>" : "cppm_flux<j>", kern, grid, block, smem, g, second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd,
-         scp2i, tab, sten, flx, tflx, sflx);
+  LAUNCH_NAMED(DIR == 0 ? "cppm_flux<i>" : "cppm_flux<j>", kern, grid, block, smem, g, second_pass, n, kchunk, dp_src,
+               dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i, scpd, tab, sten, flx, tflx, sflx);
 }
 
 template <int DIR, int NT>
@@ -802,7 +897,7 @@ void cppm_pass(bool second_pass, int n, int mm, double* dp_src, double* dp_dst, 
   }
   const long om = (long)mm * g.lev;
   launch_flux<DIR, NT>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, c.dev("p"),
-                       c.dev(DIR == 0 ? "pbu" : "pbv"), scp2i, tab, sten,
+                       c.dev(DIR == 0 ? "pbu" : "pbv"), scp2i, c.dev(DIR == 0 ? "scpx" : "scpy"), tab, sten,
                        c.dev(DIR == 0 ? "uflx" : "vflx") + om, c.dev(DIR == 0 ? "utflx" : "vtflx") + om,
                        c.dev(DIR == 0 ? "usflx" : "vsflx") + om);
 }
