@@ -12,6 +12,10 @@
 // substeps at 1 degree (working set ~58 MB < 126 MB L2).  All pointers travel in
 // one by-value parameter block.
 #include "common.cuh"
+#include "halo.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace blom {
 
@@ -185,6 +189,120 @@ __global__ void bt_veq(Geom g, BtP P, const double* __restrict__ ub, int i0, int
   P.vb_nl[x] = fmax(-P.vminb[x], fmin(P.vmaxb[x], vn));
 }
 
+// ---- persistent form of the subcycle ------------------------------------------------------------
+// One cooperative launch runs a whole block of lstep/2 substeps: the three phases of a substep
+// (continuity, first and second momentum equation) and, on one tile, the halo refresh of the
+// subcycled fields are separated by grid-wide barriers instead of kernel boundaries.  Read-write
+// fields are read with ld.global.cg (L1 is not coherent between the SMs of one launch); the ~40
+// read-only coefficient arrays use the normal cached path.  Operation order per cell is the one of
+// bt_continuity / bt_ueq / bt_veq above, so results are bit-identical to the launch-per-phase form.
+struct BtSched {
+  int lll0, nsub, ml, nl;
+  double woa, wob, wna, wnb;
+  int inkernel_halo;
+};
+
+// time-level pointers and time weights of the current substep
+struct BtLv { double *pb_ml, *pb_nl, *ub_ml, *ub_nl, *vb_ml, *vb_nl; double wo, wm, wn; };
+
+__device__ __forceinline__ void btp_continuity(const Geom& g, const BtP& P, const BtLv& V, long x) {
+  if (P.ip[x] != 1) return;
+  V.pb_nl[x] = (1. - WBARO) * __ldcg(V.pb_ml + x) + WBARO * __ldcg(V.pb_nl + x) -
+               (1. + WBARO) * P.dlt * (__ldcg(V.ub_ml + x + 1) - __ldcg(V.ub_ml + x) + __ldcg(V.vb_ml + x + g.ldi) -
+                                       __ldcg(V.vb_ml + x)) * P.scp2i[x];
+}
+__device__ __forceinline__ void btp_ueq(const Geom& g, const BtP& P, const BtLv& V, const double* __restrict__ vb, long x) {
+  const long s = g.ldi;
+  if (P.iu[x] != 1) return;
+  const double uml = __ldcg(V.ub_ml + x), unl = __ldcg(V.ub_nl + x);
+  P.ubflxs_t[x] = __ldcg(P.ubflxs_t + x) - WBARO * unl + (1. + WBARO) * uml;
+  const double v00 = __ldcg(vb + x), v01 = __ldcg(vb + x + s), vm0 = __ldcg(vb + x - 1), vm1 = __ldcg(vb + x - 1 + s);
+  double q;
+  if (P.enscon)
+    q = (v00 * P.scvxi[x] + v01 * P.scvxi[x + s] + vm0 * P.scvxi[x - 1] + vm1 * P.scvxi[x - 1 + s]) *
+        (V.wo * (P.pvo[x] + P.pvo[x + s]) + V.wm * (P.pvm[x] + P.pvm[x + s]) + V.wn * (P.pvn[x] + P.pvn[x + s])) * .125;
+  else
+    q = .25 * ((v00 * P.scvxi[x] + vm0 * P.scvxi[x - 1]) * (V.wo * P.pvo[x] + V.wm * P.pvm[x] + V.wn * P.pvn[x]) +
+               (v01 * P.scvxi[x + s] + vm1 * P.scvxi[x - 1 + s]) *
+                   (V.wo * P.pvo[x + s] + V.wm * P.pvm[x + s] + V.wn * P.pvn[x + s]));
+  P.ubcors_t[x] = __ldcg(P.ubcors_t + x) + q;
+  const double pbc = __ldcg(V.pb_nl + x), pbw = __ldcg(V.pb_nl + x - 1);
+  const double utndcy = q + (V.wo * (P.pgfxm_o[x] - (P.xixp_o[x] * pbc - P.xixm_o[x] * pbw)) +
+                             V.wm * (P.pgfxm_m[x] - (P.xixp_m[x] * pbc - P.xixm_m[x] * pbw)) +
+                             V.wn * (P.pgfxm_n[x] - (P.xixp_n[x] * pbc - P.xixm_n[x] * pbw))) * P.scuxi[x];
+  const double un = (1. - WBARO) * uml + WBARO * unl +
+                    (1. + WBARO) * P.dlt * ((utndcy + P.utotn[x]) * P.scuy[x] * fmin(pbw, pbc) - P.uglue[x] * uml);
+  V.ub_nl[x] = fmax(-P.uminb[x], fmin(P.umaxb[x], un));
+}
+__device__ __forceinline__ void btp_veq(const Geom& g, const BtP& P, const BtLv& V, const double* __restrict__ ub, long x) {
+  const long s = g.ldi;
+  if (P.iv[x] != 1) return;
+  const double vml = __ldcg(V.vb_ml + x), vnl = __ldcg(V.vb_nl + x);
+  P.vbflxs_t[x] = __ldcg(P.vbflxs_t + x) - WBARO * vnl + (1. + WBARO) * vml;
+  const double u00 = __ldcg(ub + x), u10 = __ldcg(ub + x + 1), u0m = __ldcg(ub + x - s), u1m = __ldcg(ub + x + 1 - s);
+  double q;
+  if (P.enscon)
+    q = -(u00 * P.scuyi[x] + u10 * P.scuyi[x + 1] + u0m * P.scuyi[x - s] + u1m * P.scuyi[x + 1 - s]) *
+        (V.wo * (P.pvo[x] + P.pvo[x + 1]) + V.wm * (P.pvm[x] + P.pvm[x + 1]) + V.wn * (P.pvn[x] + P.pvn[x + 1])) * .125;
+  else
+    q = -.25 * ((u00 * P.scuyi[x] + u0m * P.scuyi[x - s]) * (V.wo * P.pvo[x] + V.wm * P.pvm[x] + V.wn * P.pvn[x]) +
+                (u10 * P.scuyi[x + 1] + u1m * P.scuyi[x + 1 - s]) *
+                    (V.wo * P.pvo[x + 1] + V.wm * P.pvm[x + 1] + V.wn * P.pvn[x + 1]));
+  P.vbcors_t[x] = __ldcg(P.vbcors_t + x) + q;
+  const double pbc = __ldcg(V.pb_nl + x), pbs = __ldcg(V.pb_nl + x - s);
+  const double vtndcy = q + (V.wo * (P.pgfym_o[x] - (P.xiyp_o[x] * pbc - P.xiym_o[x] * pbs)) +
+                             V.wm * (P.pgfym_m[x] - (P.xiyp_m[x] * pbc - P.xiym_m[x] * pbs)) +
+                             V.wn * (P.pgfym_n[x] - (P.xiyp_n[x] * pbc - P.xiym_n[x] * pbs))) * P.scvyi[x];
+  const double vn = (1. - WBARO) * vml + WBARO * vnl +
+                    (1. + WBARO) * P.dlt * ((vtndcy + P.vtotn[x]) * P.scvx[x] * fmin(pbs, pbc) - P.vglue[x] * vml);
+  V.vb_nl[x] = fmax(-P.vminb[x], fmin(P.vmaxb[x], vn));
+}
+
+__global__ void __launch_bounds__(256, 2)
+bt_subcycle(Geom g, const BtP P, BtSched S, double* pb_t, double* ub_t, double* vb_t) {
+  cg::grid_group grid = cg::this_grid();
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
+  const long L = g.lev;
+  int ml = S.ml, nl = S.nl;
+  BtLv V;
+  auto for_range = [&](int i0, int i1, int j0, int j1, auto&& body) {
+    const int ni = i1 - i0 + 1;
+    const long n = (long)ni * (j1 - j0 + 1);
+    for (long idx = tid; idx < n; idx += nthr) body(ix2(g, i0 + (int)(idx % ni), j0 + (int)(idx / ni)));
+  };
+  for (int lll = S.lll0; lll < S.lll0 + S.nsub; ++lll) {
+    V.wo = S.woa * lll + S.wob; V.wn = S.wna * lll + S.wnb; V.wm = 1. - V.wo - V.wn;
+    V.pb_ml = pb_t + (long)(ml - 1) * L; V.pb_nl = pb_t + (long)(nl - 1) * L;
+    V.ub_ml = ub_t + (long)(ml - 1) * L; V.ub_nl = ub_t + (long)(nl - 1) * L;
+    V.vb_ml = vb_t + (long)(ml - 1) * L; V.vb_nl = vb_t + (long)(nl - 1) * L;
+    if (lll % 2 == 1) {
+      if (S.inkernel_halo) {
+        // xctilr(pb_t,1,2,2,2,halo_ps), (ubflx_t,..,halo_uv), (vbflx_t,1,2,2,3,halo_vv)  (:395-397)
+        for (int k = 1; k <= 2; ++k) {
+          halo_level<true>(g, pb_t + (long)(k - 1) * L, halo_ps, k, 2, 2, 1, 1, tid, nthr);
+          halo_level<true>(g, ub_t + (long)(k - 1) * L, halo_uv, k, 2, 2, 1, 1, tid, nthr);
+          halo_level<true>(g, vb_t + (long)(k - 1) * L, halo_vv, k, 2, 3, 1, 1, tid, nthr);
+        }
+        grid.sync();
+      }
+      for_range(-1, g.ii + 1, -1, g.jj + 2, [&](long x) { btp_continuity(g, P, V, x); });
+      grid.sync();
+      for_range(0, g.ii + 1, -1, g.jj + 2, [&](long x) { btp_ueq(g, P, V, V.vb_ml, x); });
+      grid.sync();
+      for_range(0, g.ii, 0, g.jj + 2, [&](long x) { btp_veq(g, P, V, V.ub_nl, x); });
+      grid.sync();
+    } else {
+      for_range(0, g.ii, 0, g.jj + 1, [&](long x) { btp_continuity(g, P, V, x); });
+      grid.sync();
+      for_range(0, g.ii, 1, g.jj + 1, [&](long x) { btp_veq(g, P, V, V.ub_ml, x); });
+      grid.sync();
+      for_range(1, g.ii, 1, g.jj, [&](long x) { btp_ueq(g, P, V, V.vb_nl, x); });
+      grid.sync();
+    }
+    const int t = ml; ml = nl; nl = t;
+  }
+}
+
 struct HvP {
   double *pb, *pbu, *pbv, *ub, *vb, *ubflx, *vbflx, *ubflxs, *vbflxs, *ubflxs_p, *vbflxs_p;
   double *pb_p, *pbu_p, *pbv_p, *ubcors_p, *vbcors_p, *pb_mn, *ub_mn, *vb_mn;
@@ -337,6 +455,15 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     LAUNCH_NAMED(name, kern, grid, 128, 0, g, P, extra, i0, i1, j0, j1);
   };
 
+  // cooperative persistent form unless option barotp_kernel=phases asks for one launch per phase
+  const bool persistent = c.option("barotp_kernel", "persistent") != "phases";
+  static int coop_grid = 0;
+  if (persistent && coop_grid == 0) {
+    int per_sm = 0, nsm = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bt_subcycle, 256, 0));
+    CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c.device));
+    coop_grid = std::max(1, per_sm) * nsm;
+  }
   int lll0 = 1, ml = 1, nl = 2;
   double woa = 0, wob = 0, wna = 0, wnb = 0;
   for (int nb = 1; nb <= 5; ++nb) {
@@ -353,27 +480,51 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
       dim3 grid(cdiv(g.ii + 2, 128), g.jj + 4);
       LAUNCH(bt_zero_acc, grid, 128, 0, g, P);
     }
-    for (int lll = lll0; lll <= lll0 + lstep / 2 - 1; ++lll) {
-      P.wo = woa * lll + wob; P.wn = wna * lll + wnb; P.wm = 1. - P.wo - P.wn;
-      set_levels(ml, nl);
-      if (lll % 2 == 1) {
-        halo_update(std::vector<HaloReq>{{pb_t, 2, halo_ps}, {ub_t, 2, halo_uv}}, 2, 2);
-        halo_update(vb_t, 2, 2, 3, halo_vv);
-        {
-          dim3 grid(cdiv(g.ii + 3, 128), g.jj + 4);
-          LAUNCH(bt_continuity, grid, 128, 0, g, P, -1, g.ii + 1, -1, g.jj + 2);
+    if (persistent) {
+      // one cooperative launch per halo interval: the whole block on one tile (halos refreshed
+      // in-kernel), two substeps per launch when band edges have to be exchanged in between
+      int lll = lll0;
+      const int lend = lll0 + lstep / 2;
+      while (lll < lend) {
+        BtSched S{};
+        S.lll0 = lll; S.ml = ml; S.nl = nl; S.woa = woa; S.wob = wob; S.wna = wna; S.wnb = wnb;
+        if (g.nranks == 1) { S.nsub = lend - lll; S.inkernel_halo = 1; }
+        else {
+          S.inkernel_halo = 0;
+          if (lll % 2 == 1) {
+            halo_update(std::vector<HaloReq>{{pb_t, 2, halo_ps}, {ub_t, 2, halo_uv}}, 2, 2);
+            halo_update(vb_t, 2, 2, 3, halo_vv);
+            S.nsub = std::min(2, lend - lll);
+          } else S.nsub = 1;
         }
-        range_launch("bt_ueq", bt_ueq, P.vb_ml, 0, g.ii + 1, -1, g.jj + 2);
-        range_launch("bt_veq", bt_veq, P.ub_nl, 0, g.ii, 0, g.jj + 2);
-      } else {
-        {
-          dim3 grid(cdiv(g.ii + 1, 128), g.jj + 2);
-          LAUNCH(bt_continuity, grid, 128, 0, g, P, 0, g.ii, 0, g.jj + 1);
-        }
-        range_launch("bt_veq", bt_veq, P.ub_ml, 0, g.ii, 1, g.jj + 1);
-        range_launch("bt_ueq", bt_ueq, P.vb_nl, 1, g.ii, 1, g.jj);
+        void* args[] = {(void*)&g, (void*)&P, (void*)&S, (void*)&pb_t, (void*)&ub_t, (void*)&vb_t};
+        launch_cooperative("bt_subcycle", (const void*)bt_subcycle, coop_grid, 256, args);
+        if (S.nsub % 2 == 1) std::swap(ml, nl);
+        lll += S.nsub;
       }
-      std::swap(ml, nl);
+    } else {
+      for (int lll = lll0; lll <= lll0 + lstep / 2 - 1; ++lll) {
+        P.wo = woa * lll + wob; P.wn = wna * lll + wnb; P.wm = 1. - P.wo - P.wn;
+        set_levels(ml, nl);
+        if (lll % 2 == 1) {
+          halo_update(std::vector<HaloReq>{{pb_t, 2, halo_ps}, {ub_t, 2, halo_uv}}, 2, 2);
+          halo_update(vb_t, 2, 2, 3, halo_vv);
+          {
+            dim3 grid(cdiv(g.ii + 3, 128), g.jj + 4);
+            LAUNCH(bt_continuity, grid, 128, 0, g, P, -1, g.ii + 1, -1, g.jj + 2);
+          }
+          range_launch("bt_ueq", bt_ueq, P.vb_ml, 0, g.ii + 1, -1, g.jj + 2);
+          range_launch("bt_veq", bt_veq, P.ub_nl, 0, g.ii, 0, g.jj + 2);
+        } else {
+          {
+            dim3 grid(cdiv(g.ii + 1, 128), g.jj + 2);
+            LAUNCH(bt_continuity, grid, 128, 0, g, P, 0, g.ii, 0, g.jj + 1);
+          }
+          range_launch("bt_veq", bt_veq, P.ub_ml, 0, g.ii, 1, g.jj + 1);
+          range_launch("bt_ueq", bt_ueq, P.vb_nl, 1, g.ii, 1, g.jj);
+        }
+        std::swap(ml, nl);
+      }
     }
     lll0 = lll0 + lstep / 2;
     set_levels(ml, nl);

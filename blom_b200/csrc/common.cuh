@@ -154,6 +154,16 @@ Ctx& C();
 #define LAUNCH(kernel, grid, block, smem, ...) \
   LAUNCH_NAMED(#kernel, kernel, grid, block, smem, __VA_ARGS__)
 
+// cooperative (grid-synchronising) launch on the library stream, counted and timed like LAUNCH
+inline void launch_cooperative(const char* kname, const void* kernel, int grid, int block, void** args) {
+  blom::Ctx& c_ = blom::C();
+  cudaEvent_t ke0_ = nullptr, ke1_ = nullptr;
+  if (c_.ktimers_on) { cudaEventCreate(&ke0_); cudaEventCreate(&ke1_); cudaEventRecord(ke0_, c_.stream); }
+  CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(block), args, 0, c_.stream));
+  if (c_.ktimers_on) { cudaEventRecord(ke1_, c_.stream); c_.kev.push_back(blom::Ctx::KEv{kname, ke0_, ke1_}); }
+  c_.launches++;
+}
+
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // RAII per-routine timer (device time via CUDA events on the library stream)

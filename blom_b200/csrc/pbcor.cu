@@ -62,32 +62,48 @@ __global__ void pbcor_prep(Geom g, double dlt, int ks, int kf, int lt, const int
 
 struct Flux3 { double f, f2, f3, ftr[MAXTR]; };
 
-// flux through the face at x whose "minus" cell is x-s (mod_pbcor.F90:166-187 'uc', :240-265 'dluc')
+// Level-independent part of one face (mod_pbcor.F90:166-187 'uc', :240-265 'dluc'): residual,
+// upstream cell and the column total / limited bottom pressure the flux is scaled with.
+struct FaceInv { bool on; double tot, div; long up; };
 template <bool DLUC>
-__device__ __forceinline__ Flux3 face_flux(long x, long s, int k, int kk, long lev, long ol /* state level offset */,
-                                           const int* __restrict__ mask, const double* __restrict__ tot,
-                                           const double* __restrict__ dp, const double* __restrict__ p,
-                                           const double* __restrict__ temp, const double* __restrict__ saln,
+__device__ __forceinline__ FaceInv face_prepare(long x, long s, int kk, long lev, const int* __restrict__ mask,
+                                                const double* __restrict__ tot, const double* __restrict__ p) {
+  FaceInv f; f.on = mask[x] == 1; f.tot = 0.; f.div = 1.; f.up = x;
+  if (!f.on) return f;
+  f.tot = tot[x];
+  f.up = f.tot > 0. ? x - s : x;
+  f.div = DLUC ? fmin(p[x + (long)kk * lev], p[x - s + (long)kk * lev]) : p[f.up + (long)kk * lev];
+  return f;
+}
+// level-dependent operands of one (i,j): own cell, the upstream cell of each of the four faces and the
+// old values of the six flux accumulators.  Loaded one level ahead (register double buffer) so that
+// the loads of level k+1 are in flight while level k is computed.
+struct LvlOps {
+  double dpc, tc, sc;
+  double dpf[4], tf[4], sf[4];   // upstream cell of faces u, v, east, north
+  double pk0[4], pk1[4];         // dluc: p(k), p(k+1) of those cells
+  double acc[6];                 // uflx, usflx, utflx, vflx, vsflx, vtflx
+};
+
+template <bool DLUC>
+__device__ __forceinline__ Flux3 face_flux(const FaceInv& F, int f, const LvlOps& L, long ol,
                                            const PbTr& T) {
   Flux3 r{};
-  if (mask[x] != 1) return r;
-  const double t = tot[x];
-  const long up = t > 0. ? x - s : x;
-  if (!DLUC) {
-    r.f = __dmul_rn(t, dp[up + ol]) / p[up + (long)kk * lev];
-  } else {
-    const double pbt = fmin(p[x + (long)kk * lev], p[x - s + (long)kk * lev]);
-    r.f = __dmul_rn(t, fmax(0., fmin(pbt, p[up + (long)k * lev]) - p[up + (long)(k - 1) * lev])) / pbt;
-  }
-  r.f2 = __dmul_rn(r.f, saln[up + ol]);
-  r.f3 = __dmul_rn(r.f, temp[up + ol]);
-  for (int nt = 0; nt < T.n; ++nt) r.ftr[nt] = __dmul_rn(r.f, T.t[nt][up + ol]);
+  if (!F.on) return r;
+  if (!DLUC) r.f = __dmul_rn(F.tot, L.dpf[f]) / F.div;
+  else r.f = __dmul_rn(F.tot, fmax(0., fmin(F.div, L.pk1[f]) - L.pk0[f])) / F.div;
+  r.f2 = __dmul_rn(r.f, L.sf[f]);
+  r.f3 = __dmul_rn(r.f, L.tf[f]);
+#pragma unroll
+  for (int nt = 0; nt < MAXTR; ++nt) if (nt < T.n) r.ftr[nt] = __dmul_rn(r.f, T.t[nt][F.up + ol]);
   return r;
 }
 
+// One thread per (i,j) and chunk of levels: the face invariants are prepared once, the level loop
+// streams dp/T/S of the cell and its four upstream candidates.
 template <int WHICH, bool DLUC>
 __global__ void __launch_bounds__(128)
-pbcor_update(Geom g, eos::Coef ec, int ks, int kf, const int* __restrict__ ip, const int* __restrict__ iu,
+pbcor_update(Geom g, eos::Coef ec, int ks, int kf, int kchunk, const int* __restrict__ ip, const int* __restrict__ iu,
              const int* __restrict__ iv, const double* __restrict__ utot, const double* __restrict__ vtot,
              const double* __restrict__ dp, const double* __restrict__ p, const double* __restrict__ temp,
              const double* __restrict__ saln, const double* __restrict__ scp2i, double* __restrict__ uflx,
@@ -95,56 +111,84 @@ pbcor_update(Geom g, eos::Coef ec, int ks, int kf, const int* __restrict__ ip, c
              double* __restrict__ vsflx, double* __restrict__ vtflx, double* __restrict__ dpB,
              double* __restrict__ tB, double* __restrict__ sB, double* __restrict__ sigma, PbTr T) {
   const double dpeps1 = 1.e-5, dpeps2 = 1.e-7;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1, k = blockIdx.z + 1;  // 1..ii+1, 1..jj+1
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;  // 1..ii+1, 1..jj+1
   if (i > g.ii + 1) return;
   const long x = ix2(g, i, j), lev = g.lev, s = g.ldi;
   const int kk = g.kdm;
-  const long ol = (long)(k + ks - 1) * lev, oa = (long)(k + kf - 1) * lev, ok = (long)(k - 1) * lev;
-  Flux3 fu{}, fv{};
-  if (j <= g.jj) {
-    fu = face_flux<DLUC>(x, 1, k, kk, lev, ol, iu, utot, dp, p, temp, saln, T);
-    if (iu[x] == 1) {
-      uflx[x + oa] = uflx[x + oa] + fu.f;
-      usflx[x + oa] = usflx[x + oa] + fu.f2;
-      utflx[x + oa] = utflx[x + oa] + fu.f3;
+  const int k0 = blockIdx.z * kchunk + 1, k1 = min(kk, k0 + kchunk - 1);
+  const bool uok = j <= g.jj, vok = i <= g.ii;
+  const bool cell = uok && vok && ip[x] == 1;
+  FaceInv F[4];
+#pragma unroll
+  for (int f = 0; f < 4; ++f) { F[f].on = false; F[f].tot = 0.; F[f].div = 1.; F[f].up = x; }
+  if (uok) F[0] = face_prepare<DLUC>(x, 1, kk, lev, iu, utot, p);
+  if (vok) F[1] = face_prepare<DLUC>(x, s, kk, lev, iv, vtot, p);
+  if (cell) {
+    F[2] = face_prepare<DLUC>(x + 1, 1, kk, lev, iu, utot, p);
+    F[3] = face_prepare<DLUC>(x + s, s, kk, lev, iv, vtot, p);
+  }
+  if (!F[0].on && !F[1].on && !cell) return;
+  const double a = cell ? scp2i[x] : 0.;
+
+  auto load = [&](int k, LvlOps& L) {
+    const long ol = (long)(k + ks - 1) * lev, oa = (long)(k + kf - 1) * lev;
+    L.dpc = dp[x + ol]; L.tc = temp[x + ol]; L.sc = saln[x + ol];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      L.dpf[f] = dp[F[f].up + ol]; L.tf[f] = temp[F[f].up + ol]; L.sf[f] = saln[F[f].up + ol];
+      if (DLUC) { L.pk0[f] = p[F[f].up + (long)(k - 1) * lev]; L.pk1[f] = p[F[f].up + (long)k * lev]; }
     }
-  }
-  if (i <= g.ii) {
-    fv = face_flux<DLUC>(x, s, k, kk, lev, ol, iv, vtot, dp, p, temp, saln, T);
-    if (iv[x] == 1) {
-      vflx[x + oa] = vflx[x + oa] + fv.f;
-      vsflx[x + oa] = vsflx[x + oa] + fv.f2;
-      vtflx[x + oa] = vtflx[x + oa] + fv.f3;
+    L.acc[0] = uflx[x + oa]; L.acc[1] = usflx[x + oa]; L.acc[2] = utflx[x + oa];
+    L.acc[3] = vflx[x + oa]; L.acc[4] = vsflx[x + oa]; L.acc[5] = vtflx[x + oa];
+  };
+  LvlOps cur, nxt;
+  load(k0, cur);
+  for (int k = k0; k <= k1; ++k) {
+    if (k < k1) load(k + 1, nxt);
+    const long ol = (long)(k + ks - 1) * lev, oa = (long)(k + kf - 1) * lev, ok = (long)(k - 1) * lev;
+    const Flux3 fu = face_flux<DLUC>(F[0], 0, cur, ol, T);
+    const Flux3 fv = face_flux<DLUC>(F[1], 1, cur, ol, T);
+    if (F[0].on) {
+      uflx[x + oa] = cur.acc[0] + fu.f;
+      usflx[x + oa] = cur.acc[1] + fu.f2;
+      utflx[x + oa] = cur.acc[2] + fu.f3;
     }
+    if (F[1].on) {
+      vflx[x + oa] = cur.acc[3] + fv.f;
+      vsflx[x + oa] = cur.acc[4] + fv.f2;
+      vtflx[x + oa] = cur.acc[5] + fv.f3;
+    }
+    if (cell) {
+      const Flux3 fue = face_flux<DLUC>(F[2], 2, cur, ol, T);
+      const Flux3 fvn = face_flux<DLUC>(F[3], 3, cur, ol, T);
+      double dpo = cur.dpc, dpn, dpni;
+      const double dm = fue.f - fu.f + fvn.f - fv.f;
+      const double ds = fue.f2 - fu.f2 + fvn.f2 - fv.f2;
+      const double dt = fue.f3 - fu.f3 + fvn.f3 - fv.f3;
+      if (WHICH == 1) {
+        dpn = fmax(0., dpo - dm * a);
+        dpo = dpo + dpeps1;
+        dpni = 1. / (dpn + dpeps1);
+      } else {
+        dpn = dpo - a * dm;
+        dpni = 1. / dpn;
+      }
+      const double sn = (dpo * cur.sc - ds * a) * dpni;
+      const double tn = (dpo * cur.tc - dt * a) * dpni;
+#pragma unroll
+      for (int nt = 0; nt < MAXTR; ++nt) if (nt < T.n) {
+        const double dtr = fue.ftr[nt] - fu.ftr[nt] + fvn.ftr[nt] - fv.ftr[nt];
+        T.tb[nt][x + ok] = (dpo * T.t[nt][x + ol] - dtr * a) * dpni;
+      }
+      if (WHICH == 2) {
+        sigma[x + ol] = eos::sig(ec, tn, sn);
+        dpn = dpn - epsilp;
+      }
+      if (dpn < dpeps2) dpn = 0.;
+      dpB[x + ok] = dpn; tB[x + ok] = tn; sB[x + ok] = sn;
+    }
+    cur = nxt;
   }
-  if (i > g.ii || j > g.jj || ip[x] != 1) return;
-  const Flux3 fue = face_flux<DLUC>(x + 1, 1, k, kk, lev, ol, iu, utot, dp, p, temp, saln, T);
-  const Flux3 fvn = face_flux<DLUC>(x + s, s, k, kk, lev, ol, iv, vtot, dp, p, temp, saln, T);
-  const double a = scp2i[x];
-  double dpo = dp[x + ol], dpn, dpni;
-  const double dm = fue.f - fu.f + fvn.f - fv.f;
-  const double ds = fue.f2 - fu.f2 + fvn.f2 - fv.f2;
-  const double dt = fue.f3 - fu.f3 + fvn.f3 - fv.f3;
-  if (WHICH == 1) {
-    dpn = fmax(0., dpo - dm * a);
-    dpo = dpo + dpeps1;
-    dpni = 1. / (dpn + dpeps1);
-  } else {
-    dpn = dpo - a * dm;
-    dpni = 1. / dpn;
-  }
-  const double sn = (dpo * saln[x + ol] - ds * a) * dpni;
-  const double tn = (dpo * temp[x + ol] - dt * a) * dpni;
-  for (int nt = 0; nt < T.n; ++nt) {
-    const double dtr = fue.ftr[nt] - fu.ftr[nt] + fvn.ftr[nt] - fv.ftr[nt];
-    T.tb[nt][x + ok] = (dpo * T.t[nt][x + ol] - dtr * a) * dpni;
-  }
-  if (WHICH == 2) {
-    sigma[x + ol] = eos::sig(ec, tn, sn);
-    dpn = dpn - epsilp;
-  }
-  if (dpn < dpeps2) dpn = 0.;
-  dpB[x + ok] = dpn; tB[x + ok] = tn; sB[x + ok] = sn;
 }
 
 template <int WHICH>
@@ -214,15 +258,16 @@ void pbcor_run(int m, int n, int mm, int nn, int k1m) {
                  c.dev("uflx"), c.dev("vflx"), utot, vtot);
   }
   {
-    dim3 grid(cdiv(g.ii + 1, 128), g.jj + 1, kk);
+    const int kchunk = kk >= 16 ? 8 : kk;
+    dim3 grid(cdiv(g.ii + 1, 128), g.jj + 1, cdiv(kk, kchunk));
     const char* nm = WHICH == 1 ? "pbcor_update<1>" : "pbcor_update<2>";
     const eos::Coef ec = WHICH == 2 ? eos::host_coef() : eos::Coef{};  // only pbcor2 refreshes sigma
     if (dluc)
-      LAUNCH_NAMED(nm, (pbcor_update<WHICH, true>), grid, 128, 0, g, ec, ks, kf, ip, iu, iv, utot, vtot,
+      LAUNCH_NAMED(nm, (pbcor_update<WHICH, true>), grid, 128, 0, g, ec, ks, kf, kchunk, ip, iu, iv, utot, vtot,
                    dp, p, temp, saln, c.dev("scp2i"), c.dev("uflx"), c.dev("usflx"), c.dev("utflx"), c.dev("vflx"),
                    c.dev("vsflx"), c.dev("vtflx"), dpB, tB, sB, c.dev("sigma"), T);
     else
-      LAUNCH_NAMED(nm, (pbcor_update<WHICH, false>), grid, 128, 0, g, ec, ks, kf, ip, iu, iv, utot, vtot,
+      LAUNCH_NAMED(nm, (pbcor_update<WHICH, false>), grid, 128, 0, g, ec, ks, kf, kchunk, ip, iu, iv, utot, vtot,
                    dp, p, temp, saln, c.dev("scp2i"), c.dev("uflx"), c.dev("usflx"), c.dev("utflx"), c.dev("vflx"),
                    c.dev("vsflx"), c.dev("vtflx"), dpB, tB, sB, c.dev("sigma"), T);
   }
