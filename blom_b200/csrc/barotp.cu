@@ -196,6 +196,8 @@ __global__ void bt_veq(Geom g, BtP P, const double* __restrict__ ub, int i0, int
 // fields are read with ld.global.cg (L1 is not coherent between the SMs of one launch); the ~40
 // read-only coefficient arrays use the normal cached path.  Operation order per cell is the one of
 // bt_continuity / bt_ueq / bt_veq above, so results are bit-identical to the launch-per-phase form.
+constexpr int BT_THREADS = 512, BT_MINBLK = 2;
+
 struct BtSched {
   int lll0, nsub, ml, nl;
   double woa, wob, wna, wnb;
@@ -258,9 +260,25 @@ __device__ __forceinline__ void btp_veq(const Geom& g, const BtP& P, const BtLv&
   V.vb_nl[x] = fmax(-P.vminb[x], fmin(P.vmaxb[x], vn));
 }
 
-__global__ void __launch_bounds__(256, 2)
-bt_subcycle(Geom g, const BtP P, BtSched S, double* pb_t, double* ub_t, double* vb_t) {
-  cg::grid_group grid = cg::this_grid();
+// Grid-wide barrier on a monotonically increasing counter (one atomic per block and barrier); cheaper
+// than the generic cooperative-groups barrier for the ~440 barriers of one call.  The cooperative
+// launch guarantees co-residency.  Writes of the block are made visible by bar.sync + the cumulative
+// gpu-scope fence of thread 0; read-write data is read with ld.global.cg afterwards.
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    while (*(volatile unsigned*)ctr < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(BT_THREADS, BT_MINBLK)
+bt_subcycle(Geom g, const BtP P, BtSched S, double* pb_t, double* ub_t, double* vb_t, unsigned* ctr) {
+  unsigned target = 0;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
   const long L = g.lev;
   int ml = S.ml, nl = S.nl;
@@ -283,21 +301,21 @@ bt_subcycle(Geom g, const BtP P, BtSched S, double* pb_t, double* ub_t, double* 
           halo_level<true>(g, ub_t + (long)(k - 1) * L, halo_uv, k, 2, 2, 1, 1, tid, nthr);
           halo_level<true>(g, vb_t + (long)(k - 1) * L, halo_vv, k, 2, 3, 1, 1, tid, nthr);
         }
-        grid.sync();
+        grid_barrier(ctr, target);
       }
       for_range(-1, g.ii + 1, -1, g.jj + 2, [&](long x) { btp_continuity(g, P, V, x); });
-      grid.sync();
+      grid_barrier(ctr, target);
       for_range(0, g.ii + 1, -1, g.jj + 2, [&](long x) { btp_ueq(g, P, V, V.vb_ml, x); });
-      grid.sync();
+      grid_barrier(ctr, target);
       for_range(0, g.ii, 0, g.jj + 2, [&](long x) { btp_veq(g, P, V, V.ub_nl, x); });
-      grid.sync();
+      grid_barrier(ctr, target);
     } else {
       for_range(0, g.ii, 0, g.jj + 1, [&](long x) { btp_continuity(g, P, V, x); });
-      grid.sync();
+      grid_barrier(ctr, target);
       for_range(0, g.ii, 1, g.jj + 1, [&](long x) { btp_veq(g, P, V, V.ub_ml, x); });
-      grid.sync();
+      grid_barrier(ctr, target);
       for_range(1, g.ii, 1, g.jj, [&](long x) { btp_ueq(g, P, V, V.vb_nl, x); });
-      grid.sync();
+      grid_barrier(ctr, target);
     }
     const int t = ml; ml = nl; nl = t;
   }
@@ -460,10 +478,11 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   static int coop_grid = 0;
   if (persistent && coop_grid == 0) {
     int per_sm = 0, nsm = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bt_subcycle, 256, 0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bt_subcycle, BT_THREADS, 0));
     CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c.device));
     coop_grid = std::max(1, per_sm) * nsm;
   }
+  unsigned* bar_ctr = reinterpret_cast<unsigned*>(c.owned("barotp_barrier", 1));
   int lll0 = 1, ml = 1, nl = 2;
   double woa = 0, wob = 0, wna = 0, wnb = 0;
   for (int nb = 1; nb <= 5; ++nb) {
@@ -497,8 +516,9 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
             S.nsub = std::min(2, lend - lll);
           } else S.nsub = 1;
         }
-        void* args[] = {(void*)&g, (void*)&P, (void*)&S, (void*)&pb_t, (void*)&ub_t, (void*)&vb_t};
-        launch_cooperative("bt_subcycle", (const void*)bt_subcycle, coop_grid, 256, args);
+        CUDA_CHECK(cudaMemsetAsync(bar_ctr, 0, sizeof(unsigned), c.stream));
+        void* args[] = {(void*)&g, (void*)&P, (void*)&S, (void*)&pb_t, (void*)&ub_t, (void*)&vb_t, (void*)&bar_ctr};
+        launch_cooperative("bt_subcycle", (const void*)bt_subcycle, coop_grid, BT_THREADS, args);
         if (S.nsub % 2 == 1) std::swap(ml, nl);
         lll += S.nsub;
       }

@@ -90,6 +90,11 @@ __global__ void eddtra_mldens(Geom g, eos::Coef ec, int nn, const int* __restric
 }
 
 // One thread per face column.  DIR 0: u faces (minus point i-1), DIR 1: v faces (j-1).
+// Only the limited total interface flux mfl(k) is kept in a thread-local array; the interface
+// pressures, the GM / submesoscale interface fluxes and the available thicknesses dlm/dlp are
+// recomputed from their (cached) inputs where they are needed — the same expressions on the same
+// operands, so the values are identical to the reference's stored work arrays, at a fifth of the
+// local-memory traffic.
 template <int DIR>
 __global__ void __launch_bounds__(128)
 eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int* __restrict__ mask,
@@ -112,8 +117,7 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
   const int kk = g.kdm;
   const double ffac = .0625, fface = .99 * ffac, eps = 1.e-14, c5_21 = 5. / 21.;
 
-  double puv[KM + 2], mflgm[KM + 2], mflsm[KM + 2], dlm[KM + 1], dlp[KM + 1];
-  double* mfl = puv;  // puv is dead once the interface fluxes are built
+  double mfl[KM + 2];
 
   const double hml = .5 * (hml_tfbnd[xm] + hml_tfbnd[x]);
   // depth-invariant submesoscale transport component (:1130-1185)
@@ -135,46 +139,61 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
   const double mfleps = eps * epsilp * sc2[x];
   const double et2mf = -grav * rho0 * delt1 * scl[x];
   const double pb = pbf[x + (long)(n - 1) * lev];
+  const double am = scp2[xm], ap = scp2[x];
 
+  // last layer with mass and the interface pressure below it (:1222-1229)
   int kmax = 1;
-  puv[1] = ptf;
-  for (int k = 1; k <= kk; ++k) {
-    const long o = (long)(k + nn - 1) * lev;
-    puv[k + 1] = puv[k] + dpf[x + o];
-    if (dp[xm + o] > epsilp || dp[x + o] > epsilp) kmax = k;
-  }
-  const double pml = fmin(puv[1] + hml * onem, puv[kmax + 1]);
-  const double dpmli = 1. / (pml - puv[1]);
-  int kml = kmax + 1;
-  for (int k = kmax; k >= 2; --k) {
-    if (puv[k] > pml) kml = k; else break;
-  }
-  for (int k = kml; k <= kmax; ++k) {
-    const long o1 = (long)(k - 2) * lev, o2 = (long)(k - 1) * lev;
-    const double kappa = .25 * (difint[xm + o1] + difint[x + o1] + difint[xm + o2] + difint[x + o2]);
-    mflgm[k] = -kappa * nslp[x + o2] * et2mf;
-  }
-  mflgm[kmax + 1] = 0.;
-  mflgm[1] = 0.;
-  mflsm[1] = 0.;
-  for (int k = 2; k <= kml - 1; ++k) {
-    mflgm[k] = mflgm[kml] * (puv[k] - puv[1]) * dpmli;
-    double q = 2. * (puv[1] - puv[k]) * dpmli + 1.;
-    q = q * q;
-    mflsm[k] = -upssm * (1. - q) * (1. + c5_21 * q) * et2mf;
-  }
-  for (int k = kml; k <= kmax + 1; ++k) mflsm[k] = 0.;
-  for (int k = 1; k <= kmax + 1; ++k) mfl[k] = mflgm[k] + mflsm[k];
+  double pbot;
   {
-    double pm0 = p[xm], pp0 = p[x];
-    for (int k = 1; k <= kmax; ++k) {
-      const double pm1 = p[xm + (long)k * lev], pp1 = p[x + (long)k * lev];
-      dlm[k] = fmax(0., fmin(pm1, pb) - fmax(pm0, ptf));
-      dlp[k] = fmax(0., fmin(pp1, pb) - fmax(pp0, ptf));
-      pm0 = pm1; pp0 = pp1;
+    double pk = ptf;
+    pbot = ptf;
+    for (int k = 1; k <= kk; ++k) {
+      const long o = (long)(k + nn - 1) * lev;
+      pk = pk + dpf[x + o];
+      if (k == 1 || dp[xm + o] > epsilp || dp[x + o] > epsilp) { kmax = k; pbot = pk; }
     }
   }
-  const double am = scp2[xm], ap = scp2[x];
+  const double pml = fmin(ptf + hml * onem, pbot);
+  const double dpmli = 1. / (pml - ptf);
+  // first interface below the mixed layer base (:1241-1248); puv is non-decreasing in k
+  int kml = kmax + 1;
+  {
+    double pk = ptf;
+    for (int k = 2; k <= kmax; ++k) {
+      pk = pk + dpf[x + (long)(k - 1 + nn - 1) * lev];
+      if (pk > pml) { kml = k; break; }
+    }
+  }
+  // GM interface flux below the mixed layer (:1252-1256)
+  auto gm_below = [&](int k) -> double {
+    const long o1 = (long)(k - 2) * lev, o2 = (long)(k - 1) * lev;
+    const double kappa = .25 * (difint[xm + o1] + difint[x + o1] + difint[xm + o2] + difint[x + o2]);
+    return -kappa * nslp[x + o2] * et2mf;
+  };
+  const double gm_kml = kml <= kmax ? gm_below(kml) : 0.;   // mflgm(kmax+1) = 0
+  // GM and submesoscale flux at interface k with pressure puv_k (:1252-1288)
+  auto gm_sm = [&](int k, double puv_k, double& gm, double& sm) {
+    if (k == 1 || k == kmax + 1) { gm = 0.; sm = 0.; }
+    else if (k >= kml) { gm = k == kml ? gm_kml : gm_below(k); sm = 0.; }
+    else {
+      gm = gm_kml * (puv_k - ptf) * dpmli;
+      double q = 2. * (ptf - puv_k) * dpmli + 1.;
+      q = q * q;
+      sm = -upssm * (1. - q) * (1. + c5_21 * q) * et2mf;
+    }
+  };
+  {
+    double pk = ptf;
+    for (int k = 1; k <= kmax + 1; ++k) {
+      double gm, sm;
+      gm_sm(k, pk, gm, sm);
+      mfl[k] = gm + sm;
+      if (k <= kmax) pk = pk + dpf[x + (long)(k + nn - 1) * lev];
+    }
+  }
+  // available thicknesses at the two scalar points (:1304-1309)
+  auto dl_m = [&](int k) { return fmax(0., fmin(p[xm + (long)k * lev], pb) - fmax(p[xm + (long)(k - 1) * lev], ptf)); };
+  auto dl_p = [&](int k) { return fmax(0., fmin(p[x + (long)k * lev], pb) - fmax(p[x + (long)(k - 1) * lev], ptf)); };
 
   // alternate downward/upward limiter sweeps (:1318-1394)
   bool changed = true;
@@ -188,8 +207,9 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
     for (int s = 0, k = k0; s < kmax; ++s, k += kdir) {
       const double lo = mfl[k], hi = mfl[k + 1];
       if (fabs(hi - lo) > fmax(mfleps, eps * fabs(hi + lo))) {
-        if (hi - lo > ffac * fmax(epsilp, dlm[k]) * am) {
-          const double q = fface * dlm[k] * am;
+        const double dlm = dl_m(k), dlp = dl_p(k);
+        if (hi - lo > ffac * fmax(epsilp, dlm) * am) {
+          const double q = fface * dlm * am;
           if (hi > -lo) {
             if (lo > -.5 * q) mfl[k + 1] = lo + q;
             else { mfl[k + 1] = .5 * q; mfl[k] = -mfl[k + 1]; }
@@ -198,8 +218,8 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
             else { mfl[k] = -.5 * q; mfl[k + 1] = -mfl[k]; }
           }
           changed = true;
-        } else if (hi - lo < -ffac * fmax(epsilp, dlp[k]) * ap) {
-          const double q = fface * dlp[k] * ap;
+        } else if (hi - lo < -ffac * fmax(epsilp, dlp) * ap) {
+          const double q = fface * dlp * ap;
           if (hi < -lo) {
             if (lo < .5 * q) mfl[k + 1] = lo - q;
             else { mfl[k + 1] = -.5 * q; mfl[k] = -mfl[k + 1]; }
@@ -213,12 +233,12 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
     }
   }
 
-  // split the limited total back into GM and submesoscale parts (:1398-1436)
-  for (int k = 1; k <= kmax + 1; ++k) {
-    const double f = mfl[k];
-    double gm = mflgm[k], sm = mflsm[k];
+  // split the limited total back into GM and submesoscale parts (:1398-1436), one interface at a time
+  auto split = [&](int k, double puv_k, double& f, double& gm, double& sm) {
+    gm_sm(k, puv_k, gm, sm);
+    f = mfl[k];
     if (fabs(f) < mfleps) {
-      mfl[k] = 0.; gm = 0.; sm = 0.;
+      f = 0.; gm = 0.; sm = 0.;
     } else if (f > 0.) {
       if (gm > sm) {
         if (f > 2. * sm) gm = f - sm; else { gm = .5 * f; sm = gm; }
@@ -232,20 +252,25 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
         if (f < 2. * gm) sm = f - gm; else { sm = .5 * f; gm = sm; }
       }
     }
-    mflgm[k] = gm; mflsm[k] = sm;
-  }
+  };
 
   // layer fluxes + heat/salt components (:1442-1468, :1876-1902)
+  double pk = ptf, f_lo, gm_lo, sm_lo;
+  split(1, pk, f_lo, gm_lo, sm_lo);
   for (int k = 1; k <= kk; ++k) {
     const long xk = x + (long)(k + mm - 1) * lev, xmk = xm + (long)(k + mm - 1) * lev;
     double fgm = 0., fsm = 0.;
     if (k <= kmax) {
-      if (fabs(mfl[k + 1] - mfl[k]) > fmax(mfleps, eps * fabs(mfl[k + 1] + mfl[k]))) {
-        fgm = mflgm[k + 1] - mflgm[k];
-        fsm = mflsm[k + 1] - mflsm[k];
+      pk = pk + dpf[x + (long)(k + nn - 1) * lev];
+      double f_hi, gm_hi, sm_hi;
+      split(k + 1, pk, f_hi, gm_hi, sm_hi);
+      if (fabs(f_hi - f_lo) > fmax(mfleps, eps * fabs(f_hi + f_lo))) {
+        fgm = gm_hi - gm_lo;
+        fsm = sm_hi - sm_lo;
       }
-      if (fgm + fsm > ffac * fmax(epsilp, dlm[k]) * am) atomicMax(err, 2);
-      if (fgm + fsm < -ffac * fmax(epsilp, dlp[k]) * ap) atomicMax(err, 3);
+      if (fgm + fsm > ffac * fmax(epsilp, dl_m(k)) * am) atomicMax(err, 2);
+      if (fgm + fsm < -ffac * fmax(epsilp, dl_p(k)) * ap) atomicMax(err, 3);
+      f_lo = f_hi; gm_lo = gm_hi; sm_lo = sm_hi;
     }
     const double qt = .5 * (temp[xmk] + temp[xk]);
     const double qs = .5 * (saln[xmk] + saln[xk]);

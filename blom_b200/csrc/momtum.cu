@@ -38,6 +38,9 @@ struct MtP {
   double *uja, *ujb, *via, *vib, *dl2u, *dl2v, *defor1, *defor2, *potvor, *vsc2u, *vsc4u, *vsc2v, *vsc4v, *drag;
   // updated velocities are staged so that both tendency kernels see the pre-update u,v
   double *su_m, *su_n, *sv_m, *sv_n;
+  // level-independent barotropic part of the total velocities, ubflxs_p*tsfac/(pbu*scuy) at time
+  // levels n and m, evaluated once per call (mt_pressures) instead of once per use and level
+  double *ubn, *ubm, *vbn, *vbm;
   double delt1, tsfac, mdv2hi, mdv2lo, mdv4hi, mdv4lo, vsc2hi, vsc2lo, vsc4hi, vsc4lo, cbar, cb;
   int m, n, mm, nn, mommth /*0 enscon 1 enecon 2 enedis*/, isopyc;
 };
@@ -51,32 +54,28 @@ __device__ __forceinline__ double sq(double a) { return a * a; }
 __device__ __forceinline__ double utotn_at(const Geom& g, const MtP& P, int i, int j, int k) {
   const long x = ix2(g, i, j);
   if (i >= -1 && i <= g.ii + 2 && j >= -1 && j <= g.jj + 2 && P.iu[x] == 1) {
-    const long x2 = x + (long)(P.n - 1) * g.lev;
-    return P.u[x + (long)(k + P.nn - 1) * g.lev] + P.ubflxs_p[x2] * P.tsfac / (P.pbu[x2] * P.scuy[x]);
+    return P.u[x + (long)(k + P.nn - 1) * g.lev] + P.ubn[x];
   }
   return P.utotn[x];
 }
 __device__ __forceinline__ double vtotn_at(const Geom& g, const MtP& P, int i, int j, int k) {
   const long x = ix2(g, i, j);
   if (i >= -1 && i <= g.ii + 2 && j >= -1 && j <= g.jj + 2 && P.iv[x] == 1) {
-    const long x2 = x + (long)(P.n - 1) * g.lev;
-    return P.v[x + (long)(k + P.nn - 1) * g.lev] + P.vbflxs_p[x2] * P.tsfac / (P.pbv[x2] * P.scvx[x]);
+    return P.v[x + (long)(k + P.nn - 1) * g.lev] + P.vbn[x];
   }
   return P.vtotn[x];
 }
 __device__ __forceinline__ double utotm_at(const Geom& g, const MtP& P, int i, int j, int k) {
   const long x = ix2(g, i, j);
   if (i >= 0 && i <= g.ii + 1 && j >= 0 && j <= g.jj + 1 && P.iu[x] == 1) {
-    const long x2 = x + (long)(P.m - 1) * g.lev;
-    return P.u[x + (long)(k + P.mm - 1) * g.lev] + P.ubflxs_p[x2] * P.tsfac / (P.pbu[x2] * P.scuy[x]);
+    return P.u[x + (long)(k + P.mm - 1) * g.lev] + P.ubm[x];
   }
   return 0.;
 }
 __device__ __forceinline__ double vtotm_at(const Geom& g, const MtP& P, int i, int j, int k) {
   const long x = ix2(g, i, j);
   if (i >= 0 && i <= g.ii + 1 && j >= 0 && j <= g.jj + 1 && P.iv[x] == 1) {
-    const long x2 = x + (long)(P.m - 1) * g.lev;
-    return P.v[x + (long)(k + P.mm - 1) * g.lev] + P.vbflxs_p[x2] * P.tsfac / (P.pbv[x2] * P.scvx[x]);
+    return P.v[x + (long)(k + P.mm - 1) * g.lev] + P.vbm[x];
   }
   return 0.;
 }
@@ -128,13 +127,18 @@ __global__ void mt_pressures(Geom g, MtP P) {
     double pk = P.p[x];
     for (int k = 1; k <= g.kdm; ++k) { pk = pk + P.dp[x + (long)(k + P.mm - 1) * g.lev]; P.p[x + (long)k * g.lev] = pk; }
   }
+  const long xn2 = x + (long)(P.n - 1) * g.lev, xm2 = x + (long)(P.m - 1) * g.lev;
   if (P.iu[x] == 1) {
     double pk = P.pu[x];
     for (int k = 1; k <= g.kdm; ++k) { pk = pk + P.dpu[x + (long)(k + P.mm - 1) * g.lev]; P.pu[x + (long)k * g.lev] = pk; }
+    P.ubn[x] = P.ubflxs_p[xn2] * P.tsfac / (P.pbu[xn2] * P.scuy[x]);
+    P.ubm[x] = P.ubflxs_p[xm2] * P.tsfac / (P.pbu[xm2] * P.scuy[x]);
   }
   if (P.iv[x] == 1) {
     double pk = P.pv[x];
     for (int k = 1; k <= g.kdm; ++k) { pk = pk + P.dpv[x + (long)(k + P.mm - 1) * g.lev]; P.pv[x + (long)k * g.lev] = pk; }
+    P.vbn[x] = P.vbflxs_p[xn2] * P.tsfac / (P.pbv[xn2] * P.scvx[x]);
+    P.vbm[x] = P.vbflxs_p[xm2] * P.tsfac / (P.pbv[xm2] * P.scvx[x]);
   }
 }
 // bottom drag (:259-293) on 0..ii x 0..jj
@@ -581,6 +585,8 @@ void momtum_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   S(vsc4v); S(su_m); S(su_n); S(sv_m); S(sv_n);
 #undef S
   P.drag = c.owned("momtum_drag", 1);
+  P.ubn = c.owned("momtum_ubn", 1); P.ubm = c.owned("momtum_ubm", 1);
+  P.vbn = c.owned("momtum_vbn", 1); P.vbm = c.owned("momtum_vbm", 1);
 
   { dim3 grid(cdiv(g.ii + 4, 128), g.jj + 4); LAUNCH(mt_pressures, grid, 128, 0, g, P); }
   { dim3 grid(cdiv(g.ii + 1, 128), g.jj + 1); LAUNCH(mt_drag, grid, 128, 0, g, P); }
