@@ -39,19 +39,33 @@ from blom_b200.driver import HotPath, available_routines, STEP_SEQUENCE  # noqa:
 
 # compulsory 8-byte words moved per interior cell per call (SURVEY.md §8a/§8d, T=2 scalars)
 WORDS = {"advect": 10 + 29, "diffus": 19, "pgforc": 15, "momtum": 29, "tmsmt1": 6, "tmsmt2": 13,
-         "eddtra": 21, "init_fluxes": 6}
-# per-kernel algorithmic words per interior cell per LAUNCH (DESIGN.md "kernels" table)
-KERNEL_WORDS = {
-    "cppm_flux<i>": 10 + 2 + 2,   # R dp,T,S,hel,her,ca,cross-ca,p(2),flux(3)  W dp,T,S,flux(3) -> see DESIGN.md
-    "cppm_flux<j>": 10 + 2 + 2,
-    "cppm_hedges<i>": 4, "cppm_hedges<j>": 4,
-    "advect_flux_area": 10,
-    "diffus_flux": 15, "diffus_update": 10,
-    "pg_dynh_march": 13, "pg_dpuv": 5, "pg_finalize": 4,
-    "tmsmt1_kernel": 6, "tmsmt2_kernel": 13,
-    "zero_fluxes": 6,
+         "eddtra": 21, "init_fluxes": 6, "pbcor1": 18, "pbcor2": 19}
+# per-kernel ALGORITHMIC 8-byte words per unit and launch (distinct arrays read + written once;
+# DESIGN.md §3).  unit: "3d" = interior (i,j,k) cells of the tile, "2d" = (i,j) points,
+# "bt" = (i,j) points x barotropic substeps covered by one launch.
+KERNELS = {
+    "zero_fluxes": (6, "3d"),
+    "tmsmt1_kernel": (6, "3d"), "tmsmt2_kernel": (13, "3d"),
+    "eddtra_column<u>": (7 + 6, "3d"), "eddtra_column<v>": (7 + 6, "3d"),   # R dp,dpu,p,difint,nslp,T,S  W 6 fluxes
+    "advect_flux_area": (10, "3d"),
+    "cppm_hedges<i>": (4, "3d"), "cppm_hedges<j>": (4, "3d"),               # R dp,(cross ca)  W hel,her
+    "cppm_flux<i>": (12 + 6, "3d"), "cppm_flux<j>": (12 + 6, "3d"),         # R dp,T,S,hel,her,ca,cross ca(2),p,flx(3)  W dp,T,S,flx(3)
+    "pbcor_update<1>": (9 + 9, "3d"), "pbcor_update<2>": (9 + 10, "3d"),     # R dp,T,S,flx(6)  W dp,T,S,flx(6)(,sigma)
+    "pbcor_finish<1>": (3 + 4, "3d"), "pbcor_finish<2>": (3 + 4, "3d"),
+    "pbcor_prep<1>": (3 + 1, "3d"), "pbcor_prep<2>": (3 + 2, "3d"),
+    "diffus_flux": (4 + 4 + 4 + 4, "3d"), "diffus_update": (7 + 3, "3d"),
+    "pg_p_from_dp": (2, "3d"), "pg_dpuv": (1 + 4, "3d"), "pg_dynh_march": (5 + 8, "3d"), "pg_finalize": (4, "3d"),
+    "mt_pressures": (3 + 3, "3d"), "mt_drag": (3, "3d"), "mt_aux": (4 + 7, "3d"), "mt_vort": (7 + 4, "3d"),
+    "mt_visc": (2 + 4, "3d"), "mt_update": (21 + 2, "3d"), "mt_update_v": (21 + 2, "3d"), "mt_column": (8 + 4, "3d"),
+    "bt_subcycle": (53, "bt"), "bt_ueq": (23, "2d"), "bt_veq": (23, "2d"), "bt_continuity": (7, "2d"),
 }
 BT_WORDS_PER_SUBSTEP = 53  # 46R + 7W distinct 2-D arrays per substep
+
+
+def measured_traffic():
+    """dram__bytes_read+write per launch from the committed ncu --set full captures (same config)."""
+    p = ROOT / "profiles" / "traffic.json"
+    return json.loads(p.read_text()) if p.exists() else {}
 
 
 def peaks():
@@ -63,42 +77,68 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (profiling recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks/throttle reasons (profiling recipe).  Started before the warm-up so the tool is
+    already polling when the timed region begins; only samples stamped inside [mark_start, mark_end]
+    are summarised."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
+    def mark_start(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        rows = [[c.strip() for c in r.split(",")] for r in Path(self.f.name).read_text().strip().splitlines()
+                if r.count(",") >= 8]
         os.unlink(self.f.name)
-        if not rows:
+        sel = []
+        for r in rows:
+            try:
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f")
+            except ValueError:
+                continue
+            if self.t0 is None or (self.t0 <= ts <= (self.t1 or ts)):
+                sel.append(r)
+        if not sel:
+            sel = rows[-3:]   # region shorter than the polling interval: nearest samples
+            out["note"] = "no sample fell inside the timed region; nearest samples used"
+        if not sel:
             return out
-        sm = [float(r[1]) for r in rows]
+        sm = [float(r[1]) for r in sel]
         out["sm_mhz"] = float(np.median(sm))
-        out["sm_max_mhz"] = float(rows[0][2])
+        out["sm_max_mhz"] = float(sel[0][2])
+        out["power_w_max"] = max(float(r[3]) for r in sel)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for k, nm in enumerate(names):
-            if any("Active" in r[5 + k] and "Not" not in r[5 + k] for r in rows):
+            if any("Active" in r[5 + k] and "Not" not in r[5 + k] for r in sel):
                 out["reasons"].append(nm)
-        out["samples"] = len(rows)
+        out["samples"] = len(sel)
         return out
 
 
@@ -113,70 +153,109 @@ def sypd(t_step_s, baclin):
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle on a bounded row-band sample of the same grid
 # ------------------------------------------------------------------------------------------
-def oracle_sample(config, routines, steps, warmup, target_rows=None):
-    from oracle.oracle import Oracle, build
-    from blom_b200.lib import time_levels
-    build()
-    itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS[config]
-    # sample = a closed band of `rows` rows, full i extent and all layers, same seed/fields
-    # ~7.5e6 cells per step is ~8 s of one host core per step for the full path
-    rows = target_rows or max(16, min(jtdm, int(7.5e6 // (itdm * kdm))))
-    sreg = nreg if rows == jtdm else (1 if nreg in (1, 2, 3) else 0)
-    syn = synth.Synth(itdm, rows, kdm, sreg, baclin=baclin, batrop=batrop)
-    grid = syn.grid(); state = syn.state(grid)
-    o = Oracle(itdm, rows, kdm, sreg)
-    arrs = {**grid, **state}
-    o.register_all(arrs)
-    scal = syn.scalars(1)
-    o.set_scalars(**scal)
-    synth.fill_halos(o, arrs)
-    o.bigrid("depths")
-    masks = {k: o.get_int(k).reshape(syn.ldj, syn.ldi) for k in ("ip", "iu", "iv", "iq")}
-    synth.derive(grid, state, masks, time_levels(1, kdm), scal, o)
-    o.inieos(); o.numerical_bounds()
-    if "advect" in routines:
-        o.init_cppm()
+def _oracle_worker(config, routines, steps, warmup, rows, widx, barrier, q):
+    """One host process stepping a closed band of `rows` rows of the grid with the oracle."""
+    try:
+        from oracle.oracle import Oracle
+        from blom_b200.lib import time_levels
+        itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS[config]
+        sreg = nreg if rows == jtdm else (1 if nreg in (1, 2, 3) else 0)
+        # same seed/fields as the GPU arm; band `widx` of the grid, closed at its own edges
+        syn = synth.Synth(itdm, rows, kdm, sreg, baclin=baclin, batrop=batrop, seed=20240611 + widx)
+        grid = syn.grid(); state = syn.state(grid)
+        o = Oracle(itdm, rows, kdm, sreg)
+        arrs = {**grid, **state}
+        o.register_all(arrs)
+        scal = syn.scalars(1)
+        o.set_scalars(**scal)
+        synth.fill_halos(o, arrs)
+        o.bigrid("depths")
+        masks = {k: o.get_int(k).reshape(syn.ldj, syn.ldi) for k in ("ip", "iu", "iv", "iq")}
+        synth.derive(grid, state, masks, time_levels(1, kdm), scal, o)
+        o.inieos(); o.numerical_bounds()
+        if "advect" in routines:
+            o.init_cppm()
 
-    def one(nstep):
-        m, n, mm, nn, k1m, k1n = time_levels(nstep, kdm)
-        o.set_scalar("nstep", nstep)
-        for r in routines:
-            if r == "tmsmt1":
-                o.tmsmt1(nn)
-                # same out-of-scope halo refreshes as HotPath.halo_refresh_out_of_scope
-                o.xctilr("u", 1, 2 * kdm, 2, 2, 13); o.xctilr("v", 1, 2 * kdm, 2, 2, 14)
-                for nm, it in (("ubflxs_p", 13), ("vbflxs_p", 14), ("pbu", 3), ("pbv", 4)):
-                    o.xctilr(nm, 1, 2, 2, 2, it)
-                o.xctilr("temp", 1, 2 * kdm, 3, 3, 1); o.xctilr("saln", 1, 2 * kdm, 3, 3, 1)
-            elif r == "tmsmt2":
-                o.tmsmt2(m, mm, nn, k1m)
-            else:
-                getattr(o, r)(m, n, mm, nn, k1m, k1n)
-    ns = 1
-    for _ in range(warmup):
-        one(ns); ns += 1
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one(ns); ns += 1
-    t = (time.perf_counter() - t0) / max(steps, 1)
-    # scale the sample time to the full grid by cell count
-    scale = (itdm * jtdm * kdm) / float(itdm * rows * kdm)
+        def one(nstep):
+            m, n, mm, nn, k1m, k1n = time_levels(nstep, kdm)
+            o.set_scalar("nstep", nstep)
+            for r in routines:
+                if r == "tmsmt1":
+                    o.tmsmt1(nn)
+                    # same out-of-scope halo refreshes as HotPath.halo_refresh_out_of_scope
+                    o.xctilr("u", 1, 2 * kdm, 2, 2, 13); o.xctilr("v", 1, 2 * kdm, 2, 2, 14)
+                    for nm, it in (("ubflxs_p", 13), ("vbflxs_p", 14), ("pbu", 3), ("pbv", 4)):
+                        o.xctilr(nm, 1, 2, 2, 2, it)
+                    o.xctilr("temp", 1, 2 * kdm, 3, 3, 1); o.xctilr("saln", 1, 2 * kdm, 3, 3, 1)
+                elif r == "tmsmt2":
+                    o.tmsmt2(m, mm, nn, k1m)
+                else:
+                    getattr(o, r)(m, n, mm, nn, k1m, k1n)
+        ns = 1
+        for _ in range(warmup):
+            one(ns); ns += 1
+        barrier.wait()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one(ns); ns += 1
+        barrier.wait()
+        q.put((widx, (time.perf_counter() - t0) / max(steps, 1)))
+    except Exception as e:  # noqa: BLE001
+        q.put((widx, repr(e)))
+        try:
+            barrier.abort()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def oracle_sample(config, routines, steps, warmup, cores=None, max_rows_per_worker=None):
+    """The reference algorithm (oracle, C++ restatement) on the host cores: `cores` processes, each
+    stepping its own closed band of the grid (bands are independent -> no halo exchange cost, which
+    flatters the CPU).  Returns (SYPD scaled to the full grid, seconds per sample step, description, cores)."""
+    import multiprocessing as mp
+    from oracle.oracle import build
+    build()
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS[config]
+    cores = cores or max(1, len(os.sched_getaffinity(0)))
+    rows = max(16, -(-jtdm // cores))
+    if max_rows_per_worker:
+        rows = min(rows, max_rows_per_worker)
+    rows = min(rows, jtdm)
+    ctx = mp.get_context("spawn")
+    barrier = ctx.Barrier(cores)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_oracle_worker, args=(config, routines, steps, warmup, rows, w, barrier, q))
+             for w in range(cores)]
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    bad = [r for r in res if not isinstance(r[1], float)]
+    if bad:
+        raise RuntimeError(f"oracle worker failed: {bad[0][1]}")
+    t = max(r[1] for r in res)
+    # scale the sample (cores bands of `rows` rows) to the full grid by cell count
+    scale = (itdm * jtdm * kdm) / float(itdm * rows * cores * kdm)
     t_full = t * scale
-    sample = (f"{rows} of {jtdm} rows x {itdm} x {kdm} layers (closed band, same seed), {steps} steps after "
-              f"{warmup} warm-up, time scaled by {scale:.2f} to the full grid")
-    return sypd(t_full, baclin), t, sample
+    sample = (f"{cores} host processes x {rows} rows x {itdm} x {kdm} layers (independent closed bands of the "
+              f"same synthetic generator; {rows * cores} of {jtdm} rows), {steps} steps after {warmup} warm-up, "
+              f"time scaled by {scale:.3f} to the full grid")
+    return sypd(t_full, baclin), t, sample, cores
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     routines = [r for r in STEP_SEQUENCE if r in available_routines()]
-    v, t, sample = oracle_sample(args.config, routines, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    v, t, sample, cores = oracle_sample(args.config, routines, max(1, min(args.steps, 3)), min(args.warmup, 1),
+                                        max_rows_per_worker=64)
     line = {"impl": "reference", "metric": "simulated_years_per_day_hot_path", "value": v, "unit": "SYPD",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": args.config, "routines": routines},
-            "cpu_baseline": {"value": v, "unit": "SYPD", "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "SYPD", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "SYPD", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "C++ restatement of the reference algorithm (oracle/); the Fortran reference cannot be "
                     "built in this image (no Fortran compiler, meson or netCDF)"}
@@ -187,8 +266,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=os.environ.get("BLOM_BENCH_CONFIG", "tnx1v4"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,17 +318,19 @@ def main():
             dist.barrier()
 
     # ---- device-resident timing ---------------------------------------------------------
+    clocks = ClockSampler(local_rank)
     for _ in range(args.warmup):
         hp.advance()
     barrier()
     g.launch_count_reset()
-    clocks = ClockSampler(local_rank)
+    clocks.mark_start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
         hp.advance()
     e1.record(stream)
     barrier()
+    clocks.mark_end()
     launches = g.launch_count()
     t_ms = e0.elapsed_time(e1)
     tt = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
@@ -294,28 +375,33 @@ def main():
     cells2d_local = hp.itdm * hp.jj
     routines_ms = {k: v["ms"] / v["calls"] for k, v in rt.items() if v["calls"]}
     ksum = sum(v["ms"] for v in kt.values()) or 1.0
-    # dominant kernel by total device time among kernels with a known algorithmic byte count
-    best = None
-    for name, v in kt.items():
-        if name in KERNEL_WORDS:
-            nbytes = 8.0 * KERNEL_WORDS[name] * cells_local
-        elif name in ("bt_ueq", "bt_veq", "bt_continuity"):
-            nbytes = 8.0 * {"bt_ueq": 23, "bt_veq": 23, "bt_continuity": 7}[name] * cells2d_local
-        else:
-            continue
-        if best is None or v["ms"] > best[1]["ms"]:
-            best = (name, v, nbytes)
-    roof = None
-    if best is not None:
-        name, v, nbytes = best
-        dur = v["ms"] / v["launches"] / 1e3
-        ach = nbytes / dur / 1e9
-        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "avg_launch_us": dur * 1e6, "share_of_step": v["ms"] / ksum,
-                "algorithmic_bytes_per_launch": nbytes}
-    # whole-step algorithmic bandwidth
+    # roofline per kernel: algorithmic bytes / live per-launch CUDA-event time; the dominant kernel
+    # (largest share of the step) is the headline `roofline`, the rest goes to `roofline_top`
     lstep = hp.scalars["lstep"]
+    traffic = measured_traffic().get(args.config, {})
+    roofs = []
+    for name, v in kt.items():
+        if name not in KERNELS or not v["launches"]:
+            continue
+        w, unit = KERNELS[name]
+        dur = v["ms"] / v["launches"] / 1e3
+        if unit == "3d":
+            nbytes = 8.0 * w * cells_local
+        elif unit == "2d":
+            nbytes = 8.0 * w * cells2d_local
+        else:  # substeps covered by one launch: 5*lstep/2 substeps over the launches of one step
+            nbytes = 8.0 * w * cells2d_local * (5 * lstep // 2) / (v["launches"] / 2.0)
+        ach = nbytes / dur / 1e9
+        r = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+             "frac": ach / hbm_peak, "traffic": traffic.get(name), "peak_source": peak_src,
+             "avg_launch_us": dur * 1e6, "share_of_step": v["ms"] / ksum, "algorithmic_bytes_per_launch": nbytes}
+        if unit == "bt":
+            r["note"] = ("streamed model (53 words per 2-D point and substep); at this grid size the 2-D working "
+                         "set is L2-resident, so DRAM traffic is far below the algorithmic bytes")
+        roofs.append(r)
+    roofs.sort(key=lambda r: -r["share_of_step"])
+    roof = roofs[0] if roofs else None
+    # whole-step algorithmic bandwidth
     alg_bytes = 8.0 * hp.cells * sum(WORDS.get(r, 0) for r in hp.routines)
     if "barotp" in hp.routines:
         alg_bytes += 8.0 * BT_WORDS_PER_SUBSTEP * hp.itdm * hp.jtdm * (5 * lstep // 2)
@@ -334,14 +420,16 @@ def main():
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roof,
+        "roofline_top": [{k: r[k] for k in ("kernel", "achieved", "frac", "share_of_step", "avg_launch_us", "traffic")}
+                         for r in roofs[1:8]],
         "step_algorithmic_GBps": alg_bytes / t_step / 1e9,
         "step_frac_of_hbm_peak": alg_bytes / t_step / 1e9 / hbm_peak,
         "routines_ms": routines_ms,
         "kernels_ms_per_step": {k: v["ms"] / 2.0 for k, v in sorted(kt.items(), key=lambda kv: -kv[1]["ms"])[:12]},
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, t, sample = oracle_sample(args.config, hp.routines, 2, 1)
-        line["cpu_baseline"] = {"value": v, "unit": "SYPD", "cores": 1, "kind": "port", "sample": sample}
+        v, t, sample, cores = oracle_sample(args.config, hp.routines, 2, 1, max_rows_per_worker=64)
+        line["cpu_baseline"] = {"value": v, "unit": "SYPD", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

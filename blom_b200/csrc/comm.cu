@@ -20,6 +20,7 @@ struct NcclApi {
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -32,7 +33,7 @@ void load_nccl() {
   if (!N.h) throw std::runtime_error(std::string("blomgpu: cannot dlopen libnccl: ") + dlerror());
 #define SYM(f) *(void**)(&N.f) = dlsym(N.h, "nccl" #f); \
   if (!N.f) throw std::runtime_error("blomgpu: libnccl lacks nccl" #f);
-  SYM(GetUniqueId) SYM(CommInitRank) SYM(Send) SYM(Recv) SYM(AllReduce) SYM(GroupStart)
+  SYM(GetUniqueId) SYM(CommInitRank) SYM(Send) SYM(Recv) SYM(AllReduce) SYM(AllGather) SYM(GroupStart)
   SYM(GroupEnd) SYM(GetErrorString)
 #undef SYM
 }
@@ -63,6 +64,170 @@ __global__ void pack_rows(Geom g, XBatch b, int nhl, int j_first, double* __rest
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// Peer-to-peer band-edge exchange over NVLink (CUDA IPC): every rank owns a
+// mailbox; a neighbour packs its edge rows STRAIGHT into that mailbox with
+// ordinary stores on the mapped peer pointer, publishes a sequence number in
+// the mailbox's flag word (system-scope fence + store), and the owner's next
+// kernel spins on the flag before unpacking.  One pack+publish launch and one
+// wait+unpack launch per exchange, no host round trip, no NCCL kernels.  Two
+// parity slots per direction are enough: a rank can only run one exchange
+// ahead of its neighbour (its wait for exchange n+1 completes after the
+// neighbour's push n+1, which follows the neighbour's unpack n in stream order).
+// Falls back to the NCCL path when IPC peer mapping is unavailable
+// (option comm=nccl forces it).
+// ---------------------------------------------------------------------------
+struct P2P {
+  bool tried = false, on = false;
+  char* block = nullptr;                 // [flags+counters 256 B][2 dirs][2 parity][cap] doubles
+  size_t cap = 0;                        // doubles per slot
+  char* peer[2] = {nullptr, nullptr};    // mapped blocks of the south / north neighbour
+  unsigned long long seq = 0;
+  unsigned long long done_target[2] = {0, 0};   // cumulative block count of the pushes per direction
+};
+P2P g_p2p;
+constexpr size_t P2P_HDR = 256;
+
+__host__ __device__ inline double* p2p_slot(char* block, size_t cap, int dir, int parity) {
+  return reinterpret_cast<double*>(block + P2P_HDR) + ((size_t)dir * 2 + parity) * cap;
+}
+// header words: [0],[1] flags "from south","from north"; [2],[3] block-done counters of the pushes
+__host__ __device__ inline unsigned long long* p2p_word(char* block, int w) {
+  return reinterpret_cast<unsigned long long*>(block) + w;
+}
+
+void p2p_close() {
+  P2P& q = g_p2p;
+  for (int d = 0; d < 2; ++d) if (q.peer[d]) { cudaIpcCloseMemHandle(q.peer[d]); q.peer[d] = nullptr; }
+  if (q.block) { cudaFree(q.block); q.block = nullptr; }
+  q.cap = 0; q.on = false;
+}
+
+// (re)allocate the mailbox for `cap` doubles per slot and map the neighbours' mailboxes.  Collective:
+// every rank issues the same sequence of exchanges, so all ranks arrive here together.
+bool p2p_setup(size_t cap) {
+  Ctx& c = C(); const Geom& g = c.g;
+  P2P& q = g_p2p;
+  ncclComm_t comm = (ncclComm_t)c.nccl;
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  p2p_close();
+  const size_t bytes = P2P_HDR + 4 * cap * sizeof(double);
+  CUDA_CHECK(cudaMalloc(&q.block, bytes));
+  CUDA_CHECK(cudaMemset(q.block, 0, P2P_HDR));
+  cudaIpcMemHandle_t mine;
+  bool ok = cudaIpcGetMemHandle(&mine, q.block) == cudaSuccess;
+  // all-gather the handles (and an ok byte) through NCCL
+  const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+  std::vector<char> h_all(rec * g.nranks, 0), h_mine(rec, 0);
+  std::memcpy(h_mine.data(), &mine, sizeof mine);
+  h_mine[sizeof mine] = ok ? 1 : 0;
+  char *d_mine = nullptr, *d_all = nullptr;
+  CUDA_CHECK(cudaMalloc(&d_mine, rec)); CUDA_CHECK(cudaMalloc(&d_all, rec * g.nranks));
+  CUDA_CHECK(cudaMemcpy(d_mine, h_mine.data(), rec, cudaMemcpyHostToDevice));
+  NCCL_CHECK(N.AllGather(d_mine, d_all, rec, ncclChar, comm, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  CUDA_CHECK(cudaMemcpy(h_all.data(), d_all, rec * g.nranks, cudaMemcpyDeviceToHost));
+  cudaFree(d_mine); cudaFree(d_all);
+  for (int r = 0; r < g.nranks; ++r) ok = ok && h_all[r * rec + sizeof mine] == 1;
+  if (ok) {
+    const int nb[2] = {g.rank - 1, g.rank + 1};
+    for (int d = 0; d < 2 && ok; ++d) {
+      if (nb[d] < 0 || nb[d] >= g.nranks) continue;
+      cudaIpcMemHandle_t h; std::memcpy(&h, h_all.data() + nb[d] * rec, sizeof h);
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); }
+      q.peer[d] = static_cast<char*>(ptr);
+    }
+  }
+  // agree on the outcome (a rank that could not map a neighbour takes everybody to the NCCL path)
+  int* d_ok = nullptr; CUDA_CHECK(cudaMalloc(&d_ok, sizeof(int)));
+  int h_ok = ok ? 1 : 0;
+  CUDA_CHECK(cudaMemcpy(d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice));
+  NCCL_CHECK(N.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, c.stream));
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  CUDA_CHECK(cudaMemcpy(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d_ok);
+  q.seq = 0; q.done_target[0] = q.done_target[1] = 0;
+  if (!h_ok) { p2p_close(); return false; }
+  q.cap = cap; q.on = true;
+  return true;
+}
+
+// pack the edge rows of every request into the neighbour's mailbox; the last block to finish
+// publishes `seq` in the neighbour's flag word.  blockIdx.z = request, blockIdx.y = level,
+// gridDim.x blocks per level; dir 0: rows 1..nhl go south, dir 1: rows jj-nhl+1..jj go north.
+__global__ void p2p_push(Geom g, XBatch b, int nhl, int dir, char* my_block, char* peer_block, size_t cap, int parity,
+                         unsigned long long seq, unsigned long long done_target) {
+  const int r = blockIdx.z, k = blockIdx.y;
+  if (r < b.n && k < b.nlev[r]) {
+    const double* a = b.base[r] + (long)k * g.lev;
+    // data sent south lands in the neighbour's "from north" slot (1) and vice versa
+    double* q = p2p_slot(peer_block, cap, 1 - dir, parity) + b.off[r] + (long)k * nhl * g.ii;
+    const int j_first = dir == 0 ? 1 : g.jj - nhl + 1;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < (long)nhl * g.ii; t += (long)gridDim.x * blockDim.x) {
+      const int rr = (int)(t / g.ii), i = (int)(t % g.ii) + 1;
+      q[t] = a[ix2(g, i, j_first + rr)];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* done = p2p_word(my_block, 2 + dir);
+    const unsigned long long prev = atomicAdd(done, 1ull);
+    if (prev + 1 == done_target) {   // cumulative count of all pushes so far in this direction
+      __threadfence_system();
+      *(volatile unsigned long long*)p2p_word(peer_block, 1 - dir) = seq;
+      __threadfence_system();
+    }
+  }
+}
+
+// wait for the neighbour's rows of exchange `seq`, then unpack them into the halo rows
+__global__ void p2p_unpack(Geom g, XBatch b, int nhl, int dir, char* my_block, size_t cap, int parity,
+                           unsigned long long seq) {
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* flag = p2p_word(my_block, dir);
+    while (*flag < seq) {}
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int r = blockIdx.z, k = blockIdx.y;
+  if (r >= b.n || k >= b.nlev[r]) return;
+  double* a = b.base[r] + (long)k * g.lev;
+  const double* q = p2p_slot(my_block, cap, dir, parity) + b.off[r] + (long)k * nhl * g.ii;
+  const int j_first = dir == 0 ? 1 - nhl : g.jj + 1;   // dir 0: rows from the south neighbour
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < (long)nhl * g.ii; t += (long)gridDim.x * blockDim.x) {
+    const int rr = (int)(t / g.ii), i = (int)(t % g.ii) + 1;
+    a[ix2(g, i, j_first + rr)] = __ldcg(q + t);
+  }
+}
+
+// returns false if the P2P path is not available (caller uses NCCL)
+bool exchange_ns_p2p(const XBatch& b, long tot, int maxlev, int nhl) {
+  Ctx& c = C(); const Geom& g = c.g;
+  P2P& q = g_p2p;
+  if (c.option("comm", "p2p") != "p2p") return false;
+  if (q.tried && !q.on) return false;
+  if (!q.on || (size_t)tot > q.cap) {
+    q.tried = true;
+    // room for the largest exchange of the step: 12 fields x kdm levels x nbdy rows
+    const size_t want = std::max<size_t>((size_t)tot, (size_t)12 * g.kdm * g.nb * g.ii);
+    if (!p2p_setup(want)) return false;
+  }
+  const bool has_s = g.rank > 0, has_n = g.rank + 1 < g.nranks;
+  const unsigned long long seq = ++q.seq;
+  const int parity = (int)(seq & 1ull);
+  dim3 grid(std::max(1, std::min(cdiv((long)nhl * g.ii, 256), 32)), maxlev, b.n);
+  const unsigned nblk = grid.x * grid.y * grid.z;
+  if (has_s) { q.done_target[0] += nblk; LAUNCH(p2p_push, grid, 256, 0, g, b, nhl, 0, q.block, q.peer[0], q.cap, parity, seq, q.done_target[0]); }
+  if (has_n) { q.done_target[1] += nblk; LAUNCH(p2p_push, grid, 256, 0, g, b, nhl, 1, q.block, q.peer[1], q.cap, parity, seq, q.done_target[1]); }
+  if (has_s) LAUNCH(p2p_unpack, grid, 256, 0, g, b, nhl, 0, q.block, q.cap, parity, seq);
+  if (has_n) LAUNCH(p2p_unpack, grid, 256, 0, g, b, nhl, 1, q.block, q.cap, parity, seq);
+  return true;
+}
+
+void comm_release_p2p() { g_p2p.tried = false; p2p_close(); }
+
 // Fill the nhl halo rows on band edges shared with a neighbouring GPU.
 void exchange_ns(const std::vector<HaloReq>& reqs, int nhl) {
   Ctx& c = C(); const Geom& g = c.g;
@@ -77,6 +242,7 @@ void exchange_ns(const std::vector<HaloReq>& reqs, int nhl) {
       tot += (long)reqs[s + r].nlev * nhl * g.ii;
       maxlev = std::max(maxlev, b.nlev[r]);
     }
+    if (exchange_ns_p2p(b, tot, maxlev, nhl)) continue;
     if ((size_t)tot > c.halo_cap) {
       CUDA_CHECK(cudaStreamSynchronize(c.stream));
       for (int q = 0; q < 2; ++q) {

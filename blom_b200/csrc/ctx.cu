@@ -5,6 +5,8 @@
 
 namespace blom {
 
+void comm_release_p2p();  // comm.cu
+
 Ctx& C() { static Ctx c; return c; }
 
 double* Ctx::owned(const std::string& n, int nlev) {
@@ -108,6 +110,7 @@ static void do_init(const int* dims, const int* tile, int device) {
 static void do_finalize() {
   Ctx& c = C();
   if (c.stream) cudaStreamSynchronize(c.stream);
+  comm_release_p2p();
   for (auto& kv : c.f) if (kv.second.d) cudaFree(kv.second.d);
   for (auto& kv : c.fi) if (kv.second.d) cudaFree(kv.second.d);
   if (c.d_red) cudaFree(c.d_red);

@@ -17,11 +17,11 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("cfg", ["mid1", "mid2"])
-def test_two_band_parity(cfg, tmp_path):
+@pytest.mark.parametrize("cfg,comm", [("mid1", "p2p"), ("mid2", "p2p"), ("mid2", "nccl")])
+def test_two_band_parity(cfg, comm, tmp_path):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, MGPU_TMP=str(tmp_path))
+    env = dict(os.environ, MGPU_TMP=str(tmp_path), MGPU_COMM=comm)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29517", str(ROOT / "tools/mgpu_parity.py"),
                         cfg, "3"], capture_output=True, text=True, env=env, timeout=600)

@@ -45,7 +45,9 @@ def main():
     uid = bytes(t.cpu().numpy().tobytes())
     tmp = os.environ.get("MGPU_TMP") or tempfile.gettempdir()
 
-    hp = HotPath(cfg, ntr=1, nstep=1, rank=rank, nranks=world, device=lr, parity=True, comm_uid=uid)
+    comm = os.environ.get("MGPU_COMM", "p2p")   # p2p: CUDA-IPC mailboxes over NVLink; nccl: send/recv
+    hp = HotPath(cfg, ntr=1, nstep=1, rank=rank, nranks=world, device=lr, parity=True, comm_uid=uid,
+                 options={"comm": comm})
     sums = []
     for _ in range(nsteps):
         hp.advance()
@@ -58,7 +60,7 @@ def main():
     hp.finalize()
     dist.barrier()
     ok = True
-    out = {"config": cfg, "n_gpus": world, "steps": nsteps}
+    out = {"config": cfg, "n_gpus": world, "steps": nsteps, "comm": comm}
     if rank == 0:
         one = HotPath(cfg, ntr=1, nstep=1, device=lr, parity=True)
         for _ in range(nsteps):
