@@ -396,8 +396,10 @@ def main():
              "frac": ach / hbm_peak, "traffic": traffic.get(name), "peak_source": peak_src,
              "avg_launch_us": dur * 1e6, "share_of_step": v["ms"] / ksum, "algorithmic_bytes_per_launch": nbytes}
         if unit == "bt":
-            r["note"] = ("streamed model (53 words per 2-D point and substep); at this grid size the 2-D working "
-                         "set is L2-resident, so DRAM traffic is far below the algorithmic bytes")
+            ws_mb = 8.0 * w * cells2d_local / 1e6
+            r["note"] = (f"streamed model (53 words per 2-D point and substep); 2-D working set {ws_mb:.0f} MB "
+                         + ("fits the 126 MB L2, so DRAM traffic is far below the algorithmic bytes"
+                            if ws_mb < 120 else "exceeds the 126 MB L2, so every substep streams from HBM"))
         roofs.append(r)
     roofs.sort(key=lambda r: -r["share_of_step"])
     roof = roofs[0] if roofs else None
@@ -413,7 +415,7 @@ def main():
         "config": {"workload": args.config, "grid": [hp.itdm, hp.jtdm, hp.kdm], "nreg": hp.nreg,
                    "routines": hp.routines, "missing_routines": [r for r in STEP_SEQUENCE if r not in hp.routines],
                    "barotropic_substeps": 5 * lstep // 2, "parallelism": f"j-bands x{world}",
-                   "cache": "state arrays (>=5 GB at tnx1v4) exceed the 126 MB L2; no flush needed",
+                   "cache": "3-D state (>= 5 GB per GPU) exceeds the 126 MB L2, every step streams it anew; no flush needed",
                    "setup_s": round(t_setup, 1)},
         "e2e": {"value": sypd(t_e2e, hp.baclin), "unit": "SYPD", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e},

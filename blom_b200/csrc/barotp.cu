@@ -13,6 +13,7 @@
 // one by-value parameter block.
 #include "common.cuh"
 #include "halo.cuh"
+#include "p2p.cuh"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -202,6 +203,10 @@ struct BtSched {
   int lll0, nsub, ml, nl;
   double woa, wob, wna, wnb;
   int inkernel_halo;
+  // band edges exchanged in-kernel through the peer mailboxes (multi-GPU); seq0 = sequence number of
+  // the first exchange of this launch
+  int p2p;
+  unsigned long long seq0;
 };
 
 // time-level pointers and time weights of the current substep
@@ -277,8 +282,9 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
 }
 
 __global__ void __launch_bounds__(BT_THREADS, BT_MINBLK)
-bt_subcycle(Geom g, const BtP P, BtSched S, double* pb_t, double* ub_t, double* vb_t, unsigned* ctr) {
+bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_t, double* vb_t, unsigned* ctr) {
   unsigned target = 0;
+  unsigned long long seq = S.seq0;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
   const long L = g.lev;
   int ml = S.ml, nl = S.nl;
@@ -294,6 +300,55 @@ bt_subcycle(Geom g, const BtP P, BtSched S, double* pb_t, double* ub_t, double* 
     V.ub_ml = ub_t + (long)(ml - 1) * L; V.ub_nl = ub_t + (long)(nl - 1) * L;
     V.vb_ml = vb_t + (long)(ml - 1) * L; V.vb_nl = vb_t + (long)(nl - 1) * L;
     if (lll % 2 == 1) {
+      if (S.p2p) {
+        // band edges: pack the nh edge rows of the three fields (2 levels each) straight into the
+        // neighbours' mailboxes over NVLink, publish the sequence number, wait for theirs, unpack
+        const int parity = (int)(seq & 1ull);
+        const int ii = g.ii;
+        const long npay = 14L * ii;   // (2+2+3) rows x 2 levels
+        for (int dir = 0; dir < 2; ++dir) {
+          if (!(dir == 0 ? X.has_s : X.has_n)) continue;
+          double* q = p2p_slot(X.peer[dir], X.cap, 1 - dir, parity);
+          for (long t = tid; t < npay; t += nthr) {
+            const int row = (int)(t / ii), i = (int)(t % ii) + 1;
+            // rows 0..3: pb_t (lev1 r0,r1, lev2 r0,r1); 4..7: ub_t; 8..13: vb_t (3 rows per level)
+            const double* a; int nh, rl;
+            if (row < 4) { a = pb_t; nh = 2; rl = row; } else if (row < 8) { a = ub_t; nh = 2; rl = row - 4; }
+            else { a = vb_t; nh = 3; rl = row - 8; }
+            const int k = rl / nh, rr = rl % nh;
+            const int j = dir == 0 ? 1 + rr : g.jj - nh + 1 + rr;
+            q[t] = __ldcg(a + (long)k * L + ix2(g, i, j));
+          }
+        }
+        if (tid < npay) __threadfence_system();   // only threads that stored to a peer
+        grid_barrier(ctr, target);
+        if (tid == 0) {
+          if (X.has_s) *(volatile unsigned long long*)p2p_word(X.peer[0], 1) = seq;
+          if (X.has_n) *(volatile unsigned long long*)p2p_word(X.peer[1], 0) = seq;
+          __threadfence_system();
+        }
+        if (threadIdx.x == 0) {
+          if (X.has_s) { volatile unsigned long long* f = p2p_word(X.my_block, 0); while (*f < seq) {} }
+          if (X.has_n) { volatile unsigned long long* f = p2p_word(X.my_block, 1); while (*f < seq) {} }
+          __threadfence_system();
+        }
+        __syncthreads();
+        for (int dir = 0; dir < 2; ++dir) {
+          if (!(dir == 0 ? X.has_s : X.has_n)) continue;
+          const double* q = p2p_slot(X.my_block, X.cap, dir, parity);
+          for (long t = tid; t < npay; t += nthr) {
+            const int row = (int)(t / ii), i = (int)(t % ii) + 1;
+            double* a; int nh, rl;
+            if (row < 4) { a = pb_t; nh = 2; rl = row; } else if (row < 8) { a = ub_t; nh = 2; rl = row - 4; }
+            else { a = vb_t; nh = 3; rl = row - 8; }
+            const int k = rl / nh, rr = rl % nh;
+            const int j = dir == 0 ? 1 - nh + rr : g.jj + 1 + rr;
+            a[(long)k * L + ix2(g, i, j)] = __ldcg(q + t);
+          }
+        }
+        grid_barrier(ctr, target);
+        ++seq;
+      }
       if (S.inkernel_halo) {
         // xctilr(pb_t,1,2,2,2,halo_ps), (ubflx_t,..,halo_uv), (vbflx_t,1,2,2,3,halo_vv)  (:395-397)
         for (int k = 1; k <= 2; ++k) {
@@ -507,8 +562,14 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
       while (lll < lend) {
         BtSched S{};
         S.lll0 = lll; S.ml = ml; S.nl = nl; S.woa = woa; S.wob = wob; S.wna = wna; S.wnb = wnb;
+        P2PView X{};
         if (g.nranks == 1) { S.nsub = lend - lll; S.inkernel_halo = 1; }
-        else {
+        else if (p2p_view(&X, (size_t)14 * g.ii)) {
+          S.nsub = lend - lll; S.inkernel_halo = 1; S.p2p = 1;
+          int nexch = 0;
+          for (int l = lll; l < lend; ++l) nexch += l % 2;
+          S.seq0 = p2p_reserve_seq(nexch);
+        } else {
           S.inkernel_halo = 0;
           if (lll % 2 == 1) {
             halo_update(std::vector<HaloReq>{{pb_t, 2, halo_ps}, {ub_t, 2, halo_uv}}, 2, 2);
@@ -517,7 +578,7 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
           } else S.nsub = 1;
         }
         CUDA_CHECK(cudaMemsetAsync(bar_ctr, 0, sizeof(unsigned), c.stream));
-        void* args[] = {(void*)&g, (void*)&P, (void*)&S, (void*)&pb_t, (void*)&ub_t, (void*)&vb_t, (void*)&bar_ctr};
+        void* args[] = {(void*)&g, (void*)&P, (void*)&S, (void*)&X, (void*)&pb_t, (void*)&ub_t, (void*)&vb_t, (void*)&bar_ctr};
         launch_cooperative("bt_subcycle", (const void*)bt_subcycle, coop_grid, BT_THREADS, args);
         if (S.nsub % 2 == 1) std::swap(ml, nl);
         lll += S.nsub;

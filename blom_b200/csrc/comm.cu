@@ -4,6 +4,7 @@
 // the library stream over NVLink.  NCCL is dlopen'ed at comm_init time so a
 // single-GPU run has no NCCL dependency.
 #include "common.cuh"
+#include "p2p.cuh"
 #include "../../include/blomgpu.h"
 #include <nccl.h>
 #include <dlfcn.h>
@@ -86,15 +87,6 @@ struct P2P {
   unsigned long long done_target[2] = {0, 0};   // cumulative block count of the pushes per direction
 };
 P2P g_p2p;
-constexpr size_t P2P_HDR = 256;
-
-__host__ __device__ inline double* p2p_slot(char* block, size_t cap, int dir, int parity) {
-  return reinterpret_cast<double*>(block + P2P_HDR) + ((size_t)dir * 2 + parity) * cap;
-}
-// header words: [0],[1] flags "from south","from north"; [2],[3] block-done counters of the pushes
-__host__ __device__ inline unsigned long long* p2p_word(char* block, int w) {
-  return reinterpret_cast<unsigned long long*>(block) + w;
-}
 
 void p2p_close() {
   P2P& q = g_p2p;
@@ -202,20 +194,35 @@ __global__ void p2p_unpack(Geom g, XBatch b, int nhl, int dir, char* my_block, s
   }
 }
 
+bool p2p_view(P2PView* v, size_t need_cap) {
+  Ctx& c = C(); const Geom& g = c.g;
+  P2P& q = g_p2p;
+  if (g.nranks < 2 || c.option("comm", "p2p") != "p2p") return false;
+  if (q.tried && !q.on) return false;
+  if (!q.on || need_cap > q.cap) {
+    q.tried = true;
+    // room for the largest exchange of the step: 12 fields x kdm levels x nbdy rows
+    const size_t want = std::max<size_t>(need_cap, (size_t)12 * g.kdm * g.nb * g.ii);
+    if (!p2p_setup(want)) return false;
+  }
+  v->my_block = q.block; v->peer[0] = q.peer[0]; v->peer[1] = q.peer[1]; v->cap = q.cap;
+  v->has_s = g.rank > 0; v->has_n = g.rank + 1 < g.nranks;
+  return true;
+}
+unsigned long long p2p_reserve_seq(int n) {
+  const unsigned long long first = g_p2p.seq + 1;
+  g_p2p.seq += n;
+  return first;
+}
+
 // returns false if the P2P path is not available (caller uses NCCL)
 bool exchange_ns_p2p(const XBatch& b, long tot, int maxlev, int nhl) {
   Ctx& c = C(); const Geom& g = c.g;
   P2P& q = g_p2p;
-  if (c.option("comm", "p2p") != "p2p") return false;
-  if (q.tried && !q.on) return false;
-  if (!q.on || (size_t)tot > q.cap) {
-    q.tried = true;
-    // room for the largest exchange of the step: 12 fields x kdm levels x nbdy rows
-    const size_t want = std::max<size_t>((size_t)tot, (size_t)12 * g.kdm * g.nb * g.ii);
-    if (!p2p_setup(want)) return false;
-  }
+  P2PView view;
+  if (!p2p_view(&view, (size_t)tot)) return false;
   const bool has_s = g.rank > 0, has_n = g.rank + 1 < g.nranks;
-  const unsigned long long seq = ++q.seq;
+  const unsigned long long seq = p2p_reserve_seq(1);
   const int parity = (int)(seq & 1ull);
   dim3 grid(std::max(1, std::min(cdiv((long)nhl * g.ii, 256), 32)), maxlev, b.n);
   const unsigned nblk = grid.x * grid.y * grid.z;
