@@ -41,6 +41,9 @@ struct MtP {
   // level-independent barotropic part of the total velocities, ubflxs_p*tsfac/(pbu*scuy) at time
   // levels n and m, evaluated once per call (mt_pressures) instead of once per use and level
   double *ubn, *ubm, *vbn, *vbm;
+  // kinetic energy and longitudinal stress fluxes at mass points, staged once per level because each
+  // is needed by two update threads (and costs ~20 loads to rebuild)
+  double *ke, *uflux1, *vflux1;
   double delt1, tsfac, mdv2hi, mdv2lo, mdv4hi, mdv4lo, vsc2hi, vsc2lo, vsc4hi, vsc4lo, cbar, cb;
   int m, n, mm, nn, mommth /*0 enscon 1 enecon 2 enedis*/, isopyc;
 };
@@ -169,6 +172,8 @@ __global__ void mt_drag(Geom g, MtP P) {
   P.ustarb[x] = sqrt(q * ubbl);
 }
 
+__device__ __forceinline__ double ke_at(const Geom& g, const MtP& P, int i, int j, int k);
+
 // ---- stage 1: auxiliary velocities, del2, tension --------------------------------------------
 __global__ void mt_aux(Geom g, MtP P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x - 1;  // -1..ii+2
@@ -193,6 +198,7 @@ __global__ void mt_aux(Geom g, MtP P) {
     P.via[xk] = a; P.vib[xk] = b;
     P.dl2v[xk] = vn - .25 * (vtotn_at(g, P, i, j + 1, k) + vtotn_at(g, P, i, j - 1, k) + a + b);
   }
+  if (i >= 0 && i <= g.ii && j >= 0 && j <= g.jj) P.ke[xk] = ke_at(g, P, i, j, k);
   if (i <= g.ii + 1 && j <= g.jj + 1 && P.ip[x] == 1)
     P.defor1[xk] = sq((utotn_at(g, P, i + 1, j, k) * P.scuy[x + 1] - utotn_at(g, P, i, j, k) * P.scuy[x]) -
                       (vtotn_at(g, P, i, j + 1, k) * P.scvx[x + g.ldi] - vtotn_at(g, P, i, j, k) * P.scvx[x])) *
@@ -359,6 +365,16 @@ __device__ __forceinline__ void vh_minmax(const Geom& g, const MtP& P, int i, in
   if (vhc > vhm) { mn = vhm; mx = vhc; } else { mx = vhm; mn = vhc; }
 }
 
+// ---- stage 3b: longitudinal stress fluxes at mass points (:858-873, :1017-1032) ------------------------
+__global__ void mt_flux1(Geom g, MtP P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..ii
+  const int j = blockIdx.y, k = blockIdx.z + 1;         // 0..jj
+  if (i > g.ii) return;
+  const long xk = ix2(g, i, j) + (long)(k - 1) * g.lev;
+  if (j >= 1) P.uflux1[xk] = uflux1_at(g, P, i, j, k);
+  if (i >= 1) P.vflux1[xk] = vflux1_at(g, P, i, j, k);
+}
+
 // ---- stage 4: tendencies and leap-frog update ------------------------------------------------------
 __global__ void __launch_bounds__(128)
 mt_update(Geom g, MtP P) {
@@ -408,7 +424,7 @@ mt_update(Geom g, MtP P) {
                           fmin(.125 * P.difmxq[x], (v4 + v4a) * P.scqx[x]) * hfharm(dpja, dpxy) * (dl2uja - d2);
     const double uflux3 = fmin(P.difmxq[x + s], (v2 + v2b) * P.scqx[x + s]) * hfharm(dpjb, dpxy) * (un - P.ujb[xk]) +
                           fmin(.125 * P.difmxq[x + s], (v4 + v4b) * P.scqx[x + s]) * hfharm(dpjb, dpxy) * (d2 - dl2ujb);
-    const double uflux1c = uflux1_at(g, P, i, j, k), uflux1w = uflux1_at(g, P, i - 1, j, k);
+    const double uflux1c = P.uflux1[xk], uflux1w = P.uflux1[xk - 1];
     // wind stress (:919-946)
     double stress;
     if (P.isopyc) stress = k == 1 ? -2. * P.taux[x] * grav * P.scux[x] / (P.p[x + L] + P.p[x - 1 + L]) : 0.;
@@ -423,7 +439,7 @@ mt_update(Geom g, MtP P) {
     const double pgf = (1. - 2. * WPGF) * P.pgfx[xm] + WPGF * (P.pgfx_o[xk] + P.pgfx[xn]);
     const double ukm = P.u[xm], ukn = P.u[xn];
     P.su_m[xk] = ukm * (WUV1 * P.dpu[xm] + onemm) + ukn * WUV2 * P.dpuold[xk];
-    P.su_n[xk] = ukn + P.delt1 * (-P.scuxi[x] * (-pgf + stress + (ke_at(g, P, i, j, k) - ke_at(g, P, i - 1, j, k))) + cau -
+    P.su_n[xk] = ukn + P.delt1 * (-P.scuxi[x] * (-pgf + stress + (P.ke[xk] - P.ke[xk - 1])) + cau -
                                P.ubcors_p[x] * P.tsfac + botstr -
                                (uflux1c - uflux1w + uflux3 - uflux2) / (P.scu2[x] * fmax(P.dpu[xm], onemm)));
   }
@@ -474,7 +490,7 @@ mt_update_v(Geom g, MtP P) {
                           fmin(.125 * P.difmxq[x], (v4 + v4a) * P.scqy[x]) * hfharm(dpia, dpxy) * (dl2via - d2);
     const double vflux3 = fmin(P.difmxq[x + 1], (v2 + v2b) * P.scqy[x + 1]) * hfharm(dpib, dpxy) * (vn - P.vib[xk]) +
                           fmin(.125 * P.difmxq[x + 1], (v4 + v4b) * P.scqy[x + 1]) * hfharm(dpib, dpxy) * (d2 - dl2vib);
-    const double vflux1c = vflux1_at(g, P, i, j, k), vflux1s = vflux1_at(g, P, i, j - 1, k);
+    const double vflux1c = P.vflux1[xk], vflux1s = P.vflux1[xk - s];
     double stress;
     if (P.isopyc) stress = k == 1 ? -2. * P.tauy[x] * grav * P.scvy[x] / (P.p[x + L] + P.p[x - s + L]) : 0.;
     else stress = -(P.mv_nonloc[xk] - P.mv_nonloc[xk + L]) * P.tauy[x] * grav * P.scvy[x] / fmax(onemm, P.dpv[xm]);
@@ -487,7 +503,7 @@ mt_update_v(Geom g, MtP P) {
     const double pgf = (1. - 2. * WPGF) * P.pgfy[xm] + WPGF * (P.pgfy_o[xk] + P.pgfy[xn]);
     const double vkm = P.v[xm], vkn = P.v[xn];
     P.sv_m[xk] = vkm * (WUV1 * P.dpv[xm] + onemm) + vkn * WUV2 * P.dpvold[xk];
-    P.sv_n[xk] = vkn + P.delt1 * (-P.scvyi[x] * (-pgf + stress + (ke_at(g, P, i, j, k) - ke_at(g, P, i, j - 1, k))) + cav -
+    P.sv_n[xk] = vkn + P.delt1 * (-P.scvyi[x] * (-pgf + stress + (P.ke[xk] - P.ke[xk - s])) + cav -
                                P.vbcors_p[x] * P.tsfac + botstr -
                                (vflux1c - vflux1s + vflux3 - vflux2) / (P.scv2[x] * fmax(P.dpv[xm], onemm)));
   }
@@ -582,7 +598,7 @@ void momtum_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   P.ip = c.idev("ip"); P.iu = c.idev("iu"); P.iv = c.idev("iv"); P.iq = c.idev("iq");
 #define S(f) P.f = c.owned("momtum_" #f, g.kdm)
   S(uja); S(ujb); S(via); S(vib); S(dl2u); S(dl2v); S(defor1); S(defor2); S(potvor); S(vsc2u); S(vsc4u); S(vsc2v);
-  S(vsc4v); S(su_m); S(su_n); S(sv_m); S(sv_n);
+  S(vsc4v); S(su_m); S(su_n); S(sv_m); S(sv_n); S(ke); S(uflux1); S(vflux1);
 #undef S
   P.drag = c.owned("momtum_drag", 1);
   P.ubn = c.owned("momtum_ubn", 1); P.ubm = c.owned("momtum_ubm", 1);
@@ -594,6 +610,7 @@ void momtum_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   { dim3 grid(cdiv(g.ii + 4, 128), g.jj + 4, g.kdm); LAUNCH(mt_aux, grid, 128, 0, g, P); }
   { dim3 grid(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm); LAUNCH(mt_vort, grid, 128, 0, g, P); }
   { dim3 grid(cdiv(g.ii + 2, 128), g.jj + 2, g.kdm); LAUNCH(mt_visc, grid, 128, 0, g, P); }
+  { dim3 grid(cdiv(g.ii + 1, 128), g.jj + 1, g.kdm); LAUNCH(mt_flux1, grid, 128, 0, g, P); }
   { dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
     LAUNCH(mt_update, grid, 128, 0, g, P);
     LAUNCH(mt_update_v, grid, 128, 0, g, P); }
