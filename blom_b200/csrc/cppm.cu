@@ -1,5 +1,5 @@
-// Layer-thickness and tracer transport: advect prelude + CPPM
-// (cppm_compatibility='full', cppm_limiting='non_oscillatory').
+// Layer-thickness and tracer transport: advect prelude + CPPM, all four variants
+// (cppm_compatibility='full'|'partial' x cppm_limiting='non_oscillatory'|'monotonic').
 //
 // Reference: phy/mod_advect.F90:59-189, phy/mod_cppm.F90:101-359 (static
 // tables), :361-434 (thickness edges), :490-818 (compatible tracer parabolas),
@@ -305,7 +305,8 @@ __global__ void advect_flux_area(Geom g, int m, int mm, int nn, double delt1, do
 // ---- thickness edges (h_edges_nosc, mod_cppm.F90:361-434) --------------------
 // DIR 0: i-pass, DIR 1: j-pass.  One thread per interior cell and level.
 // sp = element stride along the pass direction, sc = along the cross direction.
-template <int DIR>
+// MONO: h_edges_mono (:436-488) — same edges, limiter applied unconditionally, no positivity fix.
+template <int DIR, bool MONO>
 __global__ void __launch_bounds__(256)
 cppm_hedges(Geom g, bool second_pass, const double* __restrict__ dp /* level 1 of source set */,
             const double* __restrict__ cac /* cross-direction flux area, level 1 */,
@@ -341,7 +342,7 @@ cppm_hedges(Geom g, bool second_pass, const double* __restrict__ dp /* level 1 o
   const double hmm = hm[2], hm0 = hm[3], hmp = hm[4];
   const double ssc = tab[T_SSC * g.lev + x], scc = tab[T_SCC * g.lev + x];
   double sl, sr, sc_, d, q_, r, a2;
-  if (d2h[0] * d2h[1] <= K0 || d2h[1] * d2h[2] <= K0) {
+  if (MONO || d2h[0] * d2h[1] <= K0 || d2h[1] * d2h[2] <= K0) {
     sl = ssc * (hm0 - hmm);
     sr = ssc * (hmp - hm0);
     if (sl * sr > K0) {
@@ -359,16 +360,18 @@ cppm_hedges(Geom g, bool second_pass, const double* __restrict__ dp /* level 1 o
       her = hm0;
     }
   }
-  hel = fmax(hel, DPEPS);
-  her = fmax(her, DPEPS);
-  sl = K2 * (K3 * hm0 - K2 * hel - her);
-  a2 = K3 * (hel - K2 * hm0 + her);
-  sr = sl + K2 * a2;
-  if (sl < K0 && sr > K0) {
-    if (a2 * hel - K1_4 * sl * sl < a2 * DPEPS) {
-      q_ = K3 * hm0 / (K3 * sl * sr + K4 * a2 * a2);
-      hel = sl * sl * q_;
-      her = sr * sr * q_;
+  if (!MONO) {
+    hel = fmax(hel, DPEPS);
+    her = fmax(her, DPEPS);
+    sl = K2 * (K3 * hm0 - K2 * hel - her);
+    a2 = K3 * (hel - K2 * hm0 + her);
+    sr = sl + K2 * a2;
+    if (sl < K0 && sr > K0) {
+      if (a2 * hel - K1_4 * sl * sl < a2 * DPEPS) {
+        q_ = K3 * hm0 / (K3 * sl * sr + K4 * a2 * a2);
+        hel = sl * sl * q_;
+        her = sr * sr * q_;
+      }
     }
   }
   hel3[xk] = hel;
@@ -377,14 +380,15 @@ cppm_hedges(Geom g, bool second_pass, const double* __restrict__ dp /* level 1 o
 
 // arctic swap of hel/her after their halo update (mod_cppm.F90:1531-1541, :1686-1703)
 template <int DIR>
-__global__ void cppm_swap_edges(Geom g, bool fold_fix, double* hel3, double* her3) {
+__global__ void cppm_swap_edges(Geom g, bool fold_fix, int hw /* 4 nosc, 3 mono (:1848, :2015) */, double* hel3,
+                                double* her3) {
   const int k = blockIdx.y;
-  const int nrow = DIR == 0 ? 1 : 1 + 4;
+  const int nrow = DIR == 0 ? 1 : 1 + hw;
   long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long)g.ldi * nrow) return;
   const int i = (int)(t % g.ldi) + 1 - g.nb, r = (int)(t / g.ldi);
   bool doit;
-  if (DIR == 0) doit = (i >= -3 && i <= g.ii + 4);
+  if (DIR == 0) doit = (i >= 1 - hw && i <= g.ii + hw);
   // reference quirk (mod_cppm.F90:1690): only the right half of row jj is swapped unless
   // option cppm_fold_fix=1 asks for the whole (mirrored) row
   else doit = r == 0 ? (i >= (fold_fix ? 1 : max(1, g.itdm / 2 - g.i0 + 1)) && i <= g.ii)
@@ -520,18 +524,44 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // cell widths (tm_coeffs) instead of being re-read per level; only interfaces
 // on the tripolar fold rows, whose table entries are mirrored images
 // (mod_cppm.F90:2605-2646), read the tables.
-template <int NT, int TP>
+// Scheme variants (mod_cppm.F90:2748-2834): bit 0 = monotonic limiting, bit 1 = partial compatibility.
+enum { VAR_FC_NOSC = 0, VAR_FC_MONO = 1, VAR_PC_NOSC = 2, VAR_PC_MONO = 3 };
+
+template <int NT, int TP, int VAR>
 struct FluxSmem {
   static constexpr int NCELL = TP + 3;
   static constexpr int NRAW = 5 + NT;   // dp, hel, her, cross flux area (+,-), tm[NT]
   static constexpr int NOPS = 5;        // pass flux area, p(k+1), flx, tflx, sflx
   static constexpr int BUF = NRAW * NCELL + NOPS * TP;
-  // hm, 1/area, width, E|F (1+NT rows), D (NT), P (3+3NT)
-  static constexpr int WORK = 3 * NCELL + (1 + NT + NT + 3 + 3 * NT) * TP;
+  // hm, 1/area, width, E|F (1+NT rows), D (NT, +1 for the thickness curvature of the partial
+  // compatibility variants), P (3+3NT)
+  static constexpr int ND = NT + ((VAR & 2) ? 1 : 0);
+  static constexpr int WORK = 3 * NCELL + (1 + NT + ND + 3 + 3 * NT) * TP;
   static constexpr int PER_TC = 2 * BUF + WORK;
 };
 
-template <int DIR, int NT, int TP, int TC>
+// slope limiter + parabola monotonicity fix of the partial-compatibility routines (thickness and
+// tracers alike, mod_cppm.F90:1168-1190, :1209-1232, :1309-1358)
+__device__ __forceinline__ void pc_limit(double ssc, double scc, double xm, double x0, double xp, double& el,
+                                         double& er) {
+  const double sl = ssc * (x0 - xm), sr = ssc * (xp - x0);
+  if (sl * sr > K0) {
+    double scv = scc * (xp - xm);
+    scv = fsign(fmin(fmin(fabs(sl), fabs(sr)), fabs(scv)), scv);
+    if ((xm - el) * (x0 - el) > K0) el = x0 - fsign(fmin(K1_2 * fabs(scv), fabs(el - x0)), scv);
+    if ((xp - er) * (x0 - er) > K0) er = x0 + fsign(fmin(K1_2 * fabs(scv), fabs(er - x0)), scv);
+    const double d = er - el;
+    const double q = d * (K2 * x0 - el - er);
+    const double r = K1_3 * d * d;
+    if (q > r) el = K3 * x0 - K2 * er;
+    else if (-r > q) er = K3 * x0 - K2 * el;
+  } else {
+    el = x0;
+    er = x0;
+  }
+}
+
+template <int DIR, int NT, int TP, int TC, int VAR>
 __global__ void __launch_bounds__(TP* TC, DIR == 0 ? 2 : 1)
 cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */, int kchunk,
           const double* __restrict__ dp_src, double* __restrict__ dp_dst, ScalarPtrs<NT> S,
@@ -542,8 +572,9 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
           const double* __restrict__ scp2i, const double* __restrict__ scpd /* scpx or scpy */,
           const double* __restrict__ tab, const int* __restrict__ sten, double* __restrict__ flx,
           double* __restrict__ tflx, double* __restrict__ sflx /* pointers at level 1+mm */) {
-  using L = FluxSmem<NT, TP>;
+  using L = FluxSmem<NT, TP, VAR>;
   constexpr int NCELL = L::NCELL;
+  constexpr bool MONO = (VAR & 1) != 0, PC = (VAR & 2) != 0;
   extern __shared__ double smem[];
   const int tp = DIR == 0 ? threadIdx.x : threadIdx.y;
   const int tc = DIR == 0 ? threadIdx.y : threadIdx.x;
@@ -554,8 +585,8 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
   double* s_dx = s_ai + NCELL;               // [NCELL] width of the staged cells along the pass
   double* s_F = s_dx + NCELL;                // [1+NT][TP]; rows 1.. double as the edge values E
   double* s_E = s_F + TP;
-  double* s_D = s_F + (1 + NT) * TP;         // [NT][TP]
-  double* s_P = s_D + NT * TP;               // [3+3NT][TP]
+  double* s_D = s_F + (1 + NT) * TP;         // [ND][TP]; row NT = thickness curvature (PC)
+  double* s_P = s_D + L::ND * TP;            // [3+3NT][TP]
 
   constexpr int NOUT = TP - 5;
   const int npass = DIR == 0 ? g.idm : g.jdm;
@@ -588,8 +619,10 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
     for (int q = tp; q < NCELL; q += TP) {
       const long yk = addr(min(p0 - 2 + q, pmax)) + koff;
       cp_async8(B + 0 * NCELL + q, dp_src + yk);
-      cp_async8(B + 1 * NCELL + q, hel3 + yk);
-      cp_async8(B + 2 * NCELL + q, her3 + yk);
+      if (!PC) {
+        cp_async8(B + 1 * NCELL + q, hel3 + yk);
+        cp_async8(B + 2 * NCELL + q, her3 + yk);
+      }
       if (second_pass) {
         cp_async8(B + 3 * NCELL + q, cac + yk + sc);
         cp_async8(B + 4 * NCELL + q, cac + yk);
@@ -616,10 +649,15 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
   const int stencil = sten[xe];
   const double d2m = tab[T_D2M * lev + xe], ssc = tab[T_SSC * lev + xe], scc = tab[T_SCC * lev + xe];
   const double db = pbd[xe + (long)(n_lev2d - 1) * lev];
+  double hv1 = K0, hv2 = K0, hv3 = K0, hv4 = K0;   // thickness edge weights double as tracer weights (PC)
+  if (PC) {
+    hv1 = tab[T_HEVC1 * lev + xe]; hv2 = tab[T_HEVC2 * lev + xe];
+    hv3 = tab[T_HEVC3 * lev + xe]; hv4 = tab[T_HEVC4 * lev + xe];
+  }
   // interfaces on the fold rows carry mirrored table entries: read them instead of recomputing
   // (xctilr rewrites row jj of u-type tables with the mirror of row jj-1 even for nh=0, so the
   //  i-pass needs them on row jj; the j-pass on rows >= jj)
-  const bool use_tab = g.nreg == 2 && g.north && (DIR == 1 ? e >= g.jj : cc == g.jj);
+  const bool use_tab = !PC && g.nreg == 2 && g.north && (DIR == 1 ? e >= g.jj : cc == g.jj);
   double p_own = p[xe + (long)(k_first - 1) * lev];
   double p_up = p[addr(min(max(e - 1, 1 - g.nb), pmax)) + (long)(k_first - 1) * lev];
   const bool face_ok = cvalid && tp >= 2 && tp <= TP - 3 && e >= 1 && e <= npass + 1 &&
@@ -646,13 +684,22 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
     }
     __syncthreads();
 
-    const double hm_c = s_hm[qc], hel_c = s_hel[qc], her_c = s_her[qc];
+    const double hm_c = s_hm[qc];
+    double hel_c, her_c;
+    if (!PC) { hel_c = s_hel[qc]; her_c = s_her[qc]; }
     double tm_c[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) tm_c[nt] = s_tm[nt * NCELL + qc];
 
     // ---- A: tracer edge values at edge e from cells e-2..e+1 (smem tp..tp+3) ----
-    {
+    if (PC) {
+      // partial compatibility (:1143-1153): thickness and tracer edges share the static weights
+      s_F[tp] = hv1 * s_hm[tp] + hv2 * s_hm[tp + 1] + hv3 * s_hm[tp + 2] + hv4 * s_hm[tp + 3];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        s_E[nt * TP + tp] = hv1 * s_tm[nt * NCELL + tp] + hv2 * s_tm[nt * NCELL + tp + 1] +
+                            hv3 * s_tm[nt * NCELL + tp + 2] + hv4 * s_tm[nt * NCELL + tp + 3];
+    } else {
       double hm4[4], hel4[4], her4[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) { hm4[q] = s_hm[tp + q]; hel4[q] = s_hel[tp + q]; her4[q] = s_her[tp + q]; }
@@ -680,7 +727,16 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
     // ---- B: thickness factors and curvature proxy of own cell ----
     double tel[NT], ter[NT];
     double hf1m, hf1l, hf1r, hf2m, hf2l, hf2r;
-    {
+    if (PC) {
+      hel_c = s_F[tp]; her_c = s_F[tp1];
+      if (!MONO) s_D[NT * TP + tp] = d2m * (hel_c - K2 * hm_c + her_c);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        tel[nt] = s_E[nt * TP + tp];
+        ter[nt] = s_E[nt * TP + tp1];
+        if (!MONO) s_D[nt * TP + tp] = d2m * (tel[nt] - K2 * tm_c[nt] + ter[nt]);
+      }
+    } else {
       const double q = K1 / (K12 * hm_c - hel_c - her_c);
       hf1m = K60 * hm_c * q;
       hf1l = -(K42 * hm_c + K4 * hel_c - K6 * her_c) * q;
@@ -692,20 +748,81 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
       for (int nt = 0; nt < NT; ++nt) {
         tel[nt] = s_E[nt * TP + tp];
         ter[nt] = s_E[nt * TP + tp1];
-        s_D[nt * TP + tp] = d2m * (hf2m * tm_c[nt] + hf2l * tel[nt] + hf2r * ter[nt]);
+        if (!MONO) s_D[nt * TP + tp] = d2m * (hf2m * tm_c[nt] + hf2l * tel[nt] + hf2r * ter[nt]);
       }
     }
-    __syncthreads();
+    if (!MONO) __syncthreads();   // (uniform: MONO is a template constant)
 
     // ---- C: limiters and parabola coefficients of own cell ----
     double hpc0, hpc1, hpc2, tpc0[NT], tpc1[NT], tpc2[NT];
-    {
+    if (PC) {
+      // :1166-1263 (pc_nosc) / :1307-1369 (pc_mono)
+      const double hmm = s_hm[qc - 1], hmp = s_hm[qc + 1];
+      bool lim = MONO;
+      if (!MONO) {
+        const double d2c = s_D[NT * TP + tp], d2l = s_D[NT * TP + tm1], d2r = s_D[NT * TP + tp1];
+        lim = d2l * d2c <= K0 || d2c * d2r <= K0;
+      }
+      if (lim) pc_limit(ssc, scc, hmm, hm_c, hmp, hel_c, her_c);
+      if (!MONO) {
+        hel_c = fmax(hel_c, DPEPS);
+        her_c = fmax(her_c, DPEPS);
+        const double sl = K2 * (K3 * hm_c - K2 * hel_c - her_c);
+        const double a2 = K3 * (hel_c - K2 * hm_c + her_c);
+        const double sr = sl + K2 * a2;
+        if (sl < K0 && sr > K0) {
+          if (a2 * hel_c - K1_4 * sl * sl < a2 * DPEPS) {
+            const double q = K3 * hm_c / (K3 * sl * sr + K4 * a2 * a2);
+            hel_c = sl * sl * q;
+            her_c = sr * sr * q;
+          }
+        }
+      }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        const double d2c = s_D[nt * TP + tp], d2l = s_D[nt * TP + tm1], d2r = s_D[nt * TP + tp1];
+        const double tmm = s_tm[nt * NCELL + qc - 1], tmp = s_tm[nt * NCELL + qc + 1], tmc = tm_c[nt];
+        bool tl_ = MONO;
+        if (!MONO) {
+          const double d2c = s_D[nt * TP + tp], d2l = s_D[nt * TP + tm1], d2r = s_D[nt * TP + tp1];
+          tl_ = d2l * d2c <= K0 || d2c * d2r <= K0;
+        }
+        if (tl_) pc_limit(ssc, scc, tmm, tmc, tmp, tel[nt], ter[nt]);
+        if (!MONO && nt >= 1) {  // positivity (:1234-1248)
+          tel[nt] = fmax(tel[nt], K0);
+          ter[nt] = fmax(ter[nt], K0);
+          const double sl = K2 * (K3 * tmc - K2 * tel[nt] - ter[nt]);
+          const double a2 = K3 * (tel[nt] - K2 * tmc + ter[nt]);
+          const double sr = sl + K2 * a2;
+          if (sl < K0 && sr > K0) {
+            if (a2 * tel[nt] - K1_4 * sl * sl < K0) {
+              const double q = K3 * tmc / (K3 * sl * sr + K4 * a2 * a2);
+              tel[nt] = sl * sl * q;
+              ter[nt] = sr * sr * q;
+            }
+          }
+        }
+        tpc0[nt] = tel[nt];
+        tpc1[nt] = K6 * tmc - K4 * tel[nt] - K2 * ter[nt];
+        tpc2[nt] = K3 * (tel[nt] - K2 * tmc + ter[nt]);
+        s_P[(3 + 3 * nt + 0) * TP + tp] = tpc0[nt];
+        s_P[(3 + 3 * nt + 1) * TP + tp] = tpc1[nt];
+        s_P[(3 + 3 * nt + 2) * TP + tp] = tpc2[nt];
+      }
+      hpc0 = hel_c;
+      hpc1 = K6 * hm_c - K4 * hel_c - K2 * her_c;
+      hpc2 = K3 * (hel_c - K2 * hm_c + her_c);
+      s_P[0 * TP + tp] = hpc0; s_P[1 * TP + tp] = hpc1; s_P[2 * TP + tp] = hpc2;
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
         const double tmm = s_tm[nt * NCELL + qc - 1], tmp = s_tm[nt * NCELL + qc + 1], tmc = tm_c[nt];
         double sl, sr, scv, a2;
-        if (d2l * d2c <= K0 || d2c * d2r <= K0) {
+        bool lim = MONO;   // fc_mono limits every cell (:1073-1099)
+        if (!MONO) {
+          const double d2c = s_D[nt * TP + tp], d2l = s_D[nt * TP + tm1], d2r = s_D[nt * TP + tp1];
+          lim = d2l * d2c <= K0 || d2c * d2r <= K0;
+        }
+        if (lim) {
           sl = ssc * (tmc - tmm);
           sr = ssc * (tmp - tmc);
           if (sl * sr > K0) {
@@ -729,7 +846,7 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
             ter[nt] = tmc;
           }
         }
-        if (nt >= 1) {  // positivity for everything but temperature (:788-801)
+        if (!MONO && nt >= 1) {  // positivity for everything but temperature (:788-801)
           tel[nt] = fmax(tel[nt], K0);
           ter[nt] = fmax(ter[nt], K0);
           sl = hf1m * tmc + hf1l * tel[nt] + hf1r * ter[nt];
@@ -834,7 +951,7 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
   }
 }
 
-template <int DIR, int NT>
+template <int DIR, int NT, int VAR>
 void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, const ScalarPtrs<NT>& S,
                  const double* hel3, const double* her3, const double* cad, const double* cac,
                  const double* p, const double* pbd, const double* scp2i, const double* scpd, const double* tab,
@@ -843,8 +960,8 @@ void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, 
   constexpr int TP = DIR == 0 ? 128 : 32;
   constexpr int TC = DIR == 0 ? 2 : 16;
   constexpr int NOUT = TP - 5;
-  const size_t smem = sizeof(double) * FluxSmem<NT, TP>::PER_TC * TC;
-  auto kern = cppm_flux<DIR, NT, TP, TC>;
+  const size_t smem = sizeof(double) * FluxSmem<NT, TP, VAR>::PER_TC * TC;
+  auto kern = cppm_flux<DIR, NT, TP, TC, VAR>;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -870,10 +987,12 @@ void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, 
                dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i, scpd, tab, sten, flx, tflx, sflx);
 }
 
-template <int DIR, int NT>
+template <int DIR, int NT, int VAR>
 void cppm_pass(bool second_pass, int n, int mm, double* dp_src, double* dp_dst, ScalarPtrs<NT> S) {
   Ctx& c = C(); const Geom& g = c.g;
-  const int mh = DIR == 0 ? 4 : 0, nh = DIR == 0 ? 0 : 4;
+  constexpr bool MONO = (VAR & 1) != 0, PC = (VAR & 2) != 0;
+  constexpr int hw = MONO ? 3 : 4;   // halo width of the variant (:1485 vs :1802)
+  const int mh = DIR == 0 ? hw : 0, nh = DIR == 0 ? 0 : hw;
   // halo of the transported fields in the pass direction (:1485-1490 / :1640-1645)
   std::vector<HaloReq> reqs{{dp_src, g.kdm, halo_ps}};
   for (int nt = 0; nt < NT; ++nt) reqs.push_back({const_cast<double*>(S.src[nt]), g.kdm, halo_ps});
@@ -885,28 +1004,31 @@ void cppm_pass(bool second_pass, int n, int mm, double* dp_src, double* dp_dst, 
   const double* cad = c.dev(DIR == 0 ? "cau" : "cav");
   const double* cac = c.dev(DIR == 0 ? "cav" : "cau");
   const double* scp2i = c.dev("scp2i");
-  {
+  if (!PC) {   // full compatibility stages the limited thickness edges (:1493-1541)
     dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
-    LAUNCH_NAMED(DIR == 0 ? "cppm_hedges<i>" : "cppm_hedges<j>", cppm_hedges<DIR>, grid, 128, 0, g, second_pass, dp_src, cac, scp2i, tab, hel3, her3);
-  }
-  halo_update(std::vector<HaloReq>{{hel3, g.kdm, halo_ps}, {her3, g.kdm, halo_ps}}, mh, nh);
-  if (g.nreg == 2 && g.north) {
-    const int nrow = DIR == 0 ? 1 : 5;
-    dim3 grid(cdiv((long)g.ldi * nrow, 256), g.kdm);
-    LAUNCH(cppm_swap_edges<DIR>, grid, 256, 0, g, c.option("cppm_fold_fix", "0") == "1", hel3, her3);
+    auto hk = cppm_hedges<DIR, MONO>;
+    LAUNCH_NAMED(DIR == 0 ? "cppm_hedges<i>" : "cppm_hedges<j>", hk, grid, 128, 0, g,
+                 second_pass, dp_src, cac, scp2i, tab, hel3, her3);
+    halo_update(std::vector<HaloReq>{{hel3, g.kdm, halo_ps}, {her3, g.kdm, halo_ps}}, mh, nh);
+    if (g.nreg == 2 && g.north) {
+      const int nrow = DIR == 0 ? 1 : 1 + hw;
+      dim3 grid2(cdiv((long)g.ldi * nrow, 256), g.kdm);
+      LAUNCH(cppm_swap_edges<DIR>, grid2, 256, 0, g, c.option("cppm_fold_fix", "0") == "1", hw, hel3, her3);
+    }
   }
   const long om = (long)mm * g.lev;
-  launch_flux<DIR, NT>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, c.dev("p"),
-                       c.dev(DIR == 0 ? "pbu" : "pbv"), scp2i, c.dev(DIR == 0 ? "scpx" : "scpy"), tab, sten,
-                       c.dev(DIR == 0 ? "uflx" : "vflx") + om, c.dev(DIR == 0 ? "utflx" : "vtflx") + om,
-                       c.dev(DIR == 0 ? "usflx" : "vsflx") + om);
+  launch_flux<DIR, NT, VAR>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, c.dev("p"),
+                            c.dev(DIR == 0 ? "pbu" : "pbv"), scp2i, c.dev(DIR == 0 ? "scpx" : "scpy"), tab, sten,
+                            c.dev(DIR == 0 ? "uflx" : "vflx") + om, c.dev(DIR == 0 ? "utflx" : "vtflx") + om,
+                            c.dev(DIR == 0 ? "usflx" : "vsflx") + om);
 }
 
-template <int NT>
-void cppm_run(int n, int mm, int nn) {
+template <int NT, int VAR>
+void cppm_run_var(int n, int mm, int nn) {
   Ctx& c = C(); const Geom& g = c.g;
   const int nstep = (int)c.scalar("nstep");
-  halo_update(std::vector<HaloReq>{{c.dev("cau"), g.kdm, halo_uv}, {c.dev("cav"), g.kdm, halo_vv}}, 4, 4);
+  constexpr int hw = (VAR & 1) ? 3 : 4;   // :2760-2761 / :2776-2777
+  halo_update(std::vector<HaloReq>{{c.dev("cau"), g.kdm, halo_uv}, {c.dev("cav"), g.kdm, halo_vv}}, hw, hw);
   const long on = (long)nn * g.lev;
   double* dpA = c.dev("dp") + on;
   double* dpB = c.owned("cppm_tmp_dp", g.kdm);
@@ -920,11 +1042,32 @@ void cppm_run(int n, int mm, int nn) {
   }
   for (int nt = 0; nt < NT; ++nt) { AB.src[nt] = a[nt]; AB.dst[nt] = b[nt]; BA.src[nt] = b[nt]; BA.dst[nt] = a[nt]; }
   if (nstep % 2 == 1) {
-    cppm_pass<0, NT>(false, n, mm, dpA, dpB, AB);
-    cppm_pass<1, NT>(true, n, mm, dpB, dpA, BA);
+    cppm_pass<0, NT, VAR>(false, n, mm, dpA, dpB, AB);
+    cppm_pass<1, NT, VAR>(true, n, mm, dpB, dpA, BA);
   } else {
-    cppm_pass<1, NT>(false, n, mm, dpA, dpB, AB);
-    cppm_pass<0, NT>(true, n, mm, dpB, dpA, BA);
+    cppm_pass<1, NT, VAR>(false, n, mm, dpA, dpB, AB);
+    cppm_pass<0, NT, VAR>(true, n, mm, dpB, dpA, BA);
+  }
+}
+
+// resolves the namelist options exactly like init_cppm (:2524-2549), same messages
+int cppm_variant() {
+  Ctx& c = C();
+  const std::string comp = c.option("cppm_compatibility", "full"), lim = c.option("cppm_limiting", "non_oscillatory");
+  if (comp != "full" && comp != "partial")
+    throw std::runtime_error(" init_cppm: cppm_compatibility = " + comp + " is unsupported!");
+  if (lim != "monotonic" && lim != "non_oscillatory")
+    throw std::runtime_error(" init_cppm: cppm_limiting = " + lim + " is unsupported!");
+  return (comp == "partial" ? 2 : 0) | (lim == "monotonic" ? 1 : 0);
+}
+
+template <int NT>
+void cppm_run(int n, int mm, int nn) {
+  switch (cppm_variant()) {
+    case VAR_FC_NOSC: cppm_run_var<NT, VAR_FC_NOSC>(n, mm, nn); break;
+    case VAR_FC_MONO: cppm_run_var<NT, VAR_FC_MONO>(n, mm, nn); break;
+    case VAR_PC_NOSC: cppm_run_var<NT, VAR_PC_NOSC>(n, mm, nn); break;
+    default: cppm_run_var<NT, VAR_PC_MONO>(n, mm, nn); break;
   }
 }
 
@@ -933,11 +1076,7 @@ void cppm_run(int n, int mm, int nn) {
 // init_cppm (mod_cppm.F90:2504-2746)
 void init_cppm_dev() {
   Ctx& c = C(); const Geom& g = c.g;
-  const std::string comp = c.option("cppm_compatibility", "full"), lim = c.option("cppm_limiting", "non_oscillatory");
-  if (comp != "full")
-    throw std::runtime_error(" init_cppm: cppm_compatibility = " + comp + " is unsupported!");
-  if (lim != "non_oscillatory")
-    throw std::runtime_error(" init_cppm: cppm_limiting = " + lim + " is unsupported!");
+  (void)cppm_variant();   // option check with the reference's messages (:2524-2549)
   double* ti = c.owned("cppm_tab_i", T_NLEV);
   double* tj = c.owned("cppm_tab_j", T_NLEV);
   CUDA_CHECK(cudaMemsetAsync(ti, 0, sizeof(double) * g.lev * T_NLEV, c.stream));

@@ -1,6 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see core.hpp header).
-// Restatement of phy/mod_cppm.F90 (variant: cppm_compatibility='full',
-// cppm_limiting='non_oscillatory', the defaults :44-48) and of
+// Restatement of phy/mod_cppm.F90 (all four variants: cppm_compatibility =
+// 'full'|'partial' x cppm_limiting = 'non_oscillatory'|'monotonic', :44-48) and of
 // phy/mod_advect.F90:59-189 (advmth='cppm').
 #include "core.hpp"
 
@@ -241,21 +241,12 @@ void h_edges_nosc(int ijdm, int ijs, int ije, P1 hevc1, P1 hevc2, P1 hevc3, P1 h
   }
 }
 
-// :490-818
-void parabola_coeffs_fc_nosc(int ijdm, int ijs, int ije, PI1 stencil, PC tmc0, PC tmcl, PC tmcr,
-                             P1 ssc, P1 scc, P1 d2m, P1 hm, P2 tm, P1 hel, P1 her,
-                             P1 hpc0, P1 hpc1, P1 hpc2, P2 tpc0, P2 tpc1, P2 tpc2) {
-  const int nb = hm.nb, ntl = tm.nt, n1 = ijdm + 2 * nb;
-  std::vector<double> w((size_t)n1 * (3 * ntl + 6), 0.0);
-  P2 d2t{w.data(), nb, ntl}, tel{w.data() + (size_t)n1 * ntl, nb, ntl},
-     ter{w.data() + (size_t)2 * n1 * ntl, nb, ntl};
-  double* b = w.data() + (size_t)3 * n1 * ntl;
-  P1 hf1m{b, nb}, hf1l{b + n1, nb}, hf1r{b + 2 * n1, nb}, hf2m{b + 3 * n1, nb},
-     hf2l{b + 4 * n1, nb}, hf2r{b + 5 * n1, nb};
-  double h1i, h2i, h3i, h4i, a12, a22, a32, a42, a13, a23, a33, a43, a14, a24, a34, a44, q,
-         tevc1 = 0, tevc2 = 0, tevc3 = 0, tevc4 = 0, te, sl, sr, sc, a2;
-
-  for (int i = ijs - 1; i <= ije + 2; ++i) {
+// compatible tracer edge-value weights of interface i: the per-interface LU solve that
+// parabola_coeffs_fc_nosc (:519-722) and parabola_coeffs_fc_mono (:849-1052) both spell out.
+// tevc1..4 are in/out: a Fortran select without a matching case keeps the previous values.
+inline void compat_edge_weights(int i, PI1 stencil, PC tmc0, PC tmcl, PC tmcr, P1 hm, P1 hel, P1 her,
+                                double& tevc1, double& tevc2, double& tevc3, double& tevc4) {
+  double h1i, h2i, h3i, h4i, a12, a22, a32, a42, a13, a23, a33, a43, a14, a24, a34, a44, q;
     switch (stencil(i)) {
       case stencil_1111:
         h1i = c1 / hm(i - 2); h2i = c1 / hm(i - 1); h3i = c1 / hm(i); h4i = c1 / hm(i + 1);
@@ -358,6 +349,23 @@ void parabola_coeffs_fc_nosc(int ijdm, int ijs, int ije, PI1 stencil, PC tmc0, P
       default:
         break;  // Fortran select with no matching case: coefficients keep previous values
     }
+}
+
+// :490-818
+void parabola_coeffs_fc_nosc(int ijdm, int ijs, int ije, PI1 stencil, PC tmc0, PC tmcl, PC tmcr,
+                             P1 ssc, P1 scc, P1 d2m, P1 hm, P2 tm, P1 hel, P1 her,
+                             P1 hpc0, P1 hpc1, P1 hpc2, P2 tpc0, P2 tpc1, P2 tpc2) {
+  const int nb = hm.nb, ntl = tm.nt, n1 = ijdm + 2 * nb;
+  std::vector<double> w((size_t)n1 * (3 * ntl + 6), 0.0);
+  P2 d2t{w.data(), nb, ntl}, tel{w.data() + (size_t)n1 * ntl, nb, ntl},
+     ter{w.data() + (size_t)2 * n1 * ntl, nb, ntl};
+  double* b = w.data() + (size_t)3 * n1 * ntl;
+  P1 hf1m{b, nb}, hf1l{b + n1, nb}, hf1r{b + 2 * n1, nb}, hf2m{b + 3 * n1, nb},
+     hf2l{b + 4 * n1, nb}, hf2r{b + 5 * n1, nb};
+  double q, tevc1 = 0, tevc2 = 0, tevc3 = 0, tevc4 = 0, te, sl, sr, sc, a2;
+
+  for (int i = ijs - 1; i <= ije + 2; ++i) {
+    compat_edge_weights(i, stencil, tmc0, tmcl, tmcr, hm, hel, her, tevc1, tevc2, tevc3, tevc4);
     for (int nt = 1; nt <= ntl; ++nt) {
       te = tevc1 * tm(nt, i - 2) + tevc2 * tm(nt, i - 1) + tevc3 * tm(nt, i) + tevc4 * tm(nt, i + 1);
       tel(nt, i) = te;
@@ -433,6 +441,221 @@ void parabola_coeffs_fc_nosc(int ijdm, int ijs, int ije, PI1 stencil, PC tmc0, P
   }
 }
 
+// :436-488
+void h_edges_mono(int ijdm, int ijs, int ije, P1 hevc1, P1 hevc2, P1 hevc3, P1 hevc4, P1 ssc, P1 scc,
+                  P1 hm, P1 hel, P1 her) {
+  (void)ijdm;
+  double he, sl, sr, sc, d, q, r;
+  for (int i = ijs; i <= ije + 1; ++i) {
+    he = hevc1(i) * hm(i - 2) + hevc2(i) * hm(i - 1) + hevc3(i) * hm(i) + hevc4(i) * hm(i + 1);
+    hel(i) = he;
+    her(i - 1) = he;
+  }
+  for (int i = ijs; i <= ije; ++i) {
+    sl = ssc(i) * (hm(i) - hm(i - 1));
+    sr = ssc(i) * (hm(i + 1) - hm(i));
+    if (sl * sr > c0) {
+      sc = scc(i) * (hm(i + 1) - hm(i - 1));
+      sc = fsign(std::min(std::min(std::fabs(sl), std::fabs(sr)), std::fabs(sc)), sc);
+      if ((hm(i - 1) - hel(i)) * (hm(i) - hel(i)) > c0)
+        hel(i) = hm(i) - fsign(std::min(c1_2 * std::fabs(sc), std::fabs(hel(i) - hm(i))), sc);
+      if ((hm(i + 1) - her(i)) * (hm(i) - her(i)) > c0)
+        her(i) = hm(i) + fsign(std::min(c1_2 * std::fabs(sc), std::fabs(her(i) - hm(i))), sc);
+      d = her(i) - hel(i);
+      q = d * (c2 * hm(i) - hel(i) - her(i));
+      r = c1_3 * d * d;
+      if (q > r) hel(i) = c3 * hm(i) - c2 * her(i);
+      else if (-r > q) her(i) = c3 * hm(i) - c2 * hel(i);
+    } else {
+      hel(i) = hm(i);
+      her(i) = hm(i);
+    }
+  }
+}
+
+// :820-1116
+void parabola_coeffs_fc_mono(int ijdm, int ijs, int ije, PI1 stencil, PC tmc0, PC tmcl, PC tmcr,
+                             P1 ssc, P1 scc, P1 hm, P2 tm, P1 hel, P1 her,
+                             P1 hpc0, P1 hpc1, P1 hpc2, P2 tpc0, P2 tpc1, P2 tpc2) {
+  const int nb = hm.nb, ntl = tm.nt, n1 = ijdm + 2 * nb;
+  std::vector<double> w((size_t)n1 * 2 * ntl, 0.0);
+  P2 tel{w.data(), nb, ntl}, ter{w.data() + (size_t)n1 * ntl, nb, ntl};
+  double q, tevc1 = 0, tevc2 = 0, tevc3 = 0, tevc4 = 0, te, hf1m, hf1l, hf1r, hf2m, hf2l, hf2r, sl, sr,
+         sc, a2;
+  for (int i = ijs; i <= ije + 1; ++i) {
+    compat_edge_weights(i, stencil, tmc0, tmcl, tmcr, hm, hel, her, tevc1, tevc2, tevc3, tevc4);
+    for (int nt = 1; nt <= ntl; ++nt) {
+      te = tevc1 * tm(nt, i - 2) + tevc2 * tm(nt, i - 1) + tevc3 * tm(nt, i) + tevc4 * tm(nt, i + 1);
+      tel(nt, i) = te;
+      ter(nt, i - 1) = te;
+    }
+  }
+  for (int i = ijs; i <= ije; ++i) {
+    q = c1 / (c12 * hm(i) - hel(i) - her(i));
+    hf1m = c60 * hm(i) * q;
+    hf1l = -(c42 * hm(i) + c4 * hel(i) - c6 * her(i)) * q;
+    hf1r = -(c18 * hm(i) - c4 * hel(i) + c6 * her(i)) * q;
+    hf2m = -hf1m;
+    hf2l = c5 * (c6 * hm(i) + hel(i) - her(i)) * q;
+    hf2r = c5 * (c6 * hm(i) - hel(i) + her(i)) * q;
+    for (int nt = 1; nt <= ntl; ++nt) {
+      sl = ssc(i) * (tm(nt, i) - tm(nt, i - 1));
+      sr = ssc(i) * (tm(nt, i + 1) - tm(nt, i));
+      if (sl * sr > c0) {
+        sc = scc(i) * (tm(nt, i + 1) - tm(nt, i - 1));
+        sc = fsign(std::min(std::min(std::fabs(sl), std::fabs(sr)), std::fabs(sc)), sc);
+        if ((tm(nt, i - 1) - tel(nt, i)) * (tm(nt, i) - tel(nt, i)) > c0)
+          tel(nt, i) = tm(nt, i) - fsign(std::min(c1_2 * std::fabs(sc), std::fabs(tel(nt, i) - tm(nt, i))), sc);
+        if ((tm(nt, i + 1) - ter(nt, i)) * (tm(nt, i) - ter(nt, i)) > c0)
+          ter(nt, i) = tm(nt, i) + fsign(std::min(c1_2 * std::fabs(sc), std::fabs(ter(nt, i) - tm(nt, i))), sc);
+        sl = hf1m * tm(nt, i) + hf1l * tel(nt, i) + hf1r * ter(nt, i);
+        a2 = hf2m * tm(nt, i) + hf2l * tel(nt, i) + hf2r * ter(nt, i);
+        sr = sl + c2 * a2;
+        if (sl * sr < c0) {
+          if ((ter(nt, i) - tel(nt, i)) * a2 < c0)
+            tel(nt, i) = -((hf1m + c2 * hf2m) * tm(nt, i) + (hf1r + c2 * hf2r) * ter(nt, i)) / (hf1l + c2 * hf2l);
+          else
+            ter(nt, i) = -(hf1m * tm(nt, i) + hf1l * tel(nt, i)) / hf1r;
+        }
+      } else {
+        tel(nt, i) = tm(nt, i);
+        ter(nt, i) = tm(nt, i);
+      }
+    }
+    hpc0(i) = hel(i);
+    hpc1(i) = c6 * hm(i) - c4 * hel(i) - c2 * her(i);
+    hpc2(i) = c3 * (hel(i) - c2 * hm(i) + her(i));
+    for (int nt = 1; nt <= ntl; ++nt) {
+      tpc0(nt, i) = tel(nt, i);
+      tpc1(nt, i) = hf1m * tm(nt, i) + hf1l * tel(nt, i) + hf1r * ter(nt, i);
+      tpc2(nt, i) = hf2m * tm(nt, i) + hf2l * tel(nt, i) + hf2r * ter(nt, i);
+    }
+  }
+}
+
+// slope limiter + parabola monotonicity fix shared verbatim by the thickness and the tracer
+// branches of the partial-compatibility routines (:1168-1190, :1209-1232, :1309-1331, :1334-1358)
+inline void pc_limit(double ssc, double scc, double xm, double x0, double xp, double& el, double& er) {
+  double sl = ssc * (x0 - xm), sr = ssc * (xp - x0);
+  if (sl * sr > c0) {
+    double sc = scc * (xp - xm);
+    sc = fsign(std::min(std::min(std::fabs(sl), std::fabs(sr)), std::fabs(sc)), sc);
+    if ((xm - el) * (x0 - el) > c0) el = x0 - fsign(std::min(c1_2 * std::fabs(sc), std::fabs(el - x0)), sc);
+    if ((xp - er) * (x0 - er) > c0) er = x0 + fsign(std::min(c1_2 * std::fabs(sc), std::fabs(er - x0)), sc);
+    double d = er - el;
+    double q = d * (c2 * x0 - el - er);
+    double r = c1_3 * d * d;
+    if (q > r) el = c3 * x0 - c2 * er;
+    else if (-r > q) er = c3 * x0 - c2 * el;
+  } else {
+    el = x0;
+    er = x0;
+  }
+}
+
+// :1118-1264
+void parabola_coeffs_pc_nosc(int ijdm, int ijs, int ije, P1 hevc1, P1 hevc2, P1 hevc3, P1 hevc4,
+                             P1 ssc, P1 scc, P1 d2m, P1 hm, P2 tm,
+                             P1 hpc0, P1 hpc1, P1 hpc2, P2 tpc0, P2 tpc1, P2 tpc2) {
+  const int nb = hm.nb, ntl = tm.nt, n1 = ijdm + 2 * nb;
+  std::vector<double> w((size_t)n1 * (3 * ntl + 3), 0.0);
+  P2 d2t{w.data(), nb, ntl}, tel{w.data() + (size_t)n1 * ntl, nb, ntl},
+     ter{w.data() + (size_t)2 * n1 * ntl, nb, ntl};
+  double* b = w.data() + (size_t)3 * n1 * ntl;
+  P1 hel{b, nb}, her{b + n1, nb}, d2h{b + 2 * n1, nb};
+  double he, te, sl, sr, q, a2;
+  for (int i = ijs - 1; i <= ije + 2; ++i) {
+    he = hevc1(i) * hm(i - 2) + hevc2(i) * hm(i - 1) + hevc3(i) * hm(i) + hevc4(i) * hm(i + 1);
+    hel(i) = he;
+    her(i - 1) = he;
+    for (int nt = 1; nt <= ntl; ++nt) {
+      te = hevc1(i) * tm(nt, i - 2) + hevc2(i) * tm(nt, i - 1) + hevc3(i) * tm(nt, i) + hevc4(i) * tm(nt, i + 1);
+      tel(nt, i) = te;
+      ter(nt, i - 1) = te;
+    }
+  }
+  for (int i = ijs - 1; i <= ije + 1; ++i) {
+    d2h(i) = d2m(i) * (hel(i) - c2 * hm(i) + her(i));
+    for (int nt = 1; nt <= ntl; ++nt) d2t(nt, i) = d2m(i) * (tel(nt, i) - c2 * tm(nt, i) + ter(nt, i));
+  }
+  for (int i = ijs; i <= ije; ++i) {
+    if (d2h(i - 1) * d2h(i) <= c0 || d2h(i) * d2h(i + 1) <= c0)
+      pc_limit(ssc(i), scc(i), hm(i - 1), hm(i), hm(i + 1), hel(i), her(i));
+    hel(i) = std::max(hel(i), dpeps);
+    her(i) = std::max(her(i), dpeps);
+    sl = c2 * (c3 * hm(i) - c2 * hel(i) - her(i));
+    a2 = c3 * (hel(i) - c2 * hm(i) + her(i));
+    sr = sl + c2 * a2;
+    if (sl < c0 && sr > c0) {
+      if (a2 * hel(i) - c1_4 * sl * sl < a2 * dpeps) {
+        q = c3 * hm(i) / (c3 * sl * sr + c4 * a2 * a2);
+        hel(i) = sl * sl * q;
+        her(i) = sr * sr * q;
+      }
+    }
+    for (int nt = 1; nt <= ntl; ++nt)
+      if (d2t(nt, i - 1) * d2t(nt, i) <= c0 || d2t(nt, i) * d2t(nt, i + 1) <= c0)
+        pc_limit(ssc(i), scc(i), tm(nt, i - 1), tm(nt, i), tm(nt, i + 1), tel(nt, i), ter(nt, i));
+    for (int nt = 2; nt <= ntl; ++nt) {
+      tel(nt, i) = std::max(tel(nt, i), c0);
+      ter(nt, i) = std::max(ter(nt, i), c0);
+      sl = c2 * (c3 * tm(nt, i) - c2 * tel(nt, i) - ter(nt, i));
+      a2 = c3 * (tel(nt, i) - c2 * tm(nt, i) + ter(nt, i));
+      sr = sl + c2 * a2;
+      if (sl < c0 && sr > c0) {
+        if (a2 * tel(nt, i) - c1_4 * sl * sl < c0) {
+          q = c3 * tm(nt, i) / (c3 * sl * sr + c4 * a2 * a2);
+          tel(nt, i) = sl * sl * q;
+          ter(nt, i) = sr * sr * q;
+        }
+      }
+    }
+    hpc0(i) = hel(i);
+    hpc1(i) = c6 * hm(i) - c4 * hel(i) - c2 * her(i);
+    hpc2(i) = c3 * (hel(i) - c2 * hm(i) + her(i));
+    for (int nt = 1; nt <= ntl; ++nt) {
+      tpc0(nt, i) = tel(nt, i);
+      tpc1(nt, i) = c6 * tm(nt, i) - c4 * tel(nt, i) - c2 * ter(nt, i);
+      tpc2(nt, i) = c3 * (tel(nt, i) - c2 * tm(nt, i) + ter(nt, i));
+    }
+  }
+}
+
+// :1266-1371
+void parabola_coeffs_pc_mono(int ijdm, int ijs, int ije, P1 hevc1, P1 hevc2, P1 hevc3, P1 hevc4,
+                             P1 ssc, P1 scc, P1 hm, P2 tm,
+                             P1 hpc0, P1 hpc1, P1 hpc2, P2 tpc0, P2 tpc1, P2 tpc2) {
+  const int nb = hm.nb, ntl = tm.nt, n1 = ijdm + 2 * nb;
+  std::vector<double> w((size_t)n1 * (2 * ntl + 2), 0.0);
+  P2 tel{w.data(), nb, ntl}, ter{w.data() + (size_t)n1 * ntl, nb, ntl};
+  double* b = w.data() + (size_t)2 * n1 * ntl;
+  P1 hel{b, nb}, her{b + n1, nb};
+  double he, te;
+  for (int i = ijs; i <= ije + 1; ++i) {
+    he = hevc1(i) * hm(i - 2) + hevc2(i) * hm(i - 1) + hevc3(i) * hm(i) + hevc4(i) * hm(i + 1);
+    hel(i) = he;
+    her(i - 1) = he;
+    for (int nt = 1; nt <= ntl; ++nt) {
+      te = hevc1(i) * tm(nt, i - 2) + hevc2(i) * tm(nt, i - 1) + hevc3(i) * tm(nt, i) + hevc4(i) * tm(nt, i + 1);
+      tel(nt, i) = te;
+      ter(nt, i - 1) = te;
+    }
+  }
+  for (int i = ijs; i <= ije; ++i) {
+    pc_limit(ssc(i), scc(i), hm(i - 1), hm(i), hm(i + 1), hel(i), her(i));
+    for (int nt = 1; nt <= ntl; ++nt)
+      pc_limit(ssc(i), scc(i), tm(nt, i - 1), tm(nt, i), tm(nt, i + 1), tel(nt, i), ter(nt, i));
+    hpc0(i) = hel(i);
+    hpc1(i) = c6 * hm(i) - c4 * hel(i) - c2 * her(i);
+    hpc2(i) = c3 * (hel(i) - c2 * hm(i) + her(i));
+    for (int nt = 1; nt <= ntl; ++nt) {
+      tpc0(nt, i) = tel(nt, i);
+      tpc1(nt, i) = c6 * tm(nt, i) - c4 * tel(nt, i) - c2 * ter(nt, i);
+      tpc2(nt, i) = c3 * (tel(nt, i) - c2 * tm(nt, i) + ter(nt, i));
+    }
+  }
+}
+
 // :1373-1468
 void flux_integration(int ijs, int ije, P1 ca, P1 ai, P1 db, P1 du, P1 dl, P1 hpc0, P1 hpc1,
                       P1 hpc2, P2 tpc0, P2 tpc1, P2 tpc2, P1 hf, P2 htf) {
@@ -504,8 +727,11 @@ struct Scalars {
   }
 };
 
-// :1470-1623
-void cppm_fc_nosc_i(int m, int n, int mm, int nn, int k1m, int k1n, bool second_pass) {
+// :1470-1623 (fc_nosc), :1787-1939 (fc_mono), :2102-2200 (pc_nosc), :2302-2399 (pc_mono): the four
+// i-direction drivers differ only in the halo width (4 nosc / 3 mono), the pencil range that follows
+// from it, whether the thickness edges are staged through hel_3d/her_3d (full compatibility) and
+// which reconstruction routine they call.
+void cppm_pass_i(int m, int n, int mm, int nn, int k1m, int k1n, bool second_pass, bool full, bool mono) {
   (void)m; (void)k1m;
   Oracle& o = O(); const Dims& d = o.d;
   const int idm = d.idm, jdm = d.jdm, kdm = d.kdm, nb = d.nbdy, ii = d.ii, jj = d.jj;
@@ -520,11 +746,14 @@ void cppm_fc_nosc_i(int m, int n, int mm, int nn, int k1m, int k1n, bool second_
   Pencils P(idm, nb, ntl);
   auto row = [&](std::vector<double>& v, int j) { return P1{v.data() + (size_t)(j + nb - 1) * d.ldi, nb}; };
 
-  xctilr(dp.from(k1n), 1, kdm, 4, 0, halo_ps);
-  xctilr(temp.from(k1n), 1, kdm, 4, 0, halo_ps);
-  xctilr(saln.from(k1n), 1, kdm, 4, 0, halo_ps);
-  for (int nt = 3; nt <= ntl; ++nt) xctilr(trc.from(k1n + (nt - 3) * 2 * kdm), 1, kdm, 4, 0, halo_ps);
+  const int hw = mono ? 3 : 4;          // halo width
+  const int lo = mono ? -2 : -3, hi = idm + (mono ? 3 : 4);
+  xctilr(dp.from(k1n), 1, kdm, hw, 0, halo_ps);
+  xctilr(temp.from(k1n), 1, kdm, hw, 0, halo_ps);
+  xctilr(saln.from(k1n), 1, kdm, hw, 0, halo_ps);
+  for (int nt = 3; nt <= ntl; ++nt) xctilr(trc.from(k1n + (nt - 3) * 2 * kdm), 1, kdm, hw, 0, halo_ps);
 
+  if (full) {
   for (int k = 1; k <= kdm; ++k) {
     const int kn = k + nn;
     for (int j = 1; j <= jdm; ++j) {
@@ -535,42 +764,63 @@ void cppm_fc_nosc_i(int m, int n, int mm, int nn, int k1m, int k1n, bool second_
       if (second_pass)
         for (int i = -2; i <= idm + 3; ++i)
           P.hm(i) = P.hm(i) / (c1 - (cav(i, j + 1, k) - cav(i, j, k)) * P.ai(i));
-      h_edges_nosc(idm, 1, idm, row(T.hevc1i, j), row(T.hevc2i, j), row(T.hevc3i, j),
-                   row(T.hevc4i, j), row(T.ssci, j), row(T.scci, j), row(T.d2mi, j), P.hm, P.hel,
-                   P.her);
+      if (mono)
+        h_edges_mono(idm, 1, idm, row(T.hevc1i, j), row(T.hevc2i, j), row(T.hevc3i, j),
+                     row(T.hevc4i, j), row(T.ssci, j), row(T.scci, j), P.hm, P.hel, P.her);
+      else
+        h_edges_nosc(idm, 1, idm, row(T.hevc1i, j), row(T.hevc2i, j), row(T.hevc3i, j),
+                     row(T.hevc4i, j), row(T.ssci, j), row(T.scci, j), row(T.d2mi, j), P.hm, P.hel,
+                     P.her);
       for (int i = 1; i <= idm; ++i) { hel_3d(i, j, k) = P.hel(i); her_3d(i, j, k) = P.her(i); }
     }
   }
-  xctilr(hel_3d, 1, kdm, 4, 0, halo_ps);
-  xctilr(her_3d, 1, kdm, 4, 0, halo_ps);
-  if (d.nreg == 2) {  // :1532 (single tile: nproc == jpr)
+  xctilr(hel_3d, 1, kdm, hw, 0, halo_ps);
+  xctilr(her_3d, 1, kdm, hw, 0, halo_ps);
+  if (d.nreg == 2) {  // :1532 / :1848 (single tile: nproc == jpr)
     const int j = jj;
     for (int k = 1; k <= kdm; ++k)
-      for (int i = -3; i <= ii + 4; ++i) std::swap(hel_3d(i, j, k), her_3d(i, j, k));
+      for (int i = (mono ? -2 : -3); i <= ii + (mono ? 3 : 4); ++i) std::swap(hel_3d(i, j, k), her_3d(i, j, k));
   }
+  }  // full
 
   for (int k = 1; k <= kdm; ++k) {
     const int km = k + mm, kn = k + nn;
     for (int j = 1; j <= jdm; ++j) {
       for (int i = 1; i <= idm + 1; ++i) { P.ca(i) = cau(i, j, k); P.db(i) = pbu(i, j, n); }
       for (int i = 0; i <= idm + 1; ++i) { P.du(i) = p(i, j, k); P.dl(i) = p(i, j, k + 1); }
-      for (int i = -3; i <= idm + 4; ++i) {
+      for (int i = lo; i <= hi; ++i) {
         P.ai(i) = scp2i(i, j);
         P.ho(i) = std::max(c0, dp(i, j, kn)) + dpeps;
         P.hm(i) = P.ho(i);
-        P.hel(i) = hel_3d(i, j, k);
-        P.her(i) = her_3d(i, j, k);
+        if (full) {
+          P.hel(i) = hel_3d(i, j, k);
+          P.her(i) = her_3d(i, j, k);
+        }
         for (int nt = 1; nt <= ntl; ++nt) P.tm(nt, i) = S.at(nt, i, j, kn);
       }
       if (second_pass)
-        for (int i = -3; i <= idm + 4; ++i)
+        for (int i = lo; i <= hi; ++i)
           P.hm(i) = P.hm(i) / (c1 - (cav(i, j + 1, k) - cav(i, j, k)) * P.ai(i));
       const size_t ro = (size_t)(j + nb - 1) * d.ldi;
-      parabola_coeffs_fc_nosc(idm, 0, idm + 1, PI1{T.stencili.data() + ro, nb},
-                              PC{T.tmc0i.data() + ro * 12, nb}, PC{T.tmcli.data() + ro * 12, nb},
-                              PC{T.tmcri.data() + ro * 12, nb}, row(T.ssci, j), row(T.scci, j),
-                              row(T.d2mi, j), P.hm, P.tm, P.hel, P.her, P.hpc0, P.hpc1, P.hpc2,
-                              P.tpc0, P.tpc1, P.tpc2);
+      if (full && !mono)
+        parabola_coeffs_fc_nosc(idm, 0, idm + 1, PI1{T.stencili.data() + ro, nb},
+                                PC{T.tmc0i.data() + ro * 12, nb}, PC{T.tmcli.data() + ro * 12, nb},
+                                PC{T.tmcri.data() + ro * 12, nb}, row(T.ssci, j), row(T.scci, j),
+                                row(T.d2mi, j), P.hm, P.tm, P.hel, P.her, P.hpc0, P.hpc1, P.hpc2,
+                                P.tpc0, P.tpc1, P.tpc2);
+      else if (full)
+        parabola_coeffs_fc_mono(idm, 0, idm + 1, PI1{T.stencili.data() + ro, nb},
+                                PC{T.tmc0i.data() + ro * 12, nb}, PC{T.tmcli.data() + ro * 12, nb},
+                                PC{T.tmcri.data() + ro * 12, nb}, row(T.ssci, j), row(T.scci, j),
+                                P.hm, P.tm, P.hel, P.her, P.hpc0, P.hpc1, P.hpc2, P.tpc0, P.tpc1, P.tpc2);
+      else if (!mono)
+        parabola_coeffs_pc_nosc(idm, 0, idm + 1, row(T.hevc1i, j), row(T.hevc2i, j), row(T.hevc3i, j),
+                                row(T.hevc4i, j), row(T.ssci, j), row(T.scci, j), row(T.d2mi, j), P.hm,
+                                P.tm, P.hpc0, P.hpc1, P.hpc2, P.tpc0, P.tpc1, P.tpc2);
+      else
+        parabola_coeffs_pc_mono(idm, 0, idm + 1, row(T.hevc1i, j), row(T.hevc2i, j), row(T.hevc3i, j),
+                                row(T.hevc4i, j), row(T.ssci, j), row(T.scci, j), P.hm, P.tm, P.hpc0,
+                                P.hpc1, P.hpc2, P.tpc0, P.tpc1, P.tpc2);
       flux_integration(1, idm + 1, P.ca, P.ai, P.db, P.du, P.dl, P.hpc0, P.hpc1, P.hpc2, P.tpc0,
                        P.tpc1, P.tpc2, P.hf, P.htf);
       for (int i = 1; i <= idm; ++i) {
@@ -589,8 +839,8 @@ void cppm_fc_nosc_i(int m, int n, int mm, int nn, int k1m, int k1n, bool second_
   }
 }
 
-// :1625-1785
-void cppm_fc_nosc_j(int m, int n, int mm, int nn, int k1m, int k1n, bool second_pass) {
+// :1625-1785 (fc_nosc), :1941-2100 (fc_mono), :2202-2300 (pc_nosc), :2401-2498 (pc_mono)
+void cppm_pass_j(int m, int n, int mm, int nn, int k1m, int k1n, bool second_pass, bool full, bool mono) {
   (void)m; (void)k1m;
   Oracle& o = O(); const Dims& d = o.d;
   const int idm = d.idm, jdm = d.jdm, kdm = d.kdm, nb = d.nbdy, ii = d.ii, jj = d.jj;
@@ -606,11 +856,14 @@ void cppm_fc_nosc_j(int m, int n, int mm, int nn, int k1m, int k1n, bool second_
   // transposed tables: (j,i) with leading dimension ldj
   auto col = [&](std::vector<double>& v, int i) { return P1{v.data() + (size_t)(i + nb - 1) * d.ldj, nb}; };
 
-  xctilr(dp.from(k1n), 1, kdm, 0, 4, halo_ps);
-  xctilr(temp.from(k1n), 1, kdm, 0, 4, halo_ps);
-  xctilr(saln.from(k1n), 1, kdm, 0, 4, halo_ps);
-  for (int nt = 3; nt <= ntl; ++nt) xctilr(trc.from(k1n + (nt - 3) * 2 * kdm), 1, kdm, 0, 4, halo_ps);
+  const int hw = mono ? 3 : 4;
+  const int lo = mono ? -2 : -3, hi = jdm + (mono ? 3 : 4);
+  xctilr(dp.from(k1n), 1, kdm, 0, hw, halo_ps);
+  xctilr(temp.from(k1n), 1, kdm, 0, hw, halo_ps);
+  xctilr(saln.from(k1n), 1, kdm, 0, hw, halo_ps);
+  for (int nt = 3; nt <= ntl; ++nt) xctilr(trc.from(k1n + (nt - 3) * 2 * kdm), 1, kdm, 0, hw, halo_ps);
 
+  if (full) {
   for (int k = 1; k <= kdm; ++k) {
     const int kn = k + nn;
     for (int i = 1; i <= idm; ++i) {
@@ -621,15 +874,19 @@ void cppm_fc_nosc_j(int m, int n, int mm, int nn, int k1m, int k1n, bool second_
       if (second_pass)
         for (int j = -2; j <= jdm + 3; ++j)
           P.hm(j) = P.hm(j) / (c1 - (cau(i + 1, j, k) - cau(i, j, k)) * P.ai(j));
-      h_edges_nosc(jdm, 1, jdm, col(T.hevc1j, i), col(T.hevc2j, i), col(T.hevc3j, i),
-                   col(T.hevc4j, i), col(T.sscj, i), col(T.sccj, i), col(T.d2mj, i), P.hm, P.hel,
-                   P.her);
+      if (mono)
+        h_edges_mono(jdm, 1, jdm, col(T.hevc1j, i), col(T.hevc2j, i), col(T.hevc3j, i),
+                     col(T.hevc4j, i), col(T.sscj, i), col(T.sccj, i), P.hm, P.hel, P.her);
+      else
+        h_edges_nosc(jdm, 1, jdm, col(T.hevc1j, i), col(T.hevc2j, i), col(T.hevc3j, i),
+                     col(T.hevc4j, i), col(T.sscj, i), col(T.sccj, i), col(T.d2mj, i), P.hm, P.hel,
+                     P.her);
       for (int j = 1; j <= jdm; ++j) { hel_3d(i, j, k) = P.hel(j); her_3d(i, j, k) = P.her(j); }
     }
   }
-  xctilr(hel_3d, 1, kdm, 0, 4, halo_ps);
-  xctilr(her_3d, 1, kdm, 0, 4, halo_ps);
-  if (d.nreg == 2) {  // :1687-1703
+  xctilr(hel_3d, 1, kdm, 0, hw, halo_ps);
+  xctilr(her_3d, 1, kdm, 0, hw, halo_ps);
+  if (d.nreg == 2) {  // :1687-1703 / :2003-2019
     const bool fold_fix = o.option("cppm_fold_fix", "0") == "1";
     for (int k = 1; k <= kdm; ++k) {
       int j = jj;
@@ -638,33 +895,50 @@ void cppm_fc_nosc_j(int m, int n, int mm, int nn, int k1m, int k1n, bool second_
       // whole row, which restores round-off mass conservation across the fold.
       for (int i = (fold_fix ? 1 : std::max(1, d.itdm / 2 - d.i0 + 1)); i <= ii; ++i)
         std::swap(hel_3d(i, j, k), her_3d(i, j, k));
-      for (j = jj + 1; j <= jj + 4; ++j)
+      for (j = jj + 1; j <= jj + hw; ++j)
         for (int i = 1; i <= ii; ++i) std::swap(hel_3d(i, j, k), her_3d(i, j, k));
     }
   }
+  }  // full
 
   for (int k = 1; k <= kdm; ++k) {
     const int km = k + mm, kn = k + nn;
     for (int i = 1; i <= idm; ++i) {
       for (int j = 1; j <= jdm + 1; ++j) { P.ca(j) = cav(i, j, k); P.db(j) = pbv(i, j, n); }
       for (int j = 0; j <= jdm + 1; ++j) { P.du(j) = p(i, j, k); P.dl(j) = p(i, j, k + 1); }
-      for (int j = -3; j <= jdm + 4; ++j) {
+      for (int j = lo; j <= hi; ++j) {
         P.ai(j) = scp2i(i, j);
         P.ho(j) = std::max(c0, dp(i, j, kn)) + dpeps;
         P.hm(j) = P.ho(j);
-        P.hel(j) = hel_3d(i, j, k);
-        P.her(j) = her_3d(i, j, k);
+        if (full) {
+          P.hel(j) = hel_3d(i, j, k);
+          P.her(j) = her_3d(i, j, k);
+        }
         for (int nt = 1; nt <= ntl; ++nt) P.tm(nt, j) = S.at(nt, i, j, kn);
       }
       if (second_pass)
-        for (int j = -3; j <= jdm + 4; ++j)
+        for (int j = lo; j <= hi; ++j)
           P.hm(j) = P.hm(j) / (c1 - (cau(i + 1, j, k) - cau(i, j, k)) * P.ai(j));
       const size_t co = (size_t)(i + nb - 1) * d.ldj;
-      parabola_coeffs_fc_nosc(jdm, 0, jdm + 1, PI1{T.stencilj.data() + co, nb},
-                              PC{T.tmc0j.data() + co * 12, nb}, PC{T.tmclj.data() + co * 12, nb},
-                              PC{T.tmcrj.data() + co * 12, nb}, col(T.sscj, i), col(T.sccj, i),
-                              col(T.d2mj, i), P.hm, P.tm, P.hel, P.her, P.hpc0, P.hpc1, P.hpc2,
-                              P.tpc0, P.tpc1, P.tpc2);
+      if (full && !mono)
+        parabola_coeffs_fc_nosc(jdm, 0, jdm + 1, PI1{T.stencilj.data() + co, nb},
+                                PC{T.tmc0j.data() + co * 12, nb}, PC{T.tmclj.data() + co * 12, nb},
+                                PC{T.tmcrj.data() + co * 12, nb}, col(T.sscj, i), col(T.sccj, i),
+                                col(T.d2mj, i), P.hm, P.tm, P.hel, P.her, P.hpc0, P.hpc1, P.hpc2,
+                                P.tpc0, P.tpc1, P.tpc2);
+      else if (full)
+        parabola_coeffs_fc_mono(jdm, 0, jdm + 1, PI1{T.stencilj.data() + co, nb},
+                                PC{T.tmc0j.data() + co * 12, nb}, PC{T.tmclj.data() + co * 12, nb},
+                                PC{T.tmcrj.data() + co * 12, nb}, col(T.sscj, i), col(T.sccj, i),
+                                P.hm, P.tm, P.hel, P.her, P.hpc0, P.hpc1, P.hpc2, P.tpc0, P.tpc1, P.tpc2);
+      else if (!mono)
+        parabola_coeffs_pc_nosc(jdm, 0, jdm + 1, col(T.hevc1j, i), col(T.hevc2j, i), col(T.hevc3j, i),
+                                col(T.hevc4j, i), col(T.sscj, i), col(T.sccj, i), col(T.d2mj, i), P.hm,
+                                P.tm, P.hpc0, P.hpc1, P.hpc2, P.tpc0, P.tpc1, P.tpc2);
+      else
+        parabola_coeffs_pc_mono(jdm, 0, jdm + 1, col(T.hevc1j, i), col(T.hevc2j, i), col(T.hevc3j, i),
+                                col(T.hevc4j, i), col(T.sscj, i), col(T.sccj, i), P.hm, P.tm, P.hpc0,
+                                P.hpc1, P.hpc2, P.tpc0, P.tpc1, P.tpc2);
       flux_integration(1, jdm + 1, P.ca, P.ai, P.db, P.du, P.dl, P.hpc0, P.hpc1, P.hpc2, P.tpc0,
                        P.tpc1, P.tpc2, P.hf, P.htf);
       for (int j = 1; j <= jdm; ++j) {
@@ -697,7 +971,7 @@ void swap_stencil_tag(int& s) {  // :2653-2666
 
 }  // namespace
 
-// :2504-2746 (options fixed to full / non_oscillatory)
+// :2504-2746 (the tables do not depend on the compatibility / limiting options)
 void init_cppm() {
   Oracle& o = O(); const Dims& d = o.d;
   const int idm = d.idm, jdm = d.jdm, nb = d.nbdy, ii = d.ii, jj = d.jj;
@@ -826,18 +1100,25 @@ const int* cppm_stencil(const char* name, size_t* n) {
   return v->data();
 }
 
-// :2748-2834 (full / non_oscillatory branch)
+// :2748-2834
 void cppm(int m, int n, int mm, int nn, int k1m, int k1n) {
   Oracle& o = O(); const Dims& d = o.d;
   const int nstep = (int)o.scalar("nstep");
-  xctilr(o.a3("cau"), 1, d.kdm, 4, 4, halo_uv);
-  xctilr(o.a3("cav"), 1, d.kdm, 4, 4, halo_vv);
+  const std::string comp = o.option("cppm_compatibility", "full"), lim = o.option("cppm_limiting", "non_oscillatory");
+  if (comp != "full" && comp != "partial")
+    throw std::runtime_error(" init_cppm: cppm_compatibility = " + comp + " is unsupported!");
+  if (lim != "monotonic" && lim != "non_oscillatory")
+    throw std::runtime_error(" init_cppm: cppm_limiting = " + lim + " is unsupported!");
+  const bool full = comp == "full", mono = lim == "monotonic";
+  const int hw = mono ? 3 : 4;
+  xctilr(o.a3("cau"), 1, d.kdm, hw, hw, halo_uv);
+  xctilr(o.a3("cav"), 1, d.kdm, hw, hw, halo_vv);
   if (nstep % 2 == 1) {
-    cppm_fc_nosc_i(m, n, mm, nn, k1m, k1n, false);
-    cppm_fc_nosc_j(m, n, mm, nn, k1m, k1n, true);
+    cppm_pass_i(m, n, mm, nn, k1m, k1n, false, full, mono);
+    cppm_pass_j(m, n, mm, nn, k1m, k1n, true, full, mono);
   } else {
-    cppm_fc_nosc_j(m, n, mm, nn, k1m, k1n, false);
-    cppm_fc_nosc_i(m, n, mm, nn, k1m, k1n, true);
+    cppm_pass_j(m, n, mm, nn, k1m, k1n, false, full, mono);
+    cppm_pass_i(m, n, mm, nn, k1m, k1n, true, full, mono);
   }
 }
 

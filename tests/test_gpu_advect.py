@@ -81,6 +81,51 @@ def test_advect_perf_build(cfg):
         g.finalize()
 
 
+VARIANTS = {"fc_mono": ("full", "monotonic"), "pc_nosc": ("partial", "non_oscillatory"),
+            "pc_mono": ("partial", "monotonic")}  # phy/mod_cppm.F90:44-48, :1787-2502
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("cfg", ["tiny1", "tiny2", "tiny3", "tiny4"])
+@pytest.mark.parametrize("nstep", [1, 2])
+def test_advect_variants_parity_build(cfg, nstep, variant):
+    """fc_mono / pc_nosc / pc_mono against the oracle: <= 1e-13 relative with the -fmad=false build,
+    halo ring 1 of the transported fields included (advect refreshes it, mod_advect.F90:176-187)."""
+    comp, lim = VARIANTS[variant]
+    c, o, g = run_pair(cfg, 1, nstep, parity=True, opts={"cppm_compatibility": comp, "cppm_limiting": lim})
+    try:
+        for nm in FIELDS + ["trc"]:
+            halo = 1 if nm in ("dp", "temp", "saln", "trc") else 0
+            err = max_rel_err(interior(g.arrays[nm], halo=halo), interior(o.arrays[nm], halo=halo))
+            assert err <= 1e-13, (variant, nm, err)
+    finally:
+        g.finalize()
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_advect_variants_perf_build(variant):
+    comp, lim = VARIANTS[variant]
+    c, o, g = run_pair("fuk95", 1, 1, parity=False, opts={"cppm_compatibility": comp, "cppm_limiting": lim})
+    try:
+        for nm in FIELDS + ["trc"]:
+            err = max_rel_err(interior(g.arrays[nm]), interior(o.arrays[nm]))
+            assert err <= 1e-11, (variant, nm, err)
+    finally:
+        g.finalize()
+
+
+def test_init_cppm_rejects_unknown_variant():
+    from blom_b200.lib import BlomGpuError
+    c = Case("tiny1")
+    g = c.new_gpu()
+    try:
+        g.set_option("cppm_compatibility", "half")
+        with pytest.raises(BlomGpuError, match="cppm_compatibility = half is unsupported"):
+            g.init_cppm()
+    finally:
+        g.finalize()
+
+
 def test_advect_fold_fix_option():
     c, o, g = run_pair("tiny2", 0, 2, parity=True, opts={"cppm_fold_fix": "1"})
     try:

@@ -24,11 +24,21 @@ def inventories(a, c, nn, rows=slice(None)):
     return out
 
 
+VARIANTS = [("full", "non_oscillatory"), ("full", "monotonic"), ("partial", "non_oscillatory"),
+            ("partial", "monotonic")]  # phy/mod_cppm.F90:44-48
+
+
+def set_variant(b, variant):
+    b.set_option("cppm_compatibility", variant[0])
+    b.set_option("cppm_limiting", variant[1])
+
+
+@pytest.mark.parametrize("variant", VARIANTS, ids=["fc_nosc", "fc_mono", "pc_nosc", "pc_mono"])
 @pytest.mark.parametrize("cfg", ["tiny0", "tiny1", "tiny3", "tiny4"])
 @pytest.mark.parametrize("nstep", [1, 2])
-def test_conservation_roundoff(cfg, nstep):
+def test_conservation_roundoff(cfg, nstep, variant):
     c = Case(cfg, ntr=1, nstep=nstep)
-    o = c.new_oracle(); o.init_cppm()
+    o = c.new_oracle(); set_variant(o, variant); o.init_cppm()
     m, n, mm, nn, k1m, k1n = c.levels
     inv0 = inventories(o.arrays, c, nn)
     o.advect(*c.levels)
@@ -36,7 +46,8 @@ def test_conservation_roundoff(cfg, nstep):
     for k in inv0:
         assert abs(inv1[k] - inv0[k]) <= 2e-14 * abs(inv0[k]), (k, inv0[k], inv1[k])
     assert o.arrays["dp"].min() >= 0.0
-    assert interior(o.arrays["saln"]).min() >= 0.0 and interior(o.arrays["trc"]).min() >= 0.0
+    if variant[1] == "non_oscillatory":  # the positivity fix exists in the nosc routines only (:788-801, :1234-1248)
+        assert interior(o.arrays["saln"]).min() >= 0.0 and interior(o.arrays["trc"]).min() >= 0.0
     # dp actually moved
     assert np.abs(o.arrays["dp"][nn:nn + c.dims[2]] - c.state["dp"][nn:nn + c.dims[2]]).max() > 1.0
 
@@ -61,13 +72,14 @@ def test_fold_conservation(nstep):
     assert 1e-12 < res["0"]["mass"] < 1e-5  # the reference quirk is visible but small
 
 
+@pytest.mark.parametrize("variant", VARIANTS, ids=["fc_nosc", "fc_mono", "pc_nosc", "pc_mono"])
 @pytest.mark.parametrize("cfg", ["tiny1", "tiny2", "tiny3"])
-def test_uniform_tracer_stays_uniform(cfg):
+def test_uniform_tracer_stays_uniform(cfg, variant):
     c = Case(cfg, ntr=1, nstep=1)
     kk = c.dims[2]
     c.state["trc"][:] = 3.25
     c.state["temp"][:] = 7.5
-    o = c.new_oracle(); o.init_cppm()
+    o = c.new_oracle(); set_variant(o, variant); o.init_cppm()
     nn = c.levels[3]
     o.advect(*c.levels)
     ip = interior(c.masks["ip"]) == 1
@@ -87,3 +99,28 @@ def test_zero_velocity_is_identity():
     d0 = interior(c.state["dp"][nn:nn + kk]); d1 = interior(o.arrays["dp"][nn:nn + kk])
     assert np.abs(d1 - d0).max() <= 1e-9  # dpeps add/subtract only
     assert np.abs(interior(o.arrays["uflx"])).max() == 0.0
+
+
+def test_variants_differ():
+    """The four variants are different schemes: on rough data their outputs differ by far more than
+    round-off (guards against an option that is silently ignored) but stay the same order of magnitude."""
+    outs = {}
+    for v in VARIANTS:
+        c = Case("tiny3", ntr=1, nstep=1)
+        o = c.new_oracle(); set_variant(o, v); o.init_cppm()
+        o.advect(*c.levels)
+        nn, kk = c.levels[3], c.dims[2]
+        outs[v] = interior(o.arrays["temp"][nn:nn + kk]).copy()
+    ref = outs[VARIANTS[0]]
+    for v in VARIANTS[1:]:
+        d = np.abs(outs[v] - ref).max()
+        assert 1e-8 < d < 5.0, (v, d)
+
+
+def test_rejects_unknown_variant():
+    from oracle.oracle import OracleError
+    c = Case("tiny1")
+    o = c.new_oracle(); o.init_cppm()
+    o.set_option("cppm_limiting", "tvd")
+    with pytest.raises(OracleError, match="cppm_limiting = tvd is unsupported"):
+        o.advect(*c.levels)
