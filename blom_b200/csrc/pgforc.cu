@@ -1,5 +1,5 @@
-// Pressure-gradient force, pgfmth='dynamic enthalpy'
-// (phy/mod_pgforc.F90:438-615 and :262-408).
+// Pressure-gradient force (phy/mod_pgforc.F90:438-615): pgfmth='dynamic enthalpy' (:262-408, the
+// default) and pgfmth='geopotential' (:95-260).
 //
 // B200 design: the reference stages five kdm-level temporaries (pot_dynh,
 // pot_dynh_pb, dynh_a, dynh_t, alpha_r) through memory between its column sweep
@@ -164,6 +164,88 @@ pg_dynh_march(Geom g, eos::Coef ec, int n, int nn, const int* __restrict__ ip, c
   (void)s;
 }
 
+// ---- pgfmth='geopotential' (:95-260) ---------------------------------------------------------
+// Column pass: geopotential phi at the layer interfaces and phip = sum of p*alpha jumps, marched
+// bottom-up on 0..ii x 0..jj (:114-137); one thread per column, lanes along i.
+__global__ void pg_geop_column(Geom g, int nn, const int* __restrict__ ip, const double* __restrict__ p,
+                               const double* __restrict__ dp, const double* __restrict__ temp,
+                               const double* __restrict__ saln, double* __restrict__ phi,
+                               double* __restrict__ phip) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j);
+  if (ip[x] != 1) return;
+  const int kk = g.kdm;
+  double phik = phi[x + (long)kk * g.lev], phipk = 0., pk1 = p[x + (long)kk * g.lev];
+  phip[x + (long)kk * g.lev] = 0.;
+  for (int k = kk; k >= 1; --k) {
+    const long xn = x + (long)(k + nn - 1) * g.lev, xk = x + (long)(k - 1) * g.lev;
+    const double pk = p[xk];
+    if (!(dp[xn] < epsilp)) {
+      double dphi, alpu, alpl;
+      eos::delphi(pk, pk1, temp[xn], saln[xn], dphi, alpu, alpl);
+      phik = phik - dphi;
+      phipk = phipk + pk1 * alpl - pk * alpu;
+    }
+    phi[xk] = phik;
+    phip[xk] = phipk;
+    pk1 = pk;
+  }
+}
+
+// Face pass (:141-256): for every u (DIR 0) or v (DIR 1) face column march bottom-up, track the
+// layers kp/km of the two adjacent columns that contain the face's mid-layer pressure (monotone
+// search, the reference's do-while), evaluate both geopotentials at that pressure and difference
+// them.  Also takes the pgfx_o/pgfy_o copy of the caller (:507-521) so pgfx is touched once.
+template <int DIR>
+__global__ void pg_geop_face(Geom g, int n, int nn, const int* __restrict__ imask, const double* __restrict__ p,
+                             const double* __restrict__ pd, const double* __restrict__ dpd,
+                             const double* __restrict__ temp, const double* __restrict__ saln,
+                             const double* __restrict__ phi, const double* __restrict__ phip,
+                             double* __restrict__ pgf, double* __restrict__ pgf_o, double* __restrict__ pgfm,
+                             double* __restrict__ xip, double* __restrict__ xim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j);
+  if (imask[x] != 1) return;
+  const long xm = x - (DIR == 0 ? 1 : g.ldi), lev = g.lev;
+  const int kk = g.kdm;
+  int kp = kk, km = kk;
+  double a_xip = 0., a_xim = 0., a_pgfm = 0.;
+  double pp1 = p[x + (long)kk * lev], pm1 = p[xm + (long)kk * lev];   // p(k+1) of the two columns
+  for (int k = kk; k >= 1; --k) {
+    const long xn = x + (long)(k + nn - 1) * lev, xk = x + (long)(k - 1) * lev;
+    const double dd = dpd[xn];
+    const double prs = pd[x + (long)k * lev] - .5 * dd;
+    // p(.,1) = 0 <= prs stops the search at the surface; the bound only guards corrupt input
+    while (kp > 1 && p[x + (long)(kp - 1) * lev] > prs) kp = kp - 1;
+    while (km > 1 && p[xm + (long)(km - 1) * lev] > prs) km = km - 1;
+    double dphip, alpup, alplp, dphim, alpum, alplm;
+    const double pkp1 = p[x + (long)kp * lev], pkm1 = p[xm + (long)km * lev];
+    eos::delphi(prs, pkp1, temp[x + (long)(kp + nn - 1) * lev], saln[x + (long)(kp + nn - 1) * lev], dphip, alpup,
+                alplp);
+    eos::delphi(prs, pkm1, temp[xm + (long)(km + nn - 1) * lev], saln[xm + (long)(km + nn - 1) * lev], dphim, alpum,
+                alplm);
+    const double pp0 = p[xk], pm0 = p[xm + (long)(k - 1) * lev];
+    double cp = .25 * (pp1 + pp0);
+    double cm = .25 * (pm1 + pm0);
+    const double q = prs / (cp + cm);
+    cp = q * cp;
+    cm = q * cm;
+    const double phi_p = phi[x + (long)kp * lev] - dphip;
+    a_xip = a_xip + (phip[x + (long)kp * lev] + pkp1 * alplp - cp * (alpup - alpum)) * dd;
+    const double phi_m = phi[xm + (long)km * lev] - dphim;
+    a_xim = a_xim + (phip[xm + (long)km * lev] + pkm1 * alplm - cm * (alpum - alpup)) * dd;
+    const double f = -(phi_p - phi_m);
+    pgf_o[xk] = pgf[xn];
+    pgf[xn] = f;
+    a_pgfm = a_pgfm + f * dd;
+    pp1 = pp0; pm1 = pm0;
+  }
+  const long x2 = x + (long)(n - 1) * lev;
+  pgfm[x2] = a_pgfm; xip[x2] = a_xip; xim[x2] = a_xim;
+}
+
 // depth-mean removal and normalisation (:543-597); one thread per interior column
 __global__ void pg_finalize(Geom g, int n, int nn, const int* __restrict__ ip, const int* __restrict__ iu,
                             const int* __restrict__ iv, const double* __restrict__ pb_p,
@@ -207,7 +289,8 @@ void pgforc_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   (void)m; (void)mm; (void)k1m; (void)k1n;
   Ctx& c = C(); const Geom& g = c.g;
   const std::string pgfmth = c.option("pgfmth", "dynamic enthalpy");
-  if (pgfmth != "dynamic enthalpy") throw std::runtime_error(" pgfmth = " + pgfmth + " is unsupported!");
+  if (pgfmth != "dynamic enthalpy" && pgfmth != "geopotential")
+    throw std::runtime_error(" pgfmth = " + pgfmth + " is unsupported!");
   {
     dim3 grid(cdiv(g.ii + 5, 128), g.jj + 5);
     LAUNCH(pg_p_from_dp, grid, 128, 0, g, nn, c.idev("ip"), c.dev("dp"), c.dev("p"));
@@ -219,7 +302,18 @@ void pgforc_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
            c.dev("pgfym"), c.dev("xixp_o"), c.dev("xixm_o"), c.dev("pgfxm_o"), c.dev("xiyp_o"), c.dev("xiym_o"),
            c.dev("pgfym_o"));
   }
-  {
+  if (pgfmth == "geopotential") {
+    double* phip = c.owned("pg_phip", g.kdm + 1);   // routine-local phip of the reference (:105)
+    dim3 gridc(cdiv(g.ii + 1, 128), g.jj + 1), gridf(cdiv(g.ii, 128), g.jj);
+    LAUNCH(pg_geop_column, gridc, 128, 0, g, nn, c.idev("ip"), c.dev("p"), c.dev("dp"), c.dev("temp"),
+           c.dev("saln"), c.dev("phi"), phip);
+    LAUNCH(pg_geop_face<0>, gridf, 128, 0, g, n, nn, c.idev("iu"), c.dev("p"), c.dev("pu"), c.dev("dpu"),
+           c.dev("temp"), c.dev("saln"), c.dev("phi"), phip, c.dev("pgfx"), c.dev("pgfx_o"), c.dev("pgfxm"),
+           c.dev("xixp"), c.dev("xixm"));
+    LAUNCH(pg_geop_face<1>, gridf, 128, 0, g, n, nn, c.idev("iv"), c.dev("p"), c.dev("pv"), c.dev("dpv"),
+           c.dev("temp"), c.dev("saln"), c.dev("phi"), phip, c.dev("pgfy"), c.dev("pgfy_o"), c.dev("pgfym"),
+           c.dev("xiyp"), c.dev("xiym"));
+  } else {
     dim3 grid(cdiv(g.ii + 1, TX - 1), cdiv(g.jj + 1, TY - 1)), block(TX, TY);
     LAUNCH(pg_dynh_march, grid, block, 0, g, eos::host_coef(), n, nn, c.idev("ip"), c.idev("iu"), c.idev("iv"),
            c.dev("p"), c.dev("dp"), c.dev("temp"), c.dev("saln"), c.dev("dpu"), c.dev("dpv"), c.dev("phi"),

@@ -1,6 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see core.hpp header).
-// Restatement of phy/mod_pgforc.F90: pgforc :438-615 and
-// pgforc_dynamic_enthalpy :262-408 (pgfmth='dynamic enthalpy').
+// Restatement of phy/mod_pgforc.F90: pgforc :438-615, pgforc_dynamic_enthalpy :262-408
+// (pgfmth='dynamic enthalpy') and pgforc_geopotential :95-260 (pgfmth='geopotential').
 #include "core.hpp"
 #include "eos.hpp"
 
@@ -83,6 +83,96 @@ static void pgforc_dynamic_enthalpy(int m, int n, int mm, int nn, int k1m, int k
   }
 }
 
+// :95-260 (pgfmth='geopotential'): gradient of the geopotential on pressure surfaces.
+static void pgforc_geopotential(int m, int n, int mm, int nn, int k1m, int k1n) {
+  (void)m; (void)mm; (void)k1m; (void)k1n;
+  Oracle& o = O(); const Dims& d = o.d;
+  const int ii = d.ii, jj = d.jj, kk = d.kk;
+  A3 p = o.a3("p"), phi = o.a3("phi"), temp = o.a3("temp"), saln = o.a3("saln"), dp = o.a3("dp");
+  A3 dpu = o.a3("dpu"), dpv = o.a3("dpv"), pu = o.a3("pu"), pv = o.a3("pv"), pgfx = o.a3("pgfx"), pgfy = o.a3("pgfy");
+  A3 pgfxm = o.a3("pgfxm"), pgfym = o.a3("pgfym"), xixp = o.a3("xixp"), xixm = o.a3("xixm"),
+     xiyp = o.a3("xiyp"), xiym = o.a3("xiym");
+  I2 ip = o.i2("ip"), iu = o.i2("iu"), iv = o.i2("iv");
+  A3 phip = o.scratch("_phip", kk + 1);
+  using namespace eos;
+  double dphi, alpl, alpu;
+  for (int j = 0; j <= jj; ++j) {
+    for (int i = 0; i <= ii; ++i) if (ip(i, j) == 1) phip(i, j, kk + 1) = 0.;
+    for (int k = kk; k >= 1; --k) {
+      const int kn = k + nn;
+      for (int i = 0; i <= ii; ++i) if (ip(i, j) == 1) {
+        if (dp(i, j, kn) < epsilp) {
+          phi(i, j, k) = phi(i, j, k + 1);
+          phip(i, j, k) = phip(i, j, k + 1);
+        } else {
+          delphi(p(i, j, k), p(i, j, k + 1), temp(i, j, kn), saln(i, j, kn), dphi, alpu, alpl);
+          phi(i, j, k) = phi(i, j, k + 1) - dphi;
+          phip(i, j, k) = phip(i, j, k + 1) + p(i, j, k + 1) * alpl - p(i, j, k) * alpu;
+        }
+      }
+    }
+  }
+  std::vector<int> kup(ii + 1), kum(ii + 1), kvp(ii + 1), kvm(ii + 1);
+  double prs, dphip, dphim, alplp, alpup, alplm, alpum, cp, cm, phi_p, phi_m, q;
+  for (int j = 1; j <= jj; ++j) {
+    for (int i = 1; i <= ii; ++i) if (iu(i, j) == 1) {
+      kup[i] = kk; kum[i] = kk;
+      xixp(i, j, n) = 0.; xixm(i, j, n) = 0.; pgfxm(i, j, n) = 0.;
+    }
+    for (int i = 1; i <= ii; ++i) if (iv(i, j) == 1) {
+      kvp[i] = kk; kvm[i] = kk;
+      xiyp(i, j, n) = 0.; xiym(i, j, n) = 0.; pgfym(i, j, n) = 0.;
+    }
+    for (int k = kk; k >= 1; --k) {
+      const int kn = k + nn;
+      for (int i = 1; i <= ii; ++i) if (iu(i, j) == 1) {
+        prs = pu(i, j, k + 1) - .5 * dpu(i, j, kn);
+        while (p(i, j, kup[i]) > prs) kup[i] = kup[i] - 1;
+        while (p(i - 1, j, kum[i]) > prs) kum[i] = kum[i] - 1;
+        delphi(prs, p(i, j, kup[i] + 1), temp(i, j, kup[i] + nn), saln(i, j, kup[i] + nn), dphip, alpup, alplp);
+        delphi(prs, p(i - 1, j, kum[i] + 1), temp(i - 1, j, kum[i] + nn), saln(i - 1, j, kum[i] + nn), dphim, alpum,
+               alplm);
+        cp = .25 * (p(i, j, k + 1) + p(i, j, k));
+        cm = .25 * (p(i - 1, j, k + 1) + p(i - 1, j, k));
+        q = prs / (cp + cm);
+        cp = q * cp;
+        cm = q * cm;
+        phi_p = phi(i, j, kup[i] + 1) - dphip;
+        xixp(i, j, n) = xixp(i, j, n) +
+                        (phip(i, j, kup[i] + 1) + p(i, j, kup[i] + 1) * alplp - cp * (alpup - alpum)) * dpu(i, j, kn);
+        phi_m = phi(i - 1, j, kum[i] + 1) - dphim;
+        xixm(i, j, n) = xixm(i, j, n) +
+                        (phip(i - 1, j, kum[i] + 1) + p(i - 1, j, kum[i] + 1) * alplm - cm * (alpum - alpup)) *
+                            dpu(i, j, kn);
+        pgfx(i, j, kn) = -(phi_p - phi_m);
+        pgfxm(i, j, n) = pgfxm(i, j, n) + pgfx(i, j, kn) * dpu(i, j, kn);
+      }
+      for (int i = 1; i <= ii; ++i) if (iv(i, j) == 1) {
+        prs = pv(i, j, k + 1) - .5 * dpv(i, j, kn);
+        while (p(i, j, kvp[i]) > prs) kvp[i] = kvp[i] - 1;
+        while (p(i, j - 1, kvm[i]) > prs) kvm[i] = kvm[i] - 1;
+        delphi(prs, p(i, j, kvp[i] + 1), temp(i, j, kvp[i] + nn), saln(i, j, kvp[i] + nn), dphip, alpup, alplp);
+        delphi(prs, p(i, j - 1, kvm[i] + 1), temp(i, j - 1, kvm[i] + nn), saln(i, j - 1, kvm[i] + nn), dphim, alpum,
+               alplm);
+        cp = .25 * (p(i, j, k + 1) + p(i, j, k));
+        cm = .25 * (p(i, j - 1, k + 1) + p(i, j - 1, k));
+        q = prs / (cp + cm);
+        cp = q * cp;
+        cm = q * cm;
+        phi_p = phi(i, j, kvp[i] + 1) - dphip;
+        xiyp(i, j, n) = xiyp(i, j, n) +
+                        (phip(i, j, kvp[i] + 1) + p(i, j, kvp[i] + 1) * alplp - cp * (alpup - alpum)) * dpv(i, j, kn);
+        phi_m = phi(i, j - 1, kvm[i] + 1) - dphim;
+        xiym(i, j, n) = xiym(i, j, n) +
+                        (phip(i, j - 1, kvm[i] + 1) + p(i, j - 1, kvm[i] + 1) * alplm - cm * (alpum - alpup)) *
+                            dpv(i, j, kn);
+        pgfy(i, j, kn) = -(phi_p - phi_m);
+        pgfym(i, j, n) = pgfym(i, j, n) + pgfy(i, j, kn) * dpv(i, j, kn);
+      }
+    }
+  }
+}
+
 // :438-615
 void pgforc(int m, int n, int mm, int nn, int k1m, int k1n) {
   Oracle& o = O(); const Dims& d = o.d;
@@ -132,7 +222,8 @@ void pgforc(int m, int n, int mm, int nn, int k1m, int k1n) {
       for (int i = 1; i <= ii; ++i) if (iv(i, j) == 1) pgfy_o(i, j, k) = pgfy(i, j, kn);
     }
   const std::string pgfmth = o.option("pgfmth", "dynamic enthalpy");
-  if (pgfmth == "dynamic enthalpy") pgforc_dynamic_enthalpy(m, n, mm, nn, k1m, k1n);
+  if (pgfmth == "geopotential") pgforc_geopotential(m, n, mm, nn, k1m, k1n);
+  else if (pgfmth == "dynamic enthalpy") pgforc_dynamic_enthalpy(m, n, mm, nn, k1m, k1n);
   else throw std::runtime_error(" pgfmth = " + pgfmth + " is unsupported!");
 
   xctilr(pb_p, 1, 1, halo_ps);

@@ -70,10 +70,11 @@ def test_tmsmt(cfg, vcoord):
         g.finalize()
 
 
+@pytest.mark.parametrize("pgfmth", ["dynamic enthalpy", "geopotential"])  # phy/mod_pgforc.F90:524-534
 @pytest.mark.parametrize("cfg", ["tiny0", "tiny1", "tiny2", "tiny3", "tiny4"])
 @pytest.mark.parametrize("parity", [True, False])
-def test_pgforc(cfg, parity):
-    c, o, g = pair(cfg, parity=parity)
+def test_pgforc(cfg, parity, pgfmth):
+    c, o, g = pair(cfg, parity=parity, opts={"pgfmth": pgfmth})
     try:
         o.pgforc(*c.levels); g.pgforc(*c.levels)
         tol = 1e-12 if parity else 1e-10

@@ -119,9 +119,35 @@ def test_tmsmt(cfg):
                        rtol=1e-13)
 
 
+def test_pgforc_methods_agree_on_homogeneous_fluid():
+    """Analytic pin shared by both PGF methods (phy/mod_pgforc.F90:95-260 and :262-408): with uniform
+    T and S the geopotential is a function of pressure up to a column constant, so the baroclinic PGF
+    vanishes after the depth mean is removed, and the barotropic PGF and its bottom-pressure
+    sensitivities are the same numbers for the two discretisations."""
+    out = {}
+    for meth in ("geopotential", "dynamic enthalpy"):
+        c = Case("tiny2")
+        c.state["temp"][:] = 4.0; c.state["saln"][:] = 35.0
+        o = c.new_oracle(); o.inieos(); o.set_option("pgfmth", meth)
+        o.pgforc(*c.levels)
+        kk = c.dims[2]; n, nn = c.levels[1], c.levels[3]
+        iu = interior(c.masks["iu"]) == 1; iv = interior(c.masks["iv"]) == 1
+        a = o.arrays
+        out[meth] = [interior(a[nm][n - 1])[msk] for nm, msk in
+                     (("pgfxm", iu), ("xixp", iu), ("xixm", iu), ("pgfym", iv), ("xiyp", iv), ("xiym", iv))]
+        scale = np.abs(out[meth][0]).max()
+        assert scale > 1.0
+        assert np.abs(interior(a["pgfx"][nn:nn + kk])[:, iu]).max() <= 1e-14 * scale
+        assert np.abs(interior(a["pgfy"][nn:nn + kk])[:, iv]).max() <= 1e-14 * scale
+    for x, y in zip(out["geopotential"], out["dynamic enthalpy"]):
+        assert np.abs(x - y).max() <= 1e-13 * np.abs(y).max()
+
+
+@pytest.mark.parametrize("pgfmth", ["dynamic enthalpy", "geopotential"])
 @pytest.mark.parametrize("cfg", ["tiny1", "tiny2", "tiny4"])
-def test_pgforc_basic(cfg):
+def test_pgforc_basic(cfg, pgfmth):
     c, o = prep(cfg)
+    o.set_option("pgfmth", pgfmth)
     kk = c.dims[2]; m, n, mm, nn, k1m, k1n = c.levels
     a = o.arrays
     old_pgfx = a["pgfx"].copy()
