@@ -192,6 +192,7 @@ void bigrid_dev(const std::string& depth);
 // ---- routines ---------------------------------------------------------------
 void init_cppm_dev();
 void advect_dev(int m, int n, int mm, int nn, int k1m, int k1n);
+void advect_remap_dev(int m, int n, int mm, int nn, int k1m, int k1n);  // remap.cu
 void diffus_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void tmsmt1_dev(int nn);
 void tmsmt2_dev(int m, int mm, int nn, int k1m);

@@ -1100,17 +1100,20 @@ void init_cppm_dev() {
 
 // advect (mod_advect.F90:59-189), advmth='cppm'
 void advect_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
-  (void)k1m; (void)k1n;
   Ctx& c = C(); const Geom& g = c.g;
   const std::string advmth = c.option("advmth", "cppm");
-  if (advmth != "cppm") throw std::runtime_error(" advmth = " + advmth + " is unsupported!");
-  if (!c.has("cppm_tab_i")) throw std::runtime_error("advect: init_cppm has not been called");
+  if (advmth != "cppm" && advmth != "remap") throw std::runtime_error(" advmth = " + advmth + " is unsupported!");
+  if (advmth == "cppm" && !c.has("cppm_tab_i")) throw std::runtime_error("advect: init_cppm has not been called");
   dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
   LAUNCH(advect_flux_area, grid, 128, 0, g, m, mm, nn, c.scalar("delt1"), c.scalar("dlt"), c.idev("iu"),
          c.idev("iv"), c.dev("u"), c.dev("v"), c.dev("dpu"), c.dev("dpv"), c.dev("ubflxs_p"),
          c.dev("vbflxs_p"), c.dev("pbu"), c.dev("pbv"), c.dev("umfltd"), c.dev("vmfltd"),
          c.dev("umflsm"), c.dev("vmflsm"), c.dev("scuy"), c.dev("scvx"), c.dev("umax"), c.dev("vmax"),
          c.dev("cau"), c.dev("cav"));
+  if (advmth == "remap") {   // mod_advect.F90:96-153 (no trailing halo update in this branch)
+    advect_remap_dev(m, n, mm, nn, k1m, k1n);
+    return;
+  }
   switch (2 + g.ntr) {
     case 2: cppm_run<2>(n, mm, nn); break;
     case 3: cppm_run<3>(n, mm, nn); break;

@@ -6,6 +6,8 @@
 
 namespace orc {
 
+void advect_remap(int m, int n, int mm, int nn, int k1m, int k1n);  // remap.cpp
+
 namespace {
 
 // stencil tags, phy/mod_cppm.F90:60-68
@@ -1153,8 +1155,9 @@ void advect(int m, int n, int mm, int nn, int k1m, int k1n) {
         }
       }
     }
-  if (o.option("advmth", "cppm") != "cppm")
-    throw std::runtime_error(" advmth = " + o.option("advmth", "") + " is unsupported!");
+  const std::string advmth = o.option("advmth", "cppm");
+  if (advmth == "remap") { advect_remap(m, n, mm, nn, k1m, k1n); return; }  // :96-153 (no trailing halo update)
+  if (advmth != "cppm") throw std::runtime_error(" advmth = " + advmth + " is unsupported!");
   cppm(m, n, mm, nn, k1m, k1n);
   xctilr(o.a3("dp").from(k1n), 1, kk, 1, 1, halo_ps);
   xctilr(o.a3("temp").from(k1n), 1, kk, 1, 1, halo_ps);
