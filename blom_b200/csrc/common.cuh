@@ -201,6 +201,7 @@ void pgforc_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void momtum_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void eddtra_dev(int m, int n, int mm, int nn, int k1m, int k1n);
+void eddtra_isopyc_dev(int m, int n, int mm, int nn, int k1m, int k1n);  // eddtra_isopyc.cu
 void pbcor1_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void pbcor2_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void numerical_bounds_dev();

@@ -1,4 +1,5 @@
-// Eddy-induced transport for the hybrid coordinate: eddtra -> eddtra_ale
+// Eddy-induced transport for the hybrid coordinate (the isopycnic variants live in
+// eddtra_isopyc.cu): eddtra -> eddtra_ale
 // (phy/mod_eddtra.F90:1808-1928, :1001-1739; rmeanfilt :121-151), eitmth='gm',
 // mlrmth none|fox08|bod23.
 //
@@ -283,10 +284,11 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
 }  // namespace
 
 void eddtra_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
-  (void)m; (void)k1m; (void)k1n;
   Ctx& c = C(); const Geom& g = c.g;
-  if (c.option("vcoord", "cntiso_hybrid") == "isopyc_bulkml")
-    throw std::runtime_error("(eddtra) vcoord = 'isopyc_bulkml' is not implemented in this build");
+  if (c.option("vcoord", "cntiso_hybrid") == "isopyc_bulkml") {   // :1818-1857, eddtra_isopyc.cu
+    eddtra_isopyc_dev(m, n, mm, nn, k1m, k1n);
+    return;
+  }
   if (c.option("eitmth", "gm") != "gm")
     throw std::runtime_error("(eddtra) eitmth_opt is unsupported for vcoord = 'cntiso_hybrid'!");
   if (g.kdm > KM) throw std::runtime_error("eddtra: kdm exceeds the compiled column bound (64)");

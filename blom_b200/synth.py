@@ -119,6 +119,23 @@ class Synth:
             x = _mix(x + k[:, None, None] * np.uint64(0x8CB92BA72F3D8DD7))
         return (x >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
 
+    def _hash_uniform_padded(self, nlev, fid):
+        """U[0,1) on the whole padded band (nlev, ldj, ldi): the interior hash evaluated at global
+        indices wrapped periodically, so halo points equal the interior points they image wherever
+        the domain is periodic and every j-band sees its neighbours' values."""
+        nb = self.nb
+        jg = ((np.arange(self.ldj, dtype=np.int64) - nb + self.j0) % self.jtdm).astype(np.uint64)
+        ig = ((np.arange(self.ldi, dtype=np.int64) - nb) % self.itdm).astype(np.uint64)
+        k = np.arange(nlev, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            key = (np.uint64(self.seed) * np.uint64(0x9E3779B97F4A7C15)
+                   + np.uint64(fid) * np.uint64(0xD1B54A32D192ED03))
+            x = (key + jg[None, :, None] * np.uint64(0xA24BAED4963EE407)
+                 + ig[None, None, :] * np.uint64(0x9FB21C651E98DF25))
+            x = _mix(x)
+            x = _mix(x + k[:, None, None] * np.uint64(0x8CB92BA72F3D8DD7))
+        return (x >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+
     def _base(self, kind):
         """Base noise cubes (kdm levels), hashed once; every field is a cheap re-indexing
         of one of them (still a pure function of global indices)."""
@@ -417,6 +434,12 @@ class Synth:
         self.interior(st["dpvold"])[:] = 0.5 * (dpn + np.roll(dpn, -1, axis=2)) * ivm
         st["utotn"] = self._put(self.zeros(1), 1.0e-6 * self._normal(1) * ium)
         st["vtotn"] = self._put(self.zeros(1), 1.0e-6 * self._normal(1) * ivm)
+        # --- isopycnic bulk-mixed-layer coordinate: index of the first physical layer below the mixed
+        # layer (phy/mod_state.F90 kfpla, 2 time levels), 3..kk+1 (kk+1: mixed layer reaches the bottom).
+        # Integer fields cannot go through the r8 xctilr, so the halo is generated directly: the hash
+        # is keyed on wrapped global indices (rings outside a closed edge are land and never read).
+        u = self._hash_uniform_padded(2, 9001)
+        st["kfpla"] = np.minimum(kk + 1, 3 + np.floor(np.minimum(1.0, 1.2 * u) * (kk - 2))).astype(np.int32)
         return st
 
     def scalars(self, nstep=1):
@@ -430,6 +453,27 @@ class Synth:
                 # biharmonic terms switched on so that every branch of momtum is exercised)
                 "mdv2hi": 0.1, "mdv2lo": 0.05, "mdv4hi": 0.01, "mdv4lo": 0.005, "vsc2hi": 0.2, "vsc2lo": 0.15,
                 "vsc4hi": 0.06, "vsc4lo": 0.05, "cbar": 0.05, "cb": 0.002}
+
+
+def make_isopycnic(st):
+    """Make a synthetic state consistent with vcoord='isopyc_bulkml' (what the reference's bulk mixed
+    layer scheme guarantees before eddtra runs): layers 1-2 are the mixed layer, interior layers
+    3..kfpla-1 are massless, layer kfpla holds mass, and kfpla = kk+1 where no interior layer does.
+    The mass taken out of the emptied layers goes to layer 2, so the bottom pressure is unchanged.
+    Works on whole arrays (halo included); both time levels get the same treatment."""
+    kk = st["dp"].shape[0] // 2
+    kf = st["kfpla"]
+    dp = st["dp"]
+    kidx = np.arange(1, kk + 1)[:, None, None]
+    for lvl in range(2):
+        d = dp[lvl * kk:(lvl + 1) * kk]
+        k0 = kf[lvl][None].astype(np.int64)
+        has = np.take_along_axis(d, np.minimum(k0, kk) - 1, axis=0)[0] > 1.0e-6
+        kf[lvl][...] = np.where(has & (kf[lvl] <= kk), kf[lvl], kk + 1)
+        empty = (kidx >= 3) & (kidx < kf[lvl][None])
+        moved = np.where(empty, d, 0.0).sum(axis=0)
+        d[empty] = 0.0
+        d[1] += moved
 
 
 def fill_halos(backend, arrays: dict, nbdy=4, names=None):

@@ -190,6 +190,30 @@ def test_eddtra(cfg, mlrmth, slope, parity):
         g.finalize()
 
 
+@pytest.mark.parametrize("cfg,eitmth,slope,parity", [
+    ("tiny0", "gm", 1.0, True), ("tiny1", "gm", 3.0e3, True), ("tiny2", "gm", 1.0, True), ("tiny3", "gm", 3.0e3, True),
+    ("tiny4", "gm", 1.0, True), ("fuk95", "gm", 1.0e3, True), ("fuk95", "gm", 1.0, False),
+    ("tiny1", "intdif", 1.0, True), ("tiny2", "intdif", 1.0, True), ("fuk95", "intdif", 1.0, True),
+    ("fuk95", "intdif", 1.0, False)])
+def test_eddtra_isopycnic(cfg, eitmth, slope, parity):
+    """vcoord='isopyc_bulkml': eddtra_gm_isopyc_bulkml / eddtra_intdif_isopyc_bulkml + the heat/salt
+    diagnosis (phy/mod_eddtra.F90:153-999, :1818-1857) on a state with a consistent kfpla.  Tolerance
+    1e-13 of the field max-norm (parity build), 1e-10 (FMA build); steep slopes exercise the limiter."""
+    c = Case(cfg, ntr=0, isopycnic=True)
+    c.state["nslpx"] *= slope; c.state["nslpy"] *= slope
+    o = c.new_oracle(); g = c.new_gpu(parity=parity)
+    try:
+        for b in (o, g):
+            b.set_option("vcoord", "isopyc_bulkml"); b.set_option("eitmth", eitmth); b.inieos()
+        o.eddtra(*c.levels); g.eddtra(*c.levels)
+        g.sync()
+        check(g, o, ["umfltd", "vmfltd", "utfltd", "vtfltd", "usfltd", "vsfltd"], 1e-13 if parity else 1e-10)
+        kk = c.dims[2]; mm = c.levels[2]
+        assert np.abs(interior(g.arrays["umfltd"][mm:mm + kk])).max() > 0.0
+    finally:
+        g.finalize()
+
+
 def test_eddtra_bad_option():
     from blom_b200.lib import BlomGpuError
     c, o, g = pair("tiny0", ntr=0)
@@ -198,7 +222,10 @@ def test_eddtra_bad_option():
         with pytest.raises(BlomGpuError, match="mlrmth = bogus is unsupported"):
             g.eddtra(*c.levels)
         g.set_option("mlrmth", "fox08"); g.set_option("eitmth", "intdif")
-        with pytest.raises(BlomGpuError, match="eitmth_opt is unsupported"):
+        with pytest.raises(BlomGpuError, match="eitmth_opt is unsupported for vcoord = 'cntiso_hybrid'"):
+            g.eddtra(*c.levels)
+        g.set_option("vcoord", "isopyc_bulkml"); g.set_option("eitmth", "bogus")
+        with pytest.raises(BlomGpuError, match="eitmth_opt is unsupported for vcoord = 'isopyc_bulkml'"):
             g.eddtra(*c.levels)
     finally:
         g.finalize()

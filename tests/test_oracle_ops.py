@@ -293,3 +293,39 @@ def test_pbcor_bad_option():
     o.set_option("bmcmth", "bogus")
     with pytest.raises(OracleError, match="bmcmth = bogus is unsupported"):
         o.pbcor1(*c.levels)
+
+
+# ---- isopycnic eddy-induced transport (phy/mod_eddtra.F90:153-999) ---------------------------
+@pytest.mark.parametrize("cfg", ["tiny1", "tiny2", "fuk95"])
+@pytest.mark.parametrize("eitmth", ["gm", "intdif"])
+def test_eddtra_isopycnic_properties(cfg, eitmth):
+    """Contracts of eddtra_gm_isopyc_bulkml / eddtra_intdif_isopyc_bulkml that pin the restatement:
+    interface fluxes vanish at the surface and at the bottom, so every face column of layer fluxes
+    sums to zero; empty layers 3..kfpla-1 carry no flux; the GM fluxes respect the 1/16 depletion
+    bound the routine enforces; heat/salt components are the mass flux times the face-mean T/S."""
+    c = Case(cfg, ntr=0, isopycnic=True)
+    o = c.new_oracle(); o.inieos()
+    o.set_option("vcoord", "isopyc_bulkml"); o.set_option("eitmth", eitmth)
+    o.eddtra(*c.levels)
+    m, n, mm, nn, k1m, k1n = c.levels
+    kk = c.dims[2]
+    a = o.arrays
+    for f, t, s_, msk, sh in (("umfltd", "utfltd", "usfltd", "iu", (0, 1)), ("vmfltd", "vtfltd", "vsfltd", "iv", (1, 0))):
+        w = interior(c.masks[msk]) == 1
+        fl = interior(a[f][mm:mm + kk])
+        assert np.abs(fl[:, w]).max() > 0.0
+        scale = np.abs(fl).max()
+        assert np.abs(fl.sum(axis=0)[w]).max() <= 1e-12 * scale
+        tm = interior(a["temp"][mm:mm + kk]); tmm = interior(np.roll(a["temp"][mm:mm + kk], sh, axis=(1, 2)))
+        assert np.allclose(interior(a[t][mm:mm + kk])[:, w], (.5 * fl * (tmm + tm))[:, w], rtol=1e-14, atol=0)
+        if eitmth == "gm":
+            dpn = a["dp"][nn:nn + kk]; scp2 = a["scp2"][0]
+            mass_p = interior(dpn * scp2); mass_m = interior(np.roll(dpn * scp2, sh, axis=(1, 2)))
+            # layers 3..kk: a positive flux depletes the minus cell, a negative one the plus cell
+            assert (fl[2:][:, w] <= .0625 * np.maximum(1e-12 * interior(scp2), mass_m[2:])[:, w] * (1 + 1e-12)).all()
+            assert (-fl[2:][:, w] <= .0625 * np.maximum(1e-12 * interior(scp2), mass_p[2:])[:, w] * (1 + 1e-12)).all()
+            kf = np.maximum(interior(a["kfpla"][n - 1]), interior(np.roll(a["kfpla"][n - 1], sh, axis=(0, 1))))
+            kidx = np.arange(1, kk + 1)[:, None, None]
+            empty = (kidx >= 3) & (kidx < np.minimum(interior(a["kfpla"][n - 1]),
+                                                     interior(np.roll(a["kfpla"][n - 1], sh, axis=(0, 1)))) - 1)
+            assert np.abs(fl[empty & w[None]]).max(initial=0.0) == 0.0

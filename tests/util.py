@@ -19,7 +19,8 @@ from oracle.oracle import Oracle  # noqa: E402
 class Case:
     """Synthetic case prepared with the oracle's xctilr/bigrid (CPU)."""
 
-    def __init__(self, config="tiny2", ntr=0, nstep=1, land=True, metric="tripolar", seed=20240611):
+    def __init__(self, config="tiny2", ntr=0, nstep=1, land=True, metric="tripolar", seed=20240611,
+                 isopycnic=False):
         itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS[config]
         self.config = config
         self.dims = (itdm, jtdm, kdm, nreg)
@@ -32,6 +33,8 @@ class Case:
         self.levels = time_levels(nstep, kdm)
         prep = self.new_oracle(setup=False)
         synth.fill_halos(prep, {**self.grid, **self.state})
+        if isopycnic:  # vcoord='isopyc_bulkml': empty layers 3..kfpla-1, consistent kfpla (needs valid dp halos)
+            synth.make_isopycnic(self.state)
         prep.bigrid("depths")
         self.nreg = prep.nreg
         self.masks = {k: prep.get_int(k).reshape(self.syn.ldj, self.syn.ldi).copy() for k in ("ip", "iu", "iv", "iq")}
