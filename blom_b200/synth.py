@@ -476,6 +476,63 @@ def make_isopycnic(st):
         d[1] += moved
 
 
+def ndiff_inputs(syn, st, levels, ntr=0):
+    """Synthetic products of the ALE regrid-remap pipeline that neutral diffusion consumes
+    (phy/mod_ale_regrid_remap.F90:1614-1690 -> phy/mod_ndiff.F90): source interfaces and the deepest
+    source layer with mass, a monotone-limited parabolic (+ zero-mean quartic) reconstruction of every
+    scalar in every source layer with its interface values, regridded destination interfaces (some
+    within the 1 % snapping distance of their source interface, some not), the remapped tracers and
+    the mixed-layer pressure thickness.  Built level-wise from halo-valid dp/T/S/trc on the whole padded
+    arrays, so halos stay consistent without integer halo exchanges.  Layouts: see oracle/ndiff.cpp."""
+    m, n, mm, nn, k1m, k1n = levels
+    kk = st["dp"].shape[0] // 2
+    T = 2 + ntr
+    dp = st["dp"][nn:nn + kk]
+    out = {}
+    p_src = np.zeros((kk + 1,) + dp.shape[1:])
+    p_src[1:] = np.cumsum(dp, axis=0)
+    out["nd_p_src"] = p_src
+    has = dp > 1.0e-6
+    kidx = np.arange(1, kk + 1)[:, None, None]
+    out["nd_ksmx"] = np.maximum(1, np.where(has, kidx, 0).max(axis=0)).astype(np.int32)[None]
+    u = syn._hash_uniform_padded(kk + 1, 9101)
+    p_dst = p_src.copy()
+    dmin = np.minimum(dp[:-1], dp[1:])
+    # a third of the interfaces stay within the snapping distance (1 % of the thinner neighbour)
+    shift = np.where(u[1:kk] < 0.33, 0.004, 0.6) * dmin * (u[1:kk] - 0.5)
+    p_dst[1:kk] = p_src[1:kk] + shift
+    out["nd_p_dst"] = p_dst
+    scal = [st["temp"][nn:nn + kk], st["saln"][nn:nn + kk]]
+    for nt in range(ntr):
+        scal.append(st["trc"][nt * 2 * kk + nn:nt * 2 * kk + nn + kk])
+    tsd = np.zeros((2 * kk * T,) + dp.shape[1:])
+    tpc = np.zeros((5 * kk * T,) + dp.shape[1:])
+    trm = np.zeros((kk * T,) + dp.shape[1:])
+    w = syn._hash_uniform_padded(kk, 9102) - 0.5
+    for nt, f in enumerate(scal):
+        edge = np.zeros((kk + 1,) + dp.shape[1:])
+        edge[1:kk] = 0.5 * (f[:-1] + f[1:])
+        edge[0], edge[kk] = f[0], f[kk - 1]
+        tl, tr = edge[:-1].copy(), edge[1:].copy()
+        flat = (tr - f) * (f - tl) <= 0.0
+        tl[flat] = f[flat]; tr[flat] = f[flat]
+        c = 0.05 * w * np.abs(tr - tl)                  # zero-mean quartic c*(x^2(1-x)^2 - 1/30)
+        a0 = tl - c / 30.0
+        a1 = 6.0 * f - 4.0 * tl - 2.0 * tr
+        a2 = 3.0 * (tl - 2.0 * f + tr) + c
+        a3 = -2.0 * c
+        a4 = c
+        for k in range(kk):
+            b = (nt * kk + k) * 5
+            tpc[b + 0], tpc[b + 1], tpc[b + 2], tpc[b + 3], tpc[b + 4] = a0[k], a1[k], a2[k], a3[k], a4[k]
+            tsd[(nt * kk + k) * 2 + 0] = a0[k]
+            tsd[(nt * kk + k) * 2 + 1] = (((a4[k] + a3[k]) + a2[k]) + a1[k]) + a0[k]
+        trm[nt * kk:(nt + 1) * kk] = f
+    out["nd_t_srcdi"], out["nd_tpc_src"], out["nd_trc_rm"] = tsd, tpc, trm
+    out["dpml"] = ((10.0 + 90.0 * syn._hash_uniform_padded(1, 9103)) * ONEM)
+    return {k: np.ascontiguousarray(v) for k, v in out.items()}
+
+
 def fill_halos(backend, arrays: dict, nbdy=4, names=None):
     """xctilr(nbdy,nbdy) of every registered array with its grid type.  `backend` is a
     BlomGpu (product) or the test Oracle; arrays must already be registered."""

@@ -23,6 +23,7 @@ void numerical_bounds();
 void pbcor1(int, int, int, int, int, int);
 void pbcor2(int, int, int, int, int, int);
 void init_fluxes(int, int, int, int, int, int);
+void ndiff(int, int, int, int, int, int);
 }
 
 static char g_err[1024] = "";
@@ -128,6 +129,7 @@ int oracle_pbcor2(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::p
 int oracle_momtum(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::momtum(m, n, mm, nn, k1m, k1n)) }
 int oracle_numerical_bounds() { GUARD(orc::numerical_bounds()) }
 int oracle_init_fluxes(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::init_fluxes(m, n, mm, nn, k1m, k1n)) }
+int oracle_ndiff(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::ndiff(m, n, mm, nn, k1m, k1n)) }
 double oracle_get_scalar(const char* k) { return orc::O().scalar(k, 0.0); }
 
 // scalar access to the EOS restatement for the unit checks in tests/test_oracle_ops.py

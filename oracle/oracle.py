@@ -181,3 +181,4 @@ class Oracle:
     def momtum(self, *a): self._call("momtum", *a)
     def barotp(self, *a): self._call("barotp", *a)
     def pbcor2(self, *a): self._call("pbcor2", *a)
+    def ndiff(self, *a): self._call("ndiff", *a)
