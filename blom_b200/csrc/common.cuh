@@ -206,5 +206,6 @@ void pbcor1_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void pbcor2_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void numerical_bounds_dev();
 void init_fluxes_dev(int m, int n, int mm, int nn, int k1m, int k1n);
+void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n);  // ndiff.cu
 
 }  // namespace blom

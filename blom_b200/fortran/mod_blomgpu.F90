@@ -144,11 +144,12 @@ module mod_blomgpu
    procedure(six_int_entry), bind(C, name='blomgpu_momtum') :: blomgpu_momtum
    procedure(six_int_entry), bind(C, name='blomgpu_barotp') :: blomgpu_barotp
    procedure(six_int_entry), bind(C, name='blomgpu_pbcor2') :: blomgpu_pbcor2
+   procedure(six_int_entry), bind(C, name='blomgpu_ndiff') :: blomgpu_ndiff
 
    public :: gpu_setup, gpu_register, gpu_register_int, gpu_upload, gpu_download, &
              gpu_option, gpu_scalar, gpu_xctilr, &
              init_fluxes, tmsmt1, eddtra, advect, pbcor1, diffus, pgforc, momtum, &
-             barotp, pbcor2, tmsmt2
+             barotp, pbcor2, tmsmt2, ndiff
 
 contains
 
@@ -264,6 +265,13 @@ contains
    subroutine tmsmt2(m, mm, nn, k1m)                ! phy/mod_tmsmt.F90:281
       integer, intent(in) :: m, mm, nn, k1m
       call check(blomgpu_tmsmt2(m, mm, nn, k1m), 'tmsmt2')
+   end subroutine
+   ! neutral diffusion over the whole tile: replaces the ndiff_*_jslice calls of the slice pipeline
+   ! (phy/mod_ale_regrid_remap.F90:1607-1690, phy/mod_ndiff.F90:959-1175); its slice products are
+   ! registered as whole-domain arrays nd_* (include/blomgpu.h)
+   subroutine ndiff(m, n, mm, nn, k1m, k1n)
+      integer, intent(in) :: m, n, mm, nn, k1m, k1n
+      call check(blomgpu_ndiff(m, n, mm, nn, k1m, k1n), 'ndiff')
    end subroutine
 
 end module mod_blomgpu

@@ -34,6 +34,7 @@ ABI_SYMBOLS = [
     "blomgpu_numerical_bounds", "blomgpu_init_fluxes",
     "blomgpu_tmsmt1", "blomgpu_eddtra", "blomgpu_advect", "blomgpu_pbcor1", "blomgpu_diffus",
     "blomgpu_pgforc", "blomgpu_momtum", "blomgpu_barotp", "blomgpu_pbcor2", "blomgpu_tmsmt2",
+    "blomgpu_ndiff",
     "blomgpu_launch_count", "blomgpu_launch_count_reset", "blomgpu_timers_enable",
     "blomgpu_timers_get", "blomgpu_timers_reset", "blomgpu_stream",
     "blomgpu_ktimers_enable", "blomgpu_ktimers_get",
@@ -235,6 +236,9 @@ class BlomGpu:
 
     def pbcor2(self, *a):
         self._six(self.lib.blomgpu_pbcor2, *a)
+
+    def ndiff(self, *a):
+        self._six(self.lib.blomgpu_ndiff, *a)
 
     # -- instrumentation -----------------------------------------------------------
     def launch_count(self):

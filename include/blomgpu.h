@@ -101,6 +101,19 @@ int blomgpu_momtum(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_
 int blomgpu_barotp(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_barotp.F90:148 */
 int blomgpu_pbcor2(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_pbcor.F90:416 */
 int blomgpu_tmsmt2(int m, int mm, int nn, int k1m);           /* phy/mod_tmsmt.F90:281 */
+/* Neutral diffusion (ltedtp='neutral'): ndiff_prep_jslice, ndiff_uflx_jslice, ndiff_vflx_jslice and
+ * ndiff_update_trc_jslice (phy/mod_ndiff.F90:959-1175) over the whole tile, in the order of the slice
+ * pipeline that calls them (phy/mod_ale_regrid_remap.F90:1607-1690).  Neutral diffusion inputs are that
+ * pipeline's products, registered as whole-domain arrays in the common (i,j,level) layout, T = 2+ntr:
+ *   nd_p_src   (kdm+1)    p_src_js(k,i,js)          source interface pressures
+ *   nd_ksmx    int (1)    ksmx_js(i,js)             deepest source layer with mass
+ *   nd_t_srcdi (2*kdm*T)  t_srcdi_js(is,k,nt,i,js)  level ((nt-1)*kdm+k-1)*2+is
+ *   nd_tpc_src (5*kdm*T)  tpc_src_js(c,k,nt,i,js)   level ((nt-1)*kdm+k-1)*5+c
+ *   nd_p_dst   (kdm+1)    p_dst_js(k,i,js)          destination interface pressures
+ *   nd_trc_rm  (kdm*T)    trc_rm(k,nt,i)            level (nt-1)*kdm+k, updated in place
+ *   dpml       (1)        mixed-layer pressure thickness (option ndiff_surface_align, default '1')
+ * plus temp, saln, trc, difiso, pu, pv; updates u|v t|s flld, u|v t|s flx (level k+mm), nslpx, nslpy. */
+int blomgpu_ndiff(int m, int n, int mm, int nn, int k1m, int k1n);
 
 /* ---- instrumentation ---------------------------------------------------- */
 /* kernels launched by this library since the last reset */
