@@ -207,5 +207,7 @@ void pbcor2_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void numerical_bounds_dev();
 void init_fluxes_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n);  // ndiff.cu
+double budget_init_dev();                                       // setup_ops.cu
+void budget_sums_dev(int ncall, int n, int nn, double* out);
 
 }  // namespace blom

@@ -262,6 +262,8 @@ int blomgpu_momtum(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(Scope
 int blomgpu_barotp(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("barotp"); barotp_dev(m, n, mm, nn, k1m, k1n)) }
 int blomgpu_pbcor2(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("pbcor2"); pbcor2_dev(m, n, mm, nn, k1m, k1n)) }
 int blomgpu_ndiff(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("ndiff"); ndiff_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_budget_init(double* mass0) { GUARD(*mass0 = budget_init_dev()) }
+int blomgpu_budget_sums(int ncall, int n, int nn, double out[4]) { GUARD(budget_sums_dev(ncall, n, nn, out)) }
 int blomgpu_tmsmt2(int m, int mm, int nn, int k1m) { GUARD(ScopedTimer t("tmsmt2"); tmsmt2_dev(m, mm, nn, k1m)) }
 
 long blomgpu_launch_count(void) { return C().launches; }

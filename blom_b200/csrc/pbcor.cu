@@ -216,7 +216,9 @@ __global__ void pbcor_finish(Geom g, int ks, const int* __restrict__ ip, const d
     if (WHICH == 2) { pk = pk + d; p[x + (long)k * lev] = pk; }
     temp[x + ol] = tB[x + ok];
     saln[x + ol] = sB[x + ok];
-    for (int nt = 0; nt < T.n; ++nt) T.t[nt][x + ol] = T.tb[nt][x + ok];
+#pragma unroll
+    for (int nt = 0; nt < MAXTR; ++nt)   // static index: the pointer table stays in the constant bank
+      if (nt < T.n) T.t[nt][x + ol] = T.tb[nt][x + ok];
   }
 }
 

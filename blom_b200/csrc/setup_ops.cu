@@ -1,5 +1,6 @@
 // numerical_bounds (phy/mod_blom_init.F90:446-555) and init_fluxes
-// (phy/mod_state.F90:341-383): setup / per-step zero-fill kernels.
+// (phy/mod_state.F90:341-383): setup / per-step zero-fill kernels; budget_init / budget_sums
+// (phy/mod_budget.F90:74-196): thickness-weighted column sums feeding the strip-ordered xcsum.
 #include "common.cuh"
 
 namespace blom {
@@ -44,7 +45,65 @@ __global__ void zero_fluxes(Geom g, int mm, const int* __restrict__ iu, const in
   if (iv[x] == 1) { vflx[xm] = 0.; vtflx[xm] = 0.; vsflx[xm] = 0.; }
 }
 
+// column sums in k order (phy/mod_budget.F90:121-139,161-172): util1 = sum_k a(kn)*dp(kn)*scp2 (+ util2 for b)
+__global__ void budget_columns(Geom g, int nn, const int* __restrict__ ip, const double* __restrict__ dp,
+                               const double* __restrict__ scp2, const double* __restrict__ a,
+                               const double* __restrict__ b, double* __restrict__ util1, double* __restrict__ util2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j);
+  if (ip[x] != 1) return;
+  const double area = scp2[x];
+  double s1 = 0., s2 = 0.;
+  for (int k = 1; k <= g.kdm; ++k) {
+    const long xn = x + (long)(k + nn - 1) * g.lev;
+    const double q = dp[xn] * area;
+    s1 = s1 + a[xn] * q;
+    if (b) s2 = s2 + b[xn] * q;
+  }
+  util1[x] = s1;
+  if (b) util2[x] = s2;
+}
+// util1 = f(:,:)*scp2 on wet points (budget_init with f=pb(:,:,1); the salt_corr sum of budget_sums)
+__global__ void budget_area_weight(Geom g, const int* __restrict__ ip, const double* __restrict__ f,
+                                   const double* __restrict__ scp2, double* __restrict__ util1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j);
+  if (ip[x] == 1) util1[x] = f[x] * scp2[x];
+}
+
 }  // namespace
+
+double budget_init_dev() {
+  Ctx& c = C(); const Geom& g = c.g;
+  double* util1 = c.has("util1") ? c.dev("util1") : c.owned("util1", 1);
+  dim3 grid(cdiv(g.ii, 128), g.jj);
+  LAUNCH(budget_area_weight, grid, 128, 0, g, c.idev("ip"), c.dev("pb"), c.dev("scp2"), util1);
+  return xcsum_dev(util1, c.idev("ip"));
+}
+
+void budget_sums_dev(int ncall, int n, int nn, double* out) {
+  (void)n;
+  Ctx& c = C(); const Geom& g = c.g;
+  double* util1 = c.has("util1") ? c.dev("util1") : c.owned("util1", 1);
+  double* util2 = c.has("util2") ? c.dev("util2") : c.owned("util2", 1);
+  const int* ip = c.idev("ip");
+  dim3 grid(cdiv(g.ii, 128), g.jj);
+  LAUNCH(budget_columns, grid, 128, 0, g, nn, ip, c.dev("dp"), c.dev("scp2"), c.dev("saln"), c.dev("temp"), util1, util2);
+  out[0] = xcsum_dev(util1, ip);
+  out[1] = xcsum_dev(util2, ip);
+  if (g.ntr > 0) {
+    LAUNCH(budget_columns, grid, 128, 0, g, nn, ip, c.dev("dp"), c.dev("scp2"), c.dev("trc"), (const double*)nullptr,
+           util1, util2);
+    out[2] = xcsum_dev(util1, ip);
+  }
+  const bool isopyc = c.option("vcoord", "cntiso_hybrid") == "isopyc_bulkml";
+  if (((isopyc && ncall == 5) || (!isopyc && ncall == 4)) && c.has("salt_corr")) {
+    LAUNCH(budget_area_weight, grid, 128, 0, g, ip, c.dev("salt_corr"), c.dev("scp2"), util1);
+    out[3] = xcsum_dev(util1, ip);
+  }
+}
 
 void numerical_bounds_dev() {
   Ctx& c = C(); const Geom& g = c.g;

@@ -62,24 +62,36 @@ __global__ void diffus_flux(Geom g, double delt1, int mm, int nn, const int* __r
   const long x = ix2(g, i, j);
   const long xn = x + (long)(k + nn - 1) * g.lev, xm = x + (long)(k + mm - 1) * g.lev;
   const long xk = x + (long)(k - 1) * g.lev;
+  const long s = g.ldi;
+  // all operands are loaded unconditionally (x-1 and x-s stay inside the halo-padded arrays) so the loads
+  // of a thread are issued as one batch; the masks only gate the stores
+  const bool wu = j <= g.jj + 1 && iu[x] == 1, wv = i <= g.ii + 1 && iv[x] == 1;
   const double dpc = dp[xn], tc = temp[xn], sc = saln[xn], dc = difiso[xk];
-  if (j <= g.jj + 1 && iu[x] == 1) {
-    const double q = delt1 * .5 * (difiso[xk - 1] + dc) * scuy[x] * scuxi[x] * fmax(fmin(dp[xn - 1], dpc), dpeps);
-    const double fs = q * (saln[xn - 1] - sc), ft = q * (temp[xn - 1] - tc);
+  const double dpw = dp[xn - 1], tw = temp[xn - 1], sw = saln[xn - 1], dw = difiso[xk - 1];
+  const double dps = dp[xn - s], ts = temp[xn - s], ss = saln[xn - s], ds = difiso[xk - s];
+  const double ousf = usflx[xm], outf = utflx[xm], ovsf = vsflx[xm], ovtf = vtflx[xm];
+  const double qu = delt1 * .5 * (dw + dc) * scuy[x] * scuxi[x] * fmax(fmin(dpw, dpc), dpeps);
+  const double qv = delt1 * .5 * (ds + dc) * scvx[x] * scvyi[x] * fmax(fmin(dps, dpc), dpeps);
+  if (wu) {
+    const double fs = qu * (sw - sc), ft = qu * (tw - tc);
     usflld[xm] = fs; utflld[xm] = ft;
-    for (int nt = 0; nt < T.n; ++nt) T.fu[nt][xk] = q * (T.t[nt][xn - 1] - T.t[nt][xn]);
-    usflx[xm] = usflx[xm] + fs;
-    utflx[xm] = utflx[xm] + ft;
+    usflx[xm] = ousf + fs;
+    utflx[xm] = outf + ft;
   }
-  if (i <= g.ii + 1 && iv[x] == 1) {
-    const long s = g.ldi;
-    const double q = delt1 * .5 * (difiso[xk - s] + dc) * scvx[x] * scvyi[x] * fmax(fmin(dp[xn - s], dpc), dpeps);
-    const double fs = q * (saln[xn - s] - sc), ft = q * (temp[xn - s] - tc);
+  if (wv) {
+    const double fs = qv * (ss - sc), ft = qv * (ts - tc);
     vsflld[xm] = fs; vtflld[xm] = ft;
-    for (int nt = 0; nt < T.n; ++nt) T.fv[nt][xk] = q * (T.t[nt][xn - s] - T.t[nt][xn]);
-    vsflx[xm] = vsflx[xm] + fs;
-    vtflx[xm] = vtflx[xm] + ft;
+    vsflx[xm] = ovsf + fs;
+    vtflx[xm] = ovtf + ft;
   }
+  // static tracer index: keeps the pointer table in the constant bank (a run-time index spills it to local memory)
+#pragma unroll
+  for (int nt = 0; nt < MAXTR; ++nt)
+    if (nt < T.n) {
+      const double c0 = T.t[nt][xn];
+      if (wu) T.fu[nt][xk] = qu * (T.t[nt][xn - 1] - c0);
+      if (wv) T.fv[nt][xk] = qv * (T.t[nt][xn - s] - c0);
+    }
 }
 
 __global__ void diffus_update(Geom g, eos::Coef ec, int mm, int nn, const int* __restrict__ ip,
@@ -101,8 +113,10 @@ __global__ void diffus_update(Geom g, eos::Coef ec, int mm, int nn, const int* _
   const double tn = temp[xn] - q * (utflld[xm + 1] - utflld[xm] + vtflld[xm + s] - vtflld[xm]);
   saln[xn] = sn;
   temp[xn] = tn;
-  for (int nt = 0; nt < T.n; ++nt)
-    T.t[nt][xn] = T.t[nt][xn] - q * (T.fu[nt][xk + 1] - T.fu[nt][xk] + T.fv[nt][xk + s] - T.fv[nt][xk]);
+#pragma unroll
+  for (int nt = 0; nt < MAXTR; ++nt)
+    if (nt < T.n)
+      T.t[nt][xn] = T.t[nt][xn] - q * (T.fu[nt][xk + 1] - T.fu[nt][xk] + T.fv[nt][xk + s] - T.fv[nt][xk]);
   sigma[xn] = eos::sig(ec, tn, sn);
 }
 

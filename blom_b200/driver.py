@@ -15,6 +15,8 @@ only when this build provides them (`available_routines`).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import synth
@@ -70,7 +72,9 @@ class HotPath:
             if comm_uid is None:
                 raise ValueError("multi-rank HotPath needs the NCCL unique id")
             g.comm_init(comm_uid)
-        for k, v in (options or {}).items():
+        # development A/B switches: BLOM_OPTIONS="key=value,key=value" (e.g. momtum_form=staged)
+        env_opts = dict(kv.split("=", 1) for kv in os.environ.get("BLOM_OPTIONS", "").split(",") if "=" in kv)
+        for k, v in {**env_opts, **(options or {})}.items():
             g.set_option(k, v)
         self.arrays = {**self.grid, **self.state}
         g.register_all(self.arrays)

@@ -126,6 +126,15 @@ module mod_blomgpu
          import :: c_int
          integer(c_int), value :: m, mm, nn, k1m
       end function
+      integer(c_int) function blomgpu_budget_init(mass0) bind(C, name='blomgpu_budget_init')
+         import :: c_int, c_double
+         real(c_double), intent(out) :: mass0
+      end function
+      integer(c_int) function blomgpu_budget_sums(ncall, n, nn, out) bind(C, name='blomgpu_budget_sums')
+         import :: c_int, c_double
+         integer(c_int), value :: ncall, n, nn
+         real(c_double), intent(inout) :: out(4)
+      end function
    end interface
 
    ! the nine entry points with the common (m,n,mm,nn,k1m,k1n) signature
@@ -149,7 +158,7 @@ module mod_blomgpu
    public :: gpu_setup, gpu_register, gpu_register_int, gpu_upload, gpu_download, &
              gpu_option, gpu_scalar, gpu_xctilr, &
              init_fluxes, tmsmt1, eddtra, advect, pbcor1, diffus, pgforc, momtum, &
-             barotp, pbcor2, tmsmt2, ndiff
+             barotp, pbcor2, tmsmt2, ndiff, budget_init, budget_sums
 
 contains
 
@@ -272,6 +281,17 @@ contains
    subroutine ndiff(m, n, mm, nn, k1m, k1n)
       integer, intent(in) :: m, n, mm, nn, k1m, k1n
       call check(blomgpu_ndiff(m, n, mm, nn, k1m, k1n), 'ndiff')
+   end subroutine
+   ! conservation diagnostics, phy/mod_budget.F90:74-196; the caller (mod_budget) stores
+   ! out(1:4) into sdp(ncall,n), tdp(ncall,n), trdp(ncall,n) and sc(n)
+   subroutine budget_init(mass0)
+      real(c_double), intent(out) :: mass0
+      call check(blomgpu_budget_init(mass0), 'budget_init')
+   end subroutine
+   subroutine budget_sums(ncall, n, nn, out)
+      integer, intent(in) :: ncall, n, nn
+      real(c_double), intent(inout) :: out(4)
+      call check(blomgpu_budget_sums(ncall, n, nn, out), 'budget_sums')
    end subroutine
 
 end module mod_blomgpu

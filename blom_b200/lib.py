@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "blomgpu_numerical_bounds", "blomgpu_init_fluxes",
     "blomgpu_tmsmt1", "blomgpu_eddtra", "blomgpu_advect", "blomgpu_pbcor1", "blomgpu_diffus",
     "blomgpu_pgforc", "blomgpu_momtum", "blomgpu_barotp", "blomgpu_pbcor2", "blomgpu_tmsmt2",
-    "blomgpu_ndiff",
+    "blomgpu_ndiff", "blomgpu_budget_init", "blomgpu_budget_sums",
     "blomgpu_launch_count", "blomgpu_launch_count_reset", "blomgpu_timers_enable",
     "blomgpu_timers_get", "blomgpu_timers_reset", "blomgpu_stream",
     "blomgpu_ktimers_enable", "blomgpu_ktimers_get",
@@ -239,6 +239,18 @@ class BlomGpu:
 
     def ndiff(self, *a):
         self._six(self.lib.blomgpu_ndiff, *a)
+
+    def budget_init(self):
+        """mass0 of budget_init (phy/mod_budget.F90:74-93)"""
+        out = C.c_double()
+        self._ck(self.lib.blomgpu_budget_init(C.byref(out)))
+        return out.value
+
+    def budget_sums(self, ncall, n, nn):
+        """(sdp, tdp, trdp, sc) of budget_sums (phy/mod_budget.F90:95-196); nan = not evaluated"""
+        out = (C.c_double * 4)(*([float("nan")] * 4))
+        self._ck(self.lib.blomgpu_budget_sums(ncall, n, nn, out))
+        return tuple(out)
 
     # -- instrumentation -----------------------------------------------------------
     def launch_count(self):

@@ -115,6 +115,16 @@ int blomgpu_tmsmt2(int m, int mm, int nn, int k1m);           /* phy/mod_tmsmt.F
  * plus temp, saln, trc, difiso, pu, pv; updates u|v t|s flld, u|v t|s flx (level k+mm), nslpx, nslpy. */
 int blomgpu_ndiff(int m, int n, int mm, int nn, int k1m, int k1n);
 
+/* Conservation diagnostics (cnsvdi): budget_init (phy/mod_budget.F90:74-93) returns the global mass
+ * xcsum(pb(:,:,1)*scp2); budget_sums (phy/mod_budget.F90:95-196) the thickness-weighted global sums at
+ * time level nn: out[0]=sdp(ncall,n)  out[1]=tdp(ncall,n)  out[2]=trdp(ncall,n) (1st tracer, ntr>0)
+ * out[3]=sc(n) (salt_corr*scp2, only on ncall 4, or 5 for vcoord='isopyc_bulkml', and only when a
+ * field 'salt_corr' is registered).  Entries that are not evaluated are left untouched.  Column sums run
+ * in k order and the horizontal sum is the strip-ordered xcsum, so the values are bit-reproducible and
+ * independent of the j-band decomposition.  Work arrays util1/util2 (mod_utility) are overwritten. */
+int blomgpu_budget_init(double* mass0);
+int blomgpu_budget_sums(int ncall, int n, int nn, double out[4]);
+
 /* ---- instrumentation ---------------------------------------------------- */
 /* kernels launched by this library since the last reset */
 long blomgpu_launch_count(void);

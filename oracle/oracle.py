@@ -182,3 +182,15 @@ class Oracle:
     def barotp(self, *a): self._call("barotp", *a)
     def pbcor2(self, *a): self._call("pbcor2", *a)
     def ndiff(self, *a): self._call("ndiff", *a)
+
+    def budget_init(self):
+        """mass0 of budget_init (phy/mod_budget.F90:74-93)"""
+        out = C.c_double()
+        self._call("budget_init", C.byref(out))
+        return out.value
+
+    def budget_sums(self, ncall, n, nn):
+        """(sdp, tdp, trdp, sc) of budget_sums (phy/mod_budget.F90:95-196); nan = not evaluated"""
+        out = (C.c_double * 4)(*([float("nan")] * 4))
+        self._call("budget_sums", ncall, n, nn, out)
+        return tuple(out)

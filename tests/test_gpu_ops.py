@@ -152,6 +152,41 @@ def test_momtum(cfg, mommth, vcoord):
         g.finalize()
 
 
+@pytest.mark.parametrize("cfg,mommth,vcoord", [("tiny1", "enecon", "cntiso_hybrid"), ("tiny2", "enscon", "cntiso_hybrid"),
+                                               ("tiny3", "enedis", "cntiso_hybrid"), ("tiny4", "enscon", "isopyc_bulkml"),
+                                               ("fuk95", "enedis", "cntiso_hybrid")])
+def test_momtum_fused_equals_staged(cfg, mommth, vcoord):
+    """The shared-memory tile form (one launch, momtum_form=fused) evaluates the same
+    expressions in the same order as the staged form (one launch per stage, scratch in HBM, the default): the two
+    must agree BIT FOR BIT in the parity build, and the staged form stays within 1e-11 of the oracle."""
+    c = Case(cfg, ntr=0)
+    o = c.new_oracle()
+    o.set_option("mommth", mommth); o.set_option("vcoord", vcoord)
+    o.inieos(); o.numerical_bounds(); o.pgforc(*c.levels)
+    res = {}
+    for form in ("fused", "staged"):  # one library context at a time
+        g = c.new_gpu(parity=True)
+        try:
+            for k, v in {"mommth": mommth, "vcoord": vcoord, "momtum_form": form}.items():
+                g.set_option(k, v)
+            g.inieos(); g.numerical_bounds(); g.pgforc(*c.levels)
+            for rep in range(2):
+                g.momtum(*c.levels)
+                if form == "staged":
+                    o.momtum(*c.levels)
+                g.download_all()
+                res[form, rep] = {nm: g.arrays[nm].copy() for nm in MT_FIELDS + ["absvor", "dpvor"]}
+            res[form, "launches"] = g.launch_count()
+            if form == "staged":
+                check(g, o, MT_FIELDS, 1e-10)
+        finally:
+            g.finalize()
+    for rep in range(2):
+        for nm in MT_FIELDS + ["absvor", "dpvor"]:
+            assert np.array_equal(res["fused", rep][nm], res["staged", rep][nm]), (nm, rep)
+    assert res["fused", "launches"] < res["staged", "launches"]
+
+
 def test_momtum_perf_build():
     c, o, g = pair("tiny2", ntr=0, parity=False)
     try:
@@ -267,5 +302,56 @@ def test_pbcor_bad_option():
             g.pbcor1(*c.levels)
         with pytest.raises(BlomGpuError, match="bmcmth = bogus is unsupported"):
             g.pbcor2(*c.levels)
+    finally:
+        g.finalize()
+
+
+@pytest.mark.parametrize("cfg,ntr,parity", [("tiny0", 0, True), ("tiny2", 1, True), ("fuk95", 1, True), ("tiny2", 1, False)])
+def test_budget_sums(cfg, ntr, parity):
+    """budget_init / budget_sums (phy/mod_budget.F90:74-196): k-ordered column sums + strip-ordered
+    xcsum.  Bit-exact against the oracle in the parity build; 1e-14 relative with FMA contraction."""
+    import math
+    c = Case(cfg, ntr=ntr)
+    o = c.new_oracle(); g = c.new_gpu(parity=parity)
+    try:
+        m, n, mm, nn, k1m, k1n = c.levels
+        a, b = g.budget_init(), o.budget_init()
+        assert a == b
+        for ncall in (1, 4):
+            ga, oa = g.budget_sums(ncall, n, nn), o.budget_sums(ncall, n, nn)
+            for x, y in zip(ga, oa):
+                if math.isnan(y):
+                    assert math.isnan(x)
+                elif parity:
+                    assert x == y, (ga, oa)
+                else:
+                    assert abs(x - y) <= 1e-14 * abs(y), (ga, oa)
+        g.download_all()
+        ip = interior(c.masks["ip"]) == 1
+        if parity:
+            assert np.array_equal(interior(g.arrays["util1"])[0][ip], interior(o.arrays["util1"])[0][ip])
+    finally:
+        g.finalize()
+
+
+@pytest.mark.parametrize("cfg", ["tiny0", "tiny1", "tiny3"])
+def test_budget_conserved_through_transport_and_diffusion(cfg):
+    """the global inventories sum(S dp scp2), sum(T dp scp2), sum(trc dp scp2) as the reference's own
+    diagnostic (budget_sums) measures them are conserved to round-off (1e-13 relative) across
+    advect -> diffus on closed / periodic domains (no fold), all on device."""
+    c = Case(cfg, ntr=1)
+    g = c.new_gpu(parity=True)
+    try:
+        g.inieos(); g.numerical_bounds(); g.init_cppm()
+        m, n, mm, nn, k1m, k1n = c.levels
+        before = g.budget_sums(1, n, nn)
+        g.advect(*c.levels)
+        mid = g.budget_sums(2, n, nn)
+        g.diffus(*c.levels)
+        after = g.budget_sums(3, n, nn)
+        for i in range(3):
+            assert abs(mid[i] - before[i]) <= 1e-13 * abs(before[i]), (i, before, mid)
+            assert abs(after[i] - before[i]) <= 1e-13 * abs(before[i]), (i, before, after)
+        assert mid != before   # the fields did move
     finally:
         g.finalize()

@@ -329,3 +329,44 @@ def test_eddtra_isopycnic_properties(cfg, eitmth):
             empty = (kidx >= 3) & (kidx < np.minimum(interior(a["kfpla"][n - 1]),
                                                      interior(np.roll(a["kfpla"][n - 1], sh, axis=(0, 1)))) - 1)
             assert np.abs(fl[empty & w[None]]).max(initial=0.0) == 0.0
+
+
+@pytest.mark.parametrize("cfg,ntr", [("tiny0", 0), ("tiny2", 1), ("fuk95", 1)])
+def test_budget_sums_pinned_by_exact_summation(cfg, ntr):
+    """budget_init / budget_sums (phy/mod_budget.F90:74-196).  The restatement is pinned by an
+    independent evaluation: column sums recomputed with numpy in the same k order, then summed with
+    math.fsum (exactly rounded) -- the strip-ordered xcsum must agree to 1e-14 relative; entries the
+    reference does not evaluate stay untouched (nan from the wrapper)."""
+    import math
+    c = Case(cfg, ntr=ntr)
+    o = c.new_oracle()
+    m, n, mm, nn, k1m, k1n = c.levels
+    kk = c.dims[2]
+    ip = interior(c.masks["ip"]) == 1
+    scp2 = interior(o.arrays["scp2"])[0]
+    mass0 = o.budget_init()
+    ref = math.fsum((interior(o.arrays["pb"])[0] * scp2)[ip].tolist())
+    assert abs(mass0 - ref) <= 1e-14 * abs(ref)
+    sdp, tdp, trdp, sc = o.budget_sums(1, n, nn)
+
+    def column(name):
+        acc = np.zeros_like(scp2)
+        for k in range(kk):
+            q = interior(o.arrays["dp"])[nn + k] * scp2
+            acc = acc + interior(o.arrays[name])[nn + k] * q
+        return math.fsum(acc[ip].tolist())
+    for got, name in ((sdp, "saln"), (tdp, "temp")):
+        ref = column(name)
+        assert abs(got - ref) <= 1e-14 * abs(ref), (name, got, ref)
+    if ntr:
+        ref = column("trc")
+        assert abs(trdp - ref) <= 1e-14 * abs(ref)
+    else:
+        assert math.isnan(trdp)
+    assert math.isnan(sc)          # ncall=1 and no salt_corr registered
+    # util1 holds the last column sum the reference leaves there (tracer if present, else salinity)
+    last = "trc" if ntr else "saln"
+    acc = np.zeros_like(scp2)
+    for k in range(kk):
+        acc = acc + interior(o.arrays[last])[nn + k] * (interior(o.arrays["dp"])[nn + k] * scp2)
+    assert np.array_equal(interior(o.arrays["util1"])[0][ip], acc[ip])
