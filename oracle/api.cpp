@@ -24,6 +24,10 @@ void pbcor1(int, int, int, int, int, int);
 void pbcor2(int, int, int, int, int, int);
 void init_fluxes(int, int, int, int, int, int);
 void ndiff(int, int, int, int, int, int);
+void cmnfld2(int, int, int, int, int, int);
+void cmnfld_bfsqf_ale(int, int, int, int, int, int);
+void cmnfld_nslope_ale(int, int, int, int, int, int);
+void cmnfld_nnslope_ale(int, int, int, int, int, int);
 void budget_init(double*);
 void budget_sums(int, int, int, double*);
 }
@@ -132,6 +136,10 @@ int oracle_momtum(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::m
 int oracle_numerical_bounds() { GUARD(orc::numerical_bounds()) }
 int oracle_init_fluxes(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::init_fluxes(m, n, mm, nn, k1m, k1n)) }
 int oracle_ndiff(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::ndiff(m, n, mm, nn, k1m, k1n)) }
+int oracle_cmnfld2(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::cmnfld2(m, n, mm, nn, k1m, k1n)) }
+int oracle_cmnfld_bfsqf_ale(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::cmnfld_bfsqf_ale(m, n, mm, nn, k1m, k1n)) }
+int oracle_cmnfld_nslope_ale(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::cmnfld_nslope_ale(m, n, mm, nn, k1m, k1n)) }
+int oracle_cmnfld_nnslope_ale(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(orc::cmnfld_nnslope_ale(m, n, mm, nn, k1m, k1n)) }
 int oracle_budget_init(double* mass0) { GUARD(orc::budget_init(mass0)) }
 int oracle_budget_sums(int ncall, int n, int nn, double* out) { GUARD(orc::budget_sums(ncall, n, nn, out)) }
 double oracle_get_scalar(const char* k) { return orc::O().scalar(k, 0.0); }

@@ -182,6 +182,10 @@ class Oracle:
     def barotp(self, *a): self._call("barotp", *a)
     def pbcor2(self, *a): self._call("pbcor2", *a)
     def ndiff(self, *a): self._call("ndiff", *a)
+    def cmnfld2(self, *a): self._call("cmnfld2", *a)
+    def cmnfld_bfsqf_ale(self, *a): self._call("cmnfld_bfsqf_ale", *a)
+    def cmnfld_nslope_ale(self, *a): self._call("cmnfld_nslope_ale", *a)
+    def cmnfld_nnslope_ale(self, *a): self._call("cmnfld_nnslope_ale", *a)
 
     def budget_init(self):
         """mass0 of budget_init (phy/mod_budget.F90:74-93)"""
