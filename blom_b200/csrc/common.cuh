@@ -207,6 +207,10 @@ void pbcor2_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void numerical_bounds_dev();
 void init_fluxes_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n);  // ndiff.cu
+void cmnfld2_dev(int m, int n, int mm, int nn, int k1m, int k1n);             // cmnfld.cu
+void cmnfld_bfsqf_ale_dev(int m, int n, int mm, int nn, int k1m, int k1n);
+void cmnfld_nslope_ale_dev(int m, int n, int mm, int nn, int k1m, int k1n);
+void cmnfld_nnslope_ale_dev(int m, int n, int mm, int nn, int k1m, int k1n);
 double budget_init_dev();                                       // setup_ops.cu
 void budget_sums_dev(int ncall, int n, int nn, double* out);
 

@@ -262,6 +262,10 @@ int blomgpu_momtum(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(Scope
 int blomgpu_barotp(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("barotp"); barotp_dev(m, n, mm, nn, k1m, k1n)) }
 int blomgpu_pbcor2(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("pbcor2"); pbcor2_dev(m, n, mm, nn, k1m, k1n)) }
 int blomgpu_ndiff(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("ndiff"); ndiff_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_cmnfld2(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("cmnfld2"); cmnfld2_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_cmnfld_bfsqf_ale(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(cmnfld_bfsqf_ale_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_cmnfld_nslope_ale(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(cmnfld_nslope_ale_dev(m, n, mm, nn, k1m, k1n)) }
+int blomgpu_cmnfld_nnslope_ale(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(cmnfld_nnslope_ale_dev(m, n, mm, nn, k1m, k1n)) }
 int blomgpu_budget_init(double* mass0) { GUARD(*mass0 = budget_init_dev()) }
 int blomgpu_budget_sums(int ncall, int n, int nn, double out[4]) { GUARD(budget_sums_dev(ncall, n, nn, out)) }
 int blomgpu_tmsmt2(int m, int mm, int nn, int k1m) { GUARD(ScopedTimer t("tmsmt2"); tmsmt2_dev(m, mm, nn, k1m)) }

@@ -154,11 +154,16 @@ module mod_blomgpu
    procedure(six_int_entry), bind(C, name='blomgpu_barotp') :: blomgpu_barotp
    procedure(six_int_entry), bind(C, name='blomgpu_pbcor2') :: blomgpu_pbcor2
    procedure(six_int_entry), bind(C, name='blomgpu_ndiff') :: blomgpu_ndiff
+   procedure(six_int_entry), bind(C, name='blomgpu_cmnfld2') :: blomgpu_cmnfld2
+   procedure(six_int_entry), bind(C, name='blomgpu_cmnfld_bfsqf_ale') :: blomgpu_cmnfld_bfsqf_ale
+   procedure(six_int_entry), bind(C, name='blomgpu_cmnfld_nslope_ale') :: blomgpu_cmnfld_nslope_ale
+   procedure(six_int_entry), bind(C, name='blomgpu_cmnfld_nnslope_ale') :: blomgpu_cmnfld_nnslope_ale
 
    public :: gpu_setup, gpu_register, gpu_register_int, gpu_upload, gpu_download, &
              gpu_option, gpu_scalar, gpu_xctilr, &
              init_fluxes, tmsmt1, eddtra, advect, pbcor1, diffus, pgforc, momtum, &
-             barotp, pbcor2, tmsmt2, ndiff, budget_init, budget_sums
+             barotp, pbcor2, tmsmt2, ndiff, cmnfld2, cmnfld_bfsqf_ale, cmnfld_nslope_ale, &
+             cmnfld_nnslope_ale, budget_init, budget_sums
 
 contains
 
@@ -281,6 +286,24 @@ contains
    subroutine ndiff(m, n, mm, nn, k1m, k1n)
       integer, intent(in) :: m, n, mm, nn, k1m, k1n
       call check(blomgpu_ndiff(m, n, mm, nn, k1m, k1n), 'ndiff')
+   end subroutine
+   ! cmnfld2, hybrid (ALE) branch: halo refresh of temp/saln, filtered buoyancy frequency and the
+   ! neutral slope that eddtra/ndiff read (phy/mod_cmnfld_routines.F90:1158-1238, :229-350, :654-883)
+   subroutine cmnfld2(m, n, mm, nn, k1m, k1n)
+      integer, intent(in) :: m, n, mm, nn, k1m, k1n
+      call check(blomgpu_cmnfld2(m, n, mm, nn, k1m, k1n), 'cmnfld2')
+   end subroutine
+   subroutine cmnfld_bfsqf_ale(m, n, mm, nn, k1m, k1n)     ! phy/mod_cmnfld_routines.F90:229
+      integer, intent(in) :: m, n, mm, nn, k1m, k1n
+      call check(blomgpu_cmnfld_bfsqf_ale(m, n, mm, nn, k1m, k1n), 'cmnfld_bfsqf_ale')
+   end subroutine
+   subroutine cmnfld_nslope_ale(m, n, mm, nn, k1m, k1n)    ! phy/mod_cmnfld_routines.F90:654
+      integer, intent(in) :: m, n, mm, nn, k1m, k1n
+      call check(blomgpu_cmnfld_nslope_ale(m, n, mm, nn, k1m, k1n), 'cmnfld_nslope_ale')
+   end subroutine
+   subroutine cmnfld_nnslope_ale(m, n, mm, nn, k1m, k1n)   ! phy/mod_cmnfld_routines.F90:813
+      integer, intent(in) :: m, n, mm, nn, k1m, k1n
+      call check(blomgpu_cmnfld_nnslope_ale(m, n, mm, nn, k1m, k1n), 'cmnfld_nnslope_ale')
    end subroutine
    ! conservation diagnostics, phy/mod_budget.F90:74-196; the caller (mod_budget) stores
    ! out(1:4) into sdp(ncall,n), tdp(ncall,n), trdp(ncall,n) and sc(n)

@@ -34,7 +34,8 @@ ABI_SYMBOLS = [
     "blomgpu_numerical_bounds", "blomgpu_init_fluxes",
     "blomgpu_tmsmt1", "blomgpu_eddtra", "blomgpu_advect", "blomgpu_pbcor1", "blomgpu_diffus",
     "blomgpu_pgforc", "blomgpu_momtum", "blomgpu_barotp", "blomgpu_pbcor2", "blomgpu_tmsmt2",
-    "blomgpu_ndiff", "blomgpu_budget_init", "blomgpu_budget_sums",
+    "blomgpu_ndiff", "blomgpu_cmnfld2", "blomgpu_cmnfld_bfsqf_ale", "blomgpu_cmnfld_nslope_ale",
+    "blomgpu_cmnfld_nnslope_ale", "blomgpu_budget_init", "blomgpu_budget_sums",
     "blomgpu_launch_count", "blomgpu_launch_count_reset", "blomgpu_timers_enable",
     "blomgpu_timers_get", "blomgpu_timers_reset", "blomgpu_stream",
     "blomgpu_ktimers_enable", "blomgpu_ktimers_get",
@@ -239,6 +240,18 @@ class BlomGpu:
 
     def ndiff(self, *a):
         self._six(self.lib.blomgpu_ndiff, *a)
+
+    def cmnfld2(self, *a):
+        self._six(self.lib.blomgpu_cmnfld2, *a)
+
+    def cmnfld_bfsqf_ale(self, *a):
+        self._six(self.lib.blomgpu_cmnfld_bfsqf_ale, *a)
+
+    def cmnfld_nslope_ale(self, *a):
+        self._six(self.lib.blomgpu_cmnfld_nslope_ale, *a)
+
+    def cmnfld_nnslope_ale(self, *a):
+        self._six(self.lib.blomgpu_cmnfld_nnslope_ale, *a)
 
     def budget_init(self):
         """mass0 of budget_init (phy/mod_budget.F90:74-93)"""

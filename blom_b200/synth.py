@@ -533,6 +533,14 @@ def ndiff_inputs(syn, st, levels, ntr=0):
     return {k: np.ascontiguousarray(v) for k, v in out.items()}
 
 
+def cmnfld_arrays(syn):
+    """Output arrays of cmnfld2's hybrid branch (phy/mod_cmnfld.F90:51-75): bfsqi, bfsqf on kdm+1
+    interfaces, bfsql on kdm layers, nnslpx/nnslpy on kdm interfaces.  nslpx/nslpy are part of state()."""
+    kk = syn.kdm
+    return {"bfsqi": syn.zeros(kk + 1), "bfsqf": syn.zeros(kk + 1), "bfsql": syn.zeros(kk),
+            "nnslpx": syn.zeros(kk), "nnslpy": syn.zeros(kk)}
+
+
 def fill_halos(backend, arrays: dict, nbdy=4, names=None):
     """xctilr(nbdy,nbdy) of every registered array with its grid type.  `backend` is a
     BlomGpu (product) or the test Oracle; arrays must already be registered."""

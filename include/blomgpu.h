@@ -115,6 +115,17 @@ int blomgpu_tmsmt2(int m, int mm, int nn, int k1m);           /* phy/mod_tmsmt.F
  * plus temp, saln, trc, difiso, pu, pv; updates u|v t|s flld, u|v t|s flx (level k+mm), nslpx, nslpy. */
 int blomgpu_ndiff(int m, int n, int mm, int nn, int k1m, int k1n);
 
+/* cmnfld2 (phy/mod_cmnfld_routines.F90:1158-1238), hybrid/ALE branch: the producer of nslpx/nslpy that
+ * eddtra and ndiff consume, called between tmsmt1 and eddtra (phy/mod_blom_step.F90:136).  Refreshes the
+ * temp/saln halos (3,3), then cmnfld_bfsqf_ale (:229-350; bfsqi, bfsqf kdm+1 levels, bfsql kdm) and, for
+ * edritp='large scale' or eitmth='gm', cmnfld_nslope_ale (:654-811; phi, nslpx, nslpy, nnslpx, nnslpy)
+ * or, with ltedtp='neutral', cmnfld_nnslope_ale (:813-883).  Scalars sls0, bfsqmn default to
+ * phy/mod_cmnfld.F90:36,46.  vcoord='isopyc_bulkml' fails with the reference-style message. */
+int blomgpu_cmnfld2(int m, int n, int mm, int nn, int k1m, int k1n);
+int blomgpu_cmnfld_bfsqf_ale(int m, int n, int mm, int nn, int k1m, int k1n);
+int blomgpu_cmnfld_nslope_ale(int m, int n, int mm, int nn, int k1m, int k1n);
+int blomgpu_cmnfld_nnslope_ale(int m, int n, int mm, int nn, int k1m, int k1n);
+
 /* Conservation diagnostics (cnsvdi): budget_init (phy/mod_budget.F90:74-93) returns the global mass
  * xcsum(pb(:,:,1)*scp2); budget_sums (phy/mod_budget.F90:95-196) the thickness-weighted global sums at
  * time level nn: out[0]=sdp(ncall,n)  out[1]=tdp(ncall,n)  out[2]=trdp(ncall,n) (1st tracer, ntr>0)
