@@ -378,6 +378,147 @@ cppm_hedges(Geom g, bool second_pass, const double* __restrict__ dp /* level 1 o
   her3[xk] = her;
 }
 
+// Level-marching tile form of the thickness edges.  A block owns TPO cells along the pass direction
+// times TC across it and marches through a chunk of levels; per level the three stencil stages
+// (cell thickness hm -> edge values he -> curvature proxy d2h) flow through shared memory, so every
+// hm (one division on the second pass), he and d2h is evaluated once per tile instead of 7/4/3 times
+// per cell, and the static weights of a thread's own edge/cell stay in registers across the levels.
+// dp (and the cross flux areas) of level k+1 are fetched into registers while level k is computed.
+// Expressions and their order are those of cppm_hedges above, so both forms are bit-identical.
+template <int DIR, bool MONO, int TPO, int TC>
+__global__ void __launch_bounds__(TPO* TC)
+cppm_hedges_tile(Geom g, bool second_pass, int kchunk, const double* __restrict__ dp,
+                 const double* __restrict__ cac, const double* __restrict__ scp2i,
+                 const double* __restrict__ tab, double* __restrict__ hel3, double* __restrict__ her3) {
+  constexpr int NP = TPO + 6;              // staged cells along the pass: s0-3 .. s0+TPO+2
+  constexpr int NE = TPO + 3;              // edges s0-1 .. s0+TPO+1
+  constexpr int ND = TPO + 2;              // d2h of cells s0-1 .. s0+TPO
+  constexpr int NX = (NP + TPO - 1) / TPO; // staged cells per thread (2)
+  __shared__ double s_hm[NP * TC], s_he[NE * TC], s_d2[ND * TC];
+  const int tp = DIR == 0 ? threadIdx.x : threadIdx.y;
+  const int tc = DIR == 0 ? threadIdx.y : threadIdx.x;
+  auto sidx = [&](int p, int n) { return DIR == 0 ? tc * n + p : p * TC + tc; };
+  const int npass = DIR == 0 ? g.ii : g.jj, ncross = DIR == 0 ? g.jj : g.ii;
+  const int s0 = 1 + (DIR == 0 ? blockIdx.x : blockIdx.y) * TPO;
+  const int cc = 1 + (DIR == 0 ? blockIdx.y : blockIdx.x) * TC + tc;
+  const int ccl = min(cc, ncross);
+  const long sc = DIR == 0 ? g.ldi : 1;
+  const long lev = g.lev;
+  // clamped addresses (positions beyond the last cell + 3 are never used by a stored result)
+  auto addr = [&](int pi) -> long {
+    const int pc = min(pi, npass + 3);
+    return DIR == 0 ? ix2(g, pc, ccl) : ix2(g, ccl, pc);
+  };
+  const int k_first = blockIdx.z * kchunk + 1;
+  const int k_last = min(g.kdm, k_first + kchunk - 1);
+
+  // ---- per-thread invariants ----
+  long ycell[NX]; double ai[NX];
+#pragma unroll
+  for (int r = 0; r < NX; ++r) {
+    const int q = tp + r * TPO;
+    ycell[r] = addr(s0 - 3 + min(q, NP - 1));
+    ai[r] = second_pass ? scp2i[ycell[r]] : K0;
+  }
+  // own edge r = tp (cell index s0-1+tp) and own d2h cell r' = tp (cell s0-1+tp)
+  const long ye = addr(s0 - 1 + tp);
+  const double w1 = tab[T_HEVC1 * lev + ye], w2 = tab[T_HEVC2 * lev + ye], w3 = tab[T_HEVC3 * lev + ye],
+               w4 = tab[T_HEVC4 * lev + ye], d2m_e = tab[T_D2M * lev + ye];
+  // own cell c = s0+tp
+  const int c = s0 + tp;
+  const long xc = addr(c);
+  const double ssc = tab[T_SSC * lev + xc], scc = tab[T_SCC * lev + xc];
+  const bool store = c <= npass && cc <= ncross;
+
+  double raw[NX], cp_[NX], cm_[NX];
+  auto fetch = [&](int k) {
+    const long koff = (long)(k - 1) * lev;
+#pragma unroll
+    for (int r = 0; r < NX; ++r) {
+      if (tp + r * TPO < NP) {
+        raw[r] = dp[ycell[r] + koff];
+        if (second_pass) { cp_[r] = cac[ycell[r] + koff + sc]; cm_[r] = cac[ycell[r] + koff]; }
+      }
+    }
+  };
+  fetch(k_first);
+  for (int k = k_first; k <= k_last; ++k) {
+    // ---- cell thickness of the staged cells ----
+#pragma unroll
+    for (int r = 0; r < NX; ++r) {
+      const int q = tp + r * TPO;
+      if (q < NP) {
+        double h = fmax(K0, raw[r]) + DPEPS;
+        if (second_pass) h = h / (K1 - (cp_[r] - cm_[r]) * ai[r]);
+        s_hm[sidx(q, NP)] = h;
+      }
+    }
+    if (k < k_last) fetch(k + 1);
+    __syncthreads();
+    // ---- edge values ----
+    s_he[sidx(tp, NE)] = w1 * s_hm[sidx(tp, NP)] + w2 * s_hm[sidx(tp + 1, NP)] + w3 * s_hm[sidx(tp + 2, NP)] +
+                         w4 * s_hm[sidx(tp + 3, NP)];
+    if (tp < NE - TPO) {
+      const int r = tp + TPO;
+      const long y = addr(s0 - 1 + r);
+      s_he[sidx(r, NE)] = tab[T_HEVC1 * lev + y] * s_hm[sidx(r, NP)] + tab[T_HEVC2 * lev + y] * s_hm[sidx(r + 1, NP)] +
+                          tab[T_HEVC3 * lev + y] * s_hm[sidx(r + 2, NP)] + tab[T_HEVC4 * lev + y] * s_hm[sidx(r + 3, NP)];
+    }
+    __syncthreads();
+    // ---- curvature proxy ----
+    s_d2[sidx(tp, ND)] = d2m_e * (s_he[sidx(tp, NE)] - K2 * s_hm[sidx(tp + 2, NP)] + s_he[sidx(tp + 1, NE)]);
+    if (tp < ND - TPO) {
+      const int r = tp + TPO;
+      s_d2[sidx(r, ND)] = tab[T_D2M * lev + addr(s0 - 1 + r)] *
+                          (s_he[sidx(r, NE)] - K2 * s_hm[sidx(r + 2, NP)] + s_he[sidx(r + 1, NE)]);
+    }
+    __syncthreads();
+    // ---- limiter of the own cell ----
+    const double d2l = s_d2[sidx(tp, ND)], d2c = s_d2[sidx(tp + 1, ND)], d2r = s_d2[sidx(tp + 2, ND)];
+    double hel = s_he[sidx(tp + 1, NE)], her = s_he[sidx(tp + 2, NE)];
+    const double hmm = s_hm[sidx(tp + 2, NP)], hm0 = s_hm[sidx(tp + 3, NP)], hmp = s_hm[sidx(tp + 4, NP)];
+    double sl, sr, sc_, d, q_, r_, a2;
+    if (MONO || d2l * d2c <= K0 || d2c * d2r <= K0) {
+      sl = ssc * (hm0 - hmm);
+      sr = ssc * (hmp - hm0);
+      if (sl * sr > K0) {
+        sc_ = scc * (hmp - hmm);
+        sc_ = fsign(fmin(fmin(fabs(sl), fabs(sr)), fabs(sc_)), sc_);
+        if ((hmm - hel) * (hm0 - hel) > K0) hel = hm0 - fsign(fmin(K1_2 * fabs(sc_), fabs(hel - hm0)), sc_);
+        if ((hmp - her) * (hm0 - her) > K0) her = hm0 + fsign(fmin(K1_2 * fabs(sc_), fabs(her - hm0)), sc_);
+        d = her - hel;
+        q_ = d * (K2 * hm0 - hel - her);
+        r_ = K1_3 * d * d;
+        if (q_ > r_) hel = K3 * hm0 - K2 * her;
+        else if (-r_ > q_) her = K3 * hm0 - K2 * hel;
+      } else {
+        hel = hm0;
+        her = hm0;
+      }
+    }
+    if (!MONO) {
+      hel = fmax(hel, DPEPS);
+      her = fmax(her, DPEPS);
+      sl = K2 * (K3 * hm0 - K2 * hel - her);
+      a2 = K3 * (hel - K2 * hm0 + her);
+      sr = sl + K2 * a2;
+      if (sl < K0 && sr > K0) {
+        if (a2 * hel - K1_4 * sl * sl < a2 * DPEPS) {
+          q_ = K3 * hm0 / (K3 * sl * sr + K4 * a2 * a2);
+          hel = sl * sl * q_;
+          her = sr * sr * q_;
+        }
+      }
+    }
+    if (store) {
+      const long xk = xc + (long)(k - 1) * lev;
+      hel3[xk] = hel;
+      her3[xk] = her;
+    }
+    __syncthreads();   // everybody is done with this level's tiles
+  }
+}
+
 // arctic swap of hel/her after their halo update (mod_cppm.F90:1531-1541, :1686-1703)
 template <int DIR>
 __global__ void cppm_swap_edges(Geom g, bool fold_fix, int hw /* 4 nosc, 3 mono (:1848, :2015) */, double* hel3,
@@ -1005,10 +1146,24 @@ void cppm_pass(bool second_pass, int n, int mm, double* dp_src, double* dp_dst, 
   const double* cac = c.dev(DIR == 0 ? "cav" : "cau");
   const double* scp2i = c.dev("scp2i");
   if (!PC) {   // full compatibility stages the limited thickness edges (:1493-1541)
-    dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
-    auto hk = cppm_hedges<DIR, MONO>;
-    LAUNCH_NAMED(DIR == 0 ? "cppm_hedges<i>" : "cppm_hedges<j>", hk, grid, 128, 0, g,
-                 second_pass, dp_src, cac, scp2i, tab, hel3, her3);
+    if (c.option("hedges_form", "tile") == "flat") {
+      dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
+      auto hk = cppm_hedges<DIR, MONO>;
+      LAUNCH_NAMED(DIR == 0 ? "cppm_hedges<i>" : "cppm_hedges<j>", hk, grid, 128, 0, g,
+                   second_pass, dp_src, cac, scp2i, tab, hel3, her3);
+    } else {
+      constexpr int TPO = DIR == 0 ? 128 : 16, TC = DIR == 0 ? 2 : 32;
+      dim3 block = DIR == 0 ? dim3(TPO, TC) : dim3(TC, TPO);
+      dim3 grid = DIR == 0 ? dim3(cdiv(g.ii, TPO), cdiv(g.jj, TC), 1) : dim3(cdiv(g.ii, TC), cdiv(g.jj, TPO), 1);
+      // level chunks: ~8 waves of the 148 SMs when the tile count alone does not provide them
+      const long tiles = (long)grid.x * grid.y;
+      const int nz = (int)std::min<long>(std::max<long>(1, (148L * 8 * 8 + tiles - 1) / tiles), std::max(1, g.kdm / 4));
+      const int kchunk = cdiv(g.kdm, nz);
+      grid.z = cdiv(g.kdm, kchunk);
+      auto hk = cppm_hedges_tile<DIR, MONO, TPO, TC>;
+      LAUNCH_NAMED(DIR == 0 ? "cppm_hedges<i>" : "cppm_hedges<j>", hk, grid, block, 0, g,
+                   second_pass, kchunk, dp_src, cac, scp2i, tab, hel3, her3);
+    }
     halo_update(std::vector<HaloReq>{{hel3, g.kdm, halo_ps}, {her3, g.kdm, halo_ps}}, mh, nh);
     if (g.nreg == 2 && g.north) {
       const int nrow = DIR == 0 ? 1 : 1 + hw;

@@ -1,0 +1,45 @@
+"""Development aid: per-routine error growth of the performance (FMA) build against the oracle on a
+small case; prints, for each routine, the worst field, where it is and how thick the layer is there.
+usage: python tools/smoke_diag.py [config] [parity 0|1]"""
+import sys
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import numpy as np
+from util import Case, interior
+from blom_b200.driver import available_routines, STEP_SEQUENCE
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "fuk95"
+parity = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False
+c = Case(cfg, ntr=1, nstep=1)
+o = c.new_oracle(); g = c.new_gpu(parity=parity)
+for b in (o, g):
+    b.inieos(); b.numerical_bounds(); b.init_cppm()
+m, n, mm, nn, k1m, k1n = c.levels
+kk = c.dims[2]
+for r in [r for r in STEP_SEQUENCE if r in available_routines()]:
+    for b in (o, g):
+        if r == "tmsmt1":
+            b.tmsmt1(nn)
+        elif r == "tmsmt2":
+            b.tmsmt2(m, mm, nn, k1m)
+        else:
+            getattr(b, r)(m, n, mm, nn, k1m, k1n)
+    g.download_all()
+    rows = []
+    for nm, a in g.arrays.items():
+        if a.dtype != np.float64 or nm == "depths":
+            continue
+        A, B = interior(a), interior(o.arrays[nm])
+        d = np.abs(A - B)
+        s = np.abs(B).max()
+        if s == 0 or not np.isfinite(d).all():
+            continue
+        e = d.max() / s
+        if e > 1e-12:
+            idx = np.unravel_index(np.argmax(d), d.shape)
+            extra = ""
+            if nm in ("temp", "saln", "trc") and idx[0] < 2 * kk:
+                extra = f" dp_there={interior(o.arrays['dp'])[idx]:.3e} val={B[idx]:.6g} got={A[idx]:.6g}"
+            rows.append((e, nm, idx, extra))
+    rows.sort(reverse=True)
+    print(f"{r:12s}", "; ".join(f"{nm} {e:.2e} @{idx}{x}" for e, nm, idx, x in rows[:4]) or "all <= 1e-12", flush=True)
+g.finalize()
