@@ -64,7 +64,9 @@ def build(verbose: bool = False, force: bool = False) -> list[Path]:
         objs = [str(BUILD / f"{tag}_{s.stem}.o") for s in sources]
         out = HERE / lib
         if force or jobs or not out.exists():
-            cmd = [NVCC, *ARCH, "-shared", "-ccbin", "/usr/bin/g++", "-o", str(out), *objs,
+            # -Bsymbolic: references to the library's own symbols bind inside the library, whatever
+            # else the process has loaded (e.g. the other flavour of this library)
+            cmd = [NVCC, *ARCH, "-shared", "-ccbin", "/usr/bin/g++", "-Xlinker", "-Bsymbolic", "-o", str(out), *objs,
                    "-lcudart", "-ldl"]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:

@@ -31,7 +31,22 @@ struct Geom {
   long lev;         // elements per level = ldi*ldj
   int rank, nranks; // j-band decomposition
   int south, north; // 1 if this tile touches the global southern / northern edge
+  int lf;           // 1: level-parallel kernels are launched with the level as the fastest block index
 };
+
+// Block order of the level-parallel kernels (one block = 128 cells of a row at one level).  With the
+// plain order (i-block, j, k) a launch sweeps the whole horizontal plane once per level, so the 2-D
+// operands of a kernel (masks, metrics, barotropic parts: 10-30 arrays of 13 MB each at tnx0.25v4,
+// more than the 126 MB L2) are streamed from HBM again for every level.  With g.lf the grid is
+// launched as (k, i-block, j): the blocks of one row segment run back to back through the levels and
+// take the 2-D operands from L1/L2; only the 3-D fields stream.  Kernels read their block coordinates
+// through bid(g) and launches permute the grid with lgrid(g, grid).
+struct Bid { int x, y, z; };
+__device__ __forceinline__ Bid bid(const Geom& g) {
+  return g.lf ? Bid{(int)blockIdx.y, (int)blockIdx.z, (int)blockIdx.x}
+              : Bid{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z};
+}
+inline dim3 lgrid(const Geom& g, dim3 grid) { return g.lf ? dim3(grid.z, grid.x, grid.y) : grid; }
 
 __host__ __device__ __forceinline__ long ix2(const Geom& g, int i, int j) {
   return (long)(j + g.nb - 1) * g.ldi + (i + g.nb - 1);

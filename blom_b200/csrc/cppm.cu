@@ -284,8 +284,9 @@ __global__ void advect_flux_area(Geom g, int m, int mm, int nn, double delt1, do
                                  const double* __restrict__ scuy, const double* __restrict__ scvx,
                                  const double* __restrict__ umax, const double* __restrict__ vmax,
                                  double* __restrict__ cau, double* __restrict__ cav) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int j = blockIdx.y + 1, k = blockIdx.z + 1;
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x + 1;
+  const int j = b_.y + 1, k = b_.z + 1;
   if (i > g.ii) return;
   const long x = ix2(g, i, j);
   const long xm = x + (long)(k + mm - 1) * g.lev, xn = x + (long)(k + nn - 1) * g.lev;
@@ -1259,7 +1260,7 @@ void advect_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   const std::string advmth = c.option("advmth", "cppm");
   if (advmth != "cppm" && advmth != "remap") throw std::runtime_error(" advmth = " + advmth + " is unsupported!");
   if (advmth == "cppm" && !c.has("cppm_tab_i")) throw std::runtime_error("advect: init_cppm has not been called");
-  dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
+  const dim3 grid = lgrid(g, dim3(cdiv(g.ii, 128), g.jj, g.kdm));
   LAUNCH(advect_flux_area, grid, 128, 0, g, m, mm, nn, c.scalar("delt1"), c.scalar("dlt"), c.idev("iu"),
          c.idev("iv"), c.dev("u"), c.dev("v"), c.dev("dpu"), c.dev("dpv"), c.dev("ubflxs_p"),
          c.dev("vbflxs_p"), c.dev("pbu"), c.dev("pbv"), c.dev("umfltd"), c.dev("vmfltd"),

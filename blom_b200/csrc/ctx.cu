@@ -100,6 +100,7 @@ static void do_init(const int* dims, const int* tile, int device) {
   g.ldi = g.idm + 2 * g.nb; g.ldj = g.jdm + 2 * g.nb;
   g.lev = (long)g.ldi * g.ldj;
   g.south = (g.j0 == 0); g.north = (g.j0 + g.jj == g.jtdm);
+  g.lf = 1;
   c.device = device;
   if (!c.stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   c.red_cap = 1 << 16;
@@ -189,16 +190,21 @@ static int not_impl(const char* what) {
   return 2;
 }
 
-extern "C" {
-
-const char* blomgpu_last_error(void) { return g_err; }
-int blomgpu_parity_build(void) {
+// External-linkage C++ function behind blomgpu_parity_build(): if another flavour of this library
+// were allowed to interpose the internal calls, the entry point would report the other flavour
+// (tests/test_abi.py::test_flavours_are_isolated).
+int build_flavour() {
 #ifdef BLOM_PARITY_BUILD
   return 1;
 #else
   return 0;
 #endif
 }
+
+extern "C" {
+
+const char* blomgpu_last_error(void) { return g_err; }
+int blomgpu_parity_build(void) { return build_flavour(); }
 int blomgpu_init(const int dims[8], const int tile[6], int device) { GUARD(do_init(dims, tile, device)) }
 int blomgpu_finalize(void) { GUARD(do_finalize()) }
 
@@ -221,7 +227,12 @@ int blomgpu_device_ptr(const char* name, void** dptr, int* nlev) {
     })
 }
 
-int blomgpu_set_option(const char* key, const char* value) { GUARD(C().opt[key] = value) }
+int blomgpu_set_option(const char* key, const char* value) {
+  GUARD(
+    C().opt[key] = value;
+    // block order of the level-parallel kernels: "level" (default, level fastest) or "plane"
+    if (std::string(key) == "grid_order") C().g.lf = std::string(value) == "plane" ? 0 : 1)
+}
 int blomgpu_set_scalar(const char* key, double value) { GUARD(C().sc[key] = value) }
 int blomgpu_get_scalar(const char* key, double* value) { GUARD(*value = C().scalar(key)) }
 

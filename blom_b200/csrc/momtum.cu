@@ -177,8 +177,9 @@ __device__ __forceinline__ double ke_at(const Geom& g, const MtP& P, int i, int 
 
 // ---- stage 1: auxiliary velocities, del2, tension --------------------------------------------
 __global__ void mt_aux(Geom g, MtP P) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x - 1;  // -1..ii+2
-  const int j = (int)blockIdx.y - 1, k = blockIdx.z + 1;    // -1..jj+2
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x - 1;  // -1..ii+2
+  const int j = b_.y - 1, k = b_.z + 1;    // -1..jj+2
   if (i > g.ii + 2) return;
   const long x = ix2(g, i, j), xk = x + (long)(k - 1) * g.lev;
   if (i >= 0 && P.iu[x] == 1) {
@@ -208,8 +209,9 @@ __global__ void mt_aux(Geom g, MtP P) {
 
 // ---- stage 2: q-point gather ---------------------------------------------------------------------
 __global__ void mt_vort(Geom g, MtP P) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..ii+2
-  const int j = blockIdx.y, k = blockIdx.z + 1;         // 0..jj+2
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x;  // 0..ii+2
+  const int j = b_.y, k = b_.z + 1;         // 0..jj+2
   if (i > g.ii + 2) return;
   const long x = ix2(g, i, j), s = g.ldi, xk = x + (long)(k - 1) * g.lev;
   const double* dpm = P.dp + (long)(k + P.mm - 1) * g.lev;
@@ -275,8 +277,9 @@ __global__ void mt_vort(Geom g, MtP P) {
 
 // ---- stage 3: viscosities (:829-841, :988-1000) ---------------------------------------------------
 __global__ void mt_visc(Geom g, MtP P) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..ii+1
-  const int j = blockIdx.y, k = blockIdx.z + 1;         // 0..jj+1
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x;  // 0..ii+1
+  const int j = b_.y, k = b_.z + 1;         // 0..jj+1
   if (i > g.ii + 1) return;
   const long x = ix2(g, i, j), s = g.ldi, xk = x + (long)(k - 1) * g.lev;
   if (P.iu[x] == 1) {
@@ -371,8 +374,9 @@ __device__ __forceinline__ void vh_minmax(const Geom& g, const MtP& P, int i, in
 
 // ---- stage 3b: longitudinal stress fluxes at mass points (:858-873, :1017-1032) ------------------------
 __global__ void mt_flux1(Geom g, MtP P) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..ii
-  const int j = blockIdx.y, k = blockIdx.z + 1;         // 0..jj
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x;  // 0..ii
+  const int j = b_.y, k = b_.z + 1;         // 0..jj
   if (i > g.ii) return;
   const long xk = ix2(g, i, j) + (long)(k - 1) * g.lev;
   if (j >= 1) P.uflux1[xk] = uflux1_at(g, P, i, j, k);
@@ -382,7 +386,8 @@ __global__ void mt_flux1(Geom g, MtP P) {
 // ---- stage 4: tendencies and leap-frog update ------------------------------------------------------
 __global__ void __launch_bounds__(128)
 mt_update(Geom g, MtP P) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1, k = blockIdx.z + 1;
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x + 1, j = b_.y + 1, k = b_.z + 1;
   if (i > g.ii) return;
   const long x = ix2(g, i, j), s = g.ldi, L = g.lev;
   const long xk = x + (long)(k - 1) * L, xm = x + (long)(k + P.mm - 1) * L, xn = x + (long)(k + P.nn - 1) * L;
@@ -452,7 +457,8 @@ mt_update(Geom g, MtP P) {
 }
 __global__ void __launch_bounds__(128)
 mt_update_v(Geom g, MtP P) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1, k = blockIdx.z + 1;
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x + 1, j = b_.y + 1, k = b_.z + 1;
   if (i > g.ii) return;
   const long x = ix2(g, i, j), s = g.ldi, L = g.lev;
   const long xk = x + (long)(k - 1) * L, xm = x + (long)(k + P.mm - 1) * L, xn = x + (long)(k + P.nn - 1) * L;
@@ -891,63 +897,77 @@ mt_level(Geom g, MtP P) {
 }
 
 // ---- stage 5: column pass (:1154-1267) ------------------------------------------------------------
+// The pointers of MtP carry no aliasing information, so a store to u would fence every later load of
+// dpu/su_n and the level loop would run as one memory round trip per level (ncu: 25 long-scoreboard
+// stall cycles per issue).  col_velocity takes the column's arrays as __restrict__ parameters and the
+// operands of four levels are fetched into registers before the four levels are computed, so the
+// loads of a batch go out together.
+__device__ __forceinline__ void col_velocity(long x, long L, int kdm, int mm, int nn, double delt1, double vmx,
+                                             double vbm, double pbp, const double* __restrict__ dpf,
+                                             const double* __restrict__ s_n, const double* __restrict__ s_m,
+                                             const double* __restrict__ dpold, double* __restrict__ vel,
+                                             double* __restrict__ pf, double* __restrict__ totn) {
+  constexpr int B = 4;   // levels whose operands are fetched together
+  double tot = 0., vprev = 0.;
+  for (int k0 = 1; k0 <= kdm; k0 += B) {
+    double dm[B], dn[B], sn[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const int k = min(k0 + b, kdm);
+      dm[b] = dpf[x + (long)(k + mm - 1) * L]; dn[b] = dpf[x + (long)(k + nn - 1) * L];
+      sn[b] = s_n[x + (long)(k - 1) * L];
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const int k = k0 + b;
+      if (k <= kdm) {
+        const double q = fmin(fmin(dm[b], dn[b]), onem);
+        double vn = sn[b];
+        const double va = k == 1 ? vn : vprev;  // kan = max(1,k-1)+nn
+        vn = (vn * q + va * (onem - q)) / onem;
+        vn = fmax(-vmx, fmin(vmx, vn + vbm)) - vbm;
+        vel[x + (long)(k + nn - 1) * L] = vn;
+        vprev = vn;
+        tot = tot + vn * dn[b];
+      }
+    }
+  }
+  tot = tot / pbp;
+  double pk = pf[x];
+  for (int k0 = 1; k0 <= kdm; k0 += B) {
+    double dm[B], dn[B], sm[B], dold[B], vo[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const int k = min(k0 + b, kdm);
+      dm[b] = dpf[x + (long)(k + mm - 1) * L]; dn[b] = dpf[x + (long)(k + nn - 1) * L];
+      sm[b] = s_m[x + (long)(k - 1) * L]; dold[b] = dpold[x + (long)(k - 1) * L];
+      vo[b] = vel[x + (long)(k + nn - 1) * L];
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const int k = k0 + b;
+      if (k <= kdm) {
+        const double vn = vo[b] - tot;
+        vel[x + (long)(k + nn - 1) * L] = vn;
+        vel[x + (long)(k + mm - 1) * L] = (sm[b] + vn * WUV2 * dn[b]) / (WUV1 * dm[b] + onemm + WUV2 * (dold[b] + dn[b]));
+        pk = pk + dn[b];
+        pf[x + (long)k * L] = pk;
+      }
+    }
+  }
+  totn[x] = tot * (1. / delt1);
+}
+
 __global__ void mt_column(Geom g, MtP P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
   if (i > g.ii) return;
   const long x = ix2(g, i, j), L = g.lev, m2 = (long)(P.m - 1) * L;
-  const double dt1inv = 1. / P.delt1;
-  if (P.iu[x] == 1) {
-    const double umx = P.umax[x], ubm = P.ub[x + m2];
-    double tot = 0., uprev = 0.;
-    for (int k = 1; k <= g.kdm; ++k) {
-      const long xm = x + (long)(k + P.mm - 1) * L, xn = x + (long)(k + P.nn - 1) * L;
-      const double q = fmin(fmin(P.dpu[xm], P.dpu[xn]), onem);
-      double un = P.su_n[x + (long)(k - 1) * L];
-      const double ua = k == 1 ? un : uprev;  // kan = max(1,k-1)+nn
-      un = (un * q + ua * (onem - q)) / onem;
-      un = fmax(-umx, fmin(umx, un + ubm)) - ubm;
-      P.u[xn] = un;
-      uprev = un;
-      tot = tot + un * P.dpu[xn];
-    }
-    tot = tot / P.pbu_p[x];
-    double pk = P.pu[x];
-    for (int k = 1; k <= g.kdm; ++k) {
-      const long xm = x + (long)(k + P.mm - 1) * L, xn = x + (long)(k + P.nn - 1) * L, xk = x + (long)(k - 1) * L;
-      const double un = P.u[xn] - tot;
-      P.u[xn] = un;
-      P.u[xm] = (P.su_m[xk] + un * WUV2 * P.dpu[xn]) / (WUV1 * P.dpu[xm] + onemm + WUV2 * (P.dpuold[xk] + P.dpu[xn]));
-      pk = pk + P.dpu[xn];
-      P.pu[x + (long)k * L] = pk;
-    }
-    P.utotn[x] = tot * dt1inv;
-  }
-  if (P.iv[x] == 1) {
-    const double vmx = P.vmax[x], vbm = P.vb[x + m2];
-    double tot = 0., vprev = 0.;
-    for (int k = 1; k <= g.kdm; ++k) {
-      const long xm = x + (long)(k + P.mm - 1) * L, xn = x + (long)(k + P.nn - 1) * L;
-      const double q = fmin(fmin(P.dpv[xm], P.dpv[xn]), onem);
-      double vn = P.sv_n[x + (long)(k - 1) * L];
-      const double va = k == 1 ? vn : vprev;
-      vn = (vn * q + va * (onem - q)) / onem;
-      vn = fmax(-vmx, fmin(vmx, vn + vbm)) - vbm;
-      P.v[xn] = vn;
-      vprev = vn;
-      tot = tot + vn * P.dpv[xn];
-    }
-    tot = tot / P.pbv_p[x];
-    double pk = P.pv[x];
-    for (int k = 1; k <= g.kdm; ++k) {
-      const long xm = x + (long)(k + P.mm - 1) * L, xn = x + (long)(k + P.nn - 1) * L, xk = x + (long)(k - 1) * L;
-      const double vn = P.v[xn] - tot;
-      P.v[xn] = vn;
-      P.v[xm] = (P.sv_m[xk] + vn * WUV2 * P.dpv[xn]) / (WUV1 * P.dpv[xm] + onemm + WUV2 * (P.dpvold[xk] + P.dpv[xn]));
-      pk = pk + P.dpv[xn];
-      P.pv[x + (long)k * L] = pk;
-    }
-    P.vtotn[x] = tot * dt1inv;
-  }
+  if (P.iu[x] == 1)
+    col_velocity(x, L, g.kdm, P.mm, P.nn, P.delt1, P.umax[x], P.ub[x + m2], P.pbu_p[x], P.dpu, P.su_n, P.su_m,
+                 P.dpuold, P.u, P.pu, P.utotn);
+  if (P.iv[x] == 1)
+    col_velocity(x, L, g.kdm, P.mm, P.nn, P.delt1, P.vmax[x], P.vb[x + m2], P.pbv_p[x], P.dpv, P.sv_n, P.sv_m,
+                 P.dpvold, P.v, P.pv, P.vtotn);
 }
 
 }  // namespace
@@ -1009,11 +1029,11 @@ void momtum_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     LAUNCH_NAMED("mt_level", (mt_level<TX, TY>), grid, T::NT, T::bytes, g, P);
   } else {
     // staged form (default): one launch per stage, layer-sized scratch arrays in HBM
-    { dim3 grid(cdiv(g.ii + 4, 128), g.jj + 4, g.kdm); LAUNCH(mt_aux, grid, 128, 0, g, P); }
-    { dim3 grid(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm); LAUNCH(mt_vort, grid, 128, 0, g, P); }
-    { dim3 grid(cdiv(g.ii + 2, 128), g.jj + 2, g.kdm); LAUNCH(mt_visc, grid, 128, 0, g, P); }
-    { dim3 grid(cdiv(g.ii + 1, 128), g.jj + 1, g.kdm); LAUNCH(mt_flux1, grid, 128, 0, g, P); }
-    { dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
+    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 4, 128), g.jj + 4, g.kdm)); LAUNCH(mt_aux, grid, 128, 0, g, P); }
+    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm)); LAUNCH(mt_vort, grid, 128, 0, g, P); }
+    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 2, 128), g.jj + 2, g.kdm)); LAUNCH(mt_visc, grid, 128, 0, g, P); }
+    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 1, 128), g.jj + 1, g.kdm)); LAUNCH(mt_flux1, grid, 128, 0, g, P); }
+    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii, 128), g.jj, g.kdm));
       LAUNCH(mt_update, grid, 128, 0, g, P);
       LAUNCH(mt_update_v, grid, 128, 0, g, P); }
   }

@@ -111,11 +111,12 @@ pbcor_update(Geom g, eos::Coef ec, int ks, int kf, int kchunk, const int* __rest
              double* __restrict__ vsflx, double* __restrict__ vtflx, double* __restrict__ dpB,
              double* __restrict__ tB, double* __restrict__ sB, double* __restrict__ sigma, PbTr T) {
   const double dpeps1 = 1.e-5, dpeps2 = 1.e-7;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;  // 1..ii+1, 1..jj+1
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x + 1, j = b_.y + 1;  // 1..ii+1, 1..jj+1
   if (i > g.ii + 1) return;
   const long x = ix2(g, i, j), lev = g.lev, s = g.ldi;
   const int kk = g.kdm;
-  const int k0 = blockIdx.z * kchunk + 1, k1 = min(kk, k0 + kchunk - 1);
+  const int k0 = b_.z * kchunk + 1, k1 = min(kk, k0 + kchunk - 1);
   const bool uok = j <= g.jj, vok = i <= g.ii;
   const bool cell = uok && vok && ip[x] == 1;
   FaceInv F[4];
@@ -261,7 +262,7 @@ void pbcor_run(int m, int n, int mm, int nn, int k1m) {
   }
   {
     const int kchunk = kk >= 16 ? 8 : kk;
-    dim3 grid(cdiv(g.ii + 1, 128), g.jj + 1, cdiv(kk, kchunk));
+    const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 1, 128), g.jj + 1, cdiv(kk, kchunk)));
     const char* nm = WHICH == 1 ? "pbcor_update<1>" : "pbcor_update<2>";
     const eos::Coef ec = WHICH == 2 ? eos::host_coef() : eos::Coef{};  // only pbcor2 refreshes sigma
     if (dluc)

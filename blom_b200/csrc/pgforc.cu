@@ -103,13 +103,23 @@ pg_dynh_march(Geom g, eos::Coef ec, int n, int nn, const int* __restrict__ ip, c
   double pk1 = col ? p[x + (long)kk * g.lev] : 0.;
   double tn = 0., sn = 0.;
   double a_pgfxm = 0., a_xixm = 0., a_xixp = 0., a_pgfym = 0., a_xiym = 0., a_xiyp = 0.;
+  // level operands are fetched one level ahead of the (EOS-heavy) computation that uses them
+  double t_f = 0., sa_f = 0., dpk_f = 0., pk_f = 0., gx_f = 0., du_f = 0., gy_f = 0., dv_f = 0.;
+  auto fetch = [&](int k) {
+    const long xn = x + (long)(k + nn - 1) * g.lev;
+    if (col) { t_f = temp[xn]; sa_f = saln[xn]; dpk_f = dp[xn]; pk_f = p[x + (long)(k - 1) * g.lev]; }
+    if (isu) { gx_f = pgfx[xn]; du_f = dpu[xn]; }
+    if (isv) { gy_f = pgfy[xn]; dv_f = dpv[xn]; }
+  };
+  fetch(kk);
   for (int k = kk; k >= 1; --k) {
     const int b = k & 1;
     const long xn = x + (long)(k + nn - 1) * g.lev, xk = x + (long)(k - 1) * g.lev;
     double t = 0., sa = 0., dyn_a = 0., dyn_t = 0., ar = 0., dpk = 0.;
+    const double pk = pk_f, gx = gx_f, du = du_f, gy = gy_f, dv = dv_f;
+    t = t_f; sa = sa_f; dpk = dpk_f;
+    if (k > 1) fetch(k - 1);
     if (col) {
-      t = temp[xn]; sa = saln[xn]; dpk = dp[xn];
-      const double pk = p[xk];
       if (k == kk) {
         pot = phik + eos::p_alpha(p0_dynh, pk1, t, sa);
         potpb = eos::alp(pk1, t, sa) * pk1;
@@ -137,9 +147,8 @@ pg_dynh_march(Geom g, eos::Coef ec, int n, int nn, const int* __restrict__ ip, c
       if (sm[b][6][ty][tx - 1] >= onemm && dpk >= onemm)
         f = f + .5 * ((sm[b][3][ty][tx - 1] + dyn_t) * (t - sm[b][5][ty][tx - 1]) +
                       (sm[b][2][ty][tx - 1] + dyn_a) * (ar - sm[b][4][ty][tx - 1]));
-      pgfx_o[xk] = pgfx[xn];
+      pgfx_o[xk] = gx;
       pgfx[xn] = f;
-      const double du = dpu[xn];
       a_pgfxm = a_pgfxm + f * du;
       a_xixm = a_xixm + potpb_w * du;
       a_xixp = a_xixp + potpb * du;
@@ -150,9 +159,8 @@ pg_dynh_march(Geom g, eos::Coef ec, int n, int nn, const int* __restrict__ ip, c
       if (sm[b][6][ty - 1][tx] >= onemm && dpk >= onemm)
         f = f + .5 * ((sm[b][3][ty - 1][tx] + dyn_t) * (t - sm[b][5][ty - 1][tx]) +
                       (sm[b][2][ty - 1][tx] + dyn_a) * (ar - sm[b][4][ty - 1][tx]));
-      pgfy_o[xk] = pgfy[xn];
+      pgfy_o[xk] = gy;
       pgfy[xn] = f;
-      const double dv = dpv[xn];
       a_pgfym = a_pgfym + f * dv;
       a_xiym = a_xiym + potpb_s * dv;
       a_xiyp = a_xiyp + potpb * dv;

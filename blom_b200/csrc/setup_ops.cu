@@ -37,8 +37,9 @@ __global__ void nb_umax(Geom g, double baclin, const int* __restrict__ ip, const
 __global__ void zero_fluxes(Geom g, int mm, const int* __restrict__ iu, const int* __restrict__ iv,
                             double* __restrict__ uflx, double* __restrict__ utflx, double* __restrict__ usflx,
                             double* __restrict__ vflx, double* __restrict__ vtflx, double* __restrict__ vsflx) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..ii+2
-  const int j = blockIdx.y, k = blockIdx.z + 1;         // 0..jj+2
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x;  // 0..ii+2
+  const int j = b_.y, k = b_.z + 1;         // 0..jj+2
   if (i > g.ii + 2) return;
   const long x = ix2(g, i, j), xm = x + (long)(k + mm - 1) * g.lev;
   if (iu[x] == 1) { uflx[xm] = 0.; utflx[xm] = 0.; usflx[xm] = 0.; }
@@ -122,7 +123,7 @@ void numerical_bounds_dev() {
 void init_fluxes_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   (void)m; (void)n; (void)k1m; (void)k1n;
   Ctx& c = C(); const Geom& g = c.g;
-  dim3 grid(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm);
+  const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm));
   LAUNCH(zero_fluxes, grid, 128, 0, g, mm, c.idev("iu"), c.idev("iv"), c.dev("uflx"), c.dev("utflx"), c.dev("usflx"),
          c.dev("vflx"), c.dev("vtflx"), c.dev("vsflx"));
   const long on = (long)nn * g.lev;

@@ -56,8 +56,9 @@ __global__ void diffus_flux(Geom g, double delt1, int mm, int nn, const int* __r
                             double* __restrict__ utflx, double* __restrict__ vsflx,
                             double* __restrict__ vtflx, TrcPtrs T) {
   const double dpeps = 1.e-5;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..ii+2
-  const int j = blockIdx.y, k = blockIdx.z + 1;         // j 0..jj+2
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x;  // 0..ii+2
+  const int j = b_.y, k = b_.z + 1;         // j 0..jj+2
   if (i > g.ii + 2) return;
   const long x = ix2(g, i, j);
   const long xn = x + (long)(k + nn - 1) * g.lev, xm = x + (long)(k + mm - 1) * g.lev;
@@ -101,8 +102,9 @@ __global__ void diffus_update(Geom g, eos::Coef ec, int mm, int nn, const int* _
                               const double* __restrict__ utflld, const double* __restrict__ vsflld,
                               const double* __restrict__ vtflld, TrcPtrs T) {
   const double dpeps = 1.e-5;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..ii+1
-  const int j = blockIdx.y, k = blockIdx.z + 1;         // 0..jj+1
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x;  // 0..ii+1
+  const int j = b_.y, k = b_.z + 1;         // 0..jj+1
   if (i > g.ii + 1) return;
   const long x = ix2(g, i, j);
   if (ip[x] != 1) return;
@@ -128,8 +130,9 @@ __global__ void tmsmt1_kernel(Geom g, int nn, bool isopyc, const int* __restrict
                               const double* __restrict__ trc, double* __restrict__ trcold,
                               const double* __restrict__ dpu, const double* __restrict__ dpv,
                               double* __restrict__ dpuold, double* __restrict__ dpvold) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int j = blockIdx.y + 1, k = blockIdx.z + 1;
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x + 1;
+  const int j = b_.y + 1, k = b_.z + 1;
   if (i > g.ii) return;
   const long x = ix2(g, i, j);
   const long xn = x + (long)(k + nn - 1) * g.lev, xk = x + (long)(k - 1) * g.lev;
@@ -203,8 +206,9 @@ __global__ void p_from_dp(Geom g, int mm, int halo, const int* __restrict__ ip, 
 
 __global__ void dpuv_from_p(Geom g, int mm, const int* __restrict__ iu, const int* __restrict__ iv,
                             const double* __restrict__ p, double* __restrict__ dpu, double* __restrict__ dpv) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x - 1;  // -1..ii+2
-  const int j = (int)blockIdx.y - 1, k = blockIdx.z + 1;    // -1..jj+2
+  const Bid b_ = bid(g);
+  const int i = b_.x * blockDim.x + threadIdx.x - 1;  // -1..ii+2
+  const int j = b_.y - 1, k = b_.z + 1;    // -1..jj+2
   if (i > g.ii + 2) return;
   const long x = ix2(g, i, j), s = g.ldi;
   const long xb = x + (long)g.kdm * g.lev, x0 = x + (long)(k - 1) * g.lev, x1 = x0 + g.lev;
@@ -248,14 +252,14 @@ void diffus_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   halo_update(reqs, 2, 2);
   TrcPtrs T = trc_ptrs(true);
   {
-    dim3 grid(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm);
+    const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm));
     LAUNCH(diffus_flux, grid, 128, 0, g, c.scalar("delt1"), mm, nn, c.idev("iu"), c.idev("iv"), c.dev("dp"),
            c.dev("temp"), c.dev("saln"), c.dev("difiso"), c.dev("scuy"), c.dev("scuxi"), c.dev("scvx"),
            c.dev("scvyi"), c.dev("usflld"), c.dev("utflld"), c.dev("vsflld"), c.dev("vtflld"), c.dev("usflx"),
            c.dev("utflx"), c.dev("vsflx"), c.dev("vtflx"), T);
   }
   {
-    dim3 grid(cdiv(g.ii + 2, 128), g.jj + 2, g.kdm);
+    const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 2, 128), g.jj + 2, g.kdm));
     LAUNCH(diffus_update, grid, 128, 0, g, eos::host_coef(), mm, nn, c.idev("ip"), c.dev("dp"), c.dev("temp"),
            c.dev("saln"), c.dev("sigma"), c.dev("scp2"), c.dev("usflld"), c.dev("utflld"), c.dev("vsflld"),
            c.dev("vtflld"), T);
@@ -265,7 +269,7 @@ void diffus_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
 void tmsmt1_dev(int nn) {
   Ctx& c = C(); const Geom& g = c.g;
   const bool isopyc = c.option("vcoord", "cntiso_hybrid") == "isopyc_bulkml";
-  dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
+  const dim3 grid = lgrid(g, dim3(cdiv(g.ii, 128), g.jj, g.kdm));
   LAUNCH(tmsmt1_kernel, grid, 128, 0, g, nn, isopyc, c.idev("ip"), c.idev("iu"), c.idev("iv"), c.dev("dp"),
          c.dev("temp"), c.dev("saln"), c.dev("dpold"), c.dev("told"), c.dev("sold"),
          g.ntr ? c.dev("trc") : nullptr, g.ntr ? c.dev("trcold") : nullptr, isopyc ? c.dev("dpu") : nullptr,
@@ -287,7 +291,7 @@ void tmsmt2_dev(int m, int mm, int nn, int k1m) {
     LAUNCH(p_from_dp, grid, 128, 0, g, mm, 2, c.idev("ip"), c.dev("dp"), c.dev("p"));
   }
   if (c.option("vcoord", "cntiso_hybrid") == "isopyc_bulkml") {
-    dim3 grid(cdiv(g.ii + 4, 128), g.jj + 4, g.kdm);
+    const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 4, 128), g.jj + 4, g.kdm));
     LAUNCH(dpuv_from_p, grid, 128, 0, g, mm, c.idev("iu"), c.idev("iv"), c.dev("p"), c.dev("dpu"), c.dev("dpv"));
   }
 }

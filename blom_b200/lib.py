@@ -56,7 +56,10 @@ def load_library(parity: bool = False) -> C.CDLL:
         raise BlomGpuError(
             f"{path} is missing: build it with `python -m blom_b200.build` "
             "(the hot path has no CPU fallback)")
-    lib = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
+    # RTLD_LOCAL, and the libraries are linked with -Bsymbolic: the two flavours export the same C++
+    # symbols, and with a global scope the flavour loaded first would serve the internal calls of
+    # the other (its blomgpu_* entry points would launch the other flavour's kernels)
+    lib = C.CDLL(str(path), mode=C.RTLD_LOCAL)
     lib.blomgpu_last_error.restype = C.c_char_p
     lib.blomgpu_launch_count.restype = C.c_long
     lib.blomgpu_stream.restype = C.c_void_p

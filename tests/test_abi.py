@@ -35,6 +35,23 @@ def test_exports_every_declared_symbol(parity):
     assert lib.blomgpu_parity_build() == (1 if parity else 0)
 
 
+def test_flavours_are_isolated():
+    """Both flavours export the same C++ symbols.  Loaded into one process (as the tests and smoke()
+    do) each must keep calling its own code: RTLD_LOCAL + -Bsymbolic.  blomgpu_parity_build() goes
+    through an external-linkage C++ function, so interposition would show up as the wrong answer."""
+    _ensure_built()
+    import subprocess
+    for order in ((False, True), (True, False)):
+        code = ("import ctypes,sys; sys.path.insert(0, %r); from blom_b200 import lib as b; "
+                "a = b.load_library(%r); c = b.load_library(%r); "
+                "print(a.blomgpu_parity_build(), c.blomgpu_parity_build())" % (str(ROOT), order[0], order[1]))
+        out = subprocess.run(["python", "-c", code], capture_output=True, text=True, check=True).stdout.split()
+        assert out == [str(int(order[0])), str(int(order[1]))], (order, out)
+    for parity in (False, True):
+        dyn = subprocess.run(["readelf", "-d", str(blib.library_path(parity))], capture_output=True, text=True).stdout
+        assert "SYMBOLIC" in dyn
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():

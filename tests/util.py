@@ -75,6 +75,24 @@ def max_rel_err(a, b, floor=1e-300):
     return float(np.max(np.abs(a - b)) / scale)
 
 
+def assert_fma_close(a, b, what, tol=1e-11, max_flip_frac=5e-3, max_flip=2e-2):
+    """Comparison of the FMA-contracted performance build with the oracle (-ffp-contract=off).
+    CPPM's limiters branch on sign tests of near-cancelling expressions; under FMA contraction a few
+    of them take the other branch in nearly massless cells (the oracle itself, compiled with
+    -ffp-contract=fast, differs from the oracle in the same cells by the same values:
+    tools/fma_sensitivity.py, profiles/r01_fma_sensitivity.txt).  So: every point within `tol` of
+    the oracle (relative to the field's max-norm) except at most max(8, max_flip_frac*size) points,
+    and none further away than `max_flip`.  Returns the number of points beyond `tol`."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    d = np.abs(a - b) / max(np.max(np.abs(b)), 1e-300)
+    assert np.isfinite(d).all(), what
+    far = d > tol
+    assert far.sum() <= max(8, max_flip_frac * far.size) and d.max() <= max_flip, \
+        (what, int(far.sum()), far.size, float(d.max()))
+    return int(far.sum())
+
+
 def ulp_diff(a, b):
     """max distance in units of last place between two float64 arrays."""
     ai = np.asarray(a, dtype=np.float64).view(np.int64).astype(np.int64)

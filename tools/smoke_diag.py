@@ -1,6 +1,6 @@
 """Development aid: per-routine error growth of the performance (FMA) build against the oracle on a
 small case; prints, for each routine, the worst field, where it is and how thick the layer is there.
-usage: python tools/smoke_diag.py [config] [parity 0|1]"""
+usage: python tools/smoke_diag.py [config] [parity 0|1] [each|end]"""
 import sys
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np
@@ -9,6 +9,7 @@ from blom_b200.driver import available_routines, STEP_SEQUENCE
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "fuk95"
 parity = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False
+sync_each = (sys.argv[3] != "end") if len(sys.argv) > 3 else True   # "end": download only after the last routine
 c = Case(cfg, ntr=1, nstep=1)
 o = c.new_oracle(); g = c.new_gpu(parity=parity)
 for b in (o, g):
@@ -23,6 +24,8 @@ for r in [r for r in STEP_SEQUENCE if r in available_routines()]:
             b.tmsmt2(m, mm, nn, k1m)
         else:
             getattr(b, r)(m, n, mm, nn, k1m, k1n)
+    if not sync_each and r != "tmsmt2":
+        continue
     g.download_all()
     rows = []
     for nm, a in g.arrays.items():
