@@ -346,7 +346,7 @@ def main():
     w0 = time.perf_counter()
     for _ in range(args.steps):
         hp.upload_inputs()
-        hp.advance()
+        hp.advance(early_download=True)   # u,v go back over PCIe while barotp/pbcor2/tmsmt2 run
         hp.download_outputs()
     g.sync()
     w1 = time.perf_counter()

@@ -74,6 +74,7 @@ struct Ctx {
   Geom g{};
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // blomgpu_download_async: D2H copies that overlap later kernels
   std::map<std::string, DField> f;
   std::map<std::string, IFieldD> fi;
   std::map<std::string, std::string> opt;

@@ -382,8 +382,9 @@ cppm_hedges(Geom g, bool second_pass, const double* __restrict__ dp /* level 1 o
 // Level-marching tile form of the thickness edges.  A block owns TPO cells along the pass direction
 // times TC across it and marches through a chunk of levels; per level the three stencil stages
 // (cell thickness hm -> edge values he -> curvature proxy d2h) flow through shared memory, so every
-// hm (one division on the second pass), he and d2h is evaluated once per tile instead of 7/4/3 times
-// per cell, and the static weights of a thread's own edge/cell stay in registers across the levels.
+// hm (one division on the second pass) and he is evaluated once per tile instead of 7/4 times per
+// cell (the three d2h of a cell are three multiply-adds, redone per cell to save a barrier), and the
+// static weights of a thread's own edge/cell stay in registers across the levels.
 // dp (and the cross flux areas) of level k+1 are fetched into registers while level k is computed.
 // Expressions and their order are those of cppm_hedges above, so both forms are bit-identical.
 template <int DIR, bool MONO, int TPO, int TC>
@@ -393,9 +394,10 @@ cppm_hedges_tile(Geom g, bool second_pass, int kchunk, const double* __restrict_
                  const double* __restrict__ tab, double* __restrict__ hel3, double* __restrict__ her3) {
   constexpr int NP = TPO + 6;              // staged cells along the pass: s0-3 .. s0+TPO+2
   constexpr int NE = TPO + 3;              // edges s0-1 .. s0+TPO+1
-  constexpr int ND = TPO + 2;              // d2h of cells s0-1 .. s0+TPO
   constexpr int NX = (NP + TPO - 1) / TPO; // staged cells per thread (2)
-  __shared__ double s_hm[NP * TC], s_he[NE * TC], s_d2[ND * TC];
+  // double buffered by level parity: a buffer is rewritten two levels later, after every thread has
+  // passed a barrier that follows its last read, so two barriers per level are enough
+  __shared__ double s_hm2[2][NP * TC], s_he2[2][NE * TC];
   const int tp = DIR == 0 ? threadIdx.x : threadIdx.y;
   const int tc = DIR == 0 ? threadIdx.y : threadIdx.x;
   auto sidx = [&](int p, int n) { return DIR == 0 ? tc * n + p : p * TC + tc; };
@@ -421,14 +423,15 @@ cppm_hedges_tile(Geom g, bool second_pass, int kchunk, const double* __restrict_
     ycell[r] = addr(s0 - 3 + min(q, NP - 1));
     ai[r] = second_pass ? scp2i[ycell[r]] : K0;
   }
-  // own edge r = tp (cell index s0-1+tp) and own d2h cell r' = tp (cell s0-1+tp)
+  // own edge r = tp (cell index s0-1+tp)
   const long ye = addr(s0 - 1 + tp);
   const double w1 = tab[T_HEVC1 * lev + ye], w2 = tab[T_HEVC2 * lev + ye], w3 = tab[T_HEVC3 * lev + ye],
-               w4 = tab[T_HEVC4 * lev + ye], d2m_e = tab[T_D2M * lev + ye];
-  // own cell c = s0+tp
+               w4 = tab[T_HEVC4 * lev + ye];
+  // own cell c = s0+tp and the curvature masks of c-1, c, c+1
   const int c = s0 + tp;
   const long xc = addr(c);
   const double ssc = tab[T_SSC * lev + xc], scc = tab[T_SCC * lev + xc];
+  const double d2m_l = tab[T_D2M * lev + ye], d2m_c = tab[T_D2M * lev + xc], d2m_r = tab[T_D2M * lev + addr(c + 1)];
   const bool store = c <= npass && cc <= ncross;
 
   double raw[NX], cp_[NX], cm_[NX];
@@ -444,6 +447,8 @@ cppm_hedges_tile(Geom g, bool second_pass, int kchunk, const double* __restrict_
   };
   fetch(k_first);
   for (int k = k_first; k <= k_last; ++k) {
+    double* s_hm = s_hm2[(k - k_first) & 1];
+    double* s_he = s_he2[(k - k_first) & 1];
     // ---- cell thickness of the staged cells ----
 #pragma unroll
     for (int r = 0; r < NX; ++r) {
@@ -466,18 +471,13 @@ cppm_hedges_tile(Geom g, bool second_pass, int kchunk, const double* __restrict_
                           tab[T_HEVC3 * lev + y] * s_hm[sidx(r + 2, NP)] + tab[T_HEVC4 * lev + y] * s_hm[sidx(r + 3, NP)];
     }
     __syncthreads();
-    // ---- curvature proxy ----
-    s_d2[sidx(tp, ND)] = d2m_e * (s_he[sidx(tp, NE)] - K2 * s_hm[sidx(tp + 2, NP)] + s_he[sidx(tp + 1, NE)]);
-    if (tp < ND - TPO) {
-      const int r = tp + TPO;
-      s_d2[sidx(r, ND)] = tab[T_D2M * lev + addr(s0 - 1 + r)] *
-                          (s_he[sidx(r, NE)] - K2 * s_hm[sidx(r + 2, NP)] + s_he[sidx(r + 1, NE)]);
-    }
-    __syncthreads();
-    // ---- limiter of the own cell ----
-    const double d2l = s_d2[sidx(tp, ND)], d2c = s_d2[sidx(tp + 1, ND)], d2r = s_d2[sidx(tp + 2, ND)];
+    // ---- curvature proxy of c-1, c, c+1 and limiter of the own cell ----
+    const double e0 = s_he[sidx(tp, NE)], e3 = s_he[sidx(tp + 3, NE)];
     double hel = s_he[sidx(tp + 1, NE)], her = s_he[sidx(tp + 2, NE)];
     const double hmm = s_hm[sidx(tp + 2, NP)], hm0 = s_hm[sidx(tp + 3, NP)], hmp = s_hm[sidx(tp + 4, NP)];
+    const double d2l = d2m_l * (e0 - K2 * hmm + hel);
+    const double d2c = d2m_c * (hel - K2 * hm0 + her);
+    const double d2r = d2m_r * (her - K2 * hmp + e3);
     double sl, sr, sc_, d, q_, r_, a2;
     if (MONO || d2l * d2c <= K0 || d2c * d2r <= K0) {
       sl = ssc * (hm0 - hmm);
@@ -516,7 +516,6 @@ cppm_hedges_tile(Geom g, bool second_pass, int kchunk, const double* __restrict_
       hel3[xk] = hel;
       her3[xk] = her;
     }
-    __syncthreads();   // everybody is done with this level's tiles
   }
 }
 

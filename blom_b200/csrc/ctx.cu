@@ -121,10 +121,11 @@ static void do_finalize() {
     if (c.halo_send[s]) cudaFree(c.halo_send[s]);
     if (c.halo_recv[s]) cudaFree(c.halo_recv[s]);
   }
-  cudaStream_t st = c.stream;
+  if (c.copy_stream) cudaStreamSynchronize(c.copy_stream);
+  cudaStream_t st = c.stream, cst = c.copy_stream;
   void* nccl = c.nccl;
   c = Ctx();
-  c.stream = st;
+  c.stream = st; c.copy_stream = cst;
   c.nccl = nccl;
 }
 
@@ -165,6 +166,30 @@ static void do_copy(const char* name, bool up) {
   size_t bytes = sizeof(int) * (size_t)c.g.lev * fd.nlev;
   if (up) CUDA_CHECK(cudaMemcpyAsync(fd.d, fd.h, bytes, cudaMemcpyHostToDevice, c.stream));
   else CUDA_CHECK(cudaMemcpyAsync(fd.h, fd.d, bytes, cudaMemcpyDeviceToHost, c.stream));
+}
+// Device -> host copy of a field that the remaining routines of the step no longer write, on a
+// second stream: it starts when everything enqueued so far on the library stream has finished and
+// overlaps the kernels enqueued afterwards.  blomgpu_sync() waits for it.
+static void do_download_async(const char* name) {
+  Ctx& c = C();
+  auto it = c.f.find(name);
+  if (it == c.f.end()) throw std::runtime_error(std::string("blomgpu: field not registered: ") + name);
+  DField& fd = it->second;
+  if (!fd.h) throw std::runtime_error(std::string("blomgpu: no host array bound to ") + name);
+  if (!c.copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  cudaEvent_t ev;
+  CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventRecord(ev, c.stream));
+  CUDA_CHECK(cudaStreamWaitEvent(c.copy_stream, ev, 0));
+  CUDA_CHECK(cudaEventDestroy(ev));   // released once the wait has been satisfied
+  CUDA_CHECK(cudaMemcpyAsync(fd.h, fd.d, sizeof(double) * (size_t)c.g.lev * fd.nlev, cudaMemcpyDeviceToHost,
+                             c.copy_stream));
+}
+static void do_sync() {
+  Ctx& c = C();
+  CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  if (c.copy_stream) CUDA_CHECK(cudaStreamSynchronize(c.copy_stream));
+  c.check_errors();
 }
 static void do_copy_all(bool up) {
   Ctx& c = C();
@@ -214,7 +239,8 @@ int blomgpu_upload(const char* name) { GUARD(do_copy(name, true)) }
 int blomgpu_download(const char* name) { GUARD(do_copy(name, false); CUDA_CHECK(cudaStreamSynchronize(C().stream)); C().check_errors()) }
 int blomgpu_upload_all(void) { GUARD(do_copy_all(true)) }
 int blomgpu_download_all(void) { GUARD(do_copy_all(false)) }
-int blomgpu_sync(void) { GUARD(CUDA_CHECK(cudaStreamSynchronize(C().stream)); C().check_errors()) }
+int blomgpu_download_async(const char* name) { GUARD(do_download_async(name)) }
+int blomgpu_sync(void) { GUARD(do_sync()) }
 int blomgpu_device_ptr(const char* name, void** dptr, int* nlev) {
   GUARD(
     Ctx& c = C();

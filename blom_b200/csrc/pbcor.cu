@@ -261,7 +261,9 @@ void pbcor_run(int m, int n, int mm, int nn, int k1m) {
                  c.dev("uflx"), c.dev("vflx"), utot, vtot);
   }
   {
-    const int kchunk = kk >= 16 ? 8 : kk;
+    // levels marched per block (development switch pbcor_kchunk; 0 = default)
+    const int kc_opt = std::stoi(c.option("pbcor_kchunk", "0"));
+    const int kchunk = kc_opt > 0 ? std::min(kc_opt, kk) : (kk >= 16 ? cdiv(kk, 2) : kk);   // 27 beat 8 and 14 at tnx0.25v4
     const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 1, 128), g.jj + 1, cdiv(kk, kchunk)));
     const char* nm = WHICH == 1 ? "pbcor_update<1>" : "pbcor_update<2>";
     const eos::Coef ec = WHICH == 2 ? eos::host_coef() : eos::Coef{};  // only pbcor2 refreshes sigma

@@ -53,8 +53,7 @@ class HotPath:
         self.rank, self.nranks = rank, nranks
         j0, jj = band(jtdm, rank, nranks)
         self.j0, self.jj = j0, jj
-        self.syn = synth.Synth(itdm, jtdm, kdm, nreg, ntr=ntr, j0=j0, jj=jj, baclin=baclin, batrop=batrop,
-                               seed=seed)
+        self.syn = synth.make_synth(config, ntr=ntr, j0=j0, jj=jj, seed=seed)
         self.grid = self.syn.grid()
         self.state = self.syn.state(self.grid)
         if pinned_alloc is not None:  # e2e leg: prognostic state lives in pinned host memory
@@ -119,10 +118,16 @@ class HotPath:
         g.xctilr("temp", 1, 2 * kk, 3, 3, HALO_PS)       # phy/mod_cmnfld_routines.F90:1171-1172
         g.xctilr("saln", 1, 2 * kk, 3, 3, HALO_PS)
 
-    def step(self):
-        """One pass of the hot path over the resident state."""
+    # fields no routine after `momtum` writes (barotp works on ub/vb/pb, pbcor2 and tmsmt2 on
+    # dp/T/S/trc, phy/mod_blom_step.F90:169-227): their download can overlap the rest of the step
+    FINAL_AFTER = {"momtum": ("u", "v")}
+
+    def step(self, early_download=False):
+        """One pass of the hot path over the resident state.  early_download: start the device ->
+        host copy of a field on the copy stream as soon as its last writer has been enqueued."""
         g = self.gpu
         m, n, mm, nn, k1m, k1n = self.levels
+        self._early = set()
         for r in self.routines:
             if r == "tmsmt1":
                 g.tmsmt1(nn)
@@ -131,10 +136,15 @@ class HotPath:
                 g.tmsmt2(m, mm, nn, k1m)
             else:
                 getattr(g, r)(m, n, mm, nn, k1m, k1n)
+            if early_download:
+                for nm in self.FINAL_AFTER.get(r, ()):
+                    if nm in self.arrays:
+                        g.download_async(nm)
+                        self._early.add(nm)
 
-    def advance(self):
+    def advance(self, early_download=False):
         """step() followed by the leap-frog role swap of the time levels."""
-        self.step()
+        self.step(early_download)
         self.set_step(self.nstep + 1)
 
     def upload_inputs(self):
@@ -143,9 +153,13 @@ class HotPath:
                 self.gpu.upload(nm)
 
     def download_outputs(self):
+        """Bring the prognostic state back; fields whose copy advance(early_download=True) already
+        started are only waited for."""
         for nm in IO_FIELDS:
-            if nm in self.arrays:
+            if nm in self.arrays and nm not in getattr(self, "_early", ()):
                 self.gpu.download(nm)
+        self.gpu.sync()
+        self._early = set()
 
     def io_bytes(self):
         b = sum(self.arrays[nm].nbytes for nm in IO_FIELDS if nm in self.arrays)

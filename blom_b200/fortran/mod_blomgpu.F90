@@ -65,6 +65,10 @@ module mod_blomgpu
          import :: c_int, c_char
          character(kind=c_char), intent(in) :: name(*)
       end function
+      integer(c_int) function blomgpu_download_async(name) bind(C, name='blomgpu_download_async')
+         import :: c_int, c_char
+         character(kind=c_char), intent(in) :: name(*)
+      end function
       integer(c_int) function blomgpu_upload_all() bind(C, name='blomgpu_upload_all')
          import :: c_int
       end function
@@ -159,7 +163,7 @@ module mod_blomgpu
    procedure(six_int_entry), bind(C, name='blomgpu_cmnfld_nslope_ale') :: blomgpu_cmnfld_nslope_ale
    procedure(six_int_entry), bind(C, name='blomgpu_cmnfld_nnslope_ale') :: blomgpu_cmnfld_nnslope_ale
 
-   public :: gpu_setup, gpu_register, gpu_register_int, gpu_upload, gpu_download, &
+   public :: gpu_setup, gpu_register, gpu_register_int, gpu_upload, gpu_download, gpu_download_async, &
              gpu_option, gpu_scalar, gpu_xctilr, &
              init_fluxes, tmsmt1, eddtra, advect, pbcor1, diffus, pgforc, momtum, &
              barotp, pbcor2, tmsmt2, ndiff, cmnfld2, cmnfld_bfsqf_ale, cmnfld_nslope_ale, &
@@ -216,6 +220,12 @@ contains
       character(len=*), intent(in) :: name
       call check(blomgpu_download(cstr(name)), 'download '//name)
    end subroutine gpu_download
+
+   subroutine gpu_download_async(name)
+      ! device -> host on the copy stream; the array is valid after the next gpu_sync
+      character(len=*), intent(in) :: name
+      call check(blomgpu_download_async(cstr(name)), 'download_async '//name)
+   end subroutine gpu_download_async
 
    subroutine gpu_option(key, val)
       character(len=*), intent(in) :: key, val

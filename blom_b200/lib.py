@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "blomgpu_init", "blomgpu_finalize", "blomgpu_last_error", "blomgpu_parity_build",
     "blomgpu_comm_unique_id", "blomgpu_comm_init",
     "blomgpu_register", "blomgpu_register_int", "blomgpu_upload", "blomgpu_download",
-    "blomgpu_upload_all", "blomgpu_download_all", "blomgpu_sync", "blomgpu_device_ptr",
+    "blomgpu_upload_all", "blomgpu_download_all", "blomgpu_download_async", "blomgpu_sync", "blomgpu_device_ptr",
     "blomgpu_set_option", "blomgpu_set_scalar", "blomgpu_get_scalar",
     "blomgpu_xctilr", "blomgpu_xcsum", "blomgpu_xcmax", "blomgpu_xcmin", "blomgpu_chksum",
     "blomgpu_bigrid", "blomgpu_nreg", "blomgpu_init_cppm", "blomgpu_inieos",
@@ -124,6 +124,11 @@ class BlomGpu:
 
     def download(self, name):
         self._ck(self.lib.blomgpu_download(name.encode()))
+        return self.arrays[name]
+
+    def download_async(self, name):
+        """D2H on the copy stream, overlapping the routines called next; valid after sync()."""
+        self._ck(self.lib.blomgpu_download_async(name.encode()))
         return self.arrays[name]
 
     def upload_all(self):

@@ -25,7 +25,8 @@ CONFIGS = {
     "tiny4": (20, 22, 4, 4, 1800.0, 36.0),
     "mid1": (48, 44, 6, 1, 1800.0, 36.0),          # multi-band parity cases (periodic-i / tripolar)
     "mid2": (48, 46, 6, 2, 1800.0, 36.0),
-    "fuk95": (156, 32, 12, 4, 180.0, 6.0),        # tests/fuk95/limits:131-143
+    "fuk95": (156, 32, 12, 4, 180.0, 6.0),        # tests/fuk95/limits:131-143 (dims only, noisy state)
+    "fuk95_analytic": (156, 32, 12, 4, 180.0, 6.0),  # analytic geometry + jet of fuk95/mod_fuk95.F90 (fuk95.py)
     "channel": (208, 512, 53, 1, 1800.0, 36.0),    # bld/channel/patch.input.1
     "tnx1v4": (360, 385, 53, 2, 3200.0, 64.0),     # namelist_definition_blom.xml:179-201
     "tnx0.25v4": (1440, 1153, 53, 2, 900.0, 15.0),
@@ -453,6 +454,16 @@ class Synth:
                 # biharmonic terms switched on so that every branch of momtum is exercised)
                 "mdv2hi": 0.1, "mdv2lo": 0.05, "mdv4hi": 0.01, "mdv4lo": 0.005, "vsc2hi": 0.2, "vsc2lo": 0.15,
                 "vsc4hi": 0.06, "vsc4lo": 0.05, "cbar": 0.05, "cb": 0.002}
+
+
+def make_synth(config, **kw):
+    """Generator of a named configuration: the seeded noise state, or the analytic fuk95 case."""
+    itdm, jtdm, kdm, nreg, baclin, batrop = CONFIGS[config]
+    if config == "fuk95_analytic":
+        from .fuk95 import Fuk95
+        kw = {k: v for k, v in kw.items() if k in ("ntr", "j0", "jj")}
+        return Fuk95(itdm, jtdm, kdm, baclin=baclin, batrop=batrop, **kw)
+    return Synth(itdm, jtdm, kdm, nreg, baclin=baclin, batrop=batrop, **kw)
 
 
 def make_isopycnic(st):

@@ -54,6 +54,11 @@ int blomgpu_upload(const char* name);      /* host -> device */
 int blomgpu_download(const char* name);    /* device -> host */
 int blomgpu_upload_all(void);
 int blomgpu_download_all(void);
+/* device -> host on a second stream, ordered after everything enqueued so far; returns at once
+ * and overlaps the routines called afterwards (which must not write the field).  The host array
+ * is valid after the next blomgpu_sync().  Used for fields a later out-of-scope CPU routine needs
+ * (u,v are final after momtum, phy/mod_blom_step.F90:169-227). */
+int blomgpu_download_async(const char* name);
 int blomgpu_sync(void);
 /* raw device pointer of a registered/owned array (for zero-copy interop) */
 int blomgpu_device_ptr(const char* name, void** dptr, int* nlev);

@@ -24,7 +24,7 @@ def run_routine(b, r, lv):
         getattr(b, r)(m, n, mm, nn, k1m, k1n)
 
 
-@pytest.mark.parametrize("cfg", ["tiny0", "tiny1", "tiny2", "tiny3", "tiny4", "fuk95"])
+@pytest.mark.parametrize("cfg", ["tiny0", "tiny1", "tiny2", "tiny3", "tiny4", "fuk95", "fuk95_analytic"])
 def test_chained_steps(cfg):
     c = Case(cfg, ntr=1, nstep=1)
     o = c.new_oracle(); g = c.new_gpu(parity=True)
@@ -49,5 +49,60 @@ def test_chained_steps(cfg):
                         bad.append((nm, err))
                 assert not bad, (cfg, nstep, r, sorted(bad, key=lambda t: -t[1])[:6])
         assert np.isfinite(g.arrays["dp"]).all()
+    finally:
+        g.finalize()
+
+
+def test_early_download_matches_plain_download():
+    """blomgpu_download_async (u,v copied back on the copy stream while barotp/pbcor2/tmsmt2 run)
+    must hand the host exactly what a plain download after the step does."""
+    from blom_b200.driver import HotPath, IO_FIELDS
+    res = []
+    for early in (False, True):
+        hp = HotPath("tiny2", ntr=1, nstep=1, parity=True)
+        try:
+            for _ in range(2):
+                hp.upload_inputs()
+                hp.advance(early_download=early)
+                hp.download_outputs()
+            res.append({nm: hp.arrays[nm].copy() for nm in IO_FIELDS if nm in hp.arrays})
+        finally:
+            hp.finalize()
+    for nm in res[0]:
+        assert np.array_equal(res[0][nm], res[1][nm]), nm
+    assert np.abs(res[0]["u"]).max() > 0
+
+
+def test_fuk95_geostrophic_adjustment_on_gpu():
+    """The analytic fuk95 front (blom_b200/fuk95.py) stepped by the CUDA hot path alone: after half
+    an inertial period the along-channel jet has the speed u0 the front was built for, mass is
+    conserved to round-off, and the state after 160 steps stays close to the oracle's (tolerance 1e-6
+    of the field maxima: 160 chained steps of a developing instability amplify rounding differences;
+    the 3-step chain above holds 1e-10)."""
+    from blom_b200 import fuk95
+    c = Case("fuk95_analytic", ntr=1, nstep=1)
+    o = c.new_oracle(); g = c.new_gpu(parity=True)
+    try:
+        kk = c.dims[2]
+        for b in (o, g):
+            b.inieos(); b.numerical_bounds(); b.init_cppm()
+        routines = [r for r in STEP_SEQUENCE if r in available_routines()]
+        for nstep in range(1, 161):
+            lv = time_levels(nstep, kk)
+            for b in (o, g):
+                b.set_scalar("nstep", nstep)
+                for r in routines:
+                    run_routine(b, r, lv)
+        g.download_all()
+        nn = lv[3]
+        scp2 = interior(g.arrays["scp2"])[0]
+        mass = float((interior(g.arrays["dp"])[nn:nn + kk] * scp2).sum())
+        mass0 = float((interior(c.state["dp"])[:kk] * scp2).sum())
+        assert abs(mass / mass0 - 1.0) < 1e-13
+        vmax = np.abs(interior(g.arrays["v"])).max()
+        assert 0.9 * fuk95.U0 < vmax < 1.15 * fuk95.U0, vmax
+        for nm in ("dp", "temp", "saln", "u", "v", "pb"):
+            err = max_rel_err(interior(g.arrays[nm]), interior(o.arrays[nm]))
+            assert err <= 1e-6, (nm, err)
     finally:
         g.finalize()

@@ -25,8 +25,7 @@ class Case:
         self.config = config
         self.dims = (itdm, jtdm, kdm, nreg)
         self.ntr, self.nstep = ntr, nstep
-        self.syn = synth.Synth(itdm, jtdm, kdm, nreg, ntr=ntr, baclin=baclin, batrop=batrop, land=land,
-                               metric=metric, seed=seed)
+        self.syn = synth.make_synth(config, ntr=ntr, land=land, metric=metric, seed=seed)
         self.grid = self.syn.grid()
         self.state = self.syn.state(self.grid)
         self.scalars = self.syn.scalars(nstep)
