@@ -197,7 +197,7 @@ __global__ void bt_veq(Geom g, BtP P, const double* __restrict__ ub, int i0, int
 // fields are read with ld.global.cg (L1 is not coherent between the SMs of one launch); the ~40
 // read-only coefficient arrays use the normal cached path.  Operation order per cell is the one of
 // bt_continuity / bt_ueq / bt_veq above, so results are bit-identical to the launch-per-phase form.
-constexpr int BT_THREADS = 512, BT_MINBLK = 2;
+#define BT_SHAPE_DEFAULT "768x2"   // measured at tnx0.25v4: 512x2 22.7 ms, 640x2 22.2, 768x2 21.5, 1024x2 21.6, 256x2 29.6
 
 struct BtSched {
   int lll0, nsub, ml, nl;
@@ -212,15 +212,14 @@ struct BtSched {
 // time-level pointers and time weights of the current substep
 struct BtLv { double *pb_ml, *pb_nl, *ub_ml, *ub_nl, *vb_ml, *vb_nl; double wo, wm, wn; };
 
+// (the callers test the mask of the cell: P.ip for btp_continuity, P.iu for btp_ueq, P.iv for btp_veq)
 __device__ __forceinline__ void btp_continuity(const Geom& g, const BtP& P, const BtLv& V, long x) {
-  if (P.ip[x] != 1) return;
   V.pb_nl[x] = (1. - WBARO) * __ldcg(V.pb_ml + x) + WBARO * __ldcg(V.pb_nl + x) -
                (1. + WBARO) * P.dlt * (__ldcg(V.ub_ml + x + 1) - __ldcg(V.ub_ml + x) + __ldcg(V.vb_ml + x + g.ldi) -
                                        __ldcg(V.vb_ml + x)) * P.scp2i[x];
 }
 __device__ __forceinline__ void btp_ueq(const Geom& g, const BtP& P, const BtLv& V, const double* __restrict__ vb, long x) {
   const long s = g.ldi;
-  if (P.iu[x] != 1) return;
   const double uml = __ldcg(V.ub_ml + x), unl = __ldcg(V.ub_nl + x);
   P.ubflxs_t[x] = __ldcg(P.ubflxs_t + x) - WBARO * unl + (1. + WBARO) * uml;
   const double v00 = __ldcg(vb + x), v01 = __ldcg(vb + x + s), vm0 = __ldcg(vb + x - 1), vm1 = __ldcg(vb + x - 1 + s);
@@ -243,7 +242,6 @@ __device__ __forceinline__ void btp_ueq(const Geom& g, const BtP& P, const BtLv&
 }
 __device__ __forceinline__ void btp_veq(const Geom& g, const BtP& P, const BtLv& V, const double* __restrict__ ub, long x) {
   const long s = g.ldi;
-  if (P.iv[x] != 1) return;
   const double vml = __ldcg(V.vb_ml + x), vnl = __ldcg(V.vb_nl + x);
   P.vbflxs_t[x] = __ldcg(P.vbflxs_t + x) - WBARO * vnl + (1. + WBARO) * vml;
   const double u00 = __ldcg(ub + x), u10 = __ldcg(ub + x + 1), u0m = __ldcg(ub + x - s), u1m = __ldcg(ub + x + 1 - s);
@@ -265,6 +263,36 @@ __device__ __forceinline__ void btp_veq(const Geom& g, const BtP& P, const BtLv&
   V.vb_nl[x] = fmax(-P.vminb[x], fmin(P.vmaxb[x], vn));
 }
 
+// L2 prefetch of the operands a phase will read at cell x (template switch PF, option
+// barotp_prefetch).  A thread walks its cells one after the other and every cell is a chain
+// mask -> operands -> arithmetic -> store of memory round trips (ncu: 35 stall cycles per issue on the
+// long scoreboard at 58 % of the DRAM peak, L2 and LSU below 40 %); prefetching the next cell's lines
+// was expected to shorten the chain to L2 latency but measured 5 % SLOWER on B200, so it is off by
+// default and kept as a documented negative result.
+__device__ __forceinline__ void pf_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void pf_continuity(const Geom& g, const BtP& P, const BtLv& V, long x) {
+  pf_l2(V.pb_ml + x); pf_l2(V.pb_nl + x); pf_l2(V.ub_ml + x); pf_l2(V.vb_ml + x); pf_l2(V.vb_ml + x + g.ldi);
+  pf_l2(P.scp2i + x);
+}
+__device__ __forceinline__ void pf_ueq(const Geom& g, const BtP& P, const BtLv& V, const double* vb, long x) {
+  const long s = g.ldi;
+  pf_l2(V.ub_ml + x); pf_l2(V.ub_nl + x); pf_l2(P.ubflxs_t + x); pf_l2(P.ubcors_t + x); pf_l2(V.pb_nl + x);
+  pf_l2(vb + x); pf_l2(vb + x + s); pf_l2(P.scvxi + x); pf_l2(P.scvxi + x + s);
+  pf_l2(P.pvo + x); pf_l2(P.pvo + x + s); pf_l2(P.pvm + x); pf_l2(P.pvm + x + s); pf_l2(P.pvn + x); pf_l2(P.pvn + x + s);
+  pf_l2(P.pgfxm_o + x); pf_l2(P.xixp_o + x); pf_l2(P.xixm_o + x); pf_l2(P.pgfxm_m + x); pf_l2(P.xixp_m + x);
+  pf_l2(P.xixm_m + x); pf_l2(P.pgfxm_n + x); pf_l2(P.xixp_n + x); pf_l2(P.xixm_n + x);
+  pf_l2(P.scuxi + x); pf_l2(P.utotn + x); pf_l2(P.scuy + x); pf_l2(P.uglue + x); pf_l2(P.uminb + x); pf_l2(P.umaxb + x);
+}
+__device__ __forceinline__ void pf_veq(const Geom& g, const BtP& P, const BtLv& V, const double* ub, long x) {
+  const long s = g.ldi;
+  pf_l2(V.vb_ml + x); pf_l2(V.vb_nl + x); pf_l2(P.vbflxs_t + x); pf_l2(P.vbcors_t + x); pf_l2(V.pb_nl + x);
+  pf_l2(V.pb_nl + x - s); pf_l2(ub + x); pf_l2(ub + x - s); pf_l2(P.scuyi + x); pf_l2(P.scuyi + x - s);
+  pf_l2(P.pvo + x); pf_l2(P.pvm + x); pf_l2(P.pvn + x);
+  pf_l2(P.pgfym_o + x); pf_l2(P.xiyp_o + x); pf_l2(P.xiym_o + x); pf_l2(P.pgfym_m + x); pf_l2(P.xiyp_m + x);
+  pf_l2(P.xiym_m + x); pf_l2(P.pgfym_n + x); pf_l2(P.xiyp_n + x); pf_l2(P.xiym_n + x);
+  pf_l2(P.scvyi + x); pf_l2(P.vtotn + x); pf_l2(P.scvx + x); pf_l2(P.vglue + x); pf_l2(P.vminb + x); pf_l2(P.vmaxb + x);
+}
+
 // Grid-wide barrier on a monotonically increasing counter (one atomic per block and barrier); cheaper
 // than the generic cooperative-groups barrier for the ~440 barriers of one call.  The cooperative
 // launch guarantees co-residency.  Writes of the block are made visible by bar.sync + the cumulative
@@ -281,7 +309,8 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(BT_THREADS, BT_MINBLK)
+template <int THREADS, int MINBLK, bool PF>
+__global__ void __launch_bounds__(THREADS, MINBLK)
 bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_t, double* vb_t, unsigned* ctr) {
   unsigned target = 0;
   unsigned long long seq = S.seq0;
@@ -289,10 +318,31 @@ bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_
   const long L = g.lev;
   int ml = S.ml, nl = S.nl;
   BtLv V;
-  auto for_range = [&](int i0, int i1, int j0, int j1, auto&& body) {
+  // cells idx = tid, tid+nthr, ... of the range; body runs where mask == 1.  With PF the mask
+  // is read two cells ahead and the operands of the next wet cell are prefetched (pf) before the
+  // current cell is worked on.
+  auto for_range = [&](int i0, int i1, int j0, int j1, const int* __restrict__ mask, auto&& body, auto&& pf) {
     const int ni = i1 - i0 + 1;
     const long n = (long)ni * (j1 - j0 + 1);
-    for (long idx = tid; idx < n; idx += nthr) body(ix2(g, i0 + (int)(idx % ni), j0 + (int)(idx / ni)));
+    auto cell = [&](long idx) { return ix2(g, i0 + (int)(idx % ni), j0 + (int)(idx / ni)); };
+    if (!PF) {
+      for (long idx = tid; idx < n; idx += nthr) {
+        const long x = cell(idx);
+        if (mask[x] == 1) body(x);
+      }
+      return;
+    }
+    if (tid >= n) return;
+    long x0 = cell(tid), x1 = x0;
+    int m0 = mask[x0], m1 = 0;
+    if (tid + nthr < n) { x1 = cell(tid + nthr); m1 = mask[x1]; }
+    for (long idx = tid; idx < n; idx += nthr) {
+      long x2 = x1; int m2 = 0;
+      if (idx + 2 * nthr < n) { x2 = cell(idx + 2 * nthr); m2 = mask[x2]; }
+      if (m1 == 1) pf(x1);
+      if (m0 == 1) body(x0);
+      x0 = x1; m0 = m1; x1 = x2; m1 = m2;
+    }
   };
   for (int lll = S.lll0; lll < S.lll0 + S.nsub; ++lll) {
     V.wo = S.woa * lll + S.wob; V.wn = S.wna * lll + S.wnb; V.wm = 1. - V.wo - V.wn;
@@ -358,18 +408,24 @@ bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_
         }
         grid_barrier(ctr, target);
       }
-      for_range(-1, g.ii + 1, -1, g.jj + 2, [&](long x) { btp_continuity(g, P, V, x); });
+      for_range(-1, g.ii + 1, -1, g.jj + 2, P.ip, [&](long x) { btp_continuity(g, P, V, x); },
+                [&](long x) { pf_continuity(g, P, V, x); });
       grid_barrier(ctr, target);
-      for_range(0, g.ii + 1, -1, g.jj + 2, [&](long x) { btp_ueq(g, P, V, V.vb_ml, x); });
+      for_range(0, g.ii + 1, -1, g.jj + 2, P.iu, [&](long x) { btp_ueq(g, P, V, V.vb_ml, x); },
+                [&](long x) { pf_ueq(g, P, V, V.vb_ml, x); });
       grid_barrier(ctr, target);
-      for_range(0, g.ii, 0, g.jj + 2, [&](long x) { btp_veq(g, P, V, V.ub_nl, x); });
+      for_range(0, g.ii, 0, g.jj + 2, P.iv, [&](long x) { btp_veq(g, P, V, V.ub_nl, x); },
+                [&](long x) { pf_veq(g, P, V, V.ub_nl, x); });
       grid_barrier(ctr, target);
     } else {
-      for_range(0, g.ii, 0, g.jj + 1, [&](long x) { btp_continuity(g, P, V, x); });
+      for_range(0, g.ii, 0, g.jj + 1, P.ip, [&](long x) { btp_continuity(g, P, V, x); },
+                [&](long x) { pf_continuity(g, P, V, x); });
       grid_barrier(ctr, target);
-      for_range(0, g.ii, 1, g.jj + 1, [&](long x) { btp_veq(g, P, V, V.ub_ml, x); });
+      for_range(0, g.ii, 1, g.jj + 1, P.iv, [&](long x) { btp_veq(g, P, V, V.ub_ml, x); },
+                [&](long x) { pf_veq(g, P, V, V.ub_ml, x); });
       grid_barrier(ctr, target);
-      for_range(1, g.ii, 1, g.jj, [&](long x) { btp_ueq(g, P, V, V.vb_nl, x); });
+      for_range(1, g.ii, 1, g.jj, P.iu, [&](long x) { btp_ueq(g, P, V, V.vb_nl, x); },
+                [&](long x) { pf_ueq(g, P, V, V.vb_nl, x); });
       grid_barrier(ctr, target);
     }
     const int t = ml; ml = nl; nl = t;
@@ -530,12 +586,28 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
 
   // cooperative persistent form unless option barotp_kernel=phases asks for one launch per phase
   const bool persistent = c.option("barotp_kernel", "persistent") != "phases";
-  static int coop_grid = 0;
+  // block shape of the persistent kernel: threads x resident blocks per SM fixes the register budget
+  // (65536 / (threads*blocks)); development switch barotp_shape = "512x2" (64 regs) | "256x2" (128) |
+  // "384x2" (85) | "1024x1" (64) | "640x2" (48) | "768x2" (40) | "1024x2" (32); barotp_prefetch = 1 | 0
+  struct Shape { const char* name; const void* fn[2]; int threads; };
+#define BT_SHAPE(T, B) {#T "x" #B, {(const void*)bt_subcycle<T, B, false>, (const void*)bt_subcycle<T, B, true>}, T}
+  static const Shape shapes[] = {BT_SHAPE(512, 2), BT_SHAPE(256, 2), BT_SHAPE(384, 2), BT_SHAPE(1024, 1),
+                                 BT_SHAPE(640, 2), BT_SHAPE(768, 2), BT_SHAPE(1024, 2)};
+#undef BT_SHAPE
+  // measured at tnx0.25v4 (512x2): 24.0 ms with the L2 prefetch, 22.9 without - off by default
+  const int pf = c.option("barotp_prefetch", "0") == "1" ? 1 : 0;
+  const std::string shape_opt = c.option("barotp_shape", BT_SHAPE_DEFAULT);
+  const Shape* shape = nullptr;
+  for (const Shape& sh : shapes) if (shape_opt == sh.name) shape = &sh;
+  if (!shape) throw std::runtime_error("barotp: unknown barotp_shape " + shape_opt);
+  static std::map<std::string, int> coop_grids;
+  const std::string shape_key = std::string(shape->name) + (pf ? "p" : "");
+  int coop_grid = coop_grids[shape_key];
   if (persistent && coop_grid == 0) {
     int per_sm = 0, nsm = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bt_subcycle, BT_THREADS, 0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shape->fn[pf], shape->threads, 0));
     CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c.device));
-    coop_grid = std::max(1, per_sm) * nsm;
+    coop_grid = coop_grids[shape_key] = std::max(1, per_sm) * nsm;
   }
   unsigned* bar_ctr = reinterpret_cast<unsigned*>(c.owned("barotp_barrier", 1));
   int lll0 = 1, ml = 1, nl = 2;
@@ -579,7 +651,7 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
         }
         CUDA_CHECK(cudaMemsetAsync(bar_ctr, 0, sizeof(unsigned), c.stream));
         void* args[] = {(void*)&g, (void*)&P, (void*)&S, (void*)&X, (void*)&pb_t, (void*)&ub_t, (void*)&vb_t, (void*)&bar_ctr};
-        launch_cooperative("bt_subcycle", (const void*)bt_subcycle, coop_grid, BT_THREADS, args);
+        launch_cooperative("bt_subcycle", shape->fn[pf], coop_grid, shape->threads, args);
         if (S.nsub % 2 == 1) std::swap(ml, nl);
         lll += S.nsub;
       }

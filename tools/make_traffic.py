@@ -1,9 +1,13 @@
 #!/usr/bin/env python
-"""Collect per-kernel DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, per launch) from
-`ncu --set full` reports into profiles/traffic.json, keyed like bench.py's kernel names.
+"""Collect per-kernel DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, per launch) into
+profiles/traffic.json, keyed like bench.py's kernel names.  Inputs: `ncu --set full` reports
+(.ncu-rep) or the CSV log of an `ncu --metrics ...,dram__bytes_read.sum,dram__bytes_write.sum --csv`
+launch list (the whole-step pass of the profiling recipe).
 
     python tools/make_traffic.py tnx1v4 gpurun_out/prof_a.ncu-rep [more.ncu-rep ...]
+    python tools/make_traffic.py tnx0.25v4 gpurun_out/launches.csv
 """
+import io
 import collections
 import csv
 import json
@@ -21,7 +25,7 @@ def bench_name(ncu_name):
     m = re.match(r"cppm_flux<(\d)", n)
     if m:
         return "cppm_flux<i>" if m.group(1) == "0" else "cppm_flux<j>"
-    m = re.match(r"cppm_hedges<(\d)", n)
+    m = re.match(r"cppm_hedges(?:_tile)?<(\d)", n)
     if m:
         return "cppm_hedges<i>" if m.group(1) == "0" else "cppm_hedges<j>"
     m = re.match(r"eddtra_column<(\d)", n)
@@ -37,6 +41,15 @@ def main():
     cfg, reps = sys.argv[1], sys.argv[2:]
     acc = collections.defaultdict(list)
     for rep in reps:
+        if rep.endswith(".csv"):
+            lines = [l for l in open(rep) if not l.startswith("==")]
+            per = collections.defaultdict(float)
+            for r in csv.DictReader(io.StringIO("".join(lines))):
+                if r["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    per[(r["ID"], r["Kernel Name"])] += float(r["Metric Value"].replace(",", "")) * UNIT[r["Metric Unit"]]
+            for (_, kn), tot in per.items():
+                acc[bench_name(kn)].append(tot)
+            continue
         out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(out.splitlines()))
         hdr, units = rows[0], rows[1]
