@@ -309,7 +309,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
   __syncthreads();
 }
 
-template <int THREADS, int MINBLK, bool PF>
+template <int THREADS, int MINBLK, int PF>
 __global__ void __launch_bounds__(THREADS, MINBLK)
 bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_t, double* vb_t, unsigned* ctr) {
   unsigned target = 0;
@@ -339,7 +339,7 @@ bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_
     for (long idx = tid; idx < n; idx += nthr) {
       long x2 = x1; int m2 = 0;
       if (idx + 2 * nthr < n) { x2 = cell(idx + 2 * nthr); m2 = mask[x2]; }
-      if (m1 == 1) pf(x1);
+      if (PF == 2 && m1 == 1) pf(x1);
       if (m0 == 1) body(x0);
       x0 = x1; m0 = m1; x1 = x2; m1 = m2;
     }
@@ -589,19 +589,19 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   // block shape of the persistent kernel: threads x resident blocks per SM fixes the register budget
   // (65536 / (threads*blocks)); development switch barotp_shape = "512x2" (64 regs) | "256x2" (128) |
   // "384x2" (85) | "1024x1" (64) | "640x2" (48) | "768x2" (40) | "1024x2" (32); barotp_prefetch = 1 | 0
-  struct Shape { const char* name; const void* fn[2]; int threads; };
-#define BT_SHAPE(T, B) {#T "x" #B, {(const void*)bt_subcycle<T, B, false>, (const void*)bt_subcycle<T, B, true>}, T}
+  struct Shape { const char* name; const void* fn[3]; int threads; };
+#define BT_SHAPE(T, B) {#T "x" #B, {(const void*)bt_subcycle<T, B, 0>, (const void*)bt_subcycle<T, B, 1>, (const void*)bt_subcycle<T, B, 2>}, T}
   static const Shape shapes[] = {BT_SHAPE(512, 2), BT_SHAPE(256, 2), BT_SHAPE(384, 2), BT_SHAPE(1024, 1),
                                  BT_SHAPE(640, 2), BT_SHAPE(768, 2), BT_SHAPE(1024, 2)};
 #undef BT_SHAPE
   // measured at tnx0.25v4 (512x2): 24.0 ms with the L2 prefetch, 22.9 without - off by default
-  const int pf = c.option("barotp_prefetch", "0") == "1" ? 1 : 0;
+  const int pf = std::min(2, std::max(0, std::stoi(c.option("barotp_prefetch", "0"))));   // 1: mask look-ahead, 2: + L2 prefetch
   const std::string shape_opt = c.option("barotp_shape", BT_SHAPE_DEFAULT);
   const Shape* shape = nullptr;
   for (const Shape& sh : shapes) if (shape_opt == sh.name) shape = &sh;
   if (!shape) throw std::runtime_error("barotp: unknown barotp_shape " + shape_opt);
   static std::map<std::string, int> coop_grids;
-  const std::string shape_key = std::string(shape->name) + (pf ? "p" : "");
+  const std::string shape_key = std::string(shape->name) + "p" + std::to_string(pf);
   int coop_grid = coop_grids[shape_key];
   if (persistent && coop_grid == 0) {
     int per_sm = 0, nsm = 0;

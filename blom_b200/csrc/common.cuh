@@ -182,6 +182,19 @@ inline void launch_cooperative(const char* kname, const void* kernel, int grid, 
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// Resident-blocks-per-SM bound of a kernel templated on it (second __launch_bounds__ argument).
+// The stencil kernels of this path are latency-bound (ncu: long-scoreboard stalls, issue slots and
+// HBM both far from saturated), and on B200 more resident warps beat more registers per thread even
+// at the price of a few spilled values, so the defaults sit above the compilers' natural choice;
+// `opt` is a development switch to measure the alternatives.
+#define OCC_DISPATCH3(opt, dflt, VA_, VB_, VC_, ...)                                 \
+  do {                                                                              \
+    const int occ_ = std::stoi(blom::C().option(opt, #dflt));                       \
+    if (occ_ == VA_) { constexpr int OCC = VA_; __VA_ARGS__; }                      \
+    else if (occ_ == VB_) { constexpr int OCC = VB_; __VA_ARGS__; }                 \
+    else { constexpr int OCC = VC_; __VA_ARGS__; }                                  \
+  } while (0)
+
 // RAII per-routine timer (device time via CUDA events on the library stream)
 struct ScopedTimer {
   std::string name; cudaEvent_t e0 = nullptr, e1 = nullptr; long l0 = 0; bool on;

@@ -273,7 +273,8 @@ __global__ void cppm_tags_to_int(Geom g, const double* __restrict__ ti, const do
 }
 
 // ---- advect prelude (mod_advect.F90:71-94) ----------------------------------
-__global__ void advect_flux_area(Geom g, int m, int mm, int nn, double delt1, double dlt,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) advect_flux_area(Geom g, int m, int mm, int nn, double delt1, double dlt,
                                  const int* __restrict__ iu, const int* __restrict__ iv,
                                  const double* __restrict__ u, const double* __restrict__ v,
                                  const double* __restrict__ dpu, const double* __restrict__ dpv,
@@ -1260,11 +1261,12 @@ void advect_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   if (advmth != "cppm" && advmth != "remap") throw std::runtime_error(" advmth = " + advmth + " is unsupported!");
   if (advmth == "cppm" && !c.has("cppm_tab_i")) throw std::runtime_error("advect: init_cppm has not been called");
   const dim3 grid = lgrid(g, dim3(cdiv(g.ii, 128), g.jj, g.kdm));
-  LAUNCH(advect_flux_area, grid, 128, 0, g, m, mm, nn, c.scalar("delt1"), c.scalar("dlt"), c.idev("iu"),
+  OCC_DISPATCH3("advect_area_minblk", 16, 10, 12, 16,
+  LAUNCH_NAMED("advect_flux_area", advect_flux_area<OCC>, grid, 128, 0, g, m, mm, nn, c.scalar("delt1"), c.scalar("dlt"), c.idev("iu"),
          c.idev("iv"), c.dev("u"), c.dev("v"), c.dev("dpu"), c.dev("dpv"), c.dev("ubflxs_p"),
          c.dev("vbflxs_p"), c.dev("pbu"), c.dev("pbv"), c.dev("umfltd"), c.dev("vmfltd"),
          c.dev("umflsm"), c.dev("vmflsm"), c.dev("scuy"), c.dev("scvx"), c.dev("umax"), c.dev("vmax"),
-         c.dev("cau"), c.dev("cav"));
+         c.dev("cau"), c.dev("cav")));
   if (advmth == "remap") {   // mod_advect.F90:96-153 (no trailing halo update in this branch)
     advect_remap_dev(m, n, mm, nn, k1m, k1n);
     return;

@@ -96,8 +96,8 @@ __global__ void eddtra_mldens(Geom g, eos::Coef ec, int nn, const int* __restric
 // recomputed from their (cached) inputs where they are needed — the same expressions on the same
 // operands, so the values are identical to the reference's stored work arrays, at a fifth of the
 // local-memory traffic.
-template <int DIR>
-__global__ void __launch_bounds__(128)
+template <int DIR, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int* __restrict__ mask,
               const double* __restrict__ p, const double* __restrict__ dp, const double* __restrict__ dpf,
               const double* __restrict__ temp, const double* __restrict__ saln,
@@ -332,16 +332,17 @@ void eddtra_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     halo_update(util1, 1, 1, 1, halo_ps);
   }
   int* err = c.error_flag();
-  LAUNCH_NAMED("eddtra_column<u>", eddtra_column<0>, grid2, 128, 0, g, P, n, mm, nn, delt1, c.idev("iu"),
+  OCC_DISPATCH3("eddtra_minblk", 16, 9, 12, 16,
+  LAUNCH_NAMED("eddtra_column<u>", (eddtra_column<0, OCC>), grid2, 128, 0, g, P, n, mm, nn, delt1, c.idev("iu"),
                c.dev("p"), c.dev("dp"), c.dev("dpu"), c.dev("temp"), c.dev("saln"), c.dev("difint"),
                c.dev("nslpx"), c.dev("pbu"), c.dev("scu2"), c.dev("scuy"), c.dev("scp2"), coriop, hbl_tf, wpup_tf,
                hml_tfbnd, util1, c.dev("umfltd"), c.dev("umflsm"), c.dev("utfltd"), c.dev("utflsm"),
                c.dev("usfltd"), c.dev("usflsm"), err);
-  LAUNCH_NAMED("eddtra_column<v>", eddtra_column<1>, grid2, 128, 0, g, P, n, mm, nn, delt1, c.idev("iv"),
+  LAUNCH_NAMED("eddtra_column<v>", (eddtra_column<1, OCC>), grid2, 128, 0, g, P, n, mm, nn, delt1, c.idev("iv"),
                c.dev("p"), c.dev("dp"), c.dev("dpv"), c.dev("temp"), c.dev("saln"), c.dev("difint"),
                c.dev("nslpy"), c.dev("pbv"), c.dev("scv2"), c.dev("scvx"), c.dev("scp2"), coriop, hbl_tf, wpup_tf,
                hml_tfbnd, util1, c.dev("vmfltd"), c.dev("vmflsm"), c.dev("vtfltd"), c.dev("vtflsm"),
-               c.dev("vsfltd"), c.dev("vsflsm"), err);
+               c.dev("vsfltd"), c.dev("vsflsm"), err));
   c.error_source = "(eddtra_ale) 1: no convergence, 2: flux exceeds +ffac*mass, 3: flux exceeds -ffac*mass";
 }
 

@@ -176,7 +176,8 @@ __global__ void mt_drag(Geom g, MtP P) {
 __device__ __forceinline__ double ke_at(const Geom& g, const MtP& P, int i, int j, int k);
 
 // ---- stage 1: auxiliary velocities, del2, tension --------------------------------------------
-__global__ void mt_aux(Geom g, MtP P) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) mt_aux(Geom g, MtP P) {
   const Bid b_ = bid(g);
   const int i = b_.x * blockDim.x + threadIdx.x - 1;  // -1..ii+2
   const int j = b_.y - 1, k = b_.z + 1;    // -1..jj+2
@@ -208,7 +209,8 @@ __global__ void mt_aux(Geom g, MtP P) {
 }
 
 // ---- stage 2: q-point gather ---------------------------------------------------------------------
-__global__ void mt_vort(Geom g, MtP P) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) mt_vort(Geom g, MtP P) {
   const Bid b_ = bid(g);
   const int i = b_.x * blockDim.x + threadIdx.x;  // 0..ii+2
   const int j = b_.y, k = b_.z + 1;         // 0..jj+2
@@ -373,7 +375,8 @@ __device__ __forceinline__ void vh_minmax(const Geom& g, const MtP& P, int i, in
 }
 
 // ---- stage 3b: longitudinal stress fluxes at mass points (:858-873, :1017-1032) ------------------------
-__global__ void mt_flux1(Geom g, MtP P) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) mt_flux1(Geom g, MtP P) {
   const Bid b_ = bid(g);
   const int i = b_.x * blockDim.x + threadIdx.x;  // 0..ii
   const int j = b_.y, k = b_.z + 1;         // 0..jj
@@ -384,7 +387,8 @@ __global__ void mt_flux1(Geom g, MtP P) {
 }
 
 // ---- stage 4: tendencies and leap-frog update ------------------------------------------------------
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 mt_update(Geom g, MtP P) {
   const Bid b_ = bid(g);
   const int i = b_.x * blockDim.x + threadIdx.x + 1, j = b_.y + 1, k = b_.z + 1;
@@ -455,7 +459,8 @@ mt_update(Geom g, MtP P) {
                                (uflux1c - uflux1w + uflux3 - uflux2) / (P.scu2[x] * fmax(P.dpu[xm], onemm)));
   }
 }
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 mt_update_v(Geom g, MtP P) {
   const Bid b_ = bid(g);
   const int i = b_.x * blockDim.x + threadIdx.x + 1, j = b_.y + 1, k = b_.z + 1;
@@ -958,7 +963,8 @@ __device__ __forceinline__ void col_velocity(long x, long L, int kdm, int mm, in
   totn[x] = tot * (1. / delt1);
 }
 
-__global__ void mt_column(Geom g, MtP P) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) mt_column(Geom g, MtP P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
   if (i > g.ii) return;
   const long x = ix2(g, i, j), L = g.lev, m2 = (long)(P.m - 1) * L;
@@ -1029,15 +1035,17 @@ void momtum_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     LAUNCH_NAMED("mt_level", (mt_level<TX, TY>), grid, T::NT, T::bytes, g, P);
   } else {
     // staged form (default): one launch per stage, layer-sized scratch arrays in HBM
-    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 4, 128), g.jj + 4, g.kdm)); LAUNCH(mt_aux, grid, 128, 0, g, P); }
-    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm)); LAUNCH(mt_vort, grid, 128, 0, g, P); }
+    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 4, 128), g.jj + 4, g.kdm)); OCC_DISPATCH3("mt_aux_minblk", 12, 12, 14, 16, LAUNCH_NAMED("mt_aux", mt_aux<OCC>, grid, 128, 0, g, P)); }
+    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm)); OCC_DISPATCH3("mt_vort_minblk", 12, 7, 12, 16, LAUNCH_NAMED("mt_vort", mt_vort<OCC>, grid, 128, 0, g, P)); }
     { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 2, 128), g.jj + 2, g.kdm)); LAUNCH(mt_visc, grid, 128, 0, g, P); }
-    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 1, 128), g.jj + 1, g.kdm)); LAUNCH(mt_flux1, grid, 128, 0, g, P); }
+    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 1, 128), g.jj + 1, g.kdm)); OCC_DISPATCH3("mt_flux1_minblk", 12, 12, 14, 16, LAUNCH_NAMED("mt_flux1", mt_flux1<OCC>, grid, 128, 0, g, P)); }
     { const dim3 grid = lgrid(g, dim3(cdiv(g.ii, 128), g.jj, g.kdm));
-      LAUNCH(mt_update, grid, 128, 0, g, P);
-      LAUNCH(mt_update_v, grid, 128, 0, g, P); }
+      OCC_DISPATCH3("momtum_minblk", 12, 7, 12, 16,
+                    LAUNCH_NAMED("mt_update", mt_update<OCC>, grid, 128, 0, g, P);
+                    LAUNCH_NAMED("mt_update_v", mt_update_v<OCC>, grid, 128, 0, g, P)); }
   }
-  { dim3 grid(cdiv(g.ii, 128), g.jj); LAUNCH(mt_column, grid, 128, 0, g, P); }
+  { dim3 grid(cdiv(g.ii, 128), g.jj);
+    OCC_DISPATCH3("mt_column_minblk", 7, 7, 10, 12, LAUNCH_NAMED("mt_column", mt_column<OCC>, grid, 128, 0, g, P)); }
 }
 
 }  // namespace blom

@@ -101,8 +101,8 @@ __device__ __forceinline__ Flux3 face_flux(const FaceInv& F, int f, const LvlOps
 
 // One thread per (i,j) and chunk of levels: the face invariants are prepared once, the level loop
 // streams dp/T/S of the cell and its four upstream candidates.
-template <int WHICH, bool DLUC>
-__global__ void __launch_bounds__(128)
+template <int WHICH, bool DLUC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 pbcor_update(Geom g, eos::Coef ec, int ks, int kf, int kchunk, const int* __restrict__ ip, const int* __restrict__ iu,
              const int* __restrict__ iv, const double* __restrict__ utot, const double* __restrict__ vtot,
              const double* __restrict__ dp, const double* __restrict__ p, const double* __restrict__ temp,
@@ -267,14 +267,12 @@ void pbcor_run(int m, int n, int mm, int nn, int k1m) {
     const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 1, 128), g.jj + 1, cdiv(kk, kchunk)));
     const char* nm = WHICH == 1 ? "pbcor_update<1>" : "pbcor_update<2>";
     const eos::Coef ec = WHICH == 2 ? eos::host_coef() : eos::Coef{};  // only pbcor2 refreshes sigma
-    if (dluc)
-      LAUNCH_NAMED(nm, (pbcor_update<WHICH, true>), grid, 128, 0, g, ec, ks, kf, kchunk, ip, iu, iv, utot, vtot,
-                   dp, p, temp, saln, c.dev("scp2i"), c.dev("uflx"), c.dev("usflx"), c.dev("utflx"), c.dev("vflx"),
-                   c.dev("vsflx"), c.dev("vtflx"), dpB, tB, sB, c.dev("sigma"), T);
-    else
-      LAUNCH_NAMED(nm, (pbcor_update<WHICH, false>), grid, 128, 0, g, ec, ks, kf, kchunk, ip, iu, iv, utot, vtot,
-                   dp, p, temp, saln, c.dev("scp2i"), c.dev("uflx"), c.dev("usflx"), c.dev("utflx"), c.dev("vflx"),
-                   c.dev("vsflx"), c.dev("vtflx"), dpB, tB, sB, c.dev("sigma"), T);
+#define PB_LAUNCH(D)                                                                                            \
+    LAUNCH_NAMED(nm, (pbcor_update<WHICH, D, OCC>), grid, 128, 0, g, ec, ks, kf, kchunk, ip, iu, iv, utot, vtot, dp, \
+                 p, temp, saln, c.dev("scp2i"), c.dev("uflx"), c.dev("usflx"), c.dev("utflx"), c.dev("vflx"),     \
+                 c.dev("vsflx"), c.dev("vtflx"), dpB, tB, sB, c.dev("sigma"), T)
+    OCC_DISPATCH3("pbcor_minblk", 4, 3, 4, 5, if (dluc) PB_LAUNCH(true); else PB_LAUNCH(false));
+#undef PB_LAUNCH
   }
   {
     dim3 grid(cdiv(g.ii, 128), g.jj);

@@ -81,7 +81,8 @@ constexpr int TX = 32, TY = 8, NV = 7;  // values shared per column and level
 
 // bottom-up march; thread (tx,ty) owns p-column (i,j) = (bx*31+tx, by*7+ty), i.e. a one-column
 // skirt on the west and south of the 31x7 output tile.
-__global__ void __launch_bounds__(TX* TY)
+template <int MINB>
+__global__ void __launch_bounds__(TX* TY, MINB)
 pg_dynh_march(Geom g, eos::Coef ec, int n, int nn, const int* __restrict__ ip, const int* __restrict__ iu,
               const int* __restrict__ iv, const double* __restrict__ p, const double* __restrict__ dp,
               const double* __restrict__ temp, const double* __restrict__ saln, const double* __restrict__ dpu,
@@ -323,10 +324,11 @@ void pgforc_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
            c.dev("xiyp"), c.dev("xiym"));
   } else {
     dim3 grid(cdiv(g.ii + 1, TX - 1), cdiv(g.jj + 1, TY - 1)), block(TX, TY);
-    LAUNCH(pg_dynh_march, grid, block, 0, g, eos::host_coef(), n, nn, c.idev("ip"), c.idev("iu"), c.idev("iv"),
+    OCC_DISPATCH3("pgforc_minblk", 2, 2, 3, 4,
+    LAUNCH_NAMED("pg_dynh_march", pg_dynh_march<OCC>, grid, block, 0, g, eos::host_coef(), n, nn, c.idev("ip"), c.idev("iu"), c.idev("iv"),
            c.dev("p"), c.dev("dp"), c.dev("temp"), c.dev("saln"), c.dev("dpu"), c.dev("dpv"), c.dev("phi"),
            c.dev("pgfx"), c.dev("pgfy"), c.dev("pgfx_o"), c.dev("pgfy_o"), c.dev("pgfxm"), c.dev("xixp"),
-           c.dev("xixm"), c.dev("pgfym"), c.dev("xiyp"), c.dev("xiym"));
+           c.dev("xixm"), c.dev("pgfym"), c.dev("xiyp"), c.dev("xiym")));
   }
   halo_update(c.dev("pb_p"), 1, 1, 1, halo_ps);
   {
