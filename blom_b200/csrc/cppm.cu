@@ -388,8 +388,8 @@ cppm_hedges(Geom g, bool second_pass, const double* __restrict__ dp /* level 1 o
 // static weights of a thread's own edge/cell stay in registers across the levels.
 // dp (and the cross flux areas) of level k+1 are fetched into registers while level k is computed.
 // Expressions and their order are those of cppm_hedges above, so both forms are bit-identical.
-template <int DIR, bool MONO, int TPO, int TC>
-__global__ void __launch_bounds__(TPO* TC)
+template <int DIR, bool MONO, int TPO, int TC, int MINB>
+__global__ void __launch_bounds__(TPO* TC, MINB)
 cppm_hedges_tile(Geom g, bool second_pass, int kchunk, const double* __restrict__ dp,
                  const double* __restrict__ cac, const double* __restrict__ scp2i,
                  const double* __restrict__ tab, double* __restrict__ hel3, double* __restrict__ her3) {
@@ -1161,9 +1161,12 @@ void cppm_pass(bool second_pass, int n, int mm, double* dp_src, double* dp_dst, 
       const int nz = (int)std::min<long>(std::max<long>(1, (148L * 8 * 8 + tiles - 1) / tiles), std::max(1, g.kdm / 4));
       const int kchunk = cdiv(g.kdm, nz);
       grid.z = cdiv(g.kdm, kchunk);
-      auto hk = cppm_hedges_tile<DIR, MONO, TPO, TC>;
-      LAUNCH_NAMED(DIR == 0 ? "cppm_hedges<i>" : "cppm_hedges<j>", hk, grid, block, 0, g,
-                   second_pass, kchunk, dp_src, cac, scp2i, tab, hel3, her3);
+      // resident blocks asked for: 256-thread blocks on the i pass (3 natural, 5, 8), 512-thread blocks on
+      // the j pass (2 natural, 3, 4)
+      OCC_DISPATCH3("hedges_minblk", 0, 0, 1, 2,
+                    LAUNCH_NAMED(DIR == 0 ? "cppm_hedges<i>" : "cppm_hedges<j>",
+                                 (cppm_hedges_tile<DIR, MONO, TPO, TC, DIR == 0 ? (OCC == 0 ? 3 : OCC == 1 ? 5 : 8) : OCC + 2>), grid,
+                                 block, 0, g, second_pass, kchunk, dp_src, cac, scp2i, tab, hel3, her3));
     }
     halo_update(std::vector<HaloReq>{{hel3, g.kdm, halo_ps}, {her3, g.kdm, halo_ps}}, mh, nh);
     if (g.nreg == 2 && g.north) {
