@@ -667,6 +667,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // on the tripolar fold rows, whose table entries are mirrored images
 // (mod_cppm.F90:2605-2646), read the tables.
 // Scheme variants (mod_cppm.F90:2748-2834): bit 0 = monotonic limiting, bit 1 = partial compatibility.
+#define CPPM_J_TILE_DEFAULT "32x16"
 enum { VAR_FC_NOSC = 0, VAR_FC_MONO = 1, VAR_PC_NOSC = 2, VAR_PC_MONO = 3 };
 
 template <int NT, int TP, int VAR>
@@ -1093,14 +1094,12 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
   }
 }
 
-template <int DIR, int NT, int VAR>
-void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, const ScalarPtrs<NT>& S,
+template <int DIR, int NT, int VAR, int TP, int TC>
+void launch_flux_shape(bool second_pass, int n, const double* dp_src, double* dp_dst, const ScalarPtrs<NT>& S,
                  const double* hel3, const double* her3, const double* cad, const double* cac,
                  const double* p, const double* pbd, const double* scp2i, const double* scpd, const double* tab,
                  const int* sten, double* flx, double* tflx, double* sflx) {
   Ctx& c = C(); const Geom& g = c.g;
-  constexpr int TP = DIR == 0 ? 128 : 32;
-  constexpr int TC = DIR == 0 ? 2 : 16;
   constexpr int NOUT = TP - 5;
   const size_t smem = sizeof(double) * FluxSmem<NT, TP, VAR>::PER_TC * TC;
   auto kern = cppm_flux<DIR, NT, TP, TC, VAR>;
@@ -1127,6 +1126,25 @@ void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, 
   // thread tp = npass+1-p0 <= TP-3 of the last tile owns it.
   LAUNCH_NAMED(DIR == 0 ? "cppm_flux<i>" : "cppm_flux<j>", kern, grid, block, smem, g, second_pass, n, kchunk, dp_src,
                dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i, scpd, tab, sten, flx, tflx, sflx);
+}
+
+// Tile shape of the flux kernel: TP positions along the pass (TP-5 of them updated) x TC across it.
+// i pass: 128 x 2.  j pass: lanes must run along i, so the tile is TC wide in i and TP long in j;
+// 32 x 16 recomputes 5 of 32 rows, 64 x 8 only 5 of 64 (development switch cppm_j_tile).
+template <int DIR, int NT, int VAR>
+void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, const ScalarPtrs<NT>& S,
+                 const double* hel3, const double* her3, const double* cad, const double* cac,
+                 const double* p, const double* pbd, const double* scp2i, const double* scpd, const double* tab,
+                 const int* sten, double* flx, double* tflx, double* sflx) {
+  if (DIR == 0)
+    launch_flux_shape<DIR, NT, VAR, 128, 2>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
+                                            scpd, tab, sten, flx, tflx, sflx);
+  else if (C().option("cppm_j_tile", CPPM_J_TILE_DEFAULT) == "64x8")
+    launch_flux_shape<DIR, NT, VAR, 64, 8>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
+                                           scpd, tab, sten, flx, tflx, sflx);
+  else
+    launch_flux_shape<DIR, NT, VAR, 32, 16>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
+                                            scpd, tab, sten, flx, tflx, sflx);
 }
 
 template <int DIR, int NT, int VAR>
