@@ -544,14 +544,15 @@ __global__ void cppm_swap_edges(Geom g, bool fold_fix, int hw /* 4 nosc, 3 mono 
 // c0..c3 are the 4 cells e-2..e+1; t0/tl/tr are this interface's moment coefficients.
 __device__ __forceinline__ void tracer_edge_weights(int stencil, const double* __restrict__ t0,
                                                     const double* __restrict__ tl, const double* __restrict__ tr,
-                                                    const double hm[4], const double hel[4],
+                                                    const double hi[4] /* 1/hm of the four cells */,
+                                                    const double hel[4],
                                                     const double her[4], double& tevc1, double& tevc2,
                                                     double& tevc3, double& tevc4) {
   double h1i, h2i, h3i, h4i, a12, a22, a32, a42, a13, a23, a33, a43, a14, a24, a34, a44, q;
 #define EL(r, c, hi) (t0[(r) - 1] + (tl[(r) - 1] * hel[c] + tr[(r) - 1] * her[c]) * hi)
   switch (stencil) {
     case stencil_1111:
-      h1i = K1 / hm[0]; h2i = K1 / hm[1]; h3i = K1 / hm[2]; h4i = K1 / hm[3];
+      h1i = hi[0]; h2i = hi[1]; h3i = hi[2]; h4i = hi[3];
       a12 = EL(1, 0, h1i); a13 = EL(2, 0, h1i); a14 = EL(3, 0, h1i);
       a22 = EL(4, 1, h2i) - a12; a23 = EL(5, 1, h2i) - a13; a24 = EL(6, 1, h2i) - a14;
       a32 = EL(7, 2, h3i) - a12; a33 = EL(8, 2, h3i) - a13; a34 = EL(9, 2, h3i) - a14;
@@ -574,7 +575,7 @@ __device__ __forceinline__ void tracer_edge_weights(int stencil, const double* _
       tevc1 = K1 - tevc2 - tevc3 - tevc4;
       break;
     case stencil_1110:
-      h1i = K1 / hm[0]; h2i = K1 / hm[1]; h3i = K1 / hm[2];
+      h1i = hi[0]; h2i = hi[1]; h3i = hi[2];
       a12 = EL(1, 0, h1i); a13 = EL(2, 0, h1i);
       a22 = EL(4, 1, h2i) - a12; a23 = EL(5, 1, h2i) - a13;
       a32 = EL(7, 2, h3i) - a12; a33 = EL(8, 2, h3i) - a13;
@@ -588,7 +589,7 @@ __device__ __forceinline__ void tracer_edge_weights(int stencil, const double* _
       tevc4 = K0;
       break;
     case stencil_0111:
-      h2i = K1 / hm[1]; h3i = K1 / hm[2]; h4i = K1 / hm[3];
+      h2i = hi[1]; h3i = hi[2]; h4i = hi[3];
       a22 = EL(4, 1, h2i); a23 = EL(5, 1, h2i);
       a32 = EL(7, 2, h3i) - a22; a33 = EL(8, 2, h3i) - a23;
       a42 = EL(10, 3, h4i) - a22; a43 = EL(11, 3, h4i) - a23;
@@ -602,7 +603,7 @@ __device__ __forceinline__ void tracer_edge_weights(int stencil, const double* _
       tevc1 = K0;
       break;
     case stencil_1100:
-      h1i = K1 / hm[0]; h2i = K1 / hm[1];
+      h1i = hi[0]; h2i = hi[1];
       a12 = EL(1, 0, h1i);
       a22 = EL(4, 1, h2i) - a12;
       tevc2 = -a12 / a22;
@@ -610,7 +611,7 @@ __device__ __forceinline__ void tracer_edge_weights(int stencil, const double* _
       tevc3 = K0; tevc4 = K0;
       break;
     case stencil_0110:
-      h2i = K1 / hm[1]; h3i = K1 / hm[2];
+      h2i = hi[1]; h3i = hi[2];
       a22 = EL(4, 1, h2i);
       a32 = EL(7, 2, h3i) - a22;
       tevc3 = -a22 / a32;
@@ -618,7 +619,7 @@ __device__ __forceinline__ void tracer_edge_weights(int stencil, const double* _
       tevc1 = K0; tevc4 = K0;
       break;
     case stencil_0011:
-      h3i = K1 / hm[2]; h4i = K1 / hm[3];
+      h3i = hi[2]; h4i = hi[3];
       a32 = EL(7, 2, h3i);
       a42 = EL(10, 3, h4i) - a32;
       tevc4 = -a32 / a42;
@@ -676,10 +677,10 @@ struct FluxSmem {
   static constexpr int NRAW = 5 + NT;   // dp, hel, her, cross flux area (+,-), tm[NT]
   static constexpr int NOPS = 5;        // pass flux area, p(k+1), flx, tflx, sflx
   static constexpr int BUF = NRAW * NCELL + NOPS * TP;
-  // hm, 1/area, width, E|F (1+NT rows), D (NT, +1 for the thickness curvature of the partial
+  // hm, 1/hm, 1/area, width, E|F (1+NT rows), D (NT, +1 for the thickness curvature of the partial
   // compatibility variants), P (3+3NT)
   static constexpr int ND = NT + ((VAR & 2) ? 1 : 0);
-  static constexpr int WORK = 3 * NCELL + (1 + NT + ND + 3 + 3 * NT) * TP;
+  static constexpr int WORK = 4 * NCELL + (1 + NT + ND + 3 + 3 * NT) * TP;
   static constexpr int PER_TC = 2 * BUF + WORK;
 };
 
@@ -726,7 +727,8 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
   double* s_hm = base + 2 * L::BUF;          // [NCELL]
   double* s_ai = s_hm + NCELL;               // [NCELL] 1/area of the staged cells
   double* s_dx = s_ai + NCELL;               // [NCELL] width of the staged cells along the pass
-  double* s_F = s_dx + NCELL;                // [1+NT][TP]; rows 1.. double as the edge values E
+  double* s_hi = s_dx + NCELL;               // [NCELL] 1/hm, shared by the four interfaces that use a cell
+  double* s_F = s_hi + NCELL;                // [1+NT][TP]; rows 1.. double as the edge values E
   double* s_E = s_F + TP;
   double* s_D = s_F + (1 + NT) * TP;         // [ND][TP]; row NT = thickness curvature (PC)
   double* s_P = s_D + L::ND * TP;            // [3+3NT][TP]
@@ -824,6 +826,7 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
       double h = fmax(K0, s_dp[q]) + DPEPS;
       if (second_pass) h = h / (K1 - (B[3 * NCELL + q] - B[4 * NCELL + q]) * s_ai[q]);
       s_hm[q] = h;
+      if (!PC) s_hi[q] = K1 / h;
     }
     __syncthreads();
 
@@ -843,9 +846,9 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
         s_E[nt * TP + tp] = hv1 * s_tm[nt * NCELL + tp] + hv2 * s_tm[nt * NCELL + tp + 1] +
                             hv3 * s_tm[nt * NCELL + tp + 2] + hv4 * s_tm[nt * NCELL + tp + 3];
     } else {
-      double hm4[4], hel4[4], her4[4];
+      double hi4[4], hel4[4], her4[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { hm4[q] = s_hm[tp + q]; hel4[q] = s_hel[tp + q]; her4[q] = s_her[tp + q]; }
+      for (int q = 0; q < 4; ++q) { hi4[q] = s_hi[tp + q]; hel4[q] = s_hel[tp + q]; her4[q] = s_her[tp + q]; }
       double w1, w2, w3, w4;
       TmCoef tcf;
       if (use_tab) {
@@ -859,7 +862,7 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
         double av[12];
         tm_coeffs(s_dx[tp], s_dx[tp + 1], s_dx[tp + 2], s_dx[tp + 3], tcf, av);
       }
-      tracer_edge_weights(stencil, tcf.t0, tcf.tl, tcf.tr, hm4, hel4, her4, w1, w2, w3, w4);
+      tracer_edge_weights(stencil, tcf.t0, tcf.tl, tcf.tr, hi4, hel4, her4, w1, w2, w3, w4);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
         s_E[nt * TP + tp] = w1 * s_tm[nt * NCELL + tp] + w2 * s_tm[nt * NCELL + tp + 1] +
@@ -1136,15 +1139,17 @@ void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, 
                  const double* hel3, const double* her3, const double* cad, const double* cac,
                  const double* p, const double* pbd, const double* scp2i, const double* scpd, const double* tab,
                  const int* sten, double* flx, double* tflx, double* sflx) {
-  if (DIR == 0)
+  if constexpr (DIR == 0)
     launch_flux_shape<DIR, NT, VAR, 128, 2>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
                                             scpd, tab, sten, flx, tflx, sflx);
-  else if (C().option("cppm_j_tile", CPPM_J_TILE_DEFAULT) == "64x8")
-    launch_flux_shape<DIR, NT, VAR, 64, 8>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
-                                           scpd, tab, sten, flx, tflx, sflx);
-  else
-    launch_flux_shape<DIR, NT, VAR, 32, 16>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
-                                            scpd, tab, sten, flx, tflx, sflx);
+  else {
+    if (C().option("cppm_j_tile", CPPM_J_TILE_DEFAULT) == "64x8")
+      launch_flux_shape<DIR, NT, VAR, 64, 8>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
+                                             scpd, tab, sten, flx, tflx, sflx);
+    else
+      launch_flux_shape<DIR, NT, VAR, 32, 16>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd,
+                                              scp2i, scpd, tab, sten, flx, tflx, sflx);
+  }
 }
 
 template <int DIR, int NT, int VAR>
