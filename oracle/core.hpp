@@ -9,7 +9,9 @@
 // toolchain).  Pinned here by (i) the CRC-32 check value
 // 0xCBF43926 for mod_crc32, (ii) hand-derived fold/halo index fixtures under
 // tests/golden/, (iii) analytic invariants (uniform-field preservation,
-// conservation) of the restated routines.
+// conservation) of the restated routines, (iv) the physical known answer of
+// the reference's own idealized test: the fuk95 density front adjusts to a
+// geostrophic jet of the speed u0 it was built for (tests/test_oracle_fuk95.py).
 //
 // Conventions: every `real` of the reference is real(8) (meson.build:10
 // -fdefault-real-8); arrays are column-major a(1-nbdy:idm+nbdy,

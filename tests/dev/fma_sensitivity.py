@@ -3,10 +3,10 @@ sensitivity to FP contraction?  Builds a second copy of the ORACLE with -ffp-con
 (into oracle/_build/fma/, test infrastructure only) and runs one chained step on both: the two CPU
 builds differ from each other in the same few nearly massless cells, by the same values, as
 libblomgpu.so differs from the oracle on the GPU (profiles/r01_fma_sensitivity.txt).
-usage: python tools/fma_sensitivity.py [config]"""
+usage: python tests/dev/fma_sensitivity.py [config]"""
 import subprocess, sys
 from pathlib import Path
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import numpy as np
 import oracle.oracle as om

@@ -1,3 +1,5 @@
+"""Development check (uses the test scaffolding): cppm_flux j-pass tile shapes 32x16 and 64x8 give
+bit-identical advect results.  usage: python tests/dev/jtile_check.py"""
 import sys
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np

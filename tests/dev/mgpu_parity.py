@@ -2,7 +2,7 @@
 """Multi-GPU parity of the j-band path (run under torchrun, one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 tools/mgpu_parity.py mid2 3
+        --master-port 29511 tests/dev/mgpu_parity.py mid2 3
 
 Every rank steps its band of the synthetic state through the full hot path; rank 0 then runs
 the SAME case on one GPU (one tile) and on the CPU oracle and compares the assembled bands:
@@ -17,7 +17,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 

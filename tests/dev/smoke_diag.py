@@ -1,6 +1,6 @@
 """Development aid: per-routine error growth of the performance (FMA) build against the oracle on a
 small case; prints, for each routine, the worst field, where it is and how thick the layer is there.
-usage: python tools/smoke_diag.py [config] [parity 0|1] [each|end]"""
+usage: python tests/dev/smoke_diag.py [config] [parity 0|1] [each|end]"""
 import sys
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np

@@ -68,6 +68,12 @@ def test_product_does_not_reference_oracle():
             assert "oracle" not in txt.lower().replace("test oracle", "").replace("the oracle", "") or p.name == "synth.py", p
 
 
+def test_tools_do_not_reference_oracle():
+    """tools/ holds profiling helpers of the product; scripts that need the oracle live in tests/dev/."""
+    for p in (ROOT / "tools").glob("*.py"):
+        assert "oracle" not in p.read_text().lower(), p
+
+
 def test_time_levels():
     assert blib.time_levels(0, 12) == (1, 2, 0, 12, 1, 13)
     assert blib.time_levels(1, 12) == (2, 1, 12, 0, 13, 1)

@@ -1,5 +1,5 @@
 """Multi-GPU (j-band) parity, run on the box when >= 2 GPUs are visible: the bands of a 2-rank NCCL
-run are bit-identical to the one-tile run and within 1e-10 of the oracle (tools/mgpu_parity.py)."""
+run are bit-identical to the one-tile run and within 1e-10 of the oracle (tests/dev/mgpu_parity.py)."""
 import json
 import os
 import subprocess
@@ -23,7 +23,7 @@ def test_two_band_parity(cfg, comm, tmp_path):
         pytest.skip("needs 2 GPUs")
     env = dict(os.environ, MGPU_TMP=str(tmp_path), MGPU_COMM=comm)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(ROOT / "tools/mgpu_parity.py"),
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(ROOT / "tests/dev/mgpu_parity.py"),
                         cfg, "3"], capture_output=True, text=True, env=env, timeout=600)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert lines, r.stdout[-2000:] + r.stderr[-2000:]

@@ -79,7 +79,7 @@ def assert_fma_close(a, b, what, tol=1e-11, max_flip_frac=5e-3, max_flip=2e-2):
     CPPM's limiters branch on sign tests of near-cancelling expressions; under FMA contraction a few
     of them take the other branch in nearly massless cells (the oracle itself, compiled with
     -ffp-contract=fast, differs from the oracle in the same cells by the same values:
-    tools/fma_sensitivity.py, profiles/r01_fma_sensitivity.txt).  So: every point within `tol` of
+    tests/dev/fma_sensitivity.py, profiles/r01_fma_sensitivity.txt).  So: every point within `tol` of
     the oracle (relative to the field's max-norm) except at most max(8, max_flip_frac*size) points,
     and none further away than `max_flip`.  Returns the number of points beyond `tol`."""
     a = np.asarray(a, dtype=np.float64)
