@@ -75,7 +75,8 @@ def x_psi(x):
 class Fuk95(Synth):
     """The fuk95 case on the reference's grid (156 x 32 x 12 by default; any even itdm works)."""
 
-    def __init__(self, itdm=156, jtdm=32, kdm=12, *, ntr=0, j0=0, jj=None, baclin=180.0, batrop=6.0):
+    def __init__(self, itdm=156, jtdm=32, kdm=12, *, ntr=0, j0=0, jj=None, baclin=180.0, batrop=6.0, u0=U0):
+        self.u0 = u0   # jet speed the front is built for; 0 gives level isopycnals (a state of rest)
         super().__init__(itdm, jtdm, kdm, 4, ntr=ntr, j0=j0, jj=jj, baclin=baclin, batrop=batrop, land=False,
                          metric="uniform")
 
@@ -116,7 +117,7 @@ class Fuk95(Synth):
         s0 = RHOB - RHO0
         sg = np.zeros((kk, self.jj, self.itdm))
         for k in range(kk):
-            s1 = RHOC * (1.0 + F0 * U0 * x_psi(x) / (GRAV * H1)) - RHO0 + 0.5 * DRHO * (z[k + 1] + z[k] - H1) / H1
+            s1 = RHOC * (1.0 + F0 * self.u0 * x_psi(x) / (GRAV * H1)) - RHO0 + 0.5 * DRHO * (z[k + 1] + z[k] - H1) / H1
             sg[k] = (s1 * max(0.0, min(z[k + 1], H1) - z[k]) + s0 * max(0.0, z[k + 1] - max(z[k], H1))) / (z[k + 1] - z[k])
         return sg
 

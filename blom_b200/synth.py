@@ -461,7 +461,7 @@ def make_synth(config, **kw):
     itdm, jtdm, kdm, nreg, baclin, batrop = CONFIGS[config]
     if config == "fuk95_analytic":
         from .fuk95 import Fuk95
-        kw = {k: v for k, v in kw.items() if k in ("ntr", "j0", "jj")}
+        kw = {k: v for k, v in kw.items() if k in ("ntr", "j0", "jj", "u0")}
         return Fuk95(itdm, jtdm, kdm, baclin=baclin, batrop=batrop, **kw)
     return Synth(itdm, jtdm, kdm, nreg, baclin=baclin, batrop=batrop, **kw)
 

@@ -69,3 +69,29 @@ def test_geostrophic_adjustment_known_answer():
     assert vmax[9] < 0.01 < vmax[79]                       # starts at rest, spins up
     assert 0.9 * fuk95.U0 < max(vmax) < 1.15 * fuk95.U0    # 0.318 m/s at step ~160
     assert np.abs(interior(o.arrays["u"])).max() < fuk95.U0
+
+
+def test_level_isopycnals_stay_at_rest():
+    """The same channel without the front (u0 = 0: horizontally uniform stratification, no forcing):
+    the pressure gradient force must vanish identically, so the state of rest is a fixed point of
+    pgforc + momtum + barotp and the thickness/tracer fields must not move."""
+    c = Case("fuk95_analytic", ntr=1, nstep=1, u0=0.0)
+    o = c.new_oracle()
+    o.inieos(); o.numerical_bounds(); o.init_cppm()
+    kk = c.dims[2]
+    dp0 = interior(o.arrays["dp"]).copy()
+    t0 = interior(o.arrays["temp"]).copy()
+    for nstep in range(1, 11):
+        m, n, mm, nn, k1m, k1n = time_levels(nstep, kk)
+        o.set_scalar("nstep", nstep)
+        for r in STEP_SEQUENCE:
+            if r == "tmsmt1":
+                o.tmsmt1(nn)
+            elif r == "tmsmt2":
+                o.tmsmt2(m, mm, nn, k1m)
+            else:
+                getattr(o, r)(m, n, mm, nn, k1m, k1n)
+    for nm in ("u", "v", "pgfx", "pgfy", "ubflxs_p", "vbflxs_p"):
+        assert np.abs(interior(o.arrays[nm])).max() < 1e-12, nm
+    assert np.abs(interior(o.arrays["dp"]) - dp0).max() < 1e-6          # Pa, of 1.6e5
+    assert np.abs(interior(o.arrays["temp"]) - t0).max() < 1e-12

@@ -20,12 +20,12 @@ class Case:
     """Synthetic case prepared with the oracle's xctilr/bigrid (CPU)."""
 
     def __init__(self, config="tiny2", ntr=0, nstep=1, land=True, metric="tripolar", seed=20240611,
-                 isopycnic=False):
+                 isopycnic=False, **synth_kw):
         itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS[config]
         self.config = config
         self.dims = (itdm, jtdm, kdm, nreg)
         self.ntr, self.nstep = ntr, nstep
-        self.syn = synth.make_synth(config, ntr=ntr, land=land, metric=metric, seed=seed)
+        self.syn = synth.make_synth(config, ntr=ntr, land=land, metric=metric, seed=seed, **synth_kw)
         self.grid = self.syn.grid()
         self.state = self.syn.state(self.grid)
         self.scalars = self.syn.scalars(nstep)
