@@ -708,7 +708,7 @@ __device__ __forceinline__ void pc_limit(double ssc, double scc, double xm, doub
 }
 
 template <int DIR, int NT, int TP, int TC, int VAR>
-__global__ void __launch_bounds__(TP* TC, DIR == 0 ? 2 : 1)
+__global__ void __launch_bounds__(TP* TC, TP* TC <= 256 ? 2 : 1)
 cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */, int kchunk,
           const double* __restrict__ dp_src, double* __restrict__ dp_dst, ScalarPtrs<NT> S,
           const double* __restrict__ hel3, const double* __restrict__ her3,
@@ -1143,7 +1143,8 @@ void launch_flux_shape(bool second_pass, int n, const double* dp_src, double* dp
 
 // Tile shape of the flux kernel: TP positions along the pass (TP-5 of them updated) x TC across it.
 // i pass: 128 x 2.  j pass: lanes must run along i, so the tile is TC wide in i and TP long in j;
-// 32 x 16 recomputes 5 of 32 rows, 64 x 8 only 5 of 64 (development switch cppm_j_tile).
+// 32 x 16 recomputes 5 of 32 rows, 64 x 8 only 5 of 64, 32 x 8 gives two resident blocks of 256
+// threads instead of one of 512 (development switch cppm_j_tile).
 template <int DIR, int NT, int VAR>
 void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, const ScalarPtrs<NT>& S,
                  const double* hel3, const double* her3, const double* cad, const double* cac,
@@ -1153,7 +1154,11 @@ void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, 
     launch_flux_shape<DIR, NT, VAR, 128, 2>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
                                             scpd, tab, sten, flx, tflx, sflx);
   else {
-    if (C().option("cppm_j_tile", CPPM_J_TILE_DEFAULT) == "64x8")
+    const std::string jt = C().option("cppm_j_tile", CPPM_J_TILE_DEFAULT);
+    if (jt == "32x8")
+      launch_flux_shape<DIR, NT, VAR, 32, 8>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
+                                             scpd, tab, sten, flx, tflx, sflx);
+    else if (jt == "64x8")
       launch_flux_shape<DIR, NT, VAR, 64, 8>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
                                              scpd, tab, sten, flx, tflx, sflx);
     else

@@ -269,8 +269,11 @@ void diffus_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
 void tmsmt1_dev(int nn) {
   Ctx& c = C(); const Geom& g = c.g;
   const bool isopyc = c.option("vcoord", "cntiso_hybrid") == "isopyc_bulkml";
-  const dim3 grid = lgrid(g, dim3(cdiv(g.ii, 128), g.jj, g.kdm));
-  LAUNCH(tmsmt1_kernel, grid, 128, 0, g, nn, isopyc, c.idev("ip"), c.idev("iu"), c.idev("iv"), c.dev("dp"),
+  // pure copy of three fields with two masks: nothing 2-D worth keeping in cache, and the plane order
+  // measured faster (0.79 vs 0.89 ms at tnx0.25v4)
+  Geom gp = g; gp.lf = 0;
+  const dim3 grid(cdiv(g.ii, 128), g.jj, g.kdm);
+  LAUNCH(tmsmt1_kernel, grid, 128, 0, gp, nn, isopyc, c.idev("ip"), c.idev("iu"), c.idev("iv"), c.dev("dp"),
          c.dev("temp"), c.dev("saln"), c.dev("dpold"), c.dev("told"), c.dev("sold"),
          g.ntr ? c.dev("trc") : nullptr, g.ntr ? c.dev("trcold") : nullptr, isopyc ? c.dev("dpu") : nullptr,
          isopyc ? c.dev("dpv") : nullptr, isopyc ? c.dev("dpuold") : nullptr, isopyc ? c.dev("dpvold") : nullptr);
