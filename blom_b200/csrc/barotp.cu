@@ -605,7 +605,11 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
 #undef BT_SHAPE
   // measured at tnx0.25v4 (512x2): 24.0 ms with the L2 prefetch, 22.9 without - off by default
   const int pf = std::min(2, std::max(0, std::stoi(c.option("barotp_prefetch", "0"))));   // 1: mask look-ahead, 2: + L2 prefetch
-  const std::string shape_opt = c.option("barotp_shape", BT_SHAPE_DEFAULT);
+  // default: 768x2 where every thread walks several cells per phase (1.67 M points at tnx0.25v4: 21.5 ms
+  // against 22.7 for 512x2), 512x2 (no spills) where a phase is a single cell per thread and the time
+  // goes into the chain of one cell plus the grid barrier (tnx1v4: 2.05 ms against 2.46)
+  const bool many_cells = (long)(g.ii + 3) * (g.jj + 4) >= 4L * 148 * 1536;
+  const std::string shape_opt = c.option("barotp_shape", many_cells ? BT_SHAPE_DEFAULT : "512x2");
   const Shape* shape = nullptr;
   for (const Shape& sh : shapes) if (shape_opt == sh.name) shape = &sh;
   if (!shape) throw std::runtime_error("barotp: unknown barotp_shape " + shape_opt);
