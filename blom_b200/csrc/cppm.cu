@@ -1155,7 +1155,9 @@ void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, 
                                             scpd, tab, sten, flx, tflx, sflx);
   else {
     const std::string jt = C().option("cppm_j_tile", CPPM_J_TILE_DEFAULT);
-    if (jt == "32x8")
+    // with two passive tracers (NT = 4) a 16-wide tile needs 232 KB of shared memory, more than the
+    // 227 KB a block may have: the 8-wide tile (116 KB) is used instead
+    if (NT >= 4 || jt == "32x8")
       launch_flux_shape<DIR, NT, VAR, 32, 8>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
                                              scpd, tab, sten, flx, tflx, sflx);
     else if (jt == "64x8")

@@ -106,3 +106,37 @@ def test_fuk95_geostrophic_adjustment_on_gpu():
             assert err <= 1e-6, (nm, err)
     finally:
         g.finalize()
+
+
+@pytest.mark.parametrize("cfg", ["tiny2", "tiny4"])
+def test_chained_step_two_passive_tracers(cfg):
+    """ntr = 2 (the largest tracer count the transport kernels are instantiated for): one chained
+    step, every registered array against the oracle after every routine, parity build, 1e-10."""
+    c = Case(cfg, ntr=2, nstep=1)
+    o = c.new_oracle(); g = c.new_gpu(parity=True)
+    try:
+        for b in (o, g):
+            b.inieos(); b.numerical_bounds(); b.init_cppm()
+        lv = time_levels(1, c.dims[2])
+        for r in [r for r in STEP_SEQUENCE if r in available_routines()]:
+            run_routine(o, r, lv); run_routine(g, r, lv)
+            g.download_all()
+            bad = [(nm, max_rel_err(interior(a), interior(o.arrays[nm]))) for nm, a in g.arrays.items()
+                   if nm not in SKIP and a.dtype == np.float64]
+            bad = [(nm, e) for nm, e in bad if not e <= 1e-10]
+            assert not bad, (cfg, r, sorted(bad, key=lambda t: -t[1])[:6])
+        assert np.abs(interior(g.arrays["trc"])).max() > 0
+    finally:
+        g.finalize()
+
+
+def test_three_passive_tracers_rejected():
+    from blom_b200.lib import BlomGpuError
+    c = Case("tiny1", ntr=3, nstep=1)
+    g = c.new_gpu(parity=True)
+    try:
+        g.inieos(); g.numerical_bounds(); g.init_cppm()
+        with pytest.raises(BlomGpuError, match="at most 2 passive tracers"):
+            g.advect(*c.levels)
+    finally:
+        g.finalize()
