@@ -36,7 +36,7 @@ def run_pair(cfg, ntr, nstep, parity, align="1"):
 
 @pytest.mark.parametrize("cfg", ["tiny0", "tiny1", "tiny2", "tiny3", "tiny4", "fuk95"])
 @pytest.mark.parametrize("align", ["1", "0"])
-@pytest.mark.parametrize("ntr", [0, 1])
+@pytest.mark.parametrize("ntr", [0, 1, 2])
 def test_ndiff_parity_build(cfg, align, ntr):
     c, o, g, nd_o, nd_g = run_pair(cfg, ntr, 1, True, align)
     try:

@@ -26,7 +26,7 @@ def run_pair(cfg, ntr, nstep, parity):
 
 @pytest.mark.parametrize("cfg", ["tiny0", "tiny1", "tiny2", "tiny3", "tiny4"])
 @pytest.mark.parametrize("nstep", [1, 2])
-@pytest.mark.parametrize("ntr", [0, 1])
+@pytest.mark.parametrize("ntr", [0, 1, 2])
 def test_remap_parity_build(cfg, nstep, ntr):
     c, o, g = run_pair(cfg, ntr, nstep, parity=True)
     try:
