@@ -56,7 +56,8 @@ KERNELS = {
     "diffus_flux": (4 + 4 + 4 + 4, "3d"), "diffus_update": (7 + 3, "3d"),
     "pg_p_from_dp": (2, "3d"), "pg_dpuv": (1 + 4, "3d"), "pg_dynh_march": (5 + 8, "3d"), "pg_finalize": (4, "3d"),
     "mt_pressures": (3 + 3, "3d"), "mt_drag": (3, "3d"), "mt_aux": (4 + 7, "3d"), "mt_vort": (7 + 4, "3d"),
-    "mt_visc": (2 + 4, "3d"), "mt_update": (21 + 2, "3d"), "mt_update_v": (21 + 2, "3d"), "mt_column": (8 + 4, "3d"),
+    "mt_visc": (2 + 4, "3d"), "mt_flux1": (10 + 2, "3d"),   # R dpu,vsc2u,vsc4u,u,dl2u (+ v set)  W uflux1,vflux1
+     "mt_update": (21 + 2, "3d"), "mt_update_v": (21 + 2, "3d"), "mt_column": (8 + 4, "3d"),
     "bt_subcycle": (53, "bt"), "bt_ueq": (23, "2d"), "bt_veq": (23, "2d"), "bt_continuity": (7, "2d"),
 }
 BT_WORDS_PER_SUBSTEP = 53  # 46R + 7W distinct 2-D arrays per substep
