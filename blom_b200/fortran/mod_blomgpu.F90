@@ -103,6 +103,21 @@ module mod_blomgpu
          integer(c_int), value :: lev
          real(c_double), intent(out) :: s
       end function
+      integer(c_int) function blomgpu_xcmax(name, lev, mask, s) bind(C, name='blomgpu_xcmax')
+         import :: c_int, c_char, c_double
+         character(kind=c_char), intent(in) :: name(*), mask(*)
+         integer(c_int), value :: lev
+         real(c_double), intent(out) :: s
+      end function
+      integer(c_int) function blomgpu_xcmin(name, lev, mask, s) bind(C, name='blomgpu_xcmin')
+         import :: c_int, c_char, c_double
+         character(kind=c_char), intent(in) :: name(*), mask(*)
+         integer(c_int), value :: lev
+         real(c_double), intent(out) :: s
+      end function
+      integer(c_int) function blomgpu_nreg() bind(C, name='blomgpu_nreg')
+         import :: c_int
+      end function
       integer(c_int) function blomgpu_chksum(name, kcsd, itype, crc) bind(C, name='blomgpu_chksum')
          import :: c_int, c_char, c_int32_t
          character(kind=c_char), intent(in) :: name(*)
@@ -164,7 +179,7 @@ module mod_blomgpu
    procedure(six_int_entry), bind(C, name='blomgpu_cmnfld_nnslope_ale') :: blomgpu_cmnfld_nnslope_ale
 
    public :: gpu_setup, gpu_register, gpu_register_int, gpu_upload, gpu_download, gpu_download_async, &
-             gpu_option, gpu_scalar, gpu_xctilr, &
+             gpu_option, gpu_scalar, gpu_xctilr, gpu_xcsum, gpu_xcmax, gpu_xcmin, gpu_chksum, gpu_nreg, &
              init_fluxes, tmsmt1, eddtra, advect, pbcor1, diffus, pgforc, momtum, &
              barotp, pbcor2, tmsmt2, ndiff, cmnfld2, cmnfld_bfsqf_ale, cmnfld_nslope_ale, &
              cmnfld_nnslope_ale, budget_init, budget_sums
@@ -244,6 +259,44 @@ contains
       integer, intent(in) :: koff, l1, ld, mh, nh, itype
       call check(blomgpu_xctilr(cstr(name), koff, l1, ld, mh, nh, itype), 'xctilr '//name)
    end subroutine gpu_xctilr
+
+   ! xcsum / xcmax / xcmin of level lev of a registered field over mask 'ip'|'iu'|'iv'|'iq'
+   ! (phy/mod_xc.F90:2071, 1157, 1285): same strip order as the reference, bit-reproducible
+   subroutine gpu_xcsum(s, name, lev, mask)
+      real(c_double), intent(out) :: s
+      character(len=*), intent(in) :: name, mask
+      integer, intent(in) :: lev
+      call check(blomgpu_xcsum(cstr(name), int(lev, c_int), cstr(mask), s), 'xcsum '//name)
+   end subroutine gpu_xcsum
+
+   subroutine gpu_xcmax(s, name, lev, mask)
+      real(c_double), intent(out) :: s
+      character(len=*), intent(in) :: name, mask
+      integer, intent(in) :: lev
+      call check(blomgpu_xcmax(cstr(name), int(lev, c_int), cstr(mask), s), 'xcmax '//name)
+   end subroutine gpu_xcmax
+
+   subroutine gpu_xcmin(s, name, lev, mask)
+      real(c_double), intent(out) :: s
+      character(len=*), intent(in) :: name, mask
+      integer, intent(in) :: lev
+      call check(blomgpu_xcmin(cstr(name), int(lev, c_int), cstr(mask), s), 'xcmin '//name)
+   end subroutine gpu_xcmin
+
+   ! chksum(a, kcsd, text) of the reference (phy/mod_checksum.F90:41-74) on the device copy; prints the
+   ! reference's line ' chksum: <text>: 0x%08X' so that csdiag logs can be diffed
+   subroutine gpu_chksum(name, kcsd, itype, text)
+      character(len=*), intent(in) :: name, text
+      integer, intent(in) :: kcsd, itype
+      integer(c_int32_t) :: crc
+      call check(blomgpu_chksum(cstr(name), int(kcsd, c_int), int(itype, c_int), crc), 'chksum '//name)
+      if (mnproc == 1) write (lp, '(3a,z8.8)') ' chksum: ', text, ': 0x', crc
+   end subroutine gpu_chksum
+
+   ! region type found by the device bigrid (0 closed ... 4 periodic in j), phy/mod_xc.F90:54-92
+   integer function gpu_nreg()
+      gpu_nreg = blomgpu_nreg()
+   end function gpu_nreg
 
    ! -- the reference entry points, same names and argument lists ---------------
    subroutine init_fluxes(m, n, mm, nn, k1m, k1n)   ! phy/mod_state.F90:341

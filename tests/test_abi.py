@@ -68,6 +68,24 @@ def test_product_does_not_reference_oracle():
             assert "oracle" not in txt.lower().replace("test oracle", "").replace("the oracle", "") or p.name == "synth.py", p
 
 
+def test_fortran_shim_binds_the_abi():
+    """blom_b200/fortran/mod_blomgpu.F90 cannot be compiled here (no Fortran compiler), so at least its
+    bind(C) names are checked against include/blomgpu.h: every name it binds exists, and everything a
+    Fortran host needs (all but the Python-side instrumentation entries) is bound."""
+    f90 = (ROOT / "blom_b200" / "fortran" / "mod_blomgpu.F90").read_text()
+    bound = set(re.findall(r"bind\(C,\s*name='(blomgpu_\w+)'\)", f90))
+    declared = set(header_symbols())
+    assert bound <= declared, sorted(bound - declared)
+    instrumentation = {"blomgpu_device_ptr", "blomgpu_ktimers_enable", "blomgpu_ktimers_get", "blomgpu_launch_count",
+                       "blomgpu_launch_count_reset", "blomgpu_parity_build", "blomgpu_stream", "blomgpu_timers_enable",
+                       "blomgpu_timers_get", "blomgpu_timers_reset"}
+    assert declared - bound <= instrumentation, sorted(declared - bound - instrumentation)
+    # the reference's entry points keep their names (phy/mod_blom_step.F90:96-227)
+    for name in ("init_fluxes", "tmsmt1", "eddtra", "advect", "pbcor1", "diffus", "pgforc", "momtum", "barotp",
+                 "pbcor2", "tmsmt2"):
+        assert re.search(r"subroutine %s\(" % name, f90), name
+
+
 def test_tools_do_not_reference_oracle():
     """tools/ holds profiling helpers of the product; scripts that need the oracle live in tests/dev/."""
     for p in (ROOT / "tools").glob("*.py"):
