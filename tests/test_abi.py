@@ -80,6 +80,21 @@ def test_fortran_shim_binds_the_abi():
                        "blomgpu_launch_count_reset", "blomgpu_parity_build", "blomgpu_stream", "blomgpu_timers_enable",
                        "blomgpu_timers_get", "blomgpu_timers_reset"}
     assert declared - bound <= instrumentation, sorted(declared - bound - instrumentation)
+    # same number of arguments on both sides of every binding
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "blomgpu.h").read_text(), flags=re.S)
+    nargs_c = {}
+    for m in re.finditer(r"\b(blomgpu_\w+)\s*\(([^)]*)\)\s*;", text):
+        a = m.group(2).strip()
+        nargs_c[m.group(1)] = 0 if a in ("void", "") else len(a.split(","))
+    joined = re.sub(r"&\s*\n\s*", "", f90)
+    nargs_f = {}
+    for m in re.finditer(r"function\s+(blomgpu_\w+)\s*\(([^)]*)\)\s*bind\(C", joined):
+        a = m.group(2).strip()
+        nargs_f[m.group(1)] = 0 if a == "" else len(a.split(","))
+    for m in re.finditer(r"procedure\(six_int_entry\),\s*bind\(C,\s*name='(blomgpu_\w+)'\)", joined):
+        nargs_f[m.group(1)] = 6
+    assert set(nargs_f) == bound
+    assert not [(k, nargs_c[k], v) for k, v in nargs_f.items() if nargs_c[k] != v]
     # the reference's entry points keep their names (phy/mod_blom_step.F90:96-227)
     for name in ("init_fluxes", "tmsmt1", "eddtra", "advect", "pbcor1", "diffus", "pgforc", "momtum", "barotp",
                  "pbcor2", "tmsmt2"):
