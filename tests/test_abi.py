@@ -68,6 +68,22 @@ def test_product_does_not_reference_oracle():
             assert "oracle" not in txt.lower().replace("test oracle", "").replace("the oracle", "") or p.name == "synth.py", p
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/blomgpu.h compiles as C99 (no C++ or torch types) and a C
+    program links against the library and calls it."""
+    import subprocess
+    _ensure_built()
+    src = tmp_path / "host.c"
+    src.write_text('#include "blomgpu.h"\nint main(void) { return blomgpu_parity_build(); }\n')
+    exe = tmp_path / "host"
+    libdir = blib.library_path(False).parent
+    for lib, expect in (("blomgpu", 0), ("blomgpu_parity", 1)):
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"),
+                        str(src), "-o", str(exe), "-L", str(libdir), f"-l{lib}", f"-Wl,-rpath,{libdir}"],
+                       check=True, capture_output=True)
+        assert subprocess.run([str(exe)]).returncode == expect
+
+
 def test_fortran_shim_binds_the_abi():
     """blom_b200/fortran/mod_blomgpu.F90 cannot be compiled here (no Fortran compiler), so at least its
     bind(C) names are checked against include/blomgpu.h: every name it binds exists, and everything a
