@@ -100,3 +100,22 @@ def test_gloo_two_ranks_band_state_and_exchange():
                                   s1["temp"][:, nb + lo["jj"]:nb + lo["jj"] + nh, nb:nb + itdm])
     np.testing.assert_array_equal(hi["temp"][:, nb - nh:nb, nb:nb + itdm],
                                   s1["temp"][:, nb + hi["j0"] - nh:nb + hi["j0"], nb:nb + itdm])
+
+
+def test_fuk95_bands_equal_one_tile():
+    """The analytic fuk95 generator is a pure function of global indices: the j-bands of a 2- and a
+    4-rank decomposition hold exactly the rows of the one-tile state (what lets a multi-GPU run be
+    compared band by band with the one-tile run and the oracle)."""
+    from blom_b200.fuk95 import Fuk95
+    one = Fuk95(ntr=1)
+    g1 = one.grid(); s1 = one.state(g1)
+    nb = 4
+    for world in (2, 4):
+        for rank in range(world):
+            j0, jj = band(32, rank, world)
+            b = Fuk95(ntr=1, j0=j0, jj=jj)
+            gb = b.grid(); sb = b.state(gb)
+            for nm in ("depths", "scpx", "corioq"):
+                assert np.array_equal(gb[nm][:, nb:nb + jj, nb:-nb], g1[nm][:, nb + j0:nb + j0 + jj, nb:-nb]), nm
+            for nm in ("dp", "temp", "saln", "sigma", "trc", "phi", "pb", "difiso", "dpuold", "dpvold"):
+                assert np.array_equal(sb[nm][:, nb:nb + jj, nb:-nb], s1[nm][:, nb + j0:nb + j0 + jj, nb:-nb]), (world, rank, nm)
