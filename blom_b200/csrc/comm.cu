@@ -1,8 +1,10 @@
 // Multi-GPU plumbing for j-band tiles: replaces the MPI half of mod_xc
 // (phy/mod_xc.F90:2954-3188 xctilr_nonarctic N/S exchange, :2071-2192 xcsum
-// gather, :1157-1201 xcmax allreduce) with NCCL point-to-point / collectives on
-// the library stream over NVLink.  NCCL is dlopen'ed at comm_init time so a
-// single-GPU run has no NCCL dependency.
+// gather, :1157-1201 xcmax allreduce).  Band edges go through peer-memory mailboxes
+// over NVLink (CUDA IPC; p2p_push / p2p_unpack below and the in-kernel exchange of
+// barotp.cu) when peer access exists, else through NCCL send/recv groups on the
+// library stream; the reductions use NCCL collectives.  NCCL is dlopen'ed at
+// comm_init time so a single-GPU run has no NCCL dependency.
 #include "common.cuh"
 #include "p2p.cuh"
 #include "../../include/blomgpu.h"
