@@ -90,9 +90,23 @@ struct P2P {
 };
 P2P g_p2p;
 
+// Two-phase teardown: every rank first closes its mappings of the neighbours' mailboxes, then all ranks
+// meet in an NCCL barrier, and only then is the exported block freed (freeing IPC-exported memory that
+// an importer still maps is undefined).  Collective whenever the mailboxes are in use (q.on is agreed
+// by all ranks in p2p_setup), which holds for the capacity-growth path and for blomgpu_finalize.
 void p2p_close() {
   P2P& q = g_p2p;
+  Ctx& c = C();
   for (int d = 0; d < 2; ++d) if (q.peer[d]) { cudaIpcCloseMemHandle(q.peer[d]); q.peer[d] = nullptr; }
+  if (q.on && c.nccl && c.g.nranks > 1 && c.stream) {
+    int* d_b = nullptr;
+    if (cudaMalloc(&d_b, sizeof(int)) == cudaSuccess) {
+      cudaMemsetAsync(d_b, 0, sizeof(int), c.stream);
+      N.AllReduce(d_b, d_b, 1, ncclInt, ncclSum, (ncclComm_t)c.nccl, c.stream);
+      cudaStreamSynchronize(c.stream);
+      cudaFree(d_b);
+    }
+  }
   if (q.block) { cudaFree(q.block); q.block = nullptr; }
   q.cap = 0; q.on = false;
 }
@@ -316,7 +330,7 @@ void allreduce_minmax(double* d_val, bool is_max) {
 }  // namespace blom
 
 using namespace blom;
-static char g_cerr[512];
+namespace blom { void set_last_error(const char* msg); }   // ctx.cu
 extern "C" {
 int blomgpu_comm_unique_id(char id[128]) {
   try {
@@ -326,7 +340,7 @@ int blomgpu_comm_unique_id(char id[128]) {
     static_assert(sizeof(u) == 128, "ncclUniqueId size");
     std::memcpy(id, &u, 128);
     return 0;
-  } catch (const std::exception& e) { std::fprintf(stderr, "blomgpu error: %s\n", e.what()); return 1; }
+  } catch (const std::exception& e) { set_last_error(e.what()); return 1; }
 }
 int blomgpu_comm_init(const char id[128], int rank, int nranks) {
   try {
@@ -336,6 +350,6 @@ int blomgpu_comm_init(const char id[128], int rank, int nranks) {
     NCCL_CHECK(N.CommInitRank(&comm, nranks, u, rank));
     C().nccl = comm;
     return 0;
-  } catch (const std::exception& e) { std::fprintf(stderr, "blomgpu error: %s\n", e.what()); return 1; }
+  } catch (const std::exception& e) { set_last_error(e.what()); return 1; }
 }
 }

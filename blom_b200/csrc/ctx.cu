@@ -72,6 +72,13 @@ ScopedTimer::~ScopedTimer() {
 using namespace blom;
 
 static char g_err[2048] = "";
+namespace blom {
+// comm.cu reports through the same buffer, so blomgpu_last_error() covers the blomgpu_comm_* entries
+void set_last_error(const char* msg) {
+  std::snprintf(g_err, sizeof g_err, "%s", msg);
+  std::fprintf(stderr, "blomgpu error: %s\n", g_err);
+}
+}
 
 #define GUARD(...)                                          \
   try { __VA_ARGS__; return 0; }                            \
@@ -81,6 +88,7 @@ static char g_err[2048] = "";
     return 1;                                               \
   }
 
+static void do_finalize();
 static void do_init(const int* dims, const int* tile, int device) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -88,6 +96,9 @@ static void do_init(const int* dims, const int* tile, int device) {
     throw std::runtime_error("blomgpu_init: no CUDA device available (this library has no CPU fallback)");
   CUDA_CHECK(cudaSetDevice(device));
   Ctx& c = C();
+  // a second init without finalize (e.g. a host that aborted a run half way) must not inherit device
+  // arrays sized for the previous tile: release everything first
+  if (c.d_red || !c.f.empty() || !c.fi.empty()) do_finalize();
   Geom& g = c.g;
   g.itdm = dims[0]; g.jtdm = dims[1]; g.kdm = dims[2]; g.idm = dims[3]; g.jdm = dims[4];
   g.nb = dims[5]; g.ntr = dims[6]; g.nreg = dims[7];
@@ -209,6 +220,19 @@ static const int* mask_for_itype(int itype) {
   }
 }
 
+// Halo refreshes that difest_lateral_hybrid / difest_isobml (phy/mod_difest.F90:826-831) and cmnfld2
+// (phy/mod_cmnfld_routines.F90:1171-1172) issue between tmsmt1 and eddtra.  Those routines are out of scope
+// (column physics), but momtum and eddtra rely on the halo validity they leave behind (SURVEY.md appendix A,
+// validity chain 1 and 6), so a host that keeps the state device-resident calls this entry in their place.
+// Two batched launches instead of eight xctilr calls; identical result (the fields are independent).
+static void difest_halos_dev() {
+  Ctx& c = C(); const int kk = c.g.kdm;
+  halo_update(std::vector<HaloReq>{{c.dev("u"), 2 * kk, halo_uv}, {c.dev("v"), 2 * kk, halo_vv},
+                                   {c.dev("ubflxs_p"), 2, halo_uv}, {c.dev("vbflxs_p"), 2, halo_vv},
+                                   {c.dev("pbu"), 2, halo_us}, {c.dev("pbv"), 2, halo_vs}}, 2, 2);
+  halo_update(std::vector<HaloReq>{{c.dev("temp"), 2 * kk, halo_ps}, {c.dev("saln"), 2 * kk, halo_ps}}, 3, 3);
+}
+
 static int not_impl(const char* what) {
   std::snprintf(g_err, sizeof g_err, "blomgpu: %s is not implemented in this build", what);
   std::fprintf(stderr, "%s\n", g_err);
@@ -289,6 +313,10 @@ int blomgpu_inieos(void) { GUARD(inieos_dev()) }
 int blomgpu_numerical_bounds(void) { GUARD(numerical_bounds_dev()) }
 int blomgpu_init_fluxes(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(init_fluxes_dev(m, n, mm, nn, k1m, k1n)) }
 
+int blomgpu_difest_halos(int m, int n, int mm, int nn, int k1m, int k1n) {
+  (void)m; (void)n; (void)mm; (void)nn; (void)k1m; (void)k1n;
+  GUARD(ScopedTimer t("difest_halos"); difest_halos_dev())
+}
 int blomgpu_tmsmt1(int nn) { GUARD(ScopedTimer t("tmsmt1"); tmsmt1_dev(nn)) }
 int blomgpu_eddtra(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("eddtra"); eddtra_dev(m, n, mm, nn, k1m, k1n)) }
 int blomgpu_advect(int m, int n, int mm, int nn, int k1m, int k1n) { GUARD(ScopedTimer t("advect"); advect_dev(m, n, mm, nn, k1m, k1n)) }

@@ -4,14 +4,20 @@ that this package replaces, on synthetic state.
 `HotPath` owns one BlomGpu tile, builds its band of the synthetic state, and runs
 the reference's call order for the routines on the path:
 
-    init_fluxes -> tmsmt1 -> [eddtra] -> advect -> [pbcor1] -> diffus -> pgforc
-                -> [momtum] -> barotp -> [pbcor2] -> tmsmt2
+    init_fluxes -> tmsmt1 -> [difest_halos] -> [ndiff] -> eddtra -> advect -> pbcor1 -> diffus
+                -> pgforc -> momtum -> barotp -> pbcor2 -> tmsmt2
 
 Routines that the reference runs in between (ALE regrid, cmnfld2, difest, column
 physics, forcing) are out of scope; the halo refreshes those routines would have
 done for the path (phy/mod_difest.F90:826-831, phy/mod_cmnfld_routines.F90:1171-1172)
-are issued here so that the chain stays valid on device.  Bracketed routines run
-only when this build provides them (`available_routines`).
+are issued through `blomgpu_difest_halos` so that the chain stays valid on device.
+`ndiff` (neutral diffusion, called from inside the ALE slice pipeline,
+phy/mod_ale_regrid_remap.F90:1607-1690) is on the path whenever ltedtp='neutral',
+which is the reference's default for the hybrid coordinate.
+
+Option sets follow the reference's namelist defaults per vertical coordinate and grid
+(cime_config/namelist_definition_blom.xml:367-460,1548-1575,1851-1862), see
+`reference_options`.
 """
 from __future__ import annotations
 
@@ -20,13 +26,45 @@ import os
 import numpy as np
 
 from . import synth
-from .lib import (BlomGpu, BlomGpuError, time_levels, HALO_PS, HALO_UV, HALO_VV, HALO_US, HALO_VS)
+from .lib import BlomGpu, BlomGpuError, time_levels  # noqa: F401
 
-# reference order of one baroclinic step (phy/mod_blom_step.F90:96-227)
-STEP_SEQUENCE = ["init_fluxes", "tmsmt1", "eddtra", "advect", "pbcor1", "diffus", "pgforc", "momtum",
+# reference order of one baroclinic step (phy/mod_blom_step.F90:96-227); `ndiff` runs only with
+# ltedtp='neutral', inside ale_regrid_remap (:128), i.e. between tmsmt1 and eddtra
+STEP_SEQUENCE = ["init_fluxes", "tmsmt1", "ndiff", "eddtra", "advect", "pbcor1", "diffus", "pgforc", "momtum",
                  "barotp", "pbcor2", "tmsmt2"]
 # prognostic arrays that cross the host<->device boundary in the end-to-end leg
 IO_FIELDS = ("dp", "temp", "saln", "u", "v", "trc")
+
+
+def reference_options(config: str, vcoord: str = "cntiso_hybrid") -> dict:
+    """Namelist defaults the reference's build system writes for this grid and vertical coordinate
+    (cime_config/namelist_definition_blom.xml: mommth :367, pgfmth :377, bmcmth :388, advmth :399,
+    mlrmth :440, eitmth :1548, ltedtp :1851-1862)."""
+    if vcoord == "isopyc_bulkml":
+        return {"vcoord": vcoord, "mommth": "enscon", "pgfmth": "geopotential", "bmcmth": "uc", "advmth": "remap",
+                "mlrmth": "fox08", "eitmth": "gm", "ltedtp": "layer"}
+    return {"vcoord": vcoord, "mommth": "enscon", "pgfmth": "dynamic enthalpy", "bmcmth": "dluc", "advmth": "cppm",
+            "mlrmth": "bod23", "eitmth": "gm", "ltedtp": "layer" if config == "tnx0.125v4" else "neutral"}
+
+
+def step_routines(options: dict, routines=None):
+    """The routines of STEP_SEQUENCE that run under this option set (optionally restricted)."""
+    seq = [r for r in STEP_SEQUENCE if r != "ndiff" or options.get("ltedtp") == "neutral"]
+    return [r for r in seq if routines is None or r in routines]
+
+
+def run_step(b, routines, levels):
+    """One pass of the hot path on backend `b` (BlomGpu, or the test oracle which mirrors its
+    interface).  Same call order and arguments as phy/mod_blom_step.F90:96-227."""
+    m, n, mm, nn, k1m, k1n = levels
+    for r in routines:
+        if r == "tmsmt1":
+            b.tmsmt1(nn)
+            b.difest_halos(m, n, mm, nn, k1m, k1n)
+        elif r == "tmsmt2":
+            b.tmsmt2(m, mm, nn, k1m)
+        else:
+            getattr(b, r)(m, n, mm, nn, k1m, k1n)
 
 
 def band(jtdm: int, rank: int, nranks: int):
@@ -37,13 +75,8 @@ def band(jtdm: int, rank: int, nranks: int):
     return j0, jj
 
 
-def available_routines():
-    """Routines of STEP_SEQUENCE implemented by the loaded library (stubs raise)."""
-    return list(STEP_SEQUENCE)
-
-
 class HotPath:
-    def __init__(self, config="tnx1v4", *, ntr=0, nstep=1, rank=0, nranks=1, device=0, parity=False,
+    def __init__(self, config="tnx1v4", *, ntr=0, nstep=1, rank=0, nranks=1, device=0, parity=True,
                  comm_uid: bytes | None = None, routines=None, seed=20240611, options=None,
                  pinned_alloc=None):
         itdm, jtdm, kdm, nreg, baclin, batrop = synth.CONFIGS[config]
@@ -53,6 +86,11 @@ class HotPath:
         self.rank, self.nranks = rank, nranks
         j0, jj = band(jtdm, rank, nranks)
         self.j0, self.jj = j0, jj
+        # namelist options: reference defaults for this grid, then BLOM_OPTIONS="key=value,..." (development
+        # A/B switches, e.g. momtum_form=staged), then the caller's
+        env_opts = dict(kv.split("=", 1) for kv in os.environ.get("BLOM_OPTIONS", "").split(",") if "=" in kv)
+        self.options = {**reference_options(config), **env_opts, **(options or {})}
+        self.routines = step_routines(self.options, routines)
         self.syn = synth.make_synth(config, ntr=ntr, j0=j0, jj=jj, seed=seed)
         self.grid = self.syn.grid()
         self.state = self.syn.state(self.grid)
@@ -71,9 +109,7 @@ class HotPath:
             if comm_uid is None:
                 raise ValueError("multi-rank HotPath needs the NCCL unique id")
             g.comm_init(comm_uid)
-        # development A/B switches: BLOM_OPTIONS="key=value,key=value" (e.g. momtum_form=staged)
-        env_opts = dict(kv.split("=", 1) for kv in os.environ.get("BLOM_OPTIONS", "").split(",") if "=" in kv)
-        for k, v in {**env_opts, **(options or {})}.items():
+        for k, v in self.options.items():
             g.set_option(k, v)
         self.arrays = {**self.grid, **self.state}
         g.register_all(self.arrays)
@@ -86,7 +122,11 @@ class HotPath:
                      sync_in=lambda names: [g.upload(n) for n in names],
                      sync_out=lambda names: [g.download(n) for n in names])
         g.upload_all()
-        self.routines = [r for r in STEP_SEQUENCE if r in (routines or available_routines())]
+        if "ndiff" in self.routines:
+            # products of the (out-of-scope) ALE slice pipeline that neutral diffusion consumes
+            nd = synth.ndiff_inputs(self.syn, self.state, self.levels, ntr=ntr)
+            g.register_all(nd)
+            self.arrays.update(nd)
         self.setup()
 
     def setup(self):
@@ -107,17 +147,6 @@ class HotPath:
         self.levels = time_levels(nstep, self.kdm)
         self.gpu.set_scalar("nstep", nstep)
 
-    def halo_refresh_out_of_scope(self):
-        """Halo updates that out-of-scope routines (difest, cmnfld2, ALE) issue between the
-        hot-path routines; kept so the on-device chain sees the validity the reference has."""
-        g, kk = self.gpu, self.kdm
-        g.xctilr("u", 1, 2 * kk, 2, 2, HALO_UV)          # phy/mod_difest.F90:826-827
-        g.xctilr("v", 1, 2 * kk, 2, 2, HALO_VV)
-        for nm, it in (("ubflxs_p", HALO_UV), ("vbflxs_p", HALO_VV), ("pbu", HALO_US), ("pbv", HALO_VS)):
-            g.xctilr(nm, 1, 2, 2, 2, it)                 # phy/mod_difest.F90:828-831
-        g.xctilr("temp", 1, 2 * kk, 3, 3, HALO_PS)       # phy/mod_cmnfld_routines.F90:1171-1172
-        g.xctilr("saln", 1, 2 * kk, 3, 3, HALO_PS)
-
     # fields no routine after `momtum` writes (barotp works on ub/vb/pb, pbcor2 and tmsmt2 on
     # dp/T/S/trc, phy/mod_blom_step.F90:169-227): their download can overlap the rest of the step
     FINAL_AFTER = {"momtum": ("u", "v")}
@@ -126,21 +155,16 @@ class HotPath:
         """One pass of the hot path over the resident state.  early_download: start the device ->
         host copy of a field on the copy stream as soon as its last writer has been enqueued."""
         g = self.gpu
-        m, n, mm, nn, k1m, k1n = self.levels
         self._early = set()
+        if not early_download:
+            run_step(g, self.routines, self.levels)
+            return
         for r in self.routines:
-            if r == "tmsmt1":
-                g.tmsmt1(nn)
-                self.halo_refresh_out_of_scope()
-            elif r == "tmsmt2":
-                g.tmsmt2(m, mm, nn, k1m)
-            else:
-                getattr(g, r)(m, n, mm, nn, k1m, k1n)
-            if early_download:
-                for nm in self.FINAL_AFTER.get(r, ()):
-                    if nm in self.arrays:
-                        g.download_async(nm)
-                        self._early.add(nm)
+            run_step(g, [r], self.levels)
+            for nm in self.FINAL_AFTER.get(r, ()):
+                if nm in self.arrays:
+                    g.download_async(nm)
+                    self._early.add(nm)
 
     def advance(self, early_download=False):
         """step() followed by the leap-frog role swap of the time levels."""

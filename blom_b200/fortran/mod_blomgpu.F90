@@ -164,6 +164,7 @@ module mod_blomgpu
       end function
    end interface
    procedure(six_int_entry), bind(C, name='blomgpu_init_fluxes') :: blomgpu_init_fluxes
+   procedure(six_int_entry), bind(C, name='blomgpu_difest_halos') :: blomgpu_difest_halos
    procedure(six_int_entry), bind(C, name='blomgpu_eddtra') :: blomgpu_eddtra
    procedure(six_int_entry), bind(C, name='blomgpu_advect') :: blomgpu_advect
    procedure(six_int_entry), bind(C, name='blomgpu_pbcor1') :: blomgpu_pbcor1
@@ -180,7 +181,7 @@ module mod_blomgpu
 
    public :: gpu_setup, gpu_register, gpu_register_int, gpu_upload, gpu_download, gpu_download_async, &
              gpu_option, gpu_scalar, gpu_xctilr, gpu_xcsum, gpu_xcmax, gpu_xcmin, gpu_chksum, gpu_nreg, &
-             init_fluxes, tmsmt1, eddtra, advect, pbcor1, diffus, pgforc, momtum, &
+             init_fluxes, tmsmt1, difest_halos, eddtra, advect, pbcor1, diffus, pgforc, momtum, &
              barotp, pbcor2, tmsmt2, ndiff, cmnfld2, cmnfld_bfsqf_ale, cmnfld_nslope_ale, &
              cmnfld_nnslope_ale, budget_init, budget_sums
 
@@ -306,6 +307,11 @@ contains
    subroutine tmsmt1(nn)                            ! phy/mod_tmsmt.F90:209
       integer, intent(in) :: nn
       call check(blomgpu_tmsmt1(nn), 'tmsmt1')
+   end subroutine
+   ! halo refreshes of difest_lateral_hybrid / cmnfld2 on the device-resident state
+   subroutine difest_halos(m, n, mm, nn, k1m, k1n)  ! phy/mod_difest.F90:826-831, phy/mod_cmnfld_routines.F90:1171
+      integer, intent(in) :: m, n, mm, nn, k1m, k1n
+      call check(blomgpu_difest_halos(m, n, mm, nn, k1m, k1n), 'difest_halos')
    end subroutine
    subroutine eddtra(m, n, mm, nn, k1m, k1n)        ! phy/mod_eddtra.F90:1808
       integer, intent(in) :: m, n, mm, nn, k1m, k1n

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "blomgpu_xctilr", "blomgpu_xcsum", "blomgpu_xcmax", "blomgpu_xcmin", "blomgpu_chksum",
     "blomgpu_bigrid", "blomgpu_nreg", "blomgpu_init_cppm", "blomgpu_inieos",
     "blomgpu_numerical_bounds", "blomgpu_init_fluxes",
-    "blomgpu_tmsmt1", "blomgpu_eddtra", "blomgpu_advect", "blomgpu_pbcor1", "blomgpu_diffus",
+    "blomgpu_tmsmt1", "blomgpu_difest_halos", "blomgpu_eddtra", "blomgpu_advect", "blomgpu_pbcor1", "blomgpu_diffus",
     "blomgpu_pgforc", "blomgpu_momtum", "blomgpu_barotp", "blomgpu_pbcor2", "blomgpu_tmsmt2",
     "blomgpu_ndiff", "blomgpu_cmnfld2", "blomgpu_cmnfld_bfsqf_ale", "blomgpu_cmnfld_nslope_ale",
     "blomgpu_cmnfld_nnslope_ale", "blomgpu_budget_init", "blomgpu_budget_sums",
@@ -221,6 +221,9 @@ class BlomGpu:
 
     def _six(self, fn, m, n, mm, nn, k1m, k1n):
         self._ck(fn(m, n, mm, nn, k1m, k1n))
+
+    def difest_halos(self, *a):
+        self._six(self.lib.blomgpu_difest_halos, *a)
 
     def eddtra(self, *a):
         self._six(self.lib.blomgpu_eddtra, *a)

@@ -196,7 +196,9 @@ class Synth:
             depth[:, -1] = 0.0
         if nreg == 2:
             depth[-3:, :] = np.maximum(depth[-3:, :], 300.0)  # open water at the fold
-        for _ in range(50):
+        # remove wet cells with three or more dry neighbours until none is left; every pass dries at
+        # least one cell, so the loop ends for any band height (a short band may need many passes)
+        for _ in range(itdm * jtdm + 1):
             if nreg == 2:
                 depth[-1, :] = depth[-2, ::-1]  # p-grid fold: a(i,jj) = a(ii+1-i,jj-1)
             d = self._pad_global(depth)

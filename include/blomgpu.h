@@ -97,6 +97,12 @@ int blomgpu_init_fluxes(int m, int n, int mm, int nn, int k1m, int k1n);
 
 /* ---- hot-path entry points, same argument lists as the reference -------- */
 int blomgpu_tmsmt1(int nn);                                   /* phy/mod_tmsmt.F90:209 */
+/* The halo refreshes of the (out-of-scope) lateral-diffusivity and common-field routines that run between
+ * tmsmt1 and eddtra: xctilr of u,v (2*kk levels), ubflxs_p, vbflxs_p, pbu, pbv (2 levels) with (2,2)
+ * (phy/mod_difest.F90:826-831) and of temp, saln (2*kk levels) with (3,3)
+ * (phy/mod_cmnfld_routines.F90:1171-1172).  momtum and eddtra rely on them; a host that keeps the state on
+ * the device calls this where difest_lateral_hybrid / cmnfld2 would have refreshed the host arrays. */
+int blomgpu_difest_halos(int m, int n, int mm, int nn, int k1m, int k1n);
 int blomgpu_eddtra(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_eddtra.F90:1808 */
 int blomgpu_advect(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_advect.F90:59 */
 int blomgpu_pbcor1(int m, int n, int mm, int nn, int k1m, int k1n);  /* phy/mod_pbcor.F90:66 */

@@ -182,6 +182,14 @@ class Oracle:
     def barotp(self, *a): self._call("barotp", *a)
     def pbcor2(self, *a): self._call("pbcor2", *a)
     def ndiff(self, *a): self._call("ndiff", *a)
+
+    def difest_halos(self, m, n, mm, nn, k1m, k1n):
+        """xctilr calls of phy/mod_difest.F90:826-831 and phy/mod_cmnfld_routines.F90:1171-1172."""
+        kk = self.kdm
+        self.xctilr("u", 1, 2 * kk, 2, 2, 13); self.xctilr("v", 1, 2 * kk, 2, 2, 14)
+        for nm, it in (("ubflxs_p", 13), ("vbflxs_p", 14), ("pbu", 3), ("pbv", 4)):
+            self.xctilr(nm, 1, 2, 2, 2, it)
+        self.xctilr("temp", 1, 2 * kk, 3, 3, 1); self.xctilr("saln", 1, 2 * kk, 3, 3, 1)
     def cmnfld2(self, *a): self._call("cmnfld2", *a)
     def cmnfld_bfsqf_ale(self, *a): self._call("cmnfld_bfsqf_ale", *a)
     def cmnfld_nslope_ale(self, *a): self._call("cmnfld_nslope_ale", *a)

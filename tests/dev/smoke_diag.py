@@ -4,26 +4,19 @@ usage: python tests/dev/smoke_diag.py [config] [parity 0|1] [each|end]"""
 import sys
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np
-from util import Case, interior
-from blom_b200.driver import available_routines, STEP_SEQUENCE
+from util import Case, interior, prepare_step
+from blom_b200.driver import run_step
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "fuk95"
 parity = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False
 sync_each = (sys.argv[3] != "end") if len(sys.argv) > 3 else True   # "end": download only after the last routine
 c = Case(cfg, ntr=1, nstep=1)
 o = c.new_oracle(); g = c.new_gpu(parity=parity)
-for b in (o, g):
-    b.inieos(); b.numerical_bounds(); b.init_cppm()
-m, n, mm, nn, k1m, k1n = c.levels
+routines, _ = prepare_step(c, (o, g))
 kk = c.dims[2]
-for r in [r for r in STEP_SEQUENCE if r in available_routines()]:
+for r in routines:
     for b in (o, g):
-        if r == "tmsmt1":
-            b.tmsmt1(nn)
-        elif r == "tmsmt2":
-            b.tmsmt2(m, mm, nn, k1m)
-        else:
-            getattr(b, r)(m, n, mm, nn, k1m, k1n)
+        run_step(b, [r], c.levels)
     if not sync_each and r != "tmsmt2":
         continue
     g.download_all()

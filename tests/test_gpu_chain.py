@@ -5,49 +5,47 @@ chained steps, parity build."""
 import numpy as np
 import pytest
 
-from blom_b200.driver import STEP_SEQUENCE, available_routines
+from blom_b200.driver import run_step
 from blom_b200.lib import time_levels
-from util import Case, interior, max_rel_err
+from util import Case, interior, max_rel_err, prepare_step
 
 pytestmark = pytest.mark.gpu
 
 SKIP = {"depths"}
 
 
-def run_routine(b, r, lv):
-    m, n, mm, nn, k1m, k1n = lv
-    if r == "tmsmt1":
-        b.tmsmt1(nn)
-    elif r == "tmsmt2":
-        b.tmsmt2(m, mm, nn, k1m)
-    else:
-        getattr(b, r)(m, n, mm, nn, k1m, k1n)
+# the reference's option set for the hybrid coordinate (neutral diffusion through ndiff, dluc, bod23) and
+# the layer-diffusion / uc / fox08 set (the isopycnic defaults, which exercise diffus' flux branch)
+OPTION_SETS = {"reference": None, "layer": {"ltedtp": "layer", "bmcmth": "uc", "mlrmth": "fox08"}}
 
 
+def compare_all(g, o, what, tol=1e-10):
+    g.download_all()
+    bad = []
+    for nm, a in g.arrays.items():
+        if nm in SKIP or a.dtype != np.float64:
+            continue
+        err = max_rel_err(interior(a), interior(o.arrays[nm]))
+        if not err <= tol:
+            bad.append((nm, err))
+    assert not bad, (what, sorted(bad, key=lambda t: -t[1])[:6])
+
+
+@pytest.mark.parametrize("optset", ["reference", "layer"])
 @pytest.mark.parametrize("cfg", ["tiny0", "tiny1", "tiny2", "tiny3", "tiny4", "fuk95", "fuk95_analytic"])
-def test_chained_steps(cfg):
+def test_chained_steps(cfg, optset):
     c = Case(cfg, ntr=1, nstep=1)
     o = c.new_oracle(); g = c.new_gpu(parity=True)
     try:
-        for b in (o, g):
-            b.inieos(); b.numerical_bounds(); b.init_cppm()
-        routines = [r for r in STEP_SEQUENCE if r in available_routines()]
+        routines, _ = prepare_step(c, (o, g), OPTION_SETS[optset])
         kk = c.dims[2]
         for nstep in (1, 2, 3):
             lv = time_levels(nstep, kk)
             for b in (o, g):
                 b.set_scalar("nstep", nstep)
             for r in routines:
-                run_routine(o, r, lv); run_routine(g, r, lv)
-                g.download_all()
-                bad = []
-                for nm, a in g.arrays.items():
-                    if nm in SKIP or a.dtype != np.float64:
-                        continue
-                    err = max_rel_err(interior(a), interior(o.arrays[nm]))
-                    if not err <= 1e-10:
-                        bad.append((nm, err))
-                assert not bad, (cfg, nstep, r, sorted(bad, key=lambda t: -t[1])[:6])
+                run_step(o, [r], lv); run_step(g, [r], lv)
+                compare_all(g, o, (cfg, nstep, r))
         assert np.isfinite(g.arrays["dp"]).all()
     finally:
         g.finalize()
@@ -84,15 +82,12 @@ def test_fuk95_geostrophic_adjustment_on_gpu():
     o = c.new_oracle(); g = c.new_gpu(parity=True)
     try:
         kk = c.dims[2]
-        for b in (o, g):
-            b.inieos(); b.numerical_bounds(); b.init_cppm()
-        routines = [r for r in STEP_SEQUENCE if r in available_routines()]
+        routines, _ = prepare_step(c, (o, g))
         for nstep in range(1, 161):
             lv = time_levels(nstep, kk)
             for b in (o, g):
                 b.set_scalar("nstep", nstep)
-                for r in routines:
-                    run_routine(b, r, lv)
+                run_step(b, routines, lv)
         g.download_all()
         nn = lv[3]
         scp2 = interior(g.arrays["scp2"])[0]
@@ -115,16 +110,11 @@ def test_chained_step_two_passive_tracers(cfg):
     c = Case(cfg, ntr=2, nstep=1)
     o = c.new_oracle(); g = c.new_gpu(parity=True)
     try:
-        for b in (o, g):
-            b.inieos(); b.numerical_bounds(); b.init_cppm()
+        routines, _ = prepare_step(c, (o, g))
         lv = time_levels(1, c.dims[2])
-        for r in [r for r in STEP_SEQUENCE if r in available_routines()]:
-            run_routine(o, r, lv); run_routine(g, r, lv)
-            g.download_all()
-            bad = [(nm, max_rel_err(interior(a), interior(o.arrays[nm]))) for nm, a in g.arrays.items()
-                   if nm not in SKIP and a.dtype == np.float64]
-            bad = [(nm, e) for nm, e in bad if not e <= 1e-10]
-            assert not bad, (cfg, r, sorted(bad, key=lambda t: -t[1])[:6])
+        for r in routines:
+            run_step(o, [r], lv); run_step(g, [r], lv)
+            compare_all(g, o, (cfg, r))
         assert np.abs(interior(g.arrays["trc"])).max() > 0
     finally:
         g.finalize()

@@ -5,9 +5,13 @@ speed u0 = 0.3 m/s - recovered by the ORACLE running only the hot-path routines.
 import numpy as np
 
 from blom_b200 import fuk95
-from blom_b200.driver import STEP_SEQUENCE
+from blom_b200.driver import run_step, step_routines
 from blom_b200.lib import time_levels
 from util import Case, interior
+
+# library defaults (layer diffusion inside diffus): with ltedtp='neutral' the diffused scalars would only reach
+# T,S through the out-of-scope ALE step
+ROUTINES = step_routines({})
 
 
 def test_geometry_and_initial_state():
@@ -53,13 +57,7 @@ def test_geostrophic_adjustment_known_answer():
     for nstep in range(1, 161):
         m, n, mm, nn, k1m, k1n = time_levels(nstep, kk)
         o.set_scalar("nstep", nstep)
-        for r in STEP_SEQUENCE:
-            if r == "tmsmt1":
-                o.tmsmt1(nn)
-            elif r == "tmsmt2":
-                o.tmsmt2(m, mm, nn, k1m)
-            else:
-                getattr(o, r)(m, n, mm, nn, k1m, k1n)
+        run_step(o, ROUTINES, (m, n, mm, nn, k1m, k1n))
         if nstep == 1:
             m0, s0 = inventory(None, nn), inventory("saln", nn)
         vmax.append(np.abs(interior(o.arrays["v"])).max())
@@ -84,13 +82,7 @@ def test_level_isopycnals_stay_at_rest():
     for nstep in range(1, 11):
         m, n, mm, nn, k1m, k1n = time_levels(nstep, kk)
         o.set_scalar("nstep", nstep)
-        for r in STEP_SEQUENCE:
-            if r == "tmsmt1":
-                o.tmsmt1(nn)
-            elif r == "tmsmt2":
-                o.tmsmt2(m, mm, nn, k1m)
-            else:
-                getattr(o, r)(m, n, mm, nn, k1m, k1n)
+        run_step(o, ROUTINES, (m, n, mm, nn, k1m, k1n))
     for nm in ("u", "v", "pgfx", "pgfy", "ubflxs_p", "vbflxs_p"):
         assert np.abs(interior(o.arrays[nm])).max() < 1e-12, nm
     assert np.abs(interior(o.arrays["dp"]) - dp0).max() < 1e-6          # Pa, of 1.6e5

@@ -61,6 +61,23 @@ class Case:
         return g
 
 
+def prepare_step(c, backends, options=None):
+    """Set the namelist options (default: the reference's defaults for the hybrid coordinate, as
+    driver.reference_options) on every backend, register the ALE products neutral diffusion consumes
+    when ndiff is on the path, and run the setup routines.  Returns (routines, options)."""
+    from blom_b200.driver import reference_options, step_routines
+    opts = {**reference_options(c.config), **(options or {})}
+    routines = step_routines(opts)
+    for b in backends:
+        for k, v in opts.items():
+            b.set_option(k, v)
+        if "ndiff" in routines:
+            nd = synth.ndiff_inputs(c.syn, c.state, c.levels, ntr=c.ntr)
+            b.register_all({k: v.copy() for k, v in nd.items()})
+        b.inieos(); b.numerical_bounds(); b.init_cppm()
+    return routines, opts
+
+
 def interior(a, nb=4, halo=0):
     """View of the interior (+`halo` rings) of a (nlev, ldj, ldi) array."""
     s = nb - halo
