@@ -8,8 +8,9 @@ A "step" is one pass of the hot path (driver.step_routines, reference call order
 phy/mod_blom_step.F90:96-227, namelist defaults of the named grid) over one synthetic state.
   value  : SYPD = 86400 / (steps_per_year * t_step), steps_per_year = 365*86400/baclin,
            state resident in HBM, CUDA-event time on the library stream, max over ranks
-  e2e    : same metric through the public host API with pinned HOST buffers: per step
-           upload of the prognostic state, the step, download of the result (wall clock)
+  e2e    : same metric through the public host API with pinned HOST buffers (wall clock): per step the host
+           hands over the time level its own routines wrote (new level of dp,T,S,u,v) and gets both levels
+           back; the copies run on their own streams and overlap the kernels (driver.HotPath.step_pipelined)
   roofline: dominant kernel, algorithmic bytes (SURVEY.md §8d word counts) / live CUDA-event
            duration, against the measured HBM copy peak in MEASURED_PEAKS.json
   cpu_baseline: the oracle (C++ restatement of the reference, kind "port") timed on a
@@ -414,16 +415,15 @@ def main():
     barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):
-        hp.upload_inputs()
-        hp.advance(early_download=True)   # u,v go back over PCIe while barotp/pbcor2/tmsmt2 run
-        hp.download_outputs()
+        hp.step_pipelined()               # H2D of the new level, the step, D2H of both levels; ends with a sync
+        hp.set_step(hp.nstep + 1)
     g.sync()
     w1 = time.perf_counter()
     te = torch.tensor([(w1 - w0) / args.steps], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e = float(te.item())
-    h2d, d2h = hp.io_bytes()
+    h2d, d2h = hp.io_bytes_pipelined()
     if dist is not None:   # whole-job bytes
         tb = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
         dist.all_reduce(tb, op=dist.ReduceOp.SUM)

@@ -212,85 +212,84 @@ struct BtSched {
 // time-level pointers and time weights of the current substep
 struct BtLv { double *pb_ml, *pb_nl, *ub_ml, *ub_nl, *vb_ml, *vb_nl; double wo, wm, wn; };
 
+// Time-weight pattern of a block of substeps (phy/mod_barotp.F90:330-358): the weights wo/wm/wn of the
+// old/mid/new baroclinic forcing are fixed per block, and in every block at least one of them is exactly
+// zero for all its substeps: block 1 has wn = 0, blocks 2-3 have wo = 0, blocks 4-5 have wo = wm = 0, wn = 1.
+// A term `0 * a` contributes +-0 to its sum, so the arrays that only enter through a zero weight are not
+// read at all (7 of the 53 words per point and substep in blocks 1-3, 14 in blocks 4-5); the result is the
+// same number (at most the sign of an exact zero differs).
+enum { W_ALL = 0, W_NO_N = 1, W_NO_O = 2, W_ONLY_N = 3 };
+template <int WM> struct Wsel {
+  static constexpr bool o = (WM == W_ALL || WM == W_NO_N), m = (WM != W_ONLY_N), n = (WM != W_NO_N);
+};
+// wo*a_o + wm*a_m + wn*a_n in the reference's order, without the terms whose weight is zero
+template <int WM>
+__device__ __forceinline__ double wsum3(const BtLv& V, double a_o, double a_m, double a_n) {
+  if (WM == W_ALL) return V.wo * a_o + V.wm * a_m + V.wn * a_n;
+  if (WM == W_NO_N) return V.wo * a_o + V.wm * a_m;
+  if (WM == W_NO_O) return V.wm * a_m + V.wn * a_n;
+  return V.wn * a_n;
+}
+
 // (the callers test the mask of the cell: P.ip for btp_continuity, P.iu for btp_ueq, P.iv for btp_veq)
 __device__ __forceinline__ void btp_continuity(const Geom& g, const BtP& P, const BtLv& V, long x) {
   V.pb_nl[x] = (1. - WBARO) * __ldcg(V.pb_ml + x) + WBARO * __ldcg(V.pb_nl + x) -
                (1. + WBARO) * P.dlt * (__ldcg(V.ub_ml + x + 1) - __ldcg(V.ub_ml + x) + __ldcg(V.vb_ml + x + g.ldi) -
                                        __ldcg(V.vb_ml + x)) * P.scp2i[x];
 }
+template <int WM>
 __device__ __forceinline__ void btp_ueq(const Geom& g, const BtP& P, const BtLv& V, const double* __restrict__ vb, long x) {
+  using W = Wsel<WM>;
   const long s = g.ldi;
   const double uml = __ldcg(V.ub_ml + x), unl = __ldcg(V.ub_nl + x);
   P.ubflxs_t[x] = __ldcg(P.ubflxs_t + x) - WBARO * unl + (1. + WBARO) * uml;
   const double v00 = __ldcg(vb + x), v01 = __ldcg(vb + x + s), vm0 = __ldcg(vb + x - 1), vm1 = __ldcg(vb + x - 1 + s);
+  const double pvo0 = W::o ? P.pvo[x] : 0., pvo1 = W::o ? P.pvo[x + s] : 0.;
+  const double pvm0 = W::m ? P.pvm[x] : 0., pvm1 = W::m ? P.pvm[x + s] : 0.;
+  const double pvn0 = W::n ? P.pvn[x] : 0., pvn1 = W::n ? P.pvn[x + s] : 0.;
   double q;
   if (P.enscon)
     q = (v00 * P.scvxi[x] + v01 * P.scvxi[x + s] + vm0 * P.scvxi[x - 1] + vm1 * P.scvxi[x - 1 + s]) *
-        (V.wo * (P.pvo[x] + P.pvo[x + s]) + V.wm * (P.pvm[x] + P.pvm[x + s]) + V.wn * (P.pvn[x] + P.pvn[x + s])) * .125;
+        wsum3<WM>(V, pvo0 + pvo1, pvm0 + pvm1, pvn0 + pvn1) * .125;
   else
-    q = .25 * ((v00 * P.scvxi[x] + vm0 * P.scvxi[x - 1]) * (V.wo * P.pvo[x] + V.wm * P.pvm[x] + V.wn * P.pvn[x]) +
-               (v01 * P.scvxi[x + s] + vm1 * P.scvxi[x - 1 + s]) *
-                   (V.wo * P.pvo[x + s] + V.wm * P.pvm[x + s] + V.wn * P.pvn[x + s]));
+    q = .25 * ((v00 * P.scvxi[x] + vm0 * P.scvxi[x - 1]) * wsum3<WM>(V, pvo0, pvm0, pvn0) +
+               (v01 * P.scvxi[x + s] + vm1 * P.scvxi[x - 1 + s]) * wsum3<WM>(V, pvo1, pvm1, pvn1));
   P.ubcors_t[x] = __ldcg(P.ubcors_t + x) + q;
   const double pbc = __ldcg(V.pb_nl + x), pbw = __ldcg(V.pb_nl + x - 1);
-  const double utndcy = q + (V.wo * (P.pgfxm_o[x] - (P.xixp_o[x] * pbc - P.xixm_o[x] * pbw)) +
-                             V.wm * (P.pgfxm_m[x] - (P.xixp_m[x] * pbc - P.xixm_m[x] * pbw)) +
-                             V.wn * (P.pgfxm_n[x] - (P.xixp_n[x] * pbc - P.xixm_n[x] * pbw))) * P.scuxi[x];
+  const double t_o = W::o ? P.pgfxm_o[x] - (P.xixp_o[x] * pbc - P.xixm_o[x] * pbw) : 0.;
+  const double t_m = W::m ? P.pgfxm_m[x] - (P.xixp_m[x] * pbc - P.xixm_m[x] * pbw) : 0.;
+  const double t_n = W::n ? P.pgfxm_n[x] - (P.xixp_n[x] * pbc - P.xixm_n[x] * pbw) : 0.;
+  const double utndcy = q + wsum3<WM>(V, t_o, t_m, t_n) * P.scuxi[x];
   const double un = (1. - WBARO) * uml + WBARO * unl +
                     (1. + WBARO) * P.dlt * ((utndcy + P.utotn[x]) * P.scuy[x] * fmin(pbw, pbc) - P.uglue[x] * uml);
   V.ub_nl[x] = fmax(-P.uminb[x], fmin(P.umaxb[x], un));
 }
+template <int WM>
 __device__ __forceinline__ void btp_veq(const Geom& g, const BtP& P, const BtLv& V, const double* __restrict__ ub, long x) {
+  using W = Wsel<WM>;
   const long s = g.ldi;
   const double vml = __ldcg(V.vb_ml + x), vnl = __ldcg(V.vb_nl + x);
   P.vbflxs_t[x] = __ldcg(P.vbflxs_t + x) - WBARO * vnl + (1. + WBARO) * vml;
   const double u00 = __ldcg(ub + x), u10 = __ldcg(ub + x + 1), u0m = __ldcg(ub + x - s), u1m = __ldcg(ub + x + 1 - s);
+  const double pvo0 = W::o ? P.pvo[x] : 0., pvo1 = W::o ? P.pvo[x + 1] : 0.;
+  const double pvm0 = W::m ? P.pvm[x] : 0., pvm1 = W::m ? P.pvm[x + 1] : 0.;
+  const double pvn0 = W::n ? P.pvn[x] : 0., pvn1 = W::n ? P.pvn[x + 1] : 0.;
   double q;
   if (P.enscon)
     q = -(u00 * P.scuyi[x] + u10 * P.scuyi[x + 1] + u0m * P.scuyi[x - s] + u1m * P.scuyi[x + 1 - s]) *
-        (V.wo * (P.pvo[x] + P.pvo[x + 1]) + V.wm * (P.pvm[x] + P.pvm[x + 1]) + V.wn * (P.pvn[x] + P.pvn[x + 1])) * .125;
+        wsum3<WM>(V, pvo0 + pvo1, pvm0 + pvm1, pvn0 + pvn1) * .125;
   else
-    q = -.25 * ((u00 * P.scuyi[x] + u0m * P.scuyi[x - s]) * (V.wo * P.pvo[x] + V.wm * P.pvm[x] + V.wn * P.pvn[x]) +
-                (u10 * P.scuyi[x + 1] + u1m * P.scuyi[x + 1 - s]) *
-                    (V.wo * P.pvo[x + 1] + V.wm * P.pvm[x + 1] + V.wn * P.pvn[x + 1]));
+    q = -.25 * ((u00 * P.scuyi[x] + u0m * P.scuyi[x - s]) * wsum3<WM>(V, pvo0, pvm0, pvn0) +
+                (u10 * P.scuyi[x + 1] + u1m * P.scuyi[x + 1 - s]) * wsum3<WM>(V, pvo1, pvm1, pvn1));
   P.vbcors_t[x] = __ldcg(P.vbcors_t + x) + q;
   const double pbc = __ldcg(V.pb_nl + x), pbs = __ldcg(V.pb_nl + x - s);
-  const double vtndcy = q + (V.wo * (P.pgfym_o[x] - (P.xiyp_o[x] * pbc - P.xiym_o[x] * pbs)) +
-                             V.wm * (P.pgfym_m[x] - (P.xiyp_m[x] * pbc - P.xiym_m[x] * pbs)) +
-                             V.wn * (P.pgfym_n[x] - (P.xiyp_n[x] * pbc - P.xiym_n[x] * pbs))) * P.scvyi[x];
+  const double t_o = W::o ? P.pgfym_o[x] - (P.xiyp_o[x] * pbc - P.xiym_o[x] * pbs) : 0.;
+  const double t_m = W::m ? P.pgfym_m[x] - (P.xiyp_m[x] * pbc - P.xiym_m[x] * pbs) : 0.;
+  const double t_n = W::n ? P.pgfym_n[x] - (P.xiyp_n[x] * pbc - P.xiym_n[x] * pbs) : 0.;
+  const double vtndcy = q + wsum3<WM>(V, t_o, t_m, t_n) * P.scvyi[x];
   const double vn = (1. - WBARO) * vml + WBARO * vnl +
                     (1. + WBARO) * P.dlt * ((vtndcy + P.vtotn[x]) * P.scvx[x] * fmin(pbs, pbc) - P.vglue[x] * vml);
   V.vb_nl[x] = fmax(-P.vminb[x], fmin(P.vmaxb[x], vn));
-}
-
-// L2 prefetch of the operands a phase will read at cell x (template switch PF, option
-// barotp_prefetch).  A thread walks its cells one after the other and every cell is a chain
-// mask -> operands -> arithmetic -> store of memory round trips (ncu: 35 stall cycles per issue on the
-// long scoreboard at 58 % of the DRAM peak, L2 and LSU below 40 %); prefetching the next cell's lines
-// was expected to shorten the chain to L2 latency but measured 5 % SLOWER on B200, so it is off by
-// default and kept as a documented negative result.
-__device__ __forceinline__ void pf_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void pf_continuity(const Geom& g, const BtP& P, const BtLv& V, long x) {
-  pf_l2(V.pb_ml + x); pf_l2(V.pb_nl + x); pf_l2(V.ub_ml + x); pf_l2(V.vb_ml + x); pf_l2(V.vb_ml + x + g.ldi);
-  pf_l2(P.scp2i + x);
-}
-__device__ __forceinline__ void pf_ueq(const Geom& g, const BtP& P, const BtLv& V, const double* vb, long x) {
-  const long s = g.ldi;
-  pf_l2(V.ub_ml + x); pf_l2(V.ub_nl + x); pf_l2(P.ubflxs_t + x); pf_l2(P.ubcors_t + x); pf_l2(V.pb_nl + x);
-  pf_l2(vb + x); pf_l2(vb + x + s); pf_l2(P.scvxi + x); pf_l2(P.scvxi + x + s);
-  pf_l2(P.pvo + x); pf_l2(P.pvo + x + s); pf_l2(P.pvm + x); pf_l2(P.pvm + x + s); pf_l2(P.pvn + x); pf_l2(P.pvn + x + s);
-  pf_l2(P.pgfxm_o + x); pf_l2(P.xixp_o + x); pf_l2(P.xixm_o + x); pf_l2(P.pgfxm_m + x); pf_l2(P.xixp_m + x);
-  pf_l2(P.xixm_m + x); pf_l2(P.pgfxm_n + x); pf_l2(P.xixp_n + x); pf_l2(P.xixm_n + x);
-  pf_l2(P.scuxi + x); pf_l2(P.utotn + x); pf_l2(P.scuy + x); pf_l2(P.uglue + x); pf_l2(P.uminb + x); pf_l2(P.umaxb + x);
-}
-__device__ __forceinline__ void pf_veq(const Geom& g, const BtP& P, const BtLv& V, const double* ub, long x) {
-  const long s = g.ldi;
-  pf_l2(V.vb_ml + x); pf_l2(V.vb_nl + x); pf_l2(P.vbflxs_t + x); pf_l2(P.vbcors_t + x); pf_l2(V.pb_nl + x);
-  pf_l2(V.pb_nl + x - s); pf_l2(ub + x); pf_l2(ub + x - s); pf_l2(P.scuyi + x); pf_l2(P.scuyi + x - s);
-  pf_l2(P.pvo + x); pf_l2(P.pvm + x); pf_l2(P.pvn + x);
-  pf_l2(P.pgfym_o + x); pf_l2(P.xiyp_o + x); pf_l2(P.xiym_o + x); pf_l2(P.pgfym_m + x); pf_l2(P.xiyp_m + x);
-  pf_l2(P.xiym_m + x); pf_l2(P.pgfym_n + x); pf_l2(P.xiyp_n + x); pf_l2(P.xiym_n + x);
-  pf_l2(P.scvyi + x); pf_l2(P.vtotn + x); pf_l2(P.scvx + x); pf_l2(P.vglue + x); pf_l2(P.vminb + x); pf_l2(P.vmaxb + x);
 }
 
 // Grid-wide barrier on a monotonically increasing counter (one atomic per block and barrier); cheaper
@@ -309,7 +308,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
   __syncthreads();
 }
 
-template <int THREADS, int MINBLK, int PF>
+template <int THREADS, int MINBLK, int WM>
 __global__ void __launch_bounds__(THREADS, MINBLK)
 bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_t, double* vb_t, unsigned* ctr) {
   unsigned target = 0;
@@ -318,39 +317,23 @@ bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_
   const long L = g.lev;
   int ml = S.ml, nl = S.nl;
   BtLv V;
-  // cells idx = tid, tid+nthr, ... of the range; body runs where mask == 1.  With PF the mask
-  // is read two cells ahead and the operands of the next wet cell are prefetched (pf) before the
-  // current cell is worked on.
-  auto for_range = [&](int i0, int i1, int j0, int j1, const int* __restrict__ mask, auto&& body, auto&& pf) {
+  // cells idx = tid, tid+nthr, ... of the range; body runs where mask == 1.  (i,j) of the thread's cells is
+  // advanced incrementally: one 32-bit division per phase instead of a 64-bit division and modulo in front
+  // of every cell's load chain.  (An L2 prefetch of the next cell's operands and a mask look-ahead were
+  // measured 5 % slower in round 1 and removed.)
+  auto for_range = [&](int i0, int i1, int j0, int j1, const int* __restrict__ mask, auto&& body) {
     const int ni = i1 - i0 + 1;
     const long n = (long)ni * (j1 - j0 + 1);
-    auto cell = [&](long idx) { return ix2(g, i0 + (int)(idx % ni), j0 + (int)(idx / ni)); };
-    if (!PF) {
-      // (i,j) of the thread's cells advanced incrementally: one 32-bit division per phase instead of a
-      // 64-bit division and modulo in front of every cell's load chain
-      if (tid >= n) return;
-      const unsigned t0 = (unsigned)tid, un = (unsigned)ni, st = (unsigned)nthr;
-      int j = (int)(t0 / un), i = (int)(t0 - (unsigned)j * un);
-      const int dj = (int)(st / un), di = (int)(st - (unsigned)dj * un);
-      const int nj = j1 - j0 + 1;
-      while (j < nj) {
-        const long x = ix2(g, i0 + i, j0 + j);
-        if (mask[x] == 1) body(x);
-        i += di; j += dj;
-        if (i >= ni) { i -= ni; ++j; }
-      }
-      return;
-    }
     if (tid >= n) return;
-    long x0 = cell(tid), x1 = x0;
-    int m0 = mask[x0], m1 = 0;
-    if (tid + nthr < n) { x1 = cell(tid + nthr); m1 = mask[x1]; }
-    for (long idx = tid; idx < n; idx += nthr) {
-      long x2 = x1; int m2 = 0;
-      if (idx + 2 * nthr < n) { x2 = cell(idx + 2 * nthr); m2 = mask[x2]; }
-      if (PF == 2 && m1 == 1) pf(x1);
-      if (m0 == 1) body(x0);
-      x0 = x1; m0 = m1; x1 = x2; m1 = m2;
+    const unsigned t0 = (unsigned)tid, un = (unsigned)ni, st = (unsigned)nthr;
+    int j = (int)(t0 / un), i = (int)(t0 - (unsigned)j * un);
+    const int dj = (int)(st / un), di = (int)(st - (unsigned)dj * un);
+    const int nj = j1 - j0 + 1;
+    while (j < nj) {
+      const long x = ix2(g, i0 + i, j0 + j);
+      if (mask[x] == 1) body(x);
+      i += di; j += dj;
+      if (i >= ni) { i -= ni; ++j; }
     }
   };
   for (int lll = S.lll0; lll < S.lll0 + S.nsub; ++lll) {
@@ -382,9 +365,11 @@ bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_
         if (tid < npay) __threadfence_system();   // only threads that stored to a peer
         grid_barrier(ctr, target);
         if (tid == 0) {
+          // release: the grid barrier made every block's (system-fenced) mailbox stores visible to this
+          // thread; the system-scope fence orders them before the flag stores the peers acquire on
+          __threadfence_system();
           if (X.has_s) *(volatile unsigned long long*)p2p_word(X.peer[0], 1) = seq;
           if (X.has_n) *(volatile unsigned long long*)p2p_word(X.peer[1], 0) = seq;
-          __threadfence_system();
         }
         if (threadIdx.x == 0) {
           if (X.has_s) { volatile unsigned long long* f = p2p_word(X.my_block, 0); while (*f < seq) {} }
@@ -417,24 +402,18 @@ bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_
         }
         grid_barrier(ctr, target);
       }
-      for_range(-1, g.ii + 1, -1, g.jj + 2, P.ip, [&](long x) { btp_continuity(g, P, V, x); },
-                [&](long x) { pf_continuity(g, P, V, x); });
+      for_range(-1, g.ii + 1, -1, g.jj + 2, P.ip, [&](long x) { btp_continuity(g, P, V, x); });
       grid_barrier(ctr, target);
-      for_range(0, g.ii + 1, -1, g.jj + 2, P.iu, [&](long x) { btp_ueq(g, P, V, V.vb_ml, x); },
-                [&](long x) { pf_ueq(g, P, V, V.vb_ml, x); });
+      for_range(0, g.ii + 1, -1, g.jj + 2, P.iu, [&](long x) { btp_ueq<WM>(g, P, V, V.vb_ml, x); });
       grid_barrier(ctr, target);
-      for_range(0, g.ii, 0, g.jj + 2, P.iv, [&](long x) { btp_veq(g, P, V, V.ub_nl, x); },
-                [&](long x) { pf_veq(g, P, V, V.ub_nl, x); });
+      for_range(0, g.ii, 0, g.jj + 2, P.iv, [&](long x) { btp_veq<WM>(g, P, V, V.ub_nl, x); });
       grid_barrier(ctr, target);
     } else {
-      for_range(0, g.ii, 0, g.jj + 1, P.ip, [&](long x) { btp_continuity(g, P, V, x); },
-                [&](long x) { pf_continuity(g, P, V, x); });
+      for_range(0, g.ii, 0, g.jj + 1, P.ip, [&](long x) { btp_continuity(g, P, V, x); });
       grid_barrier(ctr, target);
-      for_range(0, g.ii, 1, g.jj + 1, P.iv, [&](long x) { btp_veq(g, P, V, V.ub_ml, x); },
-                [&](long x) { pf_veq(g, P, V, V.ub_ml, x); });
+      for_range(0, g.ii, 1, g.jj + 1, P.iv, [&](long x) { btp_veq<WM>(g, P, V, V.ub_ml, x); });
       grid_barrier(ctr, target);
-      for_range(1, g.ii, 1, g.jj, P.iu, [&](long x) { btp_ueq(g, P, V, V.vb_nl, x); },
-                [&](long x) { pf_ueq(g, P, V, V.vb_nl, x); });
+      for_range(1, g.ii, 1, g.jj, P.iu, [&](long x) { btp_ueq<WM>(g, P, V, V.vb_nl, x); });
       grid_barrier(ctr, target);
     }
     const int t = ml; ml = nl; nl = t;
@@ -531,7 +510,10 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   const std::string mommth = c.option("mommth", "enscon");
   if (mommth != "enscon" && mommth != "enecon" && mommth != "enedis")
     throw std::runtime_error(" mommth = " + mommth + " is unsupported!");
-  double *pb_t = c.owned("barotp_pb_t", 2), *ub_t = c.owned("barotp_ubflx_t", 2), *vb_t = c.owned("barotp_vbflx_t", 2);
+  // the three subcycled fields (pb_t, ubflx_t, vbflx_t of phy/mod_barotp.F90:155-157, two time levels each) live in
+  // one allocation so that one L2 access-policy window can cover them (see below)
+  double* bt_state = c.owned("barotp_state", 6);
+  double *pb_t = bt_state, *ub_t = bt_state + 2 * L, *vb_t = bt_state + 4 * L;
   double *umaxb = c.owned("barotp_umaxb", 1), *uminb = c.owned("barotp_uminb", 1), *vmaxb = c.owned("barotp_vmaxb", 1),
          *vminb = c.owned("barotp_vminb", 1), *uglue = c.owned("barotp_uglue", 1), *vglue = c.owned("barotp_vglue", 1);
   const dim3 gint(cdiv(g.ii, 128), g.jj);
@@ -596,15 +578,13 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   // cooperative persistent form unless option barotp_kernel=phases asks for one launch per phase
   const bool persistent = c.option("barotp_kernel", "persistent") != "phases";
   // block shape of the persistent kernel: threads x resident blocks per SM fixes the register budget
-  // (65536 / (threads*blocks)); development switch barotp_shape = "512x2" (64 regs) | "256x2" (128) |
-  // "384x2" (85) | "1024x1" (64) | "640x2" (48) | "768x2" (40) | "1024x2" (32); barotp_prefetch = 1 | 0
-  struct Shape { const char* name; const void* fn[3]; int threads; };
-#define BT_SHAPE(T, B) {#T "x" #B, {(const void*)bt_subcycle<T, B, 0>, (const void*)bt_subcycle<T, B, 1>, (const void*)bt_subcycle<T, B, 2>}, T}
-  static const Shape shapes[] = {BT_SHAPE(512, 2), BT_SHAPE(256, 2), BT_SHAPE(384, 2), BT_SHAPE(1024, 1),
-                                 BT_SHAPE(640, 2), BT_SHAPE(768, 2), BT_SHAPE(1024, 2)};
+  // (65536 / (threads*blocks)); development switch barotp_shape = "512x2" (64 regs) | "768x2" (40) | "1024x2" (32).
+  // Measured at tnx0.25v4 in round 1: 256x2 29.6 ms, 512x2 22.7, 640x2 22.2, 768x2 21.5, 1024x2 21.6.
+  struct Shape { const char* name; const void* fn[4]; int threads; };
+#define BT_SHAPE(T, B) {#T "x" #B, {(const void*)bt_subcycle<T, B, W_ALL>, (const void*)bt_subcycle<T, B, W_NO_N>, \
+                                    (const void*)bt_subcycle<T, B, W_NO_O>, (const void*)bt_subcycle<T, B, W_ONLY_N>}, T}
+  static const Shape shapes[] = {BT_SHAPE(512, 2), BT_SHAPE(768, 2), BT_SHAPE(1024, 2)};
 #undef BT_SHAPE
-  // measured at tnx0.25v4 (512x2): 24.0 ms with the L2 prefetch, 22.9 without - off by default
-  const int pf = std::min(2, std::max(0, std::stoi(c.option("barotp_prefetch", "0"))));   // 1: mask look-ahead, 2: + L2 prefetch
   // default: 768x2 where every thread walks several cells per phase (1.67 M points at tnx0.25v4: 21.5 ms
   // against 22.7 for 512x2), 512x2 (no spills) where a phase is a single cell per thread and the time
   // goes into the chain of one cell plus the grid barrier (tnx1v4: 2.05 ms against 2.46)
@@ -613,14 +593,47 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   const Shape* shape = nullptr;
   for (const Shape& sh : shapes) if (shape_opt == sh.name) shape = &sh;
   if (!shape) throw std::runtime_error("barotp: unknown barotp_shape " + shape_opt);
+  // zero-weight arrays are skipped unless barotp_wskip=0 (development switch)
+  const bool wskip = c.option("barotp_wskip", "1") != "0";
   static std::map<std::string, int> coop_grids;
-  const std::string shape_key = std::string(shape->name) + "p" + std::to_string(pf);
-  int coop_grid = coop_grids[shape_key];
-  if (persistent && coop_grid == 0) {
-    int per_sm = 0, nsm = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shape->fn[pf], shape->threads, 0));
-    CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c.device));
-    coop_grid = coop_grids[shape_key] = std::max(1, per_sm) * nsm;
+  auto coop_grid_of = [&](int wm) {
+    const std::string key = std::string(shape->name) + "w" + std::to_string(wm);
+    int& cg_ = coop_grids[key];
+    if (cg_ == 0) {
+      int per_sm = 0, nsm = 0;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shape->fn[wm], shape->threads, 0));
+      CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c.device));
+      cg_ = std::max(1, per_sm) * nsm;
+    }
+    return cg_;
+  };
+  // L2 residency of the subcycled state.  The six levels of pb_t/ubflx_t/vbflx_t are read and written in every
+  // phase of every substep (15 of the 53 words per point and substep) while the coefficient arrays stream
+  // through once per phase and would evict them; when the 2-D working set exceeds the L2 (tnx0.25v4 on one
+  // GPU: 704 MB against 126 MB) the state is pinned with a persisting access-policy window on the library
+  // stream for the duration of the subcycle (option barotp_l2persist=0 switches it off).
+  bool l2_window = false;
+  if (persistent && c.option("barotp_l2persist", "1") != "0") {
+    int max_persist = 0, max_window = 0, l2_bytes = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
+    cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, c.device);
+    const size_t state_bytes = sizeof(double) * 6 * (size_t)L;
+    const size_t working_set = sizeof(double) * 53 * (size_t)L;
+    if (max_persist > 0 && max_window > 0 && working_set > (size_t)l2_bytes) {
+      // the carve-out is taken away from every other kernel's L2 (the level-parallel kernels of this path rely on
+      // L2 for their 2-D operands), so it only exists for the duration of the subcycle
+      const size_t carve = std::min<size_t>((size_t)max_persist, (size_t)(0.7 * l2_bytes));
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+      cudaStreamAttrValue attr{};
+      attr.accessPolicyWindow.base_ptr = bt_state;
+      attr.accessPolicyWindow.num_bytes = std::min(state_bytes, (size_t)max_window);
+      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      l2_window = cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+      if (!l2_window) cudaGetLastError();
+    }
   }
   unsigned* bar_ctr = reinterpret_cast<unsigned*>(c.owned("barotp_barrier", 1));
   int lll0 = 1, ml = 1, nl = 2;
@@ -664,7 +677,9 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
         }
         CUDA_CHECK(cudaMemsetAsync(bar_ctr, 0, sizeof(unsigned), c.stream));
         void* args[] = {(void*)&g, (void*)&P, (void*)&S, (void*)&X, (void*)&pb_t, (void*)&ub_t, (void*)&vb_t, (void*)&bar_ctr};
-        launch_cooperative("bt_subcycle", shape->fn[pf], coop_grid, shape->threads, args);
+        // time-weight pattern of this block (see Wsel): block 1 wn = 0; blocks 2,3 wo = 0; blocks 4,5 wn = 1
+        const int wmode = !wskip ? W_ALL : (nb == 1 ? W_NO_N : (nb <= 3 ? W_NO_O : W_ONLY_N));
+        launch_cooperative("bt_subcycle", shape->fn[wmode], coop_grid_of(wmode), shape->threads, args);
         if (S.nsub % 2 == 1) std::swap(ml, nl);
         lll += S.nsub;
       }
@@ -695,6 +710,13 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     lll0 = lll0 + lstep / 2;
     set_levels(ml, nl);
     LAUNCH(bt_harvest, gint, 128, 0, g, P, H, nb, m, n, ml, nl);
+  }
+  if (l2_window) {   // back to the default policy for the kernels that follow; drop the persisting lines
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaCtxResetPersistingL2Cache();
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
   }
 }
 

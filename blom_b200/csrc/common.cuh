@@ -75,6 +75,8 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // blomgpu_download_async: D2H copies that overlap later kernels
+  cudaStream_t up_stream = nullptr;     // blomgpu_upload_async: H2D copies that overlap earlier kernels
+  std::map<std::string, cudaEvent_t> up_done;   // completion event of the last asynchronous upload per field
   std::map<std::string, DField> f;
   std::map<std::string, IFieldD> fi;
   std::map<std::string, std::string> opt;

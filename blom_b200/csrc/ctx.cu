@@ -133,10 +133,12 @@ static void do_finalize() {
     if (c.halo_recv[s]) cudaFree(c.halo_recv[s]);
   }
   if (c.copy_stream) cudaStreamSynchronize(c.copy_stream);
-  cudaStream_t st = c.stream, cst = c.copy_stream;
+  if (c.up_stream) cudaStreamSynchronize(c.up_stream);
+  for (auto& kv : c.up_done) if (kv.second) cudaEventDestroy(kv.second);
+  cudaStream_t st = c.stream, cst = c.copy_stream, ust = c.up_stream;
   void* nccl = c.nccl;
   c = Ctx();
-  c.stream = st; c.copy_stream = cst;
+  c.stream = st; c.copy_stream = cst; c.up_stream = ust;
   c.nccl = nccl;
 }
 
@@ -196,8 +198,57 @@ static void do_download_async(const char* name) {
   CUDA_CHECK(cudaMemcpyAsync(fd.h, fd.d, sizeof(double) * (size_t)c.g.lev * fd.nlev, cudaMemcpyDeviceToHost,
                              c.copy_stream));
 }
+// Level range [koff, koff+nlev) (1-based) of a double field, checked against the registration.
+static DField& field_range(const char* name, int koff, int nlev, size_t* off, size_t* bytes) {
+  Ctx& c = C();
+  auto it = c.f.find(name);
+  if (it == c.f.end()) throw std::runtime_error(std::string("blomgpu: field not registered: ") + name);
+  DField& fd = it->second;
+  if (!fd.h) throw std::runtime_error(std::string("blomgpu: no host array bound to ") + name);
+  if (koff < 1 || nlev < 1 || koff - 1 + nlev > fd.nlev)
+    throw std::runtime_error(std::string("blomgpu: level range outside array: ") + name);
+  *off = (size_t)(koff - 1) * c.g.lev;
+  *bytes = sizeof(double) * (size_t)c.g.lev * nlev;
+  return fd;
+}
+static void stream_after(cudaStream_t waiter, cudaStream_t producer) {
+  cudaEvent_t ev;
+  CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventRecord(ev, producer));
+  CUDA_CHECK(cudaStreamWaitEvent(waiter, ev, 0));
+  CUDA_CHECK(cudaEventDestroy(ev));   // released once the wait has been satisfied
+}
+// Host -> device copy of a level range on the upload stream.  It starts when everything enqueued so far
+// (kernels and downloads that may still read the old content) has finished and overlaps the routines
+// called afterwards; a routine that reads the field must be preceded by blomgpu_wait_upload(name).
+static void do_upload_async(const char* name, int koff, int nlev) {
+  Ctx& c = C();
+  size_t off, bytes;
+  DField& fd = field_range(name, koff, nlev, &off, &bytes);
+  if (!c.up_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c.up_stream, cudaStreamNonBlocking));
+  stream_after(c.up_stream, c.stream);
+  if (c.copy_stream) stream_after(c.up_stream, c.copy_stream);
+  CUDA_CHECK(cudaMemcpyAsync(fd.d + off, fd.h + off, bytes, cudaMemcpyHostToDevice, c.up_stream));
+  cudaEvent_t& ev = c.up_done[name];
+  if (!ev) CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventRecord(ev, c.up_stream));
+}
+static void do_wait_upload(const char* name) {
+  Ctx& c = C();
+  auto it = c.up_done.find(name);
+  if (it != c.up_done.end() && it->second) CUDA_CHECK(cudaStreamWaitEvent(c.stream, it->second, 0));
+}
+static void do_download_levels_async(const char* name, int koff, int nlev) {
+  Ctx& c = C();
+  size_t off, bytes;
+  DField& fd = field_range(name, koff, nlev, &off, &bytes);
+  if (!c.copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  stream_after(c.copy_stream, c.stream);
+  CUDA_CHECK(cudaMemcpyAsync(fd.h + off, fd.d + off, bytes, cudaMemcpyDeviceToHost, c.copy_stream));
+}
 static void do_sync() {
   Ctx& c = C();
+  if (c.up_stream) CUDA_CHECK(cudaStreamSynchronize(c.up_stream));
   CUDA_CHECK(cudaStreamSynchronize(c.stream));
   if (c.copy_stream) CUDA_CHECK(cudaStreamSynchronize(c.copy_stream));
   c.check_errors();
@@ -264,6 +315,9 @@ int blomgpu_download(const char* name) { GUARD(do_copy(name, false); CUDA_CHECK(
 int blomgpu_upload_all(void) { GUARD(do_copy_all(true)) }
 int blomgpu_download_all(void) { GUARD(do_copy_all(false)) }
 int blomgpu_download_async(const char* name) { GUARD(do_download_async(name)) }
+int blomgpu_download_levels_async(const char* name, int koff, int nlev) { GUARD(do_download_levels_async(name, koff, nlev)) }
+int blomgpu_upload_async(const char* name, int koff, int nlev) { GUARD(do_upload_async(name, koff, nlev)) }
+int blomgpu_wait_upload(const char* name) { GUARD(do_wait_upload(name)) }
 int blomgpu_sync(void) { GUARD(do_sync()) }
 int blomgpu_device_ptr(const char* name, void** dptr, int* nlev) {
   GUARD(
@@ -301,6 +355,12 @@ int blomgpu_xcmax(const char* name, int lev, const char* mask, double* out) {
 }
 int blomgpu_xcmin(const char* name, int lev, const char* mask, double* out) {
   GUARD(Ctx& c = C(); *out = xcmax_dev(c.dev(name) + (size_t)(lev - 1) * c.g.lev, c.idev(mask), false))
+}
+int blomgpu_chksum_at(const char* name, int koff, int kcsd, int itype, uint32_t* crc) {
+  GUARD(
+    Ctx& c = C();
+    if (koff < 1 || koff - 1 + kcsd > c.nlev(name)) throw std::runtime_error("blomgpu_chksum_at: level range outside array");
+    *crc = xccrc_dev(c.dev(name) + (size_t)(koff - 1) * c.g.lev, kcsd, mask_for_itype(itype)))
 }
 int blomgpu_chksum(const char* name, int kcsd, int itype, uint32_t* crc) {
   GUARD(Ctx& c = C(); *crc = xccrc_dev(c.dev(name), kcsd, mask_for_itype(itype)))

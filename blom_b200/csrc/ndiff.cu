@@ -48,8 +48,12 @@ __device__ __forceinline__ double eos_drhods(double p, double th, double s) {
   return (EA13 + EA15 * th + 2. * EA16 * s + EB13 * p - (EA23 + EA25 * th + 2. * EA26 * s + EB23 * p) * r1 * r2i) * r2i;
 }
 
+// Packed record of one source-layer interface of one cell column: {drhodt, drhods, T, S} at (is,k), 32 bytes =
+// one memory sector.  The first search evaluates the density difference between two interfaces at every step
+// and its lanes sit at different layers, so four separate level-strided arrays cost four sectors per lane
+// where the record costs one.  Layout: record ((k-1)*2+is-1) of cell x at rec[(((k-1)*2+is-1)*lev + x)*4].
 struct NdArgs {
-  const double *p_src, *tsd, *tpc, *drdt, *drds, *p_dst, *snp;
+  const double *p_src, *tsd, *tpc, *rec, *p_dst, *snp;
   const int *ksmx, *kdmx, *mask;
   const double *dpml, *difiso;
   const double* tlev[NTMAX];   // scalar nt at time level nn, level 1
@@ -62,14 +66,20 @@ struct NdArgs {
 };
 
 // one cell column with the reference's 1-based indices
+struct Rec { double drdt, drds, t, s; };
 struct Col {
-  const double *p_src, *tsd, *tpc, *drdt, *drds, *p_dst, *snp;
+  const double *p_src, *tsd, *tpc, *rec, *p_dst, *snp;
   long lev; int kk;
+  __device__ __forceinline__ Rec record(int s, int k) const {
+    const double2* r = reinterpret_cast<const double2*>(rec + (long)((k - 1) * 2 + s - 1) * lev * 4);
+    const double2 a = r[0], b = r[1];
+    return Rec{a.x, a.y, b.x, b.y};
+  }
   __device__ __forceinline__ double psd(int s, int k) const { return p_src[(long)(k + s - 2) * lev]; }
   __device__ __forceinline__ double tsrcdi(int s, int k, int nt) const { return tsd[(long)(((nt - 1) * kk + k - 1) * 2 + s - 1) * lev]; }
   __device__ __forceinline__ double tpcc(int c, int k, int nt) const { return tpc[(long)(((nt - 1) * kk + k - 1) * 5 + c - 1) * lev]; }
-  __device__ __forceinline__ double drhodt(int s, int k) const { return drdt[(long)((k - 1) * 2 + s - 1) * lev]; }
-  __device__ __forceinline__ double drhods(int s, int k) const { return drds[(long)((k - 1) * 2 + s - 1) * lev]; }
+  __device__ __forceinline__ double drhodt(int s, int k) const { return rec[(long)((k - 1) * 2 + s - 1) * lev * 4]; }
+  __device__ __forceinline__ double drhods(int s, int k) const { return rec[(long)((k - 1) * 2 + s - 1) * lev * 4 + 1]; }
   __device__ __forceinline__ double pdst(int k) const { return p_dst[(long)(k - 1) * lev]; }
   __device__ __forceinline__ double dstsnp(int k) const { return snp[(long)(k - 1) * lev]; }
 };
@@ -92,15 +102,15 @@ __device__ __forceinline__ double pmeval(const Col& c, int k, int nt, double x0,
 }
 // :104-148: Newton search for the position in layer k of column c that is neutral to (tf,sf); the ten
 // polynomial coefficients are loaded once instead of once per iteration
-__device__ double drhoroot(const Col& c, int k, double tf, double sf, double drhodt_l, double drhodt_u,
-                           double drhods_l, double drhods_u) {
+__device__ __forceinline__ double drhoroot(const double* __restrict__ tpc, long lev, int kk, int k, double tf, double sf,
+                                           double drhodt_l, double drhodt_u, double drhods_l, double drhods_u) {
   const double eps = 1.e-14, x_tol = 1.e-4;
   double x = .5;
   const double ddrdtdx = drhodt_l - drhodt_u, ddrdsdx = drhods_l - drhods_u;
-  const double T1 = c.tpcc(1, k, IT), T2 = c.tpcc(2, k, IT), T3 = c.tpcc(3, k, IT), T4 = c.tpcc(4, k, IT),
-               T5 = c.tpcc(5, k, IT);
-  const double S1 = c.tpcc(1, k, IS), S2 = c.tpcc(2, k, IS), S3 = c.tpcc(3, k, IS), S4 = c.tpcc(4, k, IS),
-               S5 = c.tpcc(5, k, IS);
+  const double* bt = tpc + (long)(((IT - 1) * kk + k - 1) * 5) * lev;
+  const double* bs = tpc + (long)(((IS - 1) * kk + k - 1) * 5) * lev;
+  const double T1 = bt[0], T2 = bt[lev], T3 = bt[2 * lev], T4 = bt[3 * lev], T5 = bt[4 * lev];
+  const double S1 = bs[0], S2 = bs[lev], S3 = bs[2 * lev], S4 = bs[3 * lev], S5 = bs[4 * lev];
   for (int n = 1; n <= 10; ++n) {
     const double dt = tf - (T1 + (T2 + (T3 + (T4 + T5 * x) * x) * x) * x);
     const double ds = sf - (S1 + (S2 + (S3 + (S4 + S5 * x) * x) * x) * x);
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(128)
 ndiff_prep(Geom g, int mm, int T, const int* __restrict__ ip, const int* __restrict__ iu,
            const int* __restrict__ iv, const int* __restrict__ ksmx, const double* __restrict__ p_src,
            const double* __restrict__ tsd, const double* __restrict__ p_dst, int* __restrict__ kdmx,
-           double* __restrict__ drdt, double* __restrict__ drds, double* __restrict__ snp,
+           double* __restrict__ rec, double* __restrict__ snp,
            double* __restrict__ utflld, double* __restrict__ usflld, double* __restrict__ vtflld,
            double* __restrict__ vsflld) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
@@ -148,8 +158,9 @@ ndiff_prep(Geom g, int mm, int T, const int* __restrict__ ip, const int* __restr
       const double ps = p_src[x + (long)(k + s - 2) * lev];
       const double t = tsd[x + (long)(((IT - 1) * kk + k - 1) * 2 + s - 1) * lev];
       const double sa = tsd[x + (long)(((IS - 1) * kk + k - 1) * 2 + s - 1) * lev];
-      drdt[x + (long)((k - 1) * 2 + s - 1) * lev] = eos_drhodt(ps, t, sa);
-      drds[x + (long)((k - 1) * 2 + s - 1) * lev] = eos_drhods(ps, t, sa);
+      double2* r = reinterpret_cast<double2*>(rec + ((long)((k - 1) * 2 + s - 1) * lev + x) * 4);
+      r[0] = make_double2(eos_drhodt(ps, t, sa), eos_drhods(ps, t, sa));
+      r[1] = make_double2(t, sa);
     }
   // p_dstsnp(1..kdmx+1)
   double pk = p_dst[x], pk1 = p_dst[x + lev];
@@ -191,8 +202,8 @@ struct SideAcc {
 };
 
 // ndiff_flx (:160-953) for the face between cell M (i-1|j-1) and cell P (i,j)
-template <int DIR, int NT>
-__global__ void __launch_bounds__(128)
+template <int DIR, int NT, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 ndiff_face(Geom g, NdArgs A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
   if (i > g.ii + (DIR == 0 ? 1 : 0)) return;
@@ -200,13 +211,12 @@ ndiff_face(Geom g, NdArgs A) {
   if (A.mask[x] != 1) return;
   const long xm = x - (DIR == 0 ? 1 : g.ldi), lev = g.lev;
   const int kk = g.kdm, T = NT > 0 ? NT : A.T, mm = A.mm;
-  const Col M{A.p_src + xm, A.tsd + xm, A.tpc + xm, A.drdt + xm, A.drds + xm, A.p_dst + xm, A.snp + xm, lev, kk};
-  const Col P{A.p_src + x, A.tsd + x, A.tpc + x, A.drdt + x, A.drds + x, A.p_dst + x, A.snp + x, lev, kk};
+  const Col M{A.p_src + xm, A.tsd + xm, A.tpc + xm, A.rec + xm * 4, A.p_dst + xm, A.snp + xm, lev, kk};
+  const Col P{A.p_src + x, A.tsd + x, A.tpc + x, A.rec + x * 4, A.p_dst + x, A.snp + x, lev, kk};
   const int ksmx_m = A.ksmx[xm], ksmx_p = A.ksmx[x], kdmx_m = A.kdmx[xm], kdmx_p = A.kdmx[x];
   const double cdiff = A.delt1 * A.sca[x] * A.scbi[x];          // :1064 / :1126
   const double cnslp = alpha0 * A.scbi[x] / grav;
 
-  double nslp_src[4 * (KMN + 1) + 1], p_nslp_src[4 * (KMN + 1) + 1];
   double pnm[2 * (KMN + 1) + 2], pnp[2 * (KMN + 1) + 2];
   for (int q = 0; q < 2 * (kk + 1) + 2; ++q) { pnm[q] = mval; pnp[q] = mval; }
 #define PNM(s, k) pnm[2 * (k) + (s) - 1]
@@ -214,14 +224,36 @@ ndiff_face(Geom g, NdArgs A) {
   unsigned long long stab_m = 0ull, stab_p = 0ull;   // bit k-1 <-> stab(k), k = 1..64
   auto stabm = [&](int k) { return k >= 1 && ((stab_m >> (k - 1)) & 1ull); };
   auto stabp = [&](int k) { return k >= 1 && ((stab_p >> (k - 1)) & 1ull); };
-  double t_ni_m[2][NT > 0 ? NT : NTMAX], t_ni_p[2][NT > 0 ? NT : NTMAX];
-  double x_ni_m[2], x_ni_p[2], p_ni_m[2], p_ni_p[2];   // index nip-1 / nic-1
   double pml = 0., drho_curr = 0., p_ni_m_prev, p_ni_p_prev;
   int nns = 0, kssa_m = 0, kssa_p = 0, is_m, is_p, ks_m, ks_p;
 
+  // records of the current interfaces (is_m,ks_m) and (is_p,ks_p); only the side that moved is reloaded
+  Rec rm{0., 0., 0., 0.}, rp{0., 0., 0., 0.};
   auto drho_at = [&]() {
-    return .5 * (M.drhodt(is_m, ks_m) + P.drhodt(is_p, ks_p)) * (P.tsrcdi(is_p, ks_p, IT) - M.tsrcdi(is_m, ks_m, IT)) +
-           .5 * (M.drhods(is_m, ks_m) + P.drhods(is_p, ks_p)) * (P.tsrcdi(is_p, ks_p, IS) - M.tsrcdi(is_m, ks_m, IS));
+    return .5 * (rm.drdt + rp.drdt) * (rp.t - rm.t) + .5 * (rm.drds + rp.drds) * (rp.s - rm.s);
+  };
+
+  // Neutral slope at the destination interfaces (:913-951), evaluated while the first search produces the
+  // (slope, pressure) pairs instead of from stored lists afterwards.  The reference scans the destination
+  // interfaces kd = 1..kk in order and for each one advances a source pointer ks to the first pair at or
+  // below it, never moving ks back; handing every new pair to the still-unfilled destination interfaces
+  // visits exactly the same (kd, ks) combinations, so the interpolated values are identical and the two
+  // lists of up to 4*(kk+1) doubles per thread never exist.
+  double* nslp = A.nslp + x;
+  int kd_sl = 1;
+  double pd_sl = .5 * (M.pdst(1) + P.pdst(1)), s_prev = 0., p_prev = 0.;
+  auto emit_slope = [&](double sl, double pr) {
+    nns = nns + 1;
+    while (kd_sl <= kk && !(pd_sl > pr)) {
+      if (nns == 1) nslp[(long)(kd_sl - 1) * lev] = sl;
+      else {
+        const double q = (pr - pd_sl) / fmax(pr - p_prev, epsilp);
+        nslp[(long)(kd_sl - 1) * lev] = q * s_prev + (1. - q) * sl;
+      }
+      kd_sl = kd_sl + 1;
+      if (kd_sl <= kk) pd_sl = .5 * (M.pdst(kd_sl) + P.pdst(kd_sl));
+    }
+    s_prev = sl; p_prev = pr;
   };
 
   // ---- first search: neutral interfaces anchored at source layer interfaces (:212-406)
@@ -243,93 +275,81 @@ ndiff_face(Geom g, NdArgs A) {
     is_m = 1; ks_m = 1; is_p = 1; ks_p = 1;
     p_ni_m_prev = M.psd(1, 1); p_ni_p_prev = P.psd(1, 1);
   }
-  if (ks_m <= ksmx_m && ks_p <= ksmx_p) drho_curr = drho_at();
+  if (ks_m <= ksmx_m && ks_p <= ksmx_p) { rm = M.record(is_m, ks_m); rp = P.record(is_p, ks_p); drho_curr = drho_at(); }
 
-  [&]() {  // search_loop1
-    while (ks_m <= ksmx_m && ks_p <= ksmx_p) {
+  // search_loop1.  The reference handles the minus and the plus column in separate, mirrored code blocks
+  // (root search in M when drho < 0, in P when drho > 0; advance M, then advance P).  Lanes of a warp sit in
+  // different blocks at the same time, so the mirrored blocks are written ONCE with the column chosen per
+  // lane (`side`: 0 = M, offset xm; 1 = P, offset x): lanes that advance M and lanes that advance P, or that
+  // solve for a root in M and in P, then execute together instead of one after the other.  The arithmetic
+  // per lane is the reference's (sums are commuted only where a + b == b + a exactly).
+  auto rec_at = [&](long o, int is, int ks) {
+    const double2* r = reinterpret_cast<const double2*>(A.rec + (o + (long)((ks - 1) * 2 + is - 1) * lev) * 4);
+    const double2 a = r[0], b = r[1];
+    return Rec{a.x, a.y, b.x, b.y};
+  };
+  auto psd_at = [&](long o, int is, int ks) { return A.p_src[o + (long)(ks + is - 2) * lev]; };
+  {
+    bool done1 = false;
+    while (!done1 && ks_m <= ksmx_m && ks_p <= ksmx_p) {
       const bool drho_neg = drho_curr <= -rho_eps;
       const bool drho_pos = drho_curr >= rho_eps;
       const bool drho_zero = !(drho_neg || drho_pos);
       if (is_m + ks_m > 2 && is_p + ks_p > 2) {
-        if (drho_neg) {
-          if (is_m == 2) {
-            const double dtp = P.drhodt(is_p, ks_p), dsp = P.drhods(is_p, ks_p);
-            const double drhodt_x0 = .5 * (M.drhodt(1, ks_m) + dtp), drhodt_x1 = .5 * (M.drhodt(2, ks_m) + dtp);
-            const double drhods_x0 = .5 * (M.drhods(1, ks_m) + dsp), drhods_x1 = .5 * (M.drhods(2, ks_m) + dsp);
-            const double x_ni = drhoroot(M, ks_m, P.tsrcdi(is_p, ks_p, IT), P.tsrcdi(is_p, ks_p, IS), drhodt_x1,
-                                         drhodt_x0, drhods_x1, drhods_x0);
-            const double p_ni = M.psd(2, ks_m) * x_ni + M.psd(1, ks_m) * (1. - x_ni);
-            if (p_ni > p_ni_m_prev) {
-              p_ni_m_prev = p_ni;
-              PNP(is_p, ks_p) = p_ni;
-              nns = nns + 1;
-              const double pp = P.psd(is_p, ks_p);
-              nslp_src[nns] = -cnslp * (pp - p_ni);
-              p_nslp_src[nns] = .5 * (pp + p_ni);
-            }
+        const bool rootm = drho_neg && is_m == 2, rootp = drho_pos && is_p == 2;
+        if (rootm || rootp) {
+          // layer kr of the searched column (offset o) against the fixed interface fx of the other column
+          const long o = rootm ? xm : x;
+          const int kr = rootm ? ks_m : ks_p;
+          const Rec fx = rootm ? rp : rm;
+          const double* r1 = A.rec + (o + (long)((kr - 1) * 2) * lev) * 4;
+          const double* r2 = r1 + lev * 4;
+          const double drhodt_x0 = .5 * (r1[0] + fx.drdt), drhodt_x1 = .5 * (r2[0] + fx.drdt);
+          const double drhods_x0 = .5 * (r1[1] + fx.drds), drhods_x1 = .5 * (r2[1] + fx.drds);
+          const double x_ni = drhoroot(A.tpc + o, lev, kk, kr, fx.t, fx.s, drhodt_x1, drhodt_x0, drhods_x1, drhods_x0);
+          const double p_ni = psd_at(o, 2, kr) * x_ni + psd_at(o, 1, kr) * (1. - x_ni);
+          if (p_ni > (rootm ? p_ni_m_prev : p_ni_p_prev)) {
+            // pressure of the fixed interface in its own column
+            const double pe = rootm ? psd_at(x, is_p, ks_p) : psd_at(xm, is_m, ks_m);
+            if (rootm) { p_ni_m_prev = p_ni; PNP(is_p, ks_p) = p_ni; }
+            else { p_ni_p_prev = p_ni; PNM(is_m, ks_m) = p_ni; }
+            const double pa = rootm ? pe : p_ni, pb = rootm ? p_ni : pe;   // (plus side) - (minus side)
+            emit_slope(-cnslp * (pa - pb), .5 * (pa + pb));
           }
-        } else if (drho_pos) {
-          if (is_p == 2) {
-            const double dtm = M.drhodt(is_m, ks_m), dsm = M.drhods(is_m, ks_m);
-            const double drhodt_x0 = .5 * (dtm + P.drhodt(1, ks_p)), drhodt_x1 = .5 * (dtm + P.drhodt(2, ks_p));
-            const double drhods_x0 = .5 * (dsm + P.drhods(1, ks_p)), drhods_x1 = .5 * (dsm + P.drhods(2, ks_p));
-            const double x_ni = drhoroot(P, ks_p, M.tsrcdi(is_m, ks_m, IT), M.tsrcdi(is_m, ks_m, IS), drhodt_x1,
-                                         drhodt_x0, drhods_x1, drhods_x0);
-            const double p_ni = P.psd(2, ks_p) * x_ni + P.psd(1, ks_p) * (1. - x_ni);
-            if (p_ni > p_ni_p_prev) {
-              p_ni_p_prev = p_ni;
-              PNM(is_m, ks_m) = p_ni;
-              nns = nns + 1;
-              const double pm = M.psd(is_m, ks_m);
-              nslp_src[nns] = -cnslp * (p_ni - pm);
-              p_nslp_src[nns] = .5 * (p_ni + pm);
-            }
-          }
-        } else {
+        } else if (drho_zero) {
           const double pm = M.psd(is_m, ks_m), pp = P.psd(is_p, ks_p);
           PNP(is_p, ks_p) = pm;
           PNM(is_m, ks_m) = pp;
-          nns = nns + 1;
-          nslp_src[nns] = -cnslp * (pp - pm);
-          p_nslp_src[nns] = .5 * (pp + pm);
+          emit_slope(-cnslp * (pp - pm), .5 * (pp + pm));
         }
       }
-      if (drho_zero || drho_pos) {
-        for (;;) {
-          const double drho_prev = drho_curr;
-          if (is_m == 1) is_m = 2;
-          else {
-            ks_m = ks_m + 1;
-            if (ks_m > ksmx_m) return;
-            is_m = 1;
-          }
-          drho_curr = drho_at();
-          if (drho_prev - drho_curr > rho_eps) {
-            if (is_m == 2 && M.psd(2, ks_m) - M.psd(1, ks_m) > onemm) stab_m |= 1ull << (ks_m - 1);
-            break;
-          }
-          if (is_m == 1) PNM(is_m, ks_m) = PNM(2, ks_m - 1);
+      // advance the minus column (drho >= 0), then the plus column (drho <= 0)
+      int side = (drho_zero || drho_pos) ? 0 : 1;
+      bool then_p = drho_zero;
+      for (;;) {
+        const double drho_prev = drho_curr;
+        int is = side ? is_p : is_m, ks = side ? ks_p : ks_m;
+        if (is == 1) is = 2;
+        else {
+          ks = ks + 1;
+          if (ks > (side ? ksmx_p : ksmx_m)) { if (side) ks_p = ks; else ks_m = ks; done1 = true; break; }
+          is = 1;
         }
-      }
-      if (drho_zero || drho_neg) {
-        for (;;) {
-          const double drho_prev = drho_curr;
-          if (is_p == 1) is_p = 2;
-          else {
-            ks_p = ks_p + 1;
-            if (ks_p > ksmx_p) return;
-            is_p = 1;
+        const long o = side ? x : xm;
+        const Rec r = rec_at(o, is, ks);
+        if (side) { rp = r; is_p = is; ks_p = ks; } else { rm = r; is_m = is; ks_m = ks; }
+        drho_curr = drho_at();
+        if ((side ? drho_curr - drho_prev : drho_prev - drho_curr) > rho_eps) {
+          if (is == 2 && psd_at(o, 2, ks) - psd_at(o, 1, ks) > onemm) {
+            if (side) stab_p |= 1ull << (ks - 1); else stab_m |= 1ull << (ks - 1);
           }
-          drho_curr = drho_at();
-          if (drho_curr - drho_prev > rho_eps) {
-            if (is_p == 2 && P.psd(2, ks_p) - P.psd(1, ks_p) > onemm) stab_p |= 1ull << (ks_p - 1);
-            break;
-          }
-          if (is_p == 1) PNP(is_p, ks_p) = PNP(2, ks_p - 1);
+          if (then_p) { then_p = false; side = 1; continue; }
+          break;
         }
+        if (is == 1) { double* pn = side ? pnp : pnm; pn[2 * ks] = pn[2 * ks - 1]; }   // PN(1,ks) = PN(2,ks-1)
       }
     }
-  }();
+  }
 
   if (A.surface_align) {  // :408-479
     int issa_m = 1;
@@ -391,78 +411,112 @@ ndiff_face(Geom g, NdArgs A) {
   }
 
   // ---- second search: neutral layers and their fluxes (:525-911)
+  // The reference keeps the previous/current neutral interface in two slots that swap (nip/nic); here they
+  // are plain "prev"/"cur" registers and cur is copied to prev when an interface has been found (a slot
+  // index would put them in local memory).  The polynomial coefficients of the current source layer of
+  // each side (tpc_src, 5 per scalar) stay in registers while ks_m / ks_p do not change: peval and pmeval
+  // are evaluated for every neutral interface found inside a layer, which took a quarter of all
+  // instructions as strided loads and their address arithmetic.  The branches of the case analysis only
+  // decide HOW the interface values are obtained (ev_m/ev_p); the evaluation itself and the flux
+  // computation run after the branches have reconverged.
   SideAcc<NT> accm, accp;
   accm.init(A.cvm + x, lev, kk, T);
   accp.init(A.cvp + x, lev, kk, T);
   {
+    constexpr int NTC = NT > 0 ? NT : NTMAX;
+    constexpr bool CACHE = NT > 0 && NT <= 3;     // register budget: 10 doubles per scalar
+    double cfm[CACHE ? NTC : 1][5], cfp[CACHE ? NTC : 1][5];
+    int kc_m = 0, kc_p = 0;                        // layers whose coefficients are cached
+    auto coef = [&](const Col& c, int k, int nt, double (&o)[5]) {
+      const double* b5 = c.tpc + (long)(((nt - 1) * kk + k - 1) * 5) * lev;
+      o[0] = b5[0]; o[1] = b5[lev]; o[2] = b5[2 * lev]; o[3] = b5[3 * lev]; o[4] = b5[4 * lev];
+    };
+    auto need_m = [&]() {
+      if (CACHE && kc_m != ks_m) {
+#pragma unroll
+        for (int nt = 1; nt <= NTC; ++nt) coef(M, ks_m, nt, cfm[CACHE ? nt - 1 : 0]);
+        kc_m = ks_m;
+      }
+    };
+    auto need_p = [&]() {
+      if (CACHE && kc_p != ks_p) {
+#pragma unroll
+        for (int nt = 1; nt <= NTC; ++nt) coef(P, ks_p, nt, cfp[CACHE ? nt - 1 : 0]);
+        kc_p = ks_p;
+      }
+    };
+    auto pe = [&](const double (&c)[5], double xx) { return (((c[4] * xx + c[3]) * xx + c[2]) * xx + c[1]) * xx + c[0]; };
+    auto pme = [&](const double (&c)[5], double x0, double x1) {
+      const double c1_2 = 1. / 2., c1_3 = 1. / 3., c1_4 = 1. / 4., c1_5 = 1. / 5.;
+      const double b5 = c1_5 * c[4];
+      const double b4 = b5 * x1 + c1_4 * c[3];
+      const double b3 = b4 * x1 + c1_3 * c[2];
+      const double b2 = b3 * x1 + c1_2 * c[1];
+      const double b1 = b2 * x1 + c[0];
+      return (((b5 * x0 + b4) * x0 + b3) * x0 + b2) * x0 + b1;
+    };
+
     is_m = 2; ks_m = 0; is_p = 2; ks_p = 0;
     int kd_m = 0, kd_p = 0, isn_m = 1, isn_p = 1, ksn_m = 1, ksn_p = 1, ks_m_prev = 0, ks_p_prev = 0;
     bool advance_src_m = true, advance_src_p = true, advance_dst_m = true, advance_dst_p = true;
-    int nip = 0, nic = 1;
-    p_ni_m[nip] = -mval; p_ni_p[nip] = -mval;
+    double p_prev_m = -mval, p_prev_p = -mval, p_cur_m = 0., p_cur_p = 0.;
+    double x_prev_m = 0., x_prev_p = 0., x_cur_m = 0., x_cur_p = 0.;
+    double t_prev_m[NTC], t_prev_p[NTC], t_cur_m[NTC], t_cur_p[NTC];
+#pragma unroll
+    for (int q = 0; q < NTC; ++q) { t_prev_m[q] = 0.; t_prev_p[q] = 0.; t_cur_m[q] = 0.; t_cur_p[q] = 0.; }
     int kuv = 1;
     const double* puvx = A.puv + x;
     auto puv = [&](int k) { return puvx[(long)(k - 1) * lev]; };
 
     for (;;) {
-      if (advance_src_m) {
-        bool out = false;
+      // advance to the next source interface of the minus and/or the plus column (mirrored blocks of the
+      // reference, written once; lanes that advance different columns run together)
+      if (advance_src_m || advance_src_p) {
+        int side = advance_src_m ? 0 : 1;
+        bool then_p = advance_src_m && advance_src_p, out = false;
         for (;;) {
-          if (is_m == 1) {
-            is_m = 2;
-            if (stabm(ks_m)) break;
-          } else {
-            ks_m = ks_m + 1;
-            if (ks_m > ksmx_m) { out = true; break; }
-            is_m = 1;
-            if (stabm(ks_m) && PNM(is_m, ks_m) != mval) break;
+          int is = side ? is_p : is_m, ks = side ? ks_p : ks_m;
+          const int kmx = side ? ksmx_p : ksmx_m;
+          const unsigned long long stab = side ? stab_p : stab_m;
+          const double* pn = side ? pnp : pnm;
+          for (;;) {
+            if (is == 1) {
+              is = 2;
+              if (ks >= 1 && ((stab >> (ks - 1)) & 1ull)) break;
+            } else {
+              ks = ks + 1;
+              if (ks > kmx) { out = true; break; }
+              is = 1;
+              if (((stab >> (ks - 1)) & 1ull) && pn[2 * ks + is - 1] != mval) break;
+            }
           }
+          if (out) break;
+          int isn = is, ksn = ks;
+          while (pn[2 * ksn + isn - 1] == mval) {
+            if (isn == 1) isn = 2;
+            else {
+              if (ksn == kmx) break;
+              ksn = ksn + 1;
+              isn = 1;
+            }
+          }
+          if (side) { is_p = is; ks_p = ks; isn_p = isn; ksn_p = ksn; }
+          else { is_m = is; ks_m = ks; isn_m = isn; ksn_m = ksn; }
+          if (then_p) { then_p = false; side = 1; continue; }
+          break;
         }
         if (out) break;
-        isn_m = is_m; ksn_m = ks_m;
-        while (PNM(isn_m, ksn_m) == mval) {
-          if (isn_m == 1) isn_m = 2;
-          else {
-            if (ksn_m == ksmx_m) break;
-            ksn_m = ksn_m + 1;
-            isn_m = 1;
-          }
-        }
-      }
-      if (advance_src_p) {
-        bool out = false;
-        for (;;) {
-          if (is_p == 1) {
-            is_p = 2;
-            if (stabp(ks_p)) break;
-          } else {
-            ks_p = ks_p + 1;
-            if (ks_p > ksmx_p) { out = true; break; }
-            is_p = 1;
-            if (stabp(ks_p) && PNP(is_p, ks_p) != mval) break;
-          }
-        }
-        if (out) break;
-        isn_p = is_p; ksn_p = ks_p;
-        while (PNP(isn_p, ksn_p) == mval) {
-          if (isn_p == 1) isn_p = 2;
-          else {
-            if (ksn_p == ksmx_p) break;
-            ksn_p = ksn_p + 1;
-            isn_p = 1;
-          }
-        }
       }
       // the quantities every branch below looks at
       const double pnm_n = PNM(isn_m, ksn_m), pnp_n = PNP(isn_p, ksn_p);
       const double psm_n = M.psd(isn_m, ksn_m), psp_n = P.psd(isn_p, ksn_p);
-      if (p_ni_m[nip] == -mval) {
+      if (p_prev_m == -mval) {
         if ((pnm_n - psp_n) < (pnp_n - psm_n)) {
-          p_ni_m[nip] = psm_n;
-          p_ni_p[nip] = pnm_n;
+          p_prev_m = psm_n;
+          p_prev_p = pnm_n;
         } else {
-          p_ni_m[nip] = pnp_n;
-          p_ni_p[nip] = psp_n;
+          p_prev_m = pnp_n;
+          p_prev_p = psp_n;
         }
       }
       if (advance_dst_m) {
@@ -476,13 +530,13 @@ ndiff_face(Geom g, NdArgs A) {
       const double psm1 = M.psd(1, ks_m), psm2 = M.psd(2, ks_m), psp1 = P.psd(1, ks_p), psp2 = P.psd(2, ks_p);
       {
         bool out = false;
-        const double lim_m = fmax(psm1, p_ni_m[nip]);
+        const double lim_m = fmax(psm1, p_prev_m);
         while (M.dstsnp(kd_m + 1) <= lim_m) {
           kd_m = kd_m + 1;
           if (kd_m > kdmx_m) { out = true; break; }
         }
         if (out) break;
-        const double lim_p = fmax(psp1, p_ni_p[nip]);
+        const double lim_p = fmax(psp1, p_prev_p);
         while (P.dstsnp(kd_p + 1) <= lim_p) {
           kd_p = kd_p + 1;
           if (kd_p > kdmx_p) { out = true; break; }
@@ -506,20 +560,15 @@ ndiff_face(Geom g, NdArgs A) {
         case_p = 2;
       }
       bool found_ni = false;
-      auto eval_both = [&]() {
-#pragma unroll
-        for (int nt = 1; nt <= (NT > 0 ? NT : NTMAX); ++nt)
-          if (nt <= T) {
-            t_ni_m[nic][nt - 1] = peval(M, ks_m, nt, x_ni_m[nic]);
-            t_ni_p[nic][nt - 1] = peval(P, ks_p, nt, x_ni_p[nic]);
-          }
-      };
+      // how the scalar values at the new interface are obtained: 1 = polynomial at x_cur, 2 = stored
+      // interface value t_srcdi(is,ks)
+      int ev_m = 0, ev_p = 0;
 
       if (case_m == 3 && case_p == 3) {
         if (is_p == 2 && is_m == 2) {
-          p_ni_m[nic] = snp_m;
-          p_ni_p[nic] = snp_p;
-          const double pu_m = p_ni_m[nip], pu_p = p_ni_p[nip];
+          p_cur_m = snp_m;
+          p_cur_p = snp_p;
+          const double pu_m = p_prev_m, pu_p = p_prev_p;
           double pl_m, pl_p;
           if ((pnm_n - psp_n) < (pnp_n - psm_n)) {
             pl_m = psm_n;
@@ -528,22 +577,22 @@ ndiff_face(Geom g, NdArgs A) {
             pl_m = pnp_n;
             pl_p = psp_n;
           }
-          const double pp1 = (p_ni_m[nic] - pu_m) * (pl_p - pu_p);
-          const double pp2 = (p_ni_p[nic] - pu_p) * (pl_m - pu_m);
+          const double pp1 = (p_cur_m - pu_m) * (pl_p - pu_p);
+          const double pp2 = (p_cur_p - pu_p) * (pl_m - pu_m);
           if (fabs(pp1 - pp2) < dp_eps * fmax(dp_eps, pl_m - pu_m + pl_p - pu_p)) {
             advance_dst_m = true;
             advance_dst_p = true;
           } else if (pp1 < pp2) {
-            p_ni_p[nic] = pu_p + pp1 / (pl_m - pu_m);
+            p_cur_p = pu_p + pp1 / (pl_m - pu_m);
             advance_dst_m = true;
           } else {
-            p_ni_m[nic] = pu_m + pp2 / (pl_p - pu_p);
+            p_cur_m = pu_m + pp2 / (pl_p - pu_p);
             advance_dst_p = true;
           }
-          if (p_ni_m[nic] >= psm1 && p_ni_m[nic] <= psm2 && p_ni_p[nic] >= psp1 && p_ni_p[nic] <= psp2) {
-            x_ni_m[nic] = (p_ni_m[nic] - psm1) / (psm2 - psm1);
-            x_ni_p[nic] = (p_ni_p[nic] - psp1) / (psp2 - psp1);
-            eval_both();
+          if (p_cur_m >= psm1 && p_cur_m <= psm2 && p_cur_p >= psp1 && p_cur_p <= psp2) {
+            x_cur_m = (p_cur_m - psm1) / (psm2 - psm1);
+            x_cur_p = (p_cur_p - psp1) / (psp2 - psp1);
+            ev_m = 1; ev_p = 1;
             found_ni = true;
           }
         } else {
@@ -552,15 +601,15 @@ ndiff_face(Geom g, NdArgs A) {
         }
       } else if (case_m == 3) {
         if (is_p == 2) {
-          p_ni_m[nic] = snp_m;
+          p_cur_m = snp_m;
           if (case_p == 1)
-            p_ni_p[nic] = p_ni_p[nip] + (p_ni_m[nic] - p_ni_m[nip]) * (psp_n - p_ni_p[nip]) / (pnp_n - p_ni_m[nip]);
+            p_cur_p = p_prev_p + (p_cur_m - p_prev_m) * (psp_n - p_prev_p) / (pnp_n - p_prev_m);
           else
-            p_ni_p[nic] = p_ni_p[nip] + (p_ni_m[nic] - p_ni_m[nip]) * (pnm_n - p_ni_p[nip]) / (psm_n - p_ni_m[nip]);
-          if (p_ni_p[nic] >= psp1 && p_ni_p[nic] <= psp2) {
-            x_ni_m[nic] = (snp_m - psm1) / (psm2 - psm1);
-            x_ni_p[nic] = (p_ni_p[nic] - psp1) / (psp2 - psp1);
-            eval_both();
+            p_cur_p = p_prev_p + (p_cur_m - p_prev_m) * (pnm_n - p_prev_p) / (psm_n - p_prev_m);
+          if (p_cur_p >= psp1 && p_cur_p <= psp2) {
+            x_cur_m = (snp_m - psm1) / (psm2 - psm1);
+            x_cur_p = (p_cur_p - psp1) / (psp2 - psp1);
+            ev_m = 1; ev_p = 1;
             found_ni = true;
             advance_dst_m = true;
           } else {
@@ -572,15 +621,15 @@ ndiff_face(Geom g, NdArgs A) {
         }
       } else if (case_p == 3) {
         if (is_m == 2) {
-          p_ni_p[nic] = snp_p;
+          p_cur_p = snp_p;
           if (case_m == 1)
-            p_ni_m[nic] = p_ni_m[nip] + (p_ni_p[nic] - p_ni_p[nip]) * (psm_n - p_ni_m[nip]) / (pnm_n - p_ni_p[nip]);
+            p_cur_m = p_prev_m + (p_cur_p - p_prev_p) * (psm_n - p_prev_m) / (pnm_n - p_prev_p);
           else
-            p_ni_m[nic] = p_ni_m[nip] + (p_ni_p[nic] - p_ni_p[nip]) * (pnp_n - p_ni_m[nip]) / (psp_n - p_ni_p[nip]);
-          if (p_ni_m[nic] >= psm1 && p_ni_m[nic] <= psm2) {
-            x_ni_p[nic] = (snp_p - psp1) / (psp2 - psp1);
-            x_ni_m[nic] = (p_ni_m[nic] - psm1) / (psm2 - psm1);
-            eval_both();
+            p_cur_m = p_prev_m + (p_cur_p - p_prev_p) * (pnp_n - p_prev_m) / (psp_n - p_prev_p);
+          if (p_cur_m >= psm1 && p_cur_m <= psm2) {
+            x_cur_p = (snp_p - psp1) / (psp2 - psp1);
+            x_cur_m = (p_cur_m - psm1) / (psm2 - psm1);
+            ev_m = 1; ev_p = 1;
             found_ni = true;
             advance_dst_p = true;
           } else {
@@ -593,16 +642,11 @@ ndiff_face(Geom g, NdArgs A) {
       } else if (case_m == 1 && case_p == 1) {
         const double pnm_c = PNM(is_m, ks_m), pnp_c = PNP(is_p, ks_p);
         if (pnm_c != mval && pnp_c != mval) {
-          x_ni_m[nic] = (double)(is_m - 1);
-          p_ni_m[nic] = psm;
-          x_ni_p[nic] = (double)(is_p - 1);
-          p_ni_p[nic] = psp;
-#pragma unroll
-          for (int nt = 1; nt <= (NT > 0 ? NT : NTMAX); ++nt)
-            if (nt <= T) {
-              t_ni_m[nic][nt - 1] = M.tsrcdi(is_m, ks_m, nt);
-              t_ni_p[nic][nt - 1] = P.tsrcdi(is_p, ks_p, nt);
-            }
+          x_cur_m = (double)(is_m - 1);
+          p_cur_m = psm;
+          x_cur_p = (double)(is_p - 1);
+          p_cur_p = psp;
+          ev_m = 2; ev_p = 2;
           found_ni = true;
           advance_src_m = true;
           advance_src_p = true;
@@ -613,32 +657,22 @@ ndiff_face(Geom g, NdArgs A) {
       } else if (case_m == 1) {
         const double pnm_c = PNM(is_m, ks_m);
         if (pnm_c != mval && pnm_c >= psp1) {
-          x_ni_m[nic] = (double)(is_m - 1);
-          p_ni_m[nic] = psm;
-          p_ni_p[nic] = pnm_c;
-          x_ni_p[nic] = (p_ni_p[nic] - psp1) / (psp2 - psp1);
-#pragma unroll
-          for (int nt = 1; nt <= (NT > 0 ? NT : NTMAX); ++nt)
-            if (nt <= T) {
-              t_ni_m[nic][nt - 1] = M.tsrcdi(is_m, ks_m, nt);
-              t_ni_p[nic][nt - 1] = peval(P, ks_p, nt, x_ni_p[nic]);
-            }
+          x_cur_m = (double)(is_m - 1);
+          p_cur_m = psm;
+          p_cur_p = pnm_c;
+          x_cur_p = (p_cur_p - psp1) / (psp2 - psp1);
+          ev_m = 2; ev_p = 1;
           found_ni = true;
         }
         advance_src_m = true;
       } else if (case_p == 1) {
         const double pnp_c = PNP(is_p, ks_p);
         if (pnp_c != mval && pnp_c >= psm1) {
-          x_ni_p[nic] = (double)(is_p - 1);
-          p_ni_p[nic] = psp;
-          p_ni_m[nic] = pnp_c;
-          x_ni_m[nic] = (p_ni_m[nic] - psm1) / (psm2 - psm1);
-#pragma unroll
-          for (int nt = 1; nt <= (NT > 0 ? NT : NTMAX); ++nt)
-            if (nt <= T) {
-              t_ni_p[nic][nt - 1] = P.tsrcdi(is_p, ks_p, nt);
-              t_ni_m[nic][nt - 1] = peval(M, ks_m, nt, x_ni_m[nic]);
-            }
+          x_cur_p = (double)(is_p - 1);
+          p_cur_p = psp;
+          p_cur_m = pnp_c;
+          x_cur_m = (p_cur_m - psm1) / (psm2 - psm1);
+          ev_p = 2; ev_m = 1;
           found_ni = true;
         }
         advance_src_p = true;
@@ -648,24 +682,35 @@ ndiff_face(Geom g, NdArgs A) {
       }
 
       if (found_ni) {  // :795-907
-        const double dp_ni_m = fmin(p_ni_m[nic] - p_ni_m[nip], M.pdst(kd_m + 1) - M.pdst(kd_m));
-        const double dp_ni_p = fmin(p_ni_p[nic] - p_ni_p[nip], P.pdst(kd_p + 1) - P.pdst(kd_p));
+        // NOTE: advance_src_* set above only act at the top of the next iteration: is/ks are still the
+        // ones the interface was found for
+        need_m(); need_p();
+#pragma unroll
+        for (int nt = 1; nt <= NTC; ++nt)
+          if (nt <= T) {
+            t_cur_m[nt - 1] = ev_m == 2 ? M.tsrcdi(is_m, ks_m, nt)
+                                        : (CACHE ? pe(cfm[CACHE ? nt - 1 : 0], x_cur_m) : peval(M, ks_m, nt, x_cur_m));
+            t_cur_p[nt - 1] = ev_p == 2 ? P.tsrcdi(is_p, ks_p, nt)
+                                        : (CACHE ? pe(cfp[CACHE ? nt - 1 : 0], x_cur_p) : peval(P, ks_p, nt, x_cur_p));
+          }
+        const double dp_ni_m = fmin(p_cur_m - p_prev_m, M.pdst(kd_m + 1) - M.pdst(kd_m));
+        const double dp_ni_p = fmin(p_cur_p - p_prev_p, P.pdst(kd_p + 1) - P.pdst(kd_p));
         const double dp_ni = 2. * dp_ni_m * dp_ni_p / fmax(dp_ni_m + dp_ni_p, 2. * dp_eps);
-        if (ks_m == ks_m_prev && ks_p == ks_p_prev && p_ni_m[nip] >= M.dstsnp(kd_m) && p_ni_m[nic] <= snp_m &&
-            p_ni_p[nip] >= P.dstsnp(kd_p) && p_ni_p[nic] <= snp_p && dp_ni > 2. * dp_eps) {
+        if (ks_m == ks_m_prev && ks_p == ks_p_prev && p_prev_m >= M.dstsnp(kd_m) && p_cur_m <= snp_m &&
+            p_prev_p >= P.dstsnp(kd_p) && p_cur_p <= snp_p && dp_ni > 2. * dp_eps) {
           accm.advance(kd_m);
           accp.advance(kd_p);
           const double q = .5 * cdiff * (A.difiso[xm + (long)(ks_m - 1) * lev] + A.difiso[x + (long)(ks_p - 1) * lev]) * dp_ni;
           double tflx = 0., sflx = 0.;
           bool ts_ok = true;
 #pragma unroll
-          for (int nt = 1; nt <= (NT > 0 ? NT : NTMAX); ++nt)
+          for (int nt = 1; nt <= NTC; ++nt)
             if (nt <= T) {
-              const double d = pmeval(M, ks_m, nt, x_ni_m[nip], x_ni_m[nic]) -
-                               pmeval(P, ks_p, nt, x_ni_p[nip], x_ni_p[nic]);
+              const double d = CACHE ? pme(cfm[CACHE ? nt - 1 : 0], x_prev_m, x_cur_m) - pme(cfp[CACHE ? nt - 1 : 0], x_prev_p, x_cur_p)
+                                     : pmeval(M, ks_m, nt, x_prev_m, x_cur_m) - pmeval(P, ks_p, nt, x_prev_p, x_cur_p);
               const double cm = A.tlev[nt - 1][xm + (long)(ks_m - 1) * lev], cp = A.tlev[nt - 1][x + (long)(ks_p - 1) * lev];
-              const bool ok = d * (cm - cp) >= 0. && d * (t_ni_m[nip][nt - 1] - t_ni_p[nip][nt - 1]) >= 0. &&
-                              d * (t_ni_m[nic][nt - 1] - t_ni_p[nic][nt - 1]) >= 0.;
+              const bool ok = d * (cm - cp) >= 0. && d * (t_prev_m[nt - 1] - t_prev_p[nt - 1]) >= 0. &&
+                              d * (t_cur_m[nt - 1] - t_cur_p[nt - 1]) >= 0.;
               if (nt == IT) { tflx = q * d; ts_ok = ok; }
               else if (nt == IS) { sflx = q * d; ts_ok = ts_ok && ok; }
               else if (ok) {
@@ -677,8 +722,8 @@ ndiff_face(Geom g, NdArgs A) {
           if (ts_ok) {
             accm.a[IT - 1] += tflx; accp.a[IT - 1] -= tflx;
             accm.a[IS - 1] += sflx; accp.a[IS - 1] -= sflx;
-            const double p_ni_up = .5 * (p_ni_m[nip] + p_ni_p[nip]);
-            const double p_ni_lo = .5 * (p_ni_m[nic] + p_ni_p[nic]);
+            const double p_ni_up = .5 * (p_prev_m + p_prev_p);
+            const double p_ni_lo = .5 * (p_cur_m + p_cur_p);
             const double dp_ni_i = 1. / fmax(epsilp, p_ni_lo - p_ni_up);
             while (kuv <= kk) {
               const long o = x + (long)(kuv + mm - 1) * lev;
@@ -697,44 +742,17 @@ ndiff_face(Geom g, NdArgs A) {
         }
         ks_m_prev = ks_m;
         ks_p_prev = ks_p;
-        nip = 1 - nip;
-        nic = 1 - nic;
+        p_prev_m = p_cur_m; p_prev_p = p_cur_p; x_prev_m = x_cur_m; x_prev_p = x_cur_p;
+#pragma unroll
+        for (int q2 = 0; q2 < NTC; ++q2) { t_prev_m[q2] = t_cur_m[q2]; t_prev_p[q2] = t_cur_p[q2]; }
       }
     }
   }
   accm.finish();
   accp.finish();
 
-  // ---- neutral slope at the destination interfaces (:913-951)
-  double* nslp = A.nslp + x;
-  if (nns == 0) {
-    for (int k = 1; k <= kk; ++k) nslp[(long)(k - 1) * lev] = 0.;
-  } else {
-    double p_nslp_dst = 0.;
-    int kd;
-    for (kd = 1; kd <= kk; ++kd) {
-      p_nslp_dst = .5 * (M.pdst(kd) + P.pdst(kd));
-      if (p_nslp_dst > p_nslp_src[1]) break;
-      nslp[(long)(kd - 1) * lev] = nslp_src[1];
-    }
-    if (kd <= kk) {
-      int ks = 1;
-      bool done = false;
-      for (;;) {
-        while (p_nslp_dst > p_nslp_src[ks]) {
-          if (ks == nns) { done = true; break; }
-          ks = ks + 1;
-        }
-        if (done) break;
-        const double q = (p_nslp_src[ks] - p_nslp_dst) / fmax(p_nslp_src[ks] - p_nslp_src[ks - 1], epsilp);
-        nslp[(long)(kd - 1) * lev] = q * nslp_src[ks - 1] + (1. - q) * nslp_src[ks];
-        kd = kd + 1;
-        if (kd > kk) break;
-        p_nslp_dst = .5 * (M.pdst(kd) + P.pdst(kd));
-      }
-      for (; kd <= kk; ++kd) nslp[(long)(kd - 1) * lev] = nslp_src[nns];
-    }
-  }
+  // ---- neutral slope at the destination interfaces below the last pair (:913-951, tail of emit_slope)
+  for (; kd_sl <= kk; ++kd_sl) nslp[(long)(kd_sl - 1) * lev] = nns == 0 ? 0. : s_prev;
 #undef PNM
 #undef PNP
 }
@@ -775,8 +793,7 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   if (T > NTMAX) throw std::runtime_error("ndiff: more than 8 diffused scalars are not compiled in");
   const bool surface_align = c.option("ndiff_surface_align", "1") == "1";   // namelist default .true.
   if (surface_align) halo_update(c.dev("dpml"), 1, 1, 1, halo_ps);
-  double* drdt = c.owned("_nd_drhodt", 2 * kk);
-  double* drds = c.owned("_nd_drhods", 2 * kk);
+  double* rec = c.owned("_nd_rec", 8 * kk);   // 2*kk interface records of 4 doubles per cell
   double* snp = c.owned("_nd_dstsnp", kk + 1);
   int* kdmx = c.owned_int("_nd_kdmx", 1);
   double* ucm = c.owned("_nd_ucm", kk * T);
@@ -785,12 +802,12 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   double* vcp = c.owned("_nd_vcp", kk * T);
 
   LAUNCH(ndiff_prep, dim3(cdiv(g.ii + 2, 128), g.jj + 2), 128, 0, g, mm, T, c.idev("ip"), c.idev("iu"), c.idev("iv"),
-         c.idev("nd_ksmx"), c.dev("nd_p_src"), c.dev("nd_t_srcdi"), c.dev("nd_p_dst"), kdmx, drdt, drds, snp,
+         c.idev("nd_ksmx"), c.dev("nd_p_src"), c.dev("nd_t_srcdi"), c.dev("nd_p_dst"), kdmx, rec, snp,
          c.dev("utflld"), c.dev("usflld"), c.dev("vtflld"), c.dev("vsflld"));
 
   NdArgs A{};
   A.p_src = c.dev("nd_p_src"); A.tsd = c.dev("nd_t_srcdi"); A.tpc = c.dev("nd_tpc_src");
-  A.drdt = drdt; A.drds = drds; A.p_dst = c.dev("nd_p_dst"); A.snp = snp;
+  A.rec = rec; A.p_dst = c.dev("nd_p_dst"); A.snp = snp;
   A.ksmx = c.idev("nd_ksmx"); A.kdmx = kdmx;
   A.dpml = c.dev("dpml"); A.difiso = c.dev("difiso");
   A.tlev[0] = c.dev("temp") + (long)nn * g.lev;
@@ -808,16 +825,16 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   V.nslp = c.dev("nslpy"); V.cvm = vcm; V.cvp = vcp;
 
   const dim3 gu(cdiv(g.ii + 1, 128), g.jj), gv(cdiv(g.ii, 128), g.jj + 1);
-  if (T == 2) {
-    LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, 2>), gu, 128, 0, g, U);
-    LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, 2>), gv, 128, 0, g, V);
-  } else if (T == 3) {
-    LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, 3>), gu, 128, 0, g, U);
-    LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, 3>), gv, 128, 0, g, V);
-  } else {
-    LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, 0>), gu, 128, 0, g, U);
-    LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, 0>), gv, 128, 0, g, V);
-  }
+  // resident blocks per SM (register budget 65536/(128*MINB)): development switch ndiff_minblk = 4 | 5 | 6
+  // (tnx1v4, one direction: 2 blocks 10.4 ms, 3 blocks 8.4 ms, 4 blocks 7.3 ms)
+#define ND_FACE(NT_)                                                                              \
+  OCC_DISPATCH3("ndiff_minblk", 4, 4, 5, 6,                                                       \
+                LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, OCC>), gu, 128, 0, g, U);       \
+                LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, NT_, OCC>), gv, 128, 0, g, V))
+  if (T == 2) { ND_FACE(2); }
+  else if (T == 3) { ND_FACE(3); }
+  else { ND_FACE(0); }
+#undef ND_FACE
   LAUNCH(ndiff_update, dim3(cdiv(g.ii, 256), g.jj, kk), 256, 0, g, T, c.idev("ip"), c.idev("iu"), c.idev("iv"),
          c.dev("scp2"), c.dev("nd_p_dst"), ucm, ucp, vcm, vcp, c.dev("nd_trc_rm"));
 }

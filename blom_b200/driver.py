@@ -166,6 +166,63 @@ class HotPath:
                     g.download_async(nm)
                     self._early.add(nm)
 
+    def step_pipelined(self):
+        """One end-to-end pass with the host<->device copies overlapped with the kernels (the call sequence a
+        host that keeps its own copy of the prognostic state would issue):
+          H2D  the time level the host physics wrote (new level n) of dp,T,S[,trc], then u,v, on the upload
+               stream; tmsmt1 waits for dp/T/S, u,v are first read by momtum (advect only reads the resident
+               mid level), so their copy hides behind tmsmt1..pgforc.  The u,v halo refresh of difest
+               (phy/mod_difest.F90:826-827) moves with them to just before momtum - nothing reads or writes
+               u,v in between, so the values are the ones run_step produces.
+          D2H  on the copy stream as soon as a field's last writer has been enqueued: u,v (both levels,
+               momtum also rewrites the mid level) after momtum; dp,T,S[,trc] new level after pbcor2, mid
+               level after tmsmt2 (phy/mod_blom_step.F90:169-227).
+        Ends with everything on the host (sync).  Falls back to upload / step / download when the routine set
+        is restricted."""
+        g, kk = self.gpu, self.kdm
+        m, n, mm, nn, k1m, k1n = self.levels
+        need = ("tmsmt1", "momtum", "pbcor2", "tmsmt2")
+        if any(r not in self.routines for r in need):
+            self.upload_inputs(); self.step(early_download=True); self.download_outputs()
+            return
+        from .lib import HALO_PS, HALO_UV, HALO_VV, HALO_US, HALO_VS
+        scal = [("dp", 0), ("temp", 0), ("saln", 0)] + [("trc", nt * 2 * kk) for nt in range(self.ntr)]
+        for nm, off in scal:
+            g.upload_async(nm, off + k1n, kk)
+        for nm in ("u", "v"):
+            g.upload_async(nm, k1n, kk)
+        for r in self.routines:
+            if r == "tmsmt1":
+                for nm in {nm for nm, _ in scal}:
+                    g.wait_upload(nm)
+                g.tmsmt1(nn)
+                for nm, it in (("ubflxs_p", HALO_UV), ("vbflxs_p", HALO_VV), ("pbu", HALO_US), ("pbv", HALO_VS)):
+                    g.xctilr(nm, 1, 2, 2, 2, it)
+                g.xctilr("temp", 1, 2 * kk, 3, 3, HALO_PS)
+                g.xctilr("saln", 1, 2 * kk, 3, 3, HALO_PS)
+            elif r == "momtum":
+                g.wait_upload("u"); g.wait_upload("v")
+                g.xctilr("u", 1, 2 * kk, 2, 2, HALO_UV)
+                g.xctilr("v", 1, 2 * kk, 2, 2, HALO_VV)
+                g.momtum(m, n, mm, nn, k1m, k1n)
+                g.download_async("u"); g.download_async("v")
+            elif r == "pbcor2":
+                g.pbcor2(m, n, mm, nn, k1m, k1n)
+                for nm, off in scal:
+                    g.download_levels_async(nm, off + k1n, kk)
+            elif r == "tmsmt2":
+                g.tmsmt2(m, mm, nn, k1m)
+                for nm, off in scal:
+                    g.download_levels_async(nm, off + k1m, kk)
+            else:
+                run_step(g, [r], self.levels)
+        g.sync()
+
+    def io_bytes_pipelined(self):
+        """(H2D, D2H) bytes of one step_pipelined(): the new level up, both levels down."""
+        b = sum(self.arrays[nm].nbytes for nm in IO_FIELDS if nm in self.arrays)
+        return b // 2, b
+
     def advance(self, early_download=False):
         """step() followed by the leap-frog role swap of the time levels."""
         self.step(early_download)

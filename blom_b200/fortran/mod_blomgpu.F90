@@ -69,6 +69,20 @@ module mod_blomgpu
          import :: c_int, c_char
          character(kind=c_char), intent(in) :: name(*)
       end function
+      integer(c_int) function blomgpu_download_levels_async(name, koff, nlev) bind(C, name='blomgpu_download_levels_async')
+         import :: c_int, c_char
+         character(kind=c_char), intent(in) :: name(*)
+         integer(c_int), value :: koff, nlev
+      end function
+      integer(c_int) function blomgpu_upload_async(name, koff, nlev) bind(C, name='blomgpu_upload_async')
+         import :: c_int, c_char
+         character(kind=c_char), intent(in) :: name(*)
+         integer(c_int), value :: koff, nlev
+      end function
+      integer(c_int) function blomgpu_wait_upload(name) bind(C, name='blomgpu_wait_upload')
+         import :: c_int, c_char
+         character(kind=c_char), intent(in) :: name(*)
+      end function
       integer(c_int) function blomgpu_upload_all() bind(C, name='blomgpu_upload_all')
          import :: c_int
       end function
@@ -122,6 +136,12 @@ module mod_blomgpu
          import :: c_int, c_char, c_int32_t
          character(kind=c_char), intent(in) :: name(*)
          integer(c_int), value :: kcsd, itype
+         integer(c_int32_t), intent(out) :: crc
+      end function
+      integer(c_int) function blomgpu_chksum_at(name, koff, kcsd, itype, crc) bind(C, name='blomgpu_chksum_at')
+         import :: c_int, c_char, c_int32_t
+         character(kind=c_char), intent(in) :: name(*)
+         integer(c_int), value :: koff, kcsd, itype
          integer(c_int32_t), intent(out) :: crc
       end function
       integer(c_int) function blomgpu_bigrid(depth_name) bind(C, name='blomgpu_bigrid')
@@ -180,7 +200,8 @@ module mod_blomgpu
    procedure(six_int_entry), bind(C, name='blomgpu_cmnfld_nnslope_ale') :: blomgpu_cmnfld_nnslope_ale
 
    public :: gpu_setup, gpu_register, gpu_register_int, gpu_upload, gpu_download, gpu_download_async, &
-             gpu_option, gpu_scalar, gpu_xctilr, gpu_xcsum, gpu_xcmax, gpu_xcmin, gpu_chksum, gpu_nreg, &
+             gpu_download_levels_async, gpu_upload_async, gpu_wait_upload, &
+             gpu_option, gpu_scalar, gpu_xctilr, gpu_xcsum, gpu_xcmax, gpu_xcmin, gpu_chksum, gpu_chksum_at, gpu_nreg, &
              init_fluxes, tmsmt1, difest_halos, eddtra, advect, pbcor1, diffus, pgforc, momtum, &
              barotp, pbcor2, tmsmt2, ndiff, cmnfld2, cmnfld_bfsqf_ale, cmnfld_nslope_ale, &
              cmnfld_nnslope_ale, budget_init, budget_sums
@@ -243,6 +264,26 @@ contains
       call check(blomgpu_download_async(cstr(name)), 'download_async '//name)
    end subroutine gpu_download_async
 
+   subroutine gpu_download_levels_async(name, koff, nlev)
+      ! levels koff..koff+nlev-1 (e.g. k1n,kk: the new time level) device -> host on the copy stream
+      character(len=*), intent(in) :: name
+      integer, intent(in) :: koff, nlev
+      call check(blomgpu_download_levels_async(cstr(name), koff, nlev), 'download_levels_async '//name)
+   end subroutine gpu_download_levels_async
+
+   subroutine gpu_upload_async(name, koff, nlev)
+      ! host -> device on the upload stream, overlapping the routines called next
+      character(len=*), intent(in) :: name
+      integer, intent(in) :: koff, nlev
+      call check(blomgpu_upload_async(cstr(name), koff, nlev), 'upload_async '//name)
+   end subroutine gpu_upload_async
+
+   subroutine gpu_wait_upload(name)
+      ! the library stream waits for the last gpu_upload_async of this field (the host does not block)
+      character(len=*), intent(in) :: name
+      call check(blomgpu_wait_upload(cstr(name)), 'wait_upload '//name)
+   end subroutine gpu_wait_upload
+
    subroutine gpu_option(key, val)
       character(len=*), intent(in) :: key, val
       call check(blomgpu_set_option(cstr(key), cstr(val)), 'option '//key)
@@ -293,6 +334,16 @@ contains
       call check(blomgpu_chksum(cstr(name), int(kcsd, c_int), int(itype, c_int), crc), 'chksum '//name)
       if (mnproc == 1) write (lp, '(3a,z8.8)') ' chksum: ', text, ': 0x', crc
    end subroutine gpu_chksum
+
+   ! chksum(a(1-nbdy,1-nbdy,koff), kcsd, itype, text), e.g. the k1m level block of the flux arrays
+   subroutine gpu_chksum_at(name, koff, kcsd, itype, text)
+      character(len=*), intent(in) :: name, text
+      integer, intent(in) :: koff, kcsd, itype
+      integer(c_int32_t) :: crc
+      call check(blomgpu_chksum_at(cstr(name), int(koff, c_int), int(kcsd, c_int), int(itype, c_int), crc), &
+                 'chksum '//name)
+      if (mnproc == 1) write (lp, '(3a,z8.8)') ' chksum: ', text, ': 0x', crc
+   end subroutine gpu_chksum_at
 
    ! region type found by the device bigrid (0 closed ... 4 periodic in j), phy/mod_xc.F90:54-92
    integer function gpu_nreg()

@@ -27,9 +27,10 @@ ABI_SYMBOLS = [
     "blomgpu_init", "blomgpu_finalize", "blomgpu_last_error", "blomgpu_parity_build",
     "blomgpu_comm_unique_id", "blomgpu_comm_init",
     "blomgpu_register", "blomgpu_register_int", "blomgpu_upload", "blomgpu_download",
-    "blomgpu_upload_all", "blomgpu_download_all", "blomgpu_download_async", "blomgpu_sync", "blomgpu_device_ptr",
+    "blomgpu_upload_all", "blomgpu_download_all", "blomgpu_download_async", "blomgpu_download_levels_async",
+    "blomgpu_upload_async", "blomgpu_wait_upload", "blomgpu_sync", "blomgpu_device_ptr",
     "blomgpu_set_option", "blomgpu_set_scalar", "blomgpu_get_scalar",
-    "blomgpu_xctilr", "blomgpu_xcsum", "blomgpu_xcmax", "blomgpu_xcmin", "blomgpu_chksum",
+    "blomgpu_xctilr", "blomgpu_xcsum", "blomgpu_xcmax", "blomgpu_xcmin", "blomgpu_chksum", "blomgpu_chksum_at",
     "blomgpu_bigrid", "blomgpu_nreg", "blomgpu_init_cppm", "blomgpu_inieos",
     "blomgpu_numerical_bounds", "blomgpu_init_fluxes",
     "blomgpu_tmsmt1", "blomgpu_difest_halos", "blomgpu_eddtra", "blomgpu_advect", "blomgpu_pbcor1", "blomgpu_diffus",
@@ -131,6 +132,16 @@ class BlomGpu:
         self._ck(self.lib.blomgpu_download_async(name.encode()))
         return self.arrays[name]
 
+    def download_levels_async(self, name, koff, nlev):
+        self._ck(self.lib.blomgpu_download_levels_async(name.encode(), koff, nlev))
+
+    def upload_async(self, name, koff, nlev):
+        """H2D of levels koff..koff+nlev-1 on the upload stream; wait_upload(name) before the first reader."""
+        self._ck(self.lib.blomgpu_upload_async(name.encode(), koff, nlev))
+
+    def wait_upload(self, name):
+        self._ck(self.lib.blomgpu_wait_upload(name.encode()))
+
     def upload_all(self):
         self._ck(self.lib.blomgpu_upload_all())
 
@@ -194,6 +205,11 @@ class BlomGpu:
     def chksum(self, name, kcsd, itype):
         out = C.c_uint32()
         self._ck(self.lib.blomgpu_chksum(name.encode(), kcsd, itype, C.byref(out)))
+        return out.value
+
+    def chksum_at(self, name, koff, kcsd, itype):
+        out = C.c_uint32()
+        self._ck(self.lib.blomgpu_chksum_at(name.encode(), koff, kcsd, itype, C.byref(out)))
         return out.value
 
     # -- setup --------------------------------------------------------------------

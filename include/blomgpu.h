@@ -59,6 +59,15 @@ int blomgpu_download_all(void);
  * is valid after the next blomgpu_sync().  Used for fields a later out-of-scope CPU routine needs
  * (u,v are final after momtum, phy/mod_blom_step.F90:169-227). */
 int blomgpu_download_async(const char* name);
+/* the same for levels koff..koff+nlev-1 (1-based) of a field: e.g. the new time level of dp/temp/saln is final
+ * after pbcor2 and the mid level after tmsmt2 (phy/mod_pbcor.F90:416, phy/mod_tmsmt.F90:281) */
+int blomgpu_download_levels_async(const char* name, int koff, int nlev);
+/* host -> device of levels koff..koff+nlev-1 on a third stream: starts when everything enqueued so far has
+ * finished and overlaps the routines called next.  Before the first routine that reads the field call
+ * blomgpu_wait_upload(name) (the library stream then waits for the copy, the host does not).  Lets the host
+ * hand over u,v while tmsmt1..pgforc already run (their first reader is momtum). */
+int blomgpu_upload_async(const char* name, int koff, int nlev);
+int blomgpu_wait_upload(const char* name);
 int blomgpu_sync(void);
 /* raw device pointer of a registered/owned array (for zero-copy interop) */
 int blomgpu_device_ptr(const char* name, void** dptr, int* nlev);
@@ -81,6 +90,9 @@ int blomgpu_xcmax(const char* name, int lev, const char* mask, double* out);
 int blomgpu_xcmin(const char* name, int lev, const char* mask, double* out);
 /* chksum(a,kcsd,itype,text) -> crc  phy/mod_checksum.F90:41-74, phy/mod_xc.F90:2195,4164 */
 int blomgpu_chksum(const char* name, int kcsd, int itype, uint32_t* crc);
+/* the same with the Fortran actual argument a(1-nbdy,1-nbdy,koff), e.g. chksum(utflld(1-nbdy,1-nbdy,k1m),kk,...)
+ * (phy/mod_diffus.F90:175) */
+int blomgpu_chksum_at(const char* name, int koff, int kcsd, int itype, uint32_t* crc);
 
 /* ---- setup ------------------------------------------------------------- */
 /* bigrid(depth): masks ip,iu,iv,iq (+nreg resolution)  phy/mod_bigrid.F90:44-317 */

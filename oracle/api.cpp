@@ -113,6 +113,9 @@ int oracle_xcsum(const char* name, int lev, const char* mask, double* out) {
 int oracle_xccrc(const char* name, int ld, const char* mask, uint32_t* out) {
   GUARD(*out = orc::xccrc(orc::O().a3(name), ld, orc::O().i2(mask)))
 }
+int oracle_xccrc_at(const char* name, int koff, int ld, const char* mask, uint32_t* out) {
+  GUARD(*out = orc::xccrc(orc::O().a3(name).from(koff), ld, orc::O().i2(mask)))
+}
 uint32_t oracle_crc32(const void* p, long n, uint32_t init) { return orc::crc32_bytes(p, (size_t)n, init); }
 int oracle_bigrid(const char* depth) { GUARD(orc::bigrid(orc::O().a2(depth))) }
 

@@ -146,6 +146,13 @@ class Oracle:
         self._ck(self.lib.oracle_xccrc(name.encode(), kcsd, mask.encode(), C.byref(out)))
         return out.value
 
+    def chksum_at(self, name, koff, kcsd, itype):
+        """chksum(a(1-nbdy,1-nbdy,koff), kcsd, itype, text), phy/mod_checksum.F90:41-74"""
+        mask = {1: "ip", 11: "ip", 2: "iq", 12: "iq", 3: "iu", 13: "iu", 4: "iv", 14: "iv"}[itype]
+        out = C.c_uint32()
+        self._ck(self.lib.oracle_xccrc_at(name.encode(), koff, kcsd, mask.encode(), C.byref(out)))
+        return out.value
+
     def crc32(self, data: bytes, init=0):
         return self.lib.oracle_crc32(data, C.c_long(len(data)), C.c_uint32(init))
 

@@ -51,23 +51,30 @@ def test_chained_steps(cfg, optset):
         g.finalize()
 
 
-def test_early_download_matches_plain_download():
-    """blomgpu_download_async (u,v copied back on the copy stream while barotp/pbcor2/tmsmt2 run)
-    must hand the host exactly what a plain download after the step does."""
+@pytest.mark.parametrize("ntr", [0, 1])
+def test_pipelined_step_matches_plain_step(ntr):
+    """HotPath.step_pipelined (asynchronous upload of the new time level, u,v halo refresh moved to its
+    first reader, downloads started after each field's last writer) must leave exactly the host arrays
+    that upload / step / download leave, and so must the early-download variant of step()."""
     from blom_b200.driver import HotPath, IO_FIELDS
     res = []
-    for early in (False, True):
-        hp = HotPath("tiny2", ntr=1, nstep=1, parity=True)
+    for mode in ("plain", "early", "pipelined"):
+        hp = HotPath("tiny2", ntr=ntr, nstep=1, parity=True)
         try:
-            for _ in range(2):
-                hp.upload_inputs()
-                hp.advance(early_download=early)
-                hp.download_outputs()
+            for _ in range(3):
+                if mode == "pipelined":
+                    hp.step_pipelined()
+                    hp.set_step(hp.nstep + 1)
+                else:
+                    hp.upload_inputs()
+                    hp.advance(early_download=(mode == "early"))
+                    hp.download_outputs()
             res.append({nm: hp.arrays[nm].copy() for nm in IO_FIELDS if nm in hp.arrays})
         finally:
             hp.finalize()
-    for nm in res[0]:
-        assert np.array_equal(res[0][nm], res[1][nm]), nm
+    for other in res[1:]:
+        for nm in res[0]:
+            assert np.array_equal(res[0][nm], other[nm]), nm
     assert np.abs(res[0]["u"]).max() > 0
 
 
@@ -82,7 +89,9 @@ def test_fuk95_geostrophic_adjustment_on_gpu():
     o = c.new_oracle(); g = c.new_gpu(parity=True)
     try:
         kk = c.dims[2]
-        routines, _ = prepare_step(c, (o, g))
+        # layer diffusion inside diffus: with ltedtp='neutral' the diffused scalars would only reach T,S
+        # through the out-of-scope ALE step, and the undiffused front overshoots u0
+        routines, _ = prepare_step(c, (o, g), {"ltedtp": "layer"})
         for nstep in range(1, 161):
             lv = time_levels(nstep, kk)
             for b in (o, g):

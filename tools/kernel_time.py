@@ -1,6 +1,7 @@
 """Development timing: per-kernel device time (event pair per launch) of the hot path, ms per step.
 usage: python tools/kernel_time.py [config] [steps]
   BLOM_OPTIONS=key=value,...        option set of the main measurement
+  BLOM_ROUTINES=r1,r2,...           restrict the step to these routines (e.g. ndiff)
   BLOM_AB="k=v,k=v;k=v"             further option sets measured afterwards on the same resident state
                                     (each set is applied on top of the previous ones)"""
 import os, sys, time, json
@@ -10,7 +11,8 @@ from blom_b200.driver import HotPath
 cfg = sys.argv[1] if len(sys.argv) > 1 else "tnx0.25v4"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 t0 = time.time()
-hp = HotPath(cfg, ntr=0, nstep=1)
+rts = [r for r in os.environ.get("BLOM_ROUTINES", "").split(",") if r] or None
+hp = HotPath(cfg, ntr=0, nstep=1, routines=rts)
 g = hp.gpu
 
 
