@@ -607,34 +607,10 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     }
     return cg_;
   };
-  // L2 residency of the subcycled state.  The six levels of pb_t/ubflx_t/vbflx_t are read and written in every
-  // phase of every substep (15 of the 53 words per point and substep) while the coefficient arrays stream
-  // through once per phase and would evict them; when the 2-D working set exceeds the L2 (tnx0.25v4 on one
-  // GPU: 704 MB against 126 MB) the state is pinned with a persisting access-policy window on the library
-  // stream for the duration of the subcycle (option barotp_l2persist=0 switches it off).
-  bool l2_window = false;
-  if (persistent && c.option("barotp_l2persist", "1") != "0") {
-    int max_persist = 0, max_window = 0, l2_bytes = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
-    cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, c.device);
-    const size_t state_bytes = sizeof(double) * 6 * (size_t)L;
-    const size_t working_set = sizeof(double) * 53 * (size_t)L;
-    if (max_persist > 0 && max_window > 0 && working_set > (size_t)l2_bytes) {
-      // the carve-out is taken away from every other kernel's L2 (the level-parallel kernels of this path rely on
-      // L2 for their 2-D operands), so it only exists for the duration of the subcycle
-      const size_t carve = std::min<size_t>((size_t)max_persist, (size_t)(0.7 * l2_bytes));
-      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
-      cudaStreamAttrValue attr{};
-      attr.accessPolicyWindow.base_ptr = bt_state;
-      attr.accessPolicyWindow.num_bytes = std::min(state_bytes, (size_t)max_window);
-      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
-      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      l2_window = cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
-      if (!l2_window) cudaGetLastError();
-    }
-  }
+  // (Round 2 negative result: pinning the six levels of the subcycled state in L2 with a persisting
+  // access-policy window - they carry 15 of the 53 words per point and substep - changed nothing at tnx0.25v4,
+  // 18.26 ms with the window against 18.35 without, gpurun_out/r2d_kt_a/b.json, while a carve-out left in place
+  // halved the speed of every other kernel of the step.  Removed.)
   unsigned* bar_ctr = reinterpret_cast<unsigned*>(c.owned("barotp_barrier", 1));
   int lll0 = 1, ml = 1, nl = 2;
   double woa = 0, wob = 0, wna = 0, wnb = 0;
@@ -710,13 +686,6 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     lll0 = lll0 + lstep / 2;
     set_levels(ml, nl);
     LAUNCH(bt_harvest, gint, 128, 0, g, P, H, nb, m, n, ml, nl);
-  }
-  if (l2_window) {   // back to the default policy for the kernels that follow; drop the persisting lines
-    cudaStreamAttrValue attr{};
-    attr.accessPolicyWindow.num_bytes = 0;
-    cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-    cudaCtxResetPersistingL2Cache();
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
   }
 }
 

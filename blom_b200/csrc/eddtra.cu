@@ -96,7 +96,13 @@ __global__ void eddtra_mldens(Geom g, eos::Coef ec, int nn, const int* __restric
 // recomputed from their (cached) inputs where they are needed — the same expressions on the same
 // operands, so the values are identical to the reference's stored work arrays, at a fifth of the
 // local-memory traffic.
-template <int DIR, int MINB>
+// SMEM (development switch eddtra_mfl=smem): the limited interface fluxes mfl(1..kmax+1) of the block's 128
+// columns in shared memory, interleaved by column (mfl(k) of thread t at [k*128 + t], conflict-free), instead of
+// in a thread-local array.  The limiter sweeps index the array dynamically, so the local array sits in local
+// memory and at 2048 resident threads per SM its 528 bytes per thread spill through L1/L2 into HBM (round 1:
+// 32 GB of DRAM traffic for 14.8 GB of algorithmic bytes) - but the shared-memory form measured 1.5x SLOWER
+// (see eddtra_dev), so the local array stays the default.
+template <int DIR, int MINB, bool SMEM>
 __global__ void __launch_bounds__(128, MINB)
 eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int* __restrict__ mask,
               const double* __restrict__ p, const double* __restrict__ dp, const double* __restrict__ dpf,
@@ -118,7 +124,9 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
   const int kk = g.kdm;
   const double ffac = .0625, fface = .99 * ffac, eps = 1.e-14, c5_21 = 5. / 21.;
 
-  double mfl[KM + 2];
+  extern __shared__ double mfl_sm[];
+  double mfl_loc[SMEM ? 1 : KM + 2];
+#define mfl(k) (*(SMEM ? &mfl_sm[(k) * 128 + threadIdx.x] : &mfl_loc[SMEM ? 0 : (k)]))
 
   const double hml = .5 * (hml_tfbnd[xm] + hml_tfbnd[x]);
   // depth-invariant submesoscale transport component (:1130-1185)
@@ -188,7 +196,7 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
     for (int k = 1; k <= kmax + 1; ++k) {
       double gm, sm;
       gm_sm(k, pk, gm, sm);
-      mfl[k] = gm + sm;
+      mfl(k) = gm + sm;
       if (k <= kmax) pk = pk + dpf[x + (long)(k + nn - 1) * lev];
     }
   }
@@ -206,27 +214,27 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
     kdir = -kdir;
     const int k0 = (1 + kdir + (1 - kdir) * kmax) / 2;
     for (int s = 0, k = k0; s < kmax; ++s, k += kdir) {
-      const double lo = mfl[k], hi = mfl[k + 1];
+      const double lo = mfl(k), hi = mfl(k + 1);
       if (fabs(hi - lo) > fmax(mfleps, eps * fabs(hi + lo))) {
         const double dlm = dl_m(k), dlp = dl_p(k);
         if (hi - lo > ffac * fmax(epsilp, dlm) * am) {
           const double q = fface * dlm * am;
           if (hi > -lo) {
-            if (lo > -.5 * q) mfl[k + 1] = lo + q;
-            else { mfl[k + 1] = .5 * q; mfl[k] = -mfl[k + 1]; }
+            if (lo > -.5 * q) mfl(k + 1) = lo + q;
+            else { mfl(k + 1) = .5 * q; mfl(k) = -mfl(k + 1); }
           } else {
-            if (hi < .5 * q) mfl[k] = hi - q;
-            else { mfl[k] = -.5 * q; mfl[k + 1] = -mfl[k]; }
+            if (hi < .5 * q) mfl(k) = hi - q;
+            else { mfl(k) = -.5 * q; mfl(k + 1) = -mfl(k); }
           }
           changed = true;
         } else if (hi - lo < -ffac * fmax(epsilp, dlp) * ap) {
           const double q = fface * dlp * ap;
           if (hi < -lo) {
-            if (lo < .5 * q) mfl[k + 1] = lo - q;
-            else { mfl[k + 1] = -.5 * q; mfl[k] = -mfl[k + 1]; }
+            if (lo < .5 * q) mfl(k + 1) = lo - q;
+            else { mfl(k + 1) = -.5 * q; mfl(k) = -mfl(k + 1); }
           } else {
-            if (hi > -.5 * q) mfl[k] = hi + q;
-            else { mfl[k] = .5 * q; mfl[k + 1] = -mfl[k]; }
+            if (hi > -.5 * q) mfl(k) = hi + q;
+            else { mfl(k) = .5 * q; mfl(k + 1) = -mfl(k); }
           }
           changed = true;
         }
@@ -237,7 +245,7 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
   // split the limited total back into GM and submesoscale parts (:1398-1436), one interface at a time
   auto split = [&](int k, double puv_k, double& f, double& gm, double& sm) {
     gm_sm(k, puv_k, gm, sm);
-    f = mfl[k];
+    f = mfl(k);
     if (fabs(f) < mfleps) {
       f = 0.; gm = 0.; sm = 0.;
     } else if (f > 0.) {
@@ -279,6 +287,7 @@ eddtra_column(Geom g, MlParams P, int n, int mm, int nn, double delt1, const int
     tfltd[xk] = fgm * qt; tflsm[xk] = fsm * qt;
     sfltd[xk] = fgm * qs; sflsm[xk] = fsm * qs;
   }
+#undef mfl
 }
 
 }  // namespace
@@ -332,17 +341,36 @@ void eddtra_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     halo_update(util1, 1, 1, 1, halo_ps);
   }
   int* err = c.error_flag();
-  OCC_DISPATCH3("eddtra_minblk", 16, 9, 12, 16,
-  LAUNCH_NAMED("eddtra_column<u>", (eddtra_column<0, OCC>), grid2, 128, 0, g, P, n, mm, nn, delt1, c.idev("iu"),
-               c.dev("p"), c.dev("dp"), c.dev("dpu"), c.dev("temp"), c.dev("saln"), c.dev("difint"),
-               c.dev("nslpx"), c.dev("pbu"), c.dev("scu2"), c.dev("scuy"), c.dev("scp2"), coriop, hbl_tf, wpup_tf,
-               hml_tfbnd, util1, c.dev("umfltd"), c.dev("umflsm"), c.dev("utfltd"), c.dev("utflsm"),
-               c.dev("usfltd"), c.dev("usflsm"), err);
-  LAUNCH_NAMED("eddtra_column<v>", (eddtra_column<1, OCC>), grid2, 128, 0, g, P, n, mm, nn, delt1, c.idev("iv"),
-               c.dev("p"), c.dev("dp"), c.dev("dpv"), c.dev("temp"), c.dev("saln"), c.dev("difint"),
-               c.dev("nslpy"), c.dev("pbv"), c.dev("scv2"), c.dev("scvx"), c.dev("scp2"), coriop, hbl_tf, wpup_tf,
-               hml_tfbnd, util1, c.dev("vmfltd"), c.dev("vmflsm"), c.dev("vtfltd"), c.dev("vtflsm"),
-               c.dev("vsfltd"), c.dev("vsflsm"), err));
+  // eddtra_mfl = local (default) | smem: where the limiter's interface-flux column lives (see eddtra_column).
+  // Measured at tnx0.25v4 (round 2, gpurun_out/r2d_kt_a.json): shared memory 7.1 + 7.9 ms (u + v), local array
+  // 4.4 + 5.4 ms - the 56 KB per block leave 16 warps per SM against 64, and the kernel is latency-bound on its
+  // global operands, not on the flux column.  Kept as a switch, off.
+  const bool mfl_smem = c.option("eddtra_mfl", "local") == "smem";
+  const size_t smem = mfl_smem ? (size_t)(g.kdm + 2) * 128 * sizeof(double) : 0;
+#define EDDTRA_LAUNCH(SM_, OCC_)                                                                                       \
+  do {                                                                                                                 \
+    if (SM_) {                                                                                                         \
+      static bool attr_set = false;                                                                                    \
+      if (!attr_set) {                                                                                                 \
+        CUDA_CHECK(cudaFuncSetAttribute(eddtra_column<0, OCC_, SM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 128 * 8)); \
+        CUDA_CHECK(cudaFuncSetAttribute(eddtra_column<1, OCC_, SM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 128 * 8)); \
+        attr_set = true;                                                                                               \
+      }                                                                                                                \
+    }                                                                                                                  \
+    LAUNCH_NAMED("eddtra_column<u>", (eddtra_column<0, OCC_, SM_>), grid2, 128, smem, g, P, n, mm, nn, delt1, c.idev("iu"), \
+                 c.dev("p"), c.dev("dp"), c.dev("dpu"), c.dev("temp"), c.dev("saln"), c.dev("difint"),                  \
+                 c.dev("nslpx"), c.dev("pbu"), c.dev("scu2"), c.dev("scuy"), c.dev("scp2"), coriop, hbl_tf, wpup_tf,    \
+                 hml_tfbnd, util1, c.dev("umfltd"), c.dev("umflsm"), c.dev("utfltd"), c.dev("utflsm"),                  \
+                 c.dev("usfltd"), c.dev("usflsm"), err);                                                               \
+    LAUNCH_NAMED("eddtra_column<v>", (eddtra_column<1, OCC_, SM_>), grid2, 128, smem, g, P, n, mm, nn, delt1, c.idev("iv"), \
+                 c.dev("p"), c.dev("dp"), c.dev("dpv"), c.dev("temp"), c.dev("saln"), c.dev("difint"),                  \
+                 c.dev("nslpy"), c.dev("pbv"), c.dev("scv2"), c.dev("scvx"), c.dev("scp2"), coriop, hbl_tf, wpup_tf,    \
+                 hml_tfbnd, util1, c.dev("vmfltd"), c.dev("vmflsm"), c.dev("vtfltd"), c.dev("vtflsm"),                  \
+                 c.dev("vsfltd"), c.dev("vsflsm"), err);                                                               \
+  } while (0)
+  if (mfl_smem) EDDTRA_LAUNCH(true, 4);      // 4 blocks of 56 KB per SM; the register budget is no longer the limit
+  else { OCC_DISPATCH3("eddtra_minblk", 16, 9, 12, 16, EDDTRA_LAUNCH(false, OCC)); }
+#undef EDDTRA_LAUNCH
   c.error_source = "(eddtra_ale) 1: no convergence, 2: flux exceeds +ffac*mass, 3: flux exceeds -ffac*mass";
 }
 

@@ -30,6 +30,8 @@ CONFIGS = {
     "channel": (208, 512, 53, 1, 1800.0, 36.0),    # bld/channel/patch.input.1
     "tnx1v4": (360, 385, 53, 2, 3200.0, 64.0),     # namelist_definition_blom.xml:179-201
     "tnx0.25v4": (1440, 1153, 53, 2, 900.0, 15.0),
+    "tnx0.25v4_band": (1440, 64, 53, 1, 900.0, 15.0),   # a closed 64-row band at full zonal width (parity at the tile widths
+                                                        # the 0.25 degree kernels run with; also the CPU-baseline sample)
     "tnx0.125v4": (2880, 2165, 53, 2, 300.0, 6.0),
 }
 

@@ -7,7 +7,7 @@ import pytest
 
 from blom_b200.driver import run_step
 from blom_b200.lib import time_levels
-from util import Case, interior, max_rel_err, prepare_step
+from util import Case, compare_all, interior, max_rel_err, prepare_step
 
 pytestmark = pytest.mark.gpu
 
@@ -17,18 +17,6 @@ SKIP = {"depths"}
 # the reference's option set for the hybrid coordinate (neutral diffusion through ndiff, dluc, bod23) and
 # the layer-diffusion / uc / fox08 set (the isopycnic defaults, which exercise diffus' flux branch)
 OPTION_SETS = {"reference": None, "layer": {"ltedtp": "layer", "bmcmth": "uc", "mlrmth": "fox08"}}
-
-
-def compare_all(g, o, what, tol=1e-10):
-    g.download_all()
-    bad = []
-    for nm, a in g.arrays.items():
-        if nm in SKIP or a.dtype != np.float64:
-            continue
-        err = max_rel_err(interior(a), interior(o.arrays[nm]))
-        if not err <= tol:
-            bad.append((nm, err))
-    assert not bad, (what, sorted(bad, key=lambda t: -t[1])[:6])
 
 
 @pytest.mark.parametrize("optset", ["reference", "layer"])

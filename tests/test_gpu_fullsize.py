@@ -1,5 +1,12 @@
-"""GPU checks at BASELINE.json's full grid sizes (channel 208x512x53, tnx1v4 360x385x53) through
-size-independent properties — the oracle is too slow to be the checker here:
+"""GPU checks at BASELINE.json's full grid sizes (channel 208x512x53, tnx1v4 360x385x53).
+
+test_one_step_against_oracle_full_size compares the CUDA path with the oracle on the whole channel and tnx1v4
+grids and on a closed 1440 x 64 x 53 band of tnx0.25v4 (the zonal width the 0.25 degree kernels tile): one
+baroclinic step under the reference's option set, every registered array after every routine, parity
+build, 1e-10 of the field's max-norm.  This is where the tile-edge and level-chunk logic of the tiled kernels
+(cppm_flux, pbcor level chunks, the 768x2 barotropic shape, ndiff) meets the checker at production widths.
+
+The other tests use size-independent properties:
   * CPPM transport conserves the global mass and heat/salt inventories to round-off
     (closed/periodic channel; tripolar grid with the whole-row fold swap, cppm_fold_fix=1),
   * a uniform passive tracer stays uniform (compatibility of thickness and tracer fluxes),
@@ -14,7 +21,7 @@ import pytest
 
 from blom_b200.driver import HotPath
 from blom_b200.lib import HALO_PS
-from util import interior
+from util import Case, compare_all, interior, prepare_step
 
 pytestmark = pytest.mark.gpu
 
@@ -102,3 +109,18 @@ def test_pbcor_column_total_full_size():
         assert np.abs(col - pbp)[wet].max() <= 1e-13 * pbp.max()
     finally:
         hp.finalize()
+
+
+@pytest.mark.parametrize("cfg", ["channel", "tnx1v4", "tnx0.25v4_band"])
+def test_one_step_against_oracle_full_size(cfg):
+    from blom_b200.driver import run_step
+    c = Case(cfg, ntr=0, nstep=1)
+    o = c.new_oracle(); g = c.new_gpu(parity=True)
+    try:
+        routines, _ = prepare_step(c, (o, g))
+        for r in routines:
+            run_step(o, [r], c.levels); run_step(g, [r], c.levels)
+            compare_all(g, o, (cfg, r))
+        assert np.isfinite(g.arrays["dp"]).all() and np.abs(interior(g.arrays["u"])).max() > 0
+    finally:
+        g.finalize()

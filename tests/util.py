@@ -78,6 +78,20 @@ def prepare_step(c, backends, options=None):
     return routines, opts
 
 
+def compare_all(g, o, what, tol=1e-10, skip=("depths",)):
+    """Download every registered array of the CUDA backend and compare its interior with the oracle's
+    (max-norm relative error <= tol)."""
+    g.download_all()
+    bad = []
+    for nm, a in g.arrays.items():
+        if nm in skip or a.dtype != np.float64:
+            continue
+        err = max_rel_err(interior(a), interior(o.arrays[nm]))
+        if not err <= tol:
+            bad.append((nm, err))
+    assert not bad, (what, sorted(bad, key=lambda t: -t[1])[:6])
+
+
 def interior(a, nb=4, halo=0):
     """View of the interior (+`halo` rings) of a (nlev, ldj, ldi) array."""
     s = nb - halo
