@@ -52,9 +52,16 @@ __device__ __forceinline__ double eos_drhods(double p, double th, double s) {
 // one memory sector.  The first search evaluates the density difference between two interfaces at every step
 // and its lanes sit at different layers, so four separate level-strided arrays cost four sectors per lane
 // where the record costs one.  Layout: record ((k-1)*2+is-1) of cell x at rec[(((k-1)*2+is-1)*lev + x)*4].
+// Non-binding L1 prefetch.  Every thread walks its two columns strictly downwards, so the addresses it will
+// load a few iterations later are known; the searches are chains of dependent loads (ncu: 57 % of the stall
+// samples on the long scoreboard at 13 resident warps per SM), and a prefetch issued a few iterations ahead
+// turns the later demand load into an L1 hit.  Switch: template parameter PF (option ndiff_prefetch).
+__device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 struct NdArgs {
   const double *p_src, *tsd, *tpc, *rec, *p_dst, *snp;
   const int *ksmx, *kdmx, *mask;
+  const int* faces; int nfaces;   // offsets ix2(i,j) of the wet faces of this direction
   const double *dpml, *difiso;
   const double* tlev[NTMAX];   // scalar nt at time level nn, level 1
   const double *sca, *scbi;    // scuy,scuxi | scvx,scvyi
@@ -202,13 +209,15 @@ struct SideAcc {
 };
 
 // ndiff_flx (:160-953) for the face between cell M (i-1|j-1) and cell P (i,j)
-template <int DIR, int NT, int MINB>
+template <int DIR, int NT, int MINB, bool PF>
 __global__ void __launch_bounds__(128, MINB)
 ndiff_face(Geom g, NdArgs A) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
-  if (i > g.ii + (DIR == 0 ? 1 : 0)) return;
-  const long x = ix2(g, i, j);
-  if (A.mask[x] != 1) return;
+  // wet faces only: thread t owns face A.faces[t] (linear (i,j) offset of the face's plus-side cell).  A thread
+  // of a land face would idle for the whole life of its warp - the kernel is issue- and latency-bound, so the
+  // compacted list (built once, the masks are static) removes that share of the warps outright.
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.nfaces) return;
+  const long x = A.faces[t];
   const long xm = x - (DIR == 0 ? 1 : g.ldi), lev = g.lev;
   const int kk = g.kdm, T = NT > 0 ? NT : A.T, mm = A.mm;
   const Col M{A.p_src + xm, A.tsd + xm, A.tpc + xm, A.rec + xm * 4, A.p_dst + xm, A.snp + xm, lev, kk};
@@ -336,6 +345,12 @@ ndiff_face(Geom g, NdArgs A) {
           is = 1;
         }
         const long o = side ? x : xm;
+        if (PF) {   // records and source interfaces this side reaches 3 and 4 advances from now
+          const int rn = min((ks - 1) * 2 + is - 1 + 3, 2 * kk - 2);
+          pf_l1(A.rec + (o + (long)rn * lev) * 4);
+          pf_l1(A.rec + (o + (long)(rn + 1) * lev) * 4);
+          pf_l1(A.p_src + o + (long)min(ks + 2, kk) * lev);
+        }
         const Rec r = rec_at(o, is, ks);
         if (side) { rp = r; is_p = is; ks_p = ks; } else { rm = r; is_m = is; ks_m = ks; }
         drho_curr = drho_at();
@@ -431,11 +446,28 @@ ndiff_face(Geom g, NdArgs A) {
       const double* b5 = c.tpc + (long)(((nt - 1) * kk + k - 1) * 5) * lev;
       o[0] = b5[0]; o[1] = b5[lev]; o[2] = b5[2 * lev]; o[3] = b5[3 * lev]; o[4] = b5[4 * lev];
     };
+    // what the next source layer of a column will need: its polynomial coefficients, interface values,
+    // diffusivity and layer means (read when ks advances, several neutral interfaces from now)
+    auto pf_layer = [&](long o, int k) {
+      if (!PF || k > kk) return;
+#pragma unroll
+      for (int nt = 1; nt <= NTC; ++nt)
+        if (nt <= T) {
+          const double* b5 = A.tpc + o + (long)(((nt - 1) * kk + k - 1) * 5) * lev;
+          pf_l1(b5); pf_l1(b5 + lev); pf_l1(b5 + 2 * lev); pf_l1(b5 + 3 * lev); pf_l1(b5 + 4 * lev);
+          pf_l1(A.tsd + o + (long)(((nt - 1) * kk + k - 1) * 2) * lev);
+          pf_l1(A.tsd + o + (long)(((nt - 1) * kk + k - 1) * 2 + 1) * lev);
+          pf_l1(A.tlev[nt - 1] + o + (long)(k - 1) * lev);
+        }
+      pf_l1(A.difiso + o + (long)(k - 1) * lev);
+      pf_l1(A.p_src + o + (long)k * lev);
+    };
     auto need_m = [&]() {
       if (CACHE && kc_m != ks_m) {
 #pragma unroll
         for (int nt = 1; nt <= NTC; ++nt) coef(M, ks_m, nt, cfm[CACHE ? nt - 1 : 0]);
         kc_m = ks_m;
+        pf_layer(xm, ks_m + 1);
       }
     };
     auto need_p = [&]() {
@@ -443,6 +475,7 @@ ndiff_face(Geom g, NdArgs A) {
 #pragma unroll
         for (int nt = 1; nt <= NTC; ++nt) coef(P, ks_p, nt, cfp[CACHE ? nt - 1 : 0]);
         kc_p = ks_p;
+        pf_layer(x, ks_p + 1);
       }
     };
     auto pe = [&](const double (&c)[5], double xx) { return (((c[4] * xx + c[3]) * xx + c[2]) * xx + c[1]) * xx + c[0]; };
@@ -467,6 +500,18 @@ ndiff_face(Geom g, NdArgs A) {
     int kuv = 1;
     const double* puvx = A.puv + x;
     auto puv = [&](int k) { return puvx[(long)(k - 1) * lev]; };
+    // The face fluxes of a neutral sublayer are binned on the face's layers (:870-905).  A layer collects
+    // the contributions of several sublayers one after the other; its four running sums (tflld, sflld, tflx,
+    // sflx of layer kuv_acc) are kept in registers from the first contribution until the binning moves on
+    // to the next layer: the additions and their order are the reference's, each array element is read
+    // once and written once instead of once per contribution.
+    int kuv_acc = 0;
+    double a_tflld = 0., a_sflld = 0., a_tflx = 0., a_sflx = 0., pk_c = 0., pk1_c = 0.;
+    auto flush_layer = [&]() {
+      if (kuv_acc == 0) return;
+      const long o = x + (long)(kuv_acc + mm - 1) * lev;
+      A.tflld[o] = a_tflld; A.sflld[o] = a_sflld; A.tflx[o] = a_tflx; A.sflx[o] = a_sflx;
+    };
 
     for (;;) {
       // advance to the next source interface of the minus and/or the plus column (mirrored blocks of the
@@ -522,10 +567,12 @@ ndiff_face(Geom g, NdArgs A) {
       if (advance_dst_m) {
         kd_m = kd_m + 1;
         if (kd_m > kdmx_m) break;
+        if (PF) { pf_l1(A.snp + xm + (long)min(kd_m + 2, kk) * lev); pf_l1(A.p_dst + xm + (long)min(kd_m + 2, kk) * lev); }
       }
       if (advance_dst_p) {
         kd_p = kd_p + 1;
         if (kd_p > kdmx_p) break;
+        if (PF) { pf_l1(A.snp + x + (long)min(kd_p + 2, kk) * lev); pf_l1(A.p_dst + x + (long)min(kd_p + 2, kk) * lev); }
       }
       const double psm1 = M.psd(1, ks_m), psm2 = M.psd(2, ks_m), psp1 = P.psd(1, ks_p), psp2 = P.psd(2, ks_p);
       {
@@ -726,15 +773,21 @@ ndiff_face(Geom g, NdArgs A) {
             const double p_ni_lo = .5 * (p_cur_m + p_cur_p);
             const double dp_ni_i = 1. / fmax(epsilp, p_ni_lo - p_ni_up);
             while (kuv <= kk) {
-              const long o = x + (long)(kuv + mm - 1) * lev;
-              const double pk = puv(kuv), pk1 = puv(kuv + 1);
+              if (kuv_acc != kuv) {   // bring layer kuv's four sums into registers (the previous layer's go out)
+                flush_layer();
+                const long o = x + (long)(kuv + mm - 1) * lev;
+                a_tflld = A.tflld[o]; a_sflld = A.sflld[o]; a_tflx = A.tflx[o]; a_sflx = A.sflx[o];
+                pk_c = puv(kuv); pk1_c = puv(kuv + 1);
+                kuv_acc = kuv;
+              }
+              const double pk = pk_c, pk1 = pk1_c;
               const bool below = pk1 < p_ni_lo;
               const double mlfrac = below ? fmax(0., pk1 - fmax(p_ni_up, pk)) * dp_ni_i
                                           : (p_ni_lo - fmax(p_ni_up, pk)) * dp_ni_i;
-              A.tflld[o] = A.tflld[o] + tflx * mlfrac;
-              A.sflld[o] = A.sflld[o] + sflx * mlfrac;
-              A.tflx[o] = A.tflx[o] + tflx * mlfrac;
-              A.sflx[o] = A.sflx[o] + sflx * mlfrac;
+              a_tflld = a_tflld + tflx * mlfrac;
+              a_sflld = a_sflld + sflx * mlfrac;
+              a_tflx = a_tflx + tflx * mlfrac;
+              a_sflx = a_sflx + sflx * mlfrac;
               if (!below) break;
               kuv = kuv + 1;
             }
@@ -747,6 +800,7 @@ ndiff_face(Geom g, NdArgs A) {
         for (int q2 = 0; q2 < NTC; ++q2) { t_prev_m[q2] = t_cur_m[q2]; t_prev_p[q2] = t_cur_p[q2]; }
       }
     }
+    flush_layer();
   }
   accm.finish();
   accp.finish();
@@ -824,13 +878,43 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   V.tflld = c.dev("vtflld"); V.sflld = c.dev("vsflld"); V.tflx = c.dev("vtflx"); V.sflx = c.dev("vsflx");
   V.nslp = c.dev("nslpy"); V.cvm = vcm; V.cvp = vcp;
 
-  const dim3 gu(cdiv(g.ii + 1, 128), g.jj), gv(cdiv(g.ii, 128), g.jj + 1);
-  // resident blocks per SM (register budget 65536/(128*MINB)): development switch ndiff_minblk = 4 | 5 | 6
+  // compacted lists of the wet u faces (1..ii+1 x 1..jj) and v faces (1..ii x 1..jj+1); the masks are static
+  // after bigrid, so the lists are built once per tile
+  int* list_u = c.owned_int("_nd_faces_u", 1);
+  int* list_v = c.owned_int("_nd_faces_v", 1);
+  if (!c.sc.count("_nd_nfaces_u")) {   // (bigrid erases the counts when the masks are rebuilt)
+    std::vector<int> hu(g.lev), hv(g.lev), lu, lv;
+    CUDA_CHECK(cudaMemcpyAsync(hu.data(), c.idev("iu"), sizeof(int) * g.lev, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaMemcpyAsync(hv.data(), c.idev("iv"), sizeof(int) * g.lev, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    for (int j = 1; j <= g.jj + 1; ++j)
+      for (int i = 1; i <= g.ii + 1; ++i) {
+        const long x = ix2(g, i, j);
+        if (j <= g.jj && hu[x] == 1) lu.push_back((int)x);
+        if (i <= g.ii && hv[x] == 1) lv.push_back((int)x);
+      }
+    if (!lu.empty()) CUDA_CHECK(cudaMemcpyAsync(list_u, lu.data(), sizeof(int) * lu.size(), cudaMemcpyHostToDevice, c.stream));
+    if (!lv.empty()) CUDA_CHECK(cudaMemcpyAsync(list_v, lv.data(), sizeof(int) * lv.size(), cudaMemcpyHostToDevice, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.sc["_nd_nfaces_u"] = (double)lu.size();
+    c.sc["_nd_nfaces_v"] = (double)lv.size();
+  }
+  U.faces = list_u; U.nfaces = (int)c.sc["_nd_nfaces_u"];
+  V.faces = list_v; V.nfaces = (int)c.sc["_nd_nfaces_v"];
+  const dim3 gu(std::max(1, cdiv(U.nfaces, 128))), gv(std::max(1, cdiv(V.nfaces, 128)));
+  // resident blocks per SM (register budget 65536/(128*MINB)): development switch ndiff_minblk = 3 | 4 | 5
   // (tnx1v4, one direction: 2 blocks 10.4 ms, 3 blocks 8.4 ms, 4 blocks 7.3 ms)
-#define ND_FACE(NT_)                                                                              \
-  OCC_DISPATCH3("ndiff_minblk", 4, 4, 5, 6,                                                       \
-                LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, OCC>), gu, 128, 0, g, U);       \
-                LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, NT_, OCC>), gv, 128, 0, g, V))
+  // ndiff_prefetch=1: L1 prefetch of the operands a few iterations ahead; measured 5 % slower at tnx1v4 (14.2 vs 13.6 ms), off
+  const bool pf = c.option("ndiff_prefetch", "0") == "1";
+#define ND_FACE(NT_)                                                                                   \
+  OCC_DISPATCH3("ndiff_minblk", 4, 3, 4, 5,                                                            \
+                if (pf) {                                                                              \
+                  LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, OCC, true>), gu, 128, 0, g, U);    \
+                  LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, NT_, OCC, true>), gv, 128, 0, g, V);    \
+                } else {                                                                               \
+                  LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, OCC, false>), gu, 128, 0, g, U);   \
+                  LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, NT_, OCC, false>), gv, 128, 0, g, V);   \
+                })
   if (T == 2) { ND_FACE(2); }
   else if (T == 3) { ND_FACE(3); }
   else { ND_FACE(0); }

@@ -317,6 +317,7 @@ __global__ void mask_finish(Geom g, const double* __restrict__ u1, const double*
 }
 
 void bigrid_dev(const std::string& depth_name) {
+  C().sc.erase("_nd_nfaces_u"); C().sc.erase("_nd_nfaces_v");   // ndiff's wet-face lists follow the masks
   Ctx& c = C(); Geom& g = c.g;
   double* depth = c.dev(depth_name);
   bool lperiodi, lperiodj, larctic;

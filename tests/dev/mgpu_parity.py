@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Multi-GPU parity of the j-band path (run under torchrun, one rank per GPU):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 tests/dev/mgpu_parity.py mid2 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/dev/mgpu_parity.py tnx1v4 1
 
 Every rank steps its band of the synthetic state through the full hot path; rank 0 then runs
 the SAME case on one GPU (one tile) and on the CPU oracle and compares the assembled bands:
@@ -22,7 +22,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 FIELDS = ["dp", "temp", "saln", "u", "v", "uflx", "vflx", "utflx", "usflx", "pgfx", "pgfy", "pb", "ubflxs_p",
-          "p", "sigma", "umfltd", "vmflsm", "ub", "vb"]
+          "p", "sigma", "umfltd", "vmflsm", "ub", "vb", "nslpx", "nslpy", "nd_trc_rm", "utflld"]
 
 
 def main():
@@ -68,28 +68,18 @@ def main():
         s1 = one.gpu.xcsum("dp", "ip", lev=1)
         crc1 = one.gpu.chksum("temp", 2 * one.kdm, 1)
         one.gpu.download_all()
-        # CPU oracle on the same case (test infrastructure)
-        from util import Case
-        from blom_b200.driver import STEP_SEQUENCE
+        # CPU oracle on the same case (test infrastructure), same option set and call order
+        from util import Case, prepare_step
+        from blom_b200.driver import run_step
         from blom_b200.lib import time_levels
         c = Case(cfg, ntr=1, nstep=1)
         o = c.new_oracle()
-        o.inieos(); o.numerical_bounds(); o.init_cppm()
+        routines, _ = prepare_step(c, (o,))
+        assert routines == one.routines
         kk = c.dims[2]
         for ns in range(1, nsteps + 1):
-            m, n, mm, nn, k1m, k1n = time_levels(ns, kk)
             o.set_scalar("nstep", ns)
-            for r in STEP_SEQUENCE:
-                if r == "tmsmt1":
-                    o.tmsmt1(nn)
-                    o.xctilr("u", 1, 2 * kk, 2, 2, 13); o.xctilr("v", 1, 2 * kk, 2, 2, 14)
-                    for nm, it in (("ubflxs_p", 13), ("vbflxs_p", 14), ("pbu", 3), ("pbv", 4)):
-                        o.xctilr(nm, 1, 2, 2, 2, it)
-                    o.xctilr("temp", 1, 2 * kk, 3, 3, 1); o.xctilr("saln", 1, 2 * kk, 3, 3, 1)
-                elif r == "tmsmt2":
-                    o.tmsmt2(m, mm, nn, k1m)
-                else:
-                    getattr(o, r)(m, n, mm, nn, k1m, k1n)
+            run_step(o, routines, time_levels(ns, kk))
         worst_bit, worst_orc = 0.0, 0.0
         bands = [np.load(os.path.join(tmp, f"mgpu_band_{r}.npz")) for r in range(world)]
         for f in FIELDS:

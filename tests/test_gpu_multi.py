@@ -1,5 +1,8 @@
-"""Multi-GPU (j-band) parity, run on the box when >= 2 GPUs are visible: the bands of a 2-rank NCCL
-run are bit-identical to the one-tile run and within 1e-10 of the oracle (tests/dev/mgpu_parity.py)."""
+"""Multi-GPU (j-band) parity, run on the box when enough GPUs are visible: the bands of an N-rank run are
+bit-identical to the one-tile run (fields, strip-ordered xcsum, CRC) and within 1e-10 of the oracle
+(tests/dev/mgpu_parity.py).  2 ranks on the small tripolar / periodic grids with both transports, 3 and 4 ranks
+(ranks with a neighbour on both sides, the in-kernel barotropic exchange in both directions), and 2, 4 and 8
+bands of the full tnx1v4 grid (360 x 385 x 53) under the reference's option set."""
 import json
 import os
 import subprocess
@@ -17,14 +20,19 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("cfg,comm", [("mid1", "p2p"), ("mid2", "p2p"), ("mid2", "nccl")])
-def test_two_band_parity(cfg, comm, tmp_path):
-    if _ngpu() < 2:
-        pytest.skip("needs 2 GPUs")
+CASES = [("mid1", "p2p", 2, 3), ("mid2", "p2p", 2, 3), ("mid2", "nccl", 2, 3), ("mid2", "p2p", 3, 3),
+         ("mid2", "p2p", 4, 3), ("mid1", "nccl", 4, 2), ("tnx1v4", "p2p", 2, 1), ("tnx1v4", "p2p", 4, 1),
+         ("tnx1v4", "p2p", 8, 1)]
+
+
+@pytest.mark.parametrize("cfg,comm,nranks,steps", CASES)
+def test_band_parity(cfg, comm, nranks, steps, tmp_path):
+    if _ngpu() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
     env = dict(os.environ, MGPU_TMP=str(tmp_path), MGPU_COMM=comm)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks),
                         "--master-addr", "127.0.0.1", "--master-port", "29517", str(ROOT / "tests/dev/mgpu_parity.py"),
-                        cfg, "3"], capture_output=True, text=True, env=env, timeout=600)
+                        cfg, str(steps)], capture_output=True, text=True, env=env, timeout=1200)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert lines, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads(lines[-1])
