@@ -717,7 +717,9 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
           const double* __restrict__ p, const double* __restrict__ pbd /* pbu or pbv */,
           const double* __restrict__ scp2i, const double* __restrict__ scpd /* scpx or scpy */,
           const double* __restrict__ tab, const int* __restrict__ sten, double* __restrict__ flx,
-          double* __restrict__ tflx, double* __restrict__ sflx /* pointers at level 1+mm */) {
+          double* __restrict__ tflx, double* __restrict__ sflx /* pointers at level 1+mm */,
+          int extra /* 1: the scalars are a further group of passive tracers transported with the thickness
+                       fluxes of the pass; thickness and the flux accumulators were written by the first group */) {
   using L = FluxSmem<NT, TP, VAR>;
   constexpr int NCELL = L::NCELL;
   constexpr bool MONO = (VAR & 1) != 0, PC = (VAR & 2) != 0;
@@ -1096,10 +1098,10 @@ cppm_flux(Geom g, bool second_pass, int n_lev2d /* level (1-based) of pbu/pbv */
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
         S.dst[nt][xek] = (ho * tm_c[nt] - (s_F[(1 + nt) * TP + tp + 1] - htf[nt]) * ai_c) * hni;
-      dp_dst[xek] = fmax(K0, hn - DPEPS);
+      if (!extra) dp_dst[xek] = fmax(K0, hn - DPEPS);
     }
     // faces s0..s0+NOUT-1 belong to this tile; the last tile also owns face npass+1
-    if (face_ok) {
+    if (face_ok && !extra) {
       flx[xek] = O[2 * TP + tp] + hf;
       tflx[xek] = O[3 * TP + tp] + htf[0];
       sflx[xek] = O[4 * TP + tp] + htf[1];
@@ -1111,7 +1113,7 @@ template <int DIR, int NT, int VAR, int TP, int TC>
 void launch_flux_shape(bool second_pass, int n, const double* dp_src, double* dp_dst, const ScalarPtrs<NT>& S,
                  const double* hel3, const double* her3, const double* cad, const double* cac,
                  const double* p, const double* pbd, const double* scp2i, const double* scpd, const double* tab,
-                 const int* sten, double* flx, double* tflx, double* sflx) {
+                 const int* sten, double* flx, double* tflx, double* sflx, int extra) {
   Ctx& c = C(); const Geom& g = c.g;
   constexpr int NOUT = TP - 5;
   const size_t smem = sizeof(double) * FluxSmem<NT, TP, VAR>::PER_TC * TC;
@@ -1138,7 +1140,7 @@ void launch_flux_shape(bool second_pass, int n, const double* dp_src, double* dp
   // NB: the face npass+1 must be covered: tiles cover cells 1..ntile*NOUT >= npass and
   // thread tp = npass+1-p0 <= TP-3 of the last tile owns it.
   LAUNCH_NAMED(DIR == 0 ? "cppm_flux<i>" : "cppm_flux<j>", kern, grid, block, smem, g, second_pass, n, kchunk, dp_src,
-               dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i, scpd, tab, sten, flx, tflx, sflx);
+               dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i, scpd, tab, sten, flx, tflx, sflx, extra);
 }
 
 // Tile shape of the flux kernel: TP positions along the pass (TP-5 of them updated) x TC across it.
@@ -1149,23 +1151,23 @@ template <int DIR, int NT, int VAR>
 void launch_flux(bool second_pass, int n, const double* dp_src, double* dp_dst, const ScalarPtrs<NT>& S,
                  const double* hel3, const double* her3, const double* cad, const double* cac,
                  const double* p, const double* pbd, const double* scp2i, const double* scpd, const double* tab,
-                 const int* sten, double* flx, double* tflx, double* sflx) {
+                 const int* sten, double* flx, double* tflx, double* sflx, int extra = 0) {
   if constexpr (DIR == 0)
     launch_flux_shape<DIR, NT, VAR, 128, 2>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
-                                            scpd, tab, sten, flx, tflx, sflx);
+                                            scpd, tab, sten, flx, tflx, sflx, extra);
   else {
     const std::string jt = C().option("cppm_j_tile", CPPM_J_TILE_DEFAULT);
     // with two passive tracers (NT = 4) a 16-wide tile needs 232 KB of shared memory, more than the
     // 227 KB a block may have: the 8-wide tile (116 KB) is used instead
     if (NT >= 4 || jt == "32x8")
       launch_flux_shape<DIR, NT, VAR, 32, 8>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
-                                             scpd, tab, sten, flx, tflx, sflx);
+                                             scpd, tab, sten, flx, tflx, sflx, extra);
     else if (jt == "64x8")
       launch_flux_shape<DIR, NT, VAR, 64, 8>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd, scp2i,
-                                             scpd, tab, sten, flx, tflx, sflx);
+                                             scpd, tab, sten, flx, tflx, sflx, extra);
     else
       launch_flux_shape<DIR, NT, VAR, 32, 16>(second_pass, n, dp_src, dp_dst, S, hel3, her3, cad, cac, p, pbd,
-                                              scp2i, scpd, tab, sten, flx, tflx, sflx);
+                                              scp2i, scpd, tab, sten, flx, tflx, sflx, extra);
   }
 }
 
@@ -1222,6 +1224,35 @@ void cppm_pass(bool second_pass, int n, int mm, double* dp_src, double* dp_dst, 
                             c.dev(DIR == 0 ? "usflx" : "vsflx") + om);
 }
 
+// Further passive tracers of a pass, two per launch: the same thickness edges, flux areas and face fluxes as the
+// first group (hel3/her3 and dp_src are still those of this pass), only the tracer columns change.  The reference
+// loops nt = 1..ntr inside one sweep (phy/mod_cppm.F90:1599-1618); per tracer the operations are the same, so the
+// result does not depend on the grouping.  `ex` holds (source, destination) level-1 pointers of the extra tracers;
+// an odd one out is paired with itself (both copies write the same values).
+template <int DIR, int VAR>
+void cppm_pass_extra(bool second_pass, int n, int mm, const double* dp_src, double* dp_dst,
+                     const std::vector<std::pair<double*, double*>>& ex) {
+  if (ex.empty()) return;
+  Ctx& c = C(); const Geom& g = c.g;
+  constexpr int hw = (VAR & 1) ? 3 : 4;
+  const int mh = DIR == 0 ? hw : 0, nh = DIR == 0 ? 0 : hw;
+  std::vector<HaloReq> reqs;
+  for (auto& e : ex) reqs.push_back({e.first, g.kdm, halo_ps});
+  halo_update(reqs, mh, nh);
+  const long om = (long)mm * g.lev;
+  for (size_t q = 0; q < ex.size(); q += 2) {
+    const size_t q1 = std::min(q + 1, ex.size() - 1);
+    ScalarPtrs<2> S{};
+    S.src[0] = ex[q].first; S.dst[0] = ex[q].second; S.src[1] = ex[q1].first; S.dst[1] = ex[q1].second;
+    launch_flux<DIR, 2, VAR>(second_pass, n, dp_src, dp_dst, S, c.owned("cppm_hel_3d", g.kdm), c.owned("cppm_her_3d", g.kdm),
+                             c.dev(DIR == 0 ? "cau" : "cav"), c.dev(DIR == 0 ? "cav" : "cau"), c.dev("p"),
+                             c.dev(DIR == 0 ? "pbu" : "pbv"), c.dev("scp2i"), c.dev(DIR == 0 ? "scpx" : "scpy"),
+                             c.dev(DIR == 0 ? "cppm_tab_i" : "cppm_tab_j"), c.idev(DIR == 0 ? "cppm_sten_i" : "cppm_sten_j"),
+                             c.dev(DIR == 0 ? "uflx" : "vflx") + om, c.dev(DIR == 0 ? "utflx" : "vtflx") + om,
+                             c.dev(DIR == 0 ? "usflx" : "vsflx") + om, 1);
+  }
+}
+
 template <int NT, int VAR>
 void cppm_run_var(int n, int mm, int nn) {
   Ctx& c = C(); const Geom& g = c.g;
@@ -1240,12 +1271,23 @@ void cppm_run_var(int n, int mm, int nn) {
     b[nt] = c.owned("cppm_tmp_trc" + std::to_string(nt - 1), g.kdm);
   }
   for (int nt = 0; nt < NT; ++nt) { AB.src[nt] = a[nt]; AB.dst[nt] = b[nt]; BA.src[nt] = b[nt]; BA.dst[nt] = a[nt]; }
+  // passive tracers beyond the NT-2 that travel with T and S: transported in further launches of each pass
+  std::vector<std::pair<double*, double*>> exAB, exBA;
+  for (int nt = NT - 2; nt < g.ntr; ++nt) {
+    double* ta = c.dev("trc") + on + (long)nt * 2 * g.kdm * g.lev;
+    double* tb = c.owned("cppm_tmp_trc" + std::to_string(nt + 1), g.kdm);
+    exAB.push_back({ta, tb}); exBA.push_back({tb, ta});
+  }
   if (nstep % 2 == 1) {
     cppm_pass<0, NT, VAR>(false, n, mm, dpA, dpB, AB);
+    cppm_pass_extra<0, VAR>(false, n, mm, dpA, dpB, exAB);
     cppm_pass<1, NT, VAR>(true, n, mm, dpB, dpA, BA);
+    cppm_pass_extra<1, VAR>(true, n, mm, dpB, dpA, exBA);
   } else {
     cppm_pass<1, NT, VAR>(false, n, mm, dpA, dpB, AB);
+    cppm_pass_extra<1, VAR>(false, n, mm, dpA, dpB, exAB);
     cppm_pass<0, NT, VAR>(true, n, mm, dpB, dpA, BA);
+    cppm_pass_extra<0, VAR>(true, n, mm, dpB, dpA, exBA);
   }
 }
 
@@ -1314,11 +1356,10 @@ void advect_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     advect_remap_dev(m, n, mm, nn, k1m, k1n);
     return;
   }
-  switch (2 + g.ntr) {
+  switch (std::min(4, 2 + g.ntr)) {   // T, S and up to two tracers in the first group, the rest two at a time
     case 2: cppm_run<2>(n, mm, nn); break;
     case 3: cppm_run<3>(n, mm, nn); break;
-    case 4: cppm_run<4>(n, mm, nn); break;
-    default: throw std::runtime_error("advect: this build transports at most 2 passive tracers (ntr<=2)");
+    default: cppm_run<4>(n, mm, nn); break;
   }
   const long on = (long)nn * g.lev;
   std::vector<HaloReq> reqs{{c.dev("dp") + on, g.kdm, halo_ps}, {c.dev("temp") + on, g.kdm, halo_ps},

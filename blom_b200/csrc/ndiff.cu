@@ -440,11 +440,22 @@ ndiff_face(Geom g, NdArgs A) {
   {
     constexpr int NTC = NT > 0 ? NT : NTMAX;
     constexpr bool CACHE = NT > 0 && NT <= 3;     // register budget: 10 doubles per scalar
-    double cfm[CACHE ? NTC : 1][5], cfp[CACHE ? NTC : 1][5];
+    // the cache lives in shared memory, one column of 5*NT doubles per thread and side ([..][threadIdx.x],
+    // conflict-free): in registers its 40 values pushed the searches' state into spills at 128 registers
+    __shared__ double cf_sm[CACHE ? 2 * NTC * 5 : 1][128];
+    struct CoefRef {   // the five coefficients of scalar nt of one side, as the polynomial helpers read them
+      const double (*col)[128]; int t;
+      __device__ __forceinline__ double operator[](int c5) const { return col[c5][t]; }
+    };
+    auto cfm = [&](int nt) { return CoefRef{&cf_sm[CACHE ? (nt - 1) * 5 : 0], (int)threadIdx.x}; };
+    auto cfp = [&](int nt) { return CoefRef{&cf_sm[CACHE ? (NTC + nt - 1) * 5 : 0], (int)threadIdx.x}; };
     int kc_m = 0, kc_p = 0;                        // layers whose coefficients are cached
-    auto coef = [&](const Col& c, int k, int nt, double (&o)[5]) {
+    auto coef = [&](const Col& c, int k, int nt, int row0) {
       const double* b5 = c.tpc + (long)(((nt - 1) * kk + k - 1) * 5) * lev;
-      o[0] = b5[0]; o[1] = b5[lev]; o[2] = b5[2 * lev]; o[3] = b5[3 * lev]; o[4] = b5[4 * lev];
+      const double c0 = b5[0], c1 = b5[lev], c2 = b5[2 * lev], c3 = b5[3 * lev], c4 = b5[4 * lev];
+      double(*o)[128] = &cf_sm[CACHE ? row0 : 0];
+      const int t = threadIdx.x;
+      o[0][t] = c0; o[1][t] = c1; o[2][t] = c2; o[3][t] = c3; o[4][t] = c4;
     };
     // what the next source layer of a column will need: its polynomial coefficients, interface values,
     // diffusivity and layer means (read when ks advances, several neutral interfaces from now)
@@ -465,7 +476,7 @@ ndiff_face(Geom g, NdArgs A) {
     auto need_m = [&]() {
       if (CACHE && kc_m != ks_m) {
 #pragma unroll
-        for (int nt = 1; nt <= NTC; ++nt) coef(M, ks_m, nt, cfm[CACHE ? nt - 1 : 0]);
+        for (int nt = 1; nt <= NTC; ++nt) coef(M, ks_m, nt, (nt - 1) * 5);
         kc_m = ks_m;
         pf_layer(xm, ks_m + 1);
       }
@@ -473,13 +484,13 @@ ndiff_face(Geom g, NdArgs A) {
     auto need_p = [&]() {
       if (CACHE && kc_p != ks_p) {
 #pragma unroll
-        for (int nt = 1; nt <= NTC; ++nt) coef(P, ks_p, nt, cfp[CACHE ? nt - 1 : 0]);
+        for (int nt = 1; nt <= NTC; ++nt) coef(P, ks_p, nt, (NTC + nt - 1) * 5);
         kc_p = ks_p;
         pf_layer(x, ks_p + 1);
       }
     };
-    auto pe = [&](const double (&c)[5], double xx) { return (((c[4] * xx + c[3]) * xx + c[2]) * xx + c[1]) * xx + c[0]; };
-    auto pme = [&](const double (&c)[5], double x0, double x1) {
+    auto pe = [&](const CoefRef c, double xx) { return (((c[4] * xx + c[3]) * xx + c[2]) * xx + c[1]) * xx + c[0]; };
+    auto pme = [&](const CoefRef c, double x0, double x1) {
       const double c1_2 = 1. / 2., c1_3 = 1. / 3., c1_4 = 1. / 4., c1_5 = 1. / 5.;
       const double b5 = c1_5 * c[4];
       const double b4 = b5 * x1 + c1_4 * c[3];
@@ -736,9 +747,9 @@ ndiff_face(Geom g, NdArgs A) {
         for (int nt = 1; nt <= NTC; ++nt)
           if (nt <= T) {
             t_cur_m[nt - 1] = ev_m == 2 ? M.tsrcdi(is_m, ks_m, nt)
-                                        : (CACHE ? pe(cfm[CACHE ? nt - 1 : 0], x_cur_m) : peval(M, ks_m, nt, x_cur_m));
+                                        : (CACHE ? pe(cfm(nt), x_cur_m) : peval(M, ks_m, nt, x_cur_m));
             t_cur_p[nt - 1] = ev_p == 2 ? P.tsrcdi(is_p, ks_p, nt)
-                                        : (CACHE ? pe(cfp[CACHE ? nt - 1 : 0], x_cur_p) : peval(P, ks_p, nt, x_cur_p));
+                                        : (CACHE ? pe(cfp(nt), x_cur_p) : peval(P, ks_p, nt, x_cur_p));
           }
         const double dp_ni_m = fmin(p_cur_m - p_prev_m, M.pdst(kd_m + 1) - M.pdst(kd_m));
         const double dp_ni_p = fmin(p_cur_p - p_prev_p, P.pdst(kd_p + 1) - P.pdst(kd_p));
@@ -753,7 +764,7 @@ ndiff_face(Geom g, NdArgs A) {
 #pragma unroll
           for (int nt = 1; nt <= NTC; ++nt)
             if (nt <= T) {
-              const double d = CACHE ? pme(cfm[CACHE ? nt - 1 : 0], x_prev_m, x_cur_m) - pme(cfp[CACHE ? nt - 1 : 0], x_prev_p, x_cur_p)
+              const double d = CACHE ? pme(cfm(nt), x_prev_m, x_cur_m) - pme(cfp(nt), x_prev_p, x_cur_p)
                                      : pmeval(M, ks_m, nt, x_prev_m, x_cur_m) - pmeval(P, ks_p, nt, x_prev_p, x_cur_p);
               const double cm = A.tlev[nt - 1][xm + (long)(ks_m - 1) * lev], cp = A.tlev[nt - 1][x + (long)(ks_p - 1) * lev];
               const bool ok = d * (cm - cp) >= 0. && d * (t_prev_m[nt - 1] - t_prev_p[nt - 1]) >= 0. &&

@@ -109,7 +109,9 @@ pbcor_update(Geom g, eos::Coef ec, int ks, int kf, int kchunk, const int* __rest
              const double* __restrict__ saln, const double* __restrict__ scp2i, double* __restrict__ uflx,
              double* __restrict__ usflx, double* __restrict__ utflx, double* __restrict__ vflx,
              double* __restrict__ vsflx, double* __restrict__ vtflx, double* __restrict__ dpB,
-             double* __restrict__ tB, double* __restrict__ sB, double* __restrict__ sigma, PbTr T) {
+             double* __restrict__ tB, double* __restrict__ sB, double* __restrict__ sigma, PbTr T,
+             int extra /* 1: a further group of passive tracers; thickness, T, S and the flux arrays belong to the
+                          first launch and are only read */) {
   const double dpeps1 = 1.e-5, dpeps2 = 1.e-7;
   const Bid b_ = bid(g);
   const int i = b_.x * blockDim.x + threadIdx.x + 1, j = b_.y + 1;  // 1..ii+1, 1..jj+1
@@ -149,12 +151,12 @@ pbcor_update(Geom g, eos::Coef ec, int ks, int kf, int kchunk, const int* __rest
     const long ol = (long)(k + ks - 1) * lev, oa = (long)(k + kf - 1) * lev, ok = (long)(k - 1) * lev;
     const Flux3 fu = face_flux<DLUC>(F[0], 0, cur, ol, T);
     const Flux3 fv = face_flux<DLUC>(F[1], 1, cur, ol, T);
-    if (F[0].on) {
+    if (F[0].on && !extra) {
       uflx[x + oa] = cur.acc[0] + fu.f;
       usflx[x + oa] = cur.acc[1] + fu.f2;
       utflx[x + oa] = cur.acc[2] + fu.f3;
     }
-    if (F[1].on) {
+    if (F[1].on && !extra) {
       vflx[x + oa] = cur.acc[3] + fv.f;
       vsflx[x + oa] = cur.acc[4] + fv.f2;
       vtflx[x + oa] = cur.acc[5] + fv.f3;
@@ -181,15 +183,29 @@ pbcor_update(Geom g, eos::Coef ec, int ks, int kf, int kchunk, const int* __rest
         const double dtr = fue.ftr[nt] - fu.ftr[nt] + fvn.ftr[nt] - fv.ftr[nt];
         T.tb[nt][x + ok] = (dpo * T.t[nt][x + ol] - dtr * a) * dpni;
       }
-      if (WHICH == 2) {
-        sigma[x + ol] = eos::sig(ec, tn, sn);
-        dpn = dpn - epsilp;
+      if (!extra) {
+        if (WHICH == 2) {
+          sigma[x + ol] = eos::sig(ec, tn, sn);
+          dpn = dpn - epsilp;
+        }
+        if (dpn < dpeps2) dpn = 0.;
+        dpB[x + ok] = dpn; tB[x + ok] = tn; sB[x + ok] = sn;
       }
-      if (dpn < dpeps2) dpn = 0.;
-      dpB[x + ok] = dpn; tB[x + ok] = tn; sB[x + ok] = sn;
     }
     cur = nxt;
   }
+}
+
+// copy-back of a further tracer group (the first group's copy-back is part of pbcor_finish)
+__global__ void pbcor_finish_tracers(Geom g, int ks, const int* __restrict__ ip, PbTr T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1, k = blockIdx.z + 1;
+  if (i > g.ii) return;
+  const long x = ix2(g, i, j), lev = g.lev;
+  if (ip[x] != 1) return;
+  const long ok = (long)(k - 1) * lev, ol = (long)(k + ks - 1) * lev;
+#pragma unroll
+  for (int nt = 0; nt < MAXTR; ++nt)
+    if (nt < T.n) T.t[nt][x + ol] = T.tb[nt][x + ok];
 }
 
 template <int WHICH>
@@ -229,22 +245,30 @@ void pbcor_run(int m, int n, int mm, int nn, int k1m) {
   const std::string bmcmth = c.option("bmcmth", "uc");
   if (bmcmth != "uc" && bmcmth != "dluc")
     throw std::runtime_error(" bmcmth = " + bmcmth + " is unsupported! " + (WHICH == 1 ? "(pbcor1)" : "(pbcor2)"));
-  if (g.ntr > MAXTR) throw std::runtime_error("pbcor: this build handles at most 4 passive tracers");
   const bool dluc = bmcmth == "dluc";
   const double dlt = c.scalar("dlt");
   const int ks = WHICH == 1 ? nn : mm, kf = WHICH == 1 ? mm : nn, lt = WHICH == 1 ? m : n;
   const int kk = g.kdm;
-  PbTr T{}; T.n = g.ntr;
-  for (int nt = 0; nt < g.ntr; ++nt) {
-    T.t[nt] = c.dev("trc") + (long)nt * 2 * kk * g.lev;
-    T.tb[nt] = c.owned("cppm_tmp_trc" + std::to_string(nt + 1), kk);
+  // passive tracers in groups of MAXTR: the first group is corrected together with dp, T and S, further groups by
+  // extra launches of the update kernel that only touch their tracers (the reference loops nt = 1..ntr per cell,
+  // phy/mod_pbcor.F90:330-336; per tracer the operations are the same)
+  std::vector<PbTr> groups;
+  for (int n0 = 0; n0 < std::max(1, g.ntr); n0 += MAXTR) {
+    PbTr G{}; G.n = std::max(0, std::min(MAXTR, g.ntr - n0));
+    for (int q = 0; q < G.n; ++q) {
+      G.t[q] = c.dev("trc") + (long)(n0 + q) * 2 * kk * g.lev;
+      G.tb[q] = c.owned("cppm_tmp_trc" + std::to_string(n0 + q + 1), kk);
+    }
+    groups.push_back(G);
   }
+  const PbTr T = groups[0];
   if (WHICH == 2) {  // :433-440
     halo_update(std::vector<HaloReq>{{c.dev("ubflxs") + (long)(n - 1) * g.lev, 1, halo_uv},
                                      {c.dev("vbflxs") + (long)(n - 1) * g.lev, 1, halo_vv}}, 1, 1);
     if (g.ntr > 0) {
       std::vector<HaloReq> r;
-      for (int nt = 0; nt < g.ntr; ++nt) r.push_back({T.t[nt] + (long)(k1m - 1) * g.lev, kk, halo_ps});
+      for (int nt = 0; nt < g.ntr; ++nt)
+        r.push_back({c.dev("trc") + ((long)nt * 2 * kk + k1m - 1) * g.lev, kk, halo_ps});
       halo_update(r, 1, 1);
     }
   }
@@ -270,8 +294,16 @@ void pbcor_run(int m, int n, int mm, int nn, int k1m) {
 #define PB_LAUNCH(D)                                                                                            \
     LAUNCH_NAMED(nm, (pbcor_update<WHICH, D, OCC>), grid, 128, 0, g, ec, ks, kf, kchunk, ip, iu, iv, utot, vtot, dp, \
                  p, temp, saln, c.dev("scp2i"), c.dev("uflx"), c.dev("usflx"), c.dev("utflx"), c.dev("vflx"),     \
-                 c.dev("vsflx"), c.dev("vtflx"), dpB, tB, sB, c.dev("sigma"), T)
-    OCC_DISPATCH3("pbcor_minblk", 4, 3, 4, 5, if (dluc) PB_LAUNCH(true); else PB_LAUNCH(false));
+                 c.dev("vsflx"), c.dev("vtflx"), dpB, tB, sB, c.dev("sigma"), TG, EXTRA)
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      const PbTr TG = groups[gi];
+      const int EXTRA = gi > 0 ? 1 : 0;
+      OCC_DISPATCH3("pbcor_minblk", 4, 3, 4, 5, if (dluc) PB_LAUNCH(true); else PB_LAUNCH(false));
+      if (EXTRA) {
+        dim3 gridf(cdiv(g.ii, 128), g.jj, kk);
+        LAUNCH(pbcor_finish_tracers, gridf, 128, 0, g, ks, ip, TG);
+      }
+    }
 #undef PB_LAUNCH
   }
   {

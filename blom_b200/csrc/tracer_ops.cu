@@ -54,7 +54,7 @@ __global__ void diffus_flux(Geom g, double delt1, int mm, int nn, const int* __r
                             double* __restrict__ utflld, double* __restrict__ vsflld,
                             double* __restrict__ vtflld, double* __restrict__ usflx,
                             double* __restrict__ utflx, double* __restrict__ vsflx,
-                            double* __restrict__ vtflx, TrcPtrs T) {
+                            double* __restrict__ vtflx, TrcPtrs T, int extra /* 1: a further tracer group only */) {
   const double dpeps = 1.e-5;
   const Bid b_ = bid(g);
   const int i = b_.x * blockDim.x + threadIdx.x;  // 0..ii+2
@@ -73,13 +73,13 @@ __global__ void diffus_flux(Geom g, double delt1, int mm, int nn, const int* __r
   const double ousf = usflx[xm], outf = utflx[xm], ovsf = vsflx[xm], ovtf = vtflx[xm];
   const double qu = delt1 * .5 * (dw + dc) * scuy[x] * scuxi[x] * fmax(fmin(dpw, dpc), dpeps);
   const double qv = delt1 * .5 * (ds + dc) * scvx[x] * scvyi[x] * fmax(fmin(dps, dpc), dpeps);
-  if (wu) {
+  if (wu && !extra) {
     const double fs = qu * (sw - sc), ft = qu * (tw - tc);
     usflld[xm] = fs; utflld[xm] = ft;
     usflx[xm] = ousf + fs;
     utflx[xm] = outf + ft;
   }
-  if (wv) {
+  if (wv && !extra) {
     const double fs = qv * (ss - sc), ft = qv * (ts - tc);
     vsflld[xm] = fs; vtflld[xm] = ft;
     vsflx[xm] = ovsf + fs;
@@ -100,7 +100,7 @@ __global__ void diffus_update(Geom g, eos::Coef ec, int mm, int nn, const int* _
                               double* __restrict__ saln, double* __restrict__ sigma,
                               const double* __restrict__ scp2, const double* __restrict__ usflld,
                               const double* __restrict__ utflld, const double* __restrict__ vsflld,
-                              const double* __restrict__ vtflld, TrcPtrs T) {
+                              const double* __restrict__ vtflld, TrcPtrs T, int extra) {
   const double dpeps = 1.e-5;
   const Bid b_ = bid(g);
   const int i = b_.x * blockDim.x + threadIdx.x;  // 0..ii+1
@@ -113,13 +113,15 @@ __global__ void diffus_update(Geom g, eos::Coef ec, int mm, int nn, const int* _
   const double q = 1. / (scp2[x] * fmax(dp[xn], dpeps));
   const double sn = saln[xn] - q * (usflld[xm + 1] - usflld[xm] + vsflld[xm + s] - vsflld[xm]);
   const double tn = temp[xn] - q * (utflld[xm + 1] - utflld[xm] + vtflld[xm + s] - vtflld[xm]);
-  saln[xn] = sn;
-  temp[xn] = tn;
+  if (!extra) {
+    saln[xn] = sn;
+    temp[xn] = tn;
+  }
 #pragma unroll
   for (int nt = 0; nt < MAXTR; ++nt)
     if (nt < T.n)
       T.t[nt][xn] = T.t[nt][xn] - q * (T.fu[nt][xk + 1] - T.fu[nt][xk] + T.fv[nt][xk + s] - T.fv[nt][xk]);
-  sigma[xn] = eos::sig(ec, tn, sn);
+  if (!extra) sigma[xn] = eos::sig(ec, tn, sn);
 }
 
 __global__ void tmsmt1_kernel(Geom g, int nn, bool isopyc, const int* __restrict__ ip,
@@ -223,16 +225,15 @@ __global__ void dpuv_from_p(Geom g, int mm, const int* __restrict__ iu, const in
   }
 }
 
-TrcPtrs trc_ptrs(bool with_flux) {
+// passive tracers n0 .. n0+MAXTR-1 (the reference loops nt = 1..ntr inside its sweeps, phy/mod_diffus.F90:99-135;
+// here the first group travels with T and S and further groups take extra launches)
+TrcPtrs trc_ptrs(int n0) {
   Ctx& c = C(); const Geom& g = c.g;
-  TrcPtrs T{}; T.n = g.ntr;
-  if (g.ntr > MAXTR) throw std::runtime_error("diffus: this build handles at most 4 passive tracers");
-  for (int nt = 0; nt < g.ntr; ++nt) {
-    T.t[nt] = c.dev("trc") + (long)nt * 2 * g.kdm * g.lev;
-    if (with_flux) {
-      T.fu[nt] = c.owned("diffus_uflxtr" + std::to_string(nt + 1), g.kdm);
-      T.fv[nt] = c.owned("diffus_vflxtr" + std::to_string(nt + 1), g.kdm);
-    }
+  TrcPtrs T{}; T.n = std::max(0, std::min(MAXTR, g.ntr - n0));
+  for (int q = 0; q < T.n; ++q) {
+    T.t[q] = c.dev("trc") + (long)(n0 + q) * 2 * g.kdm * g.lev;
+    T.fu[q] = c.owned("diffus_uflxtr" + std::to_string(q + 1), g.kdm);   // flux scratch is reused by every group
+    T.fv[q] = c.owned("diffus_vflxtr" + std::to_string(q + 1), g.kdm);
   }
   return T;
 }
@@ -250,19 +251,22 @@ void diffus_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   if (ltedtp == "neutral") { halo_update(reqs, 1, 1); return; }
   if (ltedtp != "layer") throw std::runtime_error(" ltedtp = " + ltedtp + " is unsupported!");
   halo_update(reqs, 2, 2);
-  TrcPtrs T = trc_ptrs(true);
-  {
-    const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm));
-    LAUNCH(diffus_flux, grid, 128, 0, g, c.scalar("delt1"), mm, nn, c.idev("iu"), c.idev("iv"), c.dev("dp"),
-           c.dev("temp"), c.dev("saln"), c.dev("difiso"), c.dev("scuy"), c.dev("scuxi"), c.dev("scvx"),
-           c.dev("scvyi"), c.dev("usflld"), c.dev("utflld"), c.dev("vsflld"), c.dev("vtflld"), c.dev("usflx"),
-           c.dev("utflx"), c.dev("vsflx"), c.dev("vtflx"), T);
-  }
-  {
-    const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 2, 128), g.jj + 2, g.kdm));
-    LAUNCH(diffus_update, grid, 128, 0, g, eos::host_coef(), mm, nn, c.idev("ip"), c.dev("dp"), c.dev("temp"),
-           c.dev("saln"), c.dev("sigma"), c.dev("scp2"), c.dev("usflld"), c.dev("utflld"), c.dev("vsflld"),
-           c.dev("vtflld"), T);
+  for (int n0 = 0; n0 < std::max(1, g.ntr); n0 += MAXTR) {
+    const TrcPtrs T = trc_ptrs(n0);
+    const int extra = n0 > 0 ? 1 : 0;
+    {
+      const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm));
+      LAUNCH(diffus_flux, grid, 128, 0, g, c.scalar("delt1"), mm, nn, c.idev("iu"), c.idev("iv"), c.dev("dp"),
+             c.dev("temp"), c.dev("saln"), c.dev("difiso"), c.dev("scuy"), c.dev("scuxi"), c.dev("scvx"),
+             c.dev("scvyi"), c.dev("usflld"), c.dev("utflld"), c.dev("vsflld"), c.dev("vtflld"), c.dev("usflx"),
+             c.dev("utflx"), c.dev("vsflx"), c.dev("vtflx"), T, extra);
+    }
+    {
+      const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 2, 128), g.jj + 2, g.kdm));
+      LAUNCH(diffus_update, grid, 128, 0, g, eos::host_coef(), mm, nn, c.idev("ip"), c.dev("dp"), c.dev("temp"),
+             c.dev("saln"), c.dev("sigma"), c.dev("scp2"), c.dev("usflld"), c.dev("utflld"), c.dev("vsflld"),
+             c.dev("vtflld"), T, extra);
+    }
   }
 }
 

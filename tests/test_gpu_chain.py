@@ -117,13 +117,26 @@ def test_chained_step_two_passive_tracers(cfg):
         g.finalize()
 
 
-def test_three_passive_tracers_rejected():
-    from blom_b200.lib import BlomGpuError
-    c = Case("tiny1", ntr=3, nstep=1)
-    g = c.new_gpu(parity=True)
+@pytest.mark.parametrize("cfg,optset", [("tiny2", "reference"), ("tiny4", "layer"), ("tiny1", "layer")])
+def test_chained_steps_five_passive_tracers(cfg, optset):
+    """ntr = 5, more than any kernel carries in one launch (cppm: T, S + 2 tracers, then groups of 2; pbcor and
+    diffus: groups of 4; the reference loops nt = 1..ntr freely, phy/mod_cppm.F90:1599-1618): two chained steps,
+    every registered array against the oracle after every routine, parity build, 1e-10."""
+    c = Case(cfg, ntr=5, nstep=1)
+    o = c.new_oracle(); g = c.new_gpu(parity=True)
     try:
-        g.inieos(); g.numerical_bounds(); g.init_cppm()
-        with pytest.raises(BlomGpuError, match="at most 2 passive tracers"):
-            g.advect(*c.levels)
+        routines, _ = prepare_step(c, (o, g), OPTION_SETS[optset])
+        kk = c.dims[2]
+        for nstep in (1, 2):
+            lv = time_levels(nstep, kk)
+            for b in (o, g):
+                b.set_scalar("nstep", nstep)
+            for r in routines:
+                run_step(o, [r], lv); run_step(g, [r], lv)
+                compare_all(g, o, (cfg, nstep, r))
+        trc = interior(g.arrays["trc"])
+        assert np.abs(trc).max() > 0 and np.isfinite(trc).all()
+        # the five tracers carry different fields (the generator offsets them), so a mixed-up group would show
+        assert not np.array_equal(trc[:2 * kk], trc[8 * kk:10 * kk])
     finally:
         g.finalize()
