@@ -75,11 +75,18 @@ KERNELS = {
     "mt_aux": (4, "3d"), "mt_vort": (3 + 2, "3d"), "mt_visc": (0, "3d"), "mt_flux1": (2, "3d"),
     "mt_update": (9 + 2, "3d"), "mt_update_v": (9 + 2, "3d"), "mt_column": (8 + 4, "3d"),
     "mt_fused": (21 + 6, "3d"),
+    # neutral diffusion: per face column and layer R p_src,p_dst,snapped p_dst (3), interface records 2x4, t_srcdi 2T,
+    # tpc_src 5T, difiso, layer means T, face pressure (1)  W 4 face fluxes (read-modify-write), nslp, 2T face
+    # convergences; T = 2.  The kernel is issue- and latency-bound (data-dependent search per column), its HBM
+    # fraction is reported for completeness only
+    "ndiff_face<u>": (3 + 8 + 4 + 10 + 1 + 2 + 1 + 8 + 1 + 4, "3d"), "ndiff_face<v>": (3 + 8 + 4 + 10 + 1 + 2 + 1 + 8 + 1 + 4, "3d"),
+    "ndiff_prep": (2 + 4 + 1 + 8 + 1 + 4, "3d"), "ndiff_update": (2 + 8 + 2, "3d"),
     "bt_subcycle": (53, "bt"), "bt_ueq": (23, "2d"), "bt_veq": (23, "2d"), "bt_continuity": (7, "2d"),
 }
 KERNEL_SCRATCH_WORDS = {"mt_aux": 7, "mt_vort": 4 + 2, "mt_visc": 2 + 4, "mt_flux1": 8 + 2, "mt_update": 12,
                         "mt_update_v": 12}
-BT_WORDS_PER_SUBSTEP = 53  # 46R + 7W distinct 2-D arrays per substep
+BT_WORDS_PER_SUBSTEP = 53  # 46R + 7W distinct 2-D arrays per substep; the kernel skips the arrays
+# whose time weight is zero in a block (7 words in blocks 1-3, 14 in blocks 4-5), the model keeps the reference's 53
 
 
 def measured_traffic():

@@ -622,6 +622,10 @@ ndiff_face(Geom g, NdArgs A) {
       // interface value t_srcdi(is,ks)
       int ev_m = 0, ev_p = 0;
 
+      // The reference spells the case analysis out once per column; the two columns' branches are mirror
+      // images, so they are written once with the roles chosen per lane (a = the column that decides,
+      // b = the other one) and lanes on mirrored branches stay together.  The local coordinates x of the
+      // interface are evaluated after the branches from p_cur (same expression as in every branch).
       if (case_m == 3 && case_p == 3) {
         if (is_p == 2 && is_m == 2) {
           p_cur_m = snp_m;
@@ -648,8 +652,6 @@ ndiff_face(Geom g, NdArgs A) {
             advance_dst_p = true;
           }
           if (p_cur_m >= psm1 && p_cur_m <= psm2 && p_cur_p >= psp1 && p_cur_p <= psp2) {
-            x_cur_m = (p_cur_m - psm1) / (psm2 - psm1);
-            x_cur_p = (p_cur_p - psp1) / (psp2 - psp1);
             ev_m = 1; ev_p = 1;
             found_ni = true;
           }
@@ -657,52 +659,33 @@ ndiff_face(Geom g, NdArgs A) {
           if (is_p != 2) advance_dst_m = true;
           if (is_m != 2) advance_dst_p = true;
         }
-      } else if (case_m == 3) {
-        if (is_p == 2) {
-          p_cur_m = snp_m;
-          if (case_p == 1)
-            p_cur_p = p_prev_p + (p_cur_m - p_prev_m) * (psp_n - p_prev_p) / (pnp_n - p_prev_m);
-          else
-            p_cur_p = p_prev_p + (p_cur_m - p_prev_m) * (pnm_n - p_prev_p) / (psm_n - p_prev_m);
-          if (p_cur_p >= psp1 && p_cur_p <= psp2) {
-            x_cur_m = (snp_m - psm1) / (psm2 - psm1);
-            x_cur_p = (p_cur_p - psp1) / (psp2 - psp1);
+      } else if (case_m == 3 || case_p == 3) {
+        // exactly one column (a) meets its next destination interface first (:640-700)
+        const bool am = case_m == 3;
+        const int is_b = am ? is_p : is_m, case_b = am ? case_p : case_m;
+        if (is_b == 2) {
+          const double snp_a = am ? snp_m : snp_p;
+          const double pa_prev = am ? p_prev_m : p_prev_p, pb_prev = am ? p_prev_p : p_prev_m;
+          const double px = case_b == 1 ? (am ? psp_n : psm_n) : (am ? pnm_n : pnp_n);
+          const double py = case_b == 1 ? (am ? pnp_n : pnm_n) : (am ? psm_n : psp_n);
+          const double pb_cur = pb_prev + (snp_a - pa_prev) * (px - pb_prev) / (py - pa_prev);
+          if (am) { p_cur_m = snp_a; p_cur_p = pb_cur; } else { p_cur_p = snp_a; p_cur_m = pb_cur; }
+          if (pb_cur >= (am ? psp1 : psm1) && pb_cur <= (am ? psp2 : psm2)) {
             ev_m = 1; ev_p = 1;
             found_ni = true;
-            advance_dst_m = true;
+            if (am) advance_dst_m = true; else advance_dst_p = true;
           } else {
-            if (case_p == 1 && PNP(is_p, ks_p) == mval) advance_src_p = true;
-            else advance_dst_m = true;
+            const double pn_b = am ? PNP(is_p, ks_p) : PNM(is_m, ks_m);
+            if (case_b == 1 && pn_b == mval) { if (am) advance_src_p = true; else advance_src_m = true; }
+            else { if (am) advance_dst_m = true; else advance_dst_p = true; }
           }
         } else {
-          advance_dst_m = true;
-        }
-      } else if (case_p == 3) {
-        if (is_m == 2) {
-          p_cur_p = snp_p;
-          if (case_m == 1)
-            p_cur_m = p_prev_m + (p_cur_p - p_prev_p) * (psm_n - p_prev_m) / (pnm_n - p_prev_p);
-          else
-            p_cur_m = p_prev_m + (p_cur_p - p_prev_p) * (pnp_n - p_prev_m) / (psp_n - p_prev_p);
-          if (p_cur_m >= psm1 && p_cur_m <= psm2) {
-            x_cur_p = (snp_p - psp1) / (psp2 - psp1);
-            x_cur_m = (p_cur_m - psm1) / (psm2 - psm1);
-            ev_m = 1; ev_p = 1;
-            found_ni = true;
-            advance_dst_p = true;
-          } else {
-            if (case_m == 1 && PNM(is_m, ks_m) == mval) advance_src_m = true;
-            else advance_dst_p = true;
-          }
-        } else {
-          advance_dst_p = true;
+          if (am) advance_dst_m = true; else advance_dst_p = true;
         }
       } else if (case_m == 1 && case_p == 1) {
         const double pnm_c = PNM(is_m, ks_m), pnp_c = PNP(is_p, ks_p);
         if (pnm_c != mval && pnp_c != mval) {
-          x_cur_m = (double)(is_m - 1);
           p_cur_m = psm;
-          x_cur_p = (double)(is_p - 1);
           p_cur_p = psp;
           ev_m = 2; ev_p = 2;
           found_ni = true;
@@ -712,28 +695,16 @@ ndiff_face(Geom g, NdArgs A) {
           if (pnm_c == mval) advance_src_m = true;
           if (pnp_c == mval) advance_src_p = true;
         }
-      } else if (case_m == 1) {
-        const double pnm_c = PNM(is_m, ks_m);
-        if (pnm_c != mval && pnm_c >= psp1) {
-          x_cur_m = (double)(is_m - 1);
-          p_cur_m = psm;
-          p_cur_p = pnm_c;
-          x_cur_p = (p_cur_p - psp1) / (psp2 - psp1);
-          ev_m = 2; ev_p = 1;
+      } else if (case_m == 1 || case_p == 1) {
+        // one column (a) sits on a source interface whose neutral partner lies inside the other's layer (:745-790)
+        const bool am = case_m == 1;
+        const double pn_c = am ? PNM(is_m, ks_m) : PNP(is_p, ks_p);
+        if (pn_c != mval && pn_c >= (am ? psp1 : psm1)) {
+          if (am) { p_cur_m = psm; p_cur_p = pn_c; ev_m = 2; ev_p = 1; }
+          else { p_cur_p = psp; p_cur_m = pn_c; ev_p = 2; ev_m = 1; }
           found_ni = true;
         }
-        advance_src_m = true;
-      } else if (case_p == 1) {
-        const double pnp_c = PNP(is_p, ks_p);
-        if (pnp_c != mval && pnp_c >= psm1) {
-          x_cur_p = (double)(is_p - 1);
-          p_cur_p = psp;
-          p_cur_m = pnp_c;
-          x_cur_m = (p_cur_m - psm1) / (psm2 - psm1);
-          ev_p = 2; ev_m = 1;
-          found_ni = true;
-        }
-        advance_src_p = true;
+        if (am) advance_src_m = true; else advance_src_p = true;
       } else {
         advance_src_m = true;
         advance_src_p = true;
@@ -743,6 +714,11 @@ ndiff_face(Geom g, NdArgs A) {
         // NOTE: advance_src_* set above only act at the top of the next iteration: is/ks are still the
         // ones the interface was found for
         need_m(); need_p();
+        {
+          const double xm_ = (p_cur_m - psm1) / (psm2 - psm1), xp_ = (p_cur_p - psp1) / (psp2 - psp1);
+          x_cur_m = ev_m == 2 ? (double)(is_m - 1) : xm_;
+          x_cur_p = ev_p == 2 ? (double)(is_p - 1) : xp_;
+        }
 #pragma unroll
         for (int nt = 1; nt <= NTC; ++nt)
           if (nt <= T) {

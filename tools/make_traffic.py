@@ -34,6 +34,13 @@ def bench_name(ncu_name):
     m = re.match(r"(pbcor_\w+)<(\d)", n)
     if m:
         return f"{m.group(1)}<{m.group(2)}>"
+    m = re.match(r"ndiff_face<(\d)", n)
+    if m:
+        return "ndiff_face<u>" if m.group(1) == "0" else "ndiff_face<v>"
+    # occupancy / shape template arguments are not part of bench.py's kernel names
+    m = re.match(r"(bt_subcycle|mt_\w+|advect_flux_area|pg_\w+)<", n)
+    if m:
+        return m.group(1)
     return n
 
 
