@@ -874,12 +874,22 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     CUDA_CHECK(cudaMemcpyAsync(hu.data(), c.idev("iu"), sizeof(int) * g.lev, cudaMemcpyDeviceToHost, c.stream));
     CUDA_CHECK(cudaMemcpyAsync(hv.data(), c.idev("iv"), sizeof(int) * g.lev, cudaMemcpyDeviceToHost, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
-    for (int j = 1; j <= g.jj + 1; ++j)
+    for (int j = 1; j <= g.jj; ++j)
       for (int i = 1; i <= g.ii + 1; ++i) {
         const long x = ix2(g, i, j);
-        if (j <= g.jj && hu[x] == 1) lu.push_back((int)x);
-        if (i <= g.ii && hv[x] == 1) lv.push_back((int)x);
+        if (hu[x] == 1) lu.push_back((int)x);
       }
+    // v faces in tiles of 32 (i) x 4 (j): a 128-thread block then owns four consecutive rows of a 32-wide strip, and
+    // the cell column (i,j) that is the plus side of face (i,j) and the minus side of face (i,j+1) is fetched by one
+    // block instead of by two blocks a whole grid row apart (ncu, row-major order: 75 GB of DRAM traffic per launch
+    // for the v faces against 49 GB for the u faces, whose two columns sit in neighbouring lanes)
+    for (int j0 = 1; j0 <= g.jj + 1; j0 += 4)
+      for (int i0 = 1; i0 <= g.ii; i0 += 32)
+        for (int j = j0; j < std::min(j0 + 4, g.jj + 2); ++j)
+          for (int i = i0; i < std::min(i0 + 32, g.ii + 1); ++i) {
+            const long x = ix2(g, i, j);
+            if (hv[x] == 1) lv.push_back((int)x);
+          }
     if (!lu.empty()) CUDA_CHECK(cudaMemcpyAsync(list_u, lu.data(), sizeof(int) * lu.size(), cudaMemcpyHostToDevice, c.stream));
     if (!lv.empty()) CUDA_CHECK(cudaMemcpyAsync(list_v, lv.data(), sizeof(int) * lv.size(), cudaMemcpyHostToDevice, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
