@@ -199,9 +199,10 @@ class HotPath:
     def step_pipelined(self):
         """One end-to-end pass with the host<->device copies overlapped with the kernels (the call sequence a
         host that keeps its own copy of the prognostic state would issue):
-          H2D  the time level the host physics wrote (new level n) of dp,T,S[,trc], then u,v, on the upload
-               stream; tmsmt1 waits for dp/T/S, u,v are first read by momtum (advect only reads the resident
-               mid level), so their copy hides behind tmsmt1..pgforc.  The u,v halo refresh of difest
+          H2D  the time level the host physics wrote (new level n) of T,S[,trc], dp, then u,v, on the upload
+               stream; ndiff (which only reads T,S of that level and is independent of tmsmt1) starts as soon as
+               T,S are there, tmsmt1 follows when dp has arrived, u,v are first read by momtum (advect only reads
+               the resident mid level), so their copy hides behind ndiff..pgforc.  The u,v halo refresh of difest
                (phy/mod_difest.F90:826-827) moves with them to just before momtum - nothing reads or writes
                u,v in between, so the values are the ones run_step produces.
           D2H  on the copy stream as soon as a field's last writer has been enqueued: u,v (both levels,
@@ -216,20 +217,31 @@ class HotPath:
             self.upload_inputs(); self.step(early_download=True); self.download_outputs()
             return
         from .lib import HALO_PS, HALO_UV, HALO_VV, HALO_US, HALO_VS
-        scal = [("dp", 0), ("temp", 0), ("saln", 0)] + [("trc", nt * 2 * kk) for nt in range(self.ntr)]
+        # upload order = order of first use: T, S (neutral diffusion, the longest routine, reads only them), tracers,
+        # then dp (tmsmt1), then u, v (momtum)
+        scal = [("temp", 0), ("saln", 0)] + [("trc", nt * 2 * kk) for nt in range(self.ntr)] + [("dp", 0)]
         for nm, off in scal:
             g.upload_async(nm, off + k1n, kk)
         for nm in ("u", "v"):
             g.upload_async(nm, k1n, kk)
+        nd_first = "ndiff" in self.routines
         for r in self.routines:
             if r == "tmsmt1":
-                for nm in {nm for nm, _ in scal}:
-                    g.wait_upload(nm)
+                for nm in ("temp", "saln", "trc"):
+                    if nm in self.arrays:
+                        g.wait_upload(nm)
+                g.xctilr("temp", 1, 2 * kk, 3, 3, HALO_PS)
+                g.xctilr("saln", 1, 2 * kk, 3, 3, HALO_PS)
+                if nd_first:
+                    # ndiff and tmsmt1 touch disjoint arrays (tmsmt1 copies dp,T,S of the new level into the
+                    # smoother's work arrays, phy/mod_tmsmt.F90:209-258), so ndiff can start while dp is on its way
+                    g.ndiff(m, n, mm, nn, k1m, k1n)
+                g.wait_upload("dp")
                 g.tmsmt1(nn)
                 for nm, it in (("ubflxs_p", HALO_UV), ("vbflxs_p", HALO_VV), ("pbu", HALO_US), ("pbv", HALO_VS)):
                     g.xctilr(nm, 1, 2, 2, 2, it)
-                g.xctilr("temp", 1, 2 * kk, 3, 3, HALO_PS)
-                g.xctilr("saln", 1, 2 * kk, 3, 3, HALO_PS)
+            elif r == "ndiff" and nd_first:
+                continue
             elif r == "momtum":
                 g.wait_upload("u"); g.wait_upload("v")
                 g.xctilr("u", 1, 2 * kk, 2, 2, HALO_UV)

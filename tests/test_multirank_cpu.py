@@ -26,6 +26,35 @@ def test_band_partition_covers_grid():
             assert min(jj for _, jj in rows) >= 4  # nbdy-wide halos come from the direct neighbour only
 
 
+def test_weighted_bands_cover_grid_and_balance_wet_columns():
+    """driver.balanced_band: contiguous bands that cover the grid, at least 8 rows each, and a smaller spread of
+    wet columns per band than equal-height bands on the 0.25 degree grid at 8 ranks."""
+    from blom_b200.driver import balanced_band, weighted_bands
+    for cfg in ("tnx0.25v4", "tnx0.125v4", "tnx1v4", "mid2"):
+        jtdm = synth.CONFIGS[cfg][1]
+        for n in (1, 2, 4, 8):
+            if jtdm < 8 * n:
+                continue
+            rows = [balanced_band(cfg, r, n) for r in range(n)]
+            assert rows[0][0] == 0 and sum(jj for _, jj in rows) == jtdm
+            for (a, ja), (b, _) in zip(rows, rows[1:]):
+                assert a + ja == b
+            assert min(jj for _, jj in rows) >= 4
+    s = synth.Synth.from_config("tnx0.25v4")
+    wet = (s.depth_global > 0).sum(axis=1)
+
+    def spread(bands):
+        w = np.array([wet[j0:j0 + jj].sum() for j0, jj in bands], dtype=float)
+        return w.max() / w.mean()
+    equal = [band(1153, r, 8) for r in range(8)]
+    weighted = [balanced_band("tnx0.25v4", r, 8) for r in range(8)]
+    assert spread(weighted) < spread(equal) and spread(weighted) < 1.08
+    # degenerate cost vectors still give legal partitions
+    for cost in (np.ones(100), np.r_[np.zeros(90), np.ones(10)], np.r_[np.ones(10), np.zeros(90)]):
+        bs = weighted_bands(cost, 4)
+        assert bs[0][0] == 0 and sum(jj for _, jj in bs) == 100 and min(jj for _, jj in bs) >= 8
+
+
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
