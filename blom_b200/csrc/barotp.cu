@@ -201,6 +201,10 @@ __global__ void bt_veq(Geom g, BtP P, const double* __restrict__ ub, int i0, int
 
 struct BtSched {
   int lll0, nsub, ml, nl;
+  // levels (1-based) of the three bottom-pressure buffers that hold the mid level, the old/new level and the
+  // spare the fused form writes the new level into; fuse = 1: continuity is evaluated inside the first momentum
+  // phase of a substep (see bt_subcycle)
+  int pml, pnl, psp, fuse;
   double woa, wob, wna, wnb;
   int inkernel_halo;
   // band edges exchanged in-kernel through the peer mailboxes (multi-GPU); seq0 = sequence number of
@@ -237,8 +241,16 @@ __device__ __forceinline__ void btp_continuity(const Geom& g, const BtP& P, cons
                (1. + WBARO) * P.dlt * (__ldcg(V.ub_ml + x + 1) - __ldcg(V.ub_ml + x) + __ldcg(V.vb_ml + x + g.ldi) -
                                        __ldcg(V.vb_ml + x)) * P.scp2i[x];
 }
+__device__ __forceinline__ double btp_continuity_value(const Geom& g, const BtP& P, const BtLv& V, long x) {
+  return (1. - WBARO) * __ldcg(V.pb_ml + x) + WBARO * __ldcg(V.pb_nl + x) -
+         (1. + WBARO) * P.dlt * (__ldcg(V.ub_ml + x + 1) - __ldcg(V.ub_ml + x) + __ldcg(V.vb_ml + x + g.ldi) -
+                                 __ldcg(V.vb_ml + x)) * P.scp2i[x];
+}
+// pbc, pbw: new bottom pressure at the u point's two mass points (read from the array by the staged form,
+// recomputed from the continuity equation by the fused form - the same expression on the same operands)
 template <int WM>
-__device__ __forceinline__ void btp_ueq(const Geom& g, const BtP& P, const BtLv& V, const double* __restrict__ vb, long x) {
+__device__ __forceinline__ void btp_ueq(const Geom& g, const BtP& P, const BtLv& V, const double* __restrict__ vb, long x,
+                                        double pbc, double pbw) {
   using W = Wsel<WM>;
   const long s = g.ldi;
   const double uml = __ldcg(V.ub_ml + x), unl = __ldcg(V.ub_nl + x);
@@ -255,7 +267,6 @@ __device__ __forceinline__ void btp_ueq(const Geom& g, const BtP& P, const BtLv&
     q = .25 * ((v00 * P.scvxi[x] + vm0 * P.scvxi[x - 1]) * wsum3<WM>(V, pvo0, pvm0, pvn0) +
                (v01 * P.scvxi[x + s] + vm1 * P.scvxi[x - 1 + s]) * wsum3<WM>(V, pvo1, pvm1, pvn1));
   P.ubcors_t[x] = __ldcg(P.ubcors_t + x) + q;
-  const double pbc = __ldcg(V.pb_nl + x), pbw = __ldcg(V.pb_nl + x - 1);
   const double t_o = W::o ? P.pgfxm_o[x] - (P.xixp_o[x] * pbc - P.xixm_o[x] * pbw) : 0.;
   const double t_m = W::m ? P.pgfxm_m[x] - (P.xixp_m[x] * pbc - P.xixm_m[x] * pbw) : 0.;
   const double t_n = W::n ? P.pgfxm_n[x] - (P.xixp_n[x] * pbc - P.xixm_n[x] * pbw) : 0.;
@@ -265,7 +276,8 @@ __device__ __forceinline__ void btp_ueq(const Geom& g, const BtP& P, const BtLv&
   V.ub_nl[x] = fmax(-P.uminb[x], fmin(P.umaxb[x], un));
 }
 template <int WM>
-__device__ __forceinline__ void btp_veq(const Geom& g, const BtP& P, const BtLv& V, const double* __restrict__ ub, long x) {
+__device__ __forceinline__ void btp_veq(const Geom& g, const BtP& P, const BtLv& V, const double* __restrict__ ub, long x,
+                                        double pbc, double pbs) {
   using W = Wsel<WM>;
   const long s = g.ldi;
   const double vml = __ldcg(V.vb_ml + x), vnl = __ldcg(V.vb_nl + x);
@@ -282,7 +294,6 @@ __device__ __forceinline__ void btp_veq(const Geom& g, const BtP& P, const BtLv&
     q = -.25 * ((u00 * P.scuyi[x] + u0m * P.scuyi[x - s]) * wsum3<WM>(V, pvo0, pvm0, pvn0) +
                 (u10 * P.scuyi[x + 1] + u1m * P.scuyi[x + 1 - s]) * wsum3<WM>(V, pvo1, pvm1, pvn1));
   P.vbcors_t[x] = __ldcg(P.vbcors_t + x) + q;
-  const double pbc = __ldcg(V.pb_nl + x), pbs = __ldcg(V.pb_nl + x - s);
   const double t_o = W::o ? P.pgfym_o[x] - (P.xiyp_o[x] * pbc - P.xiym_o[x] * pbs) : 0.;
   const double t_m = W::m ? P.pgfym_m[x] - (P.xiyp_m[x] * pbc - P.xiym_m[x] * pbs) : 0.;
   const double t_n = W::n ? P.pgfym_n[x] - (P.xiyp_n[x] * pbc - P.xiym_n[x] * pbs) : 0.;
@@ -308,14 +319,21 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
   __syncthreads();
 }
 
-template <int THREADS, int MINBLK, int WM>
+template <int THREADS, int MINBLK, int WM, bool FUSE>
 __global__ void __launch_bounds__(THREADS, MINBLK)
 bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_t, double* vb_t, unsigned* ctr) {
+  // FUSED FORM (S.fuse): a substep is two phases instead of three.  The continuity equation is evaluated inside
+  // the first momentum phase: the thread of a cell computes the cell's new bottom pressure, stores it, and - if
+  // the cell's u (odd substeps) or v (even substeps) point is wet - recomputes the new pressure of the western
+  // (southern) neighbour from the same old fields to form the pressure gradient.  Same expression, same
+  // operands, so the values are those of the three-phase form; one grid barrier and one sweep over the plane
+  // per substep are gone.  The new pressure cannot overwrite the old/new level in place (the neighbour still
+  // needs the old value), so pb_t has a third level and the three rotate: (mid, old, spare) -> (spare, mid, old).
   unsigned target = 0;
   unsigned long long seq = S.seq0;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
   const long L = g.lev;
-  int ml = S.ml, nl = S.nl;
+  int ml = S.ml, nl = S.nl, pml = S.pml, pnl = S.pnl, psp = S.psp;
   BtLv V;
   // cells idx = tid, tid+nthr, ... of the range; body runs where mask == 1.  (i,j) of the thread's cells is
   // advanced incrementally: one 32-bit division per phase instead of a 64-bit division and modulo in front
@@ -336,9 +354,25 @@ bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_
       if (i >= ni) { i -= ni; ++j; }
     }
   };
+  // the same walk without a mask test, handing (x, i, j) to the body (fused first phase: two masks)
+  auto for_range_ij = [&](int i0, int i1, int j0, int j1, auto&& body) {
+    const int ni = i1 - i0 + 1;
+    const long n = (long)ni * (j1 - j0 + 1);
+    if (tid >= n) return;
+    const unsigned t0 = (unsigned)tid, un = (unsigned)ni, st = (unsigned)nthr;
+    int j = (int)(t0 / un), i = (int)(t0 - (unsigned)j * un);
+    const int dj = (int)(st / un), di = (int)(st - (unsigned)dj * un);
+    const int nj = j1 - j0 + 1;
+    while (j < nj) {
+      body(ix2(g, i0 + i, j0 + j), i0 + i, j0 + j);
+      i += di; j += dj;
+      if (i >= ni) { i -= ni; ++j; }
+    }
+  };
   for (int lll = S.lll0; lll < S.lll0 + S.nsub; ++lll) {
     V.wo = S.woa * lll + S.wob; V.wn = S.wna * lll + S.wnb; V.wm = 1. - V.wo - V.wn;
-    V.pb_ml = pb_t + (long)(ml - 1) * L; V.pb_nl = pb_t + (long)(nl - 1) * L;
+    V.pb_ml = pb_t + (long)(pml - 1) * L; V.pb_nl = pb_t + (long)(pnl - 1) * L;
+    double* const pb_new = FUSE ? pb_t + (long)(psp - 1) * L : V.pb_nl;
     V.ub_ml = ub_t + (long)(ml - 1) * L; V.ub_nl = ub_t + (long)(nl - 1) * L;
     V.vb_ml = vb_t + (long)(ml - 1) * L; V.vb_nl = vb_t + (long)(nl - 1) * L;
     if (lll % 2 == 1) {
@@ -355,11 +389,13 @@ bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_
             const int row = (int)(t / ii), i = (int)(t % ii) + 1;
             // rows 0..3: pb_t (lev1 r0,r1, lev2 r0,r1); 4..7: ub_t; 8..13: vb_t (3 rows per level)
             const double* a; int nh, rl;
-            if (row < 4) { a = pb_t; nh = 2; rl = row; } else if (row < 8) { a = ub_t; nh = 2; rl = row - 4; }
+            if (row < 4) { a = nullptr; nh = 2; rl = row; } else if (row < 8) { a = ub_t; nh = 2; rl = row - 4; }
             else { a = vb_t; nh = 3; rl = row - 8; }
             const int k = rl / nh, rr = rl % nh;
             const int j = dir == 0 ? 1 + rr : g.jj - nh + 1 + rr;
-            q[t] = __ldcg(a + (long)k * L + ix2(g, i, j));
+            // bottom pressure: "level 1" = the mid level, "level 2" = the old/new level (every rank rotates alike)
+            const double* lvl = a ? a + (long)k * L : (k == 0 ? V.pb_ml : V.pb_nl);
+            q[t] = __ldcg(lvl + ix2(g, i, j));
           }
         }
         if (tid < npay) __threadfence_system();   // only threads that stored to a peer
@@ -383,11 +419,12 @@ bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_
           for (long t = tid; t < npay; t += nthr) {
             const int row = (int)(t / ii), i = (int)(t % ii) + 1;
             double* a; int nh, rl;
-            if (row < 4) { a = pb_t; nh = 2; rl = row; } else if (row < 8) { a = ub_t; nh = 2; rl = row - 4; }
+            if (row < 4) { a = nullptr; nh = 2; rl = row; } else if (row < 8) { a = ub_t; nh = 2; rl = row - 4; }
             else { a = vb_t; nh = 3; rl = row - 8; }
             const int k = rl / nh, rr = rl % nh;
             const int j = dir == 0 ? 1 - nh + rr : g.jj + 1 + rr;
-            a[(long)k * L + ix2(g, i, j)] = __ldcg(q + t);
+            double* lvl = a ? a + (long)k * L : (k == 0 ? V.pb_ml : V.pb_nl);
+            lvl[ix2(g, i, j)] = __ldcg(q + t);
           }
         }
         grid_barrier(ctr, target);
@@ -396,26 +433,54 @@ bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_
       if (S.inkernel_halo) {
         // xctilr(pb_t,1,2,2,2,halo_ps), (ubflx_t,..,halo_uv), (vbflx_t,1,2,2,3,halo_vv)  (:395-397)
         for (int k = 1; k <= 2; ++k) {
-          halo_level<true>(g, pb_t + (long)(k - 1) * L, halo_ps, k, 2, 2, 1, 1, tid, nthr);
+          halo_level<true>(g, k == 1 ? V.pb_ml : V.pb_nl, halo_ps, k, 2, 2, 1, 1, tid, nthr);
           halo_level<true>(g, ub_t + (long)(k - 1) * L, halo_uv, k, 2, 2, 1, 1, tid, nthr);
           halo_level<true>(g, vb_t + (long)(k - 1) * L, halo_vv, k, 2, 3, 1, 1, tid, nthr);
         }
         grid_barrier(ctr, target);
       }
-      for_range(-1, g.ii + 1, -1, g.jj + 2, P.ip, [&](long x) { btp_continuity(g, P, V, x); });
-      grid_barrier(ctr, target);
-      for_range(0, g.ii + 1, -1, g.jj + 2, P.iu, [&](long x) { btp_ueq<WM>(g, P, V, V.vb_ml, x); });
-      grid_barrier(ctr, target);
-      for_range(0, g.ii, 0, g.jj + 2, P.iv, [&](long x) { btp_veq<WM>(g, P, V, V.ub_nl, x); });
+      if (FUSE) {
+        for_range_ij(-1, g.ii + 1, -1, g.jj + 2, [&](long x, int i, int j) {
+          const bool wu = i >= 0 && P.iu[x] == 1;
+          if (P.ip[x] != 1 && !wu) return;
+          const double pbc = btp_continuity_value(g, P, V, x);
+          if (P.ip[x] == 1) pb_new[x] = pbc;
+          if (wu) btp_ueq<WM>(g, P, V, V.vb_ml, x, pbc, btp_continuity_value(g, P, V, x - 1));
+        });
+        grid_barrier(ctr, target);
+      } else {
+        for_range(-1, g.ii + 1, -1, g.jj + 2, P.ip, [&](long x) { btp_continuity(g, P, V, x); });
+        grid_barrier(ctr, target);
+        for_range(0, g.ii + 1, -1, g.jj + 2, P.iu, [&](long x) {
+          btp_ueq<WM>(g, P, V, V.vb_ml, x, __ldcg(V.pb_nl + x), __ldcg(V.pb_nl + x - 1)); });
+        grid_barrier(ctr, target);
+      }
+      for_range(0, g.ii, 0, g.jj + 2, P.iv, [&](long x) {
+        btp_veq<WM>(g, P, V, V.ub_nl, x, __ldcg(pb_new + x), __ldcg(pb_new + x - g.ldi)); });
       grid_barrier(ctr, target);
     } else {
-      for_range(0, g.ii, 0, g.jj + 1, P.ip, [&](long x) { btp_continuity(g, P, V, x); });
-      grid_barrier(ctr, target);
-      for_range(0, g.ii, 1, g.jj + 1, P.iv, [&](long x) { btp_veq<WM>(g, P, V, V.ub_ml, x); });
-      grid_barrier(ctr, target);
-      for_range(1, g.ii, 1, g.jj, P.iu, [&](long x) { btp_ueq<WM>(g, P, V, V.vb_nl, x); });
+      if (FUSE) {
+        for_range_ij(0, g.ii, 0, g.jj + 1, [&](long x, int i, int j) {
+          const bool wv = j >= 1 && P.iv[x] == 1;
+          if (P.ip[x] != 1 && !wv) return;
+          const double pbc = btp_continuity_value(g, P, V, x);
+          if (P.ip[x] == 1) pb_new[x] = pbc;
+          if (wv) btp_veq<WM>(g, P, V, V.ub_ml, x, pbc, btp_continuity_value(g, P, V, x - g.ldi));
+        });
+        grid_barrier(ctr, target);
+      } else {
+        for_range(0, g.ii, 0, g.jj + 1, P.ip, [&](long x) { btp_continuity(g, P, V, x); });
+        grid_barrier(ctr, target);
+        for_range(0, g.ii, 1, g.jj + 1, P.iv, [&](long x) {
+          btp_veq<WM>(g, P, V, V.ub_ml, x, __ldcg(V.pb_nl + x), __ldcg(V.pb_nl + x - g.ldi)); });
+        grid_barrier(ctr, target);
+      }
+      for_range(1, g.ii, 1, g.jj, P.iu, [&](long x) {
+        btp_ueq<WM>(g, P, V, V.vb_nl, x, __ldcg(pb_new + x), __ldcg(pb_new + x - 1)); });
       grid_barrier(ctr, target);
     }
+    if (FUSE) { const int t3 = psp; psp = pnl; pnl = pml; pml = t3; }   // (mid, old, spare) -> (spare, mid, old)
+    else { const int t2 = pml; pml = pnl; pnl = t2; }
     const int t = ml; ml = nl; nl = t;
   }
 }
@@ -512,8 +577,11 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     throw std::runtime_error(" mommth = " + mommth + " is unsupported!");
   // the three subcycled fields (pb_t, ubflx_t, vbflx_t of phy/mod_barotp.F90:155-157, two time levels each) live in
   // one allocation so that one L2 access-policy window can cover them (see below)
-  double* bt_state = c.owned("barotp_state", 6);
-  double *pb_t = bt_state, *ub_t = bt_state + 2 * L, *vb_t = bt_state + 4 * L;
+  double* bt_state = c.owned("barotp_state", 7);
+  // pb_t has three levels: the fused form of the persistent kernel writes the new bottom pressure into a spare
+  // level and rotates (bt_subcycle); pbl = levels holding (mid, old/new, spare)
+  double *pb_t = bt_state, *ub_t = bt_state + 3 * L, *vb_t = bt_state + 5 * L;
+  int pbl[3] = {1, 2, 3};
   double *umaxb = c.owned("barotp_umaxb", 1), *uminb = c.owned("barotp_uminb", 1), *vmaxb = c.owned("barotp_vmaxb", 1),
          *vminb = c.owned("barotp_vminb", 1), *uglue = c.owned("barotp_uglue", 1), *vglue = c.owned("barotp_vglue", 1);
   const dim3 gint(cdiv(g.ii, 128), g.jj);
@@ -566,7 +634,7 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   H.scuy = c.dev("scuy"); H.scvx = c.dev("scvx");
 
   auto set_levels = [&](int ml, int nl) {
-    P.pb_ml = pb_t + (long)(ml - 1) * L; P.pb_nl = pb_t + (long)(nl - 1) * L;
+    P.pb_ml = pb_t + (long)(pbl[0] - 1) * L; P.pb_nl = pb_t + (long)(pbl[1] - 1) * L;
     P.ub_ml = ub_t + (long)(ml - 1) * L; P.ub_nl = ub_t + (long)(nl - 1) * L;
     P.vb_ml = vb_t + (long)(ml - 1) * L; P.vb_nl = vb_t + (long)(nl - 1) * L;
   };
@@ -577,12 +645,16 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
 
   // cooperative persistent form unless option barotp_kernel=phases asks for one launch per phase
   const bool persistent = c.option("barotp_kernel", "persistent") != "phases";
+  // two phases per substep (continuity inside the first momentum phase) unless barotp_fuse=0
+  const bool fuse = persistent && c.option("barotp_fuse", "1") != "0";
   // block shape of the persistent kernel: threads x resident blocks per SM fixes the register budget
   // (65536 / (threads*blocks)); development switch barotp_shape = "512x2" (64 regs) | "768x2" (40) | "1024x2" (32).
   // Measured at tnx0.25v4 in round 1: 256x2 29.6 ms, 512x2 22.7, 640x2 22.2, 768x2 21.5, 1024x2 21.6.
-  struct Shape { const char* name; const void* fn[4]; int threads; };
-#define BT_SHAPE(T, B) {#T "x" #B, {(const void*)bt_subcycle<T, B, W_ALL>, (const void*)bt_subcycle<T, B, W_NO_N>, \
-                                    (const void*)bt_subcycle<T, B, W_NO_O>, (const void*)bt_subcycle<T, B, W_ONLY_N>}, T}
+  struct Shape { const char* name; const void* fn[8]; int threads; };   // fn[wmode + 4*fuse]
+#define BT_SHAPE(T, B) {#T "x" #B, {(const void*)bt_subcycle<T, B, W_ALL, false>, (const void*)bt_subcycle<T, B, W_NO_N, false>,   \
+                                    (const void*)bt_subcycle<T, B, W_NO_O, false>, (const void*)bt_subcycle<T, B, W_ONLY_N, false>, \
+                                    (const void*)bt_subcycle<T, B, W_ALL, true>, (const void*)bt_subcycle<T, B, W_NO_N, true>,     \
+                                    (const void*)bt_subcycle<T, B, W_NO_O, true>, (const void*)bt_subcycle<T, B, W_ONLY_N, true>}, T}
   static const Shape shapes[] = {BT_SHAPE(512, 2), BT_SHAPE(768, 2), BT_SHAPE(1024, 2)};
 #undef BT_SHAPE
   // default: 768x2 where every thread walks several cells per phase (1.67 M points at tnx0.25v4: 21.5 ms
@@ -617,6 +689,7 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   for (int nb = 1; nb <= 5; ++nb) {
     if (nb == 1) {
       lll0 = 1; ml = 1; nl = 2;
+      pbl[0] = 1; pbl[1] = 2; pbl[2] = 3;
       woa = -1. / lstep; wob = .5 + (lll0 - .5) / lstep; wna = 0.; wnb = 0.;
       LAUNCH(bt_init_block1, gint, 128, 0, g, c.dev("pb_mn"), c.dev("ubflx_mn"), c.dev("vbflx_mn"), pb_t, ub_t, vb_t);
     } else if (nb == 2) {
@@ -636,6 +709,7 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
       while (lll < lend) {
         BtSched S{};
         S.lll0 = lll; S.ml = ml; S.nl = nl; S.woa = woa; S.wob = wob; S.wna = wna; S.wnb = wnb;
+        S.pml = pbl[0]; S.pnl = pbl[1]; S.psp = pbl[2]; S.fuse = fuse ? 1 : 0;
         P2PView X{};
         if (g.nranks == 1) { S.nsub = lend - lll; S.inkernel_halo = 1; }
         else if (p2p_view(&X, (size_t)14 * g.ii)) {
@@ -646,7 +720,8 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
         } else {
           S.inkernel_halo = 0;
           if (lll % 2 == 1) {
-            halo_update(std::vector<HaloReq>{{pb_t, 2, halo_ps}, {ub_t, 2, halo_uv}}, 2, 2);
+            halo_update(std::vector<HaloReq>{{pb_t + (long)(pbl[0] - 1) * L, 1, halo_ps}, {pb_t + (long)(pbl[1] - 1) * L, 1, halo_ps},
+                                             {ub_t, 2, halo_uv}}, 2, 2);
             halo_update(vb_t, 2, 2, 3, halo_vv);
             S.nsub = std::min(2, lend - lll);
           } else S.nsub = 1;
@@ -654,9 +729,13 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
         CUDA_CHECK(cudaMemsetAsync(bar_ctr, 0, sizeof(unsigned), c.stream));
         void* args[] = {(void*)&g, (void*)&P, (void*)&S, (void*)&X, (void*)&pb_t, (void*)&ub_t, (void*)&vb_t, (void*)&bar_ctr};
         // time-weight pattern of this block (see Wsel): block 1 wn = 0; blocks 2,3 wo = 0; blocks 4,5 wn = 1
-        const int wmode = !wskip ? W_ALL : (nb == 1 ? W_NO_N : (nb <= 3 ? W_NO_O : W_ONLY_N));
+        const int wmode = (!wskip ? W_ALL : (nb == 1 ? W_NO_N : (nb <= 3 ? W_NO_O : W_ONLY_N))) + (fuse ? 4 : 0);
         launch_cooperative("bt_subcycle", shape->fn[wmode], coop_grid_of(wmode), shape->threads, args);
         if (S.nsub % 2 == 1) std::swap(ml, nl);
+        for (int q = 0; q < S.nsub; ++q) {
+          if (fuse) { const int t3 = pbl[2]; pbl[2] = pbl[1]; pbl[1] = pbl[0]; pbl[0] = t3; }
+          else std::swap(pbl[0], pbl[1]);
+        }
         lll += S.nsub;
       }
     } else {
@@ -664,7 +743,8 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
         P.wo = woa * lll + wob; P.wn = wna * lll + wnb; P.wm = 1. - P.wo - P.wn;
         set_levels(ml, nl);
         if (lll % 2 == 1) {
-          halo_update(std::vector<HaloReq>{{pb_t, 2, halo_ps}, {ub_t, 2, halo_uv}}, 2, 2);
+          halo_update(std::vector<HaloReq>{{pb_t + (long)(pbl[0] - 1) * L, 1, halo_ps}, {pb_t + (long)(pbl[1] - 1) * L, 1, halo_ps},
+                                           {ub_t, 2, halo_uv}}, 2, 2);
           halo_update(vb_t, 2, 2, 3, halo_vv);
           {
             dim3 grid(cdiv(g.ii + 3, 128), g.jj + 4);
@@ -681,6 +761,7 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
           range_launch("bt_ueq", bt_ueq, P.vb_nl, 1, g.ii, 1, g.jj);
         }
         std::swap(ml, nl);
+        std::swap(pbl[0], pbl[1]);
       }
     }
     lll0 = lll0 + lstep / 2;

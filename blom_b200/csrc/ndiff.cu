@@ -209,8 +209,11 @@ struct SideAcc {
 };
 
 // ndiff_flx (:160-953) for the face between cell M (i-1|j-1) and cell P (i,j)
-template <int DIR, int NT, int MINB, bool PF>
-__global__ void __launch_bounds__(128, MINB)
+// BS threads per block at a register budget of 128 per thread (512 resident threads per SM): a block holds its
+// SM slot until its slowest warp is done and the warps' run times differ widely (every lane follows its own
+// column), so smaller blocks pack the SMs better (development switch ndiff_block = 128 | 64 | 32).
+template <int DIR, int NT, int BS, bool PF>
+__global__ void __launch_bounds__(BS, 512 / BS)
 ndiff_face(Geom g, NdArgs A) {
   // wet faces only: thread t owns face A.faces[t] (linear (i,j) offset of the face's plus-side cell).  A thread
   // of a land face would idle for the whole life of its warp - the kernel is issue- and latency-bound, so the
@@ -442,9 +445,9 @@ ndiff_face(Geom g, NdArgs A) {
     constexpr bool CACHE = NT > 0 && NT <= 3;     // register budget: 10 doubles per scalar
     // the cache lives in shared memory, one column of 5*NT doubles per thread and side ([..][threadIdx.x],
     // conflict-free): in registers its 40 values pushed the searches' state into spills at 128 registers
-    __shared__ double cf_sm[CACHE ? 2 * NTC * 5 : 1][128];
+    __shared__ double cf_sm[CACHE ? 2 * NTC * 5 : 1][BS];
     struct CoefRef {   // the five coefficients of scalar nt of one side, as the polynomial helpers read them
-      const double (*col)[128]; int t;
+      const double (*col)[BS]; int t;
       __device__ __forceinline__ double operator[](int c5) const { return col[c5][t]; }
     };
     auto cfm = [&](int nt) { return CoefRef{&cf_sm[CACHE ? (nt - 1) * 5 : 0], (int)threadIdx.x}; };
@@ -453,7 +456,7 @@ ndiff_face(Geom g, NdArgs A) {
     auto coef = [&](const Col& c, int k, int nt, int row0) {
       const double* b5 = c.tpc + (long)(((nt - 1) * kk + k - 1) * 5) * lev;
       const double c0 = b5[0], c1 = b5[lev], c2 = b5[2 * lev], c3 = b5[3 * lev], c4 = b5[4 * lev];
-      double(*o)[128] = &cf_sm[CACHE ? row0 : 0];
+      double(*o)[BS] = &cf_sm[CACHE ? row0 : 0];
       const int t = threadIdx.x;
       o[0][t] = c0; o[1][t] = c1; o[2][t] = c2; o[3][t] = c3; o[4][t] = c4;
     };
@@ -898,24 +901,28 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   }
   U.faces = list_u; U.nfaces = (int)c.sc["_nd_nfaces_u"];
   V.faces = list_v; V.nfaces = (int)c.sc["_nd_nfaces_v"];
-  const dim3 gu(std::max(1, cdiv(U.nfaces, 128))), gv(std::max(1, cdiv(V.nfaces, 128)));
-  // resident blocks per SM (register budget 65536/(128*MINB)): development switch ndiff_minblk = 3 | 4 | 5
-  // (tnx1v4, one direction: 2 blocks 10.4 ms, 3 blocks 8.4 ms, 4 blocks 7.3 ms)
   // ndiff_prefetch=1: L1 prefetch of the operands a few iterations ahead; measured 5 % slower at tnx1v4 (14.2 vs 13.6 ms), off
   const bool pf = c.option("ndiff_prefetch", "0") == "1";
-#define ND_FACE(NT_)                                                                                   \
-  OCC_DISPATCH3("ndiff_minblk", 4, 3, 4, 5,                                                            \
-                if (pf) {                                                                              \
-                  LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, OCC, true>), gu, 128, 0, g, U);    \
-                  LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, NT_, OCC, true>), gv, 128, 0, g, V);    \
-                } else {                                                                               \
-                  LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, OCC, false>), gu, 128, 0, g, U);   \
-                  LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, NT_, OCC, false>), gv, 128, 0, g, V);   \
-                })
+  const int bs = std::stoi(c.option("ndiff_block", "128"));
+  if (bs != 128 && bs != 64 && bs != 32) throw std::runtime_error("ndiff: ndiff_block must be 128, 64 or 32");
+  const dim3 gu(std::max(1, cdiv(U.nfaces, bs))), gv(std::max(1, cdiv(V.nfaces, bs)));
+#define ND_LAUNCH(NT_, BS_, PF_)                                                                  \
+  do {                                                                                            \
+    LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, BS_, PF_>), gu, BS_, 0, g, U);              \
+    LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, NT_, BS_, PF_>), gv, BS_, 0, g, V);              \
+  } while (0)
+#define ND_FACE(NT_)                                                                              \
+  do {                                                                                            \
+    if (pf) ND_LAUNCH(NT_, 128, true);                                                            \
+    else if (bs == 64) ND_LAUNCH(NT_, 64, false);                                                 \
+    else if (bs == 32) ND_LAUNCH(NT_, 32, false);                                                 \
+    else ND_LAUNCH(NT_, 128, false);                                                              \
+  } while (0)
   if (T == 2) { ND_FACE(2); }
   else if (T == 3) { ND_FACE(3); }
   else { ND_FACE(0); }
 #undef ND_FACE
+#undef ND_LAUNCH
   LAUNCH(ndiff_update, dim3(cdiv(g.ii, 256), g.jj, kk), 256, 0, g, T, c.idev("ip"), c.idev("iu"), c.idev("iv"),
          c.dev("scp2"), c.dev("nd_p_dst"), ucm, ucp, vcm, vcp, c.dev("nd_trc_rm"));
 }
