@@ -1038,7 +1038,7 @@ void momtum_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 4, 128), g.jj + 4, g.kdm)); OCC_DISPATCH3("mt_aux_minblk", 12, 12, 14, 16, LAUNCH_NAMED("mt_aux", mt_aux<OCC>, grid, 128, 0, g, P)); }
     { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 3, 128), g.jj + 3, g.kdm)); OCC_DISPATCH3("mt_vort_minblk", 12, 7, 12, 16, LAUNCH_NAMED("mt_vort", mt_vort<OCC>, grid, 128, 0, g, P)); }
     { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 2, 128), g.jj + 2, g.kdm)); LAUNCH(mt_visc, grid, 128, 0, g, P); }
-    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 1, 128), g.jj + 1, g.kdm)); OCC_DISPATCH3("mt_flux1_minblk", 12, 12, 14, 16, LAUNCH_NAMED("mt_flux1", mt_flux1<OCC>, grid, 128, 0, g, P)); }
+    { const dim3 grid = lgrid(g, dim3(cdiv(g.ii + 1, 128), g.jj + 1, g.kdm)); OCC_DISPATCH3("mt_flux1_minblk", 16, 12, 14, 16, LAUNCH_NAMED("mt_flux1", mt_flux1<OCC>, grid, 128, 0, g, P)); }
     { const dim3 grid = lgrid(g, dim3(cdiv(g.ii, 128), g.jj, g.kdm));
       OCC_DISPATCH3("momtum_minblk", 12, 7, 12, 16,
                     LAUNCH_NAMED("mt_update", mt_update<OCC>, grid, 128, 0, g, P);

@@ -298,7 +298,11 @@ void pbcor_run(int m, int n, int mm, int nn, int k1m) {
     for (size_t gi = 0; gi < groups.size(); ++gi) {
       const PbTr TG = groups[gi];
       const int EXTRA = gi > 0 ? 1 : 0;
-      OCC_DISPATCH3("pbcor_minblk", 4, 3, 4, 5, if (dluc) PB_LAUNCH(true); else PB_LAUNCH(false));
+      // resident blocks: the depth-limited branch (dluc, the hybrid default) carries the four faces' interface
+      // pressures as well and wants the registers of 3 blocks (tnx0.25v4, pbcor1/2: 3 blocks 3.76/3.89 ms, 4 blocks
+      // 4.41/4.83, 5 blocks 6.12/6.67); uc runs best with 4 (round 1)
+      if (dluc) { OCC_DISPATCH3("pbcor_minblk", 3, 2, 3, 4, PB_LAUNCH(true)); }
+      else { OCC_DISPATCH3("pbcor_minblk", 4, 3, 4, 5, PB_LAUNCH(false)); }
       if (EXTRA) {
         dim3 gridf(cdiv(g.ii, 128), g.jj, kk);
         LAUNCH(pbcor_finish_tracers, gridf, 128, 0, g, ks, ip, TG);
