@@ -482,6 +482,12 @@ def main():
              "avg_launch_us": dur * 1e6, "share_of_step": v["ms"] / ksum, "algorithmic_bytes_per_launch": nbytes}
         if name in KERNEL_SCRATCH_WORDS:
             r["scratch_words_not_counted"] = KERNEL_SCRATCH_WORDS[name]
+        if name.startswith("ndiff_face"):
+            r["note"] = ("not a bandwidth kernel: one thread per face column runs the reference's two sequential, "
+                         "data-dependent searches (phy/mod_ndiff.F90:160-953, ~250 k thread instructions per face); "
+                         "issue- and latency-bound (ncu: IPC 1.2 of 4, 15 of 32 lanes active, 9 % of the DRAM peak; "
+                         "profiles/r02_ncu_full_ndiff_face.txt) - the HBM fraction is reported because the contract "
+                         "asks for one")
         if unit == "bt":
             ws_mb = 8.0 * w * cells2d_local / 1e6
             r["note"] = (f"streamed model ({w} words per 2-D point and substep, see BT_WORDS_PER_SUBSTEP); 2-D working set {ws_mb:.0f} MB "
