@@ -355,3 +355,32 @@ def test_budget_conserved_through_transport_and_diffusion(cfg):
         assert mid != before   # the fields did move
     finally:
         g.finalize()
+
+
+def test_init_again_without_finalize_starts_clean():
+    """A host that aborts half way and calls blomgpu_init again (no finalize) must not inherit device arrays sized
+    for the previous tile: the second, LARGER tile runs pgforc + momtum and matches the oracle (a stale, too small
+    allocation would be a device heap overflow)."""
+    small = Case("tiny0", ntr=1)
+    g0 = small.new_gpu(parity=True)
+    g0.inieos(); g0.pgforc(*small.levels)
+    # no g0.finalize(): same library context, new geometry
+    c, o, g = pair("mid2", ntr=1, opts={"vcoord": "cntiso_hybrid"})
+    try:
+        for b in (o, g):
+            b.numerical_bounds()
+            b.pgforc(*c.levels)
+            b.momtum(*c.levels)
+        check(g, o, ["u", "v", "pgfx", "pgfy", "dpu", "dpv"], 1e-11)
+    finally:
+        g.finalize()
+
+
+def test_comm_errors_reach_last_error():
+    """blomgpu_comm_* report through blomgpu_last_error like every other entry (a 1-rank communicator from a
+    garbage id must fail, not hang: NCCL rejects the id during bootstrap or the rank count)."""
+    from blom_b200.lib import load_library
+    lib = load_library(True)
+    rc = lib.blomgpu_comm_init(b"\0" * 128, 3, 2)      # rank 3 of 2: invalid argument, returns at once
+    assert rc != 0
+    assert b"NCCL" in lib.blomgpu_last_error() or b"nccl" in lib.blomgpu_last_error()
