@@ -42,7 +42,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 from blom_b200 import synth  # noqa: E402
-from blom_b200.driver import HotPath, reference_options, run_step, step_routines  # noqa: E402
+from blom_b200.driver import HotPath, balanced_band, reference_options, run_step, step_routines  # noqa: E402
 
 METRIC = "simulated_years_per_day_hot_path"
 
@@ -449,6 +449,11 @@ def main():
     kt = g.ktimers()
     g.ktimers_enable(False)
 
+    # per-rank routine times (N > 1): the slowest rank sets the pace, rank 0's own times hide the imbalance
+    ranks_rt = None
+    if dist is not None:
+        ranks_rt = [None] * world
+        dist.all_gather_object(ranks_rt, {k: v["ms"] / v["calls"] for k, v in rt.items() if v["calls"]})
     if rank != 0:
         hp.finalize()
         if dist is not None:
@@ -532,6 +537,8 @@ def main():
         "step_algorithmic_GBps": alg_bytes / t_step / 1e9,
         "step_frac_of_hbm_peak": alg_bytes / t_step / 1e9 / hbm_peak,
         "routines_ms": routines_ms,
+        **({"routines_ms_max_over_ranks": {k: max(r.get(k, 0.0) for r in ranks_rt) for k in routines_ms},
+            "rows_per_rank": [balanced_band(args.config, r, world)[1] for r in range(world)]} if ranks_rt else {}),
         "kernels_ms_per_step": {k: v["ms"] / 2.0 for k, v in sorted(kt.items(), key=lambda kv: -kv[1]["ms"])},
     }
     # the GPU measurement is complete: release the device, then run the legs that may fail

@@ -161,13 +161,16 @@ bool p2p_setup(size_t cap) {
   return true;
 }
 
-// pack the edge rows of every request into the neighbour's mailbox; the last block to finish
-// publishes `seq` in the neighbour's flag word.  blockIdx.z = request, blockIdx.y = level,
-// gridDim.x blocks per level; dir 0: rows 1..nhl go south, dir 1: rows jj-nhl+1..jj go north.
-__global__ void p2p_push(Geom g, XBatch b, int nhl, int dir, char* my_block, char* peer_block, size_t cap, int parity,
-                         unsigned long long seq, unsigned long long done_target) {
-  const int r = blockIdx.z, k = blockIdx.y;
-  if (r < b.n && k < b.nlev[r]) {
+// pack the edge rows of every request into the neighbours' mailboxes; per direction the last block to finish
+// publishes `seq` in that neighbour's flag word.  One launch serves both neighbours: blockIdx.z = dir * b.n +
+// request, blockIdx.y = level, gridDim.x blocks per level; dir 0: rows 1..nhl go south, dir 1: rows
+// jj-nhl+1..jj go north.  Blocks of a direction without neighbour return at once and are not counted.
+__global__ void p2p_push(Geom g, XBatch b, int nhl, char* my_block, char* peer_s, char* peer_n, size_t cap, int parity,
+                         unsigned long long seq, unsigned long long done_target_s, unsigned long long done_target_n) {
+  const int dir = blockIdx.z / b.n, r = blockIdx.z % b.n, k = blockIdx.y;
+  char* peer_block = dir == 0 ? peer_s : peer_n;
+  if (!peer_block) return;
+  if (k < b.nlev[r]) {
     const double* a = b.base[r] + (long)k * g.lev;
     // data sent south lands in the neighbour's "from north" slot (1) and vice versa
     double* q = p2p_slot(peer_block, cap, 1 - dir, parity) + b.off[r] + (long)k * nhl * g.ii;
@@ -182,7 +185,7 @@ __global__ void p2p_push(Geom g, XBatch b, int nhl, int dir, char* my_block, cha
   if (threadIdx.x == 0) {
     unsigned long long* done = p2p_word(my_block, 2 + dir);
     const unsigned long long prev = atomicAdd(done, 1ull);
-    if (prev + 1 == done_target) {   // cumulative count of all pushes so far in this direction
+    if (prev + 1 == (dir == 0 ? done_target_s : done_target_n)) {   // cumulative count of all pushes so far in this direction
       __threadfence_system();
       *(volatile unsigned long long*)p2p_word(peer_block, 1 - dir) = seq;
       __threadfence_system();
@@ -190,17 +193,18 @@ __global__ void p2p_push(Geom g, XBatch b, int nhl, int dir, char* my_block, cha
   }
 }
 
-// wait for the neighbour's rows of exchange `seq`, then unpack them into the halo rows
-__global__ void p2p_unpack(Geom g, XBatch b, int nhl, int dir, char* my_block, size_t cap, int parity,
+// wait for the neighbours' rows of exchange `seq`, then unpack them into the halo rows (both sides in one launch)
+__global__ void p2p_unpack(Geom g, XBatch b, int nhl, int has_s, int has_n, char* my_block, size_t cap, int parity,
                            unsigned long long seq) {
+  const int dir = blockIdx.z / b.n, r = blockIdx.z % b.n, k = blockIdx.y;
+  if (!(dir == 0 ? has_s : has_n)) return;
   if (threadIdx.x == 0) {
     volatile unsigned long long* flag = p2p_word(my_block, dir);
     while (*flag < seq) {}
     __threadfence_system();
   }
   __syncthreads();
-  const int r = blockIdx.z, k = blockIdx.y;
-  if (r >= b.n || k >= b.nlev[r]) return;
+  if (k >= b.nlev[r]) return;
   double* a = b.base[r] + (long)k * g.lev;
   const double* q = p2p_slot(my_block, cap, dir, parity) + b.off[r] + (long)k * nhl * g.ii;
   const int j_first = dir == 0 ? 1 - nhl : g.jj + 1;   // dir 0: rows from the south neighbour
@@ -240,12 +244,13 @@ bool exchange_ns_p2p(const XBatch& b, long tot, int maxlev, int nhl) {
   const bool has_s = g.rank > 0, has_n = g.rank + 1 < g.nranks;
   const unsigned long long seq = p2p_reserve_seq(1);
   const int parity = (int)(seq & 1ull);
-  dim3 grid(std::max(1, std::min(cdiv((long)nhl * g.ii, 256), 32)), maxlev, b.n);
-  const unsigned nblk = grid.x * grid.y * grid.z;
-  if (has_s) { q.done_target[0] += nblk; LAUNCH(p2p_push, grid, 256, 0, g, b, nhl, 0, q.block, q.peer[0], q.cap, parity, seq, q.done_target[0]); }
-  if (has_n) { q.done_target[1] += nblk; LAUNCH(p2p_push, grid, 256, 0, g, b, nhl, 1, q.block, q.peer[1], q.cap, parity, seq, q.done_target[1]); }
-  if (has_s) LAUNCH(p2p_unpack, grid, 256, 0, g, b, nhl, 0, q.block, q.cap, parity, seq);
-  if (has_n) LAUNCH(p2p_unpack, grid, 256, 0, g, b, nhl, 1, q.block, q.cap, parity, seq);
+  dim3 grid(std::max(1, std::min(cdiv((long)nhl * g.ii, 256), 32)), maxlev, 2 * b.n);   // both directions in one launch
+  const unsigned nblk = grid.x * grid.y * b.n;
+  if (has_s) q.done_target[0] += nblk;
+  if (has_n) q.done_target[1] += nblk;
+  LAUNCH(p2p_push, grid, 256, 0, g, b, nhl, q.block, has_s ? q.peer[0] : nullptr, has_n ? q.peer[1] : nullptr, q.cap,
+         parity, seq, q.done_target[0], q.done_target[1]);
+  LAUNCH(p2p_unpack, grid, 256, 0, g, b, nhl, has_s ? 1 : 0, has_n ? 1 : 0, q.block, q.cap, parity, seq);
   return true;
 }
 
