@@ -7,10 +7,14 @@
 // a 2(3)-wide halo exactly like the reference (:395-397), so the odd substep
 // runs on the widened ranges and the even one on the interior.
 //
-// Kernel structure: each phase is one launch over the 2-D domain with i across
-// lanes; the many read-only coefficient arrays stay L2-resident across the
-// substeps at 1 degree (working set ~58 MB < 126 MB L2).  All pointers travel in
-// one by-value parameter block.
+// Kernel structure: one persistent cooperative launch per block of substeps
+// (bt_subcycle: phases separated by grid barriers, in-kernel E/W + fold halos and,
+// on several GPUs, in-kernel peer-to-peer band edges), i across lanes.  Two
+// phases per substep: the continuity equation is evaluated inside the first
+// momentum phase.  Arrays whose time weight is zero in a block are not read.
+// The launch-per-phase form (bt_continuity / bt_ueq / bt_veq, option
+// barotp_kernel=phases) is kept as the plain statement of the same operations.
+// All pointers travel in one by-value parameter block.
 #include "common.cuh"
 #include "halo.cuh"
 #include "p2p.cuh"
@@ -191,13 +195,15 @@ __global__ void bt_veq(Geom g, BtP P, const double* __restrict__ ub, int i0, int
 }
 
 // ---- persistent form of the subcycle ------------------------------------------------------------
-// One cooperative launch runs a whole block of lstep/2 substeps: the three phases of a substep
-// (continuity, first and second momentum equation) and, on one tile, the halo refresh of the
-// subcycled fields are separated by grid-wide barriers instead of kernel boundaries.  Read-write
+// One cooperative launch runs a whole block of lstep/2 substeps: the phases of a substep (continuity
+// + first momentum equation, second momentum equation; three phases with barotp_fuse=0) and, on one
+// tile, the halo refresh of the subcycled fields are separated by grid-wide barriers instead of kernel
+// boundaries.  Read-write
 // fields are read with ld.global.cg (L1 is not coherent between the SMs of one launch); the ~40
 // read-only coefficient arrays use the normal cached path.  Operation order per cell is the one of
 // bt_continuity / bt_ueq / bt_veq above, so results are bit-identical to the launch-per-phase form.
-#define BT_SHAPE_DEFAULT "768x2"   // measured at tnx0.25v4: 512x2 22.7 ms, 640x2 22.2, 768x2 21.5, 1024x2 21.6, 256x2 29.6
+#define BT_SHAPE_DEFAULT "768x2"   // tnx0.25v4, round 1: 512x2 22.7 ms, 640x2 22.2, 768x2 21.5, 1024x2 21.6, 256x2 29.6;
+                                   // round 2 (zero-weight skip + two phases): 512x2 18.5, 768x2 18.6, 1024x2 27.7
 
 struct BtSched {
   int lll0, nsub, ml, nl;
@@ -322,7 +328,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
 template <int THREADS, int MINBLK, int WM, bool FUSE>
 __global__ void __launch_bounds__(THREADS, MINBLK)
 bt_subcycle(Geom g, const BtP P, BtSched S, P2PView X, double* pb_t, double* ub_t, double* vb_t, unsigned* ctr) {
-  // FUSED FORM (S.fuse): a substep is two phases instead of three.  The continuity equation is evaluated inside
+  // FUSED FORM (template FUSE, option barotp_fuse): a substep is two phases instead of three.  The continuity equation is evaluated inside
   // the first momentum phase: the thread of a cell computes the cell's new bottom pressure, stores it, and - if
   // the cell's u (odd substeps) or v (even substeps) point is wet - recomputes the new pressure of the western
   // (southern) neighbour from the same old fields to form the pressure gradient.  Same expression, same

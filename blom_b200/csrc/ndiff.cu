@@ -23,6 +23,14 @@
 //                 order (south v face, west u face, east u face, north v face) and updates trc_rm.
 // The only floating-point reassociation against the reference is that several contributions of one
 // face to the same destination layer are summed before they meet the cell's running total.
+//
+// ndiff_face is issue- and latency-bound (every lane follows its own column; ~250 k thread instructions
+// per face), not bandwidth-bound, so what makes it fast is fewer instructions and more lanes on the same
+// path (profiles/r02_ncu_full_ndiff_face.txt): interface records of one sector,
+// the neutral slope interpolated on the fly instead of from stored lists, polynomial coefficients of the
+// current layers cached in shared memory, binned face fluxes summed in registers, the mirrored
+// minus-/plus-column code blocks of the reference written once with the column chosen per lane, and
+// compacted lists of the wet faces.
 #include "common.cuh"
 #include "eos.cuh"
 
@@ -48,16 +56,17 @@ __device__ __forceinline__ double eos_drhods(double p, double th, double s) {
   return (EA13 + EA15 * th + 2. * EA16 * s + EB13 * p - (EA23 + EA25 * th + 2. * EA26 * s + EB23 * p) * r1 * r2i) * r2i;
 }
 
+// Non-binding L1 prefetch.  Every thread walks its two columns strictly downwards, so the addresses it will
+// load a few iterations later are known; the searches are chains of dependent loads (ncu: 57 % of the stall
+// samples on the long scoreboard at 13 resident warps per SM), and a prefetch issued a few iterations ahead
+// would turn the later demand load into an L1 hit.  Measured 5 % SLOWER (tnx1v4: 14.2 vs 13.6 ms), so it is off;
+// switch: template parameter PF (option ndiff_prefetch=1).
+__device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // Packed record of one source-layer interface of one cell column: {drhodt, drhods, T, S} at (is,k), 32 bytes =
 // one memory sector.  The first search evaluates the density difference between two interfaces at every step
 // and its lanes sit at different layers, so four separate level-strided arrays cost four sectors per lane
 // where the record costs one.  Layout: record ((k-1)*2+is-1) of cell x at rec[(((k-1)*2+is-1)*lev + x)*4].
-// Non-binding L1 prefetch.  Every thread walks its two columns strictly downwards, so the addresses it will
-// load a few iterations later are known; the searches are chains of dependent loads (ncu: 57 % of the stall
-// samples on the long scoreboard at 13 resident warps per SM), and a prefetch issued a few iterations ahead
-// turns the later demand load into an L1 hit.  Switch: template parameter PF (option ndiff_prefetch).
-__device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 struct NdArgs {
   const double *p_src, *tsd, *tpc, *rec, *p_dst, *snp;
   const int *ksmx, *kdmx, *mask;
