@@ -662,6 +662,7 @@ void barotp_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
                                     (const void*)bt_subcycle<T, B, W_ALL, true>, (const void*)bt_subcycle<T, B, W_NO_N, true>,     \
                                     (const void*)bt_subcycle<T, B, W_NO_O, true>, (const void*)bt_subcycle<T, B, W_ONLY_N, true>}, T}
   static const Shape shapes[] = {BT_SHAPE(512, 2), BT_SHAPE(768, 2), BT_SHAPE(1024, 2)};
+  // (small grids, tnx1v4, two-phase form: 512x2 1.76 ms, 1024x1 1.93, 384x2 1.99, 768x2 2.28)
 #undef BT_SHAPE
   // default: 768x2 where every thread walks several cells per phase (1.67 M points at tnx0.25v4: 21.5 ms
   // against 22.7 for 512x2), 512x2 (no spills) where a phase is a single cell per thread and the time
