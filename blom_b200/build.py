@@ -35,8 +35,13 @@ def _newer(src: Path, dst: Path, extra: list[Path]) -> bool:
     return any(p.stat().st_mtime > t for p in [src, *extra])
 
 
+# per-file extra flags (development experiments: BLOM_EXTRA_<STEM>="-Xptxas -dlcm=cg")
+def _extra(src: Path) -> list[str]:
+    return os.environ.get("BLOM_EXTRA_" + src.stem.upper(), "").split()
+
+
 def _compile(src: Path, obj: Path, flags: list[str], log: Path) -> None:
-    cmd = [NVCC, *ARCH, *COMMON, *flags, "-c", str(src), "-o", str(obj)]
+    cmd = [NVCC, *ARCH, *COMMON, *flags, *_extra(src), "-c", str(src), "-o", str(obj)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.write_text(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
