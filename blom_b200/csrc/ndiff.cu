@@ -61,7 +61,11 @@ __device__ __forceinline__ double eos_drhods(double p, double th, double s) {
 // samples on the long scoreboard at 13 resident warps per SM), and a prefetch issued a few iterations ahead
 // would turn the later demand load into an L1 hit.  Measured 5 % SLOWER (tnx1v4: 14.2 vs 13.6 ms), so it is off;
 // switch: template parameter PF (option ndiff_prefetch=1).
+#ifdef BLOM_HOST_EMUL   // tests/emul: the kernels of this file compiled for the host, one emulated thread at a time
+__device__ __forceinline__ void pf_l1(const void*) {}
+#else
 __device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
 
 // Packed record of one source-layer interface of one cell column: {drhodt, drhods, T, S} at (is,k), 32 bytes =
 // one memory sector.  The first search evaluates the density difference between two interfaces at every step
@@ -836,6 +840,7 @@ ndiff_update(Geom g, int T, const int* __restrict__ ip, const int* __restrict__ 
 
 }  // namespace
 
+#ifndef BLOM_HOST_EMUL
 // neutral diffusion over the whole tile in the order of the reference's slice pipeline
 // (phy/mod_ale_regrid_remap.F90:1607-1690)
 void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
@@ -935,5 +940,6 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   LAUNCH(ndiff_update, dim3(cdiv(g.ii, 256), g.jj, kk), 256, 0, g, T, c.idev("ip"), c.idev("iu"), c.idev("iv"),
          c.dev("scp2"), c.dev("nd_p_dst"), ucm, ucp, vcm, vcp, c.dev("nd_trc_rm"));
 }
+#endif  // BLOM_HOST_EMUL
 
 }  // namespace blom
