@@ -56,17 +56,6 @@ __device__ __forceinline__ double eos_drhods(double p, double th, double s) {
   return (EA13 + EA15 * th + 2. * EA16 * s + EB13 * p - (EA23 + EA25 * th + 2. * EA26 * s + EB23 * p) * r1 * r2i) * r2i;
 }
 
-// Non-binding L1 prefetch.  Every thread walks its two columns strictly downwards, so the addresses it will
-// load a few iterations later are known; the searches are chains of dependent loads (ncu: 57 % of the stall
-// samples on the long scoreboard at 13 resident warps per SM), and a prefetch issued a few iterations ahead
-// would turn the later demand load into an L1 hit.  Measured 5 % SLOWER (tnx1v4: 14.2 vs 13.6 ms), so it is off;
-// switch: template parameter PF (option ndiff_prefetch=1).
-#ifdef BLOM_HOST_EMUL   // tests/emul: the kernels of this file compiled for the host, one emulated thread at a time
-__device__ __forceinline__ void pf_l1(const void*) {}
-#else
-__device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#endif
-
 // Packed record of one source-layer interface of one cell column: {drhodt, drhods, T, S} at (is,k), 32 bytes =
 // one memory sector.  The first search evaluates the density difference between two interfaces at every step
 // and its lanes sit at different layers, so four separate level-strided arrays cost four sectors per lane
@@ -85,52 +74,19 @@ struct NdArgs {
   int mm, T, surface_align;
 };
 
-// one cell column with the reference's 1-based indices
 struct Rec { double drdt, drds, t, s; };
-struct Col {
-  const double *p_src, *tsd, *tpc, *rec, *p_dst, *snp;
-  long lev; int kk;
-  __device__ __forceinline__ Rec record(int s, int k) const {
-    const double2* r = reinterpret_cast<const double2*>(rec + (long)((k - 1) * 2 + s - 1) * lev * 4);
-    const double2 a = r[0], b = r[1];
-    return Rec{a.x, a.y, b.x, b.y};
-  }
-  __device__ __forceinline__ double psd(int s, int k) const { return p_src[(long)(k + s - 2) * lev]; }
-  __device__ __forceinline__ double tsrcdi(int s, int k, int nt) const { return tsd[(long)(((nt - 1) * kk + k - 1) * 2 + s - 1) * lev]; }
-  __device__ __forceinline__ double tpcc(int c, int k, int nt) const { return tpc[(long)(((nt - 1) * kk + k - 1) * 5 + c - 1) * lev]; }
-  __device__ __forceinline__ double drhodt(int s, int k) const { return rec[(long)((k - 1) * 2 + s - 1) * lev * 4]; }
-  __device__ __forceinline__ double drhods(int s, int k) const { return rec[(long)((k - 1) * 2 + s - 1) * lev * 4 + 1]; }
-  __device__ __forceinline__ double pdst(int k) const { return p_dst[(long)(k - 1) * lev]; }
-  __device__ __forceinline__ double dstsnp(int k) const { return snp[(long)(k - 1) * lev]; }
-};
 
-// :62-74
-__device__ __forceinline__ double peval(const Col& c, int k, int nt, double x) {
-  const double c5 = c.tpcc(5, k, nt), c4 = c.tpcc(4, k, nt), c3 = c.tpcc(3, k, nt), c2 = c.tpcc(2, k, nt),
-               c1 = c.tpcc(1, k, nt);
-  return (((c5 * x + c4) * x + c3) * x + c2) * x + c1;
-}
-// :76-102
-__device__ __forceinline__ double pmeval(const Col& c, int k, int nt, double x0, double x1) {
-  const double c1_2 = 1. / 2., c1_3 = 1. / 3., c1_4 = 1. / 4., c1_5 = 1. / 5.;
-  const double b5 = c1_5 * c.tpcc(5, k, nt);
-  const double b4 = b5 * x1 + c1_4 * c.tpcc(4, k, nt);
-  const double b3 = b4 * x1 + c1_3 * c.tpcc(3, k, nt);
-  const double b2 = b3 * x1 + c1_2 * c.tpcc(2, k, nt);
-  const double b1 = b2 * x1 + c.tpcc(1, k, nt);
-  return (((b5 * x0 + b4) * x0 + b3) * x0 + b2) * x0 + b1;
-}
 // :104-148: Newton search for the position in layer k of column c that is neutral to (tf,sf); the ten
 // polynomial coefficients are loaded once instead of once per iteration
-__device__ __forceinline__ double drhoroot(const double* __restrict__ tpc, long lev, int kk, int k, double tf, double sf,
+template <class IX>
+__device__ __forceinline__ double drhoroot(const double* __restrict__ tpc, IX o, IX lev, int kk, int k, double tf, double sf,
                                            double drhodt_l, double drhodt_u, double drhods_l, double drhods_u) {
   const double eps = 1.e-14, x_tol = 1.e-4;
   double x = .5;
   const double ddrdtdx = drhodt_l - drhodt_u, ddrdsdx = drhods_l - drhods_u;
-  const double* bt = tpc + (long)(((IT - 1) * kk + k - 1) * 5) * lev;
-  const double* bs = tpc + (long)(((IS - 1) * kk + k - 1) * 5) * lev;
-  const double T1 = bt[0], T2 = bt[lev], T3 = bt[2 * lev], T4 = bt[3 * lev], T5 = bt[4 * lev];
-  const double S1 = bs[0], S2 = bs[lev], S3 = bs[2 * lev], S4 = bs[3 * lev], S5 = bs[4 * lev];
+  const IX bt = o + (IX)(((IT - 1) * kk + k - 1) * 5) * lev, bs = o + (IX)(((IS - 1) * kk + k - 1) * 5) * lev;
+  const double T1 = tpc[bt], T2 = tpc[bt + lev], T3 = tpc[bt + 2 * lev], T4 = tpc[bt + 3 * lev], T5 = tpc[bt + 4 * lev];
+  const double S1 = tpc[bs], S2 = tpc[bs + lev], S3 = tpc[bs + 2 * lev], S4 = tpc[bs + 3 * lev], S5 = tpc[bs + 4 * lev];
   for (int n = 1; n <= 10; ++n) {
     const double dt = tf - (T1 + (T2 + (T3 + (T4 + T5 * x) * x) * x) * x);
     const double ds = sf - (S1 + (S2 + (S3 + (S4 + S5 * x) * x) * x) * x);
@@ -198,12 +154,12 @@ ndiff_prep(Geom g, int mm, int T, const int* __restrict__ ip, const int* __restr
 }
 
 // face-owned running sums of the flux convergence of the current destination layer of one side
-template <int NT>
+template <int NT, class IX>
 struct SideAcc {
   double a[NT > 0 ? NT : NTMAX];
-  double* buf; long lev; int kk, T, cur;
-  __device__ __forceinline__ void init(double* b, long l, int k, int t) {
-    buf = b; lev = l; kk = k; T = t; cur = 0;
+  double* buf; IX x, lev; int kk, T, cur;
+  __device__ __forceinline__ void init(double* b, IX x_, IX l, int k, int t) {
+    buf = b; x = x_; lev = l; kk = k; T = t; cur = 0;
 #pragma unroll
     for (int q = 0; q < (NT > 0 ? NT : NTMAX); ++q) a[q] = 0.;
   }
@@ -212,8 +168,8 @@ struct SideAcc {
 #pragma unroll
     for (int q = 0; q < (NT > 0 ? NT : NTMAX); ++q)
       if (q < T) {
-        if (cur > 0) buf[(long)(q * kk + cur - 1) * lev] = a[q];
-        for (int k = cur + 1; k < kd; ++k) buf[(long)(q * kk + k - 1) * lev] = 0.;
+        if (cur > 0) buf[x + (IX)(q * kk + cur - 1) * lev] = a[q];
+        for (int k = cur + 1; k < kd; ++k) buf[x + (IX)(q * kk + k - 1) * lev] = 0.;
         a[q] = 0.;
       }
     cur = kd;
@@ -222,22 +178,51 @@ struct SideAcc {
 };
 
 // ndiff_flx (:160-953) for the face between cell M (i-1|j-1) and cell P (i,j)
-// BS threads per block at a register budget of 128 per thread (512 resident threads per SM): a block holds its
-// SM slot until its slowest warp is done and the warps' run times differ widely (every lane follows its own
-// column), so smaller blocks pack the SMs better (development switch ndiff_block = 128 | 64 | 32).
-template <int DIR, int NT, int BS, bool PF>
-__global__ void __launch_bounds__(BS, 512 / BS)
+// 128 threads per block at a register budget of 128 per thread (512 resident threads per SM).
+//
+// Index arithmetic: every access is `array[cell + level * lev]`.  IX is the type that arithmetic is done in:
+// `unsigned` when the largest element index of the call ((5*kk*T + 1) * lev) fits 32 bits (one IMAD for the
+// index and one IMAD.WIDE for the address instead of the six instructions of a 64-bit product; address
+// arithmetic was a third of all instructions of this kernel), `long` otherwise (ndiff_dev chooses).  The cell
+// offsets x, xm are part of the index, so no per-array cell pointers are held in registers.
+constexpr int ND_BS = 128;
+template <int DIR, int NT, class IX>
+__global__ void __launch_bounds__(ND_BS, 512 / ND_BS)
 ndiff_face(Geom g, NdArgs A) {
   // wet faces only: thread t owns face A.faces[t] (linear (i,j) offset of the face's plus-side cell).  A thread
   // of a land face would idle for the whole life of its warp - the kernel is issue- and latency-bound, so the
   // compacted list (built once, the masks are static) removes that share of the warps outright.
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= A.nfaces) return;
-  const long x = A.faces[t];
-  const long xm = x - (DIR == 0 ? 1 : g.ldi), lev = g.lev;
+  const IX x = (IX)A.faces[t];
+  const IX xm = x - (IX)(DIR == 0 ? 1 : g.ldi), lev = (IX)g.lev;
   const int kk = g.kdm, T = NT > 0 ? NT : A.T, mm = A.mm;
-  const Col M{A.p_src + xm, A.tsd + xm, A.tpc + xm, A.rec + xm * 4, A.p_dst + xm, A.snp + xm, lev, kk};
-  const Col P{A.p_src + x, A.tsd + x, A.tpc + x, A.rec + x * 4, A.p_dst + x, A.snp + x, lev, kk};
+  // the slice data of a cell column o (= x or xm) with the reference's 1-based indices
+  auto psd = [&](IX o, int s, int k) { return A.p_src[o + (IX)(k + s - 2) * lev]; };   // p_srcdi(s,k) = p_src(k+s-1)
+  auto tsrcdi = [&](IX o, int s, int k, int nt) { return A.tsd[o + (IX)(((nt - 1) * kk + k - 1) * 2 + s - 1) * lev]; };
+  auto tpcc = [&](IX o, int c, int k, int nt) { return A.tpc[o + (IX)(((nt - 1) * kk + k - 1) * 5 + c - 1) * lev]; };
+  auto pdst = [&](IX o, int k) { return A.p_dst[o + (IX)(k - 1) * lev]; };
+  auto dstsnp = [&](IX o, int k) { return A.snp[o + (IX)(k - 1) * lev]; };
+  auto rec_at = [&](IX o, int is, int ks) {
+    const double2* r = reinterpret_cast<const double2*>(A.rec) + (o + (IX)((ks - 1) * 2 + is - 1) * lev) * 2;
+    const double2 a = r[0], b = r[1];
+    return Rec{a.x, a.y, b.x, b.y};
+  };
+  // :62-74, :76-102 (only used when the coefficient cache is off)
+  auto peval = [&](IX o, int k, int nt, double xx) {
+    const double c5 = tpcc(o, 5, k, nt), c4 = tpcc(o, 4, k, nt), c3 = tpcc(o, 3, k, nt), c2 = tpcc(o, 2, k, nt),
+                 c1 = tpcc(o, 1, k, nt);
+    return (((c5 * xx + c4) * xx + c3) * xx + c2) * xx + c1;
+  };
+  auto pmeval = [&](IX o, int k, int nt, double x0, double x1) {
+    const double c1_2 = 1. / 2., c1_3 = 1. / 3., c1_4 = 1. / 4., c1_5 = 1. / 5.;
+    const double b5 = c1_5 * tpcc(o, 5, k, nt);
+    const double b4 = b5 * x1 + c1_4 * tpcc(o, 4, k, nt);
+    const double b3 = b4 * x1 + c1_3 * tpcc(o, 3, k, nt);
+    const double b2 = b3 * x1 + c1_2 * tpcc(o, 2, k, nt);
+    const double b1 = b2 * x1 + tpcc(o, 1, k, nt);
+    return (((b5 * x0 + b4) * x0 + b3) * x0 + b2) * x0 + b1;
+  };
   const int ksmx_m = A.ksmx[xm], ksmx_p = A.ksmx[x], kdmx_m = A.kdmx[xm], kdmx_p = A.kdmx[x];
   const double cdiff = A.delt1 * A.sca[x] * A.scbi[x];          // :1064 / :1126
   const double cnslp = alpha0 * A.scbi[x] / grav;
@@ -247,8 +232,6 @@ ndiff_face(Geom g, NdArgs A) {
 #define PNM(s, k) pnm[2 * (k) + (s) - 1]
 #define PNP(s, k) pnp[2 * (k) + (s) - 1]
   unsigned long long stab_m = 0ull, stab_p = 0ull;   // bit k-1 <-> stab(k), k = 1..64
-  auto stabm = [&](int k) { return k >= 1 && ((stab_m >> (k - 1)) & 1ull); };
-  auto stabp = [&](int k) { return k >= 1 && ((stab_p >> (k - 1)) & 1ull); };
   double pml = 0., drho_curr = 0., p_ni_m_prev, p_ni_p_prev;
   int nns = 0, kssa_m = 0, kssa_p = 0, is_m, is_p, ks_m, ks_p;
 
@@ -264,43 +247,42 @@ ndiff_face(Geom g, NdArgs A) {
   // below it, never moving ks back; handing every new pair to the still-unfilled destination interfaces
   // visits exactly the same (kd, ks) combinations, so the interpolated values are identical and the two
   // lists of up to 4*(kk+1) doubles per thread never exist.
-  double* nslp = A.nslp + x;
   int kd_sl = 1;
-  double pd_sl = .5 * (M.pdst(1) + P.pdst(1)), s_prev = 0., p_prev = 0.;
+  double pd_sl = .5 * (pdst(xm, 1) + pdst(x, 1)), s_prev = 0., p_prev = 0.;
   auto emit_slope = [&](double sl, double pr) {
     nns = nns + 1;
     while (kd_sl <= kk && !(pd_sl > pr)) {
-      if (nns == 1) nslp[(long)(kd_sl - 1) * lev] = sl;
+      if (nns == 1) A.nslp[x + (IX)(kd_sl - 1) * lev] = sl;
       else {
         const double q = (pr - pd_sl) / fmax(pr - p_prev, epsilp);
-        nslp[(long)(kd_sl - 1) * lev] = q * s_prev + (1. - q) * sl;
+        A.nslp[x + (IX)(kd_sl - 1) * lev] = q * s_prev + (1. - q) * sl;
       }
       kd_sl = kd_sl + 1;
-      if (kd_sl <= kk) pd_sl = .5 * (M.pdst(kd_sl) + P.pdst(kd_sl));
+      if (kd_sl <= kk) pd_sl = .5 * (pdst(xm, kd_sl) + pdst(x, kd_sl));
     }
     s_prev = sl; p_prev = pr;
   };
 
   // ---- first search: neutral interfaces anchored at source layer interfaces (:212-406)
   if (A.surface_align) {
-    pml = .5 * (M.psd(1, 1) + A.dpml[xm] + P.psd(1, 1) + A.dpml[x]);
+    pml = .5 * (psd(xm, 1, 1) + A.dpml[xm] + psd(x, 1, 1) + A.dpml[x]);
     kssa_m = 2;
     while (kssa_m <= ksmx_m) {
-      if (M.psd(1, kssa_m) > pml) break;
+      if (psd(xm, 1, kssa_m) > pml) break;
       kssa_m = kssa_m + 1;
     }
     kssa_p = 2;
     while (kssa_p <= ksmx_p) {
-      if (P.psd(1, kssa_p) > pml) break;
+      if (psd(x, 1, kssa_p) > pml) break;
       kssa_p = kssa_p + 1;
     }
     is_m = 1; ks_m = kssa_m; is_p = 1; ks_p = kssa_p;
     p_ni_m_prev = pml; p_ni_p_prev = pml;
   } else {
     is_m = 1; ks_m = 1; is_p = 1; ks_p = 1;
-    p_ni_m_prev = M.psd(1, 1); p_ni_p_prev = P.psd(1, 1);
+    p_ni_m_prev = psd(xm, 1, 1); p_ni_p_prev = psd(x, 1, 1);
   }
-  if (ks_m <= ksmx_m && ks_p <= ksmx_p) { rm = M.record(is_m, ks_m); rp = P.record(is_p, ks_p); drho_curr = drho_at(); }
+  if (ks_m <= ksmx_m && ks_p <= ksmx_p) { rm = rec_at(xm, is_m, ks_m); rp = rec_at(x, is_p, ks_p); drho_curr = drho_at(); }
 
   // search_loop1.  The reference handles the minus and the plus column in separate, mirrored code blocks
   // (root search in M when drho < 0, in P when drho > 0; advance M, then advance P).  Lanes of a warp sit in
@@ -308,12 +290,6 @@ ndiff_face(Geom g, NdArgs A) {
   // lane (`side`: 0 = M, offset xm; 1 = P, offset x): lanes that advance M and lanes that advance P, or that
   // solve for a root in M and in P, then execute together instead of one after the other.  The arithmetic
   // per lane is the reference's (sums are commuted only where a + b == b + a exactly).
-  auto rec_at = [&](long o, int is, int ks) {
-    const double2* r = reinterpret_cast<const double2*>(A.rec + (o + (long)((ks - 1) * 2 + is - 1) * lev) * 4);
-    const double2 a = r[0], b = r[1];
-    return Rec{a.x, a.y, b.x, b.y};
-  };
-  auto psd_at = [&](long o, int is, int ks) { return A.p_src[o + (long)(ks + is - 2) * lev]; };
   {
     bool done1 = false;
     while (!done1 && ks_m <= ksmx_m && ks_p <= ksmx_p) {
@@ -324,25 +300,25 @@ ndiff_face(Geom g, NdArgs A) {
         const bool rootm = drho_neg && is_m == 2, rootp = drho_pos && is_p == 2;
         if (rootm || rootp) {
           // layer kr of the searched column (offset o) against the fixed interface fx of the other column
-          const long o = rootm ? xm : x;
+          const IX o = rootm ? xm : x;
           const int kr = rootm ? ks_m : ks_p;
           const Rec fx = rootm ? rp : rm;
-          const double* r1 = A.rec + (o + (long)((kr - 1) * 2) * lev) * 4;
-          const double* r2 = r1 + lev * 4;
-          const double drhodt_x0 = .5 * (r1[0] + fx.drdt), drhodt_x1 = .5 * (r2[0] + fx.drdt);
-          const double drhods_x0 = .5 * (r1[1] + fx.drds), drhods_x1 = .5 * (r2[1] + fx.drds);
-          const double x_ni = drhoroot(A.tpc + o, lev, kk, kr, fx.t, fx.s, drhodt_x1, drhodt_x0, drhods_x1, drhods_x0);
-          const double p_ni = psd_at(o, 2, kr) * x_ni + psd_at(o, 1, kr) * (1. - x_ni);
+          const double2* r1 = reinterpret_cast<const double2*>(A.rec) + (o + (IX)((kr - 1) * 2) * lev) * 2;
+          const double2 u1 = r1[0], l1 = r1[(IX)2 * lev];
+          const double drhodt_x0 = .5 * (u1.x + fx.drdt), drhodt_x1 = .5 * (l1.x + fx.drdt);
+          const double drhods_x0 = .5 * (u1.y + fx.drds), drhods_x1 = .5 * (l1.y + fx.drds);
+          const double x_ni = drhoroot<IX>(A.tpc, o, lev, kk, kr, fx.t, fx.s, drhodt_x1, drhodt_x0, drhods_x1, drhods_x0);
+          const double p_ni = psd(o, 2, kr) * x_ni + psd(o, 1, kr) * (1. - x_ni);
           if (p_ni > (rootm ? p_ni_m_prev : p_ni_p_prev)) {
             // pressure of the fixed interface in its own column
-            const double pe = rootm ? psd_at(x, is_p, ks_p) : psd_at(xm, is_m, ks_m);
+            const double pe = rootm ? psd(x, is_p, ks_p) : psd(xm, is_m, ks_m);
             if (rootm) { p_ni_m_prev = p_ni; PNP(is_p, ks_p) = p_ni; }
             else { p_ni_p_prev = p_ni; PNM(is_m, ks_m) = p_ni; }
             const double pa = rootm ? pe : p_ni, pb = rootm ? p_ni : pe;   // (plus side) - (minus side)
             emit_slope(-cnslp * (pa - pb), .5 * (pa + pb));
           }
         } else if (drho_zero) {
-          const double pm = M.psd(is_m, ks_m), pp = P.psd(is_p, ks_p);
+          const double pm = psd(xm, is_m, ks_m), pp = psd(x, is_p, ks_p);
           PNP(is_p, ks_p) = pm;
           PNM(is_m, ks_m) = pp;
           emit_slope(-cnslp * (pp - pm), .5 * (pp + pm));
@@ -360,18 +336,12 @@ ndiff_face(Geom g, NdArgs A) {
           if (ks > (side ? ksmx_p : ksmx_m)) { if (side) ks_p = ks; else ks_m = ks; done1 = true; break; }
           is = 1;
         }
-        const long o = side ? x : xm;
-        if (PF) {   // records and source interfaces this side reaches 3 and 4 advances from now
-          const int rn = min((ks - 1) * 2 + is - 1 + 3, 2 * kk - 2);
-          pf_l1(A.rec + (o + (long)rn * lev) * 4);
-          pf_l1(A.rec + (o + (long)(rn + 1) * lev) * 4);
-          pf_l1(A.p_src + o + (long)min(ks + 2, kk) * lev);
-        }
+        const IX o = side ? x : xm;
         const Rec r = rec_at(o, is, ks);
         if (side) { rp = r; is_p = is; ks_p = ks; } else { rm = r; is_m = is; ks_m = ks; }
         drho_curr = drho_at();
         if ((side ? drho_curr - drho_prev : drho_prev - drho_curr) > rho_eps) {
-          if (is == 2 && psd_at(o, 2, ks) - psd_at(o, 1, ks) > onemm) {
+          if (is == 2 && psd(o, 2, ks) - psd(o, 1, ks) > onemm) {
             if (side) stab_p |= 1ull << (ks - 1); else stab_m |= 1ull << (ks - 1);
           }
           if (then_p) { then_p = false; side = 1; continue; }
@@ -396,35 +366,35 @@ ndiff_face(Geom g, NdArgs A) {
       else { kssa_p = kssa_p + 1; issa_p = 1; }
     }
     if (kssa_m > ksmx_m || kssa_p > ksmx_p) {
-      const double pbm = M.psd(2, ksmx_m), pbp = P.psd(2, ksmx_p);
-      PNM(1, 1) = M.psd(1, 1);
+      const double pbm = psd(xm, 2, ksmx_m), pbp = psd(x, 2, ksmx_p);
+      PNM(1, 1) = psd(xm, 1, 1);
       for (ks_m = 1; ks_m <= ksmx_m - 1; ++ks_m) {
-        if (M.psd(1, ks_m) > pbp) break;
-        const double p_ni = fmin(M.psd(2, ks_m), pbp);
+        if (psd(xm, 1, ks_m) > pbp) break;
+        const double p_ni = fmin(psd(xm, 2, ks_m), pbp);
         PNM(1, ks_m + 1) = p_ni;
         PNM(2, ks_m) = p_ni;
         stab_m |= 1ull << (ks_m - 1);
       }
-      PNP(1, 1) = P.psd(1, 1);
+      PNP(1, 1) = psd(x, 1, 1);
       for (ks_p = 1; ks_p <= ksmx_p - 1; ++ks_p) {
-        if (P.psd(1, ks_p) > pbm) break;
-        const double p_ni = fmin(P.psd(2, ks_p), pbm);
+        if (psd(x, 1, ks_p) > pbm) break;
+        const double p_ni = fmin(psd(x, 2, ks_p), pbm);
         PNP(1, ks_p + 1) = p_ni;
         PNP(2, ks_p) = p_ni;
         stab_p |= 1ull << (ks_p - 1);
       }
     } else {
       double p1_m, p2_m, p1_p, p2_p;
-      if (M.psd(issa_m, kssa_m) < PNP(issa_p, kssa_p)) {
-        p1_m = M.psd(1, 1); p2_m = M.psd(issa_m, kssa_m);
-        p1_p = P.psd(1, 1); p2_p = PNM(issa_m, kssa_m);
+      if (psd(xm, issa_m, kssa_m) < PNP(issa_p, kssa_p)) {
+        p1_m = psd(xm, 1, 1); p2_m = psd(xm, issa_m, kssa_m);
+        p1_p = psd(x, 1, 1); p2_p = PNM(issa_m, kssa_m);
       } else {
-        p1_m = M.psd(1, 1); p2_m = PNP(issa_p, kssa_p);
-        p1_p = P.psd(1, 1); p2_p = P.psd(issa_p, kssa_p);
+        p1_m = psd(xm, 1, 1); p2_m = PNP(issa_p, kssa_p);
+        p1_p = psd(x, 1, 1); p2_p = psd(x, issa_p, kssa_p);
       }
       PNM(1, 1) = p1_p;
       for (ks_m = 1; ks_m <= kssa_m - 1; ++ks_m) {
-        const double pl = M.psd(2, ks_m);
+        const double pl = psd(xm, 2, ks_m);
         const double p_ni = ((pl - p1_m) * p2_p + (p2_m - pl) * p1_p) / (p2_m - p1_m);
         PNM(1, ks_m + 1) = p_ni;
         PNM(2, ks_m) = p_ni;
@@ -432,7 +402,7 @@ ndiff_face(Geom g, NdArgs A) {
       }
       PNP(1, 1) = p1_m;
       for (ks_p = 1; ks_p <= kssa_p - 1; ++ks_p) {
-        const double pl = P.psd(2, ks_p);
+        const double pl = psd(x, 2, ks_p);
         const double p_ni = ((pl - p1_p) * p2_m + (p2_p - pl) * p1_m) / (p2_p - p1_p);
         PNP(1, ks_p + 1) = p_ni;
         PNP(2, ks_p) = p_ni;
@@ -445,66 +415,66 @@ ndiff_face(Geom g, NdArgs A) {
   // The reference keeps the previous/current neutral interface in two slots that swap (nip/nic); here they
   // are plain "prev"/"cur" registers and cur is copied to prev when an interface has been found (a slot
   // index would put them in local memory).  The polynomial coefficients of the current source layer of
-  // each side (tpc_src, 5 per scalar) stay in registers while ks_m / ks_p do not change: peval and pmeval
+  // each side (tpc_src, 5 per scalar) are cached while ks_m / ks_p do not change: peval and pmeval
   // are evaluated for every neutral interface found inside a layer, which took a quarter of all
   // instructions as strided loads and their address arithmetic.  The branches of the case analysis only
   // decide HOW the interface values are obtained (ev_m/ev_p); the evaluation itself and the flux
   // computation run after the branches have reconverged.
-  SideAcc<NT> accm, accp;
-  accm.init(A.cvm + x, lev, kk, T);
-  accp.init(A.cvp + x, lev, kk, T);
+  SideAcc<NT, IX> accm, accp;
+  accm.init(A.cvm, x, lev, kk, T);
+  accp.init(A.cvp, x, lev, kk, T);
   {
     constexpr int NTC = NT > 0 ? NT : NTMAX;
     constexpr bool CACHE = NT > 0 && NT <= 3;     // register budget: 10 doubles per scalar
     // the cache lives in shared memory, one column of 5*NT doubles per thread and side ([..][threadIdx.x],
     // conflict-free): in registers its 40 values pushed the searches' state into spills at 128 registers
-    __shared__ double cf_sm[CACHE ? 2 * NTC * 5 : 1][BS];
+    // rows 0..2*NTC*5-1: coefficients (minus side, then plus side); then per side the layer's diffusivity and its
+    // NTC layer means (difiso(ks), scalar(ks) at the new time level), which every flux of the layer reads as well
+    constexpr int LM = 2 * NTC * 5;
+    __shared__ double cf_sm[CACHE ? LM + 2 * (NTC + 1) : 1][ND_BS];
     struct CoefRef {   // the five coefficients of scalar nt of one side, as the polynomial helpers read them
-      const double (*col)[BS]; int t;
+      const double (*col)[ND_BS]; int t;
       __device__ __forceinline__ double operator[](int c5) const { return col[c5][t]; }
     };
     auto cfm = [&](int nt) { return CoefRef{&cf_sm[CACHE ? (nt - 1) * 5 : 0], (int)threadIdx.x}; };
     auto cfp = [&](int nt) { return CoefRef{&cf_sm[CACHE ? (NTC + nt - 1) * 5 : 0], (int)threadIdx.x}; };
     int kc_m = 0, kc_p = 0;                        // layers whose coefficients are cached
-    auto coef = [&](const Col& c, int k, int nt, int row0) {
-      const double* b5 = c.tpc + (long)(((nt - 1) * kk + k - 1) * 5) * lev;
-      const double c0 = b5[0], c1 = b5[lev], c2 = b5[2 * lev], c3 = b5[3 * lev], c4 = b5[4 * lev];
-      double(*o)[BS] = &cf_sm[CACHE ? row0 : 0];
-      const int t = threadIdx.x;
-      o[0][t] = c0; o[1][t] = c1; o[2][t] = c2; o[3][t] = c3; o[4][t] = c4;
+    auto coef = [&](IX o, int k, int nt, int row0) {
+      const IX b5 = o + (IX)(((nt - 1) * kk + k - 1) * 5) * lev;
+      const double c0 = A.tpc[b5], c1 = A.tpc[b5 + lev], c2 = A.tpc[b5 + 2 * lev], c3 = A.tpc[b5 + 3 * lev],
+                   c4 = A.tpc[b5 + 4 * lev];
+      double(*o5)[ND_BS] = &cf_sm[CACHE ? row0 : 0];
+      const int tx = threadIdx.x;
+      o5[0][tx] = c0; o5[1][tx] = c1; o5[2][tx] = c2; o5[3][tx] = c3; o5[4][tx] = c4;
     };
-    // what the next source layer of a column will need: its polynomial coefficients, interface values,
-    // diffusivity and layer means (read when ks advances, several neutral interfaces from now)
-    auto pf_layer = [&](long o, int k) {
-      if (!PF || k > kk) return;
+    auto layer_means = [&](IX o, int k, int row0) {
+      const IX ol = o + (IX)(k - 1) * lev;
+      const int tx = threadIdx.x;
+      double v[NTC + 1];
+      v[0] = A.difiso[ol];
 #pragma unroll
-      for (int nt = 1; nt <= NTC; ++nt)
-        if (nt <= T) {
-          const double* b5 = A.tpc + o + (long)(((nt - 1) * kk + k - 1) * 5) * lev;
-          pf_l1(b5); pf_l1(b5 + lev); pf_l1(b5 + 2 * lev); pf_l1(b5 + 3 * lev); pf_l1(b5 + 4 * lev);
-          pf_l1(A.tsd + o + (long)(((nt - 1) * kk + k - 1) * 2) * lev);
-          pf_l1(A.tsd + o + (long)(((nt - 1) * kk + k - 1) * 2 + 1) * lev);
-          pf_l1(A.tlev[nt - 1] + o + (long)(k - 1) * lev);
-        }
-      pf_l1(A.difiso + o + (long)(k - 1) * lev);
-      pf_l1(A.p_src + o + (long)k * lev);
+      for (int nt = 1; nt <= NTC; ++nt) v[nt] = A.tlev[nt - 1][ol];
+#pragma unroll
+      for (int nt = 0; nt <= NTC; ++nt) cf_sm[CACHE ? row0 + nt : 0][tx] = v[nt];
     };
     auto need_m = [&]() {
       if (CACHE && kc_m != ks_m) {
 #pragma unroll
-        for (int nt = 1; nt <= NTC; ++nt) coef(M, ks_m, nt, (nt - 1) * 5);
+        for (int nt = 1; nt <= NTC; ++nt) coef(xm, ks_m, nt, (nt - 1) * 5);
+        layer_means(xm, ks_m, LM);
         kc_m = ks_m;
-        pf_layer(xm, ks_m + 1);
       }
     };
     auto need_p = [&]() {
       if (CACHE && kc_p != ks_p) {
 #pragma unroll
-        for (int nt = 1; nt <= NTC; ++nt) coef(P, ks_p, nt, (NTC + nt - 1) * 5);
+        for (int nt = 1; nt <= NTC; ++nt) coef(x, ks_p, nt, (NTC + nt - 1) * 5);
+        layer_means(x, ks_p, LM + NTC + 1);
         kc_p = ks_p;
-        pf_layer(x, ks_p + 1);
       }
     };
+    auto lmean_m = [&](int nt) { return cf_sm[CACHE ? LM + nt : 0][threadIdx.x]; };             // nt = 0: difiso
+    auto lmean_p = [&](int nt) { return cf_sm[CACHE ? LM + NTC + 1 + nt : 0][threadIdx.x]; };
     auto pe = [&](const CoefRef c, double xx) { return (((c[4] * xx + c[3]) * xx + c[2]) * xx + c[1]) * xx + c[0]; };
     auto pme = [&](const CoefRef c, double x0, double x1) {
       const double c1_2 = 1. / 2., c1_3 = 1. / 3., c1_4 = 1. / 4., c1_5 = 1. / 5.;
@@ -517,16 +487,22 @@ ndiff_face(Geom g, NdArgs A) {
     };
 
     is_m = 2; ks_m = 0; is_p = 2; ks_p = 0;
-    int kd_m = 0, kd_p = 0, isn_m = 1, isn_p = 1, ksn_m = 1, ksn_p = 1, ks_m_prev = 0, ks_p_prev = 0;
+    int kd_m = 0, kd_p = 0, ks_m_prev = 0, ks_p_prev = 0;
     bool advance_src_m = true, advance_src_p = true, advance_dst_m = true, advance_dst_p = true;
     double p_prev_m = -mval, p_prev_p = -mval, p_cur_m = 0., p_cur_p = 0.;
     double x_prev_m = 0., x_prev_p = 0., x_cur_m = 0., x_cur_p = 0.;
     double t_prev_m[NTC], t_prev_p[NTC], t_cur_m[NTC], t_cur_p[NTC];
 #pragma unroll
     for (int q = 0; q < NTC; ++q) { t_prev_m[q] = 0.; t_prev_p[q] = 0.; t_cur_m[q] = 0.; t_cur_p[q] = 0.; }
+    // Values that only change when a column's source interface or destination layer moves are loaded at that
+    // moment and kept: the interface pressures of the current source layer (ps1, ps2), pressure and neutral
+    // partner of the next interface with a partner (ps_n, pn_n), the partner of the current interface (pn_c) and
+    // the snapped lower interface of the current destination layer (snp).  An iteration of the search moves one
+    // of the four pointers; re-reading all of these at its top cost ten loads where one to five are needed.
+    double psm1 = 0., psm2 = 0., psp1 = 0., psp2 = 0., psm_n = 0., psp_n = 0., pnm_n = 0., pnp_n = 0.;
+    double pnm_c = 0., pnp_c = 0., snp_m = 0., snp_p = 0.;
     int kuv = 1;
-    const double* puvx = A.puv + x;
-    auto puv = [&](int k) { return puvx[(long)(k - 1) * lev]; };
+    auto puv = [&](int k) { return A.puv[x + (IX)(k - 1) * lev]; };
     // The face fluxes of a neutral sublayer are binned on the face's layers (:870-905).  A layer collects
     // the contributions of several sublayers one after the other; its four running sums (tflld, sflld, tflx,
     // sflx of layer kuv_acc) are kept in registers from the first contribution until the binning moves on
@@ -536,7 +512,7 @@ ndiff_face(Geom g, NdArgs A) {
     double a_tflld = 0., a_sflld = 0., a_tflx = 0., a_sflx = 0., pk_c = 0., pk1_c = 0.;
     auto flush_layer = [&]() {
       if (kuv_acc == 0) return;
-      const long o = x + (long)(kuv_acc + mm - 1) * lev;
+      const IX o = x + (IX)(kuv_acc + mm - 1) * lev;
       A.tflld[o] = a_tflld; A.sflld[o] = a_sflld; A.tflx[o] = a_tflx; A.sflx[o] = a_sflx;
     };
 
@@ -572,16 +548,19 @@ ndiff_face(Geom g, NdArgs A) {
               isn = 1;
             }
           }
-          if (side) { is_p = is; ks_p = ks; isn_p = isn; ksn_p = ksn; }
-          else { is_m = is; ks_m = ks; isn_m = isn; ksn_m = ksn; }
+          {
+            const IX o = side ? x : xm;
+            const double ps1 = psd(o, 1, ks), ps2 = psd(o, 2, ks), ps_n = psd(o, isn, ksn);
+            const double pn_n = pn[2 * ksn + isn - 1], pn_c = pn[2 * ks + is - 1];
+            if (side) { is_p = is; ks_p = ks; psp1 = ps1; psp2 = ps2; psp_n = ps_n; pnp_n = pn_n; pnp_c = pn_c; }
+            else { is_m = is; ks_m = ks; psm1 = ps1; psm2 = ps2; psm_n = ps_n; pnm_n = pn_n; pnm_c = pn_c; }
+          }
           if (then_p) { then_p = false; side = 1; continue; }
           break;
         }
         if (out) break;
       }
       // the quantities every branch below looks at
-      const double pnm_n = PNM(isn_m, ksn_m), pnp_n = PNP(isn_p, ksn_p);
-      const double psm_n = M.psd(isn_m, ksn_m), psp_n = P.psd(isn_p, ksn_p);
       if (p_prev_m == -mval) {
         if ((pnm_n - psp_n) < (pnp_n - psm_n)) {
           p_prev_m = psm_n;
@@ -594,33 +573,33 @@ ndiff_face(Geom g, NdArgs A) {
       if (advance_dst_m) {
         kd_m = kd_m + 1;
         if (kd_m > kdmx_m) break;
-        if (PF) { pf_l1(A.snp + xm + (long)min(kd_m + 2, kk) * lev); pf_l1(A.p_dst + xm + (long)min(kd_m + 2, kk) * lev); }
+        snp_m = dstsnp(xm, kd_m + 1);
       }
       if (advance_dst_p) {
         kd_p = kd_p + 1;
         if (kd_p > kdmx_p) break;
-        if (PF) { pf_l1(A.snp + x + (long)min(kd_p + 2, kk) * lev); pf_l1(A.p_dst + x + (long)min(kd_p + 2, kk) * lev); }
+        snp_p = dstsnp(x, kd_p + 1);
       }
-      const double psm1 = M.psd(1, ks_m), psm2 = M.psd(2, ks_m), psp1 = P.psd(1, ks_p), psp2 = P.psd(2, ks_p);
       {
         bool out = false;
         const double lim_m = fmax(psm1, p_prev_m);
-        while (M.dstsnp(kd_m + 1) <= lim_m) {
+        while (snp_m <= lim_m) {
           kd_m = kd_m + 1;
           if (kd_m > kdmx_m) { out = true; break; }
+          snp_m = dstsnp(xm, kd_m + 1);
         }
         if (out) break;
         const double lim_p = fmax(psp1, p_prev_p);
-        while (P.dstsnp(kd_p + 1) <= lim_p) {
+        while (snp_p <= lim_p) {
           kd_p = kd_p + 1;
           if (kd_p > kdmx_p) { out = true; break; }
+          snp_p = dstsnp(x, kd_p + 1);
         }
         if (out) break;
       }
       advance_src_m = false; advance_src_p = false; advance_dst_m = false; advance_dst_p = false;
 
       const double psm = is_m == 1 ? psm1 : psm2, psp = is_p == 1 ? psp1 : psp2;
-      const double snp_m = M.dstsnp(kd_m + 1), snp_p = P.dstsnp(kd_p + 1);
       int case_m = 3;
       if (psm <= pnp_n) {
         if (psm <= snp_m) case_m = 1;
@@ -691,7 +670,7 @@ ndiff_face(Geom g, NdArgs A) {
             found_ni = true;
             if (am) advance_dst_m = true; else advance_dst_p = true;
           } else {
-            const double pn_b = am ? PNP(is_p, ks_p) : PNM(is_m, ks_m);
+            const double pn_b = am ? pnp_c : pnm_c;
             if (case_b == 1 && pn_b == mval) { if (am) advance_src_p = true; else advance_src_m = true; }
             else { if (am) advance_dst_m = true; else advance_dst_p = true; }
           }
@@ -699,7 +678,6 @@ ndiff_face(Geom g, NdArgs A) {
           if (am) advance_dst_m = true; else advance_dst_p = true;
         }
       } else if (case_m == 1 && case_p == 1) {
-        const double pnm_c = PNM(is_m, ks_m), pnp_c = PNP(is_p, ks_p);
         if (pnm_c != mval && pnp_c != mval) {
           p_cur_m = psm;
           p_cur_p = psp;
@@ -714,7 +692,7 @@ ndiff_face(Geom g, NdArgs A) {
       } else if (case_m == 1 || case_p == 1) {
         // one column (a) sits on a source interface whose neutral partner lies inside the other's layer (:745-790)
         const bool am = case_m == 1;
-        const double pn_c = am ? PNM(is_m, ks_m) : PNP(is_p, ks_p);
+        const double pn_c = am ? pnm_c : pnp_c;
         if (pn_c != mval && pn_c >= (am ? psp1 : psm1)) {
           if (am) { p_cur_m = psm; p_cur_p = pn_c; ev_m = 2; ev_p = 1; }
           else { p_cur_p = psp; p_cur_m = pn_c; ev_p = 2; ev_m = 1; }
@@ -738,27 +716,29 @@ ndiff_face(Geom g, NdArgs A) {
 #pragma unroll
         for (int nt = 1; nt <= NTC; ++nt)
           if (nt <= T) {
-            t_cur_m[nt - 1] = ev_m == 2 ? M.tsrcdi(is_m, ks_m, nt)
-                                        : (CACHE ? pe(cfm(nt), x_cur_m) : peval(M, ks_m, nt, x_cur_m));
-            t_cur_p[nt - 1] = ev_p == 2 ? P.tsrcdi(is_p, ks_p, nt)
-                                        : (CACHE ? pe(cfp(nt), x_cur_p) : peval(P, ks_p, nt, x_cur_p));
+            t_cur_m[nt - 1] = ev_m == 2 ? tsrcdi(xm, is_m, ks_m, nt)
+                                        : (CACHE ? pe(cfm(nt), x_cur_m) : peval(xm, ks_m, nt, x_cur_m));
+            t_cur_p[nt - 1] = ev_p == 2 ? tsrcdi(x, is_p, ks_p, nt)
+                                        : (CACHE ? pe(cfp(nt), x_cur_p) : peval(x, ks_p, nt, x_cur_p));
           }
-        const double dp_ni_m = fmin(p_cur_m - p_prev_m, M.pdst(kd_m + 1) - M.pdst(kd_m));
-        const double dp_ni_p = fmin(p_cur_p - p_prev_p, P.pdst(kd_p + 1) - P.pdst(kd_p));
+        const double dp_ni_m = fmin(p_cur_m - p_prev_m, pdst(xm, kd_m + 1) - pdst(xm, kd_m));
+        const double dp_ni_p = fmin(p_cur_p - p_prev_p, pdst(x, kd_p + 1) - pdst(x, kd_p));
         const double dp_ni = 2. * dp_ni_m * dp_ni_p / fmax(dp_ni_m + dp_ni_p, 2. * dp_eps);
-        if (ks_m == ks_m_prev && ks_p == ks_p_prev && p_prev_m >= M.dstsnp(kd_m) && p_cur_m <= snp_m &&
-            p_prev_p >= P.dstsnp(kd_p) && p_cur_p <= snp_p && dp_ni > 2. * dp_eps) {
+        if (ks_m == ks_m_prev && ks_p == ks_p_prev && p_prev_m >= dstsnp(xm, kd_m) && p_cur_m <= snp_m &&
+            p_prev_p >= dstsnp(x, kd_p) && p_cur_p <= snp_p && dp_ni > 2. * dp_eps) {
           accm.advance(kd_m);
           accp.advance(kd_p);
-          const double q = .5 * cdiff * (A.difiso[xm + (long)(ks_m - 1) * lev] + A.difiso[x + (long)(ks_p - 1) * lev]) * dp_ni;
+          const double q = .5 * cdiff * (CACHE ? lmean_m(0) + lmean_p(0)
+                                               : A.difiso[xm + (IX)(ks_m - 1) * lev] + A.difiso[x + (IX)(ks_p - 1) * lev]) * dp_ni;
           double tflx = 0., sflx = 0.;
           bool ts_ok = true;
 #pragma unroll
           for (int nt = 1; nt <= NTC; ++nt)
             if (nt <= T) {
               const double d = CACHE ? pme(cfm(nt), x_prev_m, x_cur_m) - pme(cfp(nt), x_prev_p, x_cur_p)
-                                     : pmeval(M, ks_m, nt, x_prev_m, x_cur_m) - pmeval(P, ks_p, nt, x_prev_p, x_cur_p);
-              const double cm = A.tlev[nt - 1][xm + (long)(ks_m - 1) * lev], cp = A.tlev[nt - 1][x + (long)(ks_p - 1) * lev];
+                                     : pmeval(xm, ks_m, nt, x_prev_m, x_cur_m) - pmeval(x, ks_p, nt, x_prev_p, x_cur_p);
+              const double cm = CACHE ? lmean_m(nt) : A.tlev[nt - 1][xm + (IX)(ks_m - 1) * lev];
+              const double cp = CACHE ? lmean_p(nt) : A.tlev[nt - 1][x + (IX)(ks_p - 1) * lev];
               const bool ok = d * (cm - cp) >= 0. && d * (t_prev_m[nt - 1] - t_prev_p[nt - 1]) >= 0. &&
                               d * (t_cur_m[nt - 1] - t_cur_p[nt - 1]) >= 0.;
               if (nt == IT) { tflx = q * d; ts_ok = ok; }
@@ -778,7 +758,7 @@ ndiff_face(Geom g, NdArgs A) {
             while (kuv <= kk) {
               if (kuv_acc != kuv) {   // bring layer kuv's four sums into registers (the previous layer's go out)
                 flush_layer();
-                const long o = x + (long)(kuv + mm - 1) * lev;
+                const IX o = x + (IX)(kuv + mm - 1) * lev;
                 a_tflld = A.tflld[o]; a_sflld = A.sflld[o]; a_tflx = A.tflx[o]; a_sflx = A.sflx[o];
                 pk_c = puv(kuv); pk1_c = puv(kuv + 1);
                 kuv_acc = kuv;
@@ -809,7 +789,7 @@ ndiff_face(Geom g, NdArgs A) {
   accp.finish();
 
   // ---- neutral slope at the destination interfaces below the last pair (:913-951, tail of emit_slope)
-  for (; kd_sl <= kk; ++kd_sl) nslp[(long)(kd_sl - 1) * lev] = nns == 0 ? 0. : s_prev;
+  for (; kd_sl <= kk; ++kd_sl) A.nslp[x + (IX)(kd_sl - 1) * lev] = nns == 0 ? 0. : s_prev;
 #undef PNM
 #undef PNP
 }
@@ -915,22 +895,20 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   }
   U.faces = list_u; U.nfaces = (int)c.sc["_nd_nfaces_u"];
   V.faces = list_v; V.nfaces = (int)c.sc["_nd_nfaces_v"];
-  // ndiff_prefetch=1: L1 prefetch of the operands a few iterations ahead; measured 5 % slower at tnx1v4 (14.2 vs 13.6 ms), off
-  const bool pf = c.option("ndiff_prefetch", "0") == "1";
-  const int bs = std::stoi(c.option("ndiff_block", "128"));
-  if (bs != 128 && bs != 64 && bs != 32) throw std::runtime_error("ndiff: ndiff_block must be 128, 64 or 32");
-  const dim3 gu(std::max(1, cdiv(U.nfaces, bs))), gv(std::max(1, cdiv(V.nfaces, bs)));
-#define ND_LAUNCH(NT_, BS_, PF_)                                                                  \
-  do {                                                                                            \
-    LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, BS_, PF_>), gu, BS_, 0, g, U);              \
-    LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, NT_, BS_, PF_>), gv, BS_, 0, g, V);              \
+  // 32-bit index arithmetic in ndiff_face when every element index of the call fits (tpc_src is the largest array:
+  // 5*kk*T levels; the interface records are addressed as double2, 4*kk levels of pairs): true for every tile that
+  // fits a B200 with T <= 3, e.g. tnx0.25v4 on one GPU; the 64-bit instantiation covers the rest
+  const bool ix32 = ((long)5 * kk * T + 2) * g.lev < (1l << 32) && ((long)8 * kk + 4) * g.lev < (1l << 32);
+  const dim3 gu(std::max(1, cdiv(U.nfaces, ND_BS))), gv(std::max(1, cdiv(V.nfaces, ND_BS)));
+#define ND_LAUNCH(NT_, IX_)                                                                        \
+  do {                                                                                             \
+    LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, IX_>), gu, ND_BS, 0, g, U);                  \
+    LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, NT_, IX_>), gv, ND_BS, 0, g, V);                  \
   } while (0)
-#define ND_FACE(NT_)                                                                              \
-  do {                                                                                            \
-    if (pf) ND_LAUNCH(NT_, 128, true);                                                            \
-    else if (bs == 64) ND_LAUNCH(NT_, 64, false);                                                 \
-    else if (bs == 32) ND_LAUNCH(NT_, 32, false);                                                 \
-    else ND_LAUNCH(NT_, 128, false);                                                              \
+#define ND_FACE(NT_)                                                                               \
+  do {                                                                                             \
+    if (ix32) ND_LAUNCH(NT_, unsigned);                                                            \
+    else ND_LAUNCH(NT_, long);                                                                     \
   } while (0)
   if (T == 2) { ND_FACE(2); }
   else if (T == 3) { ND_FACE(3); }

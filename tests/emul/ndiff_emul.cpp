@@ -16,7 +16,7 @@ struct EmuNdiff {
   // geometry
   int ii, jj, kdm, nb, ldi, ldj, ntr;
   // time-level arguments and options
-  int mm, nn, surface_align;
+  int mm, nn, surface_align, ix64;   // ix64: the 64-bit index instantiation of ndiff_face (else 32-bit)
   double delt1;
   // masks and inputs
   const int *ip, *iu, *iv, *ksmx;
@@ -26,10 +26,15 @@ struct EmuNdiff {
   double *utflld, *usflld, *vtflld, *vsflld, *utflx, *usflx, *vtflx, *vsflx, *nslpx, *nslpy, *trc_rm;
 };
 
-template <int NT, int BS>
+template <int NT, class IX>
 static void faces(const Geom& g, const NdArgs& U, const NdArgs& V) {
-  emu_launch(dim3(std::max(1, cdiv(U.nfaces, BS))), dim3(BS), [&] { ndiff_face<0, NT, BS, false>(g, U); });
-  emu_launch(dim3(std::max(1, cdiv(V.nfaces, BS))), dim3(BS), [&] { ndiff_face<1, NT, BS, false>(g, V); });
+  emu_launch(dim3(std::max(1, cdiv(U.nfaces, ND_BS))), dim3(ND_BS), [&] { ndiff_face<0, NT, IX>(g, U); });
+  emu_launch(dim3(std::max(1, cdiv(V.nfaces, ND_BS))), dim3(ND_BS), [&] { ndiff_face<1, NT, IX>(g, V); });
+}
+template <int NT>
+static void faces_ix(int ix64, const Geom& g, const NdArgs& U, const NdArgs& V) {
+  if (ix64) faces<NT, long>(g, U, V);
+  else faces<NT, unsigned>(g, U, V);
 }
 
 extern "C" int emu_ndiff(const EmuNdiff* e) {
@@ -71,9 +76,9 @@ extern "C" int emu_ndiff(const EmuNdiff* e) {
       if (e->iv[ix2(g, i, j)] == 1) lv.push_back((int)ix2(g, i, j));
   U.faces = lu.data(); U.nfaces = (int)lu.size();
   V.faces = lv.data(); V.nfaces = (int)lv.size();
-  if (T == 2) faces<2, 128>(g, U, V);
-  else if (T == 3) faces<3, 128>(g, U, V);
-  else faces<0, 128>(g, U, V);
+  if (T == 2) faces_ix<2>(e->ix64, g, U, V);
+  else if (T == 3) faces_ix<3>(e->ix64, g, U, V);
+  else faces_ix<0>(e->ix64, g, U, V);
 
   emu_launch(dim3(cdiv(g.ii, 256), g.jj, kk), dim3(256), [&] {
     ndiff_update(g, T, e->ip, e->iu, e->iv, e->scp2, e->p_dst, ucm.data(), ucp.data(), vcm.data(), vcp.data(), e->trc_rm);

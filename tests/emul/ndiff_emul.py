@@ -14,7 +14,7 @@ SRC = [HERE / "ndiff_emul.cpp", HERE / "cuda_host_shim.hpp", HERE.parents[1] / "
 LIB = HERE / "_build" / "libndiff_emul.so"
 
 _PD, _PI = C.POINTER(C.c_double), C.POINTER(C.c_int)
-_INTS = ["ii", "jj", "kdm", "nb", "ldi", "ldj", "ntr", "mm", "nn", "surface_align"]
+_INTS = ["ii", "jj", "kdm", "nb", "ldi", "ldj", "ntr", "mm", "nn", "surface_align", "ix64"]
 _IN_I = ["ip", "iu", "iv", "ksmx"]
 _IN_D = ["p_src", "tsd", "tpc", "p_dst", "dpml", "difiso", "temp", "saln", "trc",
          "scuy", "scuxi", "scvx", "scvyi", "scp2", "pu", "pv"]
@@ -36,7 +36,7 @@ def build(force=False):
     return LIB
 
 
-def run(dims, levels, delt1, arrays, surface_align=True):
+def run(dims, levels, delt1, arrays, surface_align=True, ix64=False):
     """dims = (ii, jj, kdm, nb, ldi, ldj, ntr); `arrays` maps the field names of EmuNdiff to C-contiguous numpy
     arrays in the common (level, j, i) layout; the OUT arrays are updated in place."""
     lib = C.CDLL(str(build()))
@@ -46,7 +46,7 @@ def run(dims, levels, delt1, arrays, surface_align=True):
     ii, jj, kdm, nb, ldi, ldj, ntr = dims
     m, n, mm, nn, k1m, k1n = levels
     for k, v in dict(ii=ii, jj=jj, kdm=kdm, nb=nb, ldi=ldi, ldj=ldj, ntr=ntr, mm=mm, nn=nn,
-                     surface_align=int(surface_align)).items():
+                     surface_align=int(surface_align), ix64=int(ix64)).items():
         setattr(e, k, v)
     e.delt1 = delt1
     keep = []
