@@ -7,11 +7,11 @@
 // (i,j,level) layout (names and level order: include/blomgpu.h, "neutral diffusion inputs").
 //
 // B200 design: the search for neutral sublayers between two columns is sequential and data dependent,
-// so ONE THREAD OWNS ONE FACE COLUMN with i across lanes (every level access of a warp is a row
-// segment).  Three launches instead of the reference's slice pipeline:
+// so ONE THREAD OWNS ONE FACE COLUMN.  Three launches instead of the reference's slice pipeline:
 //   ndiff_prep    per cell column: kdmx, drhodt/drhods at the source interfaces, the snapped destination
 //                 interfaces (a pure function of the cell, so it is evaluated once per cell instead of
-//                 once per face as in the reference), zero of the face accumulators
+//                 once per face as in the reference), zero of the face accumulators - and the TRANSPOSE of
+//                 everything the searches read into per-column records (below)
 //   ndiff_face<u|v>  per face column: both searches, fluxes, layer binning of the face fluxes and the
 //                 neutral slope.  The reference scatters flux convergences into the two cells
 //                 (flxconv(kd,nt,i-1|i)); scattering would race between faces, so each face writes
@@ -24,13 +24,20 @@
 // The only floating-point reassociation against the reference is that several contributions of one
 // face to the same destination layer are summed before they meet the cell's running total.
 //
-// ndiff_face is issue- and latency-bound (every lane follows its own column; ~250 k thread instructions
-// per face), not bandwidth-bound, so what makes it fast is fewer instructions and more lanes on the same
-// path (profiles/r02_ncu_full_ndiff_face.txt): interface records of one sector,
-// the neutral slope interpolated on the fly instead of from stored lists, polynomial coefficients of the
-// current layers cached in shared memory, binned face fluxes summed in registers, the mirrored
-// minus-/plus-column code blocks of the reference written once with the column chosen per lane, and
-// compacted lists of the wet faces.
+// What bounds ndiff_face and the layout that follows from it.  Every lane walks down its own two columns at
+// its own pace, so in the (i,j,level) layout a warp's load touches ~10 different 32-byte sectors of which each
+// lane uses 8 bytes, a thread meets a new sector for every array and level (~25 arrays x 53 levels x 2
+// columns), and each of those first touches is an L2 or DRAM round trip in the middle of a dependent chain:
+// ncu shows 52 % of the stall samples on the long scoreboard at 16 resident warps per SM, 9 % of the DRAM peak
+// and issue slots 29 % busy; removing a quarter of the instructions (32-bit index arithmetic, round 2) gained
+// 4 %.  The kernel therefore reads COLUMN RECORDS: ndiff_prep writes, per cell and source layer, one contiguous
+// record with everything both searches need of that layer (interface records, interface pressures, polynomial
+// coefficients, diffusivity, layer means; 192 bytes for T and S), and per destination interface the pair
+// {p_dst, snapped p_dst}.  A thread that steps to the next source layer of a column loads that layer's
+// record in ONE batch of independent 16-byte loads into its private column of shared memory and works from
+// there: one exposed memory round trip per layer and column instead of one per array, every fetched sector
+// used completely, no coefficient / layer-mean reloads.  The model's own arrays keep their layout; the
+// transpose costs one streaming pass inside ndiff_prep.
 #include "common.cuh"
 #include "eos.cuh"
 
@@ -56,16 +63,25 @@ __device__ __forceinline__ double eos_drhods(double p, double th, double s) {
   return (EA13 + EA15 * th + 2. * EA16 * s + EB13 * p - (EA23 + EA25 * th + 2. * EA26 * s + EB23 * p) * r1 * r2i) * r2i;
 }
 
-// Packed record of one source-layer interface of one cell column: {drhodt, drhods, T, S} at (is,k), 32 bytes =
-// one memory sector.  The first search evaluates the density difference between two interfaces at every step
-// and its lanes sit at different layers, so four separate level-strided arrays cost four sectors per lane
-// where the record costs one.  Layout: record ((k-1)*2+is-1) of cell x at rec[(((k-1)*2+is-1)*lev + x)*4].
+// Column record of source layer k of one cell (doubles; the record of layer k of cell x starts at
+// src[(x*kk + k-1) * RS], RS = nd_rs(T) = 24 + 8*(T-2)):
+//    0.. 3  {drhodt, drhods, T, S} at the upper interface (is = 1)        t_srcdi(1,k,1:2) and mod_eos derivatives
+//    4.. 7  the same at the lower interface (is = 2)
+//    8, 9   p_src(k), p_src(k+1)                                           p_srcdi(1:2,k)
+//   10..14  tpc_src(1:5,k,T)      15..19  tpc_src(1:5,k,S)
+//   20      difiso(k)             21, 22  temp(k), saln(k) at the new time level          23  unused
+//   24 + 8*(nt-3) ..  passive tracer nt >= 3: trc(k), tpc_src(1:5,k,nt), t_srcdi(1:2,k,nt)
+// The first ND_RSB = 24 doubles (192 bytes, six sectors) are what a thread stages in shared memory.
+constexpr int ND_RSB = 24, F_REC = 0, F_P = 8, F_TPC = 10, F_DIF = 20, F_TLEV = 21;
+constexpr int X_TLEV = 0, X_TPC = 1, X_TSD = 6;   // inside a passive tracer's 8 doubles
+__host__ __device__ constexpr int nd_rs(int T) { return ND_RSB + 8 * (T - 2); }
+// Destination record of interface k (1..kk+1) of cell x: dst[(x*(kk+1) + k-1)*2] = {p_dst(k), p_dstsnp(k)}.
+
 struct NdArgs {
-  const double *p_src, *tsd, *tpc, *rec, *p_dst, *snp;
+  const double *src, *dst;     // column records written by ndiff_prep
   const int *ksmx, *kdmx, *mask;
   const int* faces; int nfaces;   // offsets ix2(i,j) of the wet faces of this direction
-  const double *dpml, *difiso;
-  const double* tlev[NTMAX];   // scalar nt at time level nn, level 1
+  const double* dpml;
   const double *sca, *scbi;    // scuy,scuxi | scvx,scvyi
   const double* puv;           // pu | pv
   double *tflld, *sflld, *tflx, *sflx, *nslp;
@@ -76,17 +92,16 @@ struct NdArgs {
 
 struct Rec { double drdt, drds, t, s; };
 
-// :104-148: Newton search for the position in layer k of column c that is neutral to (tf,sf); the ten
-// polynomial coefficients are loaded once instead of once per iteration
-template <class IX>
-__device__ __forceinline__ double drhoroot(const double* __restrict__ tpc, IX o, IX lev, int kk, int k, double tf, double sf,
+// :104-148: Newton search for the position in a layer that is neutral to (tf,sf); c(q), q = 0..9, are the layer's
+// polynomial coefficients of T and S (loaded once instead of once per iteration)
+template <class CF>
+__device__ __forceinline__ double drhoroot(CF c, double tf, double sf,
                                            double drhodt_l, double drhodt_u, double drhods_l, double drhods_u) {
   const double eps = 1.e-14, x_tol = 1.e-4;
   double x = .5;
   const double ddrdtdx = drhodt_l - drhodt_u, ddrdsdx = drhods_l - drhods_u;
-  const IX bt = o + (IX)(((IT - 1) * kk + k - 1) * 5) * lev, bs = o + (IX)(((IS - 1) * kk + k - 1) * 5) * lev;
-  const double T1 = tpc[bt], T2 = tpc[bt + lev], T3 = tpc[bt + 2 * lev], T4 = tpc[bt + 3 * lev], T5 = tpc[bt + 4 * lev];
-  const double S1 = tpc[bs], S2 = tpc[bs + lev], S3 = tpc[bs + 2 * lev], S4 = tpc[bs + 3 * lev], S5 = tpc[bs + 4 * lev];
+  const double T1 = c(0), T2 = c(1), T3 = c(2), T4 = c(3), T5 = c(4);
+  const double S1 = c(5), S2 = c(6), S3 = c(7), S4 = c(8), S5 = c(9);
   for (int n = 1; n <= 10; ++n) {
     const double dt = tf - (T1 + (T2 + (T3 + (T4 + T5 * x) * x) * x) * x);
     const double ds = sf - (S1 + (S2 + (S3 + (S4 + S5 * x) * x) * x) * x);
@@ -103,54 +118,85 @@ __device__ __forceinline__ double drhoroot(const double* __restrict__ tpc, IX o,
   return x;
 }
 
-// ndiff_prep_jslice (:959-1026) on 0..ii+1 x 0..jj+1 + the destination snapping of ndiff_flx (:491-523)
+// ndiff_prep_jslice (:959-1026) on 0..ii+1 x 0..jj+1 + the destination snapping of ndiff_flx (:491-523) + the
+// column records
+struct PrepIn {
+  const int *ip, *iu, *iv, *ksmx;
+  const double *p_src, *tsd, *tpc, *p_dst, *difiso;
+  const double* tlev[NTMAX];   // scalar nt at time level nn, level 1
+};
 __global__ void __launch_bounds__(128)
-ndiff_prep(Geom g, int mm, int T, const int* __restrict__ ip, const int* __restrict__ iu,
-           const int* __restrict__ iv, const int* __restrict__ ksmx, const double* __restrict__ p_src,
-           const double* __restrict__ tsd, const double* __restrict__ p_dst, int* __restrict__ kdmx,
-           double* __restrict__ rec, double* __restrict__ snp,
+ndiff_prep(Geom g, int mm, int T, PrepIn I, int* __restrict__ kdmx, double* __restrict__ src, double* __restrict__ dst,
            double* __restrict__ utflld, double* __restrict__ usflld, double* __restrict__ vtflld,
            double* __restrict__ vsflld) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i > g.ii + 1) return;
   const long x = ix2(g, i, j), lev = g.lev;
   const int kk = g.kdm;
-  const bool wu = iu[x] == 1, wv = iv[x] == 1;
+  const bool wu = I.iu[x] == 1, wv = I.iv[x] == 1;
   if (wu || wv)
     for (int k = 1; k <= kk; ++k) {
       const long o = x + (long)(k + mm - 1) * lev;
       if (wu) { utflld[o] = 0.; usflld[o] = 0.; }
       if (wv) { vtflld[o] = 0.; vsflld[o] = 0.; }
     }
-  if (ip[x] != 1) return;
-  const double pbot = p_dst[x + (long)kk * lev];
+  if (I.ip[x] != 1) return;
+  const double pbot = I.p_dst[x + (long)kk * lev];
   int kd = kk;
   for (int k = kk; k >= 1; --k)
-    if (p_dst[x + (long)(k - 1) * lev] == pbot) kd = k - 1;
+    if (I.p_dst[x + (long)(k - 1) * lev] == pbot) kd = k - 1;
   kdmx[x] = kd;
-  const int ks = ksmx[x];
-  for (int k = 1; k <= ks; ++k)
-    for (int s = 1; s <= 2; ++s) {
-      const double ps = p_src[x + (long)(k + s - 2) * lev];
-      const double t = tsd[x + (long)(((IT - 1) * kk + k - 1) * 2 + s - 1) * lev];
-      const double sa = tsd[x + (long)(((IS - 1) * kk + k - 1) * 2 + s - 1) * lev];
-      double2* r = reinterpret_cast<double2*>(rec + ((long)((k - 1) * 2 + s - 1) * lev + x) * 4);
-      r[0] = make_double2(eos_drhodt(ps, t, sa), eos_drhods(ps, t, sa));
-      r[1] = make_double2(t, sa);
+  const int ks = I.ksmx[x], RS = nd_rs(T);
+  double* col = src + (long)x * kk * RS;
+  double p_up = I.p_src[x];
+  for (int k = 1; k <= ks; ++k) {
+    double2* r = reinterpret_cast<double2*>(col + (long)(k - 1) * RS);
+    const double p_lo = I.p_src[x + (long)k * lev];
+    const long ot = x + (long)(((IT - 1) * kk + k - 1) * 2) * lev, os = x + (long)(((IS - 1) * kk + k - 1) * 2) * lev;
+    const double t1 = I.tsd[ot], t2 = I.tsd[ot + lev], s1 = I.tsd[os], s2 = I.tsd[os + lev];
+    r[0] = make_double2(eos_drhodt(p_up, t1, s1), eos_drhods(p_up, t1, s1));
+    r[1] = make_double2(t1, s1);
+    r[2] = make_double2(eos_drhodt(p_lo, t2, s2), eos_drhods(p_lo, t2, s2));
+    r[3] = make_double2(t2, s2);
+    const double* ct = I.tpc + x + (long)(((IT - 1) * kk + k - 1) * 5) * lev;
+    const double* cs = I.tpc + x + (long)(((IS - 1) * kk + k - 1) * 5) * lev;
+    r[4] = make_double2(p_up, p_lo);
+    r[5] = make_double2(ct[0], ct[lev]);
+    r[6] = make_double2(ct[2 * lev], ct[3 * lev]);
+    r[7] = make_double2(ct[4 * lev], cs[0]);
+    r[8] = make_double2(cs[lev], cs[2 * lev]);
+    r[9] = make_double2(cs[3 * lev], cs[4 * lev]);
+    const long ol = x + (long)(k - 1) * lev;
+    r[10] = make_double2(I.difiso[ol], I.tlev[0][ol]);
+    r[11] = make_double2(I.tlev[1][ol], 0.);
+    for (int nt = 3; nt <= T; ++nt) {
+      const double* cn = I.tpc + x + (long)(((nt - 1) * kk + k - 1) * 5) * lev;
+      const long on = x + (long)(((nt - 1) * kk + k - 1) * 2) * lev;
+      double2* rn = r + 12 + 4 * (nt - 3);
+      rn[0] = make_double2(I.tlev[nt - 1][ol], cn[0]);
+      rn[1] = make_double2(cn[lev], cn[2 * lev]);
+      rn[2] = make_double2(cn[3 * lev], cn[4 * lev]);
+      rn[3] = make_double2(I.tsd[on], I.tsd[on + lev]);
     }
-  // p_dstsnp(1..kdmx+1)
-  double pk = p_dst[x], pk1 = p_dst[x + lev];
-  snp[x] = pk;
+    p_up = p_lo;
+  }
+  // {p_dst(k), p_dstsnp(k)}: p_dstsnp(1..kdmx+1) as in the reference, p_dst below
+  double2* d = reinterpret_cast<double2*>(dst + (long)x * (kk + 1) * 2);
+  double pk = I.p_dst[x], pk1 = I.p_dst[x + lev];
+  d[0] = make_double2(pk, pk);
   double dp_dst_u = pk1 - pk;
   const int kl = min(ks, kd);
   for (int k = 2; k <= kl; ++k) {
-    pk = pk1; pk1 = p_dst[x + (long)k * lev];
+    pk = pk1; pk1 = I.p_dst[x + (long)k * lev];
     const double dp_dst_l = pk1 - pk;
-    const double ps = p_src[x + (long)(k - 1) * lev];
-    snp[x + (long)(k - 1) * lev] = fabs(pk - ps) < fmin(dp_dst_u, dp_dst_l) * ndiff_dstsnp_fac ? ps : pk;
+    const double ps = I.p_src[x + (long)(k - 1) * lev];
+    d[k - 1] = make_double2(pk, fabs(pk - ps) < fmin(dp_dst_u, dp_dst_l) * ndiff_dstsnp_fac ? ps : pk);
     dp_dst_u = dp_dst_l;
   }
-  for (int k = kl + 1; k <= kd + 1; ++k) snp[x + (long)(k - 1) * lev] = p_dst[x + (long)(k - 1) * lev];
+  for (int k = kl + 1; k <= kk + 1; ++k) {
+    const double p = I.p_dst[x + (long)(k - 1) * lev];
+    d[k - 1] = make_double2(p, p);
+  }
 }
 
 // face-owned running sums of the flux convergence of the current destination layer of one side
@@ -179,49 +225,70 @@ struct SideAcc {
 
 // ndiff_flx (:160-953) for the face between cell M (i-1|j-1) and cell P (i,j)
 // 128 threads per block at a register budget of 128 per thread (512 resident threads per SM).
-//
-// Index arithmetic: every access is `array[cell + level * lev]`.  IX is the type that arithmetic is done in:
-// `unsigned` when the largest element index of the call ((5*kk*T + 1) * lev) fits 32 bits (one IMAD for the
-// index and one IMAD.WIDE for the address instead of the six instructions of a 64-bit product; address
-// arithmetic was a third of all instructions of this kernel), `long` otherwise (ndiff_dev chooses).  The cell
-// offsets x, xm are part of the index, so no per-array cell pointers are held in registers.
+// IX is the type the index arithmetic of the level-strided OUTPUT arrays is done in (`unsigned` when every
+// element index fits 32 bits - one IMAD and one IMAD.WIDE per address instead of a 64-bit product - else `long`).
+// STG: how the record of a column's current source layer is held (option ndiff_stage):
+//   1  staged in shared memory when the column steps to the layer (one batch of loads)
+//   0  read from the column record in global memory whenever needed (no shared memory, the whole L1 is cache)
+//   2  as 0, with an L1 prefetch of the record's lines when the column steps to the layer
+//   3  as 1, with an L2 prefetch of the NEXT layer's record (default; tnx1v4, u + v faces: 12.9 / 12.2 / 12.5 / 10.3 ms
+//      for 0 / 1 / 2 / 3: the prefetch turns the DRAM round trip of every layer step into an L2 hit)
 constexpr int ND_BS = 128;
-template <int DIR, int NT, class IX>
+#ifdef BLOM_HOST_EMUL
+__device__ __forceinline__ void nd_prefetch_l1(const void*) {}
+__device__ __forceinline__ void nd_prefetch_l2(const void*) {}
+#else
+__device__ __forceinline__ void nd_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void nd_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
+template <int DIR, int NT, class IX, int STG>
 __global__ void __launch_bounds__(ND_BS, 512 / ND_BS)
 ndiff_face(Geom g, NdArgs A) {
   // wet faces only: thread t owns face A.faces[t] (linear (i,j) offset of the face's plus-side cell).  A thread
-  // of a land face would idle for the whole life of its warp - the kernel is issue- and latency-bound, so the
+  // of a land face would idle for the whole life of its warp - the kernel is latency-bound, so the
   // compacted list (built once, the masks are static) removes that share of the warps outright.
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= A.nfaces) return;
+  const int tx = threadIdx.x;
   const IX x = (IX)A.faces[t];
   const IX xm = x - (IX)(DIR == 0 ? 1 : g.ldi), lev = (IX)g.lev;
   const int kk = g.kdm, T = NT > 0 ? NT : A.T, mm = A.mm;
-  // the slice data of a cell column o (= x or xm) with the reference's 1-based indices
-  auto psd = [&](IX o, int s, int k) { return A.p_src[o + (IX)(k + s - 2) * lev]; };   // p_srcdi(s,k) = p_src(k+s-1)
-  auto tsrcdi = [&](IX o, int s, int k, int nt) { return A.tsd[o + (IX)(((nt - 1) * kk + k - 1) * 2 + s - 1) * lev]; };
-  auto tpcc = [&](IX o, int c, int k, int nt) { return A.tpc[o + (IX)(((nt - 1) * kk + k - 1) * 5 + c - 1) * lev]; };
-  auto pdst = [&](IX o, int k) { return A.p_dst[o + (IX)(k - 1) * lev]; };
-  auto dstsnp = [&](IX o, int k) { return A.snp[o + (IX)(k - 1) * lev]; };
-  auto rec_at = [&](IX o, int is, int ks) {
-    const double2* r = reinterpret_cast<const double2*>(A.rec) + (o + (IX)((ks - 1) * 2 + is - 1) * lev) * 2;
-    const double2 a = r[0], b = r[1];
-    return Rec{a.x, a.y, b.x, b.y};
+  const int RS = NT > 0 ? nd_rs(NT) : nd_rs(T);
+  // column records of the two cells (side 0 = M, 1 = P)
+  const double* const col_m = A.src + (long)xm * kk * RS;
+  const double* const col_p = A.src + (long)x * kk * RS;
+  const double* const dst_m = A.dst + (long)xm * (kk + 1) * 2;
+  const double* const dst_p = A.dst + (long)x * (kk + 1) * 2;
+  // The records of the current source layers of the two columns, staged: sm[side*ND_RSB + field][thread].
+  __shared__ double sm[(STG & 1) ? 2 * ND_RSB : 1][ND_BS];
+  const double* lrec_m = col_m;   // records of the current layers (STG != 1)
+  const double* lrec_p = col_p;
+#define SM(side, f) ((STG & 1) ? sm[(STG & 1) ? (side) * ND_RSB + (f) : 0][tx] : ((side) ? lrec_p : lrec_m)[f])
+  auto stage = [&](int side, int k) {
+    const double* rec = (side ? col_p : col_m) + (k - 1) * RS;
+    if (STG & 1) {
+      const double2* r = reinterpret_cast<const double2*>(rec);
+      double2 v[ND_RSB / 2];
+#pragma unroll
+      for (int q = 0; q < ND_RSB / 2; ++q) v[q] = r[q];
+#pragma unroll
+      for (int q = 0; q < ND_RSB / 2; ++q) {
+        sm[(STG & 1) ? side * ND_RSB + 2 * q : 0][tx] = v[q].x;
+        sm[(STG & 1) ? side * ND_RSB + 2 * q + 1 : 0][tx] = v[q].y;
+      }
+      if (STG == 3 && k < kk) { nd_prefetch_l2(rec + RS); nd_prefetch_l2(rec + RS + 16); }
+    } else {
+      if (side) lrec_p = rec; else lrec_m = rec;
+      if (STG == 2) { nd_prefetch_l1(rec); nd_prefetch_l1(rec + 16); }
+    }
   };
-  // :62-74, :76-102 (only used when the coefficient cache is off)
-  auto peval = [&](IX o, int k, int nt, double xx) {
-    const double c5 = tpcc(o, 5, k, nt), c4 = tpcc(o, 4, k, nt), c3 = tpcc(o, 3, k, nt), c2 = tpcc(o, 2, k, nt),
-                 c1 = tpcc(o, 1, k, nt);
-    return (((c5 * xx + c4) * xx + c3) * xx + c2) * xx + c1;
-  };
-  auto pmeval = [&](IX o, int k, int nt, double x0, double x1) {
-    const double c1_2 = 1. / 2., c1_3 = 1. / 3., c1_4 = 1. / 4., c1_5 = 1. / 5.;
-    const double b5 = c1_5 * tpcc(o, 5, k, nt);
-    const double b4 = b5 * x1 + c1_4 * tpcc(o, 4, k, nt);
-    const double b3 = b4 * x1 + c1_3 * tpcc(o, 3, k, nt);
-    const double b2 = b3 * x1 + c1_2 * tpcc(o, 2, k, nt);
-    const double b1 = b2 * x1 + tpcc(o, 1, k, nt);
-    return (((b5 * x0 + b4) * x0 + b3) * x0 + b2) * x0 + b1;
+  // unstaged reads (layers other than the current ones): p_srcdi(s,k) = p_src(k+s-1), p_dst(k), p_dstsnp(k)
+  auto psd = [&](int side, int s, int k) { return (side ? col_p : col_m)[(k - 1) * RS + F_P + s - 1]; };
+  auto pdst = [&](int side, int k) { return (side ? dst_p : dst_m)[(k - 1) * 2]; };
+  auto dstsnp = [&](int side, int k) { return (side ? dst_p : dst_m)[(k - 1) * 2 + 1]; };
+  auto srec = [&](int side, int is) {   // interface record (is) of the staged layer
+    const int f = F_REC + 4 * (is - 1);
+    return Rec{SM(side, f), SM(side, f + 1), SM(side, f + 2), SM(side, f + 3)};
   };
   const int ksmx_m = A.ksmx[xm], ksmx_p = A.ksmx[x], kdmx_m = A.kdmx[xm], kdmx_p = A.kdmx[x];
   const double cdiff = A.delt1 * A.sca[x] * A.scbi[x];          // :1064 / :1126
@@ -248,7 +315,7 @@ ndiff_face(Geom g, NdArgs A) {
   // visits exactly the same (kd, ks) combinations, so the interpolated values are identical and the two
   // lists of up to 4*(kk+1) doubles per thread never exist.
   int kd_sl = 1;
-  double pd_sl = .5 * (pdst(xm, 1) + pdst(x, 1)), s_prev = 0., p_prev = 0.;
+  double pd_sl = .5 * (pdst(0, 1) + pdst(1, 1)), s_prev = 0., p_prev = 0.;
   auto emit_slope = [&](double sl, double pr) {
     nns = nns + 1;
     while (kd_sl <= kk && !(pd_sl > pr)) {
@@ -258,38 +325,42 @@ ndiff_face(Geom g, NdArgs A) {
         A.nslp[x + (IX)(kd_sl - 1) * lev] = q * s_prev + (1. - q) * sl;
       }
       kd_sl = kd_sl + 1;
-      if (kd_sl <= kk) pd_sl = .5 * (pdst(xm, kd_sl) + pdst(x, kd_sl));
+      if (kd_sl <= kk) pd_sl = .5 * (pdst(0, kd_sl) + pdst(1, kd_sl));
     }
     s_prev = sl; p_prev = pr;
   };
 
   // ---- first search: neutral interfaces anchored at source layer interfaces (:212-406)
   if (A.surface_align) {
-    pml = .5 * (psd(xm, 1, 1) + A.dpml[xm] + psd(x, 1, 1) + A.dpml[x]);
+    pml = .5 * (psd(0, 1, 1) + A.dpml[xm] + psd(1, 1, 1) + A.dpml[x]);
     kssa_m = 2;
     while (kssa_m <= ksmx_m) {
-      if (psd(xm, 1, kssa_m) > pml) break;
+      if (psd(0, 1, kssa_m) > pml) break;
       kssa_m = kssa_m + 1;
     }
     kssa_p = 2;
     while (kssa_p <= ksmx_p) {
-      if (psd(x, 1, kssa_p) > pml) break;
+      if (psd(1, 1, kssa_p) > pml) break;
       kssa_p = kssa_p + 1;
     }
     is_m = 1; ks_m = kssa_m; is_p = 1; ks_p = kssa_p;
     p_ni_m_prev = pml; p_ni_p_prev = pml;
   } else {
     is_m = 1; ks_m = 1; is_p = 1; ks_p = 1;
-    p_ni_m_prev = psd(xm, 1, 1); p_ni_p_prev = psd(x, 1, 1);
+    p_ni_m_prev = psd(0, 1, 1); p_ni_p_prev = psd(1, 1, 1);
   }
-  if (ks_m <= ksmx_m && ks_p <= ksmx_p) { rm = rec_at(xm, is_m, ks_m); rp = rec_at(x, is_p, ks_p); drho_curr = drho_at(); }
+  if (ks_m <= ksmx_m && ks_p <= ksmx_p) {
+    stage(0, ks_m); stage(1, ks_p);
+    rm = srec(0, is_m); rp = srec(1, is_p); drho_curr = drho_at();
+  }
 
   // search_loop1.  The reference handles the minus and the plus column in separate, mirrored code blocks
   // (root search in M when drho < 0, in P when drho > 0; advance M, then advance P).  Lanes of a warp sit in
   // different blocks at the same time, so the mirrored blocks are written ONCE with the column chosen per
-  // lane (`side`: 0 = M, offset xm; 1 = P, offset x): lanes that advance M and lanes that advance P, or that
-  // solve for a root in M and in P, then execute together instead of one after the other.  The arithmetic
-  // per lane is the reference's (sums are commuted only where a + b == b + a exactly).
+  // lane (`side`: 0 = M, 1 = P): lanes that advance M and lanes that advance P, or that solve for a root in
+  // M and in P, then execute together instead of one after the other.  The arithmetic per lane is the
+  // reference's (sums are commuted only where a + b == b + a exactly).  Every read of this loop is of the
+  // current layer of a column, i.e. of the staged records.
   {
     bool done1 = false;
     while (!done1 && ks_m <= ksmx_m && ks_p <= ksmx_p) {
@@ -299,26 +370,24 @@ ndiff_face(Geom g, NdArgs A) {
       if (is_m + ks_m > 2 && is_p + ks_p > 2) {
         const bool rootm = drho_neg && is_m == 2, rootp = drho_pos && is_p == 2;
         if (rootm || rootp) {
-          // layer kr of the searched column (offset o) against the fixed interface fx of the other column
-          const IX o = rootm ? xm : x;
-          const int kr = rootm ? ks_m : ks_p;
+          // the current layer of the searched column (side sr) against the fixed interface fx of the other column
+          const int sr = rootm ? 0 : 1;
           const Rec fx = rootm ? rp : rm;
-          const double2* r1 = reinterpret_cast<const double2*>(A.rec) + (o + (IX)((kr - 1) * 2) * lev) * 2;
-          const double2 u1 = r1[0], l1 = r1[(IX)2 * lev];
-          const double drhodt_x0 = .5 * (u1.x + fx.drdt), drhodt_x1 = .5 * (l1.x + fx.drdt);
-          const double drhods_x0 = .5 * (u1.y + fx.drds), drhods_x1 = .5 * (l1.y + fx.drds);
-          const double x_ni = drhoroot<IX>(A.tpc, o, lev, kk, kr, fx.t, fx.s, drhodt_x1, drhodt_x0, drhods_x1, drhods_x0);
-          const double p_ni = psd(o, 2, kr) * x_ni + psd(o, 1, kr) * (1. - x_ni);
+          const double drhodt_x0 = .5 * (SM(sr, F_REC) + fx.drdt), drhodt_x1 = .5 * (SM(sr, F_REC + 4) + fx.drdt);
+          const double drhods_x0 = .5 * (SM(sr, F_REC + 1) + fx.drds), drhods_x1 = .5 * (SM(sr, F_REC + 5) + fx.drds);
+          const double x_ni = drhoroot([&](int q) { return SM(sr, F_TPC + q); }, fx.t, fx.s, drhodt_x1, drhodt_x0,
+                                       drhods_x1, drhods_x0);
+          const double p_ni = SM(sr, F_P + 1) * x_ni + SM(sr, F_P) * (1. - x_ni);
           if (p_ni > (rootm ? p_ni_m_prev : p_ni_p_prev)) {
             // pressure of the fixed interface in its own column
-            const double pe = rootm ? psd(x, is_p, ks_p) : psd(xm, is_m, ks_m);
+            const double pe = rootm ? SM(1, F_P + is_p - 1) : SM(0, F_P + is_m - 1);
             if (rootm) { p_ni_m_prev = p_ni; PNP(is_p, ks_p) = p_ni; }
             else { p_ni_p_prev = p_ni; PNM(is_m, ks_m) = p_ni; }
             const double pa = rootm ? pe : p_ni, pb = rootm ? p_ni : pe;   // (plus side) - (minus side)
             emit_slope(-cnslp * (pa - pb), .5 * (pa + pb));
           }
         } else if (drho_zero) {
-          const double pm = psd(xm, is_m, ks_m), pp = psd(x, is_p, ks_p);
+          const double pm = SM(0, F_P + is_m - 1), pp = SM(1, F_P + is_p - 1);
           PNP(is_p, ks_p) = pm;
           PNM(is_m, ks_m) = pp;
           emit_slope(-cnslp * (pp - pm), .5 * (pp + pm));
@@ -335,13 +404,13 @@ ndiff_face(Geom g, NdArgs A) {
           ks = ks + 1;
           if (ks > (side ? ksmx_p : ksmx_m)) { if (side) ks_p = ks; else ks_m = ks; done1 = true; break; }
           is = 1;
+          stage(side, ks);
         }
-        const IX o = side ? x : xm;
-        const Rec r = rec_at(o, is, ks);
+        const Rec r = srec(side, is);
         if (side) { rp = r; is_p = is; ks_p = ks; } else { rm = r; is_m = is; ks_m = ks; }
         drho_curr = drho_at();
         if ((side ? drho_curr - drho_prev : drho_prev - drho_curr) > rho_eps) {
-          if (is == 2 && psd(o, 2, ks) - psd(o, 1, ks) > onemm) {
+          if (is == 2 && SM(side, F_P + 1) - SM(side, F_P) > onemm) {
             if (side) stab_p |= 1ull << (ks - 1); else stab_m |= 1ull << (ks - 1);
           }
           if (then_p) { then_p = false; side = 1; continue; }
@@ -366,35 +435,35 @@ ndiff_face(Geom g, NdArgs A) {
       else { kssa_p = kssa_p + 1; issa_p = 1; }
     }
     if (kssa_m > ksmx_m || kssa_p > ksmx_p) {
-      const double pbm = psd(xm, 2, ksmx_m), pbp = psd(x, 2, ksmx_p);
-      PNM(1, 1) = psd(xm, 1, 1);
+      const double pbm = psd(0, 2, ksmx_m), pbp = psd(1, 2, ksmx_p);
+      PNM(1, 1) = psd(0, 1, 1);
       for (ks_m = 1; ks_m <= ksmx_m - 1; ++ks_m) {
-        if (psd(xm, 1, ks_m) > pbp) break;
-        const double p_ni = fmin(psd(xm, 2, ks_m), pbp);
+        if (psd(0, 1, ks_m) > pbp) break;
+        const double p_ni = fmin(psd(0, 2, ks_m), pbp);
         PNM(1, ks_m + 1) = p_ni;
         PNM(2, ks_m) = p_ni;
         stab_m |= 1ull << (ks_m - 1);
       }
-      PNP(1, 1) = psd(x, 1, 1);
+      PNP(1, 1) = psd(1, 1, 1);
       for (ks_p = 1; ks_p <= ksmx_p - 1; ++ks_p) {
-        if (psd(x, 1, ks_p) > pbm) break;
-        const double p_ni = fmin(psd(x, 2, ks_p), pbm);
+        if (psd(1, 1, ks_p) > pbm) break;
+        const double p_ni = fmin(psd(1, 2, ks_p), pbm);
         PNP(1, ks_p + 1) = p_ni;
         PNP(2, ks_p) = p_ni;
         stab_p |= 1ull << (ks_p - 1);
       }
     } else {
       double p1_m, p2_m, p1_p, p2_p;
-      if (psd(xm, issa_m, kssa_m) < PNP(issa_p, kssa_p)) {
-        p1_m = psd(xm, 1, 1); p2_m = psd(xm, issa_m, kssa_m);
-        p1_p = psd(x, 1, 1); p2_p = PNM(issa_m, kssa_m);
+      if (psd(0, issa_m, kssa_m) < PNP(issa_p, kssa_p)) {
+        p1_m = psd(0, 1, 1); p2_m = psd(0, issa_m, kssa_m);
+        p1_p = psd(1, 1, 1); p2_p = PNM(issa_m, kssa_m);
       } else {
-        p1_m = psd(xm, 1, 1); p2_m = PNP(issa_p, kssa_p);
-        p1_p = psd(x, 1, 1); p2_p = psd(x, issa_p, kssa_p);
+        p1_m = psd(0, 1, 1); p2_m = PNP(issa_p, kssa_p);
+        p1_p = psd(1, 1, 1); p2_p = psd(1, issa_p, kssa_p);
       }
       PNM(1, 1) = p1_p;
       for (ks_m = 1; ks_m <= kssa_m - 1; ++ks_m) {
-        const double pl = psd(xm, 2, ks_m);
+        const double pl = psd(0, 2, ks_m);
         const double p_ni = ((pl - p1_m) * p2_p + (p2_m - pl) * p1_p) / (p2_m - p1_m);
         PNM(1, ks_m + 1) = p_ni;
         PNM(2, ks_m) = p_ni;
@@ -402,7 +471,7 @@ ndiff_face(Geom g, NdArgs A) {
       }
       PNP(1, 1) = p1_m;
       for (ks_p = 1; ks_p <= kssa_p - 1; ++ks_p) {
-        const double pl = psd(x, 2, ks_p);
+        const double pl = psd(1, 2, ks_p);
         const double p_ni = ((pl - p1_p) * p2_m + (p2_p - pl) * p1_m) / (p2_p - p1_p);
         PNP(1, ks_p + 1) = p_ni;
         PNP(2, ks_p) = p_ni;
@@ -414,67 +483,36 @@ ndiff_face(Geom g, NdArgs A) {
   // ---- second search: neutral layers and their fluxes (:525-911)
   // The reference keeps the previous/current neutral interface in two slots that swap (nip/nic); here they
   // are plain "prev"/"cur" registers and cur is copied to prev when an interface has been found (a slot
-  // index would put them in local memory).  The polynomial coefficients of the current source layer of
-  // each side (tpc_src, 5 per scalar) are cached while ks_m / ks_p do not change: peval and pmeval
-  // are evaluated for every neutral interface found inside a layer, which took a quarter of all
-  // instructions as strided loads and their address arithmetic.  The branches of the case analysis only
-  // decide HOW the interface values are obtained (ev_m/ev_p); the evaluation itself and the flux
-  // computation run after the branches have reconverged.
+  // index would put them in local memory).  Whenever a column lands on a new source layer that layer's record
+  // is staged, so the polynomial coefficients, interface values, diffusivity and layer means of the current
+  // layers are shared-memory reads (peval and pmeval are evaluated for every neutral interface found inside a
+  // layer).  The branches of the case analysis only decide HOW the interface values are obtained (ev_m/ev_p);
+  // the evaluation itself and the flux computation run after the branches have reconverged.
   SideAcc<NT, IX> accm, accp;
   accm.init(A.cvm, x, lev, kk, T);
   accp.init(A.cvp, x, lev, kk, T);
   {
     constexpr int NTC = NT > 0 ? NT : NTMAX;
-    constexpr bool CACHE = NT > 0 && NT <= 3;     // register budget: 10 doubles per scalar
-    // the cache lives in shared memory, one column of 5*NT doubles per thread and side ([..][threadIdx.x],
-    // conflict-free): in registers its 40 values pushed the searches' state into spills at 128 registers
-    // rows 0..2*NTC*5-1: coefficients (minus side, then plus side); then per side the layer's diffusivity and its
-    // NTC layer means (difiso(ks), scalar(ks) at the new time level), which every flux of the layer reads as well
-    constexpr int LM = 2 * NTC * 5;
-    __shared__ double cf_sm[CACHE ? LM + 2 * (NTC + 1) : 1][ND_BS];
-    struct CoefRef {   // the five coefficients of scalar nt of one side, as the polynomial helpers read them
-      const double (*col)[ND_BS]; int t;
-      __device__ __forceinline__ double operator[](int c5) const { return col[c5][t]; }
+    // scalar nt of the current layer of a column: T and S from the staged record, passive tracers from the
+    // column record itself (their 8 doubles follow the staged part)
+    struct CoefRef {   // the five polynomial coefficients, as the polynomial helpers read them
+      const double (*col)[ND_BS]; const double* g5; int t;
+      __device__ __forceinline__ double operator[](int c5) const { return g5 ? g5[c5] : col[c5][t]; }
     };
-    auto cfm = [&](int nt) { return CoefRef{&cf_sm[CACHE ? (nt - 1) * 5 : 0], (int)threadIdx.x}; };
-    auto cfp = [&](int nt) { return CoefRef{&cf_sm[CACHE ? (NTC + nt - 1) * 5 : 0], (int)threadIdx.x}; };
-    int kc_m = 0, kc_p = 0;                        // layers whose coefficients are cached
-    auto coef = [&](IX o, int k, int nt, int row0) {
-      const IX b5 = o + (IX)(((nt - 1) * kk + k - 1) * 5) * lev;
-      const double c0 = A.tpc[b5], c1 = A.tpc[b5 + lev], c2 = A.tpc[b5 + 2 * lev], c3 = A.tpc[b5 + 3 * lev],
-                   c4 = A.tpc[b5 + 4 * lev];
-      double(*o5)[ND_BS] = &cf_sm[CACHE ? row0 : 0];
-      const int tx = threadIdx.x;
-      o5[0][tx] = c0; o5[1][tx] = c1; o5[2][tx] = c2; o5[3][tx] = c3; o5[4][tx] = c4;
+    auto lrec = [&](int side) { return side ? lrec_p : lrec_m; };
+    auto xrec = [&](int side, int nt) {   // passive tracer nt >= 3 in the current layer's record
+      return (side ? col_p + (ks_p - 1) * RS : col_m + (ks_m - 1) * RS) + ND_RSB + 8 * (nt - 3);
     };
-    auto layer_means = [&](IX o, int k, int row0) {
-      const IX ol = o + (IX)(k - 1) * lev;
-      const int tx = threadIdx.x;
-      double v[NTC + 1];
-      v[0] = A.difiso[ol];
-#pragma unroll
-      for (int nt = 1; nt <= NTC; ++nt) v[nt] = A.tlev[nt - 1][ol];
-#pragma unroll
-      for (int nt = 0; nt <= NTC; ++nt) cf_sm[CACHE ? row0 + nt : 0][tx] = v[nt];
+    auto cf = [&](int side, int nt) {
+      return nt > 2    ? CoefRef{nullptr, xrec(side, nt) + X_TPC, tx}
+             : (STG & 1) ? CoefRef{&sm[(STG & 1) ? side * ND_RSB + F_TPC + (nt - 1) * 5 : 0], nullptr, tx}
+                        : CoefRef{nullptr, lrec(side) + F_TPC + (nt - 1) * 5, tx};
     };
-    auto need_m = [&]() {
-      if (CACHE && kc_m != ks_m) {
-#pragma unroll
-        for (int nt = 1; nt <= NTC; ++nt) coef(xm, ks_m, nt, (nt - 1) * 5);
-        layer_means(xm, ks_m, LM);
-        kc_m = ks_m;
-      }
+    auto tsrcdi = [&](int side, int is, int nt) {   // t_srcdi(is, ks, nt)
+      return nt <= 2 ? SM(side, F_REC + 4 * (is - 1) + 1 + nt) : xrec(side, nt)[X_TSD + is - 1];
     };
-    auto need_p = [&]() {
-      if (CACHE && kc_p != ks_p) {
-#pragma unroll
-        for (int nt = 1; nt <= NTC; ++nt) coef(x, ks_p, nt, (NTC + nt - 1) * 5);
-        layer_means(x, ks_p, LM + NTC + 1);
-        kc_p = ks_p;
-      }
-    };
-    auto lmean_m = [&](int nt) { return cf_sm[CACHE ? LM + nt : 0][threadIdx.x]; };             // nt = 0: difiso
-    auto lmean_p = [&](int nt) { return cf_sm[CACHE ? LM + NTC + 1 + nt : 0][threadIdx.x]; };
+    auto lmean = [&](int side, int nt) { return nt <= 2 ? SM(side, F_TLEV + nt - 1) : xrec(side, nt)[X_TLEV]; };
+    int kc_m = 0, kc_p = 0;                        // layers whose records are staged
     auto pe = [&](const CoefRef c, double xx) { return (((c[4] * xx + c[3]) * xx + c[2]) * xx + c[1]) * xx + c[0]; };
     auto pme = [&](const CoefRef c, double x0, double x1) {
       const double c1_2 = 1. / 2., c1_3 = 1. / 3., c1_4 = 1. / 4., c1_5 = 1. / 5.;
@@ -549,8 +587,9 @@ ndiff_face(Geom g, NdArgs A) {
             }
           }
           {
-            const IX o = side ? x : xm;
-            const double ps1 = psd(o, 1, ks), ps2 = psd(o, 2, ks), ps_n = psd(o, isn, ksn);
+            if (ks != (side ? kc_p : kc_m)) { stage(side, ks); if (side) kc_p = ks; else kc_m = ks; }
+            const double ps1 = SM(side, F_P), ps2 = SM(side, F_P + 1);
+            const double ps_n = ksn == ks ? (isn == 1 ? ps1 : ps2) : psd(side, isn, ksn);
             const double pn_n = pn[2 * ksn + isn - 1], pn_c = pn[2 * ks + is - 1];
             if (side) { is_p = is; ks_p = ks; psp1 = ps1; psp2 = ps2; psp_n = ps_n; pnp_n = pn_n; pnp_c = pn_c; }
             else { is_m = is; ks_m = ks; psm1 = ps1; psm2 = ps2; psm_n = ps_n; pnm_n = pn_n; pnm_c = pn_c; }
@@ -573,12 +612,12 @@ ndiff_face(Geom g, NdArgs A) {
       if (advance_dst_m) {
         kd_m = kd_m + 1;
         if (kd_m > kdmx_m) break;
-        snp_m = dstsnp(xm, kd_m + 1);
+        snp_m = dstsnp(0, kd_m + 1);
       }
       if (advance_dst_p) {
         kd_p = kd_p + 1;
         if (kd_p > kdmx_p) break;
-        snp_p = dstsnp(x, kd_p + 1);
+        snp_p = dstsnp(1, kd_p + 1);
       }
       {
         bool out = false;
@@ -586,14 +625,14 @@ ndiff_face(Geom g, NdArgs A) {
         while (snp_m <= lim_m) {
           kd_m = kd_m + 1;
           if (kd_m > kdmx_m) { out = true; break; }
-          snp_m = dstsnp(xm, kd_m + 1);
+          snp_m = dstsnp(0, kd_m + 1);
         }
         if (out) break;
         const double lim_p = fmax(psp1, p_prev_p);
         while (snp_p <= lim_p) {
           kd_p = kd_p + 1;
           if (kd_p > kdmx_p) { out = true; break; }
-          snp_p = dstsnp(x, kd_p + 1);
+          snp_p = dstsnp(1, kd_p + 1);
         }
         if (out) break;
       }
@@ -707,7 +746,6 @@ ndiff_face(Geom g, NdArgs A) {
       if (found_ni) {  // :795-907
         // NOTE: advance_src_* set above only act at the top of the next iteration: is/ks are still the
         // ones the interface was found for
-        need_m(); need_p();
         {
           const double xm_ = (p_cur_m - psm1) / (psm2 - psm1), xp_ = (p_cur_p - psp1) / (psp2 - psp1);
           x_cur_m = ev_m == 2 ? (double)(is_m - 1) : xm_;
@@ -716,29 +754,24 @@ ndiff_face(Geom g, NdArgs A) {
 #pragma unroll
         for (int nt = 1; nt <= NTC; ++nt)
           if (nt <= T) {
-            t_cur_m[nt - 1] = ev_m == 2 ? tsrcdi(xm, is_m, ks_m, nt)
-                                        : (CACHE ? pe(cfm(nt), x_cur_m) : peval(xm, ks_m, nt, x_cur_m));
-            t_cur_p[nt - 1] = ev_p == 2 ? tsrcdi(x, is_p, ks_p, nt)
-                                        : (CACHE ? pe(cfp(nt), x_cur_p) : peval(x, ks_p, nt, x_cur_p));
+            t_cur_m[nt - 1] = ev_m == 2 ? tsrcdi(0, is_m, nt) : pe(cf(0, nt), x_cur_m);
+            t_cur_p[nt - 1] = ev_p == 2 ? tsrcdi(1, is_p, nt) : pe(cf(1, nt), x_cur_p);
           }
-        const double dp_ni_m = fmin(p_cur_m - p_prev_m, pdst(xm, kd_m + 1) - pdst(xm, kd_m));
-        const double dp_ni_p = fmin(p_cur_p - p_prev_p, pdst(x, kd_p + 1) - pdst(x, kd_p));
+        const double dp_ni_m = fmin(p_cur_m - p_prev_m, pdst(0, kd_m + 1) - pdst(0, kd_m));
+        const double dp_ni_p = fmin(p_cur_p - p_prev_p, pdst(1, kd_p + 1) - pdst(1, kd_p));
         const double dp_ni = 2. * dp_ni_m * dp_ni_p / fmax(dp_ni_m + dp_ni_p, 2. * dp_eps);
-        if (ks_m == ks_m_prev && ks_p == ks_p_prev && p_prev_m >= dstsnp(xm, kd_m) && p_cur_m <= snp_m &&
-            p_prev_p >= dstsnp(x, kd_p) && p_cur_p <= snp_p && dp_ni > 2. * dp_eps) {
+        if (ks_m == ks_m_prev && ks_p == ks_p_prev && p_prev_m >= dstsnp(0, kd_m) && p_cur_m <= snp_m &&
+            p_prev_p >= dstsnp(1, kd_p) && p_cur_p <= snp_p && dp_ni > 2. * dp_eps) {
           accm.advance(kd_m);
           accp.advance(kd_p);
-          const double q = .5 * cdiff * (CACHE ? lmean_m(0) + lmean_p(0)
-                                               : A.difiso[xm + (IX)(ks_m - 1) * lev] + A.difiso[x + (IX)(ks_p - 1) * lev]) * dp_ni;
+          const double q = .5 * cdiff * (SM(0, F_DIF) + SM(1, F_DIF)) * dp_ni;
           double tflx = 0., sflx = 0.;
           bool ts_ok = true;
 #pragma unroll
           for (int nt = 1; nt <= NTC; ++nt)
             if (nt <= T) {
-              const double d = CACHE ? pme(cfm(nt), x_prev_m, x_cur_m) - pme(cfp(nt), x_prev_p, x_cur_p)
-                                     : pmeval(xm, ks_m, nt, x_prev_m, x_cur_m) - pmeval(x, ks_p, nt, x_prev_p, x_cur_p);
-              const double cm = CACHE ? lmean_m(nt) : A.tlev[nt - 1][xm + (IX)(ks_m - 1) * lev];
-              const double cp = CACHE ? lmean_p(nt) : A.tlev[nt - 1][x + (IX)(ks_p - 1) * lev];
+              const double d = pme(cf(0, nt), x_prev_m, x_cur_m) - pme(cf(1, nt), x_prev_p, x_cur_p);
+              const double cm = lmean(0, nt), cp = lmean(1, nt);
               const bool ok = d * (cm - cp) >= 0. && d * (t_prev_m[nt - 1] - t_prev_p[nt - 1]) >= 0. &&
                               d * (t_cur_m[nt - 1] - t_cur_p[nt - 1]) >= 0.;
               if (nt == IT) { tflx = q * d; ts_ok = ok; }
@@ -792,6 +825,7 @@ ndiff_face(Geom g, NdArgs A) {
   for (; kd_sl <= kk; ++kd_sl) A.nslp[x + (IX)(kd_sl - 1) * lev] = nns == 0 ? 0. : s_prev;
 #undef PNM
 #undef PNP
+#undef SM
 }
 
 // ndiff_update_trc_jslice (:1152-1175) with the gather of the four face contributions
@@ -831,26 +865,29 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   if (T > NTMAX) throw std::runtime_error("ndiff: more than 8 diffused scalars are not compiled in");
   const bool surface_align = c.option("ndiff_surface_align", "1") == "1";   // namelist default .true.
   if (surface_align) halo_update(c.dev("dpml"), 1, 1, 1, halo_ps);
-  double* rec = c.owned("_nd_rec", 8 * kk);   // 2*kk interface records of 4 doubles per cell
-  double* snp = c.owned("_nd_dstsnp", kk + 1);
+  const int RS = nd_rs(T);
+  double* src = c.owned("_nd_src", kk * RS);          // column records: kk records of RS doubles per cell
+  double* dst = c.owned("_nd_dst", 2 * (kk + 1));     // {p_dst, p_dstsnp} per destination interface and cell
   int* kdmx = c.owned_int("_nd_kdmx", 1);
   double* ucm = c.owned("_nd_ucm", kk * T);
   double* ucp = c.owned("_nd_ucp", kk * T);
   double* vcm = c.owned("_nd_vcm", kk * T);
   double* vcp = c.owned("_nd_vcp", kk * T);
 
-  LAUNCH(ndiff_prep, dim3(cdiv(g.ii + 2, 128), g.jj + 2), 128, 0, g, mm, T, c.idev("ip"), c.idev("iu"), c.idev("iv"),
-         c.idev("nd_ksmx"), c.dev("nd_p_src"), c.dev("nd_t_srcdi"), c.dev("nd_p_dst"), kdmx, rec, snp,
+  PrepIn I{};
+  I.ip = c.idev("ip"); I.iu = c.idev("iu"); I.iv = c.idev("iv"); I.ksmx = c.idev("nd_ksmx");
+  I.p_src = c.dev("nd_p_src"); I.tsd = c.dev("nd_t_srcdi"); I.tpc = c.dev("nd_tpc_src"); I.p_dst = c.dev("nd_p_dst");
+  I.difiso = c.dev("difiso");
+  I.tlev[0] = c.dev("temp") + (long)nn * g.lev;
+  I.tlev[1] = c.dev("saln") + (long)nn * g.lev;
+  for (int nt = 3; nt <= T; ++nt) I.tlev[nt - 1] = c.dev("trc") + (long)(nn + (nt - 3) * 2 * kk) * g.lev;
+  LAUNCH(ndiff_prep, dim3(cdiv(g.ii + 2, 128), g.jj + 2), 128, 0, g, mm, T, I, kdmx, src, dst,
          c.dev("utflld"), c.dev("usflld"), c.dev("vtflld"), c.dev("vsflld"));
 
   NdArgs A{};
-  A.p_src = c.dev("nd_p_src"); A.tsd = c.dev("nd_t_srcdi"); A.tpc = c.dev("nd_tpc_src");
-  A.rec = rec; A.p_dst = c.dev("nd_p_dst"); A.snp = snp;
+  A.src = src; A.dst = dst;
   A.ksmx = c.idev("nd_ksmx"); A.kdmx = kdmx;
-  A.dpml = c.dev("dpml"); A.difiso = c.dev("difiso");
-  A.tlev[0] = c.dev("temp") + (long)nn * g.lev;
-  A.tlev[1] = c.dev("saln") + (long)nn * g.lev;
-  for (int nt = 3; nt <= T; ++nt) A.tlev[nt - 1] = c.dev("trc") + (long)(nn + (nt - 3) * 2 * kk) * g.lev;
+  A.dpml = c.dev("dpml");
   A.delt1 = c.scalar("delt1"); A.mm = mm; A.T = T; A.surface_align = surface_align ? 1 : 0;
 
   NdArgs U = A;
@@ -895,20 +932,24 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   }
   U.faces = list_u; U.nfaces = (int)c.sc["_nd_nfaces_u"];
   V.faces = list_v; V.nfaces = (int)c.sc["_nd_nfaces_v"];
-  // 32-bit index arithmetic in ndiff_face when every element index of the call fits (tpc_src is the largest array:
-  // 5*kk*T levels; the interface records are addressed as double2, 4*kk levels of pairs): true for every tile that
-  // fits a B200 with T <= 3, e.g. tnx0.25v4 on one GPU; the 64-bit instantiation covers the rest
-  const bool ix32 = ((long)5 * kk * T + 2) * g.lev < (1l << 32) && ((long)8 * kk + 4) * g.lev < (1l << 32);
+  // 32-bit index arithmetic for the level-strided output arrays of ndiff_face when every element index fits (the
+  // face buffers are the largest: kk*T levels); the 64-bit instantiation covers the rest
+  const bool ix32 = ((long)kk * std::max(T, 2) + 2) * g.lev < (1l << 32);
   const dim3 gu(std::max(1, cdiv(U.nfaces, ND_BS))), gv(std::max(1, cdiv(V.nfaces, ND_BS)));
-#define ND_LAUNCH(NT_, IX_)                                                                        \
+  const int stg = std::stoi(c.option("ndiff_stage", "3"));
+  if (stg < 0 || stg > 3) throw std::runtime_error("ndiff: ndiff_stage must be 0, 1, 2 or 3");
+#define ND_LAUNCH(NT_, IX_, STG_)                                                                  \
   do {                                                                                             \
-    LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, IX_>), gu, ND_BS, 0, g, U);                  \
-    LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, NT_, IX_>), gv, ND_BS, 0, g, V);                  \
+    LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, IX_, STG_>), gu, ND_BS, 0, g, U);            \
+    LAUNCH_NAMED("ndiff_face<v>", (ndiff_face<1, NT_, IX_, STG_>), gv, ND_BS, 0, g, V);            \
   } while (0)
 #define ND_FACE(NT_)                                                                               \
   do {                                                                                             \
-    if (ix32) ND_LAUNCH(NT_, unsigned);                                                            \
-    else ND_LAUNCH(NT_, long);                                                                     \
+    if (!ix32) ND_LAUNCH(NT_, long, 3);                                                            \
+    else if (stg == 0) ND_LAUNCH(NT_, unsigned, 0);                                                \
+    else if (stg == 2) ND_LAUNCH(NT_, unsigned, 2);                                                \
+    else if (stg == 3) ND_LAUNCH(NT_, unsigned, 3);                                                \
+    else ND_LAUNCH(NT_, unsigned, 1);                                                              \
   } while (0)
   if (T == 2) { ND_FACE(2); }
   else if (T == 3) { ND_FACE(3); }

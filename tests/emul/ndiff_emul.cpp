@@ -16,7 +16,7 @@ struct EmuNdiff {
   // geometry
   int ii, jj, kdm, nb, ldi, ldj, ntr;
   // time-level arguments and options
-  int mm, nn, surface_align, ix64;   // ix64: the 64-bit index instantiation of ndiff_face (else 32-bit)
+  int mm, nn, surface_align, ix64;   // ix64: kernel variant, see faces_ix
   double delt1;
   // masks and inputs
   const int *ip, *iu, *iv, *ksmx;
@@ -26,15 +26,19 @@ struct EmuNdiff {
   double *utflld, *usflld, *vtflld, *vsflld, *utflx, *usflx, *vtflx, *vsflx, *nslpx, *nslpy, *trc_rm;
 };
 
-template <int NT, class IX>
+template <int NT, class IX, int STG>
 static void faces(const Geom& g, const NdArgs& U, const NdArgs& V) {
-  emu_launch(dim3(std::max(1, cdiv(U.nfaces, ND_BS))), dim3(ND_BS), [&] { ndiff_face<0, NT, IX>(g, U); });
-  emu_launch(dim3(std::max(1, cdiv(V.nfaces, ND_BS))), dim3(ND_BS), [&] { ndiff_face<1, NT, IX>(g, V); });
+  emu_launch(dim3(std::max(1, cdiv(U.nfaces, ND_BS))), dim3(ND_BS), [&] { ndiff_face<0, NT, IX, STG>(g, U); });
+  emu_launch(dim3(std::max(1, cdiv(V.nfaces, ND_BS))), dim3(ND_BS), [&] { ndiff_face<1, NT, IX, STG>(g, V); });
 }
+// variant: 0..3 = 32-bit index arithmetic with ndiff_stage = variant; 9 = the 64-bit instantiation (staged)
 template <int NT>
-static void faces_ix(int ix64, const Geom& g, const NdArgs& U, const NdArgs& V) {
-  if (ix64) faces<NT, long>(g, U, V);
-  else faces<NT, unsigned>(g, U, V);
+static void faces_ix(int variant, const Geom& g, const NdArgs& U, const NdArgs& V) {
+  if (variant == 9) faces<NT, long, 3>(g, U, V);
+  else if (variant == 3) faces<NT, unsigned, 3>(g, U, V);
+  else if (variant == 0) faces<NT, unsigned, 0>(g, U, V);
+  else if (variant == 2) faces<NT, unsigned, 2>(g, U, V);
+  else faces<NT, unsigned, 1>(g, U, V);
 }
 
 extern "C" int emu_ndiff(const EmuNdiff* e) {
@@ -44,21 +48,23 @@ extern "C" int emu_ndiff(const EmuNdiff* e) {
   const int kk = g.kdm, T = 2 + g.ntr;
   if (kk >= KMN || T > NTMAX) return 1;
   const size_t lev = (size_t)g.lev;
-  std::vector<double> rec(lev * 8 * kk, 0.), snp(lev * (kk + 1), 0.);
+  std::vector<double> src(lev * kk * nd_rs(T), 0.), dst(lev * 2 * (kk + 1), 0.);
   std::vector<double> ucm(lev * kk * T, 0.), ucp(lev * kk * T, 0.), vcm(lev * kk * T, 0.), vcp(lev * kk * T, 0.);
   std::vector<int> kdmx(lev, 0);
 
+  PrepIn I{};
+  I.ip = e->ip; I.iu = e->iu; I.iv = e->iv; I.ksmx = e->ksmx;
+  I.p_src = e->p_src; I.tsd = e->tsd; I.tpc = e->tpc; I.p_dst = e->p_dst; I.difiso = e->difiso;
+  I.tlev[0] = e->temp + (long)e->nn * g.lev;
+  I.tlev[1] = e->saln + (long)e->nn * g.lev;
+  for (int nt = 3; nt <= T; ++nt) I.tlev[nt - 1] = e->trc + (long)(e->nn + (nt - 3) * 2 * kk) * g.lev;
   emu_launch(dim3(cdiv(g.ii + 2, 128), g.jj + 2), dim3(128), [&] {
-    ndiff_prep(g, e->mm, T, e->ip, e->iu, e->iv, e->ksmx, e->p_src, e->tsd, e->p_dst, kdmx.data(), rec.data(), snp.data(),
-               e->utflld, e->usflld, e->vtflld, e->vsflld);
+    ndiff_prep(g, e->mm, T, I, kdmx.data(), src.data(), dst.data(), e->utflld, e->usflld, e->vtflld, e->vsflld);
   });
 
   NdArgs A{};
-  A.p_src = e->p_src; A.tsd = e->tsd; A.tpc = e->tpc; A.rec = rec.data(); A.p_dst = e->p_dst; A.snp = snp.data();
-  A.ksmx = e->ksmx; A.kdmx = kdmx.data(); A.dpml = e->dpml; A.difiso = e->difiso;
-  A.tlev[0] = e->temp + (long)e->nn * g.lev;
-  A.tlev[1] = e->saln + (long)e->nn * g.lev;
-  for (int nt = 3; nt <= T; ++nt) A.tlev[nt - 1] = e->trc + (long)(e->nn + (nt - 3) * 2 * kk) * g.lev;
+  A.src = src.data(); A.dst = dst.data();
+  A.ksmx = e->ksmx; A.kdmx = kdmx.data(); A.dpml = e->dpml;
   A.delt1 = e->delt1; A.mm = e->mm; A.T = T; A.surface_align = e->surface_align;
   NdArgs U = A, V = A;
   U.mask = e->iu; U.sca = e->scuy; U.scbi = e->scuxi; U.puv = e->pu;

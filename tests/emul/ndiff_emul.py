@@ -36,9 +36,10 @@ def build(force=False):
     return LIB
 
 
-def run(dims, levels, delt1, arrays, surface_align=True, ix64=False):
+def run(dims, levels, delt1, arrays, surface_align=True, variant=3):
     """dims = (ii, jj, kdm, nb, ldi, ldj, ntr); `arrays` maps the field names of EmuNdiff to C-contiguous numpy
-    arrays in the common (level, j, i) layout; the OUT arrays are updated in place."""
+    arrays in the common (level, j, i) layout; the OUT arrays are updated in place.  variant: 0..3 = option
+    ndiff_stage of the product (32-bit index instantiation), 9 = the 64-bit index instantiation."""
     lib = C.CDLL(str(build()))
     lib.emu_ndiff.argtypes = [C.POINTER(EmuNdiff)]
     lib.emu_ndiff.restype = C.c_int
@@ -46,7 +47,7 @@ def run(dims, levels, delt1, arrays, surface_align=True, ix64=False):
     ii, jj, kdm, nb, ldi, ldj, ntr = dims
     m, n, mm, nn, k1m, k1n = levels
     for k, v in dict(ii=ii, jj=jj, kdm=kdm, nb=nb, ldi=ldi, ldj=ldj, ntr=ntr, mm=mm, nn=nn,
-                     surface_align=int(surface_align), ix64=int(ix64)).items():
+                     surface_align=int(surface_align), ix64=int(variant)).items():
         setattr(e, k, v)
     e.delt1 = delt1
     keep = []

@@ -19,7 +19,7 @@ ND = {"ksmx": "nd_ksmx", "p_src": "nd_p_src", "tsd": "nd_t_srcdi", "tpc": "nd_tp
 GRID = ["dpml", "difiso", "temp", "saln", "trc", "scuy", "scuxi", "scvx", "scvyi", "scp2", "pu", "pv"]
 
 
-def run_pair(cfg, ntr, nstep, align, ix64=False):
+def run_pair(cfg, ntr, nstep, align, variant=3):
     c = Case(cfg, ntr=ntr, nstep=nstep)
     nd = {k: v.copy() for k, v in synth.ndiff_inputs(c.syn, c.state, c.levels, ntr=ntr).items()}
     o = c.new_oracle()
@@ -35,7 +35,7 @@ def run_pair(cfg, ntr, nstep, align, ix64=False):
     o.ndiff(*c.levels)
     itdm, jtdm, kdm, _ = c.dims
     ndiff_emul.run((itdm, jtdm, kdm, 4, c.syn.ldi, c.syn.ldj, ntr), c.levels, c.scalars["delt1"], emu,
-                   surface_align=align == "1", ix64=ix64)
+                   surface_align=align == "1", variant=variant)
     return c, o, emu
 
 
@@ -52,9 +52,11 @@ def test_kernel_source_against_oracle(cfg, align, ntr):
 
 
 @pytest.mark.parametrize("cfg,ntr", [("tiny2", 0), ("tiny4", 1), ("fuk95", 2)])
-def test_kernel_source_64bit_index_instantiation(cfg, ntr):
-    """ndiff_dev picks 32-bit index arithmetic when the tile allows it; the 64-bit instantiation is the same code"""
-    c, o, emu = run_pair(cfg, ntr, 1, "1", ix64=True)
+@pytest.mark.parametrize("variant", [0, 1, 2, 9])
+def test_kernel_source_other_instantiations(cfg, ntr, variant):
+    """ndiff_stage = 0 / 1 / 2 (records read in place instead of staged, other prefetches) and the 64-bit index instantiation that
+    ndiff_dev falls back to on very large tiles are the same code paths with other accessors"""
+    c, o, emu = run_pair(cfg, ntr, 1, "1", variant=variant)
     for nm in FACE:
         assert np.array_equal(interior(emu[nm]), interior(o.arrays[nm])), nm
     assert max_rel_err(interior(emu["trc_rm"]), interior(o.arrays["nd_trc_rm"])) <= 1e-13
