@@ -231,6 +231,7 @@ struct SideAcc {
 //   1  staged in shared memory when the column steps to the layer (one batch of loads)
 //   0  read from the column record in global memory whenever needed (no shared memory, the whole L1 is cache)
 //   2  as 0, with an L1 prefetch of the record's lines when the column steps to the layer
+//   4  as 0, with an L2 prefetch of the next layer's record
 //   3  as 1, with an L2 prefetch of the NEXT layer's record (default; tnx1v4, u + v faces: 12.9 / 12.2 / 12.5 / 10.3 ms
 //      for 0 / 1 / 2 / 3: the prefetch turns the DRAM round trip of every layer step into an L2 hit)
 constexpr int ND_BS = 128;
@@ -259,12 +260,21 @@ ndiff_face(Geom g, NdArgs A) {
   const double* const col_p = A.src + (long)x * kk * RS;
   const double* const dst_m = A.dst + (long)xm * (kk + 1) * 2;
   const double* const dst_p = A.dst + (long)x * (kk + 1) * 2;
-  // The records of the current source layers of the two columns, staged: sm[side*ND_RSB + field][thread].
-  __shared__ double sm[(STG & 1) ? 2 * ND_RSB : 1][ND_BS];
-  const double* lrec_m = col_m;   // records of the current layers (STG != 1)
+  // The records of the current source layers of the two columns, staged: sm[side*ND_RSS + row][thread].  The first
+  // search needs fields 0..19 (row = field); the second search needs neither drhodt nor drhods (fields 0, 1, 4, 5)
+  // but the diffusivity and the layer means (20, 21, 22), which take rows 0, 1, 4 then: 20 rows per side, 40 KB
+  // per block.  The remaining 8 KB of the 48 KB hold per-thread state that is used too rarely to deserve
+  // registers at a budget of 128 (the presence masks of the partner tables, the upper interface of the current
+  // destination layers).
+  constexpr int ND_RSS = 20;
+  __shared__ double sm[(STG & 1) ? 2 * ND_RSS : 1][ND_BS];
+  __shared__ unsigned long long smk[4][ND_BS];   // [side*2 + word]
+  __shared__ double smd[4][ND_BS];               // [side*2 + {p_dst, p_dstsnp}]
+  const double* lrec_m = col_m;   // records of the current layers (STG even)
   const double* lrec_p = col_p;
-#define SM(side, f) ((STG & 1) ? sm[(STG & 1) ? (side) * ND_RSB + (f) : 0][tx] : ((side) ? lrec_p : lrec_m)[f])
-  auto stage = [&](int side, int k) {
+#define ND_ROW(f) ((f) == F_DIF ? 0 : (f) == F_TLEV ? 1 : (f) == F_TLEV + 1 ? 4 : (f))
+#define SM(side, f) ((STG & 1) ? sm[(STG & 1) ? (side) * ND_RSS + ND_ROW(f) : 0][tx] : ((side) ? lrec_p : lrec_m)[f])
+  auto stage = [&](int side, int k, bool second) {
     const double* rec = (side ? col_p : col_m) + (k - 1) * RS;
     if (STG & 1) {
       const double2* r = reinterpret_cast<const double2*>(rec);
@@ -273,24 +283,30 @@ ndiff_face(Geom g, NdArgs A) {
       for (int q = 0; q < ND_RSB / 2; ++q) v[q] = r[q];
 #pragma unroll
       for (int q = 0; q < ND_RSB / 2; ++q) {
-        sm[(STG & 1) ? side * ND_RSB + 2 * q : 0][tx] = v[q].x;
-        sm[(STG & 1) ? side * ND_RSB + 2 * q + 1 : 0][tx] = v[q].y;
+        const int f0 = 2 * q, f1 = 2 * q + 1;
+        const bool skip0 = second ? (f0 == 0 || f0 == 4) : f0 >= ND_RSS;   // fields 0,1 / 4,5 and 23 in the second
+        const bool skip1 = second ? (f1 == 1 || f1 == 5 || f1 == 23) : f1 >= ND_RSS;   // search, 20..23 in the first
+        if (!skip0) sm[(STG & 1) ? side * ND_RSS + ND_ROW(f0) : 0][tx] = v[q].x;
+        if (!skip1) sm[(STG & 1) ? side * ND_RSS + ND_ROW(f1) : 0][tx] = v[q].y;
       }
       if (STG == 3 && k < kk) { nd_prefetch_l2(rec + RS); nd_prefetch_l2(rec + RS + 16); }
     } else {
       if (side) lrec_p = rec; else lrec_m = rec;
       if (STG == 2) { nd_prefetch_l1(rec); nd_prefetch_l1(rec + 16); }
+      if (STG == 4 && k < kk) { nd_prefetch_l2(rec + RS); nd_prefetch_l2(rec + RS + 16); }
     }
   };
   // unstaged reads (layers other than the current ones): p_srcdi(s,k) = p_src(k+s-1), p_dst(k), p_dstsnp(k)
   auto psd = [&](int side, int s, int k) { return (side ? col_p : col_m)[(k - 1) * RS + F_P + s - 1]; };
   auto pdst = [&](int side, int k) { return (side ? dst_p : dst_m)[(k - 1) * 2]; };
-  auto dstsnp = [&](int side, int k) { return (side ? dst_p : dst_m)[(k - 1) * 2 + 1]; };
   auto srec = [&](int side, int is) {   // interface record (is) of the staged layer
     const int f = F_REC + 4 * (is - 1);
     return Rec{SM(side, f), SM(side, f + 1), SM(side, f + 2), SM(side, f + 3)};
   };
   const int ksmx_m = A.ksmx[xm], ksmx_p = A.ksmx[x], kdmx_m = A.kdmx[xm], kdmx_p = A.kdmx[x];
+  if (STG >= 3) {   // the destination records of both columns (16 bytes per interface) are read front to back
+    for (int q = 0; q < 2 * (kk + 1); q += 16) { nd_prefetch_l2(dst_m + q); nd_prefetch_l2(dst_p + q); }
+  }
   const double cdiff = A.delt1 * A.sca[x] * A.scbi[x];          // :1064 / :1126
   const double cnslp = alpha0 * A.scbi[x] / grav;
 
@@ -299,6 +315,14 @@ ndiff_face(Geom g, NdArgs A) {
 #define PNM(s, k) pnm[2 * (k) + (s) - 1]
 #define PNP(s, k) pnp[2 * (k) + (s) - 1]
   unsigned long long stab_m = 0ull, stab_p = 0ull;   // bit k-1 <-> stab(k), k = 1..64
+  // Presence masks of the partner tables: bit q = 2*k + s - 1 (2..127 for kk <= 63) of hm / hp is set exactly when
+  // PNM(s,k) / PNP(s,k) != mval.  The second search scans the tables for the next interface that has a partner;
+  // with the masks the scans are bit operations and only the values actually used are read from local memory.
+  smk[0][tx] = 0ull; smk[1][tx] = 0ull; smk[2][tx] = 0ull; smk[3][tx] = 0ull;
+  auto hset = [&](int side, int q) { smk[side * 2 + (q >> 6)][tx] |= 1ull << (q & 63); };
+  auto hget = [&](int side, int q) { return ((smk[side * 2 + (q >> 6)][tx] >> (q & 63)) & 1ull) != 0ull; };
+#define PNM_SET(s, k, v) do { PNM(s, k) = (v); hset(0, 2 * (k) + (s) - 1); } while (0)
+#define PNP_SET(s, k, v) do { PNP(s, k) = (v); hset(1, 2 * (k) + (s) - 1); } while (0)
   double pml = 0., drho_curr = 0., p_ni_m_prev, p_ni_p_prev;
   int nns = 0, kssa_m = 0, kssa_p = 0, is_m, is_p, ks_m, ks_p;
 
@@ -350,7 +374,7 @@ ndiff_face(Geom g, NdArgs A) {
     p_ni_m_prev = psd(0, 1, 1); p_ni_p_prev = psd(1, 1, 1);
   }
   if (ks_m <= ksmx_m && ks_p <= ksmx_p) {
-    stage(0, ks_m); stage(1, ks_p);
+    stage(0, ks_m, false); stage(1, ks_p, false);
     rm = srec(0, is_m); rp = srec(1, is_p); drho_curr = drho_at();
   }
 
@@ -381,15 +405,15 @@ ndiff_face(Geom g, NdArgs A) {
           if (p_ni > (rootm ? p_ni_m_prev : p_ni_p_prev)) {
             // pressure of the fixed interface in its own column
             const double pe = rootm ? SM(1, F_P + is_p - 1) : SM(0, F_P + is_m - 1);
-            if (rootm) { p_ni_m_prev = p_ni; PNP(is_p, ks_p) = p_ni; }
-            else { p_ni_p_prev = p_ni; PNM(is_m, ks_m) = p_ni; }
+            if (rootm) { p_ni_m_prev = p_ni; PNP_SET(is_p, ks_p, p_ni); }
+            else { p_ni_p_prev = p_ni; PNM_SET(is_m, ks_m, p_ni); }
             const double pa = rootm ? pe : p_ni, pb = rootm ? p_ni : pe;   // (plus side) - (minus side)
             emit_slope(-cnslp * (pa - pb), .5 * (pa + pb));
           }
         } else if (drho_zero) {
           const double pm = SM(0, F_P + is_m - 1), pp = SM(1, F_P + is_p - 1);
-          PNP(is_p, ks_p) = pm;
-          PNM(is_m, ks_m) = pp;
+          PNP_SET(is_p, ks_p, pm);
+          PNM_SET(is_m, ks_m, pp);
           emit_slope(-cnslp * (pp - pm), .5 * (pp + pm));
         }
       }
@@ -404,7 +428,7 @@ ndiff_face(Geom g, NdArgs A) {
           ks = ks + 1;
           if (ks > (side ? ksmx_p : ksmx_m)) { if (side) ks_p = ks; else ks_m = ks; done1 = true; break; }
           is = 1;
-          stage(side, ks);
+          stage(side, ks, false);
         }
         const Rec r = srec(side, is);
         if (side) { rp = r; is_p = is; ks_p = ks; } else { rm = r; is_m = is; ks_m = ks; }
@@ -416,7 +440,11 @@ ndiff_face(Geom g, NdArgs A) {
           if (then_p) { then_p = false; side = 1; continue; }
           break;
         }
-        if (is == 1) { double* pn = side ? pnp : pnm; pn[2 * ks] = pn[2 * ks - 1]; }   // PN(1,ks) = PN(2,ks-1)
+        if (is == 1 && hget(side, 2 * ks - 1)) {   // PN(1,ks) = PN(2,ks-1); both are mval when the bit is clear
+          double* pn = side ? pnp : pnm;
+          pn[2 * ks] = pn[2 * ks - 1];
+          hset(side, 2 * ks);
+        }
       }
     }
   }
@@ -424,32 +452,32 @@ ndiff_face(Geom g, NdArgs A) {
   if (A.surface_align) {  // :408-479
     int issa_m = 1;
     while (kssa_m <= ksmx_m) {
-      if (PNM(issa_m, kssa_m) != mval) break;
+      if (hget(0, 2 * kssa_m + issa_m - 1)) break;
       if (issa_m == 1) issa_m = 2;
       else { kssa_m = kssa_m + 1; issa_m = 1; }
     }
     int issa_p = 1;
     while (kssa_p <= ksmx_p) {
-      if (PNP(issa_p, kssa_p) != mval) break;
+      if (hget(1, 2 * kssa_p + issa_p - 1)) break;
       if (issa_p == 1) issa_p = 2;
       else { kssa_p = kssa_p + 1; issa_p = 1; }
     }
     if (kssa_m > ksmx_m || kssa_p > ksmx_p) {
       const double pbm = psd(0, 2, ksmx_m), pbp = psd(1, 2, ksmx_p);
-      PNM(1, 1) = psd(0, 1, 1);
+      PNM_SET(1, 1, psd(0, 1, 1));
       for (ks_m = 1; ks_m <= ksmx_m - 1; ++ks_m) {
         if (psd(0, 1, ks_m) > pbp) break;
         const double p_ni = fmin(psd(0, 2, ks_m), pbp);
-        PNM(1, ks_m + 1) = p_ni;
-        PNM(2, ks_m) = p_ni;
+        PNM_SET(1, ks_m + 1, p_ni);
+        PNM_SET(2, ks_m, p_ni);
         stab_m |= 1ull << (ks_m - 1);
       }
-      PNP(1, 1) = psd(1, 1, 1);
+      PNP_SET(1, 1, psd(1, 1, 1));
       for (ks_p = 1; ks_p <= ksmx_p - 1; ++ks_p) {
         if (psd(1, 1, ks_p) > pbm) break;
         const double p_ni = fmin(psd(1, 2, ks_p), pbm);
-        PNP(1, ks_p + 1) = p_ni;
-        PNP(2, ks_p) = p_ni;
+        PNP_SET(1, ks_p + 1, p_ni);
+        PNP_SET(2, ks_p, p_ni);
         stab_p |= 1ull << (ks_p - 1);
       }
     } else {
@@ -461,20 +489,20 @@ ndiff_face(Geom g, NdArgs A) {
         p1_m = psd(0, 1, 1); p2_m = PNP(issa_p, kssa_p);
         p1_p = psd(1, 1, 1); p2_p = psd(1, issa_p, kssa_p);
       }
-      PNM(1, 1) = p1_p;
+      PNM_SET(1, 1, p1_p);
       for (ks_m = 1; ks_m <= kssa_m - 1; ++ks_m) {
         const double pl = psd(0, 2, ks_m);
         const double p_ni = ((pl - p1_m) * p2_p + (p2_m - pl) * p1_p) / (p2_m - p1_m);
-        PNM(1, ks_m + 1) = p_ni;
-        PNM(2, ks_m) = p_ni;
+        PNM_SET(1, ks_m + 1, p_ni);
+        PNM_SET(2, ks_m, p_ni);
         stab_m |= 1ull << (ks_m - 1);
       }
-      PNP(1, 1) = p1_m;
+      PNP_SET(1, 1, p1_m);
       for (ks_p = 1; ks_p <= kssa_p - 1; ++ks_p) {
         const double pl = psd(1, 2, ks_p);
         const double p_ni = ((pl - p1_p) * p2_m + (p2_p - pl) * p1_m) / (p2_p - p1_p);
-        PNP(1, ks_p + 1) = p_ni;
-        PNP(2, ks_p) = p_ni;
+        PNP_SET(1, ks_p + 1, p_ni);
+        PNP_SET(2, ks_p, p_ni);
         stab_p |= 1ull << (ks_p - 1);
       }
     }
@@ -505,7 +533,7 @@ ndiff_face(Geom g, NdArgs A) {
     };
     auto cf = [&](int side, int nt) {
       return nt > 2    ? CoefRef{nullptr, xrec(side, nt) + X_TPC, tx}
-             : (STG & 1) ? CoefRef{&sm[(STG & 1) ? side * ND_RSB + F_TPC + (nt - 1) * 5 : 0], nullptr, tx}
+             : (STG & 1) ? CoefRef{&sm[(STG & 1) ? side * ND_RSS + F_TPC + (nt - 1) * 5 : 0], nullptr, tx}
                         : CoefRef{nullptr, lrec(side) + F_TPC + (nt - 1) * 5, tx};
     };
     auto tsrcdi = [&](int side, int is, int nt) {   // t_srcdi(is, ks, nt)
@@ -538,7 +566,21 @@ ndiff_face(Geom g, NdArgs A) {
     // the snapped lower interface of the current destination layer (snp).  An iteration of the search moves one
     // of the four pointers; re-reading all of these at its top cost ten loads where one to five are needed.
     double psm1 = 0., psm2 = 0., psp1 = 0., psp2 = 0., psm_n = 0., psp_n = 0., pnm_n = 0., pnp_n = 0.;
-    double pnm_c = 0., pnp_c = 0., snp_m = 0., snp_p = 0.;
+    double pnm_c = 0., pnp_c = 0.;
+    // Destination layer kd of a column: {p_dst, p_dstsnp} of its upper (pdu, snu) and lower (pdl, snp) interface.
+    // The layers are visited in order, so stepping to kd + 1 shifts lower to upper and loads ONE 16-byte pair;
+    // for kd = 0 the "lower" interface is interface 1.  The upper pair lives in shared memory (smd).
+    double snp_m, snp_p, pdl_m, pdl_p;
+    { const double2 d0 = *reinterpret_cast<const double2*>(dst_m); pdl_m = d0.x; snp_m = d0.y; }
+    { const double2 d0 = *reinterpret_cast<const double2*>(dst_p); pdl_p = d0.x; snp_p = d0.y; }
+    auto step_dst_m = [&]() {   // kd_m has just been incremented (kd_m <= kdmx_m)
+      const double2 d = reinterpret_cast<const double2*>(dst_m)[kd_m];
+      smd[0][tx] = pdl_m; smd[1][tx] = snp_m; pdl_m = d.x; snp_m = d.y;
+    };
+    auto step_dst_p = [&]() {
+      const double2 d = reinterpret_cast<const double2*>(dst_p)[kd_p];
+      smd[2][tx] = pdl_p; smd[3][tx] = snp_p; pdl_p = d.x; snp_p = d.y;
+    };
     int kuv = 1;
     auto puv = [&](int k) { return A.puv[x + (IX)(k - 1) * lev]; };
     // The face fluxes of a neutral sublayer are binned on the face's layers (:870-905).  A layer collects
@@ -573,21 +615,29 @@ ndiff_face(Geom g, NdArgs A) {
               ks = ks + 1;
               if (ks > kmx) { out = true; break; }
               is = 1;
-              if (((stab >> (ks - 1)) & 1ull) && pn[2 * ks + is - 1] != mval) break;
+              if (((stab >> (ks - 1)) & 1ull) && hget(side, 2 * ks + is - 1)) break;
             }
           }
           if (out) break;
-          int isn = is, ksn = ks;
-          while (pn[2 * ksn + isn - 1] == mval) {
-            if (isn == 1) isn = 2;
-            else {
-              if (ksn == kmx) break;
-              ksn = ksn + 1;
-              isn = 1;
-            }
-          }
+          // the next interface at or below (is,ks) that has a partner, (2,kmx) at the latest: the reference steps
+          // through (is,ks) = q -> q + 1 while PN == mval, i.e. it looks for the first set bit at or above q
+          int qn = 2 * ks + is - 1;
           {
-            if (ks != (side ? kc_p : kc_m)) { stage(side, ks); if (side) kc_p = ks; else kc_m = ks; }
+            const unsigned long long w0 = smk[side * 2][tx], w1 = smk[side * 2 + 1][tx];
+            int qf = 128;
+            if (qn < 64) {
+              const unsigned long long lo = w0 >> qn;
+              if (lo != 0ull) qf = qn + __ffsll((long long)lo) - 1;
+              else if (w1 != 0ull) qf = 64 + __ffsll((long long)w1) - 1;
+            } else {
+              const unsigned long long hi = w1 >> (qn - 64);
+              if (hi != 0ull) qf = qn + __ffsll((long long)hi) - 1;
+            }
+            qn = min(qf, 2 * kmx + 1);
+          }
+          const int isn = (qn & 1) + 1, ksn = qn >> 1;
+          {
+            if (ks != (side ? kc_p : kc_m)) { stage(side, ks, true); if (side) kc_p = ks; else kc_m = ks; }
             const double ps1 = SM(side, F_P), ps2 = SM(side, F_P + 1);
             const double ps_n = ksn == ks ? (isn == 1 ? ps1 : ps2) : psd(side, isn, ksn);
             const double pn_n = pn[2 * ksn + isn - 1], pn_c = pn[2 * ks + is - 1];
@@ -612,12 +662,12 @@ ndiff_face(Geom g, NdArgs A) {
       if (advance_dst_m) {
         kd_m = kd_m + 1;
         if (kd_m > kdmx_m) break;
-        snp_m = dstsnp(0, kd_m + 1);
+        step_dst_m();
       }
       if (advance_dst_p) {
         kd_p = kd_p + 1;
         if (kd_p > kdmx_p) break;
-        snp_p = dstsnp(1, kd_p + 1);
+        step_dst_p();
       }
       {
         bool out = false;
@@ -625,14 +675,14 @@ ndiff_face(Geom g, NdArgs A) {
         while (snp_m <= lim_m) {
           kd_m = kd_m + 1;
           if (kd_m > kdmx_m) { out = true; break; }
-          snp_m = dstsnp(0, kd_m + 1);
+          step_dst_m();
         }
         if (out) break;
         const double lim_p = fmax(psp1, p_prev_p);
         while (snp_p <= lim_p) {
           kd_p = kd_p + 1;
           if (kd_p > kdmx_p) { out = true; break; }
-          snp_p = dstsnp(1, kd_p + 1);
+          step_dst_p();
         }
         if (out) break;
       }
@@ -757,11 +807,11 @@ ndiff_face(Geom g, NdArgs A) {
             t_cur_m[nt - 1] = ev_m == 2 ? tsrcdi(0, is_m, nt) : pe(cf(0, nt), x_cur_m);
             t_cur_p[nt - 1] = ev_p == 2 ? tsrcdi(1, is_p, nt) : pe(cf(1, nt), x_cur_p);
           }
-        const double dp_ni_m = fmin(p_cur_m - p_prev_m, pdst(0, kd_m + 1) - pdst(0, kd_m));
-        const double dp_ni_p = fmin(p_cur_p - p_prev_p, pdst(1, kd_p + 1) - pdst(1, kd_p));
+        const double dp_ni_m = fmin(p_cur_m - p_prev_m, pdl_m - smd[0][tx]);
+        const double dp_ni_p = fmin(p_cur_p - p_prev_p, pdl_p - smd[2][tx]);
         const double dp_ni = 2. * dp_ni_m * dp_ni_p / fmax(dp_ni_m + dp_ni_p, 2. * dp_eps);
-        if (ks_m == ks_m_prev && ks_p == ks_p_prev && p_prev_m >= dstsnp(0, kd_m) && p_cur_m <= snp_m &&
-            p_prev_p >= dstsnp(1, kd_p) && p_cur_p <= snp_p && dp_ni > 2. * dp_eps) {
+        if (ks_m == ks_m_prev && ks_p == ks_p_prev && p_prev_m >= smd[1][tx] && p_cur_m <= snp_m &&
+            p_prev_p >= smd[3][tx] && p_cur_p <= snp_p && dp_ni > 2. * dp_eps) {
           accm.advance(kd_m);
           accp.advance(kd_p);
           const double q = .5 * cdiff * (SM(0, F_DIF) + SM(1, F_DIF)) * dp_ni;
@@ -881,6 +931,8 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   I.tlev[0] = c.dev("temp") + (long)nn * g.lev;
   I.tlev[1] = c.dev("saln") + (long)nn * g.lev;
   for (int nt = 3; nt <= T; ++nt) I.tlev[nt - 1] = c.dev("trc") + (long)(nn + (nt - 3) * 2 * kk) * g.lev;
+  // (A writer with one thread per 16-byte piece of a record, i.e. fully coalesced stores, measured equal: 1.03 ms at
+  // tnx1v4 either way - the pass is bound by the scattered 192-byte chunks in DRAM, not by the store pattern.)
   LAUNCH(ndiff_prep, dim3(cdiv(g.ii + 2, 128), g.jj + 2), 128, 0, g, mm, T, I, kdmx, src, dst,
          c.dev("utflld"), c.dev("usflld"), c.dev("vtflld"), c.dev("vsflld"));
 
@@ -917,10 +969,12 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     // the cell column (i,j) that is the plus side of face (i,j) and the minus side of face (i,j+1) is fetched by one
     // block instead of by two blocks a whole grid row apart (ncu, row-major order: 75 GB of DRAM traffic per launch
     // for the v faces against 49 GB for the u faces, whose two columns sit in neighbouring lanes)
+    // (walking the tiles in patches of 8 x 4, which puts the two faces of a shared column into one warp, measured equal)
+    const int pw = 32;
     for (int j0 = 1; j0 <= g.jj + 1; j0 += 4)
-      for (int i0 = 1; i0 <= g.ii; i0 += 32)
+      for (int i0 = 1; i0 <= g.ii; i0 += pw)
         for (int j = j0; j < std::min(j0 + 4, g.jj + 2); ++j)
-          for (int i = i0; i < std::min(i0 + 32, g.ii + 1); ++i) {
+          for (int i = i0; i < std::min(i0 + pw, g.ii + 1); ++i) {
             const long x = ix2(g, i, j);
             if (hv[x] == 1) lv.push_back((int)x);
           }
@@ -937,7 +991,7 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   const bool ix32 = ((long)kk * std::max(T, 2) + 2) * g.lev < (1l << 32);
   const dim3 gu(std::max(1, cdiv(U.nfaces, ND_BS))), gv(std::max(1, cdiv(V.nfaces, ND_BS)));
   const int stg = std::stoi(c.option("ndiff_stage", "3"));
-  if (stg < 0 || stg > 3) throw std::runtime_error("ndiff: ndiff_stage must be 0, 1, 2 or 3");
+  if (stg < 0 || stg > 4) throw std::runtime_error("ndiff: ndiff_stage must be 0 .. 4");
 #define ND_LAUNCH(NT_, IX_, STG_)                                                                  \
   do {                                                                                             \
     LAUNCH_NAMED("ndiff_face<u>", (ndiff_face<0, NT_, IX_, STG_>), gu, ND_BS, 0, g, U);            \
@@ -948,8 +1002,9 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
     if (!ix32) ND_LAUNCH(NT_, long, 3);                                                            \
     else if (stg == 0) ND_LAUNCH(NT_, unsigned, 0);                                                \
     else if (stg == 2) ND_LAUNCH(NT_, unsigned, 2);                                                \
-    else if (stg == 3) ND_LAUNCH(NT_, unsigned, 3);                                                \
-    else ND_LAUNCH(NT_, unsigned, 1);                                                              \
+    else if (stg == 4) ND_LAUNCH(NT_, unsigned, 4);                                                \
+    else if (stg == 1) ND_LAUNCH(NT_, unsigned, 1);                                                \
+    else ND_LAUNCH(NT_, unsigned, 3);                                                              \
   } while (0)
   if (T == 2) { ND_FACE(2); }
   else if (T == 3) { ND_FACE(3); }

@@ -23,6 +23,7 @@ CONFIGS = {
     "tiny2": (24, 20, 5, 2, 1800.0, 36.0),
     "tiny3": (20, 18, 4, 3, 1800.0, 36.0),
     "tiny4": (20, 22, 4, 4, 1800.0, 36.0),
+    "tiny2k53": (24, 20, 53, 2, 1800.0, 36.0),      # tiny2 with the production layer count (kdm-dependent code paths)
     "mid1": (48, 44, 6, 1, 1800.0, 36.0),          # multi-band parity cases (periodic-i / tripolar)
     "mid2": (48, 46, 6, 2, 1800.0, 36.0),
     "fuk95": (156, 32, 12, 4, 180.0, 6.0),        # tests/fuk95/limits:131-143 (dims only, noisy state)

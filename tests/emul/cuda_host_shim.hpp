@@ -11,6 +11,8 @@
 using std::min;   // CUDA's global integer min/max
 using std::max;
 
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+
 #ifndef __launch_bounds__
 #define __launch_bounds__(...)
 #endif

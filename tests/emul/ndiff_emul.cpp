@@ -31,10 +31,11 @@ static void faces(const Geom& g, const NdArgs& U, const NdArgs& V) {
   emu_launch(dim3(std::max(1, cdiv(U.nfaces, ND_BS))), dim3(ND_BS), [&] { ndiff_face<0, NT, IX, STG>(g, U); });
   emu_launch(dim3(std::max(1, cdiv(V.nfaces, ND_BS))), dim3(ND_BS), [&] { ndiff_face<1, NT, IX, STG>(g, V); });
 }
-// variant: 0..3 = 32-bit index arithmetic with ndiff_stage = variant; 9 = the 64-bit instantiation (staged)
+// variant: 0..4 = 32-bit index arithmetic with ndiff_stage = variant; 9 = the 64-bit instantiation (staged)
 template <int NT>
 static void faces_ix(int variant, const Geom& g, const NdArgs& U, const NdArgs& V) {
   if (variant == 9) faces<NT, long, 3>(g, U, V);
+  else if (variant == 4) faces<NT, unsigned, 4>(g, U, V);
   else if (variant == 3) faces<NT, unsigned, 3>(g, U, V);
   else if (variant == 0) faces<NT, unsigned, 0>(g, U, V);
   else if (variant == 2) faces<NT, unsigned, 2>(g, U, V);

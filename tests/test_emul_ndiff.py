@@ -52,11 +52,21 @@ def test_kernel_source_against_oracle(cfg, align, ntr):
 
 
 @pytest.mark.parametrize("cfg,ntr", [("tiny2", 0), ("tiny4", 1), ("fuk95", 2)])
-@pytest.mark.parametrize("variant", [0, 1, 2, 9])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 9])
 def test_kernel_source_other_instantiations(cfg, ntr, variant):
     """ndiff_stage = 0 / 1 / 2 (records read in place instead of staged, other prefetches) and the 64-bit index instantiation that
     ndiff_dev falls back to on very large tiles are the same code paths with other accessors"""
     c, o, emu = run_pair(cfg, ntr, 1, "1", variant=variant)
+    for nm in FACE:
+        assert np.array_equal(interior(emu[nm]), interior(o.arrays[nm])), nm
+    assert max_rel_err(interior(emu["trc_rm"]), interior(o.arrays["nd_trc_rm"])) <= 1e-13
+
+
+@pytest.mark.parametrize("align", ["1", "0"])
+@pytest.mark.parametrize("ntr", [0, 1])
+def test_kernel_source_53_layers(align, ntr):
+    """kdm = 53 as in the production grids: the partner-table masks use their second word, columns are deep"""
+    c, o, emu = run_pair("tiny2k53", ntr, 1, align)
     for nm in FACE:
         assert np.array_equal(interior(emu[nm]), interior(o.arrays[nm])), nm
     assert max_rel_err(interior(emu["trc_rm"]), interior(o.arrays["nd_trc_rm"])) <= 1e-13
