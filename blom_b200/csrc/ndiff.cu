@@ -72,9 +72,18 @@ __device__ __forceinline__ double eos_drhods(double p, double th, double s) {
 //   20      difiso(k)             21, 22  temp(k), saln(k) at the new time level          23  unused
 //   24 + 8*(nt-3) ..  passive tracer nt >= 3: trc(k), tpc_src(1:5,k,nt), t_srcdi(1:2,k,nt)
 // The first ND_RSB = 24 doubles (192 bytes, six sectors) are what a thread stages in shared memory.
+// Cells are grouped in blocks of CB consecutive cells (linear (i,j) offsets); inside a block the records are ordered
+// (layer, cell), i.e. the record of layer k of cell x starts at src[(((x/CB)*kk + k-1)*CB + x%CB) * RS]: the
+// layer-k records of 32 neighbouring cells are one contiguous 6 KB piece, which is what a warp of ndiff_prep writes
+// and what the lanes of a warp of ndiff_face read while they are at the same depth (DRAM pages instead of 192-byte
+// pieces a whole column apart).  CB = ND_CB = 32.
 constexpr int ND_RSB = 24, F_REC = 0, F_P = 8, F_TPC = 10, F_DIF = 20, F_TLEV = 21;
 constexpr int X_TLEV = 0, X_TPC = 1, X_TSD = 6;   // inside a passive tracer's 8 doubles
 __host__ __device__ constexpr int nd_rs(int T) { return ND_RSB + 8 * (T - 2); }
+constexpr int ND_CB = 32;
+__host__ __device__ __forceinline__ long nd_col(long x, int kk, int RS) {   // record of layer 1 of cell x
+  return ((x / ND_CB) * kk * ND_CB + x % ND_CB) * RS;
+}
 // Destination record of interface k (1..kk+1) of cell x: dst[(x*(kk+1) + k-1)*2] = {p_dst(k), p_dstsnp(k)}.
 
 struct NdArgs {
@@ -147,10 +156,11 @@ ndiff_prep(Geom g, int mm, int T, PrepIn I, int* __restrict__ kdmx, double* __re
     if (I.p_dst[x + (long)(k - 1) * lev] == pbot) kd = k - 1;
   kdmx[x] = kd;
   const int ks = I.ksmx[x], RS = nd_rs(T);
-  double* col = src + (long)x * kk * RS;
+  double* col = src + nd_col(x, kk, RS);
+  const long LS = (long)ND_CB * RS;   // from one layer's record to the next
   double p_up = I.p_src[x];
   for (int k = 1; k <= ks; ++k) {
-    double2* r = reinterpret_cast<double2*>(col + (long)(k - 1) * RS);
+    double2* r = reinterpret_cast<double2*>(col + (k - 1) * LS);
     const double p_lo = I.p_src[x + (long)k * lev];
     const long ot = x + (long)(((IT - 1) * kk + k - 1) * 2) * lev, os = x + (long)(((IS - 1) * kk + k - 1) * 2) * lev;
     const double t1 = I.tsd[ot], t2 = I.tsd[ot + lev], s1 = I.tsd[os], s2 = I.tsd[os + lev];
@@ -256,8 +266,9 @@ ndiff_face(Geom g, NdArgs A) {
   const int kk = g.kdm, T = NT > 0 ? NT : A.T, mm = A.mm;
   const int RS = NT > 0 ? nd_rs(NT) : nd_rs(T);
   // column records of the two cells (side 0 = M, 1 = P)
-  const double* const col_m = A.src + (long)xm * kk * RS;
-  const double* const col_p = A.src + (long)x * kk * RS;
+  const double* const col_m = A.src + nd_col((long)xm, kk, RS);
+  const double* const col_p = A.src + nd_col((long)x, kk, RS);
+  const int LS = ND_CB * RS;   // from one layer's record to the next
   const double* const dst_m = A.dst + (long)xm * (kk + 1) * 2;
   const double* const dst_p = A.dst + (long)x * (kk + 1) * 2;
   // The records of the current source layers of the two columns, staged: sm[side*ND_RSS + row][thread].  The first
@@ -275,7 +286,7 @@ ndiff_face(Geom g, NdArgs A) {
 #define ND_ROW(f) ((f) == F_DIF ? 0 : (f) == F_TLEV ? 1 : (f) == F_TLEV + 1 ? 4 : (f))
 #define SM(side, f) ((STG & 1) ? sm[(STG & 1) ? (side) * ND_RSS + ND_ROW(f) : 0][tx] : ((side) ? lrec_p : lrec_m)[f])
   auto stage = [&](int side, int k, bool second) {
-    const double* rec = (side ? col_p : col_m) + (k - 1) * RS;
+    const double* rec = (side ? col_p : col_m) + (k - 1) * LS;
     if (STG & 1) {
       const double2* r = reinterpret_cast<const double2*>(rec);
       double2 v[ND_RSB / 2];
@@ -289,15 +300,15 @@ ndiff_face(Geom g, NdArgs A) {
         if (!skip0) sm[(STG & 1) ? side * ND_RSS + ND_ROW(f0) : 0][tx] = v[q].x;
         if (!skip1) sm[(STG & 1) ? side * ND_RSS + ND_ROW(f1) : 0][tx] = v[q].y;
       }
-      if (STG == 3 && k < kk) { nd_prefetch_l2(rec + RS); nd_prefetch_l2(rec + RS + 16); }
+      if (STG == 3 && k < kk) { nd_prefetch_l2(rec + LS); nd_prefetch_l2(rec + LS + 16); }
     } else {
       if (side) lrec_p = rec; else lrec_m = rec;
       if (STG == 2) { nd_prefetch_l1(rec); nd_prefetch_l1(rec + 16); }
-      if (STG == 4 && k < kk) { nd_prefetch_l2(rec + RS); nd_prefetch_l2(rec + RS + 16); }
+      if (STG == 4 && k < kk) { nd_prefetch_l2(rec + LS); nd_prefetch_l2(rec + LS + 16); }
     }
   };
   // unstaged reads (layers other than the current ones): p_srcdi(s,k) = p_src(k+s-1), p_dst(k), p_dstsnp(k)
-  auto psd = [&](int side, int s, int k) { return (side ? col_p : col_m)[(k - 1) * RS + F_P + s - 1]; };
+  auto psd = [&](int side, int s, int k) { return (side ? col_p : col_m)[(k - 1) * LS + F_P + s - 1]; };
   auto pdst = [&](int side, int k) { return (side ? dst_p : dst_m)[(k - 1) * 2]; };
   auto srec = [&](int side, int is) {   // interface record (is) of the staged layer
     const int f = F_REC + 4 * (is - 1);
@@ -529,7 +540,7 @@ ndiff_face(Geom g, NdArgs A) {
     };
     auto lrec = [&](int side) { return side ? lrec_p : lrec_m; };
     auto xrec = [&](int side, int nt) {   // passive tracer nt >= 3 in the current layer's record
-      return (side ? col_p + (ks_p - 1) * RS : col_m + (ks_m - 1) * RS) + ND_RSB + 8 * (nt - 3);
+      return (side ? col_p + (ks_p - 1) * LS : col_m + (ks_m - 1) * LS) + ND_RSB + 8 * (nt - 3);
     };
     auto cf = [&](int side, int nt) {
       return nt > 2    ? CoefRef{nullptr, xrec(side, nt) + X_TPC, tx}
@@ -916,7 +927,8 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   const bool surface_align = c.option("ndiff_surface_align", "1") == "1";   // namelist default .true.
   if (surface_align) halo_update(c.dev("dpml"), 1, 1, 1, halo_ps);
   const int RS = nd_rs(T);
-  double* src = c.owned("_nd_src", kk * RS);          // column records: kk records of RS doubles per cell
+  // column records: kk records of RS doubles per cell, whole cell blocks
+  double* src = c.owned("_nd_src", cdiv((long)cdiv(g.lev, ND_CB) * ND_CB * kk * RS, g.lev));
   double* dst = c.owned("_nd_dst", 2 * (kk + 1));     // {p_dst, p_dstsnp} per destination interface and cell
   int* kdmx = c.owned_int("_nd_kdmx", 1);
   double* ucm = c.owned("_nd_ucm", kk * T);

@@ -49,7 +49,7 @@ extern "C" int emu_ndiff(const EmuNdiff* e) {
   const int kk = g.kdm, T = 2 + g.ntr;
   if (kk >= KMN || T > NTMAX) return 1;
   const size_t lev = (size_t)g.lev;
-  std::vector<double> src(lev * kk * nd_rs(T), 0.), dst(lev * 2 * (kk + 1), 0.);
+  std::vector<double> src((size_t)cdiv((long)lev, ND_CB) * ND_CB * kk * nd_rs(T), 0.), dst(lev * 2 * (kk + 1), 0.);
   std::vector<double> ucm(lev * kk * T, 0.), ucp(lev * kk * T, 0.), vcm(lev * kk * T, 0.), vcp(lev * kk * T, 0.);
   std::vector<int> kdmx(lev, 0);
 
