@@ -77,10 +77,11 @@ KERNELS = {
     "mt_fused": (21 + 6, "3d"),
     # neutral diffusion: per face column and layer R p_src,p_dst,snapped p_dst (3), interface records 2x4, t_srcdi 2T,
     # tpc_src 5T, difiso, layer means T, face pressure (1)  W 4 face fluxes (read-modify-write), nslp, 2T face
-    # convergences; T = 2.  The kernel is issue- and latency-bound (data-dependent search per column), its HBM
-    # fraction is reported for completeness only
+    # convergences; T = 2.  The kernel is latency-bound (data-dependent search per column), its HBM
+    # fraction is reported for completeness only.  ndiff_prep: R the ALE products of a cell (p_src, p_dst, t_srcdi 2T,
+    # tpc_src 5T), difiso, layer means T  W the column records (24 words per layer), {p_dst, snapped p_dst}, 4 face sums
     "ndiff_face<u>": (3 + 8 + 4 + 10 + 1 + 2 + 1 + 8 + 1 + 4, "3d"), "ndiff_face<v>": (3 + 8 + 4 + 10 + 1 + 2 + 1 + 8 + 1 + 4, "3d"),
-    "ndiff_prep": (2 + 4 + 1 + 8 + 1 + 4, "3d"), "ndiff_update": (2 + 8 + 2, "3d"),
+    "ndiff_prep": (2 + 4 + 10 + 1 + 2 + 24 + 2 + 4, "3d"), "ndiff_update": (2 + 8 + 2, "3d"),
     "bt_subcycle": (43.2, "bt"), "bt_ueq": (23, "2d"), "bt_veq": (23, "2d"), "bt_continuity": (7, "2d"),
 }
 KERNEL_SCRATCH_WORDS = {"mt_aux": 7, "mt_vort": 4 + 2, "mt_visc": 2 + 4, "mt_flux1": 8 + 2, "mt_update": 12,
@@ -489,10 +490,13 @@ def main():
             r["scratch_words_not_counted"] = KERNEL_SCRATCH_WORDS[name]
         if name.startswith("ndiff_face"):
             r["note"] = ("not a bandwidth kernel: one thread per face column runs the reference's two sequential, "
-                         "data-dependent searches (phy/mod_ndiff.F90:160-953, ~250 k thread instructions per face); "
-                         "issue- and latency-bound (ncu: IPC 1.2 of 4, 15 of 32 lanes active, 9 % of the DRAM peak; "
-                         "profiles/r02_ncu_full_ndiff_face.txt) - the HBM fraction is reported because the contract "
-                         "asks for one")
+                         "data-dependent searches (phy/mod_ndiff.F90:160-953); bound by the latency of dependent "
+                         "loads and instructions at 16 warps per SM (ncu at tnx1v4, profiles/r02_ncu_full_ndiff_face.txt: "
+                         "IPC 1.2 of 4, 16 of 32 lanes active, 9 % of the DRAM peak, 47 % of the stall samples on the "
+                         "long scoreboard).  Round 2: per-column source records staged in shared memory with an L2 "
+                         "prefetch of the next layer (152.8 -> 115.4 ms for both directions at tnx0.25v4).  The HBM "
+                         "fraction is reported because the contract asks for one; `traffic` is measured at tnx1v4 only "
+                         "(3.9 GB per launch there for 2.5 GB of algorithmic bytes)")
         if unit == "bt":
             ws_mb = 8.0 * w * cells2d_local / 1e6
             r["note"] = (f"streamed model ({w} words per 2-D point and substep, see BT_WORDS_PER_SUBSTEP); 2-D working set {ws_mb:.0f} MB "
