@@ -86,6 +86,19 @@ __host__ __device__ __forceinline__ long nd_col(long x, int kk, int RS) {   // r
 }
 // Destination record of interface k (1..kk+1) of cell x: dst[(x*(kk+1) + k-1)*2] = {p_dst(k), p_dstsnp(k)}.
 
+// 32-byte (one sector) global store of sm_100 (STG.E.ENL2.256).  ndiff_prep writes a record sector by sector: a lane's
+// 16-byte stores leave half-written sectors behind (every lane writes to its own record), and those cost the pass a factor
+// of two (tnx1v4: 1.17 ms with sixteen-byte stores, 0.55 ms with these; a writer with one thread per 16-byte piece, whose
+// warps do write whole sectors, was as slow because its loads were scattered instead).
+struct Quad { double a, b, c, d; };
+#ifdef BLOM_HOST_EMUL
+__device__ __forceinline__ void st_quad(double* p, Quad q) { p[0] = q.a; p[1] = q.b; p[2] = q.c; p[3] = q.d; }
+#else
+__device__ __forceinline__ void st_quad(double* p, Quad q) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(q.a), "d"(q.b), "d"(q.c), "d"(q.d) : "memory");
+}
+#endif
+
 struct NdArgs {
   const double *src, *dst;     // column records written by ndiff_prep
   const int *ksmx, *kdmx, *mask;
@@ -160,33 +173,25 @@ ndiff_prep(Geom g, int mm, int T, PrepIn I, int* __restrict__ kdmx, double* __re
   const long LS = (long)ND_CB * RS;   // from one layer's record to the next
   double p_up = I.p_src[x];
   for (int k = 1; k <= ks; ++k) {
-    double2* r = reinterpret_cast<double2*>(col + (k - 1) * LS);
+    double* r = col + (k - 1) * LS;
     const double p_lo = I.p_src[x + (long)k * lev];
     const long ot = x + (long)(((IT - 1) * kk + k - 1) * 2) * lev, os = x + (long)(((IS - 1) * kk + k - 1) * 2) * lev;
     const double t1 = I.tsd[ot], t2 = I.tsd[ot + lev], s1 = I.tsd[os], s2 = I.tsd[os + lev];
-    r[0] = make_double2(eos_drhodt(p_up, t1, s1), eos_drhods(p_up, t1, s1));
-    r[1] = make_double2(t1, s1);
-    r[2] = make_double2(eos_drhodt(p_lo, t2, s2), eos_drhods(p_lo, t2, s2));
-    r[3] = make_double2(t2, s2);
+    st_quad(r, Quad{eos_drhodt(p_up, t1, s1), eos_drhods(p_up, t1, s1), t1, s1});
+    st_quad(r + 4, Quad{eos_drhodt(p_lo, t2, s2), eos_drhods(p_lo, t2, s2), t2, s2});
     const double* ct = I.tpc + x + (long)(((IT - 1) * kk + k - 1) * 5) * lev;
     const double* cs = I.tpc + x + (long)(((IS - 1) * kk + k - 1) * 5) * lev;
-    r[4] = make_double2(p_up, p_lo);
-    r[5] = make_double2(ct[0], ct[lev]);
-    r[6] = make_double2(ct[2 * lev], ct[3 * lev]);
-    r[7] = make_double2(ct[4 * lev], cs[0]);
-    r[8] = make_double2(cs[lev], cs[2 * lev]);
-    r[9] = make_double2(cs[3 * lev], cs[4 * lev]);
+    st_quad(r + 8, Quad{p_up, p_lo, ct[0], ct[lev]});
+    st_quad(r + 12, Quad{ct[2 * lev], ct[3 * lev], ct[4 * lev], cs[0]});
+    st_quad(r + 16, Quad{cs[lev], cs[2 * lev], cs[3 * lev], cs[4 * lev]});
     const long ol = x + (long)(k - 1) * lev;
-    r[10] = make_double2(I.difiso[ol], I.tlev[0][ol]);
-    r[11] = make_double2(I.tlev[1][ol], 0.);
+    st_quad(r + 20, Quad{I.difiso[ol], I.tlev[0][ol], I.tlev[1][ol], 0.});
     for (int nt = 3; nt <= T; ++nt) {
       const double* cn = I.tpc + x + (long)(((nt - 1) * kk + k - 1) * 5) * lev;
       const long on = x + (long)(((nt - 1) * kk + k - 1) * 2) * lev;
-      double2* rn = r + 12 + 4 * (nt - 3);
-      rn[0] = make_double2(I.tlev[nt - 1][ol], cn[0]);
-      rn[1] = make_double2(cn[lev], cn[2 * lev]);
-      rn[2] = make_double2(cn[3 * lev], cn[4 * lev]);
-      rn[3] = make_double2(I.tsd[on], I.tsd[on + lev]);
+      double* rn = r + ND_RSB + 8 * (nt - 3);
+      st_quad(rn, Quad{I.tlev[nt - 1][ol], cn[0], cn[lev], cn[2 * lev]});
+      st_quad(rn + 4, Quad{cn[3 * lev], cn[4 * lev], I.tsd[on], I.tsd[on + lev]});
     }
     p_up = p_lo;
   }
@@ -288,6 +293,8 @@ ndiff_face(Geom g, NdArgs A) {
   auto stage = [&](int side, int k, bool second) {
     const double* rec = (side ? col_p : col_m) + (k - 1) * LS;
     if (STG & 1) {
+      // (16-byte loads: staging with six 32-byte loads measured 5 - 15 % slower, tnx1v4 u / v 4.88 / 5.42 against
+      // 4.66 / 4.72 ms)
       const double2* r = reinterpret_cast<const double2*>(rec);
       double2 v[ND_RSB / 2];
 #pragma unroll
@@ -943,8 +950,6 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   I.tlev[0] = c.dev("temp") + (long)nn * g.lev;
   I.tlev[1] = c.dev("saln") + (long)nn * g.lev;
   for (int nt = 3; nt <= T; ++nt) I.tlev[nt - 1] = c.dev("trc") + (long)(nn + (nt - 3) * 2 * kk) * g.lev;
-  // (A writer with one thread per 16-byte piece of a record, i.e. fully coalesced stores, measured equal: 1.03 ms at
-  // tnx1v4 either way - the pass is bound by the scattered 192-byte chunks in DRAM, not by the store pattern.)
   LAUNCH(ndiff_prep, dim3(cdiv(g.ii + 2, 128), g.jj + 2), 128, 0, g, mm, T, I, kdmx, src, dst,
          c.dev("utflld"), c.dev("usflld"), c.dev("vtflld"), c.dev("vsflld"));
 
