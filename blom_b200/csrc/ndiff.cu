@@ -150,7 +150,8 @@ struct PrepIn {
 __global__ void __launch_bounds__(128)
 ndiff_prep(Geom g, int mm, int T, PrepIn I, int* __restrict__ kdmx, double* __restrict__ src, double* __restrict__ dst,
            double* __restrict__ utflld, double* __restrict__ usflld, double* __restrict__ vtflld,
-           double* __restrict__ vsflld) {
+           double* __restrict__ vsflld, double* __restrict__ ucm, double* __restrict__ ucp, double* __restrict__ vcm,
+           double* __restrict__ vcp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i > g.ii + 1) return;
   const long x = ix2(g, i, j), lev = g.lev;
@@ -161,6 +162,12 @@ ndiff_prep(Geom g, int mm, int T, PrepIn I, int* __restrict__ kdmx, double* __re
       const long o = x + (long)(k + mm - 1) * lev;
       if (wu) { utflld[o] = 0.; usflld[o] = 0.; }
       if (wv) { vtflld[o] = 0.; vsflld[o] = 0.; }
+    }
+  if (wu || wv)   // face-owned convergence buffers (SideAcc)
+    for (int q = 0; q < T * kk; ++q) {
+      const long o = x + (long)q * lev;
+      if (wu) { ucm[o] = 0.; ucp[o] = 0.; }
+      if (wv) { vcm[o] = 0.; vcp[o] = 0.; }
     }
   if (I.ip[x] != 1) return;
   const double pbot = I.p_dst[x + (long)kk * lev];
@@ -214,7 +221,10 @@ ndiff_prep(Geom g, int mm, int T, PrepIn I, int* __restrict__ kdmx, double* __re
   }
 }
 
-// face-owned running sums of the flux convergence of the current destination layer of one side
+// face-owned running sums of the flux convergence of the current destination layer of one side.  The buffers are
+// zeroed by ndiff_prep (coalesced); a face writes the layers it has contributions for, each exactly once (the zero
+// fill of the layers in between and below used to be a tenth of the warp instructions of ndiff_face, issued by the
+// last lanes alive of every warp, 8 bytes per store)
 template <int NT, class IX>
 struct SideAcc {
   double a[NT > 0 ? NT : NTMAX];
@@ -230,7 +240,6 @@ struct SideAcc {
     for (int q = 0; q < (NT > 0 ? NT : NTMAX); ++q)
       if (q < T) {
         if (cur > 0) buf[x + (IX)(q * kk + cur - 1) * lev] = a[q];
-        for (int k = cur + 1; k < kd; ++k) buf[x + (IX)(q * kk + k - 1) * lev] = 0.;
         a[q] = 0.;
       }
     cur = kd;
@@ -328,8 +337,13 @@ ndiff_face(Geom g, NdArgs A) {
   const double cdiff = A.delt1 * A.sca[x] * A.scbi[x];          // :1064 / :1126
   const double cnslp = alpha0 * A.scbi[x] / grav;
 
+  // Partner tables PN(s,k), thread-local.  They are NOT initialised: an entry is only read where its presence bit
+  // (below) is set, a clear bit stands for the reference's "mval"; filling 2 x 110 doubles per thread with mval
+  // first cost 216 local stores and their share of the L1/L2.
   double pnm[2 * (KMN + 1) + 2], pnp[2 * (KMN + 1) + 2];
-  for (int q = 0; q < 2 * (kk + 1) + 2; ++q) { pnm[q] = mval; pnp[q] = mval; }
+#ifdef BLOM_HOST_EMUL   // tests/emul: poison, so that a read of an entry that was never written cannot go unnoticed
+  for (int q = 0; q < 2 * (KMN + 1) + 2; ++q) { pnm[q] = __builtin_nan(""); pnp[q] = __builtin_nan(""); }
+#endif
 #define PNM(s, k) pnm[2 * (k) + (s) - 1]
 #define PNP(s, k) pnp[2 * (k) + (s) - 1]
   unsigned long long stab_m = 0ull, stab_p = 0ull;   // bit k-1 <-> stab(k), k = 1..64
@@ -658,7 +672,8 @@ ndiff_face(Geom g, NdArgs A) {
             if (ks != (side ? kc_p : kc_m)) { stage(side, ks, true); if (side) kc_p = ks; else kc_m = ks; }
             const double ps1 = SM(side, F_P), ps2 = SM(side, F_P + 1);
             const double ps_n = ksn == ks ? (isn == 1 ? ps1 : ps2) : psd(side, isn, ksn);
-            const double pn_n = pn[2 * ksn + isn - 1], pn_c = pn[2 * ks + is - 1];
+            const double pn_n = hget(side, qn) ? pn[qn] : mval;
+            const double pn_c = hget(side, 2 * ks + is - 1) ? pn[2 * ks + is - 1] : mval;
             if (side) { is_p = is; ks_p = ks; psp1 = ps1; psp2 = ps2; psp_n = ps_n; pnp_n = pn_n; pnp_c = pn_c; }
             else { is_m = is; ks_m = ks; psm1 = ps1; psm2 = ps2; psm_n = ps_n; pnm_n = pn_n; pnm_c = pn_c; }
           }
@@ -951,7 +966,7 @@ void ndiff_dev(int m, int n, int mm, int nn, int k1m, int k1n) {
   I.tlev[1] = c.dev("saln") + (long)nn * g.lev;
   for (int nt = 3; nt <= T; ++nt) I.tlev[nt - 1] = c.dev("trc") + (long)(nn + (nt - 3) * 2 * kk) * g.lev;
   LAUNCH(ndiff_prep, dim3(cdiv(g.ii + 2, 128), g.jj + 2), 128, 0, g, mm, T, I, kdmx, src, dst,
-         c.dev("utflld"), c.dev("usflld"), c.dev("vtflld"), c.dev("vsflld"));
+         c.dev("utflld"), c.dev("usflld"), c.dev("vtflld"), c.dev("vsflld"), ucm, ucp, vcm, vcp);
 
   NdArgs A{};
   A.src = src; A.dst = dst;

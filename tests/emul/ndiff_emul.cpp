@@ -50,7 +50,9 @@ extern "C" int emu_ndiff(const EmuNdiff* e) {
   if (kk >= KMN || T > NTMAX) return 1;
   const size_t lev = (size_t)g.lev;
   std::vector<double> src((size_t)cdiv((long)lev, ND_CB) * ND_CB * kk * nd_rs(T), 0.), dst(lev * 2 * (kk + 1), 0.);
-  std::vector<double> ucm(lev * kk * T, 0.), ucp(lev * kk * T, 0.), vcm(lev * kk * T, 0.), vcp(lev * kk * T, 0.);
+  // (poisoned: ndiff_prep has to zero what ndiff_update reads)
+  const double nan = __builtin_nan("");
+  std::vector<double> ucm(lev * kk * T, nan), ucp(lev * kk * T, nan), vcm(lev * kk * T, nan), vcp(lev * kk * T, nan);
   std::vector<int> kdmx(lev, 0);
 
   PrepIn I{};
@@ -60,7 +62,8 @@ extern "C" int emu_ndiff(const EmuNdiff* e) {
   I.tlev[1] = e->saln + (long)e->nn * g.lev;
   for (int nt = 3; nt <= T; ++nt) I.tlev[nt - 1] = e->trc + (long)(e->nn + (nt - 3) * 2 * kk) * g.lev;
   emu_launch(dim3(cdiv(g.ii + 2, 128), g.jj + 2), dim3(128), [&] {
-    ndiff_prep(g, e->mm, T, I, kdmx.data(), src.data(), dst.data(), e->utflld, e->usflld, e->vtflld, e->vsflld);
+    ndiff_prep(g, e->mm, T, I, kdmx.data(), src.data(), dst.data(), e->utflld, e->usflld, e->vtflld, e->vsflld,
+               ucm.data(), ucp.data(), vcm.data(), vcp.data());
   });
 
   NdArgs A{};
