@@ -135,7 +135,9 @@ int blomgpu_tmsmt2(int m, int mm, int nn, int k1m);           /* phy/mod_tmsmt.F
  *   nd_p_dst   (kdm+1)    p_dst_js(k,i,js)          destination interface pressures
  *   nd_trc_rm  (kdm*T)    trc_rm(k,nt,i)            level (nt-1)*kdm+k, updated in place
  *   dpml       (1)        mixed-layer pressure thickness (option ndiff_surface_align, default '1')
- * plus temp, saln, trc, difiso, pu, pv; updates u|v t|s flld, u|v t|s flx (level k+mm), nslpx, nslpy. */
+ * plus temp, saln, trc, difiso, pu, pv; updates u|v t|s flld, u|v t|s flx (level k+mm), nslpx, nslpy.
+ * Library-owned scratch of the call: (8*T + 8)*kdm + 2*(kdm+1) + 4*T*kdm levels (the per-column copy of the inputs the
+ * searches read, and the face buffers; 192 bytes per cell and layer for T = 2, 24 GB in all at tnx0.25v4). */
 int blomgpu_ndiff(int m, int n, int mm, int nn, int k1m, int k1n);
 
 /* cmnfld2 (phy/mod_cmnfld_routines.F90:1158-1238), hybrid/ALE branch: the producer of nslpx/nslpy that
