@@ -72,6 +72,15 @@ def test_kernel_source_53_layers(align, ntr):
     assert max_rel_err(interior(emu["trc_rm"]), interior(o.arrays["nd_trc_rm"])) <= 1e-13
 
 
+@pytest.mark.parametrize("cfg,ntr", [("tiny2", 5), ("tiny2k53", 6)])
+def test_kernel_source_many_passive_tracers(cfg, ntr):
+    """T = 7 and the compiled maximum T = 8: the generic instantiation, tracer parts of the records read in place"""
+    c, o, emu = run_pair(cfg, ntr, 1, "1")
+    for nm in FACE:
+        assert np.array_equal(interior(emu[nm]), interior(o.arrays[nm])), nm
+    assert max_rel_err(interior(emu["trc_rm"]), interior(o.arrays["nd_trc_rm"])) <= 1e-13
+
+
 def test_kernel_source_full_size_tnx1v4():
     """the whole 360 x 385 x 53 grid (tripolar fold, 53 layers, ~116 000 wet faces per direction): about a minute"""
     c, o, emu = run_pair("tnx1v4", 0, 1, "1")
