@@ -35,9 +35,13 @@
 // coefficients, diffusivity, layer means; 192 bytes for T and S), and per destination interface the pair
 // {p_dst, snapped p_dst}.  A thread that steps to the next source layer of a column loads that layer's
 // record in ONE batch of independent 16-byte loads into its private column of shared memory and works from
-// there: one exposed memory round trip per layer and column instead of one per array, every fetched sector
-// used completely, no coefficient / layer-mean reloads.  The model's own arrays keep their layout; the
-// transpose costs one streaming pass inside ndiff_prep.
+// there, and it prefetches the NEXT layer's record into the L2: one memory round trip per layer and column
+// instead of one per array, and that one an L2 hit; every fetched sector used completely, no coefficient /
+// layer-mean reloads.  The thread-local partner tables of the searches get presence masks in shared memory (their
+// scans are bit operations), the destination layers are walked with shift registers.  The model's own arrays keep
+// their layout; the transpose costs one streaming pass inside ndiff_prep (written with 32-byte sector stores).
+// Measurements: profiles/r02_tuning_log.md, profiles/r02_ncu_full_ndiff_face_records.txt.  Every step of this
+// rebuild was checked bit for bit on the CPU first: tests/emul compiles THIS file for the host (BLOM_HOST_EMUL).
 #include "common.cuh"
 #include "eos.cuh"
 
@@ -63,15 +67,15 @@ __device__ __forceinline__ double eos_drhods(double p, double th, double s) {
   return (EA13 + EA15 * th + 2. * EA16 * s + EB13 * p - (EA23 + EA25 * th + 2. * EA26 * s + EB23 * p) * r1 * r2i) * r2i;
 }
 
-// Column record of source layer k of one cell (doubles; the record of layer k of cell x starts at
-// src[(x*kk + k-1) * RS], RS = nd_rs(T) = 24 + 8*(T-2)):
+// Column record of source layer k of one cell (RS = nd_rs(T) = 24 + 8*(T-2) doubles; where it starts: nd_col below):
 //    0.. 3  {drhodt, drhods, T, S} at the upper interface (is = 1)        t_srcdi(1,k,1:2) and mod_eos derivatives
 //    4.. 7  the same at the lower interface (is = 2)
 //    8, 9   p_src(k), p_src(k+1)                                           p_srcdi(1:2,k)
 //   10..14  tpc_src(1:5,k,T)      15..19  tpc_src(1:5,k,S)
 //   20      difiso(k)             21, 22  temp(k), saln(k) at the new time level          23  unused
 //   24 + 8*(nt-3) ..  passive tracer nt >= 3: trc(k), tpc_src(1:5,k,nt), t_srcdi(1:2,k,nt)
-// The first ND_RSB = 24 doubles (192 bytes, six sectors) are what a thread stages in shared memory.
+// The first ND_RSB = 24 doubles (192 bytes, six sectors) are what a thread loads when it stages a layer (20 of them
+// are kept per search, see ndiff_face).
 // Cells are grouped in blocks of CB consecutive cells (linear (i,j) offsets); inside a block the records are ordered
 // (layer, cell), i.e. the record of layer k of cell x starts at src[(((x/CB)*kk + k-1)*CB + x%CB) * RS]: the
 // layer-k records of 32 neighbouring cells are one contiguous 6 KB piece, which is what a warp of ndiff_prep writes
